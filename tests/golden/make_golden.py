@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE's own code (read-only, /root/reference).
+
+TensorFlow, tensorflow-probability, gym, optuna, termcolor and matplotlib are not installable in
+this image, so `import xagents` cannot work as is.  This script installs import-time stand-ins:
+
+* permissive stub modules for everything the reference imports but the hot path never calls;
+* a NumPy-backed shim of exactly the TensorFlow / tfp ops the hot path calls
+  (range, random.shuffle, gather, reduce_mean, math.reduce_std, clip_by_value, square, maximum,
+  exp, squeeze, cast, numpy_function, function, GradientTape, clip_by_global_norm;
+  Categorical.log_prob / entropy / sample) following their published definitions, fp32;
+* fake gym environments that replay a seeded synthetic stream, and a tiny NumPy "model".
+
+It then constructs the genuine `xagents.PPO` / `xagents.A2C` objects and calls their genuine
+`train_step()` / `calculate_returns()` / `concat_step_batches()` / `get_mini_batches()` /
+`run_ppo_epochs()` / `update_gradients()`; thin recorders wrapped around the bound methods save
+inputs and outputs.  Nothing from the reference is copied into this repository -- only the arrays
+it produced.  The fixtures travel to the GPU box; /root/reference does not.
+
+Usage:  python tests/golden/make_golden.py   (needs /root/reference; writes next to this file)
+"""
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get('XAGENTS_REFERENCE', '/root/reference')
+STUB_ROOTS = ('tensorflow', 'tensorflow_probability', 'gym', 'optuna', 'termcolor', 'matplotlib')
+F32 = np.float32
+
+
+# ------------------------------------------------------------------ permissive stubs
+class _StubMeta(type):
+    def __getattr__(cls, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return _make_stub(f'{cls.__name__}.{name}')
+
+    def __call__(cls, *args, **kwargs):
+        # decorator use (tf.function): hand the function back untouched
+        if len(args) == 1 and not kwargs and isinstance(args[0], types.FunctionType):
+            return args[0]
+        return super().__call__()
+
+
+def _make_stub(name):
+    return _StubMeta(name, (), {'__init__': lambda self, *a, **k: None,
+                                '__getattr__': lambda self, n: _make_stub(n),
+                                '__call__': lambda self, *a, **k: None})
+
+
+class _StubModule(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        value = _make_stub(name)
+        setattr(self, name, value)
+        return value
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split('.')[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        _populate(module)
+
+
+# ------------------------------------------------------------------ numpy-backed TF / tfp shim
+RECORD = {'shuffles': [], 'means': [], 'losses': []}
+_SHUFFLE_RNG = np.random.default_rng(4321)
+_SAMPLE_RNG = np.random.default_rng(99)
+
+
+def _f32(x):
+    return np.asarray(x, F32)
+
+
+class _Tensor(np.ndarray):
+    """ndarray that answers .numpy() like an eager tensor."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def _shuffle(indices):
+    out = _SHUFFLE_RNG.permutation(np.asarray(indices)).astype(np.int32)
+    RECORD['shuffles'].append(out.copy())
+    return out
+
+
+def _reduce_mean(x):
+    m = np.asarray(x).mean(dtype=F32)
+    RECORD['means'].append(F32(m))
+    return m
+
+
+def _reduce_std(x):
+    x = np.asarray(x)
+    return np.sqrt(np.square(x - x.mean(dtype=F32)).mean(dtype=F32))
+
+
+class _Tape:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def gradient(self, loss, variables):
+        RECORD['losses'].append(F32(loss))
+        return []
+
+
+def _log_softmax(x):
+    z = x - x.max(axis=-1, keepdims=True)
+    return z - np.log(np.exp(z).sum(axis=-1, keepdims=True))
+
+
+class Categorical:
+    """tfp.distributions.Categorical (0.15.0) restated: see SURVEY.md appendix A."""
+
+    def __init__(self, logits=None, probs=None):
+        raw = _f32(logits) if logits is not None else np.log(_f32(probs))
+        self.lsm = _log_softmax(raw)
+
+    def log_prob(self, actions):
+        a = np.asarray(actions).astype(np.int64).reshape(-1, 1)
+        return np.take_along_axis(self.lsm, a, axis=-1)[:, 0]
+
+    def entropy(self):
+        return -(np.exp(self.lsm) * self.lsm).sum(axis=-1, dtype=F32)
+
+    def sample(self, seed=None):
+        g = _SAMPLE_RNG.gumbel(size=self.lsm.shape)
+        return np.argmax(self.lsm + g, axis=-1).astype(np.int32)
+
+
+class MultivariateNormalDiag:
+    def __init__(self, loc):
+        self.loc = _f32(loc)
+
+    def log_prob(self, actions):
+        k = self.loc.shape[-1]
+        d = _f32(actions).reshape(self.loc.shape) - self.loc
+        return F32(-0.5) * np.square(d).sum(-1, dtype=F32) - F32(0.5 * k) * F32(np.log(2 * np.pi))
+
+    def entropy(self):
+        k = self.loc.shape[-1]
+        return np.full(self.loc.shape[0], F32(0.5 * k) * (F32(1) + F32(np.log(2 * np.pi))), F32)
+
+    def sample(self, seed=None):
+        return (self.loc + _SAMPLE_RNG.standard_normal(self.loc.shape)).astype(F32)
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def seed(self, s):
+        pass
+
+
+class Box:
+    def __init__(self, shape):
+        self.shape = shape
+
+    def seed(self, s):
+        pass
+
+
+def _populate(module):
+    name = module.__name__
+    if name == 'tensorflow':
+        module.function = lambda fn: fn
+        module.float32 = 'float32'
+        module.numpy_function = lambda fn, args, dtypes: fn(*args)
+        module.range = lambda n: np.arange(n, dtype=np.int32)
+        module.gather = lambda item, idx: np.take(np.asarray(item), np.asarray(idx), axis=0)
+        module.reduce_mean = _reduce_mean
+        module.clip_by_value = lambda x, lo, hi: np.clip(x, F32(lo), F32(hi))
+        module.square = np.square
+        module.maximum = np.maximum
+        module.exp = np.exp
+        module.squeeze = lambda x: np.squeeze(np.asarray(x)).view(_Tensor)
+        module.cast = lambda x, dtype: _f32(x)
+        module.GradientTape = _Tape
+        module.clip_by_global_norm = lambda grads, norm: (grads, F32(0))
+    elif name == 'tensorflow.random':
+        module.shuffle = _shuffle
+        module.set_seed = lambda s: None
+    elif name == 'tensorflow.math':
+        module.reduce_std = _reduce_std
+    elif name == 'tensorflow_probability.python.distributions':
+        module.Categorical = Categorical
+        module.MultivariateNormalDiag = MultivariateNormalDiag
+    elif name in ('gym.spaces', 'gym.spaces.discrete', 'gym.spaces.box'):
+        module.Discrete = Discrete
+        module.Box = Box
+
+
+def _import_reference():
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REFERENCE)
+    import tensorflow  # noqa: F401  (the stub)
+    import tensorflow.math  # noqa: F401
+    import tensorflow.random  # noqa: F401
+    import xagents
+    assert os.path.realpath(xagents.__file__).startswith(os.path.realpath(REFERENCE))
+    return xagents
+
+
+# ------------------------------------------------------------------ fake envs and model
+class ReplayEnv:
+    """Replays a fixed stream: step k -> (obs[k+1], reward[k], done[k]); reset -> fresh obs."""
+
+    def __init__(self, obs, rewards, dones, resets, action_space):
+        self.obs, self.rewards, self.dones, self.resets = obs, rewards, dones, resets
+        self.k = 0
+        self.n_resets = 0
+        self.action_space = action_space
+        self.observation_space = types.SimpleNamespace(shape=obs.shape[1:])
+        self.spec = types.SimpleNamespace(id='Replay-v0')
+
+    def reset(self):
+        out = self.resets[self.n_resets % len(self.resets)]
+        self.n_resets += 1
+        return out
+
+    def step(self, action):
+        k = self.k
+        self.k += 1
+        return self.obs[k + 1], float(self.rewards[k]), bool(self.dones[k]), {}
+
+    def seed(self, s):
+        pass
+
+
+class TinyModel:
+    """[actor_out, critic_out] = fixed fp32 linear maps of the first features of the input."""
+
+    def __init__(self, in_features, n_actions, rng, softmax=False):
+        self.wa = (rng.standard_normal((in_features, n_actions)) * 0.7).astype(F32)
+        self.wc = (rng.standard_normal((in_features, 1)) * 0.7).astype(F32)
+        self.drift = F32(0.0)          # set > 0 to emulate "weights moved since the rollout"
+        self.softmax = softmax
+        act = sys.modules['tensorflow'].keras.activations.softmax if softmax else None
+        self.layers = [types.SimpleNamespace(activation=None), types.SimpleNamespace(activation=act),
+                       types.SimpleNamespace(activation=None)]
+        self.trainable_variables = []
+        self.optimizer = types.SimpleNamespace(apply_gradients=lambda pairs: None)
+        self.calls = []
+
+    def __call__(self, inputs, training=True):
+        x = _f32(inputs).reshape(len(inputs), -1)[:, :self.wa.shape[0]]
+        actor = x @ (self.wa * (F32(1) + self.drift)) + self.drift
+        critic = x @ (self.wc * (F32(1) - self.drift)) - self.drift
+        if self.softmax:
+            actor = np.exp(_log_softmax(actor))
+        self.calls.append((actor.copy(), critic.copy()))
+        return [actor, critic]
+
+
+def _streams(rng, n_steps, n_envs, obs_shape, image, p_done):
+    if image:
+        obs = rng.integers(0, 256, size=(n_envs, n_steps + 2) + obs_shape, dtype=np.uint8)
+        resets = rng.integers(0, 256, size=(n_envs, 4) + obs_shape, dtype=np.uint8)
+    else:
+        obs = rng.standard_normal((n_envs, n_steps + 2) + obs_shape).astype(F32)
+        resets = rng.standard_normal((n_envs, 4) + obs_shape).astype(F32)
+    rewards = rng.standard_normal((n_envs, n_steps + 1)).astype(F32)
+    dones = rng.random((n_envs, n_steps + 1)) < p_done
+    return obs, rewards, dones, resets
+
+
+def _wrap(agent, name, sink):
+    inner = getattr(agent, name)
+
+    def recorder(*args, **kwargs):
+        out = inner(*args, **kwargs)
+        sink.append((args, out))
+        return out
+
+    setattr(agent, name, recorder)
+
+
+def _build(xagents, kind, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, softmax=False, **kw):
+    rng = np.random.default_rng(seed)
+    obs, rewards, dones, resets = _streams(rng, n_steps, n_envs, obs_shape, image, p_done)
+    space = Discrete(n_actions)
+    envs = [ReplayEnv(obs[i], rewards[i], dones[i], resets[i], space) for i in range(n_envs)]
+    model = TinyModel(min(int(np.prod(obs_shape)), 24), n_actions, rng, softmax)
+    cls = xagents.PPO if kind == 'ppo' else xagents.A2C
+    agent = cls(envs, model, n_steps=n_steps, quiet=True, **kw)
+    return agent, model
+
+
+def ppo_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, drift=0.05, **kw):
+    for k in RECORD:
+        RECORD[k].clear()
+    agent, model = _build(xagents, 'ppo', seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw)
+    rec = {k: [] for k in ('calculate_returns', 'get_batch', 'get_mini_batches', 'update_gradients')}
+    for name in rec:
+        _wrap(agent, name, rec[name])
+    # weights "move" between the rollout and the updates so that ratio != 1 and clips engage
+    inner_epochs = agent.run_ppo_epochs
+
+    def run_epochs(*batch):
+        model.drift = F32(drift)
+        model.calls.clear()
+        return inner_epochs(*batch)
+
+    agent.run_ppo_epochs = run_epochs
+    agent.train_step()                                     # the reference's own PPO.train_step
+    update_calls = list(model.calls)
+    (rewards, dones, values), returns = rec['calculate_returns'][0]
+    _, batch = rec['get_batch'][0]
+    _, minibatches = rec['get_mini_batches'][0]
+    n_mb = len(minibatches)
+    next_values = None
+    # bootstrap value = critic of the model call made inside calculate_returns: recompute
+    model.drift = F32(0)
+    next_values = np.squeeze(model(_f32(agent.get_states()) / F32(255.0) if image else _f32(agent.get_states()))[1])
+    out = dict(
+        n_steps=n_steps, n_envs=n_envs, gamma=agent.gamma, lam=agent.lam, clip_norm=agent.clip_norm,
+        entropy_coef=agent.entropy_coef, value_loss_coef=agent.value_loss_coef,
+        advantage_epsilon=agent.advantage_epsilon, mini_batch_size=agent.mini_batch_size,
+        ppo_epochs=agent.ppo_epochs, steps_after=agent.steps,
+        rewards=rewards, dones=dones, values=values, next_values=np.atleast_1d(next_values), returns=returns,
+        flat_states=batch[0], flat_actions=batch[1], flat_returns=batch[2], flat_values=batch[3],
+        flat_log_probs=batch[4],
+        shuffles=np.stack(RECORD['shuffles']),
+        losses=np.asarray(RECORD['losses'], F32),
+        means=np.asarray(RECORD['means'], F32).reshape(n_mb, 4),   # per update: adv mean, entropy, max-vl mean, pg
+    )
+    assert len(rec['update_gradients']) == n_mb == len(update_calls)
+    for i, ((args, _), (actor, critic)) in enumerate(zip(rec['update_gradients'], update_calls)):
+        states, actions, old_values, rets, old_logp, adv = args
+        mb = minibatches[i]
+        out[f'mb{i}_states'] = mb[0]
+        out[f'mb{i}_actions'] = np.asarray(actions)
+        out[f'mb{i}_old_values'] = np.asarray(old_values)
+        out[f'mb{i}_returns'] = np.asarray(rets)
+        out[f'mb{i}_old_log_probs'] = np.asarray(old_logp)
+        out[f'mb{i}_advantages'] = np.asarray(adv)
+        out[f'mb{i}_actor'] = actor
+        out[f'mb{i}_critic'] = np.squeeze(critic)
+    # time-major rollout as the reference assembled it (lists of per-step arrays -> asarray fp32)
+    states_tm = batch[0].reshape((n_envs, n_steps) + batch[0].shape[1:]).swapaxes(0, 1)
+    out['states_time_major'] = np.ascontiguousarray(states_tm)
+    np.savez_compressed(os.path.join(HERE, f'{tag}.npz'), **out)
+    print(f'{tag}: T={n_steps} E={n_envs} minibatches={n_mb} loss[0]={out["losses"][0]:.6f}')
+
+
+def a2c_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw):
+    for k in RECORD:
+        RECORD[k].clear()
+    agent, model = _build(xagents, 'a2c', seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw)
+    rec = {k: [] for k in ('calculate_returns', 'np_train_step')}
+    for name in rec:
+        _wrap(agent, name, rec[name])
+    inner = agent.np_train_step
+
+    def after_batch():
+        out = inner()
+        model.drift = F32(0.05)
+        model.calls.clear()
+        return out
+
+    agent.np_train_step = after_batch
+    agent.train_step()                                     # the reference's own A2C.train_step
+    (rewards, dones), returns = rec['calculate_returns'][0]
+    _, (states, flat_returns, actions, old_values) = rec['np_train_step'][0]
+    actor, critic = model.calls[0]
+    model.drift = F32(0)
+    x = _f32(agent.get_states()) / F32(255.0) if image else _f32(agent.get_states())
+    next_values = np.squeeze(model(x)[1])
+    np.savez_compressed(
+        os.path.join(HERE, f'{tag}.npz'),
+        n_steps=n_steps, n_envs=n_envs, gamma=agent.gamma, entropy_coef=agent.entropy_coef,
+        value_loss_coef=agent.value_loss_coef, steps_after=agent.steps,
+        rewards=rewards, dones=dones, next_values=np.atleast_1d(next_values), returns=returns,
+        flat_states=states, flat_returns=flat_returns, flat_actions=actions, flat_values=old_values,
+        actor=actor, critic=np.squeeze(critic), loss=np.asarray(RECORD['losses'], F32),
+        means=np.asarray(RECORD['means'], F32))            # entropy, adv*logp mean, value mse
+    print(f'{tag}: T={n_steps} E={n_envs} loss={RECORD["losses"][0]:.6f}')
+
+
+def kat_case(xagents):
+    """SURVEY.md 8c KAT-1/KAT-2 inputs through the reference's calculate_returns + flatten."""
+    T, E = 4, 3
+    rewards = _f32([[1, 0, -1], [0, 2, .5], [1, 1, 1], [.5, 0, -2]])
+    values = _f32([[.5, .1, -.3], [.2, .4, 0], [-.1, .3, .7], [.9, -.5, .2]])
+    dones = _f32([[0, 0, 0], [0, 1, 0], [0, 0, 0], [1, 0, 0], [0, 0, 1]])
+    next_values = _f32([.3, -.2, .6])
+
+    def bare(cls):
+        a = object.__new__(cls)
+        a.n_steps, a.n_envs, a.gamma, a.lam, a.output_models = T, E, 0.99, 0.95, []
+        a.get_states = lambda: None
+        a.get_model_outputs = lambda *args, **kw: (
+            None, None, types.SimpleNamespace(numpy=lambda: next_values.copy(), shape=(E,)), None, None)
+        return a
+
+    ppo_ret = xagents.PPO.calculate_returns(bare(xagents.PPO), rewards, dones, values)
+    a2c = bare(xagents.A2C)
+    a2c.get_model_outputs = lambda *args, **kw: (None, None, next_values.copy(), None, None)
+    a2c_ret = xagents.A2C.calculate_returns(a2c, rewards, dones)
+    flat = xagents.PPO.concat_step_batches(ppo_ret, values)
+    np.savez_compressed(os.path.join(HERE, 'kat_returns.npz'), rewards=rewards, values=values, dones=dones,
+                        next_values=next_values, gamma=0.99, lam=0.95, ppo_returns=ppo_ret,
+                        a2c_returns=a2c_ret, flat_returns=flat[0], flat_values=flat[1])
+    print('kat_returns:', ppo_ret[0], a2c_ret[0])
+
+
+def main():
+    xagents = _import_reference()
+    kat_case(xagents)
+    # PPO, image observations (uint8-valued, 8x8x4), 6 actions: Atari-shaped in miniature
+    ppo_case(xagents, 'ppo_image', 11, n_steps=16, n_envs=8, obs_shape=(8, 8, 4), image=True,
+             n_actions=6, p_done=0.08, mini_batches=4, ppo_epochs=4)
+    # PPO, CartPole-shaped vectors (C1 in miniature: E=16, T=128, A=2)
+    ppo_case(xagents, 'ppo_cartpole', 12, n_steps=128, n_envs=16, obs_shape=(4,), image=False,
+             n_actions=2, p_done=0.02, mini_batches=4, ppo_epochs=4)
+    # PPO with N % mini_batches != 0 -> trailing short minibatch; single env; harsher clip
+    ppo_case(xagents, 'ppo_ragged', 13, n_steps=7, n_envs=3, obs_shape=(5,), image=False,
+             n_actions=3, p_done=0.3, mini_batches=4, ppo_epochs=2, clip_norm=0.02, drift=0.2)
+    ppo_case(xagents, 'ppo_single_env', 14, n_steps=9, n_envs=1, obs_shape=(6, 6, 1), image=True,
+             n_actions=4, p_done=0.2, mini_batches=3, ppo_epochs=2)
+    # A2C C2-shaped (E=16, T=5) with small frames, and a vector case
+    a2c_case(xagents, 'a2c_image', 21, n_steps=5, n_envs=16, obs_shape=(8, 8, 4), image=True,
+             n_actions=6, p_done=0.1)
+    a2c_case(xagents, 'a2c_vector', 22, n_steps=12, n_envs=5, obs_shape=(4,), image=False,
+             n_actions=2, p_done=0.15)
+
+
+if __name__ == '__main__':
+    main()
