@@ -1,0 +1,166 @@
+/*
+ * xagents_b200 -- C ABI of the B200-native on-policy rollout-to-update hot path.
+ *
+ * The reference (abstractguy/xagents, pure Python on TF2) has no FFI of its own: the seam is the
+ * method-override surface of its agent classes.  Each entry point below replaces the arithmetic of
+ * one reference method (cited as file:line relative to the reference tree); the Python classes in
+ * xagents_b200/agents/ keep the reference signatures and call these through ctypes, passing device
+ * pointers taken from DLPack capsules (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *   - the caller owns every buffer; the library allocates nothing the caller sees;
+ *   - calls are stream-ordered and asynchronous: `stream` is a cudaStream_t (NULL = legacy default);
+ *   - return 0 on success, a negative XA_E* code for argument errors, a positive cudaError_t for
+ *     launch errors; the message is in xa_last_error() (thread-local); nothing aborts or throws;
+ *   - layouts: "time-major" = [T, E, ...] as the rollout is produced; "env-major flat" index
+ *     b = e*T + t is what BaseAgent.concat_step_batches (xagents/base.py:549-564) produces.  Kernels
+ *     taking (n_steps, n_envs) read time-major buffers through env-major indices
+ *     (row = (b % T)*E + b / T), so that flatten copy never happens; n_steps = 0 disables the remap.
+ *   - there is no CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef XAGENTS_B200_H
+#define XAGENTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XA_VERSION 10000 /* 1.0.0 */
+
+#define XA_OK 0
+#define XA_EINVAL (-1)    /* null pointer, non-positive size, unknown mode */
+#define XA_EALIGN (-2)    /* pointer not aligned for its element type */
+#define XA_EOVERFLOW (-3) /* size does not fit the index type of the kernel */
+#define XA_ENOSPACE (-4)  /* workspace too small */
+
+typedef void* xa_stream_t;
+
+int xa_version(void);
+const char* xa_last_error(void);
+/* sm_count / cc of `device` (host out-params; any may be NULL). Fails when no CUDA device exists. */
+int xa_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- returns -------------------------------------------------------------------------------- */
+#define XA_SCAN_AUTO 0       /* pick by shape */
+#define XA_SCAN_SEQUENTIAL 1 /* one thread walks T per env: bit-identical to the reference's op order */
+#define XA_SCAN_CHUNKED 2    /* T split across warps, carries combined as affine maps (re-associates) */
+
+/* PPO.calculate_returns, xagents/ppo/agent.py:80-94 (the bootstrap model call at :72-79 is the
+ * caller's: pass its output as last_values).  rewards [T,E]; values [T,E]; last_values [E];
+ * dones [T+1,E] fp32, row t+1 gates step t; returns [T,E]; advantages [T,E] or NULL.
+ * gamma / lam are doubles because the reference folds gamma*lam as Python floats before the product
+ * meets the fp32 arrays (ppo/agent.py:92): gamma_lam = (float)(gamma*lam), gamma = (float)gamma. */
+int xa_gae_f32(const float* rewards, const float* values, const float* last_values, const float* dones,
+               float* returns, float* advantages, int n_steps, int n_envs, double gamma, double lam,
+               int mode, xa_stream_t stream);
+
+/* A2C.calculate_returns, xagents/a2c/agent.py:165-171.  returns [T,E]. */
+int xa_nstep_returns_f32(const float* rewards, const float* dones, const float* last_values,
+                         float* returns, int n_steps, int n_envs, double gamma, int mode,
+                         xa_stream_t stream);
+
+/* ---- permute-gather ------------------------------------------------------------------------- */
+#define XA_GATHER_AUTO 0
+#define XA_GATHER_BULK 1   /* TMA bulk copies global->shared->global; needs 16-B aligned rows */
+#define XA_GATHER_VECTOR 2 /* 128-bit (or narrower, by alignment) LDG/STG */
+
+/* tf.gather(item, batch_indices) of PPO.get_mini_batches, xagents/ppo/agent.py:149-154, fused with
+ * the env-major flatten of xagents/base.py:559-564.  dst[i, :] = src[row(idx[i]), :], whole rows of
+ * row_bytes bytes, bit-exact.  n_src_rows bounds idx (precondition: 0 <= idx[i] < n_src_rows). */
+int xa_gather_rows(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes,
+                   int64_t n_src_rows, int n_steps, int n_envs, int mode, xa_stream_t stream);
+
+/* Same gather for up to XA_MAX_FIELDS fp32 scalar-per-sample fields at once (actions, returns,
+ * old values, old log-probs).  src/dst: HOST arrays of n_fields device pointers. */
+#define XA_MAX_FIELDS 8
+int xa_gather_fields_f32(const float* const* src, float* const* dst, int n_fields, const int32_t* idx,
+                         int64_t n_idx, int n_steps, int n_envs, xa_stream_t stream);
+
+/* One launch for a whole minibatch (or epoch): observation rows + scalar fields. */
+int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, int64_t n_src_rows,
+                        const float* const* field_src, float* const* field_dst, int n_fields,
+                        const int32_t* idx, int64_t n_idx, int n_steps, int n_envs, int mode,
+                        xa_stream_t stream);
+
+/* BaseAgent.get_model_outputs image scaling, xagents/base.py:505-506, fused behind the gather:
+ * dst fp32 [n_idx, row_bytes] = float(src u8) / 255.0f (true division). */
+int xa_gather_rows_u8_scaled_f32(const uint8_t* src, const int32_t* idx, float* dst, int64_t n_idx,
+                                 int64_t row_bytes, int64_t n_src_rows, int n_steps, int n_envs,
+                                 xa_stream_t stream);
+
+/* ---- advantage moments ---------------------------------------------------------------------- */
+/* Per-minibatch count / mean / M2 of adv = returns - old_values (PPO.run_ppo_epochs,
+ * xagents/ppo/agent.py:180-183; population std = sqrt(M2/count)).  Minibatch m covers
+ * idx[mb_offsets[m] .. mb_offsets[m+1]) (mb_offsets: HOST array of n_minibatches+1); idx NULL =
+ * identity.  moments: [n_minibatches][XA_MOMENT_STRIDE] doubles {count, mean, M2, 0}.  Exposed
+ * separately from the loss so that a cross-rank all-gather of the partial moments can sit between. */
+#define XA_MOMENT_STRIDE 4
+int xa_adv_moments_f32(const float* returns, const float* old_values, const int32_t* idx,
+                       const int64_t* mb_offsets, int n_minibatches, int n_steps, int n_envs,
+                       double* moments, xa_stream_t stream);
+
+/* ---- losses --------------------------------------------------------------------------------- */
+#define XA_ACTOR_LOGITS 0 /* Categorical(logits=)            a2c/agent.py:63 */
+#define XA_ACTOR_PROBS 1  /* Categorical(probs=)             a2c/agent.py:61-62 */
+#define XA_ACTOR_NORMAL 2 /* MultivariateNormalDiag(loc)     a2c/agent.py:59-60 */
+
+typedef struct xa_loss_args {
+  /* model outputs for the minibatch (forward pass at ppo/agent.py:113-115) */
+  const float* actor_out; /* [n, n_actions] logits | probs | loc */
+  const float* values;    /* [n] critic output */
+  /* per-sample rollout fields: already gathered [n] when idx == NULL, else full buffers read at
+   * row(idx[i]) (time-major when n_steps > 0) so the scalar gathers never materialise */
+  const float* actions;       /* [.] fp32-encoded ints, or [., n_actions] for XA_ACTOR_NORMAL */
+  const float* old_log_probs; /* PPO only */
+  const float* old_values;
+  const float* returns;
+  const int32_t* idx; /* [n] or NULL */
+  int32_t n_steps, n_envs;
+  /* advantage normalisation (PPO): either supplied advantages [n] (already normalised, gathered),
+   * or moment parts to combine: part p at moments + p*moment_part_stride (doubles). */
+  const float* advantages;
+  const double* moments;
+  int32_t n_moment_parts;
+  int64_t moment_part_stride;
+  int64_t n;
+  int32_t n_actions;
+  int32_t actor_kind;
+  float clip;       /* PPO clip_norm, used for ratio AND value clip (ppo/agent.py:117-127) */
+  float ent_coef;   /* entropy_coef */
+  float vf_coef;    /* value_loss_coef */
+  float adv_eps;    /* advantage_epsilon */
+  /* outputs */
+  float* out_scalars;    /* [4] loss, pg_loss, value_loss, entropy */
+  float* d_actor;        /* [n, n_actions] d loss / d actor_out, or NULL */
+  float* d_values;       /* [n] d loss / d values, or NULL */
+  float* advantages_out; /* [n] normalised advantages as used, or NULL */
+  void* workspace;       /* xa_loss_workspace_bytes(n) bytes, zero-filled once; kernels leave it zeroed */
+  int64_t workspace_bytes;
+} xa_loss_args;
+
+int64_t xa_loss_workspace_bytes(int64_t n);
+/* PPO.update_gradients forward + the gradients the tape hands back, xagents/ppo/agent.py:112-134. */
+int xa_ppo_loss_f32(const xa_loss_args* args, xa_stream_t stream);
+/* A2C.train_step loss, xagents/a2c/agent.py:202-215 (advantages = returns - old_values, raw). */
+int xa_a2c_loss_f32(const xa_loss_args* args, xa_stream_t stream);
+
+/* ---- optimiser step (row "next": the step right after the path) ------------------------------ */
+/* tf.clip_by_global_norm + Keras Adam.apply_gradients, xagents/ppo/agent.py:135-137,
+ * xagents/a2c/agent.py:216-218, over ONE flat fp32 buffer holding every trainable tensor.
+ * xa_grad_sumsq_f32 leaves sum(g^2) in the workspace (zero-filled once; kernels leave it reusable);
+ * xa_clip_adam_f32 then applies g' = g * grad_scale * clip*min(1/|g*grad_scale|, 1/clip) (clip_norm
+ * <= 0: no clipping, workspace unused) and the bias-corrected-lr Adam update for 1-based `step`. */
+int64_t xa_clip_adam_workspace_bytes(int64_t n);
+int xa_grad_sumsq_f32(const float* grads, int64_t n, void* workspace, int64_t workspace_bytes,
+                      xa_stream_t stream);
+int xa_clip_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n,
+                     const void* workspace, double lr, double beta1, double beta2, double eps,
+                     double clip_norm, int64_t step, double grad_scale, xa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XAGENTS_B200_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of include/xagents_b200.h (the only way the Python layer reaches the kernels).
+
+There is deliberately no fallback: if the shared library is missing, or a call returns non-zero, an
+exception is raised.  Build it with `python -m xagents_b200._build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+from ._build import LIB_PATH
+
+c_f32p = ctypes.c_void_p      # device pointers travel as integers
+c_stream = ctypes.c_void_p
+
+XA_SCAN_AUTO, XA_SCAN_SEQUENTIAL, XA_SCAN_CHUNKED = 0, 1, 2
+XA_GATHER_AUTO, XA_GATHER_BULK, XA_GATHER_VECTOR = 0, 1, 2
+XA_ACTOR_LOGITS, XA_ACTOR_PROBS, XA_ACTOR_NORMAL = 0, 1, 2
+XA_MAX_FIELDS = 8
+XA_MOMENT_STRIDE = 4
+
+
+class XAError(RuntimeError):
+    def __init__(self, fn, code, message):
+        super().__init__(f'{fn} failed with code {code}: {message}')
+        self.fn, self.code, self.message = fn, code, message
+
+
+class LossArgs(ctypes.Structure):
+    """struct xa_loss_args"""
+    _fields_ = [
+        ('actor_out', ctypes.c_void_p), ('values', ctypes.c_void_p), ('actions', ctypes.c_void_p),
+        ('old_log_probs', ctypes.c_void_p), ('old_values', ctypes.c_void_p), ('returns', ctypes.c_void_p),
+        ('idx', ctypes.c_void_p), ('n_steps', ctypes.c_int32), ('n_envs', ctypes.c_int32),
+        ('advantages', ctypes.c_void_p), ('moments', ctypes.c_void_p), ('n_moment_parts', ctypes.c_int32),
+        ('moment_part_stride', ctypes.c_int64), ('n', ctypes.c_int64), ('n_actions', ctypes.c_int32),
+        ('actor_kind', ctypes.c_int32), ('clip', ctypes.c_float), ('ent_coef', ctypes.c_float),
+        ('vf_coef', ctypes.c_float), ('adv_eps', ctypes.c_float), ('out_scalars', ctypes.c_void_p),
+        ('d_actor', ctypes.c_void_p), ('d_values', ctypes.c_void_p), ('advantages_out', ctypes.c_void_p),
+        ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/xagents_b200.h declares
+PROTOTYPES = {
+    'xa_version': (ctypes.c_int, []),
+    'xa_last_error': (ctypes.c_char_p, []),
+    'xa_device_info': (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3),
+    'xa_gae_f32': (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                  ctypes.c_int, c_stream]),
+    'xa_nstep_returns_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                                            c_stream]),
+    'xa_gather_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_stream]),
+    'xa_gather_fields_f32': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_stream]),
+    'xa_gather_minibatch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           c_stream]),
+    'xa_gather_rows_u8_scaled_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_stream]),
+    'xa_adv_moments_f32': (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_stream]),
+    'xa_loss_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64]),
+    'xa_ppo_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),
+    'xa_a2c_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),
+    'xa_clip_adam_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64]),
+    'xa_grad_sumsq_f32': (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_clip_adam_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+                                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                                       ctypes.c_double, c_stream]),
+}
+
+_lib = None
+
+
+def library_path():
+    return os.environ.get('XAGENTS_B200_LIB', LIB_PATH)
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError(f'{path} is missing: run `python -m xagents_b200._build` (nvcc, sm_100a). '
+                              'xagents_b200 has no CPU or framework fallback.')
+        handle = ctypes.CDLL(path)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(handle, name)          # AttributeError here = header and library out of sync
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+def check(fn_name, code):
+    if code != 0:
+        raise XAError(fn_name, code, lib().xa_last_error().decode('utf-8', 'replace'))
+
+
+def call(fn_name, *args):
+    """Call an int-returning entry point and raise XAError on a non-zero code."""
+    check(fn_name, getattr(lib(), fn_name)(*args))

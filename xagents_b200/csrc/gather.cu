@@ -1,0 +1,360 @@
+// Permute-gather of rollout rows into minibatches.
+//
+// Replaces the five tf.gather calls per minibatch of PPO.get_mini_batches (xagents/ppo/agent.py:149-154)
+// and folds in the env-major flatten of BaseAgent.concat_step_batches (xagents/base.py:559-564): the
+// source stays in the time-major layout the rollout was written in and the flat env-major sample id is
+// remapped to a row on the fly, so the reference's full-rollout transpose copy never happens.
+//
+// This is pure byte movement, ~99.8 % of the path's traffic (2 * row_bytes per sample per epoch), and
+// HBM-bound.  Two data paths:
+//
+//  * BULK  -- rows are moved by the TMA engine as non-tensor bulk copies: global -> shared
+//             (cp.async.bulk ... mbarrier::complete_tx) then shared -> global (cp.async.bulk ... bulk_group).
+//             One elected lane per warp drives one stage of a shared-memory ring, so a CTA keeps `stages`
+//             whole rows (28 224 B for 84x84x4 frames) in flight with ~10 instructions per row and no
+//             register staging.  One more warp gathers the fp32 scalar fields for the CTA's slice.
+//  * VECTOR -- 128-bit LDG/STG (narrower when alignment forces it), 8 independent loads per thread before
+//             the stores; the general path for short or unaligned rows.
+#include "xa_common.cuh"
+
+namespace {
+
+constexpr int kMaxStages = 16;
+constexpr int kSmemBudget = 227 * 1024 - 1024;  // dynamic shared memory we allow one CTA to take
+
+struct GatherParams {
+  const uint8_t* src;
+  uint8_t* dst;
+  const int32_t* idx;
+  int64_t n_idx;
+  int64_t row_bytes;
+  int n_steps, n_envs;
+  // bulk path: a row is cut into chunks_per_row pieces of chunk_bytes (the last one may be shorter)
+  int chunks_per_row;
+  uint32_t chunk_bytes;
+  int stages;
+  // scalar fields riding along
+  int n_fields;
+  const float* fsrc[XA_MAX_FIELDS];
+  float* fdst[XA_MAX_FIELDS];
+};
+
+// ------------------------------------------------------------------------------------------ bulk
+__global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(const GatherParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * p.chunk_bytes);
+
+  if (warp < stages) {
+    if (lane != 0) return;
+    uint64_t* bar = bars + warp;
+    uint8_t* buf = smem + static_cast<size_t>(warp) * p.chunk_bytes;
+    xa::mbar_init(bar, 1);
+    xa::fence_barrier_init();
+    const uint64_t policy = xa::policy_evict_first();
+    const int64_t n_items = p.n_idx * p.chunks_per_row;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * stages;
+    int64_t k = static_cast<int64_t>(blockIdx.x) * stages + warp;
+    uint32_t parity = 0;
+    int32_t b = k < n_items ? p.idx[k / p.chunks_per_row] : 0;
+    for (; k < n_items; k += stride) {
+      const int64_t i = k / p.chunks_per_row;
+      const int64_t off = (k - i * p.chunks_per_row) * static_cast<int64_t>(p.chunk_bytes);
+      const int64_t left = p.row_bytes - off;
+      const uint32_t bytes = left < static_cast<int64_t>(p.chunk_bytes) ? static_cast<uint32_t>(left) : p.chunk_bytes;
+      const int64_t row = xa::sample_row(b, p.n_steps, p.n_envs);
+      xa::mbar_expect_tx(bar, bytes);
+      xa::bulk_g2s(buf, p.src + row * p.row_bytes + off, bytes, bar, policy);
+      const int64_t kn = k + stride;
+      if (kn < n_items) b = p.idx[kn / p.chunks_per_row];  // next index travels under the copy
+      xa::mbar_wait(bar, parity);
+      parity ^= 1u;
+      xa::bulk_s2g(p.dst + i * p.row_bytes + off, buf, bytes);
+      xa::bulk_commit();
+      xa::bulk_wait_read<0>();  // the engine has read the stage out: it may be refilled
+    }
+    xa::bulk_wait_all<0>();
+    return;
+  }
+
+  // last warp: scalar fields for this CTA's contiguous slice of samples
+  if (p.n_fields > 0) {
+    const int64_t per = (p.n_idx + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = per * blockIdx.x;
+    const int64_t hi = lo + per < p.n_idx ? lo + per : p.n_idx;
+    for (int64_t i = lo + lane; i < hi; i += 32) {
+      const int64_t row = xa::sample_row(p.idx[i], p.n_steps, p.n_envs);
+#pragma unroll
+      for (int f = 0; f < XA_MAX_FIELDS; ++f)
+        if (f < p.n_fields) p.fdst[f][i] = __ldg(p.fsrc[f] + row);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ vector
+template <typename V>
+__device__ __forceinline__ V load_vec(const V* p) {
+  return __ldg(p);
+}
+template <>
+__device__ __forceinline__ int4 load_vec<int4>(const int4* p) {
+  return xa::ld_stream(p);
+}
+template <typename V>
+__device__ __forceinline__ void store_vec(V* p, const V& v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void store_vec<int4>(int4* p, const int4& v) {
+  xa::st_stream(p, v);
+}
+
+constexpr int kVecThreads = 256;
+constexpr int kVecUnroll = 8;
+
+// threads_per_row (power of two <= 256) lanes cooperate on a row; 256/threads_per_row rows per block pass
+template <typename V>
+__global__ void __launch_bounds__(kVecThreads) gather_vector_kernel(const GatherParams p, int threads_per_row_log2) {
+  const int tpr = 1 << threads_per_row_log2;
+  const int rows_per_block = kVecThreads >> threads_per_row_log2;
+  const int sub = threadIdx.x >> threads_per_row_log2;
+  const int lane = threadIdx.x & (tpr - 1);
+  const int64_t n_vec = p.row_bytes / static_cast<int64_t>(sizeof(V));
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * rows_per_block + sub; i < p.n_idx;
+       i += static_cast<int64_t>(gridDim.x) * rows_per_block) {
+    const int64_t row = xa::sample_row(p.idx[i], p.n_steps, p.n_envs);
+    const V* s = reinterpret_cast<const V*>(p.src + row * p.row_bytes);
+    V* d = reinterpret_cast<V*>(p.dst + i * p.row_bytes);
+    for (int64_t base = lane; base < n_vec; base += static_cast<int64_t>(tpr) * kVecUnroll) {
+      V regs[kVecUnroll];
+#pragma unroll
+      for (int u = 0; u < kVecUnroll; ++u) {
+        const int64_t v = base + static_cast<int64_t>(u) * tpr;
+        if (v < n_vec) regs[u] = load_vec(s + v);
+      }
+#pragma unroll
+      for (int u = 0; u < kVecUnroll; ++u) {
+        const int64_t v = base + static_cast<int64_t>(u) * tpr;
+        if (v < n_vec) store_vec(d + v, regs[u]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_fields_kernel(const GatherParams p) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n_idx;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = xa::sample_row(p.idx[i], p.n_steps, p.n_envs);
+#pragma unroll
+    for (int f = 0; f < XA_MAX_FIELDS; ++f)
+      if (f < p.n_fields) p.fdst[f][i] = __ldg(p.fsrc[f] + row);
+  }
+}
+
+// uint8 frame -> fp32 / 255 (base.py:505-506) behind the gather: each thread turns 4 pixels into one float4
+template <bool kVec4>
+__global__ void __launch_bounds__(256) gather_scaled_kernel(const GatherParams p) {
+  float* out = reinterpret_cast<float*>(p.dst);
+  for (int64_t i = blockIdx.x; i < p.n_idx; i += gridDim.x) {
+    const int64_t row = xa::sample_row(p.idx[i], p.n_steps, p.n_envs);
+    const uint8_t* s = p.src + row * p.row_bytes;
+    float* d = out + i * p.row_bytes;
+    if (kVec4) {
+      const int64_t n4 = p.row_bytes >> 2;
+      for (int64_t v = threadIdx.x; v < n4; v += blockDim.x) {
+        const uchar4 px = __ldg(reinterpret_cast<const uchar4*>(s) + v);
+        float4 o;
+        o.x = __fdiv_rn(static_cast<float>(px.x), 255.0f);
+        o.y = __fdiv_rn(static_cast<float>(px.y), 255.0f);
+        o.z = __fdiv_rn(static_cast<float>(px.z), 255.0f);
+        o.w = __fdiv_rn(static_cast<float>(px.w), 255.0f);
+        __stcs(reinterpret_cast<float4*>(d) + v, o);
+      }
+    } else {
+      for (int64_t v = threadIdx.x; v < p.row_bytes; v += blockDim.x) d[v] = __fdiv_rn(static_cast<float>(s[v]), 255.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int widest_vector(const GatherParams& p) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(p.src) | reinterpret_cast<uintptr_t>(p.dst) |
+                         static_cast<uintptr_t>(p.row_bytes);
+  if ((bits & 15) == 0) return 16;
+  if ((bits & 7) == 0) return 8;
+  if ((bits & 3) == 0) return 4;
+  if ((bits & 1) == 0) return 2;
+  return 1;
+}
+
+int log2_ceil_pow2(int64_t n, int cap_log2) {
+  int l = 0;
+  while ((int64_t(1) << l) < n && l < cap_log2) ++l;
+  return l;
+}
+
+template <typename V>
+void launch_vector(const GatherParams& p, cudaStream_t stream) {
+  const int64_t n_vec = p.row_bytes / static_cast<int64_t>(sizeof(V));
+  const int tpr_log2 = log2_ceil_pow2((n_vec + kVecUnroll - 1) / kVecUnroll, 8);
+  const int rows_per_block = kVecThreads >> tpr_log2;
+  const int64_t want = (p.n_idx + rows_per_block - 1) / rows_per_block;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t cap = static_cast<int64_t>(sms) * 8 * 4;  // a few waves of 8 resident blocks per SM
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  gather_vector_kernel<V><<<grid, kVecThreads, 0, stream>>>(p, tpr_log2);
+}
+
+int launch_fields(const GatherParams& p, cudaStream_t stream) {
+  if (p.n_fields == 0) return XA_OK;
+  const int64_t want = (p.n_idx + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(want < 4096 ? want : 4096);
+  gather_fields_kernel<<<grid, 256, 0, stream>>>(p);
+  return xa::check_launch("xa_gather_fields_f32");
+}
+
+bool bulk_eligible(const GatherParams& p) {
+  return ((reinterpret_cast<uintptr_t>(p.src) | reinterpret_cast<uintptr_t>(p.dst) | static_cast<uintptr_t>(p.row_bytes)) & 15) == 0;
+}
+
+int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what) {
+  if (p.n_idx == 0) return XA_OK;
+  const bool can_bulk = bulk_eligible(p);
+  if (mode == XA_GATHER_BULK)
+    XA_REQUIRE(can_bulk, XA_EALIGN, "%s: XA_GATHER_BULK needs 16-byte aligned src, dst and row_bytes (row_bytes=%lld)", what,
+               static_cast<long long>(p.row_bytes));
+  const bool use_bulk = mode == XA_GATHER_BULK || (mode == XA_GATHER_AUTO && can_bulk && p.row_bytes >= 2048);
+  if (use_bulk) {
+    // cut rows into equal 16-B-multiple chunks of at most 56 KB so that at least 4 stages fit
+    constexpr int64_t kMaxChunk = 56 * 1024;
+    p.chunks_per_row = static_cast<int>((p.row_bytes + kMaxChunk - 1) / kMaxChunk);
+    int64_t chunk = (p.row_bytes + p.chunks_per_row - 1) / p.chunks_per_row;
+    chunk = (chunk + 15) & ~int64_t(15);
+    p.chunk_bytes = static_cast<uint32_t>(chunk);
+    int stages = static_cast<int>((kSmemBudget - 8 * kMaxStages) / chunk);
+    if (stages > kMaxStages) stages = kMaxStages;
+    // short rows: prefer two CTAs per SM of 8 stages over one of 16
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    const size_t smem = static_cast<size_t>(stages) * chunk + 8 * kMaxStages;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) {
+        xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+        return static_cast<int>(e);
+      }
+      configured = kSmemBudget;
+    }
+    const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+    const int ctas_per_sm = static_cast<int>(kSmemBudget / (smem + 1024)) > 0 ? static_cast<int>(kSmemBudget / (smem + 1024)) : 1;
+    const int64_t items = p.n_idx * p.chunks_per_row;
+    int64_t grid = (items + stages - 1) / stages;
+    const int64_t cap = static_cast<int64_t>(sms) * (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+    if (grid > cap) grid = cap;
+    gather_bulk_kernel<<<static_cast<unsigned>(grid), 32 * (stages + 1), smem, stream>>>(p);
+    return xa::check_launch(what);
+  }
+  switch (widest_vector(p)) {
+    case 16: launch_vector<int4>(p, stream); break;
+    case 8: launch_vector<int2>(p, stream); break;
+    case 4: launch_vector<int>(p, stream); break;
+    case 2: launch_vector<short>(p, stream); break;
+    default: launch_vector<char>(p, stream); break;
+  }
+  if (int rc = xa::check_launch(what)) return rc;
+  return launch_fields(p, stream);
+}
+
+int fill_common(GatherParams& p, const char* what, const void* src, const int32_t* idx, void* dst, int64_t n_idx,
+                int64_t row_bytes, int64_t n_src_rows, int n_steps, int n_envs) {
+  XA_REQUIRE(n_idx >= 0 && row_bytes > 0 && n_src_rows > 0, XA_EINVAL, "%s: n_idx=%lld row_bytes=%lld n_src_rows=%lld", what,
+             static_cast<long long>(n_idx), static_cast<long long>(row_bytes), static_cast<long long>(n_src_rows));
+  XA_REQUIRE(n_idx == 0 || (src && idx && dst), XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(xa::aligned(idx, 4), XA_EALIGN, "%s: idx must be 4-byte aligned", what);
+  XA_REQUIRE(n_steps >= 0 && n_envs >= 0, XA_EINVAL, "%s: negative n_steps/n_envs", what);
+  if (n_steps > 0)
+    XA_REQUIRE(static_cast<int64_t>(n_steps) * n_envs == n_src_rows, XA_EINVAL, "%s: n_steps*n_envs=%lld != n_src_rows=%lld", what,
+               static_cast<long long>(n_steps) * n_envs, static_cast<long long>(n_src_rows));
+  XA_REQUIRE(n_src_rows <= INT32_MAX, XA_EOVERFLOW, "%s: n_src_rows exceeds int32 indices", what);
+  p = GatherParams{};
+  p.src = static_cast<const uint8_t*>(src);
+  p.dst = static_cast<uint8_t*>(dst);
+  p.idx = idx;
+  p.n_idx = n_idx;
+  p.row_bytes = row_bytes;
+  p.n_steps = n_steps;
+  p.n_envs = n_envs;
+  return XA_OK;
+}
+
+int fill_fields(GatherParams& p, const char* what, const float* const* src, float* const* dst, int n_fields) {
+  XA_REQUIRE(n_fields >= 0 && n_fields <= XA_MAX_FIELDS, XA_EINVAL, "%s: n_fields=%d not in [0,%d]", what, n_fields, XA_MAX_FIELDS);
+  XA_REQUIRE(n_fields == 0 || (src && dst), XA_EINVAL, "%s: null field table", what);
+  p.n_fields = n_fields;
+  for (int f = 0; f < n_fields; ++f) {
+    XA_REQUIRE(src[f] && dst[f], XA_EINVAL, "%s: null pointer for field %d", what, f);
+    XA_REQUIRE(xa::aligned(src[f], 4) && xa::aligned(dst[f], 4), XA_EALIGN, "%s: field %d not 4-byte aligned", what, f);
+    p.fsrc[f] = src[f];
+    p.fdst[f] = dst[f];
+  }
+  return XA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xa_gather_rows(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src_rows,
+                   int n_steps, int n_envs, int mode, xa_stream_t stream) {
+  GatherParams p;
+  if (int rc = fill_common(p, "xa_gather_rows", src, idx, dst, n_idx, row_bytes, n_src_rows, n_steps, n_envs)) return rc;
+  XA_REQUIRE(mode >= XA_GATHER_AUTO && mode <= XA_GATHER_VECTOR, XA_EINVAL, "xa_gather_rows: unknown mode %d", mode);
+  return launch_rows(p, mode, static_cast<cudaStream_t>(stream), "xa_gather_rows");
+}
+
+int xa_gather_fields_f32(const float* const* src, float* const* dst, int n_fields, const int32_t* idx, int64_t n_idx, int n_steps,
+                         int n_envs, xa_stream_t stream) {
+  XA_REQUIRE(n_idx >= 0, XA_EINVAL, "xa_gather_fields_f32: n_idx=%lld", static_cast<long long>(n_idx));
+  XA_REQUIRE(n_idx == 0 || idx, XA_EINVAL, "xa_gather_fields_f32: null idx");
+  XA_REQUIRE(n_steps >= 0 && n_envs >= 0, XA_EINVAL, "xa_gather_fields_f32: negative n_steps/n_envs");
+  GatherParams p{};
+  p.idx = idx;
+  p.n_idx = n_idx;
+  p.n_steps = n_steps;
+  p.n_envs = n_envs;
+  if (int rc = fill_fields(p, "xa_gather_fields_f32", src, dst, n_fields)) return rc;
+  if (n_idx == 0) return XA_OK;
+  return launch_fields(p, static_cast<cudaStream_t>(stream));
+}
+
+int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, int64_t n_src_rows, const float* const* field_src,
+                        float* const* field_dst, int n_fields, const int32_t* idx, int64_t n_idx, int n_steps, int n_envs,
+                        int mode, xa_stream_t stream) {
+  GatherParams p;
+  if (int rc = fill_common(p, "xa_gather_minibatch", obs_src, idx, obs_dst, n_idx, row_bytes, n_src_rows, n_steps, n_envs)) return rc;
+  XA_REQUIRE(mode >= XA_GATHER_AUTO && mode <= XA_GATHER_VECTOR, XA_EINVAL, "xa_gather_minibatch: unknown mode %d", mode);
+  if (int rc = fill_fields(p, "xa_gather_minibatch", field_src, field_dst, n_fields)) return rc;
+  return launch_rows(p, mode, static_cast<cudaStream_t>(stream), "xa_gather_minibatch");
+}
+
+int xa_gather_rows_u8_scaled_f32(const uint8_t* src, const int32_t* idx, float* dst, int64_t n_idx, int64_t row_bytes,
+                                 int64_t n_src_rows, int n_steps, int n_envs, xa_stream_t stream) {
+  GatherParams p;
+  if (int rc = fill_common(p, "xa_gather_rows_u8_scaled_f32", src, idx, dst, n_idx, row_bytes, n_src_rows, n_steps, n_envs)) return rc;
+  XA_REQUIRE(xa::aligned(dst, 4), XA_EALIGN, "xa_gather_rows_u8_scaled_f32: dst must be 4-byte aligned");
+  if (n_idx == 0) return XA_OK;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t cap = static_cast<int64_t>(sms) * 8 * 4;
+  const unsigned grid = static_cast<unsigned>(n_idx < cap ? n_idx : cap);
+  const bool vec4 = (row_bytes & 3) == 0 && xa::aligned(src, 4) && xa::aligned(dst, 16);
+  if (vec4)
+    gather_scaled_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    gather_scaled_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return xa::check_launch("xa_gather_rows_u8_scaled_f32");
+}
+
+}  // extern "C"

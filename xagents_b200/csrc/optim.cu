@@ -1,0 +1,151 @@
+// Fused global-norm clip + Adam over one flat fp32 parameter buffer (the step right after the loss).
+//
+// Replaces tf.clip_by_global_norm + Keras Adam.apply_gradients at xagents/ppo/agent.py:135-137 and
+// xagents/a2c/agent.py:216-218 (Adam built at xagents/utils/common.py:476,589-594).  All trainable
+// tensors live back to back in one buffer (1.69 M floats for the Nature CNN), so "multi-tensor" is one
+// launch: pass 1 reduces sum(g^2) deterministically (fp64 partials, last block finishes), pass 2 reads
+// g, m, v, theta once and writes m, v, theta once (28 B per parameter) with the clip scale and an
+// optional 1/world_size factor (gradient averaging after the all-reduce) folded in.
+#include <math.h>
+
+#include "xa_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 4;
+constexpr int kMaxBlocks = 148 * 8;
+
+struct OptimWorkspace {
+  unsigned int ticket;
+  unsigned int pad;
+  double sumsq;
+  double partials[1];  // [kMaxBlocks]
+};
+
+__global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(const float* __restrict__ g, int64_t n, OptimWorkspace* ws) {
+  __shared__ double scratch[kThreads / 32];
+  __shared__ bool s_last;
+  double acc = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const int64_t n4 = n / kVec;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(g4 + i);
+    acc += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y + static_cast<double>(x.z) * x.z +
+           static_cast<double>(x.w) * x.w;
+  }
+  for (int64_t i = n4 * kVec + static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride)
+    acc += static_cast<double>(g[i]) * g[i];
+  const double total = xa::block_sum<kThreads / 32>(acc, scratch);
+  if (threadIdx.x == 0) {
+    ws->partials[blockIdx.x] = total;
+    __threadfence();
+    s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double t = 0.0;
+  for (unsigned k = threadIdx.x; k < gridDim.x; k += kThreads) t += const_cast<const volatile double*>(ws->partials)[k];
+  t = xa::block_sum<kThreads / 32>(t, scratch);
+  if (threadIdx.x == 0) {
+    ws->sumsq = t;
+    ws->ticket = 0;
+  }
+}
+
+struct AdamParams {
+  float* param;
+  const float* grad;
+  float* m;
+  float* v;
+  int64_t n;
+  const OptimWorkspace* ws;
+  float lr_t, beta1, beta2, eps, clip, grad_scale;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamParams& a, float scale) {
+  g *= scale;
+  m = a.beta1 * m + (1.0f - a.beta1) * g;
+  v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+  p -= a.lr_t * m / (sqrtf(v) + a.eps);
+}
+
+__global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a) {
+  float scale = a.grad_scale;
+  if (a.clip > 0.0f) {
+    // tf.clip_by_global_norm: g * clip * min(1/norm, 1/clip)
+    const float norm = a.grad_scale * static_cast<float>(sqrt(a.ws->sumsq));
+    scale *= a.clip * fminf(1.0f / norm, 1.0f / a.clip);
+  }
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const int64_t n4 = a.n / kVec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    float4 p = reinterpret_cast<float4*>(a.param)[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.grad) + i);
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    adam_one(p.x, g.x, m.x, v.x, a, scale);
+    adam_one(p.y, g.y, m.y, v.y, a, scale);
+    adam_one(p.z, g.z, m.z, v.z, a, scale);
+    adam_one(p.w, g.w, m.w, v.w, a, scale);
+    reinterpret_cast<float4*>(a.param)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+  }
+  for (int64_t i = n4 * kVec + static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < a.n; i += stride)
+    adam_one(a.param[i], a.grad[i], a.m[i], a.v[i], a, scale);
+}
+
+unsigned blocks_for(int64_t n) {
+  const int64_t want = (n + kThreads * kVec - 1) / (kThreads * kVec);
+  return static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t xa_clip_adam_workspace_bytes(int64_t n) {
+  (void)n;
+  return 16 + static_cast<int64_t>(sizeof(double)) * kMaxBlocks;
+}
+
+int xa_grad_sumsq_f32(const float* grads, int64_t n, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
+  XA_REQUIRE(grads && workspace, XA_EINVAL, "xa_grad_sumsq_f32: null pointer");
+  XA_REQUIRE(n > 0, XA_EINVAL, "xa_grad_sumsq_f32: n=%lld", static_cast<long long>(n));
+  XA_REQUIRE(workspace_bytes >= xa_clip_adam_workspace_bytes(n), XA_ENOSPACE, "xa_grad_sumsq_f32: workspace too small");
+  XA_REQUIRE(xa::aligned(grads, 16) && xa::aligned(workspace, 16), XA_EALIGN, "xa_grad_sumsq_f32: 16-byte alignment required");
+  grad_sumsq_kernel<<<blocks_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(grads, n, static_cast<OptimWorkspace*>(workspace));
+  return xa::check_launch("xa_grad_sumsq_f32");
+}
+
+int xa_clip_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, const void* workspace, double lr,
+                     double beta1, double beta2, double eps, double clip_norm, int64_t step, double grad_scale,
+                     xa_stream_t stream) {
+  XA_REQUIRE(param && grad && m && v, XA_EINVAL, "xa_clip_adam_f32: null pointer");
+  XA_REQUIRE(n > 0 && step > 0, XA_EINVAL, "xa_clip_adam_f32: n=%lld step=%lld must be positive", static_cast<long long>(n),
+             static_cast<long long>(step));
+  XA_REQUIRE(clip_norm <= 0.0 || workspace != nullptr, XA_EINVAL, "xa_clip_adam_f32: clipping needs the sumsq workspace");
+  XA_REQUIRE(xa::aligned(param, 16) && xa::aligned(grad, 16) && xa::aligned(m, 16) && xa::aligned(v, 16), XA_EALIGN,
+             "xa_clip_adam_f32: 16-byte alignment required");
+  AdamParams a;
+  a.param = param;
+  a.grad = grad;
+  a.m = m;
+  a.v = v;
+  a.n = n;
+  a.ws = static_cast<const OptimWorkspace*>(workspace);
+  // Keras Adam: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+  a.lr_t = static_cast<float>(lr * sqrt(1.0 - pow(beta2, static_cast<double>(step))) / (1.0 - pow(beta1, static_cast<double>(step))));
+  a.beta1 = static_cast<float>(beta1);
+  a.beta2 = static_cast<float>(beta2);
+  a.eps = static_cast<float>(eps);
+  a.clip = static_cast<float>(clip_norm);
+  a.grad_scale = static_cast<float>(grad_scale);
+  clip_adam_kernel<<<blocks_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return xa::check_launch("xa_clip_adam_f32");
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// Reverse segmented scans over the rollout: GAE returns (PPO) and discounted n-step returns (A2C).
+//
+// Replaces PPO.calculate_returns (xagents/ppo/agent.py:80-94) and A2C.calculate_returns
+// (xagents/a2c/agent.py:165-171), which walk T in a Python loop of NumPy calls on [E] vectors.
+//
+// Both recurrences are x_t = b_t + c_t * x_{t+1} with c_t = 0 wherever the next step is terminal, so a
+// done flag cuts the carry exactly like a segment head.  Layout is time-major
+// [T, E]: lanes run along E (every load/store is a coalesced 128-B line), warps run along T.
+// Warp w of a block owns a chunk of kChunk consecutive steps for 32 envs; it loads the chunk once into
+// registers (3*kChunk+1 independent loads in flight per thread), reduces it to the affine map (C, B),
+// exchanges maps through shared memory, derives its carry-in from the later chunks and then replays its
+// chunk from registers.  Inputs are read once and outputs written once: 16 B per env-step for GAE,
+// 12 B for n-step returns.  With one warp per block (XA_SCAN_SEQUENTIAL) no map is ever composed and the
+// arithmetic is the reference's, operation for operation (explicit _rn intrinsics: no FMA contraction),
+// so results are bit-identical to the NumPy loop.
+#include "xa_common.cuh"
+
+namespace {
+
+constexpr int kChunk = 8;
+constexpr int kMaxWarps = 16;
+
+struct ScanParams {
+  const float* rewards;
+  const float* values;       // GAE only
+  const float* last_values;  // [E] bootstrap
+  const float* dones;        // [T+1, E]
+  float* returns;
+  float* advantages;  // GAE only, may be null
+  int n_steps;
+  int n_envs;
+  float gamma;
+  float gamma_lam;  // fp32(double(gamma) * double(lam)), folded as the reference folds it
+};
+
+template <bool kNstep, bool kMulti>
+__global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const ScanParams p) {
+  __shared__ float s_c[kMulti ? kMaxWarps : 1][32];
+  __shared__ float s_b[kMulti ? kMaxWarps : 1][32];
+  __shared__ float s_carry[32];
+
+  const int lane = threadIdx.x;
+  const int w = threadIdx.y;
+  const int n_warps = blockDim.y;
+  const int env = blockIdx.x * 32 + lane;
+  const bool active = env < p.n_envs;
+  const int T = p.n_steps;
+  const size_t E = static_cast<size_t>(p.n_envs);
+  const float gamma = p.gamma;
+  const float gl = p.gamma_lam;
+
+  // value flowing in from the future: R_T for n-step returns (a2c/agent.py:165-166), 0 for GAE (ppo/agent.py:81)
+  float carry = (kNstep && active) ? p.last_values[env] : 0.0f;
+
+  for (int hi = T; hi > 0; hi -= n_warps * kChunk) {
+    const int t1 = hi - (n_warps - 1 - w) * kChunk;  // exclusive end of this warp's chunk
+    const int t0 = max(t1 - kChunk, 0);
+
+    float coef[kChunk];  // GAE: gamma*lam*alive ; n-step: alive
+    float bias[kChunk];  // GAE: delta          ; n-step: reward
+    float val[kChunk];   // GAE: V_t (needed again for returns = A + V)
+    if (active && t1 > 0) {
+      float rew[kChunk], done[kChunk];
+      float v_next = 0.0f;
+      if (!kNstep) v_next = (t1 == T) ? p.last_values[env] : p.values[static_cast<size_t>(t1) * E + env];
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) {
+        const int t = t0 + j;
+        if (t < t1) {
+          const size_t o = static_cast<size_t>(t) * E + env;
+          rew[j] = p.rewards[o];
+          done[j] = p.dones[o + E];  // row t+1 gates step t (a2c/agent.py:116,129,138)
+          if (!kNstep) val[j] = p.values[o];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) {
+        if (t0 + j < t1) {
+          const float alive = __fsub_rn(1.0f, done[j]);  // ppo/agent.py:85
+          if (kNstep) {
+            coef[j] = alive;
+            bias[j] = rew[j];
+          } else {
+            const float vn = (j + 1 < kChunk && t0 + j + 1 < t1) ? val[j + 1] : v_next;
+            // delta = r + gamma*V_{t+1}*alive - V_t, evaluated left to right (ppo/agent.py:87-91)
+            bias[j] = __fsub_rn(__fadd_rn(rew[j], __fmul_rn(__fmul_rn(gamma, vn), alive)), val[j]);
+            coef[j] = __fmul_rn(gl, alive);  // ppo/agent.py:92
+          }
+        }
+      }
+    }
+
+    float x = carry;
+    if (kMulti) {
+      // reduce the chunk to x -> B + C*x and publish it
+      float cc = 1.0f, bb = 0.0f;
+      if (active && t1 > 0) {
+#pragma unroll
+        for (int j = kChunk - 1; j >= 0; --j) {
+          if (t0 + j < t1) {
+            const float c = kNstep ? __fmul_rn(gamma, coef[j]) : coef[j];
+            bb = __fadd_rn(bias[j], __fmul_rn(c, bb));
+            cc = __fmul_rn(cc, c);
+          }
+        }
+      }
+      s_c[w][lane] = cc;
+      s_b[w][lane] = bb;
+      __syncthreads();
+      for (int w2 = n_warps - 1; w2 > w; --w2) x = __fadd_rn(s_b[w2][lane], __fmul_rn(s_c[w2][lane], x));
+    }
+
+    if (active && t1 > 0) {
+#pragma unroll
+      for (int j = kChunk - 1; j >= 0; --j) {
+        const int t = t0 + j;
+        if (t < t1) {
+          const size_t o = static_cast<size_t>(t) * E + env;
+          if (kNstep) {
+            // R_t = r_t + gamma*R_{t+1}*(1-d_{t+1})   (a2c/agent.py:168-170)
+            x = __fadd_rn(bias[j], __fmul_rn(__fmul_rn(gamma, x), coef[j]));
+            p.returns[o] = x;
+          } else {
+            // last_lam = delta + gamma*lam*alive*last_lam ; returns = last_lam + V   (ppo/agent.py:92-94)
+            x = __fadd_rn(bias[j], __fmul_rn(coef[j], x));
+            p.returns[o] = __fadd_rn(x, val[j]);
+            if (p.advantages != nullptr) p.advantages[o] = x;
+          }
+        }
+      }
+    }
+
+    if (kMulti) {
+      if (w == 0) s_carry[lane] = x;  // earliest chunk of this span: its value is what flows further back
+      __syncthreads();
+      carry = s_carry[lane];
+    } else {
+      carry = x;
+    }
+  }
+}
+
+int pick_warps(int mode, int n_steps, int n_envs) {
+  const int chunks = (n_steps + kChunk - 1) / kChunk;
+  if (mode == XA_SCAN_SEQUENTIAL || chunks <= 1) return 1;
+  const int max_w = chunks < kMaxWarps ? chunks : kMaxWarps;
+  if (mode == XA_SCAN_CHUNKED) return max_w > 1 ? max_w : 2;
+  // AUTO: aim for >= 32 resident warps per SM so the load latency of a chunk hides behind other warps
+  const long blocks = (n_envs + 31) / 32;
+  const long want = 32L * (xa::sm_count() > 0 ? xa::sm_count() : 148);
+  long wps = (want + blocks - 1) / blocks;
+  if (wps < 1) wps = 1;
+  if (wps > max_w) wps = max_w;
+  return static_cast<int>(wps);
+}
+
+template <bool kNstep>
+int launch(const ScanParams& p, int mode, cudaStream_t stream, const char* what) {
+  const int n_warps = pick_warps(mode, p.n_steps, p.n_envs);
+  const dim3 block(32, n_warps);
+  const dim3 grid((p.n_envs + 31) / 32);
+  if (n_warps == 1)
+    returns_scan_kernel<kNstep, false><<<grid, block, 0, stream>>>(p);
+  else
+    returns_scan_kernel<kNstep, true><<<grid, block, 0, stream>>>(p);
+  return xa::check_launch(what);
+}
+
+int check_shape(const char* what, int n_steps, int n_envs, int mode) {
+  XA_REQUIRE(n_steps > 0 && n_envs > 0, XA_EINVAL, "%s: n_steps=%d n_envs=%d must be positive", what, n_steps, n_envs);
+  XA_REQUIRE(mode >= XA_SCAN_AUTO && mode <= XA_SCAN_CHUNKED, XA_EINVAL, "%s: unknown mode %d", what, mode);
+  XA_REQUIRE((static_cast<int64_t>(n_steps) + 1) * n_envs < (int64_t(1) << 40), XA_EOVERFLOW, "%s: rollout too large", what);
+  return XA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xa_gae_f32(const float* rewards, const float* values, const float* last_values, const float* dones, float* returns,
+               float* advantages, int n_steps, int n_envs, double gamma, double lam, int mode, xa_stream_t stream) {
+  if (int rc = check_shape("xa_gae_f32", n_steps, n_envs, mode)) return rc;
+  XA_REQUIRE(rewards && values && last_values && dones && returns, XA_EINVAL, "xa_gae_f32: null pointer");
+  XA_REQUIRE(xa::aligned(rewards, 4) && xa::aligned(values, 4) && xa::aligned(last_values, 4) && xa::aligned(dones, 4) &&
+                 xa::aligned(returns, 4) && xa::aligned(advantages, 4),
+             XA_EALIGN, "xa_gae_f32: pointers must be 4-byte aligned");
+  ScanParams p{rewards, values, last_values, dones, returns, advantages, n_steps, n_envs, static_cast<float>(gamma),
+               static_cast<float>(gamma * lam)};
+  return launch<false>(p, mode, static_cast<cudaStream_t>(stream), "xa_gae_f32");
+}
+
+int xa_nstep_returns_f32(const float* rewards, const float* dones, const float* last_values, float* returns, int n_steps,
+                         int n_envs, double gamma, int mode, xa_stream_t stream) {
+  if (int rc = check_shape("xa_nstep_returns_f32", n_steps, n_envs, mode)) return rc;
+  XA_REQUIRE(rewards && dones && last_values && returns, XA_EINVAL, "xa_nstep_returns_f32: null pointer");
+  XA_REQUIRE(xa::aligned(rewards, 4) && xa::aligned(dones, 4) && xa::aligned(last_values, 4) && xa::aligned(returns, 4),
+             XA_EALIGN, "xa_nstep_returns_f32: pointers must be 4-byte aligned");
+  ScanParams p{rewards, nullptr, last_values, dones, returns, nullptr, n_steps, n_envs, static_cast<float>(gamma), 0.0f};
+  return launch<true>(p, mode, static_cast<cudaStream_t>(stream), "xa_nstep_returns_f32");
+}
+
+}  // extern "C"

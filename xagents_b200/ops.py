@@ -1,0 +1,326 @@
+"""Tensor-level entry points of the hot path: DLPack in, kernels through the C ABI, tensors out.
+
+Arguments may be torch CUDA tensors, any object with `__dlpack__`, or raw DLPack capsules (e.g.
+`tf.experimental.dlpack.to_dlpack(t)`), all zero-copy.  Outputs are allocated with torch (device
+memory and streams are torch's job here; the arithmetic is not) unless `out=` buffers are given.
+Every call is asynchronous on `stream` (default: torch's current stream).  There is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _ffi
+from ._dlpack import as_device_array
+from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_AUTO, XA_GATHER_BULK, XA_GATHER_VECTOR,
+                   XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
+
+__all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
+           'adv_moments', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
+           'launch_count', 'reset_launch_count']
+
+SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
+GATHER_MODES = {'auto': XA_GATHER_AUTO, 'bulk': XA_GATHER_BULK, 'vector': XA_GATHER_VECTOR}
+ACTOR_KINDS = {'logits': XA_ACTOR_LOGITS, 'probs': XA_ACTOR_PROBS, 'normal': XA_ACTOR_NORMAL}
+
+_launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream(stream):
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    return getattr(stream, 'cuda_stream', stream)
+
+
+def _dev(x, dtype=None):
+    return as_device_array(x, dtype)
+
+
+def _device_of(arr):
+    return torch.device('cuda', arr.device_id)
+
+
+def _ptr(x):
+    return ctypes.c_void_p(x.ptr if x is not None else None)
+
+
+def _tptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
+
+
+# ------------------------------------------------------------------------------------------ returns
+def gae_returns(rewards, values, last_values, dones, gamma, lam, *, mode='auto', with_advantages=False, out=None,
+                stream=None):
+    """PPO.calculate_returns arithmetic (xagents/ppo/agent.py:80-94).
+
+    rewards, values [T,E]; last_values [E] (bootstrap); dones [T+1,E]; fp32 on the device.
+    Returns returns [T,E] (and advantages when asked).
+    """
+    r, v, lv, d = _dev(rewards, 'float32'), _dev(values, 'float32'), _dev(last_values, 'float32'), _dev(dones, 'float32')
+    if len(r.shape) != 2:
+        raise ValueError(f'rewards must be [n_steps, n_envs], got {r.shape}')
+    T, E = r.shape
+    if v.size != T * E or lv.size != E or d.size != (T + 1) * E:
+        raise ValueError(f'shape mismatch: rewards {r.shape}, values {v.shape}, last_values {lv.shape}, dones {d.shape} '
+                         f'(dones needs n_steps+1 rows)')
+    dev = _device_of(r)
+    ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=dev)
+    adv = torch.empty((T, E), dtype=torch.float32, device=dev) if with_advantages else None
+    _ffi.call('xa_gae_f32', _ptr(r), _ptr(v), _ptr(lv), _ptr(d), _tptr(ret), _tptr(adv), T, E, float(gamma), float(lam),
+              SCAN_MODES[mode], _stream(stream))
+    _count()
+    return (ret, adv) if with_advantages else ret
+
+
+def nstep_returns(rewards, dones, last_values, gamma, *, mode='auto', out=None, stream=None):
+    """A2C.calculate_returns arithmetic (xagents/a2c/agent.py:165-171)."""
+    r, d, lv = _dev(rewards, 'float32'), _dev(dones, 'float32'), _dev(last_values, 'float32')
+    if len(r.shape) != 2:
+        raise ValueError(f'rewards must be [n_steps, n_envs], got {r.shape}')
+    T, E = r.shape
+    if lv.size != E or d.size != (T + 1) * E:
+        raise ValueError(f'shape mismatch: rewards {r.shape}, last_values {lv.shape}, dones {d.shape}')
+    ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=_device_of(r))
+    _ffi.call('xa_nstep_returns_f32', _ptr(r), _ptr(d), _ptr(lv), _tptr(ret), T, E, float(gamma), SCAN_MODES[mode],
+              _stream(stream))
+    _count()
+    return ret
+
+
+# ------------------------------------------------------------------------------------------ gathers
+def _layout(time_major):
+    if time_major is None:
+        return 0, 0
+    T, E = time_major
+    return int(T), int(E)
+
+
+def _torch_dtype(name):
+    return getattr(torch, name)
+
+
+def gather_rows(src, idx, *, time_major=None, mode='auto', out=None, stream=None):
+    """tf.gather(src, idx) along axis 0 (xagents/ppo/agent.py:154), whole rows, bit-exact.
+
+    src [rows, ...]; with time_major=(T, E) src is the time-major rollout [T, E, ...] and idx holds
+    env-major flat sample ids (base.py:559-564), so no flatten copy is needed.
+    """
+    s, i = _dev(src), _dev(idx, 'int32')
+    T, E = _layout(time_major)
+    lead = 2 if T else 1
+    n_rows = s.shape[0] * (s.shape[1] if T else 1)
+    if T and (s.shape[0], s.shape[1]) != (T, E):
+        raise ValueError(f'src {s.shape} is not time-major [{T},{E},...]')
+    row_shape = s.shape[lead:]
+    row_bytes = s.itemsize
+    for k in row_shape:
+        row_bytes *= k
+    n = i.size
+    dst = out if out is not None else torch.empty((n,) + tuple(row_shape), dtype=_torch_dtype(s.dtype), device=_device_of(s))
+    _ffi.call('xa_gather_rows', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, GATHER_MODES[mode], _stream(stream))
+    _count()
+    return dst
+
+
+def _field_tables(fields, outs, n, dev):
+    if len(fields) > XA_MAX_FIELDS:
+        raise ValueError(f'at most {XA_MAX_FIELDS} fields per call')
+    arrs = [_dev(f, 'float32') for f in fields]
+    if outs is None:
+        outs = [torch.empty((n,), dtype=torch.float32, device=dev) for _ in arrs]
+    src = (ctypes.c_void_p * len(arrs))(*[a.ptr for a in arrs])
+    dst = (ctypes.c_void_p * len(arrs))(*[o.data_ptr() for o in outs])
+    return arrs, outs, src, dst
+
+
+def gather_fields(fields, idx, *, time_major=None, out=None, stream=None):
+    """The four scalar-per-sample tf.gather calls of ppo/agent.py:154 in one launch."""
+    i = _dev(idx, 'int32')
+    T, E = _layout(time_major)
+    arrs, outs, src, dst = _field_tables(fields, out, i.size, _device_of(i))
+    _ffi.call('xa_gather_fields_f32', src, dst, len(arrs), _ptr(i), i.size, T, E, _stream(stream))
+    _count()
+    return outs
+
+
+def gather_minibatch(obs, fields, idx, *, time_major=None, mode='auto', out_obs=None, out_fields=None, stream=None):
+    """Observation rows + scalar fields of one minibatch (or a whole epoch) in one call."""
+    s, i = _dev(obs), _dev(idx, 'int32')
+    T, E = _layout(time_major)
+    lead = 2 if T else 1
+    n_rows = s.shape[0] * (s.shape[1] if T else 1)
+    row_shape = s.shape[lead:]
+    row_bytes = s.itemsize
+    for k in row_shape:
+        row_bytes *= k
+    n = i.size
+    dev = _device_of(s)
+    dst = out_obs if out_obs is not None else torch.empty((n,) + tuple(row_shape), dtype=_torch_dtype(s.dtype), device=dev)
+    arrs, outs, fsrc, fdst = _field_tables(fields, out_fields, n, dev)
+    _ffi.call('xa_gather_minibatch', _ptr(s), _tptr(dst), row_bytes, n_rows, fsrc, fdst, len(arrs), _ptr(i), n, T, E,
+              GATHER_MODES[mode], _stream(stream))
+    # bulk path: one kernel; vector path: rows kernel + fields kernel
+    _count(1 if (mode == 'bulk' or (mode == 'auto' and row_bytes >= 2048 and row_bytes % 16 == 0)) else 1 + (len(arrs) > 0))
+    return dst, outs
+
+
+def gather_rows_scaled(src_u8, idx, *, time_major=None, out=None, stream=None):
+    """gather + cast(uint8 -> fp32) / 255 (xagents/base.py:505-506) in one pass."""
+    s, i = _dev(src_u8, 'uint8'), _dev(idx, 'int32')
+    T, E = _layout(time_major)
+    lead = 2 if T else 1
+    n_rows = s.shape[0] * (s.shape[1] if T else 1)
+    row_shape = s.shape[lead:]
+    row_bytes = 1
+    for k in row_shape:
+        row_bytes *= k
+    n = i.size
+    dst = out if out is not None else torch.empty((n,) + tuple(row_shape), dtype=torch.float32, device=_device_of(s))
+    _ffi.call('xa_gather_rows_u8_scaled_f32', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, _stream(stream))
+    _count()
+    return dst
+
+
+# ------------------------------------------------------------------------------------------ moments + losses
+def adv_moments(returns, old_values, idx, mb_offsets, *, time_major=None, out=None, stream=None):
+    """(count, mean, M2) of returns - old_values for each minibatch idx[mb_offsets[m]:mb_offsets[m+1]]
+    (ppo/agent.py:180-183).  Returns float64 [n_minibatches, 4] on the device."""
+    r, v = _dev(returns, 'float32'), _dev(old_values, 'float32')
+    i = _dev(idx, 'int32') if idx is not None else None
+    T, E = _layout(time_major)
+    n_mb = len(mb_offsets) - 1
+    offs = (ctypes.c_int64 * (n_mb + 1))(*[int(o) for o in mb_offsets])
+    mom = out if out is not None else torch.empty((n_mb, XA_MOMENT_STRIDE), dtype=torch.float64, device=_device_of(r))
+    _ffi.call('xa_adv_moments_f32', _ptr(r), _ptr(v), _ptr(i), offs, n_mb, T, E, _tptr(mom), _stream(stream))
+    _count((n_mb + 63) // 64)
+    return mom
+
+
+def loss_workspace(n, device):
+    """Zero-filled scratch for ppo_loss / a2c_loss over minibatches of up to n samples (reusable)."""
+    nbytes = _ffi.lib().xa_loss_workspace_bytes(int(n))
+    return torch.zeros(((nbytes + 15) // 16) * 2, dtype=torch.float64, device=device)
+
+
+def _loss(fn, ppo, actor_out, values, actions, old_log_probs, old_values, returns, *, idx, time_major, advantages, moments,
+          clip, entropy_coef, value_loss_coef, advantage_epsilon, actor_kind, need_grads, return_advantages, workspace,
+          out, stream):
+    ao, v = _dev(actor_out, 'float32'), _dev(values, 'float32')
+    n = v.size
+    n_actions = ao.size // n
+    dev = _device_of(ao)
+    args = _ffi.LossArgs()
+    keep = [ao, v]
+
+    def put(name, obj, dtype='float32'):
+        if obj is None:
+            setattr(args, name, None)
+            return None
+        arr = _dev(obj, dtype)
+        keep.append(arr)
+        setattr(args, name, arr.ptr)
+        return arr
+
+    args.actor_out, args.values = ao.ptr, v.ptr
+    put('actions', actions)
+    put('old_log_probs', old_log_probs)
+    put('old_values', old_values)
+    put('returns', returns)
+    put('idx', idx, 'int32')
+    args.n_steps, args.n_envs = _layout(time_major)
+    put('advantages', advantages)
+    if moments is not None:
+        if isinstance(moments, tuple):          # (base tensor, offset, n_parts, part_stride), in doubles
+            base, offset, parts, stride = moments
+            mom = _dev(base, 'float64')
+            keep.append(mom)
+            args.moments = mom.ptr + 8 * int(offset)
+            args.n_moment_parts, args.moment_part_stride = int(parts), int(stride)
+        else:
+            mom = put('moments', moments, 'float64')
+            parts = 1 if len(mom.shape) == 1 else mom.shape[0]
+            args.n_moment_parts, args.moment_part_stride = parts, (mom.shape[-1] if parts > 1 else 0)
+    args.n, args.n_actions, args.actor_kind = n, n_actions, ACTOR_KINDS[actor_kind]
+    args.clip, args.ent_coef, args.vf_coef, args.adv_eps = clip, entropy_coef, value_loss_coef, advantage_epsilon
+    scalars, d_actor, d_values, adv_out = out if out is not None else (None, None, None, None)
+    if scalars is None:
+        scalars = torch.empty(4, dtype=torch.float32, device=dev)
+    if need_grads and d_actor is None:
+        d_actor = torch.empty((n, n_actions), dtype=torch.float32, device=dev)
+    if need_grads and d_values is None:
+        d_values = torch.empty((n,), dtype=torch.float32, device=dev)
+    if return_advantages and adv_out is None:
+        adv_out = torch.empty((n,), dtype=torch.float32, device=dev)
+    if workspace is None:
+        workspace = loss_workspace(n, dev)
+    args.out_scalars, args.d_actor, args.d_values = scalars.data_ptr(), _tptr(d_actor), _tptr(d_values)
+    args.advantages_out = _tptr(adv_out)
+    args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    _ffi.call(fn, ctypes.byref(args), _stream(stream))
+    _count()
+    return scalars, d_actor, d_values, adv_out
+
+
+def ppo_loss(actor_out, values, actions, old_log_probs, old_values, returns, *, idx=None, time_major=None,
+             advantages=None, moments=None, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5,
+             advantage_epsilon=1e-8, actor_kind='logits', need_grads=True, return_advantages=False, workspace=None,
+             out=None, stream=None):
+    """PPO.update_gradients loss + gradients w.r.t. the model outputs (ppo/agent.py:112-134), with the
+    per-minibatch advantage normalisation of ppo/agent.py:180-183 folded in (from `moments`: one
+    [4] row, [parts, 4] rows to combine, or a (base, offset, n_parts, part_stride) view in doubles
+    into an all-gathered [ranks, minibatches, 4] buffer) unless normalised `advantages` are supplied.
+
+    Returns (scalars[4] = loss, pg, value_loss, entropy; d_actor [n,A]; d_values [n]; advantages|None).
+    """
+    return _loss('xa_ppo_loss_f32', True, actor_out, values, actions, old_log_probs, old_values, returns, idx=idx,
+                 time_major=time_major, advantages=advantages, moments=moments, clip=clip_norm, entropy_coef=entropy_coef,
+                 value_loss_coef=value_loss_coef, advantage_epsilon=advantage_epsilon, actor_kind=actor_kind,
+                 need_grads=need_grads, return_advantages=return_advantages, workspace=workspace, out=out, stream=stream)
+
+
+def a2c_loss(actor_out, values, actions, old_values, returns, *, idx=None, time_major=None, entropy_coef=0.01,
+             value_loss_coef=0.5, actor_kind='logits', need_grads=True, workspace=None, out=None, stream=None):
+    """A2C.train_step loss + gradients (a2c/agent.py:202-215)."""
+    return _loss('xa_a2c_loss_f32', False, actor_out, values, actions, None, old_values, returns, idx=idx,
+                 time_major=time_major, advantages=None, moments=None, clip=0.0, entropy_coef=entropy_coef,
+                 value_loss_coef=value_loss_coef, advantage_epsilon=0.0, actor_kind=actor_kind, need_grads=need_grads,
+                 return_advantages=False, workspace=workspace, out=out, stream=stream)[:3]
+
+
+# ------------------------------------------------------------------------------------------ optimiser
+def optim_workspace(device):
+    nbytes = _ffi.lib().xa_clip_adam_workspace_bytes(0)
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+
+def grad_sumsq(grads, workspace, *, stream=None):
+    g = _dev(grads, 'float32')
+    _ffi.call('xa_grad_sumsq_f32', _ptr(g), g.size, workspace.data_ptr(), workspace.numel() * 8, _stream(stream))
+    _count()
+
+
+def clip_adam(param, grad, m, v, step, *, workspace=None, lr=7e-4, beta1=0.9, beta2=0.999, eps=1e-7, clip_norm=None,
+              grad_scale=1.0, stream=None):
+    """tf.clip_by_global_norm + Keras Adam on one flat fp32 buffer, in place (ppo/agent.py:135-137)."""
+    p, g, mm, vv = _dev(param, 'float32'), _dev(grad, 'float32'), _dev(m, 'float32'), _dev(v, 'float32')
+    clip = float(clip_norm) if clip_norm else 0.0
+    if clip > 0.0:
+        if workspace is None:
+            raise ValueError('clip_norm needs the workspace that grad_sumsq filled')
+        grad_sumsq(grad, workspace, stream=stream)
+    _ffi.call('xa_clip_adam_f32', _ptr(p), _ptr(g), _ptr(mm), _ptr(vv), p.size, _tptr(workspace), float(lr), float(beta1),
+              float(beta2), float(eps), clip, int(step), float(grad_scale), _stream(stream))
+    _count()
