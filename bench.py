@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Headline benchmark: PPO env-steps/s through GAE + permute-gather + loss (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [--gpus N ...]            the reference's CPU path on the host cores
+
+A "step" is one PPO train step of the hot path over one synthetic rollout: 1 GAE scan, the advantage
+moments of all K*M minibatches, then K*M x (minibatch gather of uint8 frames + 4 scalar fields, fused
+loss forward+backward).  N=1 runs config C3 (n_envs=256, n_steps=128, 4 epochs x 4 minibatches, 84x84x4
+uint8 frames); N>1 runs C4 (n_envs=4096 sharded over the ranks, NCCL gradient all-reduce per minibatch
+on a side stream + one all-gather of advantage moments per step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'ppo_env_steps_per_sec_gae_gather_loss'
+UNIT = 'env-steps/s'
+NATURE_CNN_PARAMS = 1_687_719          # Conv2D Nature CNN @84x84x4, 6 actions: C1 payload
+FALLBACK_HBM_GBS = 6650.0              # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=None, choices=[None, 'c3', 'c4'])
+    ap.add_argument('--n-envs', type=int, default=None, help='total n_envs (overrides the workload default)')
+    ap.add_argument('--n-steps', type=int, default=128)
+    ap.add_argument('--gather-mode', default='auto', choices=['auto', 'bulk', 'vector'])
+    ap.add_argument('--scan-mode', default='auto', choices=['auto', 'sequential', 'chunked'])
+    ap.add_argument('--no-overlap', action='store_true', help='gathers on the compute stream instead of a data stream')
+    ap.add_argument('--materialize-fields', action='store_true', help='gather the 4 scalar fields instead of reading them through idx')
+    ap.add_argument('--staging', type=int, default=2)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-envs', type=int, default=64)
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+
+
+def workload_of(args, world):
+    name = args.workload or ('c3' if world == 1 else 'c4')
+    total_envs = args.n_envs or (256 if name == 'c3' else 4096)
+    desc = (f'{name}: PPO on synthetic Atari frames (84x84x4 uint8), n_envs={total_envs}'
+            f'{" sharded over %d ranks" % world if world > 1 else ""}, n_steps={args.n_steps}, '
+            f'4 epochs x 4 minibatches, 6 actions')
+    return name, total_envs, desc
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(args, sample_envs, steps, warmup):
+    """The reference's CPU path (oracle port; TF is not installable here) on a bounded sample."""
+    import torch
+
+    from oracle import cpu_path
+    from xagents_b200 import synthetic
+    ro = synthetic.make_rollout(args.n_steps, sample_envs, epochs=4)
+    res = cpu_path.time_cpu_baseline(ro, steps=steps, warmup=warmup, layout='reference')
+    sample = (f'{steps} timed train steps (after {warmup} warm-up) of n_envs={sample_envs} x n_steps={args.n_steps} '
+              f'(= {sample_envs * args.n_steps} samples/step, fp32 observations as the reference stores them), '
+              f'4 epochs x 4 minibatches; env-steps/s is size-independent on the CPU')
+    return res, {'value': res['env_steps_per_sec'], 'unit': UNIT, 'cores': res['threads'], 'kind': 'port', 'sample': sample,
+                 'host_cpus': os.cpu_count(), 'torch_threads': torch.get_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return
+    name, total_envs, desc = workload_of(args, max(world, args.gpus))
+    # bound the whole run to a few minutes: ~40 ms of CPU work per env of sample per step
+    budget_s = 150.0
+    per_env_s = 0.04
+    sample = int(min(args.cpu_sample_envs, max(8, budget_s / ((args.steps + args.warmup) * per_env_s))))
+    sample -= sample % 4
+    res, base = cpu_reference(args, max(sample, 4), args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': res['env_steps_per_sec'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['seconds_per_step'] * 1e3,
+        'higher_is_better': True, 'scaling': 'weak' if args.gpus == 1 else 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'note': 'reference CPU path (NumPy + torch-CPU stand-ins for the TF-CPU ops; '
+                                             'TensorFlow is not installable in this image), host cores only'},
+        'cpu_baseline': base,
+        'e2e': {'value': res['env_steps_per_sec'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from xagents_b200 import dist as xdist
+    from xagents_b200 import hotpath
+
+    rank, local_rank, world = xdist.init_from_env()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: xagents_b200 has no CPU path'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    comm = xdist.ShardComm(device=dev) if world > 1 else None
+    name, total_envs, desc = workload_of(args, world)
+    lo, hi = xdist.shard_range(total_envs, rank, world)
+    E, T, A = hi - lo, args.n_steps, 6
+    hp = hotpath.PPOHotPath(T, E, (84, 84, 4), A, device=dev, gather_mode=args.gather_mode, scan_mode=args.scan_mode,
+                            comm=comm, fuse_fields=not args.materialize_fields, staging=args.staging,
+                            overlap=not args.no_overlap)
+    N, B, K, M = hp.N, hp.B, hp.K, hp.M
+
+    # ---- synthetic rollout, resident in HBM before the timed region ---------------------------------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    hp.obs.copy_(torch.randint(0, 256, hp.obs.shape, dtype=torch.uint8, device=dev, generator=gen))
+    rng = np.random.default_rng(1234 + rank)
+    host = {
+        'rewards': rng.standard_normal((T, E)).astype(np.float32),
+        'values': rng.standard_normal((T, E)).astype(np.float32),
+        'last_values': rng.standard_normal(E).astype(np.float32),
+        'dones': (rng.random((T + 1, E)) < 0.01).astype(np.float32),
+        'actions': rng.integers(0, A, (T, E)).astype(np.float32),
+        'log_probs': (-np.abs(rng.standard_normal((T, E))) - 0.5).astype(np.float32),
+    }
+    for k, v in host.items():
+        getattr(hp, k).copy_(torch.from_numpy(v))
+    for k in range(K):
+        hp.perms[k].copy_(torch.randperm(N, device=dev, generator=gen).to(torch.int32))
+    hp.actor_out.copy_(torch.randn(hp.actor_out.shape, device=dev, generator=gen))
+    hp.critic_out.copy_(torch.randn(hp.critic_out.shape, device=dev, generator=gen))
+    grad_buf = torch.zeros(NATURE_CNN_PARAMS, device=dev) if comm is not None else None
+    stream = torch.cuda.current_stream(dev)
+    hp.prepare(stream)
+    n_gathers = K * len(hp.slices)
+    after_loss = (lambda i: comm.all_reduce_gradients_async(grad_buf)) if comm is not None else None
+
+    def step(on_gather=None):
+        hp.run(on_gather=on_gather, after_loss=after_loss)
+        if comm is not None:
+            comm.wait_gradients()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides ------
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_gathers)]
+          for _ in range(args.steps)]
+    cur = [0]
+
+    def timed_gather(i, fn, fargs):
+        a, b = ev[cur[0]][i]
+        a.record(hp.data_stream)
+        rc = fn(*fargs)
+        b.record(hp.data_stream)
+        return rc
+
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if comm is not None:
+        comm.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.start()
+    start.record(stream)
+    for s in range(args.steps):
+        cur[0] = s
+        step(timed_gather)
+    stop.record(stream)
+    torch.cuda.synchronize(dev)
+    if comm is not None:
+        comm.barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = start.elapsed_time(stop)
+    if comm is not None:
+        elapsed_ms = comm.max_over_ranks(elapsed_ms)
+    gather_ms = [a.elapsed_time(b) for row in ev for (a, b) in row]
+    ms_per_step = elapsed_ms / args.steps
+    value = total_envs * T * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end: host buffers in, loss scalars out, every step -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = {'obs': torch.empty(hp.obs.shape, dtype=torch.uint8).pin_memory()}
+        pinned['obs'].copy_(hp.obs)
+        for k, v in host.items():
+            pinned[k] = torch.from_numpy(v).pin_memory()
+        pinned['perms'] = hp.perms.cpu().pin_memory()
+        pinned['actor_out'] = hp.actor_out.cpu().pin_memory()
+        pinned['critic_out'] = hp.critic_out.cpu().pin_memory()
+        out_host = torch.empty(hp.scalars.shape, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in pinned.values())
+        d2h = out_host.numel() * 4
+
+        def e2e_step():
+            for k, t in pinned.items():
+                getattr(hp, k).copy_(t, non_blocking=True)
+            step()
+            out_host.copy_(hp.scalars, non_blocking=True)
+            stream.synchronize()                         # the caller reads the losses of this step
+            return float(out_host[0, 0])
+
+        for _ in range(3):
+            e2e_step()
+        if comm is not None:
+            comm.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record(stream)
+        n_e2e = max(3, min(args.steps, 20))
+        for _ in range(n_e2e):
+            e2e_step()
+        e_stop.record(stream)
+        torch.cuda.synchronize(dev)
+        e_ms = e_start.elapsed_time(e_stop)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max(e_ms, wall_ms)                       # host-side waits count end to end
+        if comm is not None:
+            comm.barrier()
+            e_ms = comm.max_over_ranks(e_ms)
+        e2e = {'value': total_envs * T * n_e2e / (e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'steps': n_e2e, 'ms_per_step': e_ms / n_e2e,
+               'api': 'PPOHotPath.load-equivalent copies from pinned host buffers + run() + read of the loss scalars'}
+        del pinned
+
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    alg = hp.algorithmic_bytes()
+    g_ms = statistics.mean(gather_ms)
+    achieved = alg['gather_per_launch'] / (g_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'gather_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    step_gbs = alg['total'] / (ms_per_step * 1e-3) / 1e9     # this rank's shard; ranks are symmetric
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong',
+        'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars', 'data': 'synthetic',
+        'config': {'workload': desc, 'n_envs_per_gpu': E, 'samples_per_step_per_gpu': N, 'mini_batch_size_per_gpu': B,
+                   'gather_mode': args.gather_mode, 'scan_mode': args.scan_mode,
+                   'streams': 'gathers on a data stream, GAE/moments/losses on the compute stream' if hp.overlap else 'single stream',
+                   'scalar_fields': 'read through the permutation inside the loss' if hp.fuse_fields else 'gathered per minibatch',
+                   'l2': f'inputs larger than L2: {hp.obs.numel() / 1e6:.0f} MB of frames per GPU read once per epoch',
+                   'collectives': ('none (single GPU)' if world == 1 else
+                                   f'NCCL all-reduce of {NATURE_CNN_PARAMS} fp32 gradients per minibatch on a side stream '
+                                   f'+ 1 all-gather of advantage moments per step')},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'kernel': 'gather_bulk_kernel' if args.gather_mode != 'vector' else 'gather_vector_kernel',
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg['gather_per_launch'],
+                     'avg_launch_ms': g_ms, 'launches_timed': len(gather_ms),
+                     'whole_step': {'algorithmic_bytes_per_step_per_gpu': alg['total'], 'achieved': step_gbs,
+                                    'frac': step_gbs / peak, 'frac_of_nominal_8TBs': step_gbs / 8000.0}},
+        'gpu_launches': hp.kernel_launches_per_step * args.steps,
+        'clocks': clocks,
+    }
+    if e2e is not None:
+        line['e2e'] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        _, base = cpu_reference(args, args.cpu_sample_envs, 3, 1)
+        line['cpu_baseline'] = base
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -243,11 +243,14 @@ def clip_by_global_norm(grads, clip):
 
 
 def adam_step(param, grad, m, v, step, lr=7e-4, beta1=0.9, beta2=0.999, eps=1e-7):
-    """Keras Adam (common.py:476, defaults utils/cli.py:14-25), bias-corrected-lr form."""
+    """Keras Adam (common.py:476, defaults utils/cli.py:14-25) as TF's dense ApplyAdam evaluates it:
+    hyper-parameters are cast to fp32 first, so 1-beta is an fp32 subtraction; m += (g-m)(1-b1);
+    v += (g^2-v)(1-b2); theta -= lr_t*m/(sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t)."""
     f = np.float32
-    m = f(beta1) * m + f(1 - beta1) * grad
-    v = f(beta2) * v + f(1 - beta2) * np.square(grad)
-    lr_t = f(lr * np.sqrt(1 - beta2 ** step) / (1 - beta1 ** step))
+    b1, b2 = f(beta1), f(beta2)
+    m = m + (grad - m) * (f(1) - b1)
+    v = v + (np.square(grad) - v) * (f(1) - b2)
+    lr_t = f(lr) * np.sqrt(f(1) - b2 ** f(step)) / (f(1) - b1 ** f(step))
     return param - lr_t * m / (np.sqrt(v) + f(eps)), m, v
 
 

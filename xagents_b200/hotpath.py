@@ -1,0 +1,250 @@
+"""Device-resident PPO / A2C rollout-to-update path for one rank's shard of environments.
+
+`PPOHotPath` owns the time-major rollout buffers and the per-minibatch staging buffers and turns one
+train step of the reference --
+
+    PPO.get_batch:        calculate_returns (GAE)            xagents/ppo/agent.py:48-94, 193-213
+                          concat_step_batches (flatten)      xagents/base.py:549-564      [fused away]
+    PPO.run_ppo_epochs:   get_mini_batches (shuffle+gather)  xagents/ppo/agent.py:139-155
+                          advantage normalisation            xagents/ppo/agent.py:180-183
+    PPO.update_gradients: clipped surrogate+value+entropy    xagents/ppo/agent.py:96-134
+
+-- into 2 + 2*K*M kernel launches through the C ABI: one GAE scan, one moments launch for all K*M
+minibatches, then per minibatch one gather (observation rows by TMA bulk copy + the four scalar
+fields) and one fused loss forward+backward.  Launch arguments are resolved once (`prepare`), so a
+step is a tight loop of ctypes calls on fixed device pointers: the host stays far ahead of the GPU
+and the sequence is CUDA-graph capturable.
+
+Two streams: the caller's stream carries the arithmetic (GAE -> moments -> loss_0 .. loss_{KM-1}); a
+side "data" stream carries the gathers back to back, double-buffered through `staging` minibatch
+buffers, so the HBM-bound byte movement never waits for the latency-bound scalar kernels (in training,
+for the model's forward/backward of the previous minibatch).  With `fuse_fields=True` (default) the loss
+reads the four per-sample rollout scalars straight through the permutation (no scalar gather launch,
+no dependence of the gathers on GAE); `fuse_fields=False` materialises them like the reference does.
+
+With a `dist.ShardComm` the environments are sharded across ranks (each rank owns a contiguous
+env-major range), the per-minibatch advantage moments are all-gathered once per step (collective C2)
+so normalisation uses the GLOBAL minibatch statistics as the single-process reference does, and a
+gradient all-reduce per minibatch (collective C1) runs on a side stream under the next gather.
+"""
+import ctypes
+
+import torch
+
+from . import _ffi
+from ._ffi import XA_MOMENT_STRIDE
+from .ops import ACTOR_KINDS, GATHER_MODES, SCAN_MODES
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(None)
+
+
+class PPOHotPath:
+    FIELDS = ('actions', 'returns', 'values', 'log_probs')     # gathered per minibatch, in this order
+
+    def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
+                 gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
+                 actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
+                 fuse_fields=True, staging=2, overlap=True):
+        self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
+        self.N = self.T * self.E
+        self.K, self.M = int(ppo_epochs), int(mini_batches)
+        self.B = self.N // self.M                                  # mini_batch_size (ppo/agent.py:42-46)
+        assert self.B > 0, f'Invalid batch size to mini-batch size ratio {self.N}: {self.M}'
+        self.slices = [(lo, min(lo + self.B, self.N)) for lo in range(0, self.N, self.B)]   # ppo/agent.py:152
+        self.n_mb = self.K * len(self.slices)
+        self.obs_shape = tuple(obs_shape)
+        self.gamma, self.lam = float(gamma), float(lam)
+        self.clip_norm, self.entropy_coef = float(clip_norm), float(entropy_coef)
+        self.value_loss_coef, self.advantage_epsilon = float(value_loss_coef), float(advantage_epsilon)
+        self.actor_kind = actor_kind
+        self.device = torch.device(device)
+        self.gather_mode, self.scan_mode = gather_mode, scan_mode
+        self.comm = comm
+        self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
+        dev, f32 = self.device, torch.float32
+        T, E, N, B, A = self.T, self.E, self.N, self.B, self.A
+        # rollout, time-major (what the rollout loop writes step by step)
+        self.obs = torch.empty((T, E) + self.obs_shape, dtype=obs_dtype, device=dev)
+        self.rewards = torch.empty((T, E), dtype=f32, device=dev)
+        self.values = torch.empty((T, E), dtype=f32, device=dev)
+        self.last_values = torch.empty((E,), dtype=f32, device=dev)
+        self.dones = torch.empty((T + 1, E), dtype=f32, device=dev)
+        self.actions = torch.empty((T, E), dtype=f32, device=dev)
+        self.log_probs = torch.empty((T, E), dtype=f32, device=dev)
+        self.returns = torch.empty((T, E), dtype=f32, device=dev)
+        # permutations of env-major flat sample ids, one row per epoch
+        self.perms = torch.empty((self.K, N), dtype=torch.int32, device=dev)
+        # minibatch staging
+        self.mb_obs = torch.empty((self.staging, B) + self.obs_shape, dtype=obs_dtype, device=dev)
+        self.mb_fields = torch.empty((self.staging, len(self.FIELDS), B), dtype=f32, device=dev)
+        # model outputs for every minibatch (filled by the caller / the model forward)
+        self.actor_out = torch.empty((self.n_mb, B, A), dtype=f32, device=dev)
+        self.critic_out = torch.empty((self.n_mb, B), dtype=f32, device=dev)
+        # results
+        self.moments = torch.zeros((self.n_mb, XA_MOMENT_STRIDE), dtype=torch.float64, device=dev)
+        world = comm.world_size if comm is not None else 1
+        self.all_moments = (torch.zeros((world, self.n_mb, XA_MOMENT_STRIDE), dtype=torch.float64, device=dev)
+                            if world > 1 else None)
+        self.scalars = torch.zeros((self.n_mb, 4), dtype=f32, device=dev)
+        self.d_actor = torch.empty((B, A), dtype=f32, device=dev)
+        self.d_values = torch.empty((B,), dtype=f32, device=dev)
+        nbytes = _ffi.lib().xa_loss_workspace_bytes(B)
+        self.workspace = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        self._calls = None
+        self.row_bytes = self.obs.element_size()
+        for k in self.obs_shape:
+            self.row_bytes *= k
+
+    # ---------------------------------------------------------------------------------- data in
+    ROLLOUT_FIELDS = ('obs', 'rewards', 'values', 'last_values', 'dones', 'actions', 'log_probs')
+
+    def load(self, rollout, stream=None, non_blocking=True):
+        """Copy a rollout (host tensors / numpy / synthetic.Rollout) into the device buffers."""
+        with torch.cuda.stream(stream) if stream is not None else _null():
+            for name in self.ROLLOUT_FIELDS:
+                src = getattr(rollout, name) if not isinstance(rollout, dict) else rollout[name]
+                getattr(self, name).copy_(torch.as_tensor(src), non_blocking=non_blocking)
+
+    def h2d_bytes(self):
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.ROLLOUT_FIELDS)
+
+    # ---------------------------------------------------------------------------------- plan
+    def prepare(self, stream=None):
+        """Resolve every launch of one train step to (cfunc, args) on fixed device pointers."""
+        lib = _ffi.lib()
+        self.compute_stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.data_stream = torch.cuda.Stream(self.device) if self.overlap else self.compute_stream
+        sc = ctypes.c_void_p(self.compute_stream.cuda_stream)
+        sd = ctypes.c_void_p(self.data_stream.cuda_stream)
+        T, E, N, B = self.T, self.E, self.N, self.B
+        self._gae = (lib.xa_gae_f32, (_p(self.rewards), _p(self.values), _p(self.last_values), _p(self.dones),
+                                      _p(self.returns), _p(None), T, E, self.gamma, self.lam, SCAN_MODES[self.scan_mode], sc))
+        offsets = []
+        for k in range(self.K):
+            offsets += [k * N + lo for lo, _ in self.slices]
+        offsets.append(self.K * N)
+        # the last slice of epoch k ends where epoch k+1 starts, so one ascending table serves all K*M
+        self._offsets = (ctypes.c_int64 * len(offsets))(*offsets)
+        self._moments = (lib.xa_adv_moments_f32, (_p(self.returns), _p(self.values), _p(self.perms), self._offsets, self.n_mb,
+                                                  T, E, _p(self.moments), sc))
+        world = self.comm.world_size if self.comm is not None else 1
+        n_fields = 0 if self.fuse_fields else len(self.FIELDS)
+        self._field_src = (ctypes.c_void_p * 4)(*[getattr(self, f).data_ptr() for f in self.FIELDS])
+        self._field_dst, self._loss_args, self._gathers, self._losses = [], [], [], []
+        fsz = 4 * B
+        for slot in range(self.staging):
+            base = self.mb_fields.data_ptr() + slot * len(self.FIELDS) * fsz
+            self._field_dst.append((ctypes.c_void_p * 4)(*[base + j * fsz for j in range(4)]))
+        mb = 0
+        for k in range(self.K):
+            for lo, hi in self.slices:
+                n, slot = hi - lo, mb % self.staging
+                idx_addr = self.perms.data_ptr() + 4 * (k * N + lo)
+                obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * B * self.row_bytes)
+                self._gathers.append((lib.xa_gather_minibatch,
+                                      (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
+                                       n_fields, ctypes.c_void_p(idx_addr), n, T, E, GATHER_MODES[self.gather_mode], sd)))
+                a = _ffi.LossArgs()
+                a.actor_out = self.actor_out.data_ptr() + 4 * mb * B * self.A
+                a.values = self.critic_out.data_ptr() + 4 * mb * B
+                if self.fuse_fields:         # read the time-major rollout through the permutation
+                    a.actions, a.returns, a.old_values, a.old_log_probs = (
+                        getattr(self, f).data_ptr() for f in self.FIELDS)
+                    a.idx, a.n_steps, a.n_envs = idx_addr, T, E
+                else:
+                    base = self.mb_fields.data_ptr() + slot * len(self.FIELDS) * fsz
+                    a.actions, a.returns, a.old_values, a.old_log_probs = (base + j * fsz for j in range(4))
+                    a.idx, a.n_steps, a.n_envs = None, 0, 0
+                a.advantages = None
+                if world > 1:
+                    a.moments = self.all_moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
+                    a.n_moment_parts, a.moment_part_stride = world, self.n_mb * XA_MOMENT_STRIDE
+                else:
+                    a.moments = self.moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
+                    a.n_moment_parts, a.moment_part_stride = 1, 0
+                a.n, a.n_actions, a.actor_kind = n, self.A, ACTOR_KINDS[self.actor_kind]
+                a.clip, a.ent_coef, a.vf_coef, a.adv_eps = (self.clip_norm, self.entropy_coef, self.value_loss_coef,
+                                                            self.advantage_epsilon)
+                a.out_scalars = self.scalars.data_ptr() + 16 * mb
+                a.d_actor, a.d_values, a.advantages_out = self.d_actor.data_ptr(), self.d_values.data_ptr(), None
+                a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 8
+                self._loss_args.append(a)
+                self._losses.append((lib.xa_ppo_loss_f32, (ctypes.byref(a), sc)))
+                mb += 1
+        self._gather_done = [torch.cuda.Event() for _ in range(self.n_mb)]
+        self._loss_done = [torch.cuda.Event() for _ in range(self.n_mb)]
+        self._fork = torch.cuda.Event()
+        self._calls = True
+        self.kernel_launches_per_step = 2 + 2 * self.n_mb
+        return self
+
+    # ---------------------------------------------------------------------------------- run
+    def _check(self, tag, rc):
+        if rc != 0:
+            raise _ffi.XAError(tag, rc, _ffi.lib().xa_last_error().decode('utf-8', 'replace'))
+
+    def run(self, on_gather=None, after_loss=None):
+        """Issue one train step.  `on_gather(i, fn, args)` may wrap gather i (bench timing, on
+        `self.data_stream`); `after_loss(i)` runs after minibatch i's loss was enqueued on the compute
+        stream (model backward / collective C1)."""
+        if self._calls is None:
+            self.prepare()
+        cs, ds = self.compute_stream, self.data_stream
+        two = ds is not cs
+        # the data stream joins after everything already queued on the compute stream (rollout writes,
+        # the previous step) -- and after GAE only when the gathers carry the returns field
+        if two and self.fuse_fields:
+            self._fork.record(cs)
+            ds.wait_event(self._fork)
+        fn, args = self._gae
+        self._check('gae', fn(*args))
+        if two and not self.fuse_fields:
+            self._fork.record(cs)
+            ds.wait_event(self._fork)
+        fn, args = self._moments
+        self._check('moments', fn(*args))
+        if self.comm is not None and self.comm.world_size > 1:
+            self.comm.all_gather_moments(self.all_moments, self.moments)        # collective C2
+        for i in range(self.n_mb):
+            fn, args = self._gathers[i]
+            if two and i >= self.staging:
+                ds.wait_event(self._loss_done[i - self.staging])                # staging slot is free again
+            self._check('gather', on_gather(i, fn, args) if on_gather is not None else fn(*args))
+            if two:
+                self._gather_done[i].record(ds)
+                cs.wait_event(self._gather_done[i])
+            fn, args = self._losses[i]
+            self._check('loss', fn(*args))
+            if two:
+                self._loss_done[i].record(cs)
+            if after_loss is not None:
+                after_loss(i)
+
+    def minibatch_views(self, i):
+        """(states, actions, returns, old_values, old_log_probs) staging views of minibatch i."""
+        slot = i % self.staging
+        n = self.slices[i % len(self.slices)][1] - self.slices[i % len(self.slices)][0]
+        f = self.mb_fields[slot]
+        return (self.mb_obs[slot, :n],) + tuple(f[j, :n] for j in range(len(self.FIELDS)))
+
+    # ---------------------------------------------------------------------------------- accounting
+    def algorithmic_bytes(self):
+        """SURVEY.md 8d / BASELINE.md 3: bytes one train step must move (read + write, no re-reads)."""
+        N, E, K, A, F = self.N, self.E, self.K, self.A, self.row_bytes
+        gae = 16 * N + 4 * E
+        gather = K * (2 * F + 36) * N
+        moments = K * 8 * N
+        loss = K * (8 * A + 24) * N
+        per_launch = (2 * F + 4) * self.B if self.fuse_fields else (2 * F + 36) * self.B
+        return dict(gae=gae, gather=gather, moments=moments, loss=loss, total=gae + gather + moments + loss,
+                    gather_per_launch=per_launch)
+
+
+class _null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
