@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--no-overlap', action='store_true', help='gathers on the compute stream instead of a data stream')
     ap.add_argument('--materialize-fields', action='store_true', help='gather the 4 scalar fields instead of reading them through idx')
     ap.add_argument('--staging', type=int, default=2)
+    ap.add_argument('--gather-chunk', type=int, default=None, help='minibatches per gather launch (default: one epoch)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-envs', type=int, default=64)
@@ -178,7 +179,7 @@ def run_ours(args):
     E, T, A = hi - lo, args.n_steps, 6
     hp = hotpath.PPOHotPath(T, E, (84, 84, 4), A, device=dev, gather_mode=args.gather_mode, scan_mode=args.scan_mode,
                             comm=comm, fuse_fields=not args.materialize_fields, staging=args.staging,
-                            overlap=not args.no_overlap)
+                            overlap=not args.no_overlap, gather_chunk=args.gather_chunk)
     N, B, K, M = hp.N, hp.B, hp.K, hp.M
 
     # ---- synthetic rollout, resident in HBM before the timed region ---------------------------------
@@ -203,7 +204,7 @@ def run_ours(args):
     grad_buf = torch.zeros(NATURE_CNN_PARAMS, device=dev) if comm is not None else None
     stream = torch.cuda.current_stream(dev)
     hp.prepare(stream)
-    n_gathers = K * len(hp.slices)
+    n_gathers = hp.n_groups
     after_loss = (lambda i: comm.all_reduce_gradients_async(grad_buf)) if comm is not None else None
 
     def step(on_gather=None):
@@ -315,6 +316,7 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars', 'data': 'synthetic',
         'config': {'workload': desc, 'n_envs_per_gpu': E, 'samples_per_step_per_gpu': N, 'mini_batch_size_per_gpu': B,
                    'gather_mode': args.gather_mode, 'scan_mode': args.scan_mode,
+                   'minibatches_per_gather_launch': hp.chunk,
                    'streams': 'gathers on a data stream, GAE/moments/losses on the compute stream' if hp.overlap else 'single stream',
                    'scalar_fields': 'read through the permutation inside the loss' if hp.fuse_fields else 'gathered per minibatch',
                    'l2': f'inputs larger than L2: {hp.obs.numel() / 1e6:.0f} MB of frames per GPU read once per epoch',

@@ -417,3 +417,53 @@ def test_clip_adam_vs_oracle(n, clip):
         close(pd, p, rel=2e-6)
         close(md, m, rel=1e-5)
         close(vd, v, rel=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- PPOHotPath
+@pytest.mark.parametrize('fuse,chunk,overlap,staging', [(True, None, True, 2), (False, None, True, 2), (True, 1, True, 2),
+                                                        (False, 1, False, 1), (False, 8, True, 1), (True, 3, True, 2)])
+@pytest.mark.parametrize('T,E,mb', [(16, 8, 4), (7, 3, 4)])
+def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
+    """The prepared two-stream pipeline (what bench.py times) against the oracle's PPO.train_step,
+    including the trailing short minibatch (7*3 % 4 != 0) and every staging / granularity layout."""
+    from xagents_b200.hotpath import PPOHotPath
+    K = 2
+    ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=K, p_done=0.05, seed=T + E)
+    want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
+                                 ro.permutations, ro.new_logits, ro.new_values, mini_batches=mb, keep_states=True)
+    hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=mb, device=DEV, fuse_fields=fuse,
+                    gather_chunk=chunk, overlap=overlap, staging=staging, scan_mode='sequential')
+    hp.load(ro)
+    hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
+    for i, w in enumerate(want['minibatches']):                       # the "forward pass" outputs per minibatch
+        n = len(w['idx'])
+        hp.actor_out[i, :n].copy_(torch.as_tensor(ro.new_logits[w['idx']]))
+        hp.critic_out[i, :n].copy_(torch.as_tensor(ro.new_values[w['idx']]))
+    hp.prepare()
+    seen = {}
+
+    def after_loss(i):                                                # runs in stream order right after loss i
+        n = hp.mb_rows[i]
+        states = hp.minibatch_views(i)[0]
+        seen[i] = (hp.d_actor[:n].clone(), hp.d_values[:n].clone(), states.clone(),
+                   [f.clone() for f in hp.minibatch_views(i)[1:]])
+
+    for _ in range(2):                                                # twice: buffers and tickets must be reusable
+        seen.clear()
+        hp.run(after_loss=after_loss)
+        torch.cuda.synchronize()
+        assert np.array_equal(hp.returns.cpu().numpy(), want['returns'])
+        sc = hp.scalars.cpu().numpy()
+        assert len(want['minibatches']) == hp.n_mb
+        for i, w in enumerate(want['minibatches']):
+            scale = max(abs(float(w[name])) for name in ('loss', 'pg', 'vl', 'entropy'))
+            for j, name in enumerate(('loss', 'pg', 'vl', 'entropy')):
+                assert abs(sc[i, j] - w[name]) <= REL * scale, (i, name, sc[i, j], w[name])
+            da, dv, states, fields = seen[i]
+            close(da, w['dlogits'])
+            close(dv, w['dvalues'])
+            assert np.array_equal(states.cpu().numpy(), w['states'])
+            if not fuse:
+                flat = oracle.concat_step_batches(ro.actions, want['returns'], ro.values, ro.log_probs)
+                for got, full in zip(fields, flat):
+                    assert np.array_equal(got.cpu().numpy(), full[w['idx']])

@@ -46,7 +46,7 @@ class PPOHotPath:
     def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
                  gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
                  actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
-                 fuse_fields=True, staging=2, overlap=True):
+                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None):
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
         self.N = self.T * self.E
         self.K, self.M = int(ppo_epochs), int(mini_batches)
@@ -63,6 +63,16 @@ class PPOHotPath:
         self.gather_mode, self.scan_mode = gather_mode, scan_mode
         self.comm = comm
         self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
+        # minibatches moved per gather launch: 1 = per minibatch, M (default) = one epoch, K*M = the whole
+        # step (what get_mini_batches does: every minibatch materialised before the first update)
+        per_epoch = len(self.slices)
+        self.chunk = max(1, min(int(gather_chunk) if gather_chunk else per_epoch, self.n_mb))
+        self.n_groups = -(-self.n_mb // self.chunk)
+        self.staging = min(self.staging, self.n_groups)
+        mb_rows = [hi - lo for _ in range(self.K) for lo, hi in self.slices]
+        self.group_rows = [sum(mb_rows[g * self.chunk:(g + 1) * self.chunk]) for g in range(self.n_groups)]
+        self.mb_rows = mb_rows
+        self.cap = max(self.group_rows)
         dev, f32 = self.device, torch.float32
         T, E, N, B, A = self.T, self.E, self.N, self.B, self.A
         # rollout, time-major (what the rollout loop writes step by step)
@@ -77,8 +87,8 @@ class PPOHotPath:
         # permutations of env-major flat sample ids, one row per epoch
         self.perms = torch.empty((self.K, N), dtype=torch.int32, device=dev)
         # minibatch staging
-        self.mb_obs = torch.empty((self.staging, B) + self.obs_shape, dtype=obs_dtype, device=dev)
-        self.mb_fields = torch.empty((self.staging, len(self.FIELDS), B), dtype=f32, device=dev)
+        self.mb_obs = torch.empty((self.staging, self.cap) + self.obs_shape, dtype=obs_dtype, device=dev)
+        self.mb_fields = torch.empty((self.staging, len(self.FIELDS), self.cap), dtype=f32, device=dev)
         # model outputs for every minibatch (filled by the caller / the model forward)
         self.actor_out = torch.empty((self.n_mb, B, A), dtype=f32, device=dev)
         self.critic_out = torch.empty((self.n_mb, B), dtype=f32, device=dev)
@@ -133,51 +143,55 @@ class PPOHotPath:
         n_fields = 0 if self.fuse_fields else len(self.FIELDS)
         self._field_src = (ctypes.c_void_p * 4)(*[getattr(self, f).data_ptr() for f in self.FIELDS])
         self._field_dst, self._loss_args, self._gathers, self._losses = [], [], [], []
-        fsz = 4 * B
+        fsz = 4 * self.cap
         for slot in range(self.staging):
             base = self.mb_fields.data_ptr() + slot * len(self.FIELDS) * fsz
             self._field_dst.append((ctypes.c_void_p * 4)(*[base + j * fsz for j in range(4)]))
-        mb = 0
-        for k in range(self.K):
-            for lo, hi in self.slices:
-                n, slot = hi - lo, mb % self.staging
-                idx_addr = self.perms.data_ptr() + 4 * (k * N + lo)
-                obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * B * self.row_bytes)
-                self._gathers.append((lib.xa_gather_minibatch,
-                                      (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
-                                       n_fields, ctypes.c_void_p(idx_addr), n, T, E, GATHER_MODES[self.gather_mode], sd)))
-                a = _ffi.LossArgs()
-                a.actor_out = self.actor_out.data_ptr() + 4 * mb * B * self.A
-                a.values = self.critic_out.data_ptr() + 4 * mb * B
-                if self.fuse_fields:         # read the time-major rollout through the permutation
-                    a.actions, a.returns, a.old_values, a.old_log_probs = (
-                        getattr(self, f).data_ptr() for f in self.FIELDS)
-                    a.idx, a.n_steps, a.n_envs = idx_addr, T, E
-                else:
-                    base = self.mb_fields.data_ptr() + slot * len(self.FIELDS) * fsz
-                    a.actions, a.returns, a.old_values, a.old_log_probs = (base + j * fsz for j in range(4))
-                    a.idx, a.n_steps, a.n_envs = None, 0, 0
-                a.advantages = None
-                if world > 1:
-                    a.moments = self.all_moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
-                    a.n_moment_parts, a.moment_part_stride = world, self.n_mb * XA_MOMENT_STRIDE
-                else:
-                    a.moments = self.moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
-                    a.n_moment_parts, a.moment_part_stride = 1, 0
-                a.n, a.n_actions, a.actor_kind = n, self.A, ACTOR_KINDS[self.actor_kind]
-                a.clip, a.ent_coef, a.vf_coef, a.adv_eps = (self.clip_norm, self.entropy_coef, self.value_loss_coef,
-                                                            self.advantage_epsilon)
-                a.out_scalars = self.scalars.data_ptr() + 16 * mb
-                a.d_actor, a.d_values, a.advantages_out = self.d_actor.data_ptr(), self.d_values.data_ptr(), None
-                a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 8
-                self._loss_args.append(a)
-                self._losses.append((lib.xa_ppo_loss_f32, (ctypes.byref(a), sc)))
-                mb += 1
-        self._gather_done = [torch.cuda.Event() for _ in range(self.n_mb)]
-        self._loss_done = [torch.cuda.Event() for _ in range(self.n_mb)]
+        flat_off = list(self._offsets)                       # start of every minibatch in perms.view(-1)
+        self._mb_place = []                                  # minibatch -> (group, slot, first row in the slot)
+        for g in range(self.n_groups):
+            first, slot = g * self.chunk, g % self.staging
+            idx_addr = self.perms.data_ptr() + 4 * flat_off[first]
+            obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * self.cap * self.row_bytes)
+            self._gathers.append((lib.xa_gather_minibatch,
+                                  (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
+                                   n_fields, ctypes.c_void_p(idx_addr), self.group_rows[g], T, E,
+                                   GATHER_MODES[self.gather_mode], sd)))
+            for mb in range(first, min(first + self.chunk, self.n_mb)):
+                self._mb_place.append((g, slot, flat_off[mb] - flat_off[first]))
+        for mb in range(self.n_mb):
+            g, slot, row0 = self._mb_place[mb]
+            n = self.mb_rows[mb]
+            a = _ffi.LossArgs()
+            a.actor_out = self.actor_out.data_ptr() + 4 * mb * B * self.A
+            a.values = self.critic_out.data_ptr() + 4 * mb * B
+            if self.fuse_fields:         # read the time-major rollout through the permutation
+                a.actions, a.returns, a.old_values, a.old_log_probs = (getattr(self, f).data_ptr() for f in self.FIELDS)
+                a.idx, a.n_steps, a.n_envs = self.perms.data_ptr() + 4 * flat_off[mb], T, E
+            else:
+                base = self.mb_fields.data_ptr() + slot * len(self.FIELDS) * fsz + 4 * row0
+                a.actions, a.returns, a.old_values, a.old_log_probs = (base + j * fsz for j in range(4))
+                a.idx, a.n_steps, a.n_envs = None, 0, 0
+            a.advantages = None
+            if world > 1:
+                a.moments = self.all_moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
+                a.n_moment_parts, a.moment_part_stride = world, self.n_mb * XA_MOMENT_STRIDE
+            else:
+                a.moments = self.moments.data_ptr() + 8 * mb * XA_MOMENT_STRIDE
+                a.n_moment_parts, a.moment_part_stride = 1, 0
+            a.n, a.n_actions, a.actor_kind = n, self.A, ACTOR_KINDS[self.actor_kind]
+            a.clip, a.ent_coef, a.vf_coef, a.adv_eps = (self.clip_norm, self.entropy_coef, self.value_loss_coef,
+                                                        self.advantage_epsilon)
+            a.out_scalars = self.scalars.data_ptr() + 16 * mb
+            a.d_actor, a.d_values, a.advantages_out = self.d_actor.data_ptr(), self.d_values.data_ptr(), None
+            a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 8
+            self._loss_args.append(a)
+            self._losses.append((lib.xa_ppo_loss_f32, (ctypes.byref(a), sc)))
+        self._gather_done = [torch.cuda.Event() for _ in range(self.n_groups)]
+        self._loss_done = [torch.cuda.Event() for _ in range(self.n_groups)]
         self._fork = torch.cuda.Event()
         self._calls = True
-        self.kernel_launches_per_step = 2 + 2 * self.n_mb
+        self.kernel_launches_per_step = 2 + self.n_mb + self.n_groups
         return self
 
     # ---------------------------------------------------------------------------------- run
@@ -207,27 +221,28 @@ class PPOHotPath:
         self._check('moments', fn(*args))
         if self.comm is not None and self.comm.world_size > 1:
             self.comm.all_gather_moments(self.all_moments, self.moments)        # collective C2
-        for i in range(self.n_mb):
-            fn, args = self._gathers[i]
-            if two and i >= self.staging:
-                ds.wait_event(self._loss_done[i - self.staging])                # staging slot is free again
-            self._check('gather', on_gather(i, fn, args) if on_gather is not None else fn(*args))
+        for g in range(self.n_groups):
+            fn, args = self._gathers[g]
+            if two and g >= self.staging:
+                ds.wait_event(self._loss_done[g - self.staging])                # staging slot is free again
+            self._check('gather', on_gather(g, fn, args) if on_gather is not None else fn(*args))
             if two:
-                self._gather_done[i].record(ds)
-                cs.wait_event(self._gather_done[i])
-            fn, args = self._losses[i]
-            self._check('loss', fn(*args))
+                self._gather_done[g].record(ds)
+                cs.wait_event(self._gather_done[g])
+            for i in range(g * self.chunk, min((g + 1) * self.chunk, self.n_mb)):
+                fn, args = self._losses[i]
+                self._check('loss', fn(*args))
+                if after_loss is not None:
+                    after_loss(i)
             if two:
-                self._loss_done[i].record(cs)
-            if after_loss is not None:
-                after_loss(i)
+                self._loss_done[g].record(cs)
 
     def minibatch_views(self, i):
         """(states, actions, returns, old_values, old_log_probs) staging views of minibatch i."""
-        slot = i % self.staging
-        n = self.slices[i % len(self.slices)][1] - self.slices[i % len(self.slices)][0]
+        _, slot, row0 = self._mb_place[i]
+        n = self.mb_rows[i]
         f = self.mb_fields[slot]
-        return (self.mb_obs[slot, :n],) + tuple(f[j, :n] for j in range(len(self.FIELDS)))
+        return (self.mb_obs[slot, row0:row0 + n],) + tuple(f[j, row0:row0 + n] for j in range(len(self.FIELDS)))
 
     # ---------------------------------------------------------------------------------- accounting
     def algorithmic_bytes(self):
@@ -237,7 +252,8 @@ class PPOHotPath:
         gather = K * (2 * F + 36) * N
         moments = K * 8 * N
         loss = K * (8 * A + 24) * N
-        per_launch = (2 * F + 4) * self.B if self.fuse_fields else (2 * F + 36) * self.B
+        rows = sum(self.group_rows) / len(self.group_rows)
+        per_launch = (2 * F + 4) * rows if self.fuse_fields else (2 * F + 36) * rows
         return dict(gae=gae, gather=gather, moments=moments, loss=loss, total=gae + gather + moments + loss,
                     gather_per_launch=per_launch)
 
