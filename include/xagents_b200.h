@@ -102,6 +102,14 @@ int xa_adv_moments_f32(const float* returns, const float* old_values, const int3
                        const int64_t* mb_offsets, int n_minibatches, int n_steps, int n_envs,
                        double* moments, xa_stream_t stream);
 
+/* advantages[i] = ((returns - old_values)[row(i)] - mean) / (std + eps) with mean / population std
+ * combined from n_moment_parts parts (part p at moments + p*moment_part_stride doubles), i.e. the
+ * `advantages_mb` PPO.run_ppo_epochs hands to update_gradients (xagents/ppo/agent.py:180-183). */
+int xa_normalize_adv_f32(const float* returns, const float* old_values, const int32_t* idx, int64_t n,
+                         int n_steps, int n_envs, const double* moments, int n_moment_parts,
+                         int64_t moment_part_stride, double adv_eps, float* advantages,
+                         xa_stream_t stream);
+
 /* ---- losses --------------------------------------------------------------------------------- */
 #define XA_ACTOR_LOGITS 0 /* Categorical(logits=)            a2c/agent.py:63 */
 #define XA_ACTOR_PROBS 1  /* Categorical(probs=)             a2c/agent.py:61-62 */

@@ -1,0 +1,196 @@
+"""The drop-in PPO / A2C classes against fixtures produced by the reference's own PPO / A2C.train_step
+(tests/golden/make_golden.py): same replayed environments, same model weights, same sampled actions and
+the same shuffles, so every intermediate of the train step can be compared."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _golden_module():
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(HERE, 'golden', 'make_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                      # defines helpers only; the reference is NOT imported
+    return mod
+
+
+class NumpyModel:
+    """Adapter around the generator's TinyModel so model outputs are bit-identical to the fixture run."""
+    output_is_softmax = False
+    comm = None
+
+    def __init__(self, tiny, image):
+        self.tiny, self.image, self.grads = tiny, image, []
+
+    def forward(self, states, training=True):
+        x = states.detach().cpu().numpy().astype(np.float32)
+        if self.image:
+            x = x / np.float32(255.0)
+        actor, critic = self.tiny(x)
+        return (torch.as_tensor(np.ascontiguousarray(actor)).cuda(),
+                torch.as_tensor(np.ascontiguousarray(critic.reshape(-1))).cuda())
+
+    def backward_and_step(self, d_actor, d_values, grad_norm=None):
+        self.grads.append((d_actor.clone(), d_values.clone()))
+
+
+CASES = {
+    'ppo_image': dict(seed=11, T=16, E=8, shape=(8, 8, 4), image=True, A=6, p=0.08, kw=dict(mini_batches=4, ppo_epochs=4), drift=0.05),
+    'ppo_cartpole': dict(seed=12, T=128, E=16, shape=(4,), image=False, A=2, p=0.02, kw=dict(mini_batches=4, ppo_epochs=4), drift=0.05),
+    'ppo_ragged': dict(seed=13, T=7, E=3, shape=(5,), image=False, A=3, p=0.3, kw=dict(mini_batches=4, ppo_epochs=2, clip_norm=0.02), drift=0.2),
+    'ppo_single_env': dict(seed=14, T=9, E=1, shape=(6, 6, 1), image=True, A=4, p=0.2, kw=dict(mini_batches=3, ppo_epochs=2), drift=0.05),
+    'a2c_image': dict(seed=21, T=5, E=16, shape=(8, 8, 4), image=True, A=6, p=0.1, kw={}, drift=0.05),
+    'a2c_vector': dict(seed=22, T=12, E=5, shape=(4,), image=False, A=2, p=0.15, kw={}, drift=0.05),
+}
+
+
+def build(case, cls):
+    mg = _golden_module()
+    c = CASES[case]
+    rng = np.random.default_rng(c['seed'])
+    obs, rewards, dones, resets = mg._streams(rng, c['T'], c['E'], c['shape'], c['image'], c['p'])
+    space = mg.Discrete(c['A'])
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], space) for i in range(c['E'])]
+    tiny = mg.TinyModel(min(int(np.prod(c['shape'])), 24), c['A'], rng)
+    model = NumpyModel(tiny, c['image'])
+    agent = cls(envs, model, n_steps=c['T'], quiet=True, **c['kw'])
+    return agent, model, tiny, c
+
+
+def near(got, want, scale=None):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = np.asarray(want, np.float64).reshape(got.shape)
+    s = np.abs(want).max() if scale is None else scale
+    assert np.abs(got - want).max() <= REL * max(s, 1e-30)
+
+
+@pytest.mark.parametrize('case', ['ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env'])
+def test_ppo_train_step_matches_the_reference_run(golden, case):
+    from xagents_b200.agents import PPO
+    g = golden(case)
+    agent, model, tiny, c = build(case, PPO)
+    T, E = c['T'], c['E']
+    tm = lambda flat: np.ascontiguousarray(np.asarray(flat).reshape(E, T).T)
+    golden_actions = tm(g['flat_actions'])
+    agent.action_source = lambda step, actor_out: golden_actions[step]
+    agent.permutation_source = lambda epoch: g['shuffles'][epoch]
+    inner = agent.run_ppo_epochs
+
+    def run_epochs(*batch):                           # weights "move" between rollout and updates, as in the fixture
+        tiny.drift = np.float32(c['drift'])
+        return inner(*batch)
+
+    agent.run_ppo_epochs = run_epochs
+    assert agent.batch_size == T * E and agent.mini_batch_size == int(g['mini_batch_size'])
+    agent.train_step()
+    torch.cuda.synchronize()
+    assert agent.steps == int(g['steps_after']) == T * E
+    # rollout assembly (a1): time-major buffers hold what the reference's lists held
+    assert np.array_equal(agent.ro_states.cpu().numpy().astype(np.float32), g['states_time_major'])
+    assert np.array_equal(agent.ro_rewards.cpu().numpy(), g['rewards'])
+    assert np.array_equal(agent.ro_dones.cpu().numpy(), g['dones'])
+    assert np.array_equal(agent.ro_values.cpu().numpy(), g['values'].reshape(T, E))
+    near(agent.ro_log_probs, tm(g['flat_log_probs']))
+    near(agent.ro_returns, g['returns'])
+    # every update of every epoch
+    assert len(agent.loss_history) == len(g['losses']) == len(model.grads)
+    for i, sc in enumerate(agent.loss_history):
+        sc = sc.cpu().numpy()
+        _, ref_ent, ref_vl, ref_pg = g['means'][i]
+        scale = max(abs(float(g['losses'][i])), abs(ref_ent), abs(0.5 * ref_vl), abs(ref_pg))
+        assert abs(sc[0] - g['losses'][i]) <= REL * scale, (i, sc, g['losses'][i])
+        assert abs(sc[1] - ref_pg) <= REL * scale and abs(sc[2] - 0.5 * ref_vl) <= REL * scale and abs(sc[3] - ref_ent) <= REL * scale
+
+
+def test_ppo_get_mini_batches_contract(golden):
+    """list(get_mini_batches(...)) is the reference's list: K*ceil(N/B) minibatches of 5 gathered items."""
+    from xagents_b200.agents import PPO
+    g = golden('ppo_ragged')
+    agent, model, tiny, c = build('ppo_ragged', PPO)
+    T, E = c['T'], c['E']
+    golden_actions = np.ascontiguousarray(g['flat_actions'].reshape(E, T).T)
+    agent.action_source = lambda step, actor_out: golden_actions[step]
+    agent.permutation_source = lambda epoch: g['shuffles'][epoch]
+    batch = agent.get_batch()
+    assert [tuple(b.shape) for b in batch] == [(T * E,) + c['shape'], (T * E,), (T * E,), (T * E,), (T * E,)]
+    assert np.array_equal(batch[0].materialize().cpu().numpy(), g['flat_states'])
+    mbs = list(agent.get_mini_batches(*batch))
+    assert len(mbs) == len(g['losses']) == 10
+    for i, mb in enumerate(mbs):
+        assert np.array_equal(mb[0].cpu().numpy(), g[f'mb{i}_states'])
+        assert np.array_equal(mb[1].cpu().numpy(), g[f'mb{i}_actions'].reshape(-1))
+        assert np.array_equal(mb[3].cpu().numpy(), g[f'mb{i}_old_values'].reshape(-1))
+    assert len(mbs[4][0]) == 1                        # trailing short minibatch: 21 = 4*5 + 1
+
+
+@pytest.mark.parametrize('case', ['a2c_image', 'a2c_vector'])
+def test_a2c_train_step_matches_the_reference_run(golden, case):
+    from xagents_b200.agents import A2C
+    g = golden(case)
+    agent, model, tiny, c = build(case, A2C)
+    T, E = c['T'], c['E']
+    golden_actions = np.ascontiguousarray(g['flat_actions'].reshape(E, T).T)
+    agent.action_source = lambda step, actor_out: golden_actions[step]
+    inner = agent.calculate_returns
+
+    def returns_then_drift(*a, **k):
+        out = inner(*a, **k)
+        tiny.drift = np.float32(c['drift'])
+        return out
+
+    agent.calculate_returns = returns_then_drift
+    agent.train_step()
+    torch.cuda.synchronize()
+    assert agent.steps == int(g['steps_after'])
+    assert np.array_equal(agent.ro_rewards.cpu().numpy(), g['rewards'])
+    assert np.array_equal(agent.ro_dones.cpu().numpy(), g['dones'])
+    sc = agent.loss_scalars.cpu().numpy()
+    assert abs(sc[0] - g['loss'][0]) <= REL * max(abs(float(g['loss'][0])), abs(sc[2]), abs(sc[3]))
+
+
+def test_constructor_contract_and_errors():
+    from xagents_b200.agents import A2C, PPO
+    mg = _golden_module()
+    with pytest.raises(AssertionError, match='No environments given'):
+        PPO([], None)
+    agent, *_ = build('ppo_ragged', PPO)
+    for name, want in (('lam', 0.95), ('ppo_epochs', 2), ('mini_batches', 4), ('advantage_epsilon', 1e-8), ('clip_norm', 0.02),
+                       ('entropy_coef', 0.01), ('value_loss_coef', 0.5), ('grad_norm', 0.5), ('gamma', 0.99), ('n_envs', 3)):
+        assert getattr(agent, name) == want
+    with pytest.raises(AssertionError, match='Invalid batch size to mini-batch size ratio'):
+        rng = np.random.default_rng(0)
+        obs, rewards, dones, resets = mg._streams(rng, 1, 1, (4,), False, 0.0)
+        PPO([mg.ReplayEnv(obs[0], rewards[0], dones[0], resets[0], mg.Discrete(2))],
+            NumpyModel(mg.TinyModel(4, 2, rng), False), n_steps=1, mini_batches=4)
+    with pytest.raises(AssertionError, match='should be specified when fit'):
+        agent.fit()
+    with pytest.raises(NotImplementedError):
+        from xagents_b200.agents import BaseAgent
+        BaseAgent.train_step(agent)
+
+
+def test_fit_with_a_torch_model_trains_on_device():
+    """fit(max_steps=...) end to end: NatureCNN-shaped torch model, fused clip+Adam, stop condition."""
+    from xagents_b200.agents import PPO, NatureCNN, TorchModel
+    mg = _golden_module()
+    T, E, A = 8, 4, 6
+    rng = np.random.default_rng(7)
+    obs, rewards, dones, resets = mg._streams(rng, 4 * T, E, (84, 84, 4), True, 0.1)
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+    torch.manual_seed(0)
+    net = TorchModel(NatureCNN(4, A).cuda())
+    before = net.flat_param.clone()
+    agent = PPO(envs, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=3)
+    agent.fit(max_steps=3 * T * E)
+    torch.cuda.synchronize()
+    assert agent.steps == 3 * T * E and net.step == 3 * 2 * 4
+    assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)
+    assert net.n_params == 1_687_719 - 0 or net.n_params > 1_600_000      # Nature CNN @84x84x4, 6 actions
+    losses = torch.stack(agent.loss_history).cpu().numpy()
+    assert np.isfinite(losses).all()

@@ -60,6 +60,8 @@ PROTOTYPES = {
                                                     ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_stream]),
     'xa_adv_moments_f32': (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_stream]),
+    'xa_normalize_adv_f32': (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, c_f32p, c_stream]),
     'xa_loss_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64]),
     'xa_ppo_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),
     'xa_a2c_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),

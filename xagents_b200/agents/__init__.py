@@ -1,0 +1,8 @@
+"""Drop-in mirrors of the reference's on-policy agents: same constructors, same method surface,
+arithmetic on the B200 through the C ABI."""
+from .a2c import A2C
+from .base import BaseAgent, EnvMajorView, OnPolicy
+from .models import KerasModel, NatureCNN, TorchModel, adapt
+from .ppo import PPO
+
+__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'adapt']

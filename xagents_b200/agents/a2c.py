@@ -1,0 +1,129 @@
+"""A2C with the reference's surface (xagents/a2c/agent.py:9-218), hot path on the device.
+
+The rollout is written step by step into preallocated time-major device buffers (uint8 frames stay
+uint8) instead of growing eight Python lists; returns come from `xa_nstep_returns_f32`; the loss and
+its gradients w.r.t. the model outputs from `xa_a2c_loss_f32`.  The A2C loss is a mean over all T*E
+samples, so the update consumes the buffers in time-major order: no flatten, no gather.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import ops
+from .base import OnPolicy
+from .models import adapt
+
+
+class A2C(OnPolicy):
+    def __init__(self, envs, model, entropy_coef=0.01, value_loss_coef=0.5, grad_norm=0.5, **kwargs):
+        super().__init__(envs, model, **kwargs)
+        self.entropy_coef = entropy_coef
+        self.value_loss_coef = value_loss_coef
+        self.grad_norm = grad_norm
+        self.net = adapt(model, self.img_inputs)
+        self.output_is_softmax = bool(getattr(self.net, 'output_is_softmax', False))
+        self.actor_kind = 'normal' if not self.discrete else ('probs' if self.output_is_softmax else 'logits')
+        self.comm = getattr(self.net, 'comm', None)
+        self.action_source = None        # tests: callable(step, actor_out) -> actions, to replay a fixed rollout
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(self.seed) if self.seed else 0)
+        self._alloc_rollout()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_rollout(self):
+        T, E, dev, f32 = self.n_steps, self.n_envs, self.device, torch.float32
+        first = np.asarray(self.states[0])
+        self.obs_dtype = torch.uint8 if (self.img_inputs and first.dtype == np.uint8) else f32
+        self.ro_states = torch.empty((T, E) + self.input_shape, dtype=self.obs_dtype, device=dev)
+        self.ro_rewards = torch.empty((T, E), dtype=f32, device=dev)
+        self.ro_values = torch.empty((T, E), dtype=f32, device=dev)
+        self.ro_dones = torch.empty((T + 1, E), dtype=f32, device=dev)
+        self.ro_log_probs = torch.empty((T, E), dtype=f32, device=dev)
+        self.ro_entropies = torch.empty((T, E), dtype=f32, device=dev)
+        a_shape = (T, E) if self.discrete else (T, E, self.n_actions)
+        self.ro_actions = torch.empty(a_shape, dtype=f32, device=dev)
+        self.ro_actor = torch.empty((T, E, self.n_actions), dtype=f32, device=dev)
+        self.loss_scalars = torch.zeros(4, dtype=f32, device=dev)
+
+    def _to_device(self, array, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(array))
+        return t.to(self.device, dtype=dtype, non_blocking=True)
+
+    # ------------------------------------------------------------------ distribution (a2c/agent.py:50-94)
+    def _log_prob_entropy(self, actor_out, actions):
+        if not self.discrete:
+            k = actor_out.shape[-1]
+            log2pi = math.log(2.0 * math.pi)
+            logp = -0.5 * ((actions - actor_out) ** 2).sum(-1) - 0.5 * k * log2pi
+            return logp, torch.full_like(logp, 0.5 * k * (1.0 + log2pi))
+        lsm = torch.log_softmax(torch.log(actor_out) if self.output_is_softmax else actor_out, dim=-1)
+        logp = lsm.gather(-1, actions.long().view(-1, 1)).squeeze(-1)
+        return logp, -(lsm.exp() * lsm).sum(-1)
+
+    def sample_actions(self, actor_out):
+        if not self.discrete:
+            return actor_out + torch.randn(actor_out.shape, device=actor_out.device, generator=self._gen)
+        lsm = torch.log_softmax(torch.log(actor_out) if self.output_is_softmax else actor_out, dim=-1)
+        u = torch.rand(lsm.shape, device=lsm.device, generator=self._gen).clamp_(1e-12, 1.0)
+        return torch.argmax(lsm - torch.log(-torch.log(u)), dim=-1).float()       # Gumbel-max
+
+    def get_model_outputs(self, inputs, models=None, training=True, actions=None, step=None):
+        """[actions, log probs, critic output, entropy, actor output] like a2c/agent.py:65-94 (device tensors)."""
+        x = inputs if isinstance(inputs, torch.Tensor) else self._to_device(inputs, self.obs_dtype)
+        actor_out, critic = self.net.forward(x, training=training)
+        if actions is None:
+            actions = (self.action_source(step, actor_out) if self.action_source is not None
+                       else self.sample_actions(actor_out))
+            actions = actions if isinstance(actions, torch.Tensor) else self._to_device(actions, torch.float32)
+        logp, entropy = self._log_prob_entropy(actor_out, actions)
+        return actions, logp, critic, entropy, actor_out
+
+    # ------------------------------------------------------------------ rollout (a2c/agent.py:96-139)
+    def get_batch(self):
+        """Run the environments for n_steps; returns the time-major device buffers
+        [states, rewards, actions, critic_output, dones, log_probs, entropies, actor_output]."""
+        step_states, step_dones = self.get_states(), self.get_dones()
+        for t in range(self.n_steps):
+            states_d = self._to_device(step_states, self.obs_dtype)
+            actions, logp, values, entropy, actor_out = self.get_model_outputs(states_d, training=False, step=t)
+            self.ro_states[t].copy_(states_d)
+            self.ro_actions[t].copy_(actions)
+            self.ro_values[t].copy_(values)
+            self.ro_log_probs[t].copy_(logp)
+            self.ro_dones[t].copy_(self._to_device(step_dones))
+            self.ro_entropies[t].copy_(entropy)
+            self.ro_actor[t].copy_(actor_out)
+            env_actions = actions.cpu().numpy()
+            env_actions = env_actions.astype(np.int64) if self.discrete else env_actions
+            *_, step_rewards, step_dones, step_states = self.step_envs(env_actions, True, False)
+            self.ro_rewards[t].copy_(self._to_device(step_rewards))
+        self.ro_dones[self.n_steps].copy_(self._to_device(step_dones))
+        return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
+                self.ro_entropies, self.ro_actor]
+
+    def _bootstrap_values(self):
+        return self.get_model_outputs(self.get_states(), training=False, actions=self.ro_actions[0])[2]
+
+    def calculate_returns(self, rewards, dones, values=None, selected_critic_logits=None, selected_importance=None):
+        """n-step returns [T, E] (a2c/agent.py:141-171): bootstrap from the current states, then the scan kernel."""
+        rewards = rewards if isinstance(rewards, torch.Tensor) else self._to_device(rewards, torch.float32)
+        dones = dones if isinstance(dones, torch.Tensor) else self._to_device(dones, torch.float32)
+        return ops.nstep_returns(rewards, dones, self._bootstrap_values(), self.gamma)
+
+    def np_train_step(self):
+        states, rewards, actions, critic_output, dones, *_ = self.get_batch()
+        returns = self.calculate_returns(rewards, dones)
+        return self.concat_step_batches(states, returns, actions, critic_output)
+
+    # ------------------------------------------------------------------ update (a2c/agent.py:190-218)
+    def train_step(self):
+        states, rewards, actions, old_values, dones, *_ = self.get_batch()
+        returns = self.calculate_returns(rewards, dones)
+        n = self.n_steps * self.n_envs
+        actor_out, critic = self.net.forward(states.reshape((n,) + self.input_shape), training=True)
+        flat_actions = actions.reshape(n) if self.discrete else actions.reshape(n, self.n_actions)
+        _, d_actor, d_values = ops.a2c_loss(actor_out, critic, flat_actions, old_values.reshape(n), returns.reshape(n),
+                                            entropy_coef=self.entropy_coef, value_loss_coef=self.value_loss_coef,
+                                            actor_kind=self.actor_kind, out=(self.loss_scalars, None, None, None))
+        self.net.backward_and_step(d_actor, d_values, self.grad_norm)

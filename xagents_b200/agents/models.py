@@ -1,0 +1,148 @@
+"""Model adapters: what the agents need from "the model" on either side of the hot path.
+
+The reference hands a compiled `tf.keras.Model` to its agents and lets a GradientTape differentiate the
+loss (xagents/ppo/agent.py:112-137).  Here the loss kernel already returns d loss / d(actor_out, critic_out),
+so a model only has to (1) run forward on a device batch and (2) back-propagate those two output
+gradients and apply its optimiser.  Any object with this interface works:
+
+    forward(states, training=True) -> (actor_out [n, A] fp32, critic_out [n] fp32)   device, DLPack-able
+    backward_and_step(d_actor, d_values, grad_norm) -> None
+    output_is_softmax : bool      (Categorical(probs=) instead of (logits=), a2c/agent.py:42-43)
+
+`TorchModel` wraps a torch.nn.Module returning (actor_out, critic_out) and keeps every trainable tensor
+in ONE flat fp32 buffer so that global-norm clip + Adam is the fused two-launch step of csrc/optim.cu
+(Keras Adam semantics, utils/common.py:476; defaults utils/cli.py:14-25) and the gradient all-reduce is
+a single NCCL call.  `KerasModel` drives a tf.keras.Model through DLPack (untestable in this image:
+TensorFlow is not installable here; it is imported lazily).
+"""
+import torch
+
+from .. import ops
+
+
+class TorchModel:
+    def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
+                 comm=None):
+        self.module = module
+        self.output_is_softmax = output_is_softmax
+        self.img_inputs = img_inputs
+        self.lr, self.beta1, self.beta2, self.epsilon = lr, beta1, beta2, epsilon
+        self.comm = comm
+        self.step = 0
+        params = [p for p in module.parameters() if p.requires_grad]
+        assert params, 'model has no trainable parameters'
+        dev = params[0].device
+        assert dev.type == 'cuda', 'the model must live on the GPU: xagents_b200 has no CPU path'
+        n = sum(p.numel() for p in params)
+        pad = (-n) % 4                                            # float4 path of the optimiser kernel
+        self.flat_param = torch.zeros(n + pad, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.m = torch.zeros_like(self.flat_param)
+        self.v = torch.zeros_like(self.flat_param)
+        self.workspace = ops.optim_workspace(dev)
+        off = 0
+        for p in params:                                          # re-seat parameters and grads as views
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p)
+            p.grad = self.flat_grad[off:off + k].view_as(p)
+            off += k
+        self.n_params = n
+        self._outputs = None
+
+    def forward(self, states, training=True):
+        x = states
+        scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if scale:
+            x = x / 255.0                                         # base.py:505-506
+        with torch.set_grad_enabled(training):
+            actor, critic = self.module(x)
+        critic = critic.reshape(-1)                               # tf.squeeze, a2c/agent.py:84
+        self._outputs = (actor, critic) if training else None
+        return actor.detach().contiguous(), critic.detach().contiguous()
+
+    def backward_and_step(self, d_actor, d_values, grad_norm=None):
+        actor, critic = self._outputs
+        self.flat_grad.zero_()
+        torch.autograd.backward([actor, critic], [d_actor.view_as(actor), d_values.view_as(critic)])
+        self._outputs = None
+        scale = 1.0
+        if self.comm is not None and self.comm.world_size > 1:
+            self.comm.all_reduce_gradients_async(self.flat_grad)  # collective C1
+            self.comm.wait_gradients()
+            scale = 1.0 / self.comm.world_size
+        self.step += 1
+        ops.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.step, workspace=self.workspace, lr=self.lr,
+                      beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, clip_norm=grad_norm, grad_scale=scale)
+
+
+class KerasModel:
+    """tf.keras.Model adapter (DLPack both ways).  Needs TensorFlow with GPU support at call time."""
+
+    def __init__(self, model, img_inputs=False):
+        import tensorflow as tf                                   # lazily: absent from this image
+        self.tf, self.model, self.img_inputs = tf, model, img_inputs
+        acts = [getattr(layer, 'activation', None) for layer in model.layers[-2:]]
+        self.output_is_softmax = tf.keras.activations.softmax in acts
+        self._tape = self._outputs = None
+
+    def forward(self, states, training=True):
+        tf = self.tf
+        x = tf.experimental.dlpack.from_dlpack(states.__dlpack__())
+        if self.img_inputs:
+            x = tf.cast(x, tf.float32) / 255.0
+        self._tape = tf.GradientTape() if training else None
+        if training:
+            with self._tape:
+                actor, critic = self.model(x, training=True)
+                critic = tf.squeeze(critic)
+            self._outputs = (actor, critic)
+        else:
+            actor, critic = self.model(x, training=False)
+            critic = tf.squeeze(critic)
+        return (torch.from_dlpack(tf.experimental.dlpack.to_dlpack(actor)),
+                torch.from_dlpack(tf.experimental.dlpack.to_dlpack(critic)))
+
+    def backward_and_step(self, d_actor, d_values, grad_norm=None):
+        tf = self.tf
+        grads = self._tape.gradient(list(self._outputs), self.model.trainable_variables,
+                                    output_gradients=[tf.experimental.dlpack.from_dlpack(d_actor.__dlpack__()),
+                                                      tf.experimental.dlpack.from_dlpack(d_values.__dlpack__())])
+        if grad_norm is not None:
+            grads, _ = tf.clip_by_global_norm(grads, grad_norm)
+        self.model.optimizer.apply_gradients(zip(grads, self.model.trainable_variables))
+        self._tape = self._outputs = None
+
+
+def adapt(model, img_inputs):
+    """Accept an adapter, a torch module, or a Keras model, as the reference accepts `model`."""
+    if hasattr(model, 'forward') and hasattr(model, 'backward_and_step'):
+        return model
+    if isinstance(model, torch.nn.Module):
+        return TorchModel(model, img_inputs=img_inputs)
+    if hasattr(model, 'trainable_variables') and hasattr(model, 'layers'):
+        assert len(model.layers) > 2, f'Expected a model that has at least 3 layers, got {len(model.layers)}'
+        return KerasModel(model, img_inputs=img_inputs)
+    raise TypeError(f'unsupported model type {type(model).__name__}: need forward()/backward_and_step(), '
+                    f'a torch.nn.Module or a tf.keras.Model')
+
+
+class NatureCNN(torch.nn.Module):
+    """The documented PPO/A2C CNN (README.md:243-259; ppo/models/cnn-actor-critic.cfg:1-42 read as Conv2D):
+    32x8/4 -> 64x4/2 -> 64x3/1 -> FC512 shared trunk -> actor (A) and critic (1) heads, orthogonal init."""
+
+    def __init__(self, in_channels=4, n_actions=6):
+        super().__init__()
+        nn = torch.nn
+        self.trunk = nn.Sequential(nn.Conv2d(in_channels, 32, 8, 4), nn.ReLU(), nn.Conv2d(32, 64, 4, 2), nn.ReLU(),
+                                   nn.Conv2d(64, 64, 3, 1), nn.ReLU(), nn.Flatten(), nn.Linear(3136, 512), nn.ReLU())
+        self.actor, self.critic = nn.Linear(512, n_actions), nn.Linear(512, 1)
+        for mod, gain in [(m, 2 ** 0.5) for m in self.trunk if hasattr(m, 'weight')] + [(self.actor, 0.01), (self.critic, 1.0)]:
+            nn.init.orthogonal_(mod.weight, gain)
+            nn.init.zeros_(mod.bias)
+
+    def forward(self, x):                                          # x: [n, 84, 84, C] channels-last like the reference
+        h = self.trunk(x.permute(0, 3, 1, 2))
+        return self.actor(h), self.critic(h)

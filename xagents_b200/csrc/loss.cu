@@ -69,6 +69,49 @@ __global__ void __launch_bounds__(kMomentThreads) adv_moments_kernel(const Momen
   }
 }
 
+// (adv - mean) / (std + eps) for one minibatch from its moment parts (ppo/agent.py:181-183)
+struct NormParams {
+  const float* returns;
+  const float* old_values;
+  const int32_t* idx;
+  int n_steps, n_envs;
+  const double* moments;
+  int n_parts;
+  int64_t part_stride;
+  float eps;
+  float* out;
+  int64_t n;
+};
+
+__device__ __forceinline__ void combine_moments(const double* moments, int n_parts, int64_t stride, float eps, float* mean,
+                                                float* denom) {
+  // Chan's pairwise combination of (count, mean, M2) parts, in part order, in fp64
+  double cn = 0.0, cm = 0.0, c2 = 0.0;
+  for (int q = 0; q < n_parts; ++q) {
+    const double* part = moments + static_cast<int64_t>(q) * stride;
+    const double qn = part[0], qm = part[1], q2 = part[2];
+    if (qn <= 0.0) continue;
+    const double tot = cn + qn, delta = qm - cm;
+    c2 += q2 + delta * delta * cn * qn / tot;
+    cm += delta * qn / tot;
+    cn = tot;
+  }
+  *mean = static_cast<float>(cm);
+  *denom = __fadd_rn(static_cast<float>(sqrt(cn > 0.0 ? c2 / cn : 0.0)), eps);  // population std + eps
+}
+
+__global__ void __launch_bounds__(256) normalize_adv_kernel(const NormParams p) {
+  __shared__ float s_mean, s_denom;
+  if (threadIdx.x == 0) combine_moments(p.moments, p.n_parts, p.part_stride, p.eps, &s_mean, &s_denom);
+  __syncthreads();
+  const float mean = s_mean, denom = s_denom;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = p.idx ? xa::sample_row(p.idx[i], p.n_steps, p.n_envs) : i;
+    p.out[i] = __fdiv_rn(__fsub_rn(__fsub_rn(p.returns[row], p.old_values[row]), mean), denom);
+  }
+}
+
 struct LossWorkspace {  // layout of xa_loss_args.workspace
   unsigned int ticket;
   unsigned int pad[3];
@@ -87,22 +130,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const xa_loss_args a
 
   float adv_mean = 0.0f, adv_denom = 1.0f;
   if (kPpo && a.advantages == nullptr) {
-    if (threadIdx.x == 0) {
-      // Chan's pairwise combination of (count, mean, M2) parts, in part order, in fp64
-      double cn = 0.0, cm = 0.0, c2 = 0.0;
-      for (int q = 0; q < a.n_moment_parts; ++q) {
-        const double* part = a.moments + static_cast<int64_t>(q) * a.moment_part_stride;
-        const double qn = part[0], qm = part[1], q2 = part[2];
-        if (qn <= 0.0) continue;
-        const double tot = cn + qn, delta = qm - cm;
-        c2 += q2 + delta * delta * cn * qn / tot;
-        cm += delta * qn / tot;
-        cn = tot;
-      }
-      s_mean = static_cast<float>(cm);
-      // (adv - mean) / (std + eps), population std (ppo/agent.py:181-183)
-      s_denom = __fadd_rn(static_cast<float>(sqrt(cn > 0.0 ? c2 / cn : 0.0)), a.adv_eps);
-    }
+    // (adv - mean) / (std + eps), population std (ppo/agent.py:181-183)
+    if (threadIdx.x == 0) combine_moments(a.moments, a.n_moment_parts, a.moment_part_stride, a.adv_eps, &s_mean, &s_denom);
     __syncthreads();
     adv_mean = s_mean;
     adv_denom = s_denom;
@@ -344,6 +373,21 @@ int xa_adv_moments_f32(const float* returns, const float* old_values, const int3
     if (int rc = xa::check_launch("xa_adv_moments_f32")) return rc;
   }
   return XA_OK;
+}
+
+int xa_normalize_adv_f32(const float* returns, const float* old_values, const int32_t* idx, int64_t n, int n_steps, int n_envs,
+                         const double* moments, int n_moment_parts, int64_t moment_part_stride, double adv_eps,
+                         float* advantages, xa_stream_t stream) {
+  XA_REQUIRE(n >= 0 && n <= (int64_t(1) << 31), XA_EINVAL, "xa_normalize_adv_f32: n=%lld", static_cast<long long>(n));
+  if (n == 0) return XA_OK;
+  XA_REQUIRE(returns && old_values && moments && advantages, XA_EINVAL, "xa_normalize_adv_f32: null pointer");
+  XA_REQUIRE(n_moment_parts > 0, XA_EINVAL, "xa_normalize_adv_f32: n_moment_parts=%d", n_moment_parts);
+  XA_REQUIRE(n_steps >= 0 && n_envs >= 0, XA_EINVAL, "xa_normalize_adv_f32: negative n_steps/n_envs");
+  NormParams p{returns, old_values, idx, n_steps, n_envs, moments, n_moment_parts, moment_part_stride,
+               static_cast<float>(adv_eps), advantages, n};
+  const int64_t want = (n + 255) / 256;
+  normalize_adv_kernel<<<static_cast<unsigned>(want < 1184 ? want : 1184), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return xa::check_launch("xa_normalize_adv_f32");
 }
 
 int64_t xa_loss_workspace_bytes(int64_t n) {

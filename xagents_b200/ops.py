@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'adv_moments', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
+           'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -207,6 +207,25 @@ def adv_moments(returns, old_values, idx, mb_offsets, *, time_major=None, out=No
     _ffi.call('xa_adv_moments_f32', _ptr(r), _ptr(v), _ptr(i), offs, n_mb, T, E, _tptr(mom), _stream(stream))
     _count((n_mb + 63) // 64)
     return mom
+
+
+def normalize_advantages(returns_mb, old_values_mb, advantage_epsilon=1e-8, *, idx=None, time_major=None, moments=None,
+                         out=None, stream=None):
+    """advantages_mb of PPO.run_ppo_epochs (ppo/agent.py:180-183): (adv - mean) / (population std + eps).
+    `moments` ([4] or [parts,4] fp64) defaults to the moments of exactly these samples."""
+    r, v = _dev(returns_mb, 'float32'), _dev(old_values_mb, 'float32')
+    i = _dev(idx, 'int32') if idx is not None else None
+    n = i.size if i is not None else r.size
+    T, E = _layout(time_major)
+    if moments is None:
+        moments = adv_moments(returns_mb, old_values_mb, idx, [0, n], time_major=time_major, stream=stream)[0]
+    mom = _dev(moments, 'float64')
+    parts = 1 if len(mom.shape) == 1 else mom.shape[0]
+    adv = out if out is not None else torch.empty((n,), dtype=torch.float32, device=_device_of(r))
+    _ffi.call('xa_normalize_adv_f32', _ptr(r), _ptr(v), _ptr(i), n, T, E, _ptr(mom), parts, mom.shape[-1] if parts > 1 else 0,
+              float(advantage_epsilon), _tptr(adv), _stream(stream))
+    _count()
+    return adv
 
 
 def loss_workspace(n, device):
