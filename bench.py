@@ -306,7 +306,7 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'gather_traffic.json')) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+            traffic = json.load(f)['dram_bytes_per_row'] * (sum(hp.group_rows) / len(hp.group_rows))   # ncu, per row moved
     except Exception:
         pass
     step_gbs = alg['total'] / (ms_per_step * 1e-3) / 1e9     # this rank's shard; ranks are symmetric

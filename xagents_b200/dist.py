@@ -129,3 +129,16 @@ def init_from_env(backend=None):
             kw['device_id'] = torch.device('cuda', local_rank)
         dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
+
+
+def combine_moments(parts):
+    """Host mirror of the kernels' Chan combination: parts [G, 4] = (count, mean, M2, _) -> (count, mean, std)."""
+    cn = cm = c2 = 0.0
+    for qn, qm, q2, *_ in (tuple(float(x) for x in p) for p in parts):
+        if qn <= 0.0:
+            continue
+        tot, delta = cn + qn, qm - cm
+        c2 += q2 + delta * delta * cn * qn / tot
+        cm += delta * qn / tot
+        cn = tot
+    return cn, cm, (c2 / cn) ** 0.5 if cn > 0 else 0.0
