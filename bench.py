@@ -316,7 +316,7 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars', 'data': 'synthetic',
         'config': {'workload': desc, 'n_envs_per_gpu': E, 'samples_per_step_per_gpu': N, 'mini_batch_size_per_gpu': B,
                    'gather_mode': args.gather_mode, 'scan_mode': args.scan_mode,
-                   'minibatches_per_gather_launch': hp.chunk,
+                   'minibatches_per_gather_launch': hp.group_sizes,
                    'streams': 'gathers on a data stream, GAE/moments/losses on the compute stream' if hp.overlap else 'single stream',
                    'scalar_fields': 'read through the permutation inside the loss' if hp.fuse_fields else 'gathered per minibatch',
                    'l2': f'inputs larger than L2: {hp.obs.numel() / 1e6:.0f} MB of frames per GPU read once per epoch',

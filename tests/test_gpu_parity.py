@@ -421,7 +421,8 @@ def test_clip_adam_vs_oracle(n, clip):
 
 # ---------------------------------------------------------------------------------------------- PPOHotPath
 @pytest.mark.parametrize('fuse,chunk,overlap,staging', [(True, None, True, 2), (False, None, True, 2), (True, 1, True, 2),
-                                                        (False, 1, False, 1), (False, 8, True, 1), (True, 3, True, 2)])
+                                                        (False, 1, False, 1), (False, 8, True, 1), (True, 3, True, 2),
+                                                        (False, [3, 1, 2, 2], True, 2)])
 @pytest.mark.parametrize('T,E,mb', [(16, 8, 4), (7, 3, 4)])
 def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
     """The prepared two-stream pipeline (what bench.py times) against the oracle's PPO.train_step,

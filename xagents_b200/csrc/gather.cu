@@ -10,11 +10,13 @@
 //
 //  * BULK  -- rows are moved by the TMA engine as non-tensor bulk copies: global -> shared
 //             (cp.async.bulk ... mbarrier::complete_tx) then shared -> global (cp.async.bulk ... bulk_group).
-//             One elected lane per warp drives one stage of a shared-memory ring, so a CTA keeps `stages`
-//             whole rows (28 224 B for 84x84x4 frames) in flight with ~10 instructions per row and no
-//             register staging.  One more warp gathers the fp32 scalar fields for the CTA's slice.
+//             One elected lane per warp drives one stage of a shared-memory ring (4 stages of half a
+//             28 224-B frame: ~56 KB in flight per SM, the measured optimum), ~10 instructions per
+//             chunk and no register staging.  One more warp gathers the fp32 scalar fields.
 //  * VECTOR -- 128-bit LDG/STG (narrower when alignment forces it), 8 independent loads per thread before
 //             the stores; the general path for short or unaligned rows.
+#include <cstdlib>
+
 #include "xa_common.cuh"
 
 namespace {
@@ -33,6 +35,7 @@ struct GatherParams {
   int chunks_per_row;
   uint32_t chunk_bytes;
   int stages;
+  int load_hint, store_hint;  // L2 evict-first policy on the bulk loads / stores
   // scalar fields riding along
   int n_fields;
   const float* fsrc[XA_MAX_FIELDS];
@@ -66,12 +69,18 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
       const uint32_t bytes = left < static_cast<int64_t>(p.chunk_bytes) ? static_cast<uint32_t>(left) : p.chunk_bytes;
       const int64_t row = xa::sample_row(b, p.n_steps, p.n_envs);
       xa::mbar_expect_tx(bar, bytes);
-      xa::bulk_g2s(buf, p.src + row * p.row_bytes + off, bytes, bar, policy);
+      if (p.load_hint)
+        xa::bulk_g2s(buf, p.src + row * p.row_bytes + off, bytes, bar, policy);
+      else
+        xa::bulk_g2s_nohint(buf, p.src + row * p.row_bytes + off, bytes, bar);
       const int64_t kn = k + stride;
       if (kn < n_items) b = p.idx[kn / p.chunks_per_row];  // next index travels under the copy
       xa::mbar_wait(bar, parity);
       parity ^= 1u;
-      xa::bulk_s2g(p.dst + i * p.row_bytes + off, buf, bytes);
+      if (p.store_hint)
+        xa::bulk_s2g_hint(p.dst + i * p.row_bytes + off, buf, bytes, policy);
+      else
+        xa::bulk_s2g(p.dst + i * p.row_bytes + off, buf, bytes);
       xa::bulk_commit();
       xa::bulk_wait_read<0>();  // the engine has read the stage out: it may be refilled
     }
@@ -227,17 +236,29 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
                static_cast<long long>(p.row_bytes));
   const bool use_bulk = mode == XA_GATHER_BULK || (mode == XA_GATHER_AUTO && can_bulk && p.row_bytes >= 2048);
   if (use_bulk) {
-    // cut rows into equal 16-B-multiple chunks of at most 56 KB so that at least 4 stages fit
-    constexpr int64_t kMaxChunk = 56 * 1024;
-    p.chunks_per_row = static_cast<int>((p.row_bytes + kMaxChunk - 1) / kMaxChunk);
+    // Bytes in flight per SM decide the rate, and more is NOT better: measured on B200 (scripts/
+    // gather_microbench2.py, 32768 rows of 28224 B, random permutation) ~55 KB per SM peaks at 6.45 TB/s
+    // (98 % of a plain copy) while 110-226 KB per SM falls to 5.9-6.0 TB/s.  So rows are cut into equal
+    // 16-B-multiple chunks of <= 16 KB and the ring holds ~56 KB: 4 stages of half a frame for 84x84x4.
+    // (XA_GATHER_* environment variables are tuning knobs for the microbenchmarks.)
+    int64_t max_chunk = 16 * 1024;
+    int64_t target_inflight = 56 * 1024;
+    if (const char* e = getenv("XA_GATHER_CHUNK")) max_chunk = atoll(e) > 0 ? atoll(e) : max_chunk;
+    if (const char* e = getenv("XA_GATHER_INFLIGHT")) target_inflight = atoll(e) > 0 ? atoll(e) : target_inflight;
+    p.chunks_per_row = static_cast<int>((p.row_bytes + max_chunk - 1) / max_chunk);
     int64_t chunk = (p.row_bytes + p.chunks_per_row - 1) / p.chunks_per_row;
     chunk = (chunk + 15) & ~int64_t(15);
     p.chunk_bytes = static_cast<uint32_t>(chunk);
-    int stages = static_cast<int>((kSmemBudget - 8 * kMaxStages) / chunk);
+    int stages = static_cast<int>((target_inflight + chunk / 2) / chunk);
+    if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
-    // short rows: prefer two CTAs per SM of 8 stages over one of 16
-    if (stages > 8) stages = 8;
+    while (stages > 1 && static_cast<int64_t>(stages) * chunk + 8 * kMaxStages > kSmemBudget) --stages;
+    if (const char* e = getenv("XA_GATHER_STAGES")) stages = atoi(e) > 0 && atoi(e) <= kMaxStages ? atoi(e) : stages;
     p.stages = stages;
+    p.load_hint = 1;   // evict-first on both sides (hinting only the loads measured 2 % slower than both or neither)
+    p.store_hint = 1;
+    if (const char* e = getenv("XA_GATHER_LOAD_HINT")) p.load_hint = atoi(e);
+    if (const char* e = getenv("XA_GATHER_STORE_HINT")) p.store_hint = atoi(e);
     const size_t smem = static_cast<size_t>(stages) * chunk + 8 * kMaxStages;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -252,7 +273,9 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
     const int ctas_per_sm = static_cast<int>(kSmemBudget / (smem + 1024)) > 0 ? static_cast<int>(kSmemBudget / (smem + 1024)) : 1;
     const int64_t items = p.n_idx * p.chunks_per_row;
     int64_t grid = (items + stages - 1) / stages;
-    const int64_t cap = static_cast<int64_t>(sms) * (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+    int cta_cap = 1;
+    if (const char* e = getenv("XA_GATHER_CTAS")) cta_cap = atoi(e) > 0 && atoi(e) <= ctas_per_sm ? atoi(e) : cta_cap;
+    const int64_t cap = static_cast<int64_t>(sms) * cta_cap;
     if (grid > cap) grid = cap;
     gather_bulk_kernel<<<static_cast<unsigned>(grid), 32 * (stages + 1), smem, stream>>>(p);
     return xa::check_launch(what);

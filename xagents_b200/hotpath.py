@@ -63,14 +63,26 @@ class PPOHotPath:
         self.gather_mode, self.scan_mode = gather_mode, scan_mode
         self.comm = comm
         self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
-        # minibatches moved per gather launch: 1 = per minibatch, M (default) = one epoch, K*M = the whole
-        # step (what get_mini_batches does: every minibatch materialised before the first update)
+        # minibatches moved per gather launch.  An int = fixed group size (1 = per minibatch, K*M = the whole
+        # step, which is what get_mini_batches does: everything materialised before the first update); a list
+        # = explicit schedule.  Default: one launch per epoch (few, long, HBM-saturating launches) except the
+        # last epoch, which goes minibatch by minibatch so that only ONE loss trails the last gather.
         per_epoch = len(self.slices)
-        self.chunk = max(1, min(int(gather_chunk) if gather_chunk else per_epoch, self.n_mb))
-        self.n_groups = -(-self.n_mb // self.chunk)
+        if gather_chunk is None:
+            sizes = [per_epoch] * (self.K - 1) + [1] * per_epoch
+        elif isinstance(gather_chunk, (list, tuple)):
+            sizes = [int(x) for x in gather_chunk]
+            assert sum(sizes) == self.n_mb and min(sizes) > 0, f'gather schedule {sizes} must cover {self.n_mb} minibatches'
+        else:
+            c = max(1, min(int(gather_chunk), self.n_mb))
+            sizes = [c] * (self.n_mb // c) + ([self.n_mb % c] if self.n_mb % c else [])
+        self.group_sizes = sizes
+        self.group_first = [sum(sizes[:g]) for g in range(len(sizes))]
+        self.chunk = max(sizes)
+        self.n_groups = len(sizes)
         self.staging = min(self.staging, self.n_groups)
         mb_rows = [hi - lo for _ in range(self.K) for lo, hi in self.slices]
-        self.group_rows = [sum(mb_rows[g * self.chunk:(g + 1) * self.chunk]) for g in range(self.n_groups)]
+        self.group_rows = [sum(mb_rows[f:f + n]) for f, n in zip(self.group_first, sizes)]
         self.mb_rows = mb_rows
         self.cap = max(self.group_rows)
         dev, f32 = self.device, torch.float32
@@ -150,14 +162,14 @@ class PPOHotPath:
         flat_off = list(self._offsets)                       # start of every minibatch in perms.view(-1)
         self._mb_place = []                                  # minibatch -> (group, slot, first row in the slot)
         for g in range(self.n_groups):
-            first, slot = g * self.chunk, g % self.staging
+            first, slot = self.group_first[g], g % self.staging
             idx_addr = self.perms.data_ptr() + 4 * flat_off[first]
             obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * self.cap * self.row_bytes)
             self._gathers.append((lib.xa_gather_minibatch,
                                   (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
                                    n_fields, ctypes.c_void_p(idx_addr), self.group_rows[g], T, E,
                                    GATHER_MODES[self.gather_mode], sd)))
-            for mb in range(first, min(first + self.chunk, self.n_mb)):
+            for mb in range(first, first + self.group_sizes[g]):
                 self._mb_place.append((g, slot, flat_off[mb] - flat_off[first]))
         for mb in range(self.n_mb):
             g, slot, row0 = self._mb_place[mb]
@@ -229,7 +241,7 @@ class PPOHotPath:
             if two:
                 self._gather_done[g].record(ds)
                 cs.wait_event(self._gather_done[g])
-            for i in range(g * self.chunk, min((g + 1) * self.chunk, self.n_mb)):
+            for i in range(self.group_first[g], self.group_first[g] + self.group_sizes[g]):
                 fn, args = self._losses[i]
                 self._check('loss', fn(*args))
                 if after_loss is not None:
