@@ -422,7 +422,7 @@ def test_clip_adam_vs_oracle(n, clip):
 # ---------------------------------------------------------------------------------------------- PPOHotPath
 @pytest.mark.parametrize('fuse,chunk,overlap,staging', [(True, None, True, 2), (False, None, True, 2), (True, 1, True, 2),
                                                         (False, 1, False, 1), (False, 8, True, 1), (True, 3, True, 2),
-                                                        (False, [3, 1, 2, 2], True, 2)])
+                                                        (False, 'schedule', True, 2)])
 @pytest.mark.parametrize('T,E,mb', [(16, 8, 4), (7, 3, 4)])
 def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
     """The prepared two-stream pipeline (what bench.py times) against the oracle's PPO.train_step,
@@ -432,6 +432,9 @@ def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
     ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=K, p_done=0.05, seed=T + E)
     want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
                                  ro.permutations, ro.new_logits, ro.new_values, mini_batches=mb, keep_states=True)
+    if chunk == 'schedule':                                           # uneven explicit launch schedule
+        n_mb = K * -(-(T * E) // ((T * E) // mb))
+        chunk = [3, 1, 2] + [n_mb - 6]
     hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=mb, device=DEV, fuse_fields=fuse,
                     gather_chunk=chunk, overlap=overlap, staging=staging, scan_mode='sequential')
     hp.load(ro)

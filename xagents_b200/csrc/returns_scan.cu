@@ -7,7 +7,8 @@
 // done flag cuts the carry exactly like a segment head.  Layout is time-major
 // [T, E]: lanes run along E (every load/store is a coalesced 128-B line), warps run along T.
 // Warp w of a block owns a chunk of kChunk consecutive steps for 32 envs; it loads the chunk once into
-// registers (3*kChunk+1 independent loads in flight per thread), reduces it to the affine map (C, B),
+// registers (3*kChunk+1 independent loads per thread, issued one whole span AHEAD of their use so the
+// latency hides behind the current span's arithmetic and barriers), reduces it to the affine map (C, B),
 // exchanges maps through shared memory, derives its carry-in from the later chunks and then replays its
 // chunk from registers.  Inputs are read once and outputs written once: 16 B per env-step for GAE,
 // 12 B for n-step returns.  With one warp per block (XA_SCAN_SEQUENTIAL) no map is ever composed and the
@@ -33,6 +34,36 @@ struct ScanParams {
   float gamma_lam;  // fp32(double(gamma) * double(lam)), folded as the reference folds it
 };
 
+// One chunk of raw rollout values, exactly as loaded (kept apart from the derived maps so that the NEXT
+// chunk's loads can be in flight while the current chunk is reduced, exchanged and replayed).
+template <bool kNstep>
+struct RawChunk {
+  float rew[kChunk];
+  float done[kChunk];
+  float val[kNstep ? 1 : kChunk];
+  float v_next;
+};
+
+// Loads are unconditional: rows past the chunk end are clamped to its last valid row (the value is loaded
+// and ignored), so there is no divergence and all 3*kChunk+1 requests leave back to back.
+template <bool kNstep>
+__device__ __forceinline__ void load_chunk(RawChunk<kNstep>& q, const ScanParams& p, int t0, int len, int env) {
+  const int T = p.n_steps;
+  const size_t E = static_cast<size_t>(p.n_envs);
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j) {
+    const int t = t0 + (j < len ? j : len - 1);
+    const size_t o = static_cast<size_t>(t) * E + env;
+    q.rew[j] = p.rewards[o];
+    q.done[j] = p.dones[o + E];  // row t+1 gates step t (a2c/agent.py:116,129,138)
+    if (!kNstep) q.val[j] = p.values[o];
+  }
+  if (!kNstep) {
+    const int t1 = t0 + len;
+    q.v_next = (t1 == T) ? p.last_values[env] : p.values[static_cast<size_t>(t1) * E + env];
+  }
+}
+
 template <bool kNstep, bool kMulti>
 __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const ScanParams p) {
   __shared__ float s_c[kMulti ? kMaxWarps : 1][32];
@@ -42,51 +73,51 @@ __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const Scan
   const int lane = threadIdx.x;
   const int w = threadIdx.y;
   const int n_warps = blockDim.y;
-  const int env = blockIdx.x * 32 + lane;
-  const bool active = env < p.n_envs;
+  const int env_raw = blockIdx.x * 32 + lane;
+  const bool active = env_raw < p.n_envs;
+  const int env = active ? env_raw : p.n_envs - 1;  // inactive lanes shadow the last env and never store
   const int T = p.n_steps;
   const size_t E = static_cast<size_t>(p.n_envs);
   const float gamma = p.gamma;
   const float gl = p.gamma_lam;
+  const int span = n_warps * kChunk;
 
   // value flowing in from the future: R_T for n-step returns (a2c/agent.py:165-166), 0 for GAE (ppo/agent.py:81)
-  float carry = (kNstep && active) ? p.last_values[env] : 0.0f;
+  float carry = kNstep ? p.last_values[env] : 0.0f;
 
-  for (int hi = T; hi > 0; hi -= n_warps * kChunk) {
-    const int t1 = hi - (n_warps - 1 - w) * kChunk;  // exclusive end of this warp's chunk
-    const int t0 = max(t1 - kChunk, 0);
+  // chunk of this warp inside the span ending at `hi` (exclusive): [t0, t0+len)
+  auto chunk_of = [&](int hi, int& t0, int& len) {
+    const int t1 = hi - (n_warps - 1 - w) * kChunk;
+    t0 = t1 - kChunk > 0 ? t1 - kChunk : 0;
+    len = t1 > t0 ? t1 - t0 : 0;
+  };
+
+  RawChunk<kNstep> nxt;
+  int t0, len;
+  chunk_of(T, t0, len);
+  if (len > 0) load_chunk<kNstep>(nxt, p, t0, len, env);
+
+  for (int hi = T; hi > 0; hi -= span) {
+    const RawChunk<kNstep> cur = nxt;
+    const int c_t0 = t0, c_len = len;
+    if (hi - span > 0) {  // put the next span's loads in flight before touching this one
+      chunk_of(hi - span, t0, len);
+      if (len > 0) load_chunk<kNstep>(nxt, p, t0, len, env);
+    }
 
     float coef[kChunk];  // GAE: gamma*lam*alive ; n-step: alive
     float bias[kChunk];  // GAE: delta          ; n-step: reward
-    float val[kChunk];   // GAE: V_t (needed again for returns = A + V)
-    if (active && t1 > 0) {
-      float rew[kChunk], done[kChunk];
-      float v_next = 0.0f;
-      if (!kNstep) v_next = (t1 == T) ? p.last_values[env] : p.values[static_cast<size_t>(t1) * E + env];
 #pragma unroll
-      for (int j = 0; j < kChunk; ++j) {
-        const int t = t0 + j;
-        if (t < t1) {
-          const size_t o = static_cast<size_t>(t) * E + env;
-          rew[j] = p.rewards[o];
-          done[j] = p.dones[o + E];  // row t+1 gates step t (a2c/agent.py:116,129,138)
-          if (!kNstep) val[j] = p.values[o];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kChunk; ++j) {
-        if (t0 + j < t1) {
-          const float alive = __fsub_rn(1.0f, done[j]);  // ppo/agent.py:85
-          if (kNstep) {
-            coef[j] = alive;
-            bias[j] = rew[j];
-          } else {
-            const float vn = (j + 1 < kChunk && t0 + j + 1 < t1) ? val[j + 1] : v_next;
-            // delta = r + gamma*V_{t+1}*alive - V_t, evaluated left to right (ppo/agent.py:87-91)
-            bias[j] = __fsub_rn(__fadd_rn(rew[j], __fmul_rn(__fmul_rn(gamma, vn), alive)), val[j]);
-            coef[j] = __fmul_rn(gl, alive);  // ppo/agent.py:92
-          }
-        }
+    for (int j = 0; j < kChunk; ++j) {
+      const float alive = __fsub_rn(1.0f, cur.done[j]);  // ppo/agent.py:85
+      if (kNstep) {
+        coef[j] = alive;
+        bias[j] = cur.rew[j];
+      } else {
+        const float vn = (j + 1 < kChunk && j + 1 < c_len) ? cur.val[j + 1 < kChunk ? j + 1 : j] : cur.v_next;
+        // delta = r + gamma*V_{t+1}*alive - V_t, evaluated left to right (ppo/agent.py:87-91)
+        bias[j] = __fsub_rn(__fadd_rn(cur.rew[j], __fmul_rn(__fmul_rn(gamma, vn), alive)), cur.val[j]);
+        coef[j] = __fmul_rn(gl, alive);  // ppo/agent.py:92
       }
     }
 
@@ -94,14 +125,12 @@ __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const Scan
     if (kMulti) {
       // reduce the chunk to x -> B + C*x and publish it
       float cc = 1.0f, bb = 0.0f;
-      if (active && t1 > 0) {
 #pragma unroll
-        for (int j = kChunk - 1; j >= 0; --j) {
-          if (t0 + j < t1) {
-            const float c = kNstep ? __fmul_rn(gamma, coef[j]) : coef[j];
-            bb = __fadd_rn(bias[j], __fmul_rn(c, bb));
-            cc = __fmul_rn(cc, c);
-          }
+      for (int j = kChunk - 1; j >= 0; --j) {
+        if (j < c_len) {
+          const float c = kNstep ? __fmul_rn(gamma, coef[j]) : coef[j];
+          bb = __fadd_rn(bias[j], __fmul_rn(c, bb));
+          cc = __fmul_rn(cc, c);
         }
       }
       s_c[w][lane] = cc;
@@ -110,20 +139,19 @@ __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const Scan
       for (int w2 = n_warps - 1; w2 > w; --w2) x = __fadd_rn(s_b[w2][lane], __fmul_rn(s_c[w2][lane], x));
     }
 
-    if (active && t1 > 0) {
 #pragma unroll
-      for (int j = kChunk - 1; j >= 0; --j) {
-        const int t = t0 + j;
-        if (t < t1) {
-          const size_t o = static_cast<size_t>(t) * E + env;
-          if (kNstep) {
-            // R_t = r_t + gamma*R_{t+1}*(1-d_{t+1})   (a2c/agent.py:168-170)
-            x = __fadd_rn(bias[j], __fmul_rn(__fmul_rn(gamma, x), coef[j]));
-            p.returns[o] = x;
-          } else {
-            // last_lam = delta + gamma*lam*alive*last_lam ; returns = last_lam + V   (ppo/agent.py:92-94)
-            x = __fadd_rn(bias[j], __fmul_rn(coef[j], x));
-            p.returns[o] = __fadd_rn(x, val[j]);
+    for (int j = kChunk - 1; j >= 0; --j) {
+      if (j < c_len) {
+        const size_t o = static_cast<size_t>(c_t0 + j) * E + env;
+        if (kNstep) {
+          // R_t = r_t + gamma*R_{t+1}*(1-d_{t+1})   (a2c/agent.py:168-170)
+          x = __fadd_rn(bias[j], __fmul_rn(__fmul_rn(gamma, x), coef[j]));
+          if (active) p.returns[o] = x;
+        } else {
+          // last_lam = delta + gamma*lam*alive*last_lam ; returns = last_lam + V   (ppo/agent.py:92-94)
+          x = __fadd_rn(bias[j], __fmul_rn(coef[j], x));
+          if (active) {
+            p.returns[o] = __fadd_rn(x, cur.val[j]);
             if (p.advantages != nullptr) p.advantages[o] = x;
           }
         }
@@ -145,9 +173,10 @@ int pick_warps(int mode, int n_steps, int n_envs) {
   if (mode == XA_SCAN_SEQUENTIAL || chunks <= 1) return 1;
   const int max_w = chunks < kMaxWarps ? chunks : kMaxWarps;
   if (mode == XA_SCAN_CHUNKED) return max_w > 1 ? max_w : 2;
-  // AUTO: aim for >= 32 resident warps per SM so the load latency of a chunk hides behind other warps
+  // AUTO: with the next span prefetched, ~12 resident warps per SM already saturate HBM (measured: one
+  // warp per block is the fastest once there are >= 12 blocks per SM); split T across warps only below that
   const long blocks = (n_envs + 31) / 32;
-  const long want = 32L * (xa::sm_count() > 0 ? xa::sm_count() : 148);
+  const long want = 12L * (xa::sm_count() > 0 ? xa::sm_count() : 148);
   long wps = (want + blocks - 1) / blocks;
   if (wps < 1) wps = 1;
   if (wps > max_w) wps = max_w;
