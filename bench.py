@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--materialize-fields', action='store_true', help='gather the 4 scalar fields instead of reading them through idx')
     ap.add_argument('--staging', type=int, default=2)
     ap.add_argument('--gather-chunk', type=int, default=None, help='minibatches per gather launch (default: one epoch)')
+    ap.add_argument('--no-grad-allreduce', action='store_true', help='diagnostic: drop collective C1 (gradient all-reduce per minibatch)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-envs', type=int, default=64)
@@ -205,7 +206,8 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     hp.prepare(stream)
     n_gathers = hp.n_groups
-    after_loss = (lambda i: comm.all_reduce_gradients_async(grad_buf)) if comm is not None else None
+    with_c1 = comm is not None and not args.no_grad_allreduce
+    after_loss = (lambda i: comm.all_reduce_gradients_async(grad_buf)) if with_c1 else None
 
     def step(on_gather=None):
         hp.run(on_gather=on_gather, after_loss=after_loss)

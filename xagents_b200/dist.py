@@ -67,7 +67,11 @@ class ShardComm:
         self.world_size = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
         self.device = device
-        self.comm_stream = torch.cuda.Stream(device) if (device is not None and torch.device(device).type == 'cuda') else None
+        # High priority: measured on 8xB200, four 6.75 MB all-reduces issued under a 574 us gather cost 310 us
+        # of exposed time on a normal-priority stream (the NCCL CTAs queue behind the gather's) and 103 us
+        # on a high-priority one.
+        self.comm_stream = (torch.cuda.Stream(device, priority=-1)
+                            if (device is not None and torch.device(device).type == 'cuda') else None)
         self._pending = None
 
     # C2 ------------------------------------------------------------------------------------------
@@ -123,6 +127,10 @@ def init_from_env(backend=None):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29500')
         backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+        # The path's collectives are latency-bound (6.75 MB gradients, a few hundred bytes of moments): on
+        # 8xB200 the ring/tree kernels measured faster than NVLS here (60 vs 66 us alone, and they overlap
+        # the gathers better).  Respect an explicit user setting.
+        os.environ.setdefault('NCCL_NVLS_ENABLE', '0')
         kw = {}
         if backend == 'nccl':
             torch.cuda.set_device(local_rank)
