@@ -155,6 +155,16 @@ int xa_ppo_loss_f32(const xa_loss_args* args, xa_stream_t stream);
 /* A2C.train_step loss, xagents/a2c/agent.py:202-215 (advantages = returns - old_values, raw). */
 int xa_a2c_loss_f32(const xa_loss_args* args, xa_stream_t stream);
 
+/* ---- rollout-time policy step (row "next": the step before the path) --------------------------- */
+/* distribution.sample() / log_prob() / entropy() of A2C.get_model_outputs, xagents/a2c/agent.py:80-94,
+ * for one environment step of n envs.  Categorical: Gumbel-max over the log-softmax; `noise` [n, A] holds
+ * uniforms in (0,1) (standard normal draws for XA_ACTOR_NORMAL), or NULL to generate them in-kernel with
+ * Philox4x32-10 keyed by (seed, offset) -- advance `offset` by at least (A+3)/4 (2A... for NORMAL) per call.
+ * actions: [n] fp32-encoded ids, or [n, A] for XA_ACTOR_NORMAL; entropies may be NULL. */
+int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* noise, uint64_t seed,
+                       uint64_t offset, float* actions, float* log_probs, float* entropies, int64_t n,
+                       int n_actions, xa_stream_t stream);
+
 /* ---- optimiser step (row "next": the step right after the path) ------------------------------ */
 /* tf.clip_by_global_norm + Keras Adam.apply_gradients, xagents/ppo/agent.py:135-137,
  * xagents/a2c/agent.py:216-218, over ONE flat fp32 buffer holding every trainable tensor.

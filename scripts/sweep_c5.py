@@ -2,7 +2,7 @@
 """Config C5 (BASELINE.json): GAE / n-step / gather microbench sweep, n_steps 5-2048 x n_envs 16-65536.
 
 Prints a markdown report (commit it under profiles/).  Times are CUDA-event averages over back-to-back
-launches; shapes whose traffic is < 32 MB stay L2-resident and are latency-bound ("us" is the figure that
+launches of prepared ctypes calls (GPU time; the Python wrappers in ops.py add ~15 us of host time per call); shapes whose traffic is < 32 MB stay L2-resident and are latency-bound ("us" is the figure that
 matters there, GB/s is flagged).  The CPU column is the oracle's NumPy loop (= the reference's own loop,
 xagents/ppo/agent.py:84-93) on the host.
 """
@@ -14,8 +14,13 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes  # noqa: E402
+
 import oracle  # noqa: E402
-from xagents_b200 import ops  # noqa: E402
+from xagents_b200 import _ffi, ops  # noqa: E402
+
+lib = _ffi.lib()
+P = lambda t: ctypes.c_void_p(t.data_ptr())
 
 dev = 'cuda:0'
 PEAK = 6542.7
@@ -49,8 +54,10 @@ for T in (5, 32, 128, 512, 2048):
         out = torch.empty((T, E), device=dev)
         nbytes = 16 * T * E + 4 * E
         reps = 200 if nbytes < 64e6 else 20
-        t = {m: timeit(lambda: ops.gae_returns(rd, vd, lvd, dd, 0.99, 0.95, mode=m, out=out), reps) for m in ('auto', 'sequential', 'chunked')}
-        tn = timeit(lambda: ops.nstep_returns(rd, dd, lvd, 0.99, out=out), reps)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)   # raw prepared calls: GPU time, not wrapper time
+        t = {m: timeit(lambda: lib.xa_gae_f32(P(rd), P(vd), P(lvd), P(dd), P(out), None, T, E, 0.99, 0.95, k, st), reps)
+             for k, m in enumerate(('auto', 'sequential', 'chunked'))}
+        tn = timeit(lambda: lib.xa_nstep_returns_f32(P(rd), P(dd), P(lvd), P(out), T, E, 0.99, 0, st), reps)
         t0 = time.perf_counter()
         n_cpu = 1 if T * E > 4e6 else 3
         for _ in range(n_cpu):

@@ -471,3 +471,43 @@ def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
                 flat = oracle.concat_step_batches(ro.actions, want['returns'], ro.values, ro.log_probs)
                 for got, full in zip(fields, flat):
                     assert np.array_equal(got.cpu().numpy(), full[w['idx']])
+
+
+# ---------------------------------------------------------------------------------------------- rollout-time policy step
+@pytest.mark.parametrize('kind,A', [('logits', 6), ('probs', 4), ('logits', 18)])
+def test_policy_step_with_supplied_noise_vs_oracle(kind, A):
+    rng = np.random.default_rng(A)
+    n = 4097
+    logits = rng.standard_normal((n, A)).astype(np.float32)
+    actor = logits
+    if kind == 'probs':
+        e = np.exp(logits - logits.max(-1, keepdims=True))
+        actor = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    u = rng.random((n, A)).astype(np.float32).clip(1e-7, 1 - 1e-7)
+    _, ent, lsm = oracle.categorical_logp_entropy(actor, np.zeros(n), kind == 'probs')
+    want_a = np.argmax(lsm.astype(np.float64) - np.log(-np.log(u.astype(np.float64))), axis=-1)
+    a, lp, en = ops.policy_step(cu(actor), actor_kind=kind, noise=cu(u))
+    a = a.cpu().numpy()
+    gap = np.sort(lsm.astype(np.float64) - np.log(-np.log(u.astype(np.float64))), axis=-1)
+    clear = (gap[:, -1] - gap[:, -2]) > 1e-4                   # ignore numerically tied Gumbel scores
+    assert np.array_equal(a[clear], want_a[clear].astype(np.float32)) and clear.mean() > 0.99
+    close(lp, lsm[np.arange(n), a.astype(np.int64)])
+    close(en, ent)
+
+
+def test_policy_step_philox_sampler_statistics():
+    logits = torch.tensor([[2.0, 0.0, -1.0, 0.5, 0.5, -3.0]], device=DEV).repeat(200_000, 1).contiguous()
+    p = torch.softmax(logits[0], -1).cpu().numpy()
+    a1, lp, en = ops.policy_step(logits, seed=7, offset=0)
+    a2, _, _ = ops.policy_step(logits, seed=7, offset=0)
+    a3, _, _ = ops.policy_step(logits, seed=7, offset=12)
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)     # counter-based: reproducible, offset advances it
+    freq = np.bincount(a1.cpu().numpy().astype(np.int64), minlength=6) / len(a1)
+    sigma = np.sqrt(p * (1 - p) / len(a1))
+    assert np.all(np.abs(freq - p) < 5 * sigma), (freq, p)
+    assert abs(float(lp.mean()) - float((p * np.log(p)).sum())) < 0.01           # E[log p(a)] = -H
+    loc = torch.zeros((100_000, 3), device=DEV)
+    act, lp, en = ops.policy_step(loc, actor_kind='normal', seed=3)
+    assert abs(float(act.mean())) < 0.02 and abs(float(act.var()) - 1.0) < 0.02
+    close(lp, (-0.5 * (act.double() ** 2).sum(-1) - 1.5 * np.log(2 * np.pi)).cpu().numpy())
+    assert abs(float(en[0]) - 1.5 * (1 + np.log(2 * np.pi))) < 1e-5

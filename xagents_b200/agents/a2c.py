@@ -28,6 +28,7 @@ class A2C(OnPolicy):
         self.action_source = None        # tests: callable(step, actor_out) -> actions, to replay a fixed rollout
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(self.seed) if self.seed else 0)
+        self._rng_offset = 0             # Philox counter offset of the in-kernel sampler
         self._alloc_rollout()
 
     # ------------------------------------------------------------------ buffers
@@ -72,9 +73,14 @@ class A2C(OnPolicy):
         """[actions, log probs, critic output, entropy, actor output] like a2c/agent.py:65-94 (device tensors)."""
         x = inputs if isinstance(inputs, torch.Tensor) else self._to_device(inputs, self.obs_dtype)
         actor_out, critic = self.net.forward(x, training=training)
+        if actions is None and self.action_source is None:
+            # sample + log_prob + entropy in one kernel (Philox stream keyed by the agent seed)
+            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind,
+                                                     seed=int(self.seed) if self.seed else 0, offset=self._rng_offset)
+            self._rng_offset += 2 * self.n_actions
+            return actions, logp, critic, entropy, actor_out
         if actions is None:
-            actions = (self.action_source(step, actor_out) if self.action_source is not None
-                       else self.sample_actions(actor_out))
+            actions = self.action_source(step, actor_out)
             actions = actions if isinstance(actions, torch.Tensor) else self._to_device(actions, torch.float32)
         logp, entropy = self._log_prob_entropy(actor_out, actions)
         return actions, logp, critic, entropy, actor_out

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -192,6 +192,27 @@ def gather_rows_scaled(src_u8, idx, *, time_major=None, out=None, stream=None):
     _ffi.call('xa_gather_rows_u8_scaled_f32', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, _stream(stream))
     _count()
     return dst
+
+
+# ------------------------------------------------------------------------------------------ rollout-time policy
+def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0, out=None, stream=None):
+    """sample() + log_prob() + entropy() of A2C.get_model_outputs (a2c/agent.py:80-94) for one env step.
+    Returns (actions, log_probs, entropies); `out` may hold row views of the rollout buffers."""
+    ao = _dev(actor_out, 'float32')
+    n, A = ao.shape[0], ao.shape[-1]
+    dev = _device_of(ao)
+    actions, logp, ent = out if out is not None else (None, None, None)
+    if actions is None:
+        actions = torch.empty((n, A) if actor_kind == 'normal' else (n,), dtype=torch.float32, device=dev)
+    if logp is None:
+        logp = torch.empty((n,), dtype=torch.float32, device=dev)
+    if ent is None:
+        ent = torch.empty((n,), dtype=torch.float32, device=dev)
+    nz = _dev(noise, 'float32') if noise is not None else None
+    _ffi.call('xa_policy_step_f32', _ptr(ao), ACTOR_KINDS[actor_kind], _ptr(nz), int(seed), int(offset), _tptr(actions),
+              _tptr(logp), _tptr(ent), n, A, _stream(stream))
+    _count()
+    return actions, logp, ent
 
 
 # ------------------------------------------------------------------------------------------ moments + losses
