@@ -165,6 +165,15 @@ int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* nois
                        uint64_t offset, float* actions, float* log_probs, float* entropies, int64_t n,
                        int n_actions, xa_stream_t stream);
 
+/* ---- dense contractions on the tensor cores (row "next": the policy/value network) ------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU), bf16 operands, fp32 accumulation in TMEM (tcgen05),
+ * operands staged by TMA: the Dense layers ModelReader builds (xagents/utils/common.py:239-258; FC 3136->512
+ * and the actor/critic heads of ppo/models/cnn-actor-critic.cfg:30-42) in forward (A = activations,
+ * B = weights) and, on transposed copies, both backward products.  A, B row-major with K contiguous,
+ * 16-B aligned, K % 8 == 0; C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (1). */
+int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n,
+                    int64_t k, int64_t ldc, int out_bf16, int relu, xa_stream_t stream);
+
 /* ---- optimiser step (row "next": the step right after the path) ------------------------------ */
 /* tf.clip_by_global_norm + Keras Adam.apply_gradients, xagents/ppo/agent.py:135-137,
  * xagents/a2c/agent.py:216-218, over ONE flat fp32 buffer holding every trainable tensor.

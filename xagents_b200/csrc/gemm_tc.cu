@@ -1,0 +1,304 @@
+// bf16 GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] * B[N,K]^T (+ bias, ReLU), fp32 accumulate.
+//
+// Row "next" (SURVEY.md 8f-1): the policy/value network's dense contractions -- FC 3136->512 and the actor /
+// critic heads built by ModelReader from ppo/models/cnn-actor-critic.cfg:30-42 (xagents/utils/common.py:239-258),
+// forward and both backward products -- which the reference leaves to Keras/Eigen.  Both operands are
+// K-major (x and W of a Dense layer as they sit in memory), so y = x W^T needs no transposition.
+//
+// Warp-specialised, one 128 x BN output tile per CTA:
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (64 bf16 = one 128-B swizzle row per K block) of A
+//            and B into a ring of shared-memory stages, completion counted on "full" mbarriers;
+//   warp 1   allocates BN TMEM columns, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16, operands
+//            read from shared memory through SWIZZLE_128B descriptors, accumulator in TMEM); tcgen05.commit
+//            releases each stage ("empty" mbarrier) and finally signals the accumulator;
+//   warps 2-5 epilogue: tcgen05.ld their TMEM lane quadrant (32 rows x 32 columns per instruction), add
+//            bias, apply ReLU, convert and store.
+// SASS carries UTCHMMA / UTMALDG / LDTM (B200_PROFILING.md evidence table).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "xa_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kWatchdog = 1u << 28;
+
+struct GemmParams {
+  void* c;
+  const float* bias;
+  int64_t m, n, k, ldc;
+  int relu;
+};
+
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = xa::smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (++spins > kWatchdog) __trap();  // a descriptor / barrier bug must fault, not hang the GPU
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          xa::smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(xa::smem_u32(bar))
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+// rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
+  const uint64_t addr = xa::smem_u32(tile);
+  uint64_t d = 0;
+  d |= (addr >> 4) & 0x3FFF;              // start address            [0,14)
+  d |= static_cast<uint64_t>(1) << 16;    // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset: 8 rows * 128 B  [32,46)
+  d |= static_cast<uint64_t>(1) << 46;    // descriptor version 1       [46,48)
+  d |= static_cast<uint64_t>(2) << 61;    // layout type SWIZZLE_128B   [61,64)
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(xa::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int kStageA = kBlockM * kBlockK * 2;
+  static constexpr int kStageB = BN * kBlockK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;
+  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool kOutBf16>
+__global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStage);
+  uint64_t* empty = full + S::kStages;
+  uint64_t* acc_full = empty + S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int k_blocks = static_cast<int>((p.k + kBlockK - 1) / kBlockK);
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < S::kStages; ++s) {
+      xa::mbar_init(full + s, 1);
+      xa::mbar_init(empty + s, 1);
+    }
+    xa::mbar_init(acc_full, 1);
+    xa::fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % S::kStages;
+        const uint32_t round = kb / S::kStages;
+        if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+        uint8_t* a_dst = smem + s * S::kStage;
+        uint8_t* b_dst = a_dst + S::kStageA;
+        xa::mbar_expect_tx(full + s, S::kStage);
+        tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
+        tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      constexpr uint32_t idesc = make_idesc(kBlockM, BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % S::kStages;
+        mbar_wait_wd(full + s, (kb / S::kStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = make_smem_desc(smem + s * S::kStage);
+        const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
+      }
+      umma_commit(acc_full);  // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    const int quad = warp & 3;
+    mbar_wait_wd(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t row = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + lane;
+    const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
+      const int64_t col0 = static_cast<int64_t>(tile_n) * BN + c0;
+      if (row < p.m && col0 < p.n) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
+          if (p.relu) x = fmaxf(x, 0.0f);
+          f[j] = x;
+        }
+        if (vec_ok && col0 + 32 <= p.n) {
+          if (kOutBf16) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+              dst[j] = *reinterpret_cast<uint4*>(h);
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
+            if (kOutBf16)
+              static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + col0 + j] = __float2bfloat16_rn(f[j]);
+            else
+              static_cast<float*>(p.c)[row * p.ldc + col0 + j] = f[j];
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
+        status == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, k] -> tiles of box_rows x 64, 128-B swizzled; out-of-bounds reads give zeros
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int box_rows, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (rows=%lld k=%lld)", what, static_cast<int>(r),
+             static_cast<long long>(rows), static_cast<long long>(k));
+  return XA_OK;
+}
+
+template <int BN, bool kOutBf16>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
+  auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kBytes);
+  if (e != cudaSuccess) {
+    xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  const dim3 grid(static_cast<unsigned>((p.m + kBlockM - 1) / kBlockM), static_cast<unsigned>((p.n + BN - 1) / BN));
+  kernel<<<grid, kThreads, Smem<BN>::kBytes, stream>>>(ma, mb, p);
+  return xa::check_launch(what);
+}
+
+}  // namespace
+
+extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
+                               int64_t ldc, int out_bf16, int relu, xa_stream_t stream) {
+  const char* what = "xa_gemm_bf16_tn";
+  XA_REQUIRE(a && b && c, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(m > 0 && n > 0 && k > 0 && ldc >= n, XA_EINVAL, "%s: m=%lld n=%lld k=%lld ldc=%lld", what, static_cast<long long>(m),
+             static_cast<long long>(n), static_cast<long long>(k), static_cast<long long>(ldc));
+  XA_REQUIRE(k % 8 == 0, XA_EALIGN, "%s: k=%lld must be a multiple of 8 (16-byte row pitch for TMA)", what, static_cast<long long>(k));
+  XA_REQUIRE(xa::aligned(a, 16) && xa::aligned(b, 16), XA_EALIGN, "%s: a and b must be 16-byte aligned", what);
+  XA_REQUIRE(m < (int64_t(1) << 31) && n < (int64_t(1) << 31) && k < (int64_t(1) << 31), XA_EOVERFLOW, "%s: dimension too large", what);
+  const int bn = n > 64 ? 128 : (n > 16 ? 64 : 16);
+  CUtensorMap ma, mb;
+  if (int rc = make_map(&ma, a, m, k, kBlockM, what)) return rc;
+  if (int rc = make_map(&mb, b, n, k, bn, what)) return rc;
+  GemmParams p{c, bias, m, n, k, ldc, relu};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);
+  if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
+  return out_bf16 ? launch<16, true>(ma, mb, p, s, what) : launch<16, false>(ma, mb, p, s, what);
+}

@@ -20,7 +20,7 @@ int sm_count();                      // cached multiProcessorCount of the curren
     }                                \
   } while (0)
 
-static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+__host__ __device__ static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---- device side ------------------------------------------------------------------------------
 // env-major flat sample id b = e*T + t  ->  row of the time-major [T*E] buffer (base.py:559-564)

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -364,3 +364,19 @@ def clip_adam(param, grad, m, v, step, *, workspace=None, lr=7e-4, beta1=0.9, be
     _ffi.call('xa_clip_adam_f32', _ptr(p), _ptr(g), _ptr(mm), _ptr(vv), p.size, _tptr(workspace), float(lr), float(beta1),
               float(beta2), float(eps), clip, int(step), float(grad_scale), _stream(stream))
     _count()
+
+
+# ------------------------------------------------------------------------------------------ tensor-core GEMM
+def gemm_bf16_tn(a, b, *, bias=None, relu=False, out_dtype=torch.float32, out=None, stream=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+ bias) (ReLU) on tcgen05 tensor cores: bf16 operands, fp32 accumulate.
+    The Dense layers of the policy/value network (utils/common.py:239-258), y = x W^T + b."""
+    aa, bb = _dev(a, 'bfloat16'), _dev(b, 'bfloat16')
+    (m, k), (n, k2) = aa.shape, bb.shape
+    if k != k2:
+        raise ValueError(f'inner dimensions differ: A {aa.shape}, B {bb.shape}')
+    c = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=_device_of(aa))
+    bias_a = _dev(bias, 'float32') if bias is not None else None
+    _ffi.call('xa_gemm_bf16_tn', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
+              int(bool(relu)), _stream(stream))
+    _count()
+    return c
