@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""tcgen05 GEMM (xa_gemm_bf16_tn) vs cuBLAS (torch.matmul, bf16) on the network's dense-layer shapes."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from xagents_b200 import ops  # noqa: E402
+
+dev = 'cuda:0'
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+print('| M | N | K | what | ours us | ours TFLOP/s | cuBLAS us | cuBLAS TFLOP/s | ratio |')
+print('|---|---|---|---|---|---|---|---|---|')
+for m, n, k, what in [(8192, 512, 3136, 'fc fwd (B=8192)'), (8192, 3136, 512, 'fc dgrad'), (512, 3136, 8192, 'fc wgrad'),
+                      (65536, 512, 3136, 'fc fwd (B=65536)'), (8192, 8, 512, 'heads fwd'), (8192, 8192, 8192, 'square 8192')]:
+    a = torch.randn((m, k), device=dev).to(torch.bfloat16)
+    b = torch.randn((n, k), device=dev).to(torch.bfloat16)
+    out = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+    t_ours = timeit(lambda: ops.gemm_bf16_tn(a, b, out=out))
+    bt = b.t()
+    t_ref = timeit(lambda: torch.matmul(a, bt, out=out))
+    fl = 2.0 * m * n * k
+    print(f'| {m} | {n} | {k} | {what} | {t_ours:.1f} | {fl/t_ours/1e6:.0f} | {t_ref:.1f} | {fl/t_ref/1e6:.0f} | {t_ref/t_ours:.2f} |')

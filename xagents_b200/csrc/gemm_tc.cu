@@ -5,14 +5,18 @@
 // forward and both backward products -- which the reference leaves to Keras/Eigen.  Both operands are
 // K-major (x and W of a Dense layer as they sit in memory), so y = x W^T needs no transposition.
 //
-// Warp-specialised, one 128 x BN output tile per CTA:
+// Warp-specialised and persistent: one CTA per SM walks 128 x BN output tiles (M fastest, so CTAs running
+// together share the same weight tile in L2); the accumulator is double-buffered in TMEM so the epilogue of
+// tile i drains while the tensor core already works on tile i+1.  BN = 256 for wide outputs: a 128 x 128
+// tile needs 32 KB of operands per 256 MMA cycles (~128 B/cycle/SM, more than L2 can feed 148 SMs);
+// 128 x 256 cuts that by a third.
 //   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (64 bf16 = one 128-B swizzle row per K block) of A
 //            and B into a ring of shared-memory stages, completion counted on "full" mbarriers;
-//   warp 1   allocates BN TMEM columns, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16, operands
-//            read from shared memory through SWIZZLE_128B descriptors, accumulator in TMEM); tcgen05.commit
-//            releases each stage ("empty" mbarrier) and finally signals the accumulator;
+//   warp 1   allocates 2 x BN TMEM columns, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16,
+//            operands read from shared memory through SWIZZLE_128B descriptors, accumulator in TMEM);
+//            tcgen05.commit releases each stage ("empty" mbarrier) and signals the finished accumulator;
 //   warps 2-5 epilogue: tcgen05.ld their TMEM lane quadrant (32 rows x 32 columns per instruction), add
-//            bias, apply ReLU, convert and store.
+//            bias, apply ReLU, convert, store, then hand the accumulator back ("acc_empty").
 // SASS carries UTCHMMA / UTMALDG / LDTM (B200_PROFILING.md evidence table).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -106,7 +110,7 @@ struct Smem {
   static constexpr int kStageA = kBlockM * kBlockK * 2;
   static constexpr int kStageB = BN * kBlockK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;
+  static constexpr int kStages = (208 * 1024) / kStage > 8 ? 8 : (208 * 1024) / kStage;
   static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -118,14 +122,18 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStage);
   uint64_t* empty = full + S::kStages;
-  uint64_t* acc_full = empty + S::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + S::kStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int k_blocks = static_cast<int>((p.k + kBlockK - 1) / kBlockK);
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  const int tiles_m = static_cast<int>((p.m + kBlockM - 1) / kBlockM);
+  const int tiles_n = static_cast<int>((p.n + BN - 1) / BN);
+  const int n_tiles = tiles_m * tiles_n;
+  constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;  // the epilogue reads 32 columns at a time
+  constexpr uint32_t kTmemCols = 2 * kAccStride;      // two accumulators
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -134,7 +142,10 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
       xa::mbar_init(full + s, 1);
       xa::mbar_init(empty + s, 1);
     }
-    xa::mbar_init(acc_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      xa::mbar_init(acc_full + a, 1);
+      xa::mbar_init(acc_empty + a, 4);  // one arrival per epilogue warp
+    }
     xa::fence_barrier_init();
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
@@ -148,84 +159,105 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        const int s = kb % S::kStages;
-        const uint32_t round = kb / S::kStages;
-        if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
-        uint8_t* a_dst = smem + s * S::kStage;
-        uint8_t* b_dst = a_dst + S::kStageA;
-        xa::mbar_expect_tx(full + s, S::kStage);
-        tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
-        tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+    if (lane == 0) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % S::kStages;
+          const uint32_t round = it / S::kStages;
+          if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+          uint8_t* a_dst = smem + s * S::kStage;
+          uint8_t* b_dst = a_dst + S::kStageA;
+          xa::mbar_expect_tx(full + s, S::kStage);
+          tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
+          tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        const int s = kb % S::kStages;
-        mbar_wait_wd(full + s, (kb / S::kStages) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = make_smem_desc(smem + s * S::kStage);
-        const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
-#pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1, use = lt >> 1;
+        if (use > 0) {  // the epilogue must have drained this accumulator
+          mbar_wait_wd(acc_empty + acc, (use - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % S::kStages;
+          mbar_wait_wd(full + s, (it / S::kStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem + s * S::kStage);
+          const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
+        }
+        umma_commit(acc_full + acc);  // accumulator complete
       }
-      umma_commit(acc_full);  // accumulator complete
     }
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
     const int quad = warp & 3;
-    mbar_wait_wd(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + lane;
     const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
+      const uint32_t acc = lt & 1;
+      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
-      const int64_t col0 = static_cast<int64_t>(tile_n) * BN + c0;
-      if (row < p.m && col0 < p.n) {
-        float f[32];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
+        const int64_t col0 = static_cast<int64_t>(tile_n) * BN + c0;
+        if (row < p.m && col0 < p.n) {
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
-          if (p.relu) x = fmaxf(x, 0.0f);
-          f[j] = x;
-        }
-        if (vec_ok && col0 + 32 <= p.n) {
-          if (kOutBf16) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col0);
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
+            if (p.relu) x = fmaxf(x, 0.0f);
+            f[j] = x;
+          }
+          if (vec_ok && col0 + 32 <= p.n) {
+            if (kOutBf16) {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h[4];
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-              dst[j] = *reinterpret_cast<uint4*>(h);
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+                dst[j] = *reinterpret_cast<uint4*>(h);
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
           } else {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
-            if (kOutBf16)
-              static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + col0 + j] = __float2bfloat16_rn(f[j]);
-            else
-              static_cast<float*>(p.c)[row * p.ldc + col0 + j] = f[j];
+            for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
+              if (kOutBf16)
+                static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + col0 + j] = __float2bfloat16_rn(f[j]);
+              else
+                static_cast<float*>(p.c)[row * p.ldc + col0 + j] = f[j];
+            }
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -276,7 +308,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
     xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     return static_cast<int>(e);
   }
-  const dim3 grid(static_cast<unsigned>((p.m + kBlockM - 1) / kBlockM), static_cast<unsigned>((p.n + BN - 1) / BN));
+  const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN);
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);  // persistent: at most one CTA per SM
   kernel<<<grid, kThreads, Smem<BN>::kBytes, stream>>>(ma, mb, p);
   return xa::check_launch(what);
 }
@@ -292,12 +326,13 @@ extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const floa
   XA_REQUIRE(k % 8 == 0, XA_EALIGN, "%s: k=%lld must be a multiple of 8 (16-byte row pitch for TMA)", what, static_cast<long long>(k));
   XA_REQUIRE(xa::aligned(a, 16) && xa::aligned(b, 16), XA_EALIGN, "%s: a and b must be 16-byte aligned", what);
   XA_REQUIRE(m < (int64_t(1) << 31) && n < (int64_t(1) << 31) && k < (int64_t(1) << 31), XA_EOVERFLOW, "%s: dimension too large", what);
-  const int bn = n > 64 ? 128 : (n > 16 ? 64 : 16);
+  const int bn = n >= 256 ? 256 : (n > 64 ? 128 : (n > 16 ? 64 : 16));
   CUtensorMap ma, mb;
   if (int rc = make_map(&ma, a, m, k, kBlockM, what)) return rc;
   if (int rc = make_map(&mb, b, n, k, bn, what)) return rc;
   GemmParams p{c, bias, m, n, k, ldc, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bn == 256) return out_bf16 ? launch<256, true>(ma, mb, p, s, what) : launch<256, false>(ma, mb, p, s, what);
   if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);
   if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
   return out_bf16 ? launch<16, true>(ma, mb, p, s, what) : launch<16, false>(ma, mb, p, s, what);
