@@ -174,6 +174,11 @@ int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* nois
 int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n,
                     int64_t k, int64_t ldc, int out_bf16, int relu, xa_stream_t stream);
 
+/* fp32 | bf16 [rows, cols] -> bf16, same orientation (dst pitch ld_dst >= cols) or transposed into
+ * [cols, ld_dst >= rows]: operand preparation for the backward products (dW = dY^T X needs both transposed). */
+int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t rows, int64_t cols, int64_t ld_dst,
+               int transpose, xa_stream_t stream);
+
 /* ---- optimiser step (row "next": the step right after the path) ------------------------------ */
 /* tf.clip_by_global_norm + Keras Adam.apply_gradients, xagents/ppo/agent.py:135-137,
  * xagents/a2c/agent.py:216-218, over ONE flat fp32 buffer holding every trainable tensor.

@@ -45,3 +45,56 @@ def test_gemm_argument_errors():
         ops.gemm_bf16_tn(torch.zeros((8, 16), dtype=torch.bfloat16, device=DEV), torch.zeros((8, 8), dtype=torch.bfloat16, device=DEV))
     with pytest.raises(TypeError):
         ops.gemm_bf16_tn(torch.zeros((8, 16), device=DEV), torch.zeros((8, 16), device=DEV))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('m,k,n,relu', [(8192, 3136, 512, True), (1000, 512, 6, False), (37, 512, 1, False)])
+def test_tc_linear_forward_backward_vs_torch(m, k, n, relu):
+    """TcLinear (three tcgen05 GEMMs + transposes) against torch.nn.Linear in fp32 on the same bf16-rounded
+    weights and inputs: forward, dx, dW, db."""
+    from xagents_b200.agents.tc_dense import TcLinear
+    torch.manual_seed(m + n)
+    lin = TcLinear(k, n, relu=relu).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(lin.weight.to(torch.bfloat16).float())          # make the bf16 operand copy exact
+        lin.bias.copy_(torch.randn(n, device=DEV) * 0.1)
+    lin.refresh()
+    x = torch.randn((m, k), device=DEV).to(torch.bfloat16).float().requires_grad_(True)
+    dy = torch.randn((m, n), device=DEV).to(torch.bfloat16).float()
+    y = lin(x)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_(True)
+    wr = lin.weight.detach().double().requires_grad_(True)
+    br = lin.bias.detach().double().requires_grad_(True)
+    yr = xr @ wr.t() + br
+    if relu:
+        yr = yr.clamp_min(0)
+    yr.backward(dy.double())
+
+    def near(got, want, rel):
+        scale = float(want.abs().max())
+        assert float((got.double() - want).abs().max()) <= rel * scale
+
+    near(y, yr.detach(), 1e-5)
+    near(lin.bias.grad, br.grad, 1e-5)
+    # dy is re-rounded to bf16 only through the ReLU mask (exact), so the backward products are fp32-accumulate exact
+    near(x.grad, xr.grad, 2e-5)
+    near(lin.weight.grad, wr.grad, 2e-5)
+
+
+@pytest.mark.timeout(180)
+def test_nature_cnn_with_tensor_core_dense_trains():
+    from xagents_b200.agents import NatureCNN, TorchModel
+    torch.manual_seed(0)
+    net = TorchModel(NatureCNN(4, 6, tensor_core_dense=True).cuda())
+    ref = NatureCNN(4, 6).cuda()
+    ref.load_state_dict({k: v.clone() for k, v in net.module.state_dict().items()}, strict=True)
+    x = torch.randint(0, 256, (256, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    actor, critic = net.forward(x, training=True)
+    ra, rc = ref(x.float() / 255.0)
+    assert float((actor - ra).abs().max()) <= 2e-2 * float(ra.abs().max()) + 1e-3      # bf16 operands vs fp32
+    assert float((critic - rc.reshape(-1)).abs().max()) <= 2e-2 * float(rc.abs().max()) + 1e-3
+    before = net.flat_param.clone()
+    net.backward_and_step(torch.randn_like(actor) / 256, torch.randn_like(critic) / 256, grad_norm=0.5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)

@@ -49,6 +49,9 @@ class TorchModel:
             off += k
         self.n_params = n
         self._outputs = None
+        self._refreshable = [m for m in module.modules() if hasattr(m, 'refresh')]
+        for mod in self._refreshable:
+            mod.refresh()
 
     def forward(self, states, training=True):
         x = states
@@ -76,6 +79,8 @@ class TorchModel:
         self.step += 1
         ops.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.step, workspace=self.workspace, lr=self.lr,
                       beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, clip_norm=grad_norm, grad_scale=scale)
+        for mod in self._refreshable:                             # bf16 operand copies of tensor-core layers
+            mod.refresh()
 
 
 class KerasModel:
@@ -133,12 +138,18 @@ class NatureCNN(torch.nn.Module):
     """The documented PPO/A2C CNN (README.md:243-259; ppo/models/cnn-actor-critic.cfg:1-42 read as Conv2D):
     32x8/4 -> 64x4/2 -> 64x3/1 -> FC512 shared trunk -> actor (A) and critic (1) heads, orthogonal init."""
 
-    def __init__(self, in_channels=4, n_actions=6):
+    def __init__(self, in_channels=4, n_actions=6, tensor_core_dense=False):
         super().__init__()
         nn = torch.nn
+        if tensor_core_dense:                                     # FC512 + heads on the tcgen05 GEMM (tc_dense.py)
+            from .tc_dense import TcLinear
+            fc = [TcLinear(3136, 512, relu=True)]
+            self.actor, self.critic = TcLinear(512, n_actions), TcLinear(512, 1)
+        else:
+            fc = [nn.Linear(3136, 512), nn.ReLU()]
+            self.actor, self.critic = nn.Linear(512, n_actions), nn.Linear(512, 1)
         self.trunk = nn.Sequential(nn.Conv2d(in_channels, 32, 8, 4), nn.ReLU(), nn.Conv2d(32, 64, 4, 2), nn.ReLU(),
-                                   nn.Conv2d(64, 64, 3, 1), nn.ReLU(), nn.Flatten(), nn.Linear(3136, 512), nn.ReLU())
-        self.actor, self.critic = nn.Linear(512, n_actions), nn.Linear(512, 1)
+                                   nn.Conv2d(64, 64, 3, 1), nn.ReLU(), nn.Flatten(), *fc)
         for mod, gain in [(m, 2 ** 0.5) for m in self.trunk if hasattr(m, 'weight')] + [(self.actor, 0.01), (self.critic, 1.0)]:
             nn.init.orthogonal_(mod.weight, gain)
             nn.init.zeros_(mod.bias)

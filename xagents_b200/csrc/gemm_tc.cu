@@ -337,3 +337,48 @@ extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const floa
   if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
   return out_bf16 ? launch<16, true>(ma, mb, p, s, what) : launch<16, false>(ma, mb, p, s, what);
 }
+
+// ---------------------------------------------------------------------------------------------- layout helper
+// fp32|bf16 [rows, cols] -> bf16, optionally transposed into [cols, ld_dst] (ld_dst >= rows; the padding the
+// GEMM's K % 8 rule may need is the caller's zero-filled buffer).  32x32 shared-memory tiles, coalesced both ways.
+namespace {
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+                                                       int64_t cols, int64_t ld_dst, int transpose) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    if (r < rows && c < cols) tile[j][tx] = static_cast<float>(src[r * cols + c]);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    if (transpose) {
+      const int64_t c = c0 + j, r = r0 + tx;  // dst[c, r]
+      if (r < rows && c < cols) dst[c * ld_dst + r] = __float2bfloat16_rn(tile[tx][j]);
+    } else {
+      const int64_t r = r0 + j, c = c0 + tx;
+      if (r < rows && c < cols) dst[r * ld_dst + c] = __float2bfloat16_rn(tile[j][tx]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t rows, int64_t cols, int64_t ld_dst, int transpose,
+                          xa_stream_t stream) {
+  XA_REQUIRE(src && dst, XA_EINVAL, "xa_to_bf16: null pointer");
+  XA_REQUIRE(rows > 0 && cols > 0 && ld_dst >= (transpose ? rows : cols), XA_EINVAL, "xa_to_bf16: rows=%lld cols=%lld ld_dst=%lld",
+             static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld_dst));
+  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  XA_REQUIRE(grid.y <= 65535, XA_EOVERFLOW, "xa_to_bf16: too many rows for one launch (%lld)", static_cast<long long>(rows));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_is_f32)
+    to_bf16_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, cols, ld_dst, transpose);
+  else
+    to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, cols,
+                                                        ld_dst, transpose);
+  return xa::check_launch("xa_to_bf16");
+}

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -380,3 +380,22 @@ def gemm_bf16_tn(a, b, *, bias=None, relu=False, out_dtype=torch.float32, out=No
               int(bool(relu)), _stream(stream))
     _count()
     return c
+
+
+def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
+    """fp32|bf16 [R, C] -> bf16 [R, C] or, transposed, [C, R'] with R' = R rounded up to `pad_to` (zero-filled),
+    which is what xa_gemm_bf16_tn needs when R becomes the contraction dimension."""
+    a = _dev(src)
+    if a.dtype not in ('float32', 'bfloat16') or len(a.shape) != 2:
+        raise TypeError(f'to_bf16 needs a 2-D float32/bfloat16 tensor, got {a.dtype} {a.shape}')
+    rows, cols = a.shape
+    dev = _device_of(a)
+    if transpose:
+        ld = -(-rows // pad_to) * pad_to
+        dst = (torch.zeros if ld != rows else torch.empty)((cols, ld), dtype=torch.bfloat16, device=dev)
+    else:
+        ld = cols
+        dst = torch.empty((rows, cols), dtype=torch.bfloat16, device=dev)
+    _ffi.call('xa_to_bf16', _ptr(a), int(a.dtype == 'float32'), _tptr(dst), rows, cols, ld, int(transpose), _stream(stream))
+    _count()
+    return dst
