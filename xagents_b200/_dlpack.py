@@ -125,7 +125,7 @@ def as_device_array(obj, dtype=None, allow_host=False):
     """Borrow `obj` (a DLPack capsule or any object with __dlpack__) as a DeviceArray."""
     if isinstance(obj, DeviceArray):
         arr = obj
-    elif type(obj).__module__ == 'torch' and type(obj).__name__ in ('Tensor', 'Parameter'):
+    elif type(obj).__module__.split('.')[0] == 'torch' and hasattr(obj, 'data_ptr') and hasattr(obj, 'is_cuda'):
         arr = _from_torch(obj.detach() if obj.requires_grad else obj)
     elif type(obj).__name__ == 'PyCapsule':
         arr = from_capsule(obj)
