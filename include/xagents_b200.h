@@ -62,6 +62,13 @@ int xa_nstep_returns_f32(const float* rewards, const float* dones, const float* 
                          float* returns, int n_steps, int n_envs, double gamma, int mode,
                          xa_stream_t stream);
 
+/* ACER.calculate_returns (Retrace), xagents/acer/agent.py:198-208, on time-major [T,E] fields (row "next":
+ * the same reverse-scan machinery reused by ACER).  dones [T+1,E] as above; importance is the raw ratio
+ * (min(1, .) is applied inside); q_selected = critic output at the taken action. */
+int xa_retrace_f32(const float* rewards, const float* dones, const float* values, const float* last_values,
+                   const float* q_selected, const float* importance, float* returns, int n_steps, int n_envs,
+                   double gamma, xa_stream_t stream);
+
 /* ---- permute-gather ------------------------------------------------------------------------- */
 #define XA_GATHER_AUTO 0
 #define XA_GATHER_BULK 1   /* TMA bulk copies global->shared->global; needs 16-B aligned rows */

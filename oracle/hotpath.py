@@ -10,7 +10,7 @@ TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
 import numpy as np
 
 __all__ = [
-    'gae_returns', 'nstep_returns', 'concat_step_batches', 'env_major_to_time_major',
+    'gae_returns', 'nstep_returns', 'retrace_returns', 'concat_step_batches', 'env_major_to_time_major',
     'minibatch_slices', 'gather_minibatches', 'scale_images', 'normalize_advantages',
     'categorical_logp_entropy', 'diag_normal_logp_entropy', 'ppo_loss', 'ppo_loss_grads',
     'a2c_loss', 'a2c_loss_grads', 'clip_by_global_norm', 'adam_step', 'ppo_train_step',
@@ -58,6 +58,21 @@ def nstep_returns(rewards, dones, next_values, gamma, dtype=np.float32):
     for t in range(n_steps - 1, -1, -1):
         running = rewards[t] + (dtype(gamma) * running) * (one - dones[t + 1])   # :168-170
         out[t] = running
+    return out
+
+
+def retrace_returns(rewards, dones, values, last_values, q_selected, importance, gamma, dtype=np.float32):
+    """ACER Retrace targets, time-major [T,E] in and out.  Follows xagents/acer/agent.py:198-208
+    (dones[t] there is the flag AFTER step t, i.e. row t+1 of the [T+1,E] array used elsewhere here)."""
+    rewards, values, q_selected = (np.asarray(x, dtype) for x in (rewards, values, q_selected))
+    dones = np.asarray(dones, dtype)
+    rho = np.minimum(dtype(1.0), np.asarray(importance, dtype))                 # :198
+    current = np.asarray(last_values, dtype).reshape(-1)                        # values[-1], :203
+    out = np.empty_like(rewards)
+    for t in range(rewards.shape[0] - 1, -1, -1):
+        current = rewards[t] + dtype(gamma) * current * (dtype(1.0) - dones[t + 1])   # :205
+        out[t] = current
+        current = (rho[t] * (current - q_selected[t])) + values[t]              # :207-209
     return out
 
 

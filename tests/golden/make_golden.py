@@ -7,7 +7,7 @@ this image, so `import xagents` cannot work as is.  This script installs import-
 * permissive stub modules for everything the reference imports but the hot path never calls;
 * a NumPy-backed shim of exactly the TensorFlow / tfp ops the hot path calls
   (range, random.shuffle, gather, reduce_mean, math.reduce_std, clip_by_value, square, maximum,
-  exp, squeeze, cast, numpy_function, function, GradientTape, clip_by_global_norm;
+  exp, squeeze, cast, minimum, reshape, split, stack, numpy_function, function, GradientTape, clip_by_global_norm;
   Categorical.log_prob / entropy / sample) following their published definitions, fp32;
 * fake gym environments that replay a seeded synthetic stream, and a tiny NumPy "model".
 
@@ -192,7 +192,11 @@ def _populate(module):
         module.square = np.square
         module.maximum = np.maximum
         module.exp = np.exp
-        module.squeeze = lambda x: np.squeeze(np.asarray(x)).view(_Tensor)
+        module.squeeze = lambda x, axis=None: np.squeeze(np.asarray(x), axis).view(_Tensor)
+        module.minimum = np.minimum
+        module.reshape = lambda t, shape: np.reshape(np.asarray(t), shape)
+        module.split = lambda t, n, axis=0: np.split(np.asarray(t), n, axis)
+        module.stack = lambda items, axis=0: np.stack([np.asarray(i) for i in items], axis)
         module.cast = lambda x, dtype: _f32(x)
         module.GradientTape = _Tape
         module.clip_by_global_norm = lambda grads, norm: (grads, F32(0))
@@ -423,8 +427,28 @@ def kat_case(xagents):
     print('kat_returns:', ppo_ret[0], a2c_ret[0])
 
 
+def acer_case(xagents):
+    """ACER's Retrace returns (xagents/acer/agent.py:171-208) on flat env-major inputs, as ACER feeds them."""
+    T, E = 11, 6
+    rng = np.random.default_rng(31)
+    flat = lambda *shape: rng.standard_normal(shape).astype(F32)
+    rewards, q_sel = flat(E * T), flat(E * T)
+    dones = (rng.random(E * T) < 0.15).astype(F32)
+    values = flat(E * (T + 1))
+    importance = np.exp(0.7 * rng.standard_normal(E * T)).astype(F32)
+    a = object.__new__(xagents.ACER)
+    a.n_steps, a.n_envs, a.gamma = T, E, 0.99
+    out = xagents.ACER.calculate_returns(a, rewards, dones, values, q_sel, importance)
+    np.savez_compressed(os.path.join(HERE, 'acer_retrace.npz'), n_steps=T, n_envs=E, gamma=0.99, rewards=rewards, dones=dones,
+                        values=values, q_selected=q_sel, importance=importance, returns=np.asarray(out))
+    print('acer_retrace:', np.asarray(out)[:4])
+
+
 def main():
     xagents = _import_reference()
+    if '--acer-only' in sys.argv:
+        return acer_case(xagents)
+    acer_case(xagents)
     kat_case(xagents)
     # PPO, image observations (uint8-valued, 8x8x4), 6 actions: Atari-shaped in miniature
     ppo_case(xagents, 'ppo_image', 11, n_steps=16, n_envs=8, obs_shape=(8, 8, 4), image=True,

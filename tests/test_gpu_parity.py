@@ -511,3 +511,35 @@ def test_policy_step_philox_sampler_statistics():
     assert abs(float(act.mean())) < 0.02 and abs(float(act.var()) - 1.0) < 0.02
     close(lp, (-0.5 * (act.double() ** 2).sum(-1) - 1.5 * np.log(2 * np.pi)).cpu().numpy())
     assert abs(float(en[0]) - 1.5 * (1 + np.log(2 * np.pi))) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- next rows: ACER / TRPO reuse
+def test_acer_retrace_bit_exact(golden):
+    g = golden('acer_retrace')
+    T, E = int(g['n_steps']), int(g['n_envs'])
+    tm = lambda flat, steps=T: np.ascontiguousarray(flat.reshape(E, steps).T)
+    values = tm(g['values'], T + 1)
+    dones = np.concatenate([np.zeros((1, E), np.float32), tm(g['dones'])])
+    got = ops.retrace_returns(cu(tm(g['rewards'])), cu(dones), cu(values[:-1]), cu(values[-1]), cu(tm(g['q_selected'])),
+                              cu(tm(g['importance'])), float(g['gamma']))
+    assert np.array_equal(got.cpu().numpy(), tm(g['returns']))
+    rng = np.random.default_rng(9)
+    for T, E in ((20, 4097), (1, 3), (333, 64)):
+        f = lambda *s: rng.standard_normal(s).astype(np.float32)
+        r, v, q, lv = f(T, E), f(T, E), f(T, E), f(E)
+        d = (rng.random((T + 1, E)) < 0.1).astype(np.float32)
+        imp = np.exp(f(T, E))
+        want = oracle.retrace_returns(r, d, v, lv, q, imp, 0.99)
+        got = ops.retrace_returns(cu(r), cu(d), cu(v), cu(lv), cu(q), cu(imp), 0.99)
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_trpo_whole_batch_advantage_normalisation():
+    """TRPO.train_step normalises over the WHOLE batch with no epsilon (xagents/trpo/agent.py:311-314):
+    same kernels, one moments row, eps = 0."""
+    ro = synthetic.make_rollout(64, 32, with_obs=False, epochs=0)
+    ret = oracle.gae_returns(ro.rewards, ro.dones, ro.values, ro.last_values, 0.99, 0.95)
+    adv = (ret - ro.values).reshape(-1)
+    want = (adv - adv.mean()) / adv.std()
+    got = ops.normalize_advantages(cu(ret.reshape(-1)), cu(ro.values.reshape(-1)), 0.0)
+    close(got, want)

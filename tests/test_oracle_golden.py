@@ -123,3 +123,15 @@ def test_closed_form_grads_match_autograd(is_probs):
     dl, dvv = oracle.a2c_loss_grads(actor, new_v, actions, old_v, ret, .01, .5, is_probs)
     np.testing.assert_allclose(dl, da, atol=1e-5 * np.abs(da).max())
     np.testing.assert_allclose(dvv, dv, atol=1e-5 * np.abs(dv).max())
+
+
+def test_acer_retrace_bit_exact_vs_reference_run(golden):
+    """ACER.calculate_returns run by the reference itself (flat env-major in/out) vs the time-major oracle."""
+    g = golden('acer_retrace')
+    T, E = int(g['n_steps']), int(g['n_envs'])
+    tm = lambda flat, steps=T: np.ascontiguousarray(flat.reshape(E, steps).T)
+    values = tm(g['values'], T + 1)
+    dones = np.concatenate([np.zeros((1, E), np.float32), tm(g['dones'])])     # row t+1 = flag after step t
+    got = oracle.retrace_returns(tm(g['rewards']), dones, values[:-1], values[-1], tm(g['q_selected']), tm(g['importance']),
+                                 float(g['gamma']))
+    assert np.array_equal(got, tm(g['returns']))

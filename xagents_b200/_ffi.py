@@ -48,6 +48,7 @@ PROTOTYPES = {
                                                   ctypes.c_int, c_stream]),
     'xa_nstep_returns_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                                             c_stream]),
+    'xa_retrace_f32': (ctypes.c_int, [c_f32p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, c_stream]),
     'xa_gather_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_stream]),
     'xa_gather_fields_f32': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,

@@ -168,6 +168,64 @@ __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const Scan
   }
 }
 
+// ACER Retrace targets (xagents/acer/agent.py:198-208): a reverse recurrence with an importance-weighted
+// correction, R_t = r_t + gamma*c*(1-d_{t+1}); out_t = R_t; c = min(1,rho_t)*(R_t - Q_t) + V_t.  One thread per
+// env walks T with the next group of steps already loaded (same prefetch idea as above); the arithmetic is the
+// reference's, operation for operation.  ACER rollouts are short (n_steps ~ 16-20), so T is not split.
+struct RetraceParams {
+  const float* rewards;
+  const float* dones;  // [T+1, E]
+  const float* values;
+  const float* last_values;
+  const float* q_selected;
+  const float* importance;
+  float* returns;
+  int n_steps, n_envs;
+  float gamma;
+};
+
+constexpr int kRetraceGroup = 4;
+
+struct RetraceRaw {
+  float rew[kRetraceGroup], done[kRetraceGroup], val[kRetraceGroup], q[kRetraceGroup], imp[kRetraceGroup];
+};
+
+__device__ __forceinline__ void load_retrace(RetraceRaw& r, const RetraceParams& p, int t1, int env) {
+  const size_t E = static_cast<size_t>(p.n_envs);
+#pragma unroll
+  for (int j = 0; j < kRetraceGroup; ++j) {
+    const int t = t1 - 1 - j > 0 ? t1 - 1 - j : 0;  // clamped: loaded and ignored past the front
+    const size_t o = static_cast<size_t>(t) * E + env;
+    r.rew[j] = p.rewards[o];
+    r.done[j] = p.dones[o + E];
+    r.val[j] = p.values[o];
+    r.q[j] = p.q_selected[o];
+    r.imp[j] = p.importance[o];
+  }
+}
+
+__global__ void __launch_bounds__(128) retrace_kernel(const RetraceParams p) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.n_envs) return;
+  const size_t E = static_cast<size_t>(p.n_envs);
+  float current = p.last_values[env];
+  RetraceRaw nxt;
+  load_retrace(nxt, p, p.n_steps, env);
+  for (int t1 = p.n_steps; t1 > 0; t1 -= kRetraceGroup) {
+    const RetraceRaw cur = nxt;
+    if (t1 - kRetraceGroup > 0) load_retrace(nxt, p, t1 - kRetraceGroup, env);
+#pragma unroll
+    for (int j = 0; j < kRetraceGroup; ++j) {
+      const int t = t1 - 1 - j;
+      if (t >= 0) {
+        current = __fadd_rn(cur.rew[j], __fmul_rn(__fmul_rn(p.gamma, current), __fsub_rn(1.0f, cur.done[j])));
+        p.returns[static_cast<size_t>(t) * E + env] = current;
+        current = __fadd_rn(__fmul_rn(fminf(1.0f, cur.imp[j]), __fsub_rn(current, cur.q[j])), cur.val[j]);
+      }
+    }
+  }
+}
+
 int pick_warps(int mode, int n_steps, int n_envs) {
   const int chunks = (n_steps + kChunk - 1) / kChunk;
   if (mode == XA_SCAN_SEQUENTIAL || chunks <= 1) return 1;
@@ -226,6 +284,17 @@ int xa_nstep_returns_f32(const float* rewards, const float* dones, const float* 
              XA_EALIGN, "xa_nstep_returns_f32: pointers must be 4-byte aligned");
   ScanParams p{rewards, nullptr, last_values, dones, returns, nullptr, n_steps, n_envs, static_cast<float>(gamma), 0.0f};
   return launch<true>(p, mode, static_cast<cudaStream_t>(stream), "xa_nstep_returns_f32");
+}
+
+int xa_retrace_f32(const float* rewards, const float* dones, const float* values, const float* last_values,
+                   const float* q_selected, const float* importance, float* returns, int n_steps, int n_envs, double gamma,
+                   xa_stream_t stream) {
+  if (int rc = check_shape("xa_retrace_f32", n_steps, n_envs, XA_SCAN_AUTO)) return rc;
+  XA_REQUIRE(rewards && dones && values && last_values && q_selected && importance && returns, XA_EINVAL,
+             "xa_retrace_f32: null pointer");
+  RetraceParams p{rewards, dones, values, last_values, q_selected, importance, returns, n_steps, n_envs, static_cast<float>(gamma)};
+  retrace_kernel<<<(n_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return xa::check_launch("xa_retrace_f32");
 }
 
 }  // extern "C"

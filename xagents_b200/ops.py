@@ -14,7 +14,7 @@ from ._dlpack import as_device_array
 from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_AUTO, XA_GATHER_BULK, XA_GATHER_VECTOR,
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
-__all__ = ['gae_returns', 'nstep_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
+__all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
            'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16',
            'launch_count', 'reset_launch_count']
 
@@ -96,6 +96,18 @@ def nstep_returns(rewards, dones, last_values, gamma, *, mode='auto', out=None, 
     ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=_device_of(r))
     _ffi.call('xa_nstep_returns_f32', _ptr(r), _ptr(d), _ptr(lv), _tptr(ret), T, E, float(gamma), SCAN_MODES[mode],
               _stream(stream))
+    _count()
+    return ret
+
+
+def retrace_returns(rewards, dones, values, last_values, q_selected, importance, gamma, *, out=None, stream=None):
+    """ACER.calculate_returns (Retrace) arithmetic (xagents/acer/agent.py:198-208), time-major [T,E] fields."""
+    arrs = [_dev(x, 'float32') for x in (rewards, dones, values, last_values, q_selected, importance)]
+    T, E = arrs[0].shape
+    if arrs[1].size != (T + 1) * E or arrs[3].size != E or any(a.size != T * E for a in (arrs[2], arrs[4], arrs[5])):
+        raise ValueError('shape mismatch: [T,E] fields, dones [T+1,E], last_values [E]')
+    ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=_device_of(arrs[0]))
+    _ffi.call('xa_retrace_f32', *[_ptr(a) for a in arrs], _tptr(ret), T, E, float(gamma), _stream(stream))
     _count()
     return ret
 
