@@ -1,0 +1,78 @@
+"""Implicit-GEMM convolution on tcgen05 against a plain torch fp32 reference of the same op on the same
+bf16-rounded operands (fp32 accumulation on both sides; the output is rounded to bf16 once)."""
+import pytest
+import torch
+
+from xagents_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def torch_conv_nhwc(x, w, kh, kw, bias, relu):
+    """x [B,H,W,C], w [N, kh*kw*C] (K ordered kh,kw,c) -> [B,OH,OW,N] in fp64."""
+    n, c = w.shape[0], x.shape[-1]
+    wt = w.double().reshape(n, kh, kw, c).permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wt, bias.double() if bias is not None else None)
+    y = y.permute(0, 2, 3, 1)
+    return y.clamp_min(0) if relu else y
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('B,H,W,C,kh,kw,N,s2d', [(7, 21, 21, 64, 2, 2, 32, True), (5, 10, 10, 128, 2, 2, 64, False),
+                                                 (9, 9, 9, 64, 3, 3, 64, False), (300, 21, 21, 64, 2, 2, 32, True),
+                                                 (1000, 10, 10, 128, 2, 2, 64, False), (1001, 9, 9, 64, 3, 3, 64, False),
+                                                 (3, 12, 17, 8, 1, 8, 96, False)])
+@pytest.mark.parametrize('bias,relu', [(True, True), (False, False)])
+def test_conv2d_nhwc_vs_torch(B, H, W, C, kh, kw, N, s2d, bias, relu):
+    g = torch.Generator(device=DEV)
+    g.manual_seed(B + H * 7 + N)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn((N, kh * kw * C), device=DEV, generator=g) / (kh * kw * C) ** 0.5).to(torch.bfloat16)
+    bv = torch.randn(N, device=DEV, generator=g) if bias else None
+    want = torch_conv_nhwc(x.float(), w.float(), kh, kw, bv, relu)
+    got = ops.conv2d_nhwc_bf16(x, w, kh, kw, bias=bv, relu=relu, out_s2d=s2d)
+    torch.cuda.synchronize()
+    OH, OW = H - kh + 1, W - kw + 1
+    if s2d:                                      # undo the space-to-depth layout of the output
+        got = got.reshape(B, OH // 2, OW // 2, 2, 2, N).permute(0, 1, 3, 2, 4, 5).reshape(B, OH, OW, N)
+    assert got.shape == want.shape
+    scale = float(want.abs().max())
+    err = float((got.double() - want).abs().max())
+    assert err <= 4e-3 * scale, f'max abs err {err:.3e} vs scale {scale:.3e}'      # one bf16 rounding of the output
+
+
+@pytest.mark.timeout(60)
+def test_space_to_depth_u8():
+    x = torch.randint(0, 256, (5, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    got = ops.space_to_depth_u8_bf16(x, 4)
+    want = (x.float() / 255.0).reshape(5, 21, 4, 21, 4, 4).permute(0, 1, 3, 2, 4, 5).reshape(5, 21, 21, 64).to(torch.bfloat16)
+    assert torch.equal(got, want)
+    got = ops.space_to_depth_u8_bf16(x, 2, scale_255=False)
+    want = x.float().reshape(5, 42, 2, 42, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(5, 42, 42, 16).to(torch.bfloat16)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('B', [3, 256, 1030])
+def test_nature_cnn_forward_on_tensor_cores_vs_torch(B):
+    from xagents_b200.agents import NatureCNN
+    from xagents_b200.agents.tc_conv import NatureCnnTcForward
+    torch.manual_seed(1)
+    net = NatureCNN(4, 6).cuda()
+    with torch.no_grad():                          # non-trivial biases and a head that is not ~0
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn_like(p) * 0.1)
+        net.actor.weight.mul_(50)
+    tc = NatureCnnTcForward(net)
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    actor, critic = tc(x)
+    with torch.no_grad():
+        ra, rc = net(x.float() / 255.0)
+    torch.cuda.synchronize()
+    assert actor.shape == (B, 6) and critic.shape == (B,)
+    for got, want in ((actor, ra), (critic, rc.reshape(-1))):
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        assert err <= 3e-2 * scale, f'{err:.3e} vs {scale:.3e}'        # five bf16 layers against fp32

@@ -1,0 +1,67 @@
+"""Forward pass of the Nature CNN entirely on the tcgen05 kernels (second slice).
+
+`NatureCnnTcForward` takes the weights of a `NatureCNN` (torch layout: conv [Cout, Cin, KH, KW], NCHW flatten)
+and re-lays them once for the implicit-GEMM convolution: NHWC kernels with K ordered (kh, kw, c), the two
+strided layers rewritten as stride-1 layers over space-to-depth inputs (8x8/4 -> 2x2/1 on 21x21x64,
+4x4/2 -> 2x2/1 on 10x10x128), the FC weight permuted from (c, h, w) to (h, w, c) flatten order (which is the
+order the reference's Keras Flatten uses on NHWC), both heads stacked into one [8, 512] matrix.
+
+    uint8 frames --xa_space_to_depth_u8_bf16 (/255)--> [B,21,21,64]
+      --xa_conv2d_nhwc_bf16 (2x2, ReLU, out_s2d)-->    [B,10,10,128]
+      --xa_conv2d_nhwc_bf16 (2x2, ReLU)-->             [B,9,9,64]
+      --xa_conv2d_nhwc_bf16 (3x3, ReLU)-->             [B,7,7,64] = [B,3136]
+      --xa_gemm_bf16_tn (ReLU)--> [B,512] --xa_gemm_bf16_tn--> logits [B,A], value [B]
+
+Inference only (rollout-time policy evaluation and the bootstrap value: T+1 of the T+1+K*M forward passes of a
+train step); the backward convolutions are not built yet, so training still differentiates the torch trunk.
+"""
+import torch
+
+from .. import ops
+
+
+def _s2d_kernel(w, s):
+    """torch conv weight [N, C, KH, KW] with stride s -> [N, (KH/s)*(KW/s)*(s*s*C)] for the stride-1 conv over the
+    space-to-depth input: K ordered (kh', kw', dy, dx, c)."""
+    n, c, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)                                           # [N, KH, KW, C]
+    w = w.reshape(n, kh // s, s, kw // s, s, c).permute(0, 1, 3, 2, 4, 5)   # [N, kh', kw', dy, dx, C]
+    return w.reshape(n, -1).contiguous()
+
+
+class NatureCnnTcForward:
+    def __init__(self, module):
+        self.module = module
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        """Re-derive the bf16 operand copies from the module's fp32 weights (after an optimiser step)."""
+        convs = [m for m in self.module.trunk if isinstance(m, torch.nn.Conv2d)]
+        fc = [m for m in self.module.trunk if hasattr(m, 'weight') and m.weight.dim() == 2][0]
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        self.w1, self.b1 = bf(_s2d_kernel(convs[0].weight, 4)), convs[0].bias.float().contiguous()
+        self.w2, self.b2 = bf(_s2d_kernel(convs[1].weight, 2)), convs[1].bias.float().contiguous()
+        self.w3, self.b3 = bf(convs[2].weight.permute(0, 2, 3, 1).reshape(64, -1)), convs[2].bias.float().contiguous()
+        wf = fc.weight.reshape(fc.weight.shape[0], 64, 7, 7).permute(0, 2, 3, 1).reshape(fc.weight.shape[0], -1)
+        self.wf, self.bf_ = bf(wf), fc.bias.float().contiguous()
+        a, c = self.module.actor, self.module.critic
+        heads = torch.zeros((8 * ((a.weight.shape[0] + 1 + 7) // 8), a.weight.shape[1]), device=a.weight.device)
+        heads[:a.weight.shape[0]] = a.weight
+        heads[a.weight.shape[0]] = c.weight[0]
+        hb = torch.zeros(heads.shape[0], device=a.weight.device)
+        hb[:a.weight.shape[0]] = a.bias
+        hb[a.weight.shape[0]] = c.bias[0]
+        self.wh, self.bh, self.n_actions = bf(heads), hb.contiguous(), a.weight.shape[0]
+        return self
+
+    @torch.no_grad()
+    def __call__(self, frames_u8):
+        """uint8 [B,84,84,4] -> (actor_out [B,A] fp32, critic [B] fp32)."""
+        x = ops.space_to_depth_u8_bf16(frames_u8.contiguous(), 4)
+        x = ops.conv2d_nhwc_bf16(x, self.w1, 2, 2, bias=self.b1, relu=True, out_s2d=True)
+        x = ops.conv2d_nhwc_bf16(x, self.w2, 2, 2, bias=self.b2, relu=True)
+        x = ops.conv2d_nhwc_bf16(x, self.w3, 3, 3, bias=self.b3, relu=True)
+        h = ops.gemm_bf16_tn(x.view(x.shape[0], -1), self.wf, bias=self.bf_, relu=True, out_dtype=torch.bfloat16)
+        out = ops.gemm_bf16_tn(h, self.wh, bias=self.bh, out_dtype=torch.float32)
+        return out[:, :self.n_actions].contiguous(), out[:, self.n_actions].contiguous()

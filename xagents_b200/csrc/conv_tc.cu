@@ -1,0 +1,297 @@
+// Stride-1 NHWC convolution as an implicit GEMM on the tensor cores (forward; the policy/value network's
+// convolutional trunk, ModelReader's conv sections: ppo/models/cnn-actor-critic.cfg:1-21, README.md:243-259).
+//
+// No im2col buffer exists.  For a fixed kernel row kh the (kw, c) run of an output pixel is CONTIGUOUS in an NHWC
+// activation, so operand A of the GEMM  Y[(b,y,x), n] = sum_k X_col[(b,y,x), k] W[n, k],  k = (kh, kw, c),  is
+// fetched by TMA straight from the activation through a rank-4 tensor map whose x-stride is C elements
+// (overlapping windows): box = (64 elements of the run, bx pixels along x, by rows, bb images) = up to 128
+// GEMM rows per tile.  Strided convolutions are turned into stride-1 ones by space-to-depth (8x8/4 on 84x84x4
+// becomes 2x2/1 on 21x21x64; 4x4/2 on 20x20x32 becomes 2x2/1 on 10x10x128), which xa_space_to_depth_u8_bf16 and
+// this kernel's epilogue (out_s2d) produce directly, together with bias + ReLU.
+// Same machinery as gemm_tc.cu: persistent CTAs, TMA producer warp, single-thread tcgen05.mma issuer, fp32
+// accumulators double-buffered in TMEM, four epilogue warps.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace xa_tc;
+
+struct ConvParams {
+  __nv_bfloat16* y;
+  const float* bias;
+  int B, H, W, C, KH, KW, N, OH, OW;
+  int bx, by, bb;  // tile box over (x, y, image)
+  int relu, out_s2d;
+};
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int kStageA = kBlockM * kBlockK * 2;
+  static constexpr int kStageB = BN * kBlockK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (160 * 1024) / kStage > 8 ? 8 : (160 * 1024) / kStage;
+  static constexpr int kBytes = kStages * kStage + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                             const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+  using S = ConvSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStage);
+  uint64_t* empty = full + S::kStages;
+  uint64_t* acc_full = empty + S::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int run = p.KW * p.C;                 // contiguous elements per kernel row
+  const int kc_blocks = run / kBlockK;        // 64-element K blocks per kernel row
+  const int k_blocks = p.KH * kc_blocks;
+  const int tiles_y = (p.OH + p.by - 1) / p.by;
+  const int tiles_b = (p.B + p.bb - 1) / p.bb;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles = tiles_y * tiles_b * tiles_n;
+  const int rows = p.bx * p.by * p.bb;        // GEMM rows actually filled per tile (<= 128)
+  constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccStride;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < S::kStages; ++s) {
+      xa::mbar_init(full + s, 1);
+      xa::mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      xa::mbar_init(acc_full + a, 1);
+      xa::mbar_init(acc_empty + a, 4);
+    }
+    xa::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n tile, image block, row block); images vary fastest so neighbouring CTAs share the weights in L2
+  auto decode = [&](int tile, int& tn, int& tb, int& ty) {
+    tb = tile % tiles_b;
+    ty = (tile / tiles_b) % tiles_y;
+    tn = tile / (tiles_b * tiles_y);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      uint32_t it = 0;
+      const uint32_t stage_bytes = static_cast<uint32_t>(rows) * 128u + S::kStageB;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int tn, tb, ty;
+        decode(tile, tn, tb, ty);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int kh = kb / kc_blocks, kc = kb - kh * kc_blocks;
+          const int s = it % S::kStages;
+          const uint32_t round = it / S::kStages;
+          if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+          uint8_t* a_dst = smem + s * S::kStage;
+          xa::mbar_expect_tx(full + s, stage_bytes);
+          tma_load_4d(a_dst, &map_x, kc * kBlockK, 0, ty * p.by + kh, tb * p.bb, full + s);
+          tma_load_2d(a_dst + S::kStageA, &map_w, kh * run + kc * kBlockK, tn * BN, full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      constexpr uint32_t idesc = make_idesc(kBlockM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1, use = lt >> 1;
+        if (use > 0) {
+          mbar_wait_wd(acc_empty + acc, (use - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % S::kStages;
+          mbar_wait_wd(full + s, (it / S::kStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem + s * S::kStage);
+          const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty + s);
+        }
+        umma_commit(acc_full + acc);
+      }
+    }
+  } else {
+    // ---- epilogue
+    const int quad = warp & 3;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      int tn, tb, ty;
+      decode(tile, tn, tb, ty);
+      const uint32_t acc = lt & 1;
+      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // GEMM row r of the tile = pixel (x, y, image) in box order (x fastest)
+      const int r = quad * 32 + lane;
+      const int ox = r % p.bx;
+      const int oy = ty * p.by + (r / p.bx) % p.by;
+      const int ob = tb * p.bb + r / (p.bx * p.by);
+      const bool valid = r < rows && oy < p.OH && ob < p.B;
+      int64_t out_off = 0;
+      if (valid) {
+        if (p.out_s2d)  // [B, OH/2, OW/2, 4N], channel block (oy%2, ox%2): the next layer's space-to-depth input
+          out_off = ((static_cast<int64_t>(ob) * (p.OH / 2) + oy / 2) * (p.OW / 2) + ox / 2) * (4 * p.N) + ((oy & 1) * 2 + (ox & 1)) * p.N;
+        else
+          out_off = ((static_cast<int64_t>(ob) * p.OH + oy) * p.OW + ox) * p.N;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
+        const int col0 = tn * BN + c0;
+        if (valid && col0 < p.N) {
+          uint4* dst = reinterpret_cast<uint4*>(p.y + out_off + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a = __uint_as_float(v[8 * j + 2 * q]), b = __uint_as_float(v[8 * j + 2 * q + 1]);
+              if (p.bias != nullptr) {
+                a += __ldg(p.bias + col0 + 8 * j + 2 * q);
+                b += __ldg(p.bias + col0 + 8 * j + 2 * q + 1);
+              }
+              if (p.relu) {
+                a = fmaxf(a, 0.0f);
+                b = fmaxf(b, 0.0f);
+              }
+              h[q] = __floats2bfloat162_rn(a, b);
+            }
+            dst[j] = *reinterpret_cast<uint4*>(h);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// uint8 NHWC frames -> bf16, scaled by 1/255 (true division in fp32, base.py:505-506), rearranged block x block
+// -> channels: out[b, y/s, x/s, (y%s, x%s, c)].  One thread per output pixel-channel group of 8.
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B,
+                                                              int H, int W, int C, int s, int scale) {
+  const int OH = H / s, OW = W / s, OC = s * s * C;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * OC;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(i % OC);
+    const int64_t pix = i / OC;
+    const int ox = static_cast<int>(pix % OW), oy = static_cast<int>((pix / OW) % OH);
+    const int64_t b = pix / (static_cast<int64_t>(OW) * OH);
+    const int c = oc % C, dx = (oc / C) % s, dy = oc / (C * s);
+    const float v = static_cast<float>(src[((b * H + oy * s + dy) * W + ox * s + dx) * C + c]);
+    dst[i] = __float2bfloat16_rn(scale ? __fdiv_rn(v, 255.0f) : v);
+  }
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, cudaStream_t stream, const char* what) {
+  auto kernel = conv_fwd_kernel<BN>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes);
+  if (e != cudaSuccess) {
+    xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  const int64_t tiles = static_cast<int64_t>((p.OH + p.by - 1) / p.by) * ((p.B + p.bb - 1) / p.bb) * ((p.N + BN - 1) / BN);
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  kernel<<<static_cast<unsigned>(tiles < sms ? tiles : sms), kThreads, ConvSmem<BN>::kBytes, stream>>>(mx, mw, p);
+  return xa::check_launch(what);
+}
+
+}  // namespace
+
+extern "C" {
+
+int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels,
+                        int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+  const char* what = "xa_conv2d_nhwc_bf16";
+  XA_REQUIRE(x && w && y, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && channels > 0 && kh > 0 && kw > 0 && n_out > 0, XA_EINVAL, "%s: bad shape", what);
+  XA_REQUIRE(channels % 8 == 0, XA_EALIGN, "%s: channels=%d must be a multiple of 8 (16-byte pixel pitch for TMA)", what, channels);
+  XA_REQUIRE((kw * channels) % kBlockK == 0, XA_EINVAL, "%s: kw*channels=%d must be a multiple of 64", what, kw * channels);
+  XA_REQUIRE(n_out % 32 == 0, XA_EINVAL, "%s: n_out=%d must be a multiple of 32", what, n_out);
+  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(w, 16) && xa::aligned(y, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
+  ConvParams p{};
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.bias = bias;
+  p.B = batch, p.H = height, p.W = width, p.C = channels, p.KH = kh, p.KW = kw, p.N = n_out;
+  p.OH = height - kh + 1, p.OW = width - kw + 1;
+  p.relu = relu, p.out_s2d = out_s2d;
+  XA_REQUIRE(p.OW <= kBlockM, XA_EINVAL, "%s: output width %d exceeds one tile (128)", what, p.OW);
+  XA_REQUIRE(!out_s2d || (p.OH % 2 == 0 && p.OW % 2 == 0), XA_EINVAL, "%s: out_s2d needs even output height/width", what);
+  // tile box: whole output rows (bx = OW), by rows (a divisor of OH), bb images; maximise filled GEMM rows <= 128
+  p.bx = p.OW;
+  int best = 0;
+  for (int by = 1; by <= p.OH; ++by) {
+    if (p.OH % by) continue;
+    for (int bb = 1; bb <= 16; ++bb) {
+      const int rows = p.bx * by * bb;
+      if (rows <= kBlockM && rows > best) best = rows, p.by = by, p.bb = bb;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+  CUtensorMap mx, mw;
+  {
+    // rank-4 view of the NHWC activation with overlapping windows along x: element (i, x, y, b) -> X[b, y, x*C + i]
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kw) * channels, static_cast<cuuint64_t>(p.OW), static_cast<cuuint64_t>(height),
+                                static_cast<cuuint64_t>(batch)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(channels) * 2, static_cast<cuuint64_t>(width) * channels * 2,
+                                   static_cast<cuuint64_t>(height) * width * channels * 2};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(p.bx), static_cast<cuuint32_t>(p.by),
+                               static_cast<cuuint32_t>(p.bb)};
+    const cuuint32_t elem[4] = {1, 1, 1, 1};
+    const CUresult r = fn(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, elem,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled(activation) failed with %d", what, static_cast<int>(r));
+  }
+  const int bn = n_out >= 64 ? 64 : 32;
+  if (int rc = make_map_2d(&mw, w, n_out, static_cast<int64_t>(kh) * kw * channels, bn, what)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 64 ? launch_conv<64>(mx, mw, p, s, what) : launch_conv<32>(mx, mw, p, s, what);
+}
+
+int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels, int block, int scale_255,
+                              xa_stream_t stream) {
+  XA_REQUIRE(src && dst, XA_EINVAL, "xa_space_to_depth_u8_bf16: null pointer");
+  XA_REQUIRE(batch > 0 && block > 0 && height % block == 0 && width % block == 0 && channels > 0, XA_EINVAL,
+             "xa_space_to_depth_u8_bf16: %dx%dx%d is not divisible into %dx%d blocks", height, width, channels, block, block);
+  const int64_t total = static_cast<int64_t>(batch) * height * width * channels;
+  const int64_t want = (total + 255) / 256;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t cap = static_cast<int64_t>(sms) * 32;
+  space_to_depth_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), batch, height, width, channels, block, scale_255);
+  return xa::check_launch("xa_space_to_depth_u8_bf16");
+}
+
+}  // extern "C"

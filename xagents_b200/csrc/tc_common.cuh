@@ -1,0 +1,129 @@
+// Shared pieces of the tcgen05 kernels (GEMM and implicit-GEMM convolution): mbarrier wait with a watchdog,
+// TMA tile loads, UMMA shared-memory / instruction descriptors, tcgen05.mma / commit / ld wrappers and the
+// host-side cuTensorMapEncodeTiled entry point.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "xa_common.cuh"
+
+namespace xa_tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kWatchdog = 1u << 28;
+
+
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = xa::smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (++spins > kWatchdog) __trap();  // a descriptor / barrier bug must fault, not hang the GPU
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          xa::smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(xa::smem_u32(bar))
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+// rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
+  const uint64_t addr = xa::smem_u32(tile);
+  uint64_t d = 0;
+  d |= (addr >> 4) & 0x3FFF;              // start address            [0,14)
+  d |= static_cast<uint64_t>(1) << 16;    // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset: 8 rows * 128 B  [32,46)
+  d |= static_cast<uint64_t>(1) << 46;    // descriptor version 1       [46,48)
+  d |= static_cast<uint64_t>(2) << 61;    // layout type SWIZZLE_128B   [61,64)
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(xa::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          xa::smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(xa::smem_u32(bar))
+      : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
+        status == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, k] -> tiles of box_rows x 64, 128-B swizzled; out-of-bounds reads give zeros
+inline int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int box_rows, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (rows=%lld k=%lld)", what, static_cast<int>(r),
+             static_cast<long long>(rows), static_cast<long long>(k));
+  return XA_OK;
+}
+
+}  // namespace xa_tc

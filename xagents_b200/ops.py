@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -411,3 +411,32 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
     _ffi.call('xa_to_bf16', _ptr(a), int(a.dtype == 'float32'), _tptr(dst), rows, cols, ld, int(transpose), _stream(stream))
     _count()
     return dst
+
+
+def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, stream=None):
+    """Stride-1 NHWC convolution on tcgen05 (implicit GEMM, no im2col).  x [B,H,W,C] bf16; w [N, kh*kw*C] bf16
+    with K ordered (kh, kw, c).  Returns y [B,OH,OW,N] bf16, or its 2x2 space-to-depth form [B,OH/2,OW/2,4N]."""
+    xx, ww = _dev(x, 'bfloat16'), _dev(w, 'bfloat16')
+    B, H, W, C = xx.shape
+    N = ww.shape[0]
+    if ww.shape[1] != kh * kw * C:
+        raise ValueError(f'weights {ww.shape} do not match kh*kw*C = {kh * kw * C}')
+    OH, OW = H - kh + 1, W - kw + 1
+    shape = (B, OH // 2, OW // 2, 4 * N) if out_s2d else (B, OH, OW, N)
+    y = out if out is not None else torch.empty(shape, dtype=torch.bfloat16, device=_device_of(xx))
+    bias_a = _dev(bias, 'float32') if bias is not None else None
+    _ffi.call('xa_conv2d_nhwc_bf16', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(bool(relu)),
+              int(bool(out_s2d)), _stream(stream))
+    _count()
+    return y
+
+
+def space_to_depth_u8_bf16(frames, block, *, scale_255=True, out=None, stream=None):
+    """uint8 [B,H,W,C] -> bf16 [B,H/s,W/s,s*s*C] (channel order dy, dx, c), optionally divided by 255."""
+    f = _dev(frames, 'uint8')
+    B, H, W, C = f.shape
+    y = out if out is not None else torch.empty((B, H // block, W // block, block * block * C), dtype=torch.bfloat16,
+                                                 device=_device_of(f))
+    _ffi.call('xa_space_to_depth_u8_bf16', _ptr(f), _tptr(y), B, H, W, C, block, int(bool(scale_255)), _stream(stream))
+    _count()
+    return y
