@@ -68,11 +68,22 @@ def test_nature_cnn_forward_on_tensor_cores_vs_torch(B):
     tc = NatureCnnTcForward(net)
     x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
     actor, critic = tc(x)
+    rb = lambda t: t.to(torch.bfloat16).float()                      # the same roundings the bf16 pipeline makes
     with torch.no_grad():
-        ra, rc = net(x.float() / 255.0)
+        ra, rc = net(x.float() / 255.0)                               # plain fp32 network
+        convs = [m for m in net.trunk if isinstance(m, torch.nn.Conv2d)]
+        fc = [m for m in net.trunk if isinstance(m, torch.nn.Linear)][0]
+        h = rb(x.float() / 255.0).permute(0, 3, 1, 2)
+        for conv in convs:
+            h = rb(torch.relu(torch.nn.functional.conv2d(h, rb(conv.weight), conv.bias, conv.stride)))
+        h = h.permute(0, 2, 3, 1).reshape(B, -1)                      # NHWC flatten
+        wf = fc.weight.reshape(512, 64, 7, 7).permute(0, 2, 3, 1).reshape(512, -1)
+        h = rb(torch.relu(h @ rb(wf).t() + fc.bias))
+        ea = h @ rb(net.actor.weight).t() + net.actor.bias
+        ec = (h @ rb(net.critic.weight).t() + net.critic.bias).reshape(-1)
     torch.cuda.synchronize()
     assert actor.shape == (B, 6) and critic.shape == (B,)
-    for got, want in ((actor, ra), (critic, rc.reshape(-1))):
-        scale = float(want.abs().max())
-        err = float((got - want).abs().max())
-        assert err <= 3e-2 * scale, f'{err:.3e} vs {scale:.3e}'        # five bf16 layers against fp32
+    for got, emu, ref in ((actor, ea, ra), (critic, ec, rc.reshape(-1))):
+        scale = float(ref.abs().max())
+        assert float((got - emu).abs().max()) <= 2e-2 * scale          # same roundings; summation order can flip a bf16 tie
+        assert float((got - ref).abs().max()) <= 8e-2 * scale          # five bf16 layers against the fp32 network
