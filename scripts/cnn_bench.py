@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Nature CNN forward: tcgen05 pipeline (NatureCnnTcForward) vs torch/cuDNN in fp32(TF32 off), bf16 autocast and channels_last."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from xagents_b200 import ops  # noqa: E402
+from xagents_b200.agents import NatureCNN  # noqa: E402
+from xagents_b200.agents.tc_conv import NatureCnnTcForward  # noqa: E402
+
+dev = 'cuda:0'
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+net = NatureCNN(4, 6).cuda()
+tc = NatureCnnTcForward(net)
+FLOP = 18.7e6 * 2 / 2          # 18.7 MFLOP forward per sample
+print('| batch | ours us | ours TFLOP/s | torch fp32 us | torch bf16 autocast us | bf16 channels_last us |')
+print('|---|---|---|---|---|---|')
+for B in (256, 2048, 8192):
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=dev)
+    t_ours = timeit(lambda: tc(x))
+    with torch.no_grad():
+        xf = x.float() / 255.0
+        t_fp32 = timeit(lambda: net(xf))
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            t_bf16 = timeit(lambda: net(xf))
+        net_cl = net.to(memory_format=torch.channels_last)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            t_cl = timeit(lambda: net_cl(xf))
+    print(f'| {B} | {t_ours:.0f} | {18.7e6 * B / t_ours / 1e6:.0f} | {t_fp32:.0f} | {t_bf16:.0f} | {t_cl:.0f} |')
+# per layer (B = 8192)
+B = 8192
+x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=dev)
+x1 = ops.space_to_depth_u8_bf16(x, 4)
+t0 = timeit(lambda: ops.space_to_depth_u8_bf16(x, 4))
+x2 = ops.conv2d_nhwc_bf16(x1, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True)
+t1 = timeit(lambda: ops.conv2d_nhwc_bf16(x1, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True))
+x3 = ops.conv2d_nhwc_bf16(x2, tc.w2, 2, 2, bias=tc.b2, relu=True)
+t2 = timeit(lambda: ops.conv2d_nhwc_bf16(x2, tc.w2, 2, 2, bias=tc.b2, relu=True))
+x4 = ops.conv2d_nhwc_bf16(x3, tc.w3, 3, 3, bias=tc.b3, relu=True)
+t3 = timeit(lambda: ops.conv2d_nhwc_bf16(x3, tc.w3, 3, 3, bias=tc.b3, relu=True))
+t4 = timeit(lambda: ops.gemm_bf16_tn(x4.view(B, -1), tc.wf, bias=tc.bf_, relu=True, out_dtype=torch.bfloat16))
+print(f'\nper layer at B={B} (us): space-to-depth {t0:.0f}, conv1 {t1:.0f} ({2*B*400*256*32/t1/1e6:.0f} TFLOP/s), '
+      f'conv2 {t2:.0f} ({2*B*81*512*64/t2/1e6:.0f}), conv3 {t3:.0f} ({2*B*49*576*64/t3/1e6:.0f}), fc {t4:.0f} ({2*B*3136*512/t4/1e6:.0f})')

@@ -87,3 +87,35 @@ def test_nature_cnn_forward_on_tensor_cores_vs_torch(B):
         scale = float(ref.abs().max())
         assert float((got - emu).abs().max()) <= 2e-2 * scale          # same roundings; summation order can flip a bf16 tie
         assert float((got - ref).abs().max()) <= 8e-2 * scale          # five bf16 layers against the fp32 network
+
+
+@pytest.mark.timeout(180)
+def test_agent_rollout_uses_tensor_core_inference():
+    """PPO.fit with rollout-time policy evaluation on the tcgen05 pipeline and training through torch autograd."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    from xagents_b200.agents import PPO, NatureCNN, TorchModel
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    T, E, A = 8, 4, 6
+    rng = np.random.default_rng(7)
+    obs, rewards, dones, resets = mg._streams(rng, 4 * T, E, (84, 84, 4), True, 0.1)
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+    torch.manual_seed(0)
+    net = TorchModel(NatureCNN(4, A).cuda(), tensor_core_inference=True)
+    before = ops.launch_count()
+    agent = PPO(envs, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=3)
+    agent.fit(max_steps=2 * T * E)
+    torch.cuda.synchronize()
+    assert agent.steps == 2 * T * E and torch.isfinite(net.flat_param).all()
+    assert ops.launch_count() - before > 2 * (T + 1) * 6            # 6 tensor-core launches per rollout forward
+    # the bf16 inference path and the fp32 training path agree on the rollout's values
+    x = torch.as_tensor(obs[:, 0]).cuda()
+    _, v_tc = net.forward(x, training=False)
+    net._tc_forward, keep = None, net._tc_forward
+    _, v_ref = net.forward(x, training=False)
+    net._tc_forward = keep
+    assert float((v_tc - v_ref).abs().max()) <= 8e-2 * float(v_ref.abs().max()) + 1e-3

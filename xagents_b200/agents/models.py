@@ -22,7 +22,7 @@ from .. import ops
 
 class TorchModel:
     def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
-                 comm=None):
+                 comm=None, tensor_core_inference=False):
         self.module = module
         self.output_is_softmax = output_is_softmax
         self.img_inputs = img_inputs
@@ -52,8 +52,17 @@ class TorchModel:
         self._refreshable = [m for m in module.modules() if hasattr(m, 'refresh')]
         for mod in self._refreshable:
             mod.refresh()
+        # rollout-time policy evaluation (no grad) through the tcgen05 convolution + GEMM pipeline
+        self._tc_forward = None
+        if tensor_core_inference:
+            from .tc_conv import NatureCnnTcForward
+            assert isinstance(module, NatureCNN), 'tensor_core_inference is implemented for NatureCNN'
+            self._tc_forward = NatureCnnTcForward(module)
+            self._refreshable.append(self._tc_forward)
 
     def forward(self, states, training=True):
+        if not training and self._tc_forward is not None and states.dtype == torch.uint8:
+            return self._tc_forward(states)
         x = states
         scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
         if x.dtype != torch.float32:
