@@ -181,15 +181,16 @@ int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* nois
 int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n,
                     int64_t k, int64_t ldc, int out_bf16, int relu, xa_stream_t stream);
 
-/* Stride-1 NHWC convolution, forward, as an implicit GEMM on tcgen05 (no im2col buffer: TMA fetches operand rows
- * from the activation through a rank-4 overlapping-window tensor map): the network's convolutional trunk
- * (ppo/models/cnn-actor-critic.cfg:1-21) after space-to-depth turns its strided layers into stride-1 ones.
- * x [B,H,W,C] bf16, w [n_out, kh*kw*C] bf16 with K ordered (kh, kw, c), y [B,OH,OW,n_out] bf16 -- or, with
- * out_s2d, [B,OH/2,OW/2,4*n_out] with channel block (oy%2, ox%2), i.e. the next layer's space-to-depth input.
- * Needs C % 8 == 0, kw*C % 64 == 0, n_out % 32 == 0, OW <= 128. */
+/* Stride-1 NHWC convolution as an implicit GEMM on tcgen05 (no im2col buffer: per kernel tap TMA fetches the
+ * shifted box of the activation, zero-filled outside the image): the network's convolutional trunk
+ * (ppo/models/cnn-actor-critic.cfg:1-21) after space-to-depth turns its strided layers into stride-1 ones, and,
+ * with pad = k-1 and flipped weights, its data-gradient (relu_mask, output layout, applies the ReLU derivative of
+ * the layer below).  x [B,H,W,C] bf16, w [n_out, kh*kw*C] bf16 with K ordered (kh, kw, c), y [B,OH,OW,n_out] bf16
+ * -- or, with out_s2d, [B,OH/2,OW/2,4*n_out] with channel block (oy%2, ox%2), the next layer's space-to-depth
+ * input.  Needs C % 64 == 0, n_out % 32 == 0, OW <= 128. */
 int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int batch, int height,
-                        int width, int channels, int kh, int kw, int n_out, int relu, int out_s2d,
-                        xa_stream_t stream);
+                        int width, int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu,
+                        int out_s2d, const void* relu_mask, xa_stream_t stream);
 /* uint8 NHWC frames -> bf16 (optionally /255, xagents/base.py:505-506) rearranged block x block -> channels:
  * dst[b, y/s, x/s, (y%s, x%s, c)]. */
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,

@@ -22,7 +22,7 @@ def torch_conv_nhwc(x, w, kh, kw, bias, relu):
 @pytest.mark.parametrize('B,H,W,C,kh,kw,N,s2d', [(7, 21, 21, 64, 2, 2, 32, True), (5, 10, 10, 128, 2, 2, 64, False),
                                                  (9, 9, 9, 64, 3, 3, 64, False), (300, 21, 21, 64, 2, 2, 32, True),
                                                  (1000, 10, 10, 128, 2, 2, 64, False), (1001, 9, 9, 64, 3, 3, 64, False),
-                                                 (3, 12, 17, 8, 1, 8, 96, False)])
+                                                 (3, 12, 17, 64, 1, 3, 96, False)])
 @pytest.mark.parametrize('bias,relu', [(True, True), (False, False)])
 def test_conv2d_nhwc_vs_torch(B, H, W, C, kh, kw, N, s2d, bias, relu):
     g = torch.Generator(device=DEV)
@@ -40,6 +40,35 @@ def test_conv2d_nhwc_vs_torch(B, H, W, C, kh, kw, N, s2d, bias, relu):
     scale = float(want.abs().max())
     err = float((got.double() - want).abs().max())
     assert err <= 4e-3 * scale, f'max abs err {err:.3e} vs scale {scale:.3e}'      # one bf16 rounding of the output
+
+
+def flip_for_dgrad(w, kh, kw, c):
+    """forward weights [N, kh*kw*C] -> data-gradient weights [C, kh*kw*N]: W'[c, kh', kw', n] = W[n, KH-1-kh', KW-1-kw', c]."""
+    n = w.shape[0]
+    return w.reshape(n, kh, kw, c).flip(1, 2).permute(3, 1, 2, 0).reshape(c, kh * kw * n).contiguous()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('B,H,W,C,kh,kw,N', [(5, 9, 9, 64, 3, 3, 64), (700, 9, 9, 64, 3, 3, 64), (6, 10, 10, 128, 2, 2, 64),
+                                             (513, 10, 10, 128, 2, 2, 64)])
+@pytest.mark.parametrize('masked', [False, True])
+def test_conv_data_gradient_vs_autograd(B, H, W, C, kh, kw, N, masked):
+    """dX of a stride-1 convolution = the same kernel on dY with full zero padding and flipped weights; the ReLU
+    derivative of the layer below rides in the epilogue."""
+    g = torch.Generator(device=DEV)
+    g.manual_seed(B + C)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn((N, kh * kw * C), device=DEV, generator=g) / (kh * kw * C) ** 0.5).to(torch.bfloat16)
+    OH, OW = H - kh + 1, W - kw + 1
+    dy = torch.randn((B, OH, OW, N), device=DEV, generator=g).to(torch.bfloat16)
+    xr = x.double().requires_grad_(True)
+    yr = torch_conv_nhwc(torch.relu(xr) if masked else xr, w.float(), kh, kw, None, False)
+    yr.backward(dy.double())
+    got = ops.conv2d_nhwc_bf16(dy, flip_for_dgrad(w, kh, kw, C), kh, kw, pad=(kh - 1, kw - 1), relu_mask=x if masked else None)
+    torch.cuda.synchronize()
+    assert got.shape == (B, H, W, C)
+    scale = float(xr.grad.abs().max())
+    assert float((got.double() - xr.grad).abs().max()) <= 4e-3 * scale
 
 
 @pytest.mark.timeout(60)

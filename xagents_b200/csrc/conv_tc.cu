@@ -1,11 +1,12 @@
 // Stride-1 NHWC convolution as an implicit GEMM on the tensor cores (forward; the policy/value network's
 // convolutional trunk, ModelReader's conv sections: ppo/models/cnn-actor-critic.cfg:1-21, README.md:243-259).
 //
-// No im2col buffer exists.  For a fixed kernel row kh the (kw, c) run of an output pixel is CONTIGUOUS in an NHWC
-// activation, so operand A of the GEMM  Y[(b,y,x), n] = sum_k X_col[(b,y,x), k] W[n, k],  k = (kh, kw, c),  is
-// fetched by TMA straight from the activation through a rank-4 tensor map whose x-stride is C elements
-// (overlapping windows): box = (64 elements of the run, bx pixels along x, by rows, bb images) = up to 128
-// GEMM rows per tile.  Strided convolutions are turned into stride-1 ones by space-to-depth (8x8/4 on 84x84x4
+// No im2col buffer exists.  Operand A of the GEMM  Y[(b,y,x), n] = sum_k X_col[(b,y,x), k] W[n, k],  k = (kh, kw, c),
+// is fetched by TMA straight from the NHWC activation: one K block = 64 channels of ONE kernel tap (kh, kw), i.e.
+// the box (64 channels, bx pixels along x, by rows, bb images) of the rank-4 tensor shifted by the tap -- up to
+// 128 GEMM rows per tile.  Coordinates that fall outside the image are zero-filled by TMA, which is how padding
+// works; with full padding and flipped weights the same kernel is the data-gradient convolution (then `mask`
+// applies the previous layer's ReLU derivative in the epilogue).  Strided convolutions are turned into stride-1 ones by space-to-depth (8x8/4 on 84x84x4
 // becomes 2x2/1 on 21x21x64; 4x4/2 on 20x20x32 becomes 2x2/1 on 10x10x128), which xa_space_to_depth_u8_bf16 and
 // this kernel's epilogue (out_s2d) produce directly, together with bias + ReLU.
 // Same machinery as gemm_tc.cu: persistent CTAs, TMA producer warp, single-thread tcgen05.mma issuer, fp32
@@ -22,6 +23,8 @@ struct ConvParams {
   int B, H, W, C, KH, KW, N, OH, OW;
   int bx, by, bb;  // tile box over (x, y, image)
   int relu, out_s2d;
+  int pad_y, pad_x;
+  const __nv_bfloat16* mask;  // optional, output layout: result *= (mask > 0)
 };
 
 template <int BN>
@@ -47,9 +50,8 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int run = p.KW * p.C;                 // contiguous elements per kernel row
-  const int kc_blocks = run / kBlockK;        // 64-element K blocks per kernel row
-  const int k_blocks = p.KH * kc_blocks;
+  const int kc_blocks = p.C / kBlockK;        // 64-channel K blocks per kernel tap
+  const int k_blocks = p.KH * p.KW * kc_blocks;
   const int tiles_y = (p.OH + p.by - 1) / p.by;
   const int tiles_b = (p.B + p.bb - 1) / p.bb;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -96,14 +98,15 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
         int tn, tb, ty;
         decode(tile, tn, tb, ty);
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int kh = kb / kc_blocks, kc = kb - kh * kc_blocks;
+          const int tap = kb / kc_blocks, kc = kb - tap * kc_blocks;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
           const int s = it % S::kStages;
           const uint32_t round = it / S::kStages;
           if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
           uint8_t* a_dst = smem + s * S::kStage;
           xa::mbar_expect_tx(full + s, stage_bytes);
-          tma_load_4d(a_dst, &map_x, kc * kBlockK, 0, ty * p.by + kh, tb * p.bb, full + s);
-          tma_load_2d(a_dst + S::kStageA, &map_w, kh * run + kc * kBlockK, tn * BN, full + s);
+          tma_load_4d(a_dst, &map_x, kc * kBlockK, kw - p.pad_x, ty * p.by + kh - p.pad_y, tb * p.bb, full + s);
+          tma_load_2d(a_dst + S::kStageA, &map_w, kb * kBlockK, tn * BN, full + s);
         }
       }
     }
@@ -161,9 +164,13 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
         const int col0 = tn * BN + c0;
         if (valid && col0 < p.N) {
           uint4* dst = reinterpret_cast<uint4*>(p.y + out_off + col0);
+          const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(p.mask + out_off + col0) : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 h[4];
+            uint4 mraw = make_uint4(0, 0, 0, 0);
+            if (msk) mraw = __ldg(msk + j);
+            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float a = __uint_as_float(v[8 * j + 2 * q]), b = __uint_as_float(v[8 * j + 2 * q + 1]);
@@ -174,6 +181,10 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
               if (p.relu) {
                 a = fmaxf(a, 0.0f);
                 b = fmaxf(b, 0.0f);
+              }
+              if (msk) {  // ReLU derivative of the layer below
+                if (!(__low2float(mk[q]) > 0.0f)) a = 0.0f;
+                if (!(__high2float(mk[q]) > 0.0f)) b = 0.0f;
               }
               h[q] = __floats2bfloat162_rn(a, b);
             }
@@ -265,22 +276,28 @@ int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& 
 extern "C" {
 
 int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels,
-                        int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+                        int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_s2d, const void* relu_mask,
+                        xa_stream_t stream) {
   const char* what = "xa_conv2d_nhwc_bf16";
   XA_REQUIRE(x && w && y, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && channels > 0 && kh > 0 && kw > 0 && n_out > 0, XA_EINVAL, "%s: bad shape", what);
-  XA_REQUIRE(channels % 8 == 0, XA_EALIGN, "%s: channels=%d must be a multiple of 8 (16-byte pixel pitch for TMA)", what, channels);
-  XA_REQUIRE((kw * channels) % kBlockK == 0, XA_EINVAL, "%s: kw*channels=%d must be a multiple of 64", what, kw * channels);
+  XA_REQUIRE(batch > 0 && channels > 0 && kh > 0 && kw > 0 && n_out > 0 && pad_y >= 0 && pad_x >= 0 && pad_y < kh && pad_x < kw,
+             XA_EINVAL, "%s: bad shape", what);
+  XA_REQUIRE(height + 2 * pad_y >= kh && width + 2 * pad_x >= kw, XA_EINVAL, "%s: kernel larger than the padded image", what);
+  XA_REQUIRE(channels % kBlockK == 0, XA_EINVAL, "%s: channels=%d must be a multiple of 64 (one K block per tap)", what, channels);
   XA_REQUIRE(n_out % 32 == 0, XA_EINVAL, "%s: n_out=%d must be a multiple of 32", what, n_out);
-  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(w, 16) && xa::aligned(y, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
+  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(w, 16) && xa::aligned(y, 16) && xa::aligned(relu_mask, 16), XA_EALIGN,
+             "%s: 16-byte alignment required", what);
   ConvParams p{};
   p.y = static_cast<__nv_bfloat16*>(y);
   p.bias = bias;
   p.B = batch, p.H = height, p.W = width, p.C = channels, p.KH = kh, p.KW = kw, p.N = n_out;
-  p.OH = height - kh + 1, p.OW = width - kw + 1;
+  p.pad_y = pad_y, p.pad_x = pad_x;
+  p.OH = height + 2 * pad_y - kh + 1, p.OW = width + 2 * pad_x - kw + 1;
   p.relu = relu, p.out_s2d = out_s2d;
+  p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
   XA_REQUIRE(p.OW <= kBlockM, XA_EINVAL, "%s: output width %d exceeds one tile (128)", what, p.OW);
-  XA_REQUIRE(!out_s2d || (p.OH % 2 == 0 && p.OW % 2 == 0), XA_EINVAL, "%s: out_s2d needs even output height/width", what);
+  XA_REQUIRE(!out_s2d || (p.OH % 2 == 0 && p.OW % 2 == 0 && relu_mask == nullptr), XA_EINVAL,
+             "%s: out_s2d needs even output height/width and no mask", what);
   // tile box: whole output rows (bx = OW), by rows (a divisor of OH), bb images; maximise filled GEMM rows <= 128
   p.bx = p.OW;
   int best = 0;
@@ -295,8 +312,8 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
   XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
   CUtensorMap mx, mw;
   {
-    // rank-4 view of the NHWC activation with overlapping windows along x: element (i, x, y, b) -> X[b, y, x*C + i]
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kw) * channels, static_cast<cuuint64_t>(p.OW), static_cast<cuuint64_t>(height),
+    // the NHWC activation as a rank-4 tensor (c, x, y, b); boxes shifted by the kernel tap, zero-filled outside
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height),
                                 static_cast<cuuint64_t>(batch)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(channels) * 2, static_cast<cuuint64_t>(width) * channels * 2,
                                    static_cast<cuuint64_t>(height) * width * channels * 2};

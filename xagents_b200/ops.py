@@ -413,20 +413,24 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
     return dst
 
 
-def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, stream=None):
+def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=(0, 0), relu_mask=None, out=None, stream=None):
     """Stride-1 NHWC convolution on tcgen05 (implicit GEMM, no im2col).  x [B,H,W,C] bf16; w [N, kh*kw*C] bf16
-    with K ordered (kh, kw, c).  Returns y [B,OH,OW,N] bf16, or its 2x2 space-to-depth form [B,OH/2,OW/2,4N]."""
+    with K ordered (kh, kw, c); zero padding `pad`=(py, px).  Returns y [B,OH,OW,N] bf16, or its 2x2
+    space-to-depth form [B,OH/2,OW/2,4N].  `relu_mask` (same layout as y) zeroes y where mask <= 0."""
     xx, ww = _dev(x, 'bfloat16'), _dev(w, 'bfloat16')
     B, H, W, C = xx.shape
     N = ww.shape[0]
     if ww.shape[1] != kh * kw * C:
         raise ValueError(f'weights {ww.shape} do not match kh*kw*C = {kh * kw * C}')
-    OH, OW = H - kh + 1, W - kw + 1
+    OH, OW = H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1
     shape = (B, OH // 2, OW // 2, 4 * N) if out_s2d else (B, OH, OW, N)
     y = out if out is not None else torch.empty(shape, dtype=torch.bfloat16, device=_device_of(xx))
     bias_a = _dev(bias, 'float32') if bias is not None else None
-    _ffi.call('xa_conv2d_nhwc_bf16', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(bool(relu)),
-              int(bool(out_s2d)), _stream(stream))
+    mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
+    if mask_a is not None and mask_a.size != y.numel():
+        raise ValueError('relu_mask must have the output layout')
+    _ffi.call('xa_conv2d_nhwc_bf16', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
+              int(bool(relu)), int(bool(out_s2d)), _ptr(mask_a), _stream(stream))
     _count()
     return y
 
