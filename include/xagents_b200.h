@@ -179,7 +179,11 @@ int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* nois
  * B = weights) and, on transposed copies, both backward products.  A, B row-major with K contiguous,
  * 16-B aligned, K % 8 == 0; C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (1). */
 int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n,
-                    int64_t k, int64_t ldc, int out_bf16, int relu, xa_stream_t stream);
+                    int64_t k, int64_t ldc, int out_bf16, int relu, const void* relu_mask, void* workspace,
+                    int64_t workspace_bytes, xa_stream_t stream);
+/* Scratch for split-K (few output tiles, long K: the weight-gradient products); 0 when the shape does not split.
+ * Passing workspace = NULL simply disables splitting.  relu_mask: optional bf16 [m, ldc], c *= (mask > 0). */
+int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
 /* Stride-1 NHWC convolution as an implicit GEMM on tcgen05 (no im2col buffer: per kernel tap TMA fetches the
  * shifted box of the activation, zero-filled outside the image): the network's convolutional trunk

@@ -98,3 +98,34 @@ def test_nature_cnn_with_tensor_core_dense_trains():
     net.backward_and_step(torch.randn_like(actor) / 256, torch.randn_like(critic) / 256, grad_norm=0.5)
     torch.cuda.synchronize()
     assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('m,n,k', [(512, 3136, 8192), (64, 576, 401408), (32, 256, 40000), (8, 512, 8192)])
+def test_gemm_split_k_matches_unsplit_and_reference(m, n, k):
+    """Weight-gradient shapes: few output tiles, long K -> split along K over the SMs + deterministic reduction."""
+    from xagents_b200 import _ffi
+    g = torch.Generator(device=DEV)
+    g.manual_seed(k)
+    a = torch.randn((m, k), device=DEV, generator=g).to(torch.bfloat16)
+    b = (torch.randn((n, k), device=DEV, generator=g) / k ** 0.5).to(torch.bfloat16)
+    assert _ffi.lib().xa_gemm_workspace_bytes(m, n, k) > 0
+    split = ops.gemm_bf16_tn(a, b)
+    again = ops.gemm_bf16_tn(a, b)
+    plain = ops.gemm_bf16_tn(a, b, split_k=False)
+    torch.cuda.synchronize()
+    assert torch.equal(split, again)                               # deterministic
+    want = a.double() @ b.double().t()
+    scale = float(want.abs().max())
+    assert float((split.double() - want).abs().max()) <= 2e-5 * scale
+    assert float((plain.double() - want).abs().max()) <= 2e-5 * scale
+
+
+@pytest.mark.timeout(60)
+def test_gemm_relu_mask_epilogue():
+    a = torch.randn((300, 512), device=DEV).to(torch.bfloat16)
+    b = torch.randn((200, 512), device=DEV).to(torch.bfloat16)
+    mask = torch.randn((300, 200), device=DEV).to(torch.bfloat16)
+    got = ops.gemm_bf16_tn(a, b, relu_mask=mask)
+    want = (a.double() @ b.double().t()) * (mask > 0)
+    assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())

@@ -68,7 +68,9 @@ PROTOTYPES = {
     'xa_a2c_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),
     'xa_policy_step_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_uint64, ctypes.c_uint64, c_f32p, c_f32p, c_f32p,
                                           ctypes.c_int64, ctypes.c_int, c_stream]),
-    'xa_gemm_bf16_tn': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, c_stream]),
+    'xa_gemm_bf16_tn': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                                                                ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_conv2d_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                             [ctypes.c_void_p, c_stream]),
     'xa_space_to_depth_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [c_stream]),

@@ -29,6 +29,10 @@ struct GemmParams {
   const float* bias;
   int64_t m, n, k, ldc;
   int relu;
+  int splits;                  // > 1: split-K, fp32 partial tiles go to `partial` [splits, m, n]
+  int kb_per_split;
+  float* partial;
+  const __nv_bfloat16* mask;   // optional [m, ldc]: result *= (mask > 0)  (ReLU derivative in a backward product)
 };
 
 template <int BN>
@@ -58,6 +62,7 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
   const int tiles_m = static_cast<int>((p.m + kBlockM - 1) / kBlockM);
   const int tiles_n = static_cast<int>((p.n + BN - 1) / BN);
   const int n_tiles = tiles_m * tiles_n;
+  const int n_items = n_tiles * p.splits;  // (tile, K split) pairs; tile varies fastest
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;  // the epilogue reads 32 columns at a time
   constexpr uint32_t kTmemCols = 2 * kAccStride;      // two accumulators
 
@@ -87,9 +92,11 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item % n_tiles, split = item / n_tiles;
         const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S::kStages;
           const uint32_t round = it / S::kStages;
           if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
@@ -105,14 +112,16 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+        const int split = item / n_tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         const uint32_t acc = lt & 1, use = lt >> 1;
         if (use > 0) {  // the epilogue must have drained this accumulator
           mbar_wait_wd(acc_empty + acc, (use - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S::kStages;
           mbar_wait_wd(full + s, (it / S::kStages) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
           umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
         }
@@ -133,7 +142,8 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
     const int quad = warp & 3;
     const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16);
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+      const int tile = item % n_tiles, split = item / n_tiles;
       const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
       const uint32_t acc = lt & 1;
       mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
@@ -144,6 +154,13 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
         const int64_t col0 = static_cast<int64_t>(tile_n) * BN + c0;
+        if (p.splits > 1) {  // raw fp32 partial tile; bias / ReLU / conversion happen in the reduction pass
+          if (row < p.m && col0 < p.n) {
+            float* dstp = p.partial + (static_cast<int64_t>(split) * p.m + row) * p.n + col0;
+            for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
         if (row < p.m && col0 < p.n) {
           float f[32];
 #pragma unroll
@@ -151,6 +168,7 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
             float x = __uint_as_float(v[j]);
             if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
             if (p.relu) x = fmaxf(x, 0.0f);
+            if (p.mask != nullptr && col0 + j < p.n && !(__bfloat162float(p.mask[row * p.ldc + col0 + j]) > 0.0f)) x = 0.0f;
             f[j] = x;
           }
           if (vec_ok && col0 + 32 <= p.n) {
@@ -192,6 +210,24 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------- host
+// split-K second pass: C = sum_s partial[s] (+ bias) (ReLU), in split order -> deterministic
+template <bool kOutBf16>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
+  const int64_t total = p.m * p.n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / p.n, col = i - row * p.n;
+    float acc = 0.0f;
+    for (int s = 0; s < p.splits; ++s) acc += p.partial[static_cast<int64_t>(s) * total + i];
+    if (p.bias != nullptr) acc += p.bias[col];
+    if (p.relu) acc = fmaxf(acc, 0.0f);
+    if (kOutBf16)
+      static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + col] = __float2bfloat16_rn(acc);
+    else
+      static_cast<float*>(p.c)[row * p.ldc + col] = acc;
+  }
+}
+
 template <int BN, bool kOutBf16>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
   auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16>;
@@ -200,17 +236,44 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
     xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     return static_cast<int>(e);
   }
-  const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN);
+  const int64_t items = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN) * p.splits;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);  // persistent: at most one CTA per SM
+  const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);  // persistent: at most one CTA per SM
   kernel<<<grid, kThreads, Smem<BN>::kBytes, stream>>>(ma, mb, p);
-  return xa::check_launch(what);
+  if (int rc = xa::check_launch(what)) return rc;
+  if (p.splits > 1) {
+    const int64_t want = (p.m * p.n + 255) / 256;
+    splitk_reduce_kernel<kOutBf16><<<static_cast<unsigned>(want < 4096 ? want : 4096), 256, 0, stream>>>(p);
+    return xa::check_launch(what);
+  }
+  return XA_OK;
 }
 
 }  // namespace
 
+static int gemm_tile_n(int64_t n) { return n >= 256 ? 256 : (n > 64 ? 128 : (n > 16 ? 64 : 16)); }
+
+// K splits for shapes that would otherwise leave most SMs idle (few output tiles, long K: the weight-gradient
+// products).  0 = no split.
+static int gemm_auto_splits(int64_t m, int64_t n, int64_t k) {
+  const int bn = gemm_tile_n(n);
+  const int64_t tiles = ((m + kBlockM - 1) / kBlockM) * ((n + bn - 1) / bn);
+  const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  if (tiles * 2 > sms || k_blocks < 32) return 1;
+  int64_t splits = (sms + tiles - 1) / tiles;
+  if (splits > k_blocks / 8) splits = k_blocks / 8;
+  return splits < 2 ? 1 : static_cast<int>(splits);
+}
+
+extern "C" int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  const int splits = gemm_auto_splits(m, n, k);
+  return splits > 1 ? static_cast<int64_t>(splits) * m * n * static_cast<int64_t>(sizeof(float)) : 0;
+}
+
 extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
-                               int64_t ldc, int out_bf16, int relu, xa_stream_t stream) {
+                               int64_t ldc, int out_bf16, int relu, const void* relu_mask, void* workspace,
+                               int64_t workspace_bytes, xa_stream_t stream) {
   const char* what = "xa_gemm_bf16_tn";
   XA_REQUIRE(a && b && c, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(m > 0 && n > 0 && k > 0 && ldc >= n, XA_EINVAL, "%s: m=%lld n=%lld k=%lld ldc=%lld", what, static_cast<long long>(m),
@@ -218,11 +281,23 @@ extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const floa
   XA_REQUIRE(k % 8 == 0, XA_EALIGN, "%s: k=%lld must be a multiple of 8 (16-byte row pitch for TMA)", what, static_cast<long long>(k));
   XA_REQUIRE(xa::aligned(a, 16) && xa::aligned(b, 16), XA_EALIGN, "%s: a and b must be 16-byte aligned", what);
   XA_REQUIRE(m < (int64_t(1) << 31) && n < (int64_t(1) << 31) && k < (int64_t(1) << 31), XA_EOVERFLOW, "%s: dimension too large", what);
-  const int bn = n >= 256 ? 256 : (n > 64 ? 128 : (n > 16 ? 64 : 16));
+  const int bn = gemm_tile_n(n);
   CUtensorMap ma, mb;
   if (int rc = make_map_2d(&ma, a, m, k, kBlockM, what)) return rc;
   if (int rc = make_map_2d(&mb, b, n, k, bn, what)) return rc;
-  GemmParams p{c, bias, m, n, k, ldc, relu};
+  GemmParams p{};
+  p.c = c, p.bias = bias, p.m = m, p.n = n, p.k = k, p.ldc = ldc, p.relu = relu;
+  p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+  const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
+  int splits = workspace != nullptr ? gemm_auto_splits(m, n, k) : 1;
+  if (splits > 1 && relu_mask == nullptr && workspace_bytes >= static_cast<int64_t>(splits) * m * n * 4) {
+    p.kb_per_split = static_cast<int>((k_blocks + splits - 1) / splits);
+    p.splits = static_cast<int>((k_blocks + p.kb_per_split - 1) / p.kb_per_split);  // every split owns >= 1 block
+    p.partial = static_cast<float*>(workspace);
+  } else {
+    p.splits = 1;
+    p.kb_per_split = static_cast<int>(k_blocks);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (bn == 256) return out_bf16 ? launch<256, true>(ma, mb, p, s, what) : launch<256, false>(ma, mb, p, s, what);
   if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);

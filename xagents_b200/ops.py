@@ -379,18 +379,27 @@ def clip_adam(param, grad, m, v, step, *, workspace=None, lr=7e-4, beta1=0.9, be
 
 
 # ------------------------------------------------------------------------------------------ tensor-core GEMM
-def gemm_bf16_tn(a, b, *, bias=None, relu=False, out_dtype=torch.float32, out=None, stream=None):
+def gemm_bf16_tn(a, b, *, bias=None, relu=False, relu_mask=None, out_dtype=torch.float32, out=None, split_k=True, stream=None):
     """C[M,N] = A[M,K] @ B[N,K]^T (+ bias) (ReLU) on tcgen05 tensor cores: bf16 operands, fp32 accumulate.
-    The Dense layers of the policy/value network (utils/common.py:239-258), y = x W^T + b."""
+    The Dense layers of the policy/value network (utils/common.py:239-258), y = x W^T + b, and their backward
+    products; shapes with few output tiles and a long K (weight gradients) are split along K over the SMs and
+    reduced in a second, deterministic pass.  `relu_mask` [M,N] bf16 zeroes C where mask <= 0."""
     aa, bb = _dev(a, 'bfloat16'), _dev(b, 'bfloat16')
     (m, k), (n, k2) = aa.shape, bb.shape
     if k != k2:
         raise ValueError(f'inner dimensions differ: A {aa.shape}, B {bb.shape}')
-    c = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=_device_of(aa))
+    dev = _device_of(aa)
+    c = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=dev)
     bias_a = _dev(bias, 'float32') if bias is not None else None
+    mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
+    ws, ws_bytes = None, 0
+    if split_k and mask_a is None:
+        ws_bytes = _ffi.lib().xa_gemm_workspace_bytes(m, n, k)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
     _ffi.call('xa_gemm_bf16_tn', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
-              int(bool(relu)), _stream(stream))
-    _count()
+              int(bool(relu)), _ptr(mask_a), _tptr(ws), ws_bytes, _stream(stream))
+    _count(2 if ws is not None else 1)
     return c
 
 
