@@ -32,6 +32,7 @@ for m, n, k, what in [(8192, 512, 3136, 'fc fwd (B=8192)'), (8192, 3136, 512, 'f
     b = torch.randn((n, k), device=dev).to(torch.bfloat16)
     out = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
     t_ours = timeit(lambda: ops.gemm_bf16_tn(a, b, out=out))
+    torch.cuda.synchronize()
     bt = b.t()
     t_ref = timeit(lambda: torch.matmul(a, bt, out=out))
     fl = 2.0 * m * n * k

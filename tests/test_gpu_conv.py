@@ -148,3 +148,34 @@ def test_agent_rollout_uses_tensor_core_inference():
     _, v_ref = net.forward(x, training=False)
     net._tc_forward = keep
     assert float((v_tc - v_ref).abs().max()) <= 8e-2 * float(v_ref.abs().max()) + 1e-3
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize('B', [37, 1000])
+def test_nature_cnn_tensor_core_gradients_vs_torch(B):
+    """Every parameter gradient of the tcgen05 network (data-gradient convolutions, split-K weight gradients,
+    masked dense backward) against torch autograd on the fp32 network with the same weights."""
+    from xagents_b200.agents import NatureCNN, NatureCnnTc
+    torch.manual_seed(2)
+    tc = NatureCnnTc(4, 6).cuda()
+    with torch.no_grad():
+        for p in tc.parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn_like(p) * 0.05)
+        tc.actor.weight.mul_(30)
+    ref = NatureCNN(4, 6).cuda()
+    ref.load_state_dict(tc.state_dict())
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    d_actor = torch.randn((B, 6), device=DEV) / B
+    d_critic = torch.randn(B, device=DEV) / B
+    actor, critic = tc(x)
+    torch.autograd.backward([actor, critic], [d_actor, d_critic])
+    ra, rc = ref(x.float() / 255.0)
+    torch.autograd.backward([ra, rc.reshape(-1)], [d_actor, d_critic])
+    torch.cuda.synchronize()
+    for (name, p), q in zip(tc.named_parameters(), ref.parameters()):
+        scale = float(q.grad.abs().max())
+        err = float((p.grad - q.grad).abs().max())
+        assert p.grad.shape == q.grad.shape and err <= 6e-2 * scale + 1e-7, f'{name}: {err:.3e} vs {scale:.3e}'
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0)
+        assert float(cos) > 0.999, f'{name}: cosine {float(cos):.5f}'

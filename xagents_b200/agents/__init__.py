@@ -4,5 +4,6 @@ from .a2c import A2C
 from .base import BaseAgent, EnvMajorView, OnPolicy
 from .models import KerasModel, NatureCNN, TorchModel, adapt
 from .ppo import PPO
+from .tc_cnn import NatureCnnTc
 
-__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'adapt']
+__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'NatureCnnTc', 'adapt']

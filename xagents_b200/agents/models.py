@@ -64,11 +64,14 @@ class TorchModel:
         if not training and self._tc_forward is not None and states.dtype == torch.uint8:
             return self._tc_forward(states)
         x = states
-        scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
-        if x.dtype != torch.float32:
-            x = x.float()
-        if scale:
-            x = x / 255.0                                         # base.py:505-506
+        if getattr(self.module, 'takes_uint8', False) and x.dtype == torch.uint8:
+            pass                                                  # the tensor-core network scales inside its first kernel
+        else:
+            scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
+            if x.dtype != torch.float32:
+                x = x.float()
+            if scale:
+                x = x / 255.0                                     # base.py:505-506
         with torch.set_grad_enabled(training):
             actor, critic = self.module(x)
         critic = critic.reshape(-1)                               # tf.squeeze, a2c/agent.py:84

@@ -1,0 +1,139 @@
+"""The Nature CNN, forward AND backward, on the tcgen05 kernels.
+
+`NatureCnnTc` keeps fp32 master weights in the torch layouts of `NatureCNN` (so checkpoints, the flat-buffer
+optimiser and the gradient all-reduce are unchanged) and runs every contraction of the network through
+`xa_conv2d_nhwc_bf16` / `xa_gemm_bf16_tn` (bf16 operands, fp32 accumulation in TMEM):
+
+  forward    frames -s2d-> conv1 -> conv2 -> conv3 -> FC512 -> heads                     (tc_conv.py's pipeline)
+  backward   heads/FC: dgrad GEMMs with the ReLU derivative in the epilogue, wgrad GEMMs on transposed operands
+             conv3, conv2: data gradient = the same convolution kernel on dY with full zero padding and flipped
+             weights (+ ReLU derivative of the layer below in the epilogue)
+             all convs: weight gradient = split-K GEMM  dW = dY^T Xcol  on `xa_im2col_t_bf16` operands
+  The input layer needs no data gradient.  Bias gradients are column sums (torch reductions).
+
+Strided layers live in space-to-depth form (8x8/4 -> 2x2/1 over 21x21x64, 4x4/2 -> 2x2/1 over 10x10x128); the
+layout maps between torch's [N, C, KH, KW] and the kernels' [N, (kh, kw, c)] are applied to the (tiny) weight and
+weight-gradient tensors only.
+"""
+import torch
+
+from .. import ops
+from .models import NatureCNN
+from .tc_conv import _s2d_kernel
+
+
+def _s2d_kernel_inverse(g, n, c, kh, kw, s):
+    """[N, (kh', kw', dy, dx, c)] -> torch [N, C, KH, KW]."""
+    g = g.reshape(n, kh // s, kw // s, s, s, c).permute(0, 1, 3, 2, 4, 5).reshape(n, kh, kw, c)
+    return g.permute(0, 3, 1, 2).contiguous()
+
+
+def _flip(w, kh, kw, c):
+    """forward [N, kh*kw*C] -> data-gradient weights [C, kh*kw*N]: W'[c, kh', kw', n] = W[n, KH-1-kh', KW-1-kw', c]."""
+    n = w.shape[0]
+    return w.reshape(n, kh, kw, c).flip(1, 2).permute(3, 1, 2, 0).reshape(c, kh * kw * n).contiguous()
+
+
+class _Operands:
+    """bf16 operand copies of the weights, re-derived after every optimiser step."""
+
+    @torch.no_grad()
+    def __init__(self, m):
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        c1, c2, c3 = [x for x in m.trunk if isinstance(x, torch.nn.Conv2d)]
+        fc = [x for x in m.trunk if isinstance(x, torch.nn.Linear)][0]
+        self.w1 = bf(_s2d_kernel(c1.weight, 4))                                   # [32, 2*2*64]
+        self.w2 = bf(_s2d_kernel(c2.weight, 2))                                   # [64, 2*2*128]
+        self.w3 = bf(c3.weight.permute(0, 2, 3, 1).reshape(64, -1))               # [64, 3*3*64]
+        self.w2_flip = _flip(self.w2, 2, 2, 128)                                  # [128, 2*2*64]
+        self.w3_flip = _flip(self.w3, 3, 3, 64)                                   # [64, 3*3*64]
+        wf = fc.weight.reshape(512, 64, 7, 7).permute(0, 2, 3, 1).reshape(512, -1)
+        self.wf = bf(wf)                                                          # [512, 3136] (h, w, c)
+        self.wf_t = bf(wf.t())                                                    # [3136, 512]
+        a, c = m.actor, m.critic
+        self.n_actions = a.weight.shape[0]
+        heads = torch.zeros((8 * ((self.n_actions + 1 + 7) // 8), 512), device=a.weight.device)
+        heads[:self.n_actions] = a.weight
+        heads[self.n_actions] = c.weight[0]
+        self.wh = bf(heads)                                                       # [8, 512]
+        self.wh_t = bf(heads.t())                                                 # [512, 8]
+        self.b1, self.b2, self.b3 = (x.bias.detach().float().contiguous() for x in (c1, c2, c3))
+        self.bf_ = fc.bias.detach().float().contiguous()
+        hb = torch.zeros(heads.shape[0], device=a.weight.device)
+        hb[:self.n_actions] = a.bias
+        hb[self.n_actions] = c.bias[0]
+        self.bh = hb
+
+
+class _NatureCnnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, frames, op, w1, b1, w2, b2, w3, b3, wf, bf_, wa, ba, wc, bc):
+        x1 = ops.space_to_depth_u8_bf16(frames.contiguous(), 4)                                    # [B,21,21,64]
+        x2 = ops.conv2d_nhwc_bf16(x1, op.w1, 2, 2, bias=op.b1, relu=True, out_s2d=True)           # [B,10,10,128]
+        x3 = ops.conv2d_nhwc_bf16(x2, op.w2, 2, 2, bias=op.b2, relu=True)                         # [B,9,9,64]
+        y3 = ops.conv2d_nhwc_bf16(x3, op.w3, 3, 3, bias=op.b3, relu=True)                         # [B,7,7,64]
+        h = ops.gemm_bf16_tn(y3.view(y3.shape[0], -1), op.wf, bias=op.bf_, relu=True, out_dtype=torch.bfloat16)
+        out = ops.gemm_bf16_tn(h, op.wh, bias=op.bh, out_dtype=torch.float32)                     # [B,8]
+        ctx.op = op
+        ctx.save_for_backward(x1, x2, x3, y3, h)
+        return out[:, :op.n_actions].contiguous(), out[:, op.n_actions].contiguous()
+
+    @staticmethod
+    def backward(ctx, d_actor, d_critic):
+        op = ctx.op
+        x1, x2, x3, y3, h = ctx.saved_tensors
+        B, A = h.shape[0], op.n_actions
+        d_out = torch.zeros((B, op.wh.shape[0]), dtype=torch.float32, device=h.device)
+        d_out[:, :A] = d_actor
+        d_out[:, A] = d_critic.reshape(-1)
+        # heads
+        d_out16 = ops.to_bf16(d_out)
+        d_wh = ops.gemm_bf16_tn(ops.to_bf16(d_out, transpose=True), ops.to_bf16(h, transpose=True))          # [8,512]
+        d_bh = d_out.sum(0)
+        dh = ops.gemm_bf16_tn(d_out16, op.wh_t, relu_mask=h, out_dtype=torch.bfloat16)                       # [B,512]
+        # FC512
+        y3f = y3.view(B, -1)
+        d_wf = ops.gemm_bf16_tn(ops.to_bf16(dh, transpose=True), ops.to_bf16(y3f, transpose=True))           # [512,3136]
+        d_bf = dh.sum(0, dtype=torch.float32)
+        dy3 = ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out_dtype=torch.bfloat16).view(B, 7, 7, 64)
+        # conv3
+        d_w3 = ops.gemm_bf16_tn(ops.to_bf16(dy3.view(-1, 64), transpose=True), ops.im2col_t_bf16(x3, 3, 3))  # [64,576]
+        d_b3 = dy3.view(-1, 64).sum(0, dtype=torch.float32)
+        dy2 = ops.conv2d_nhwc_bf16(dy3, op.w3_flip, 3, 3, pad=(2, 2), relu_mask=x3)                          # [B,9,9,64]
+        # conv2 (space-to-depth form)
+        d_w2 = ops.gemm_bf16_tn(ops.to_bf16(dy2.view(-1, 64), transpose=True), ops.im2col_t_bf16(x2, 2, 2))  # [64,512]
+        d_b2 = dy2.view(-1, 64).sum(0, dtype=torch.float32)
+        dy1 = ops.conv2d_nhwc_bf16(dy2, op.w2_flip, 2, 2, pad=(1, 1), relu_mask=x2)                          # [B,10,10,128] = dY1 (s2d)
+        # conv1 (space-to-depth form; rows of dy1 enumerate pixels as (b, y/2, x/2, y%2, x%2))
+        dy1r = dy1.view(-1, 32)
+        d_w1 = ops.gemm_bf16_tn(ops.to_bf16(dy1r, transpose=True), ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True))   # [32,256]
+        d_b1 = dy1r.sum(0, dtype=torch.float32)
+        # back to torch layouts
+        g_w1 = _s2d_kernel_inverse(d_w1, 32, 4, 8, 8, 4)
+        g_w2 = _s2d_kernel_inverse(d_w2, 64, 32, 4, 4, 2)
+        g_w3 = d_w3.reshape(64, 3, 3, 64).permute(0, 3, 1, 2).contiguous()
+        g_wf = d_wf.reshape(512, 7, 7, 64).permute(0, 3, 1, 2).reshape(512, -1).contiguous()
+        return (None, None, g_w1, d_b1, g_w2, d_b2, g_w3, d_b3, g_wf, d_bf, d_wh[:A].contiguous(), d_bh[:A].contiguous(),
+                d_wh[A:A + 1].contiguous(), d_bh[A:A + 1].contiguous())
+
+
+class NatureCnnTc(NatureCNN):
+    """NatureCNN whose forward and backward run on the tcgen05 kernels.  Takes uint8 NHWC frames directly."""
+    takes_uint8 = True
+
+    def __init__(self, in_channels=4, n_actions=6):
+        assert in_channels == 4, 'the space-to-depth layouts are built for 84x84x4 frames'
+        super().__init__(in_channels, n_actions)
+        self._op = None
+
+    def refresh(self):
+        self._op = _Operands(self)
+        return self
+
+    def forward(self, frames_u8):
+        if self._op is None:
+            self.refresh()
+        c1, c2, c3 = [x for x in self.trunk if isinstance(x, torch.nn.Conv2d)]
+        fc = [x for x in self.trunk if isinstance(x, torch.nn.Linear)][0]
+        return _NatureCnnFn.apply(frames_u8, self._op, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, fc.weight, fc.bias,
+                                  self.actor.weight, self.actor.bias, self.critic.weight, self.critic.bias)

@@ -352,3 +352,81 @@ int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int heig
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- weight gradient operand
+// Transposed im2col: X [B,H,W,C] bf16 -> Xcol^T [K = KH*KW*C, ld] with ld >= M = B*OH*OW (caller zero-fills the
+// padding), column m = output pixel, row k = (kh, kw, c):  Xcol^T[k, m] = X[b, y+kh, x+kw, c].  This is the B
+// operand (K-major, M contiguous) of the weight-gradient product dW = dY^T Xcol run by xa_gemm_bf16_tn with
+// split-K.  pixel_s2d: columns enumerate pixels as (b, y/2, x/2, y%2, x%2), the order in which a layer whose
+// output was written with out_s2d holds its dY rows.  64 pixels x 64 channels per block through shared memory:
+// 128-B reads along channels, 128-B writes along pixels.
+// (Materialising Xcol^T costs K*M*2 bytes of traffic; reading NHWC tiles as MN-major UMMA operands is the
+// replacement planned for the next round.)
+namespace {
+
+__global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H,
+                                                        int W, int C, int KH, int KW, int OH, int OW, int64_t M, int64_t ld,
+                                                        int pixel_s2d) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int cblocks = C / 64;
+  const int tap = blockIdx.y / cblocks, c0 = (blockIdx.y - tap * cblocks) * 64;
+  const int kh = tap / KW, kw = tap - kh * KW;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;  // 8 warps
+  // load: warp handles pixels wrp, wrp+8, ...; lane reads 2 channels (one bf16x2)
+  for (int pi = wrp; pi < 64; pi += 8) {
+    const int64_t m = m0 + pi;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+    if (m < M) {
+      int ox, oy;
+      int64_t b;
+      if (pixel_s2d) {
+        const int sub = static_cast<int>(m & 3);
+        const int64_t q = m >> 2;
+        const int X2 = static_cast<int>(q % (OW / 2)), Y2 = static_cast<int>((q / (OW / 2)) % (OH / 2));
+        b = q / (static_cast<int64_t>(OW / 2) * (OH / 2));
+        oy = Y2 * 2 + (sub >> 1), ox = X2 * 2 + (sub & 1);
+      } else {
+        ox = static_cast<int>(m % OW), oy = static_cast<int>((m / OW) % OH);
+        b = m / (static_cast<int64_t>(OW) * OH);
+      }
+      v = *reinterpret_cast<const __nv_bfloat162*>(x + ((b * H + oy + kh) * W + ox + kw) * C + c0 + 2 * lane);
+    }
+    tile[pi][2 * lane] = __low2bfloat16(v);
+    tile[pi][2 * lane + 1] = __high2bfloat16(v);
+  }
+  __syncthreads();
+  // store: warp handles channels wrp, wrp+8, ...; lane writes 2 pixels
+  for (int ci = wrp; ci < 64; ci += 8) {
+    const int64_t k = static_cast<int64_t>(tap) * C + c0 + ci;
+    const int64_t m = m0 + 2 * lane;
+    if (m + 1 < ld || m < ld) {
+      __nv_bfloat16* dst = out + k * ld + m;
+      if (m + 1 < ld && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __halves2bfloat162(tile[2 * lane][ci], tile[2 * lane + 1][ci]);
+      } else {
+        if (m < ld) dst[0] = tile[2 * lane][ci];
+        if (m + 1 < ld) dst[1] = tile[2 * lane + 1][ci];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int xa_im2col_t_bf16(const void* x, void* out, int batch, int height, int width, int channels, int kh, int kw,
+                                int64_t ld, int pixel_s2d, xa_stream_t stream) {
+  const char* what = "xa_im2col_t_bf16";
+  XA_REQUIRE(x && out, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && kh > 0 && kw > 0 && channels % 64 == 0, XA_EINVAL, "%s: bad shape", what);
+  const int OH = height - kh + 1, OW = width - kw + 1;
+  const int64_t M = static_cast<int64_t>(batch) * OH * OW;
+  XA_REQUIRE(ld >= M && ld % 2 == 0, XA_EINVAL, "%s: ld=%lld must be even and >= %lld", what, static_cast<long long>(ld),
+             static_cast<long long>(M));
+  XA_REQUIRE(!pixel_s2d || (OH % 2 == 0 && OW % 2 == 0), XA_EINVAL, "%s: pixel_s2d needs even output size", what);
+  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(kh * kw * (channels / 64)));
+  im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                      static_cast<__nv_bfloat16*>(out), batch, height, width, channels, kh,
+                                                                      kw, OH, OW, M, ld, pixel_s2d);
+  return xa::check_launch(what);
+}

@@ -231,10 +231,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
 template <int BN, bool kOutBf16>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
   auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kBytes);
-  if (e != cudaSuccess) {
-    xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    return static_cast<int>(e);
+  static thread_local int configured_dev = -1;  // opt-in shared memory is a per-device attribute of the kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kBytes);
+    if (e != cudaSuccess) {
+      xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured_dev = dev;
   }
   const int64_t items = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN) * p.splits;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
@@ -261,7 +267,7 @@ static int gemm_auto_splits(int64_t m, int64_t n, int64_t k) {
   const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   if (tiles * 2 > sms || k_blocks < 32) return 1;
-  int64_t splits = (sms + tiles - 1) / tiles;
+  int64_t splits = sms / tiles;  // one wave: tiles * splits <= SMs
   if (splits > k_blocks / 8) splits = k_blocks / 8;
   return splits < 2 ? 1 : static_cast<int>(splits);
 }
