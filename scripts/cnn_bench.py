@@ -57,3 +57,30 @@ t3 = timeit(lambda: ops.conv2d_nhwc_bf16(x3, tc.w3, 3, 3, bias=tc.b3, relu=True)
 t4 = timeit(lambda: ops.gemm_bf16_tn(x4.view(B, -1), tc.wf, bias=tc.bf_, relu=True, out_dtype=torch.bfloat16))
 print(f'\nper layer at B={B} (us): space-to-depth {t0:.0f}, conv1 {t1:.0f} ({2*B*400*256*32/t1/1e6:.0f} TFLOP/s), '
       f'conv2 {t2:.0f} ({2*B*81*512*64/t2/1e6:.0f}), conv3 {t3:.0f} ({2*B*49*576*64/t3/1e6:.0f}), fc {t4:.0f} ({2*B*3136*512/t4/1e6:.0f})')
+
+# ---- training step: forward + backward of the whole network (B = 8192, the C3 minibatch)
+from xagents_b200.agents import NatureCnnTc  # noqa: E402
+
+B = 8192
+x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=dev)
+da, dc = torch.randn((B, 6), device=dev) / B, torch.randn(B, device=dev) / B
+tcn = NatureCnnTc(4, 6).cuda()
+
+
+def ours_step():
+    a, c = tcn(x)
+    torch.autograd.backward([a, c], [da, dc])
+
+
+def torch_step(autocast):
+    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+        a, c = net(x.float() / 255.0)
+    torch.autograd.backward([a.float(), c.float().reshape(-1)], [da, dc])
+
+
+t_ours = timeit(ours_step, 10)
+t_fp32 = timeit(lambda: torch_step(False), 5)
+t_bf16 = timeit(lambda: torch_step(True), 5)
+fl = 3 * 18.7e6 * B
+print(f'\nforward+backward at B={B}: ours {t_ours:.0f} us ({fl / t_ours / 1e6:.0f} TFLOP/s), torch fp32 {t_fp32:.0f} us, '
+      f'torch bf16 autocast {t_bf16:.0f} us  -> {t_bf16 / t_ours:.1f}x / {t_fp32 / t_ours:.1f}x')

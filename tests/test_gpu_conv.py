@@ -150,11 +150,49 @@ def test_agent_rollout_uses_tensor_core_inference():
     assert float((v_tc - v_ref).abs().max()) <= 8e-2 * float(v_ref.abs().max()) + 1e-3
 
 
+def _emulated_backward(net, x_u8, d_actor, d_critic):
+    """fp64 forward+backward of the Nature CNN with bf16 roundings at exactly the points where the tensor-core
+    pipeline rounds (weights, every activation, every back-propagated gradient tensor)."""
+    rb = lambda t: t.to(torch.bfloat16).double()
+    F = torch.nn.functional
+    convs = [m for m in net.trunk if isinstance(m, torch.nn.Conv2d)]
+    fc = [m for m in net.trunk if isinstance(m, torch.nn.Linear)][0]
+    B = x_u8.shape[0]
+    w = [rb(c.weight) for c in convs]
+    acts = [rb(x_u8.float() / 255.0).permute(0, 3, 1, 2)]
+    for c, wi in zip(convs, w):
+        acts.append(rb(torch.relu(F.conv2d(acts[-1], wi, c.bias.double(), c.stride))))
+    y3 = acts[-1].permute(0, 2, 3, 1).reshape(B, -1)                                  # NHWC flatten
+    wf = rb(fc.weight.reshape(512, 64, 7, 7).permute(0, 2, 3, 1).reshape(512, -1))
+    h = rb(torch.relu(y3 @ wf.t() + fc.bias.double()))
+    A = net.actor.weight.shape[0]
+    wh = torch.cat([rb(net.actor.weight), rb(net.critic.weight)])                      # [A+1, 512]
+    d_out = torch.cat([d_actor.double(), d_critic.double().reshape(-1, 1)], 1)
+    d_out16 = rb(d_out)
+    g = {}
+    d_wh = d_out16.t() @ h
+    g['actor.weight'], g['critic.weight'] = d_wh[:A], d_wh[A:]
+    g['actor.bias'], g['critic.bias'] = d_out[:, :A].sum(0), d_out[:, A:].sum(0)
+    dh = rb((d_out16 @ wh) * (h > 0))
+    d_wf = dh.t() @ y3
+    g['trunk.7.weight'] = d_wf.reshape(512, 7, 7, 64).permute(0, 3, 1, 2).reshape(512, -1)
+    g['trunk.7.bias'] = dh.sum(0)
+    dy = rb((dh @ wf) * (y3 > 0)).reshape(B, 7, 7, 64).permute(0, 3, 1, 2)            # NCHW
+    for li in (2, 1, 0):
+        c = convs[li]
+        g[f'trunk.{2 * li}.weight'] = torch.nn.grad.conv2d_weight(acts[li], w[li].shape, dy, c.stride)
+        g[f'trunk.{2 * li}.bias'] = dy.sum((0, 2, 3))
+        if li > 0:
+            dy = rb(torch.nn.grad.conv2d_input(acts[li].shape, w[li], dy, c.stride) * (acts[li] > 0))
+    return g
+
+
 @pytest.mark.timeout(240)
 @pytest.mark.parametrize('B', [37, 1000])
 def test_nature_cnn_tensor_core_gradients_vs_torch(B):
     """Every parameter gradient of the tcgen05 network (data-gradient convolutions, split-K weight gradients,
-    masked dense backward) against torch autograd on the fp32 network with the same weights."""
+    masked dense backward): tightly against an fp64 reference that rounds to bf16 where the pipeline does, and
+    loosely (direction / norm) against plain fp32 autograd."""
     from xagents_b200.agents import NatureCNN, NatureCnnTc
     torch.manual_seed(2)
     tc = NatureCnnTc(4, 6).cuda()
@@ -172,10 +210,46 @@ def test_nature_cnn_tensor_core_gradients_vs_torch(B):
     torch.autograd.backward([actor, critic], [d_actor, d_critic])
     ra, rc = ref(x.float() / 255.0)
     torch.autograd.backward([ra, rc.reshape(-1)], [d_actor, d_critic])
+    with torch.no_grad():
+        emu = _emulated_backward(ref, x, d_actor, d_critic)
     torch.cuda.synchronize()
+    report = []
     for (name, p), q in zip(tc.named_parameters(), ref.parameters()):
-        scale = float(q.grad.abs().max())
-        err = float((p.grad - q.grad).abs().max())
-        assert p.grad.shape == q.grad.shape and err <= 6e-2 * scale + 1e-7, f'{name}: {err:.3e} vs {scale:.3e}'
-        cos = torch.nn.functional.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0)
-        assert float(cos) > 0.999, f'{name}: cosine {float(cos):.5f}'
+        assert p.grad.shape == q.grad.shape
+        g, r, e = p.grad.flatten().double(), q.grad.flatten().double(), emu[name].flatten()
+        report.append((name, float(torch.nn.functional.cosine_similarity(g, r, dim=0)), float((g - r).norm() / r.norm()),
+                       float((g - e).norm() / e.norm()), float((g - e).abs().max() / e.abs().max())))
+    print('\n'.join(f'{n:18s} vs fp32: cos {c:.5f} rel-L2 {r:.4f} | vs bf16-emulated fp64: rel-L2 {e:.5f} max/max {m:.5f}'
+                    for n, c, r, e, m in report))
+    for name, cos, rel, rel_emu, max_emu in report:
+        # same roundings, different summation order: only bf16 ties that flip (more of them in a larger batch)
+        assert rel_emu < 2e-2 and max_emu < 5e-2, f'{name}: {rel_emu:.5f} / {max_emu:.5f} against the bf16-emulated reference'
+        # bf16 activations and gradients through five layers against the fp32 network: direction and norm agree
+        assert cos > 0.99 and rel < 0.12, f'{name}: cosine {cos:.5f}, relative L2 error {rel:.4f} against fp32'
+
+
+@pytest.mark.timeout(240)
+def test_ppo_fit_with_the_tensor_core_network():
+    """PPO.fit end to end with NatureCnnTc: rollout inference, training forward and the whole backward on tcgen05."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    from xagents_b200.agents import PPO, NatureCnnTc, TorchModel
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    T, E, A = 8, 4, 6
+    rng = np.random.default_rng(11)
+    obs, rewards, dones, resets = mg._streams(rng, 4 * T, E, (84, 84, 4), True, 0.1)
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+    torch.manual_seed(0)
+    net = TorchModel(NatureCnnTc(4, A).cuda())
+    before = net.flat_param.clone()
+    agent = PPO(envs, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=5)
+    agent.fit(max_steps=3 * T * E)
+    torch.cuda.synchronize()
+    assert agent.steps == 3 * T * E and net.step == 3 * 2 * 4
+    assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)
+    losses = torch.stack(agent.loss_history).cpu().numpy()
+    assert np.isfinite(losses).all()
