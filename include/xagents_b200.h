@@ -197,9 +197,11 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
                         int out_s2d, const void* relu_mask, xa_stream_t stream);
 /* Transposed im2col for the weight-gradient product: x [B,H,W,C] bf16 -> out [kh*kw*C, ld] bf16 with
  * out[(kh,kw,c), m] = x[b, y+kh, x+kw, c], m = output pixel (ld >= B*OH*OW, even; columns past M are written 0).
- * pixel_s2d: pixels enumerated (b, y/2, x/2, y%2, x%2).  dW = dY^T Xcol = xa_gemm_bf16_tn(dY^T, out). */
+ * pixel_s2d: pixels enumerated (b, y/2, x/2, y%2, x%2).  dW = dY^T Xcol = xa_gemm_bf16_tn(dY^T, out).
+ * ones_row: out has one more row, all ones, so the product's extra column is the bias gradient.  C % 32 == 0,
+ * ld % 8 == 0.  A 1x1 kernel makes this a plain [M, C] -> [C, ld] transpose. */
 int xa_im2col_t_bf16(const void* x, void* out, int batch, int height, int width, int channels, int kh, int kw,
-                     int64_t ld, int pixel_s2d, xa_stream_t stream);
+                     int64_t ld, int pixel_s2d, int ones_row, xa_stream_t stream);
 /* uint8 NHWC frames -> bf16 (optionally /255, xagents/base.py:505-506) rearranged block x block -> channels:
  * dst[b, y/s, x/s, (y%s, x%s, c)]. */
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,

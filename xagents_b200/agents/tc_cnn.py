@@ -88,26 +88,24 @@ class _NatureCnnFn(torch.autograd.Function):
         d_out[:, A] = d_critic.reshape(-1)
         # heads
         d_out16 = ops.to_bf16(d_out)
-        d_wh = ops.gemm_bf16_tn(ops.to_bf16(d_out, transpose=True), ops.to_bf16(h, transpose=True))          # [8,512]
+        d_wh = ops.gemm_bf16_tn(ops.to_bf16(d_out, transpose=True), ops.transpose_bf16(h))                   # [8,512]
         d_bh = d_out.sum(0)
         dh = ops.gemm_bf16_tn(d_out16, op.wh_t, relu_mask=h, out_dtype=torch.bfloat16)                       # [B,512]
         # FC512
         y3f = y3.view(B, -1)
-        d_wf = ops.gemm_bf16_tn(ops.to_bf16(dh, transpose=True), ops.to_bf16(y3f, transpose=True))           # [512,3136]
+        d_wf = ops.gemm_bf16_tn(ops.transpose_bf16(dh), ops.transpose_bf16(y3f))                             # [512,3136]
         d_bf = dh.sum(0, dtype=torch.float32)
         dy3 = ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out_dtype=torch.bfloat16).view(B, 7, 7, 64)
-        # conv3
-        d_w3 = ops.gemm_bf16_tn(ops.to_bf16(dy3.view(-1, 64), transpose=True), ops.im2col_t_bf16(x3, 3, 3))  # [64,576]
-        d_b3 = dy3.view(-1, 64).sum(0, dtype=torch.float32)
+        # convolutions: dW (and, from the row of ones, db) = dY^T [N, M'] x Xcol^T [K+8, M']^T, split along M'
+        g3 = ops.gemm_bf16_tn(ops.transpose_bf16(dy3.view(-1, 64)), ops.im2col_t_bf16(x3, 3, 3, ones_row=True))   # [64,576+8]
+        d_w3, d_b3 = g3[:, :576], g3[:, 576].contiguous()
         dy2 = ops.conv2d_nhwc_bf16(dy3, op.w3_flip, 3, 3, pad=(2, 2), relu_mask=x3)                          # [B,9,9,64]
-        # conv2 (space-to-depth form)
-        d_w2 = ops.gemm_bf16_tn(ops.to_bf16(dy2.view(-1, 64), transpose=True), ops.im2col_t_bf16(x2, 2, 2))  # [64,512]
-        d_b2 = dy2.view(-1, 64).sum(0, dtype=torch.float32)
+        g2 = ops.gemm_bf16_tn(ops.transpose_bf16(dy2.view(-1, 64)), ops.im2col_t_bf16(x2, 2, 2, ones_row=True))   # [64,512+8]
+        d_w2, d_b2 = g2[:, :512], g2[:, 512].contiguous()
         dy1 = ops.conv2d_nhwc_bf16(dy2, op.w2_flip, 2, 2, pad=(1, 1), relu_mask=x2)                          # [B,10,10,128] = dY1 (s2d)
-        # conv1 (space-to-depth form; rows of dy1 enumerate pixels as (b, y/2, x/2, y%2, x%2))
-        dy1r = dy1.view(-1, 32)
-        d_w1 = ops.gemm_bf16_tn(ops.to_bf16(dy1r, transpose=True), ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True))   # [32,256]
-        d_b1 = dy1r.sum(0, dtype=torch.float32)
+        # conv1 (rows of dy1 enumerate pixels as (b, y/2, x/2, y%2, x%2): the im2col columns follow the same order)
+        g1 = ops.gemm_bf16_tn(ops.transpose_bf16(dy1.view(-1, 32)), ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True, ones_row=True))
+        d_w1, d_b1 = g1[:, :256], g1[:, 256].contiguous()
         # back to torch layouts
         g_w1 = _s2d_kernel_inverse(d_w1, 32, 4, 8, 8, 4)
         g_w2 = _s2d_kernel_inverse(d_w2, 64, 32, 4, 4, 2)

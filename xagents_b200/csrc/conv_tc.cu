@@ -360,23 +360,43 @@ int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int heig
 // split-K.  pixel_s2d: columns enumerate pixels as (b, y/2, x/2, y%2, x%2), the order in which a layer whose
 // output was written with out_s2d holds its dY rows.  64 pixels x 64 channels per block through shared memory:
 // 128-B reads along channels, 128-B writes along pixels.
+// ones_row appends a row K of ones, so that the same GEMM also returns the bias gradient sum_m dY[m, n] as its
+// extra output column (deterministically).  With a 1x1 kernel this is simply a fast [M, C] -> [C, M] transpose.
 // (Materialising Xcol^T costs K*M*2 bytes of traffic; reading NHWC tiles as MN-major UMMA operands is the
 // replacement planned for the next round.)
 namespace {
 
+// kCB = channels per block (64 or 32).  Loads: 16-B vectors along channels (a pixel's kCB channels are contiguous);
+// stores: 16-B vectors along pixels (8 pixels of one channel), through a padded shared tile.
+template <int kCB>
 __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H,
                                                         int W, int C, int KH, int KW, int OH, int OW, int64_t M, int64_t ld,
-                                                        int pixel_s2d) {
-  __shared__ __nv_bfloat16 tile[64][66];
+                                                        int pixel_s2d, int ones_row) {
+  constexpr int kPitch = kCB + 8;              // bf16 elements; keeps 16-B alignment and spreads banks
+  constexpr int kVecPerPix = kCB / 8;          // 16-B vectors per pixel
+  constexpr int kPixPerPass = 256 / kVecPerPix;
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * kPitch];
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
-  const int cblocks = C / 64;
-  const int tap = blockIdx.y / cblocks, c0 = (blockIdx.y - tap * cblocks) * 64;
+  const int cblocks = C / kCB;
+  const int taps = KH * KW;
+  if (static_cast<int>(blockIdx.y) == taps * cblocks) {  // extra block row: the row of ones (bias gradient for free)
+    if (ones_row) {
+      const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+      for (int i = threadIdx.x; i < 64; i += 256) {
+        const int64_t m = m0 + i;
+        if (m < ld) out[static_cast<int64_t>(taps) * C * ld + m] = m < M ? one : zero;
+      }
+    }
+    return;
+  }
+  const int tap = blockIdx.y / cblocks, c0 = (blockIdx.y - tap * cblocks) * kCB;
   const int kh = tap / KW, kw = tap - kh * KW;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;  // 8 warps
-  // load: warp handles pixels wrp, wrp+8, ...; lane reads 2 channels (one bf16x2)
-  for (int pi = wrp; pi < 64; pi += 8) {
+  const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
+#pragma unroll
+  for (int pass = 0; pass < 64 / kPixPerPass; ++pass) {
+    const int pi = pass * kPixPerPass + prow;
     const int64_t m = m0 + pi;
-    __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+    uint4 v = make_uint4(0, 0, 0, 0);
     if (m < M) {
       int ox, oy;
       int64_t b;
@@ -390,24 +410,23 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __re
         ox = static_cast<int>(m % OW), oy = static_cast<int>((m / OW) % OH);
         b = m / (static_cast<int64_t>(OW) * OH);
       }
-      v = *reinterpret_cast<const __nv_bfloat162*>(x + ((b * H + oy + kh) * W + ox + kw) * C + c0 + 2 * lane);
+      v = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + oy + kh) * W + ox + kw) * C + c0) + vec);
     }
-    tile[pi][2 * lane] = __low2bfloat16(v);
-    tile[pi][2 * lane + 1] = __high2bfloat16(v);
+    *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
   }
   __syncthreads();
-  // store: warp handles channels wrp, wrp+8, ...; lane writes 2 pixels
-  for (int ci = wrp; ci < 64; ci += 8) {
-    const int64_t k = static_cast<int64_t>(tap) * C + c0 + ci;
-    const int64_t m = m0 + 2 * lane;
-    if (m + 1 < ld || m < ld) {
-      __nv_bfloat16* dst = out + k * ld + m;
-      if (m + 1 < ld && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
-        *reinterpret_cast<__nv_bfloat162*>(dst) = __halves2bfloat162(tile[2 * lane][ci], tile[2 * lane + 1][ci]);
-      } else {
-        if (m < ld) dst[0] = tile[2 * lane][ci];
-        if (m + 1 < ld) dst[1] = tile[2 * lane + 1][ci];
-      }
+  // 8 threads per channel row, each packs 8 pixels of that channel into one 16-B store
+  constexpr int kRowsPerPass = 256 / 8;
+#pragma unroll
+  for (int pass = 0; pass < kCB / kRowsPerPass; ++pass) {
+    const int ci = pass * kRowsPerPass + threadIdx.x / 8;
+    const int pg = (threadIdx.x & 7) * 8;
+    const int64_t m = m0 + pg;
+    if (m < ld) {  // ld is a multiple of 8, so a group of 8 pixels is all-in or all-out
+      __nv_bfloat16 vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
+      *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * C + c0 + ci) * ld + m) = *reinterpret_cast<uint4*>(vals);
     }
   }
 }
@@ -415,18 +434,25 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __re
 }  // namespace
 
 extern "C" int xa_im2col_t_bf16(const void* x, void* out, int batch, int height, int width, int channels, int kh, int kw,
-                                int64_t ld, int pixel_s2d, xa_stream_t stream) {
+                                int64_t ld, int pixel_s2d, int ones_row, xa_stream_t stream) {
   const char* what = "xa_im2col_t_bf16";
   XA_REQUIRE(x && out, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && kh > 0 && kw > 0 && channels % 64 == 0, XA_EINVAL, "%s: bad shape", what);
+  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && kh > 0 && kw > 0 && channels % 32 == 0, XA_EINVAL, "%s: bad shape", what);
   const int OH = height - kh + 1, OW = width - kw + 1;
   const int64_t M = static_cast<int64_t>(batch) * OH * OW;
-  XA_REQUIRE(ld >= M && ld % 2 == 0, XA_EINVAL, "%s: ld=%lld must be even and >= %lld", what, static_cast<long long>(ld),
+  XA_REQUIRE(ld >= M && ld % 8 == 0, XA_EINVAL, "%s: ld=%lld must be a multiple of 8 and >= %lld", what, static_cast<long long>(ld),
              static_cast<long long>(M));
   XA_REQUIRE(!pixel_s2d || (OH % 2 == 0 && OW % 2 == 0), XA_EINVAL, "%s: pixel_s2d needs even output size", what);
-  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(kh * kw * (channels / 64)));
-  im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x),
-                                                                      static_cast<__nv_bfloat16*>(out), batch, height, width, channels, kh,
-                                                                      kw, OH, OW, M, ld, pixel_s2d);
+  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
+  const int cb = channels % 64 == 0 ? 64 : 32;
+  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(kh * kw * (channels / cb) + (ones_row ? 1 : 0)));
+  XA_REQUIRE(grid.y <= 65535, XA_EOVERFLOW, "%s: too many kernel taps x channel blocks", what);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xs = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* os = static_cast<__nv_bfloat16*>(out);
+  if (cb == 64)
+    im2col_t_kernel<64><<<grid, 256, 0, s>>>(xs, os, batch, height, width, channels, kh, kw, OH, OW, M, ld, pixel_s2d, ones_row);
+  else
+    im2col_t_kernel<32><<<grid, 256, 0, s>>>(xs, os, batch, height, width, channels, kh, kw, OH, OW, M, ld, pixel_s2d, ones_row);
   return xa::check_launch(what);
 }

@@ -163,12 +163,23 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
         }
         if (row < p.m && col0 < p.n) {
           float f[32];
+          // ReLU-derivative mask: four 16-B loads per 32 columns when the layout allows, scalar otherwise
+          uint4 mraw[4];
+          const bool mvec = p.mask != nullptr && col0 + 32 <= p.n && (p.ldc % 8) == 0 && xa::aligned(p.mask, 16);
+          if (mvec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mraw[q] = __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.ldc + col0) + q);
+          }
+          const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(mraw);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(v[j]);
             if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
             if (p.relu) x = fmaxf(x, 0.0f);
-            if (p.mask != nullptr && col0 + j < p.n && !(__bfloat162float(p.mask[row * p.ldc + col0 + j]) > 0.0f)) x = 0.0f;
+            if (p.mask != nullptr && col0 + j < p.n) {
+              const float mval = mvec ? __bfloat162float(mv[j]) : __bfloat162float(p.mask[row * p.ldc + col0 + j]);
+              if (!(mval > 0.0f)) x = 0.0f;
+            }
             f[j] = x;
           }
           if (vec_ok && col0 + 32 <= p.n) {
@@ -320,7 +331,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(256) to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
                                                        int64_t cols, int64_t ld_dst, int transpose) {
   __shared__ float tile[32][33];
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int j = ty; j < 32; j += 8) {
     const int64_t r = r0 + j, c = c0 + tx;
@@ -345,8 +356,8 @@ extern "C" int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t ro
   XA_REQUIRE(src && dst, XA_EINVAL, "xa_to_bf16: null pointer");
   XA_REQUIRE(rows > 0 && cols > 0 && ld_dst >= (transpose ? rows : cols), XA_EINVAL, "xa_to_bf16: rows=%lld cols=%lld ld_dst=%lld",
              static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld_dst));
-  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
-  XA_REQUIRE(grid.y <= 65535, XA_EOVERFLOW, "xa_to_bf16: too many rows for one launch (%lld)", static_cast<long long>(rows));
+  const dim3 grid(static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>((cols + 31) / 32));  // rows may be millions
+  XA_REQUIRE(grid.y <= 65535, XA_EOVERFLOW, "xa_to_bf16: too many columns for one launch (%lld)", static_cast<long long>(cols));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (src_is_f32)
     to_bf16_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, cols, ld_dst, transpose);

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'im2col_t_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'im2col_t_bf16', 'transpose_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -455,14 +455,32 @@ def space_to_depth_u8_bf16(frames, block, *, scale_255=True, out=None, stream=No
     return y
 
 
-def im2col_t_bf16(x, kh, kw, *, pixel_s2d=False, pad_to=8, stream=None):
-    """x [B,H,W,C] bf16 -> Xcol^T [kh*kw*C, M'] (M' = B*OH*OW rounded up to `pad_to`, zero-filled): the K-major
-    operand of the weight-gradient product dW = gemm_bf16_tn(dY^T, Xcol^T)."""
+def im2col_t_bf16(x, kh, kw, *, pixel_s2d=False, ones_row=False, pad_to=8, stream=None):
+    """x [B,H,W,C] bf16 -> Xcol^T [kh*kw*C (+8 with ones_row), M'] (M' = B*OH*OW rounded up to 8, zero-filled):
+    the K-major operand of the weight-gradient product dW = gemm_bf16_tn(dY^T, Xcol^T).  With ones_row, row
+    kh*kw*C is all ones (the product's column kh*kw*C is then the bias gradient) and 7 zero rows follow."""
     xx = _dev(x, 'bfloat16')
     B, H, W, C = xx.shape
     M = B * (H - kh + 1) * (W - kw + 1)
     ld = -(-M // pad_to) * pad_to
-    out = torch.empty((kh * kw * C, ld), dtype=torch.bfloat16, device=_device_of(xx))
-    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), B, H, W, C, kh, kw, ld, int(bool(pixel_s2d)), _stream(stream))
+    K = kh * kw * C
+    if ones_row:
+        out = torch.empty((K + 8, ld), dtype=torch.bfloat16, device=_device_of(xx))
+        out[K + 1:].zero_()
+    else:
+        out = torch.empty((K, ld), dtype=torch.bfloat16, device=_device_of(xx))
+    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), B, H, W, C, kh, kw, ld, int(bool(pixel_s2d)), int(bool(ones_row)),
+              _stream(stream))
+    _count()
+    return out
+
+
+def transpose_bf16(x2d, *, stream=None):
+    """[M, C] bf16 (C % 32 == 0) -> [C, M'] bf16, M' = M rounded up to 8 (zero-filled): the fast path of to_bf16(transpose=True)."""
+    xx = _dev(x2d, 'bfloat16')
+    M, C = xx.shape
+    ld = -(-M // 8) * 8
+    out = torch.empty((C, ld), dtype=torch.bfloat16, device=_device_of(xx))
+    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), 1, 1, M, C, 1, 1, ld, 0, 0, _stream(stream))
     _count()
     return out
