@@ -121,7 +121,7 @@ def test_gemm_split_k_matches_unsplit_and_reference(m, n, k):
     assert float((split.double() - want).abs().max()) <= 5e-5 * scale
     # one TMEM accumulator over 400k products loses low bits (tensor-core accumulation is not a chain of IEEE adds):
     # another reason the long-K products are split
-    assert float((plain.double() - want).abs().max()) <= (2e-5 if k < 50000 else 2e-3) * scale
+    assert float((plain.double() - want).abs().max()) <= (5e-5 if k < 10000 else 2e-3) * scale
 
 
 @pytest.mark.timeout(60)

@@ -379,24 +379,21 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __re
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
   const int cblocks = C / kCB;
   const int taps = KH * KW;
-  if (static_cast<int>(blockIdx.y) == taps * cblocks) {  // extra block row: the row of ones (bias gradient for free)
-    if (ones_row) {
-      const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
-      for (int i = threadIdx.x; i < 64; i += 256) {
-        const int64_t m = m0 + i;
-        if (m < ld) out[static_cast<int64_t>(taps) * C * ld + m] = m < M ? one : zero;
-      }
+  if (ones_row) {  // the row of ones (bias gradient for free)
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+    for (int i = threadIdx.x; i < 64; i += 256) {
+      const int64_t m = m0 + i;
+      if (m < ld) out[static_cast<int64_t>(taps) * C * ld + m] = m < M ? one : zero;
     }
-    return;
   }
-  const int tap = blockIdx.y / cblocks, c0 = (blockIdx.y - tap * cblocks) * kCB;
-  const int kh = tap / KW, kw = tap - kh * KW;
+  // pixel coordinates of this thread's load row(s) are the same for every tap: decode once
   const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
+  constexpr int kPasses = 64 / kPixPerPass;
+  int64_t base[kPasses];
 #pragma unroll
-  for (int pass = 0; pass < 64 / kPixPerPass; ++pass) {
-    const int pi = pass * kPixPerPass + prow;
-    const int64_t m = m0 + pi;
-    uint4 v = make_uint4(0, 0, 0, 0);
+  for (int pass = 0; pass < kPasses; ++pass) {
+    const int64_t m = m0 + pass * kPixPerPass + prow;
+    base[pass] = -1;
     if (m < M) {
       int ox, oy;
       int64_t b;
@@ -410,24 +407,36 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __re
         ox = static_cast<int>(m % OW), oy = static_cast<int>((m / OW) % OH);
         b = m / (static_cast<int64_t>(OW) * OH);
       }
-      v = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + oy + kh) * W + ox + kw) * C + c0) + vec);
+      base[pass] = ((b * H + oy) * W + ox) * C;
     }
-    *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
   }
-  __syncthreads();
-  // 8 threads per channel row, each packs 8 pixels of that channel into one 16-B store
-  constexpr int kRowsPerPass = 256 / 8;
+  // one block walks every (tap, channel block) of its 64 pixels: the taps re-read the same few input rows, which are
+  // still in L1/L2, so the activation comes from HBM once instead of KH*KW times
+  for (int blk = 0; blk < taps * cblocks; ++blk) {
+    const int tap = blk / cblocks, c0 = (blk - tap * cblocks) * kCB;
+    const int kh = tap / KW, kw = tap - kh * KW;
 #pragma unroll
-  for (int pass = 0; pass < kCB / kRowsPerPass; ++pass) {
-    const int ci = pass * kRowsPerPass + threadIdx.x / 8;
-    const int pg = (threadIdx.x & 7) * 8;
-    const int64_t m = m0 + pg;
-    if (m < ld) {  // ld is a multiple of 8, so a group of 8 pixels is all-in or all-out
-      __nv_bfloat16 vals[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
-      *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * C + c0 + ci) * ld + m) = *reinterpret_cast<uint4*>(vals);
+    for (int pass = 0; pass < kPasses; ++pass) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (base[pass] >= 0) v = __ldg(reinterpret_cast<const uint4*>(x + base[pass] + (static_cast<int64_t>(kh) * W + kw) * C + c0) + vec);
+      *reinterpret_cast<uint4*>(tile + (pass * kPixPerPass + prow) * kPitch + vec * 8) = v;
     }
+    __syncthreads();
+    // 8 threads per channel row, each packs 8 pixels of that channel into one 16-B store
+    constexpr int kRowsPerPass = 256 / 8;
+#pragma unroll
+    for (int pass = 0; pass < kCB / kRowsPerPass; ++pass) {
+      const int ci = pass * kRowsPerPass + threadIdx.x / 8;
+      const int pg = (threadIdx.x & 7) * 8;
+      const int64_t m = m0 + pg;
+      if (m < ld) {  // ld is a multiple of 8, so a group of 8 pixels is all-in or all-out
+        __nv_bfloat16 vals[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
+        *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * C + c0 + ci) * ld + m) = *reinterpret_cast<uint4*>(vals);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -445,8 +454,7 @@ extern "C" int xa_im2col_t_bf16(const void* x, void* out, int batch, int height,
   XA_REQUIRE(!pixel_s2d || (OH % 2 == 0 && OW % 2 == 0), XA_EINVAL, "%s: pixel_s2d needs even output size", what);
   XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
   const int cb = channels % 64 == 0 ? 64 : 32;
-  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(kh * kw * (channels / cb) + (ones_row ? 1 : 0)));
-  XA_REQUIRE(grid.y <= 65535, XA_EOVERFLOW, "%s: too many kernel taps x channel blocks", what);
+  const dim3 grid(static_cast<unsigned>((ld + 63) / 64));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xs = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* os = static_cast<__nv_bfloat16*>(out);
