@@ -543,3 +543,63 @@ def test_trpo_whole_batch_advantage_normalisation():
     want = (adv - adv.mean()) / adv.std()
     got = ops.normalize_advantages(cu(ret.reshape(-1)), cu(ro.values.reshape(-1)), 0.0)
     close(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- small configs: graphs, A2C
+def test_hotpath_cuda_graph_replay_equals_eager():
+    """C1-shaped (CartPole: T=128, E=16, 4 fp32 features, 2 actions): one graph replay == the eager step."""
+    from xagents_b200.hotpath import PPOHotPath
+    T, E, A = 128, 16, 2
+    ro = synthetic.make_rollout(T, E, obs_shape=(4,), obs_dtype='float32', n_actions=A, epochs=4, p_done=0.02)
+    want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
+                                 ro.permutations, ro.new_logits, ro.new_values, mini_batches=4)
+    hp = PPOHotPath(T, E, (4,), A, obs_dtype=torch.float32, device=DEV)
+    hp.load(ro)
+    hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
+    for i, w in enumerate(want['minibatches']):
+        hp.actor_out[i].copy_(torch.as_tensor(ro.new_logits[w['idx']]))
+        hp.critic_out[i].copy_(torch.as_tensor(ro.new_values[w['idx']]))
+    hp.prepare()
+    hp.run()
+    torch.cuda.synchronize()
+    eager = hp.scalars.clone()
+    replay = hp.capture()
+    hp.scalars.zero_()
+    hp.returns.zero_()
+    replay()
+    torch.cuda.synchronize()
+    assert torch.equal(hp.scalars, eager)
+    close(hp.returns, want['returns'])
+    for i, w in enumerate(want['minibatches']):
+        scale = max(abs(float(w[k])) for k in ('loss', 'pg', 'vl', 'entropy'))
+        assert abs(float(hp.scalars[i, 0]) - w['loss']) <= REL * scale
+    hp.rewards.mul_(2.0)                                   # new data in the same buffers, replay again
+    replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(hp.scalars, eager)
+    hp.run()                                               # and the eager path still works after the capture
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('case', ['a2c_image', 'a2c_vector'])
+def test_a2c_hotpath_vs_reference_golden(golden, case):
+    from xagents_b200.hotpath import A2CHotPath
+    g = golden(case)
+    T, E = g['returns'].shape
+    A = g['actor'].shape[1]
+    hp = A2CHotPath(T, E, A, gamma=float(g['gamma']), entropy_coef=float(g['entropy_coef']),
+                    value_loss_coef=float(g['value_loss_coef']), device=DEV, scan_mode='sequential')
+    tm = lambda flat: np.ascontiguousarray(np.asarray(flat).reshape(E, T).T)
+    hp.rewards.copy_(cu(g['rewards']))
+    hp.dones.copy_(cu(g['dones']))
+    hp.last_values.copy_(cu(g['next_values']))
+    hp.values.copy_(cu(tm(g['flat_values'])))
+    hp.actions.copy_(cu(tm(g['flat_actions'])))
+    # model outputs arrive env-major in the fixture; the hot path consumes them in time-major sample order
+    hp.actor_out.copy_(cu(g['actor'].reshape(E, T, A).transpose(1, 0, 2).reshape(T * E, A)))
+    hp.critic_out.copy_(cu(tm(g['critic'])).reshape(-1))
+    hp.run()
+    torch.cuda.synchronize()
+    assert np.array_equal(hp.returns.cpu().numpy(), g['returns'])
+    ref = float(g['loss'][0])
+    assert abs(float(hp.scalars[0]) - ref) <= REL * max(abs(ref), abs(float(hp.scalars[2])), abs(float(hp.scalars[3])))

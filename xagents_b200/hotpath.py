@@ -268,6 +268,29 @@ class PPOHotPath:
             if two:
                 self._loss_done[g].record(cs)
 
+    # ---------------------------------------------------------------------------------- CUDA graph
+    def capture(self):
+        """Capture one train step (both streams, every launch) into a CUDA graph and return a replay callable.
+        For latency-bound shapes (CartPole-sized rollouts move a few hundred KB) the step is nothing but launch
+        overhead; a replay is one launch.  Buffers keep their addresses, so new rollouts / permutations / model
+        outputs are simply written into them before each replay."""
+        if self._calls is None:
+            self.prepare()
+        assert self.comm is None or self.comm.world_size == 1, 'graph capture covers the single-GPU pipeline'
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        capture_stream = torch.cuda.Stream(self.device)
+        eager_streams = (self.compute_stream, self.data_stream)
+        with torch.cuda.stream(capture_stream):
+            self.prepare(capture_stream)                    # re-resolve the launches onto the capturing stream
+            self.run()                                      # warm-up outside the capture (lazy module loading)
+            capture_stream.synchronize()
+            with torch.cuda.graph(graph, stream=capture_stream):
+                self.run()
+        self._graph = graph                                  # keep alive
+        self.prepare(eager_streams[0])                       # eager path stays usable
+        return graph.replay
+
     def minibatch_views(self, i):
         """(states, actions, returns, old_values, old_log_probs) staging views of minibatch i."""
         _, slot, row0 = self._mb_place[i]
@@ -295,3 +318,60 @@ class _null:
 
     def __exit__(self, *exc):
         return False
+
+
+class A2CHotPath:
+    """A2C.train_step's arithmetic on the device (xagents/a2c/agent.py:173-218): n-step returns over the
+    time-major rollout, then the loss + gradients over all T*E samples in time-major order (the loss is a mean
+    over the batch, so the env-major flatten of np_train_step changes nothing but the summation order).
+    Two launches per train step."""
+
+    def __init__(self, n_steps, n_envs, n_actions, *, gamma=0.99, entropy_coef=0.01, value_loss_coef=0.5, actor_kind='logits',
+                 device='cuda:0', scan_mode='auto'):
+        self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
+        self.N = self.T * self.E
+        self.gamma, self.entropy_coef, self.value_loss_coef = float(gamma), float(entropy_coef), float(value_loss_coef)
+        self.actor_kind, self.scan_mode = actor_kind, scan_mode
+        self.device = torch.device(device)
+        dev, f32, T, E, N, A = self.device, torch.float32, self.T, self.E, self.N, self.A
+        self.rewards = torch.empty((T, E), dtype=f32, device=dev)
+        self.values = torch.empty((T, E), dtype=f32, device=dev)
+        self.last_values = torch.empty((E,), dtype=f32, device=dev)
+        self.dones = torch.empty((T + 1, E), dtype=f32, device=dev)
+        self.actions = torch.empty((T, E), dtype=f32, device=dev)
+        self.returns = torch.empty((T, E), dtype=f32, device=dev)
+        self.actor_out = torch.empty((N, A), dtype=f32, device=dev)       # forward pass outputs, time-major sample order
+        self.critic_out = torch.empty((N,), dtype=f32, device=dev)
+        self.scalars = torch.zeros(4, dtype=f32, device=dev)
+        self.d_actor = torch.empty((N, A), dtype=f32, device=dev)
+        self.d_values = torch.empty((N,), dtype=f32, device=dev)
+        nbytes = _ffi.lib().xa_loss_workspace_bytes(N)
+        self.workspace = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        self.kernel_launches_per_step = 2
+        self._args = None
+
+    def prepare(self, stream=None):
+        lib = _ffi.lib()
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        s = ctypes.c_void_p(self.stream.cuda_stream)
+        self._returns = (lib.xa_nstep_returns_f32, (_p(self.rewards), _p(self.dones), _p(self.last_values), _p(self.returns), self.T,
+                                                    self.E, self.gamma, SCAN_MODES[self.scan_mode], s))
+        a = _ffi.LossArgs()
+        a.actor_out, a.values = self.actor_out.data_ptr(), self.critic_out.data_ptr()
+        a.actions, a.old_values, a.returns = self.actions.data_ptr(), self.values.data_ptr(), self.returns.data_ptr()
+        a.old_log_probs = a.idx = a.advantages = a.moments = None
+        a.n, a.n_actions, a.actor_kind = self.N, self.A, ACTOR_KINDS[self.actor_kind]
+        a.ent_coef, a.vf_coef = self.entropy_coef, self.value_loss_coef
+        a.out_scalars, a.d_actor, a.d_values = self.scalars.data_ptr(), self.d_actor.data_ptr(), self.d_values.data_ptr()
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 8
+        self._args = a
+        self._loss = (lib.xa_a2c_loss_f32, (ctypes.byref(a), s))
+        return self
+
+    def run(self):
+        if self._args is None:
+            self.prepare()
+        for tag, (fn, args) in (('nstep_returns', self._returns), ('a2c_loss', self._loss)):
+            rc = fn(*args)
+            if rc != 0:
+                raise _ffi.XAError(tag, rc, _ffi.lib().xa_last_error().decode('utf-8', 'replace'))
