@@ -155,10 +155,16 @@ class PPOHotPath:
     def prepare(self, stream=None):
         """Resolve every launch of one train step to (cfunc, args) on fixed device pointers."""
         lib = _ffi.lib()
-        self.compute_stream = stream if stream is not None else torch.cuda.current_stream(self.device)
-        self.data_stream = torch.cuda.Stream(self.device) if self.overlap else self.compute_stream
-        sc = ctypes.c_void_p(self.compute_stream.cuda_stream)
-        sd = ctypes.c_void_p(self.data_stream.cuda_stream)
+        if self.device.type != 'cuda':
+            # planning only (host-logic tests): the launch tables are built, but there is no CPU path -- run()
+            # fails in the first launch
+            self.compute_stream = self.data_stream = None
+            sc = sd = ctypes.c_void_p(None)
+        else:
+            self.compute_stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+            self.data_stream = torch.cuda.Stream(self.device) if self.overlap else self.compute_stream
+            sc = ctypes.c_void_p(self.compute_stream.cuda_stream)
+            sd = ctypes.c_void_p(self.data_stream.cuda_stream)
         T, E, N, B = self.T, self.E, self.N, self.B
         self._gae = (lib.xa_gae_f32, (_p(self.rewards), _p(self.values), _p(self.last_values), _p(self.dones),
                                       _p(self.returns), _p(None), T, E, self.gamma, self.lam, SCAN_MODES[self.scan_mode], sc))
@@ -218,9 +224,10 @@ class PPOHotPath:
             a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 8
             self._loss_args.append(a)
             self._losses.append((lib.xa_ppo_loss_f32, (ctypes.byref(a), sc)))
-        self._gather_done = [torch.cuda.Event() for _ in range(self.n_groups)]
-        self._loss_done = [torch.cuda.Event() for _ in range(self.n_groups)]
-        self._fork = torch.cuda.Event()
+        if self.device.type == 'cuda':
+            self._gather_done = [torch.cuda.Event() for _ in range(self.n_groups)]
+            self._loss_done = [torch.cuda.Event() for _ in range(self.n_groups)]
+            self._fork = torch.cuda.Event()
         self._calls = True
         self.kernel_launches_per_step = 2 + self.n_mb + self.n_groups
         return self
