@@ -1,0 +1,274 @@
+// Convolution weight gradient as an implicit GEMM on the tensor cores, with no im2col matrix.
+//
+//   dW[n, (kh, kw, c)] = sum over output pixels (b, y, x) of  dY[b, y, x, n] * X[b, y + kh, x + kw, c]
+//
+// Put dY on the INPUT grid (zero where y >= OH or x >= OW) and flatten pixels as q = (b*H + y)*W + x.  A kernel tap is
+// then nothing but a shift of the flattened pixel index, q -> q + kh*W + kw (whenever the shift would wrap into the
+// next row or image, dY is zero), so with both operands transposed to pixel-contiguous form
+//
+//   dW_tap[n, c] = sum_q dYt[n, q] * Xt[c, q + shift_tap]        dYt [N, Q], Xt [C, Q]   (bf16, K-major)
+//
+// every tap is the same K-major GEMM over q with the B operand's TMA window moved by `shift_tap` elements.  One CTA
+// owns a slice of the q range (split-K over the SMs) and keeps the accumulators of ALL taps in TMEM (taps*C <= 512
+// columns), so dYt is fetched once per slice and the overlapping Xt windows of the taps come out of L2.  Per slice the
+// fp32 partial [N, taps*C] goes to a workspace; a second pass adds the slices in order (deterministic).
+// HBM traffic: (N + C) * Q * 2 bytes, against 2 * taps * C * Q * 2 for a materialised im2col operand.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace xa_tc;
+
+constexpr int kMaxTaps = 16;
+
+struct WgradParams {
+  float* partial;  // [splits, n_out, ld_out]
+  int n_out, C, n_taps, tap0, ld_out;
+  int64_t q_total;
+  int kb_per_split, splits;
+  int shift[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                         const __grid_constant__ CUtensorMap map_x, const WgradParams p, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t tile_a = kBlockM * kBlockK * 2;                      // dYt tile: 128 rows (n; rows >= n_out are zero-filled)
+  const uint32_t tile_b = static_cast<uint32_t>(p.C) * kBlockK * 2;   // Xt tile of one tap: C rows
+  const uint32_t stage_bytes = tile_a + p.n_taps * tile_b;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t k_blocks = (p.q_total + kBlockK - 1) / kBlockK;
+  const int split = blockIdx.x;
+  const int64_t kb0 = static_cast<int64_t>(split) * p.kb_per_split;
+  const int64_t kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      xa::mbar_init(full + s, 1);
+      xa::mbar_init(empty + s, 1);
+    }
+    xa::mbar_init(acc_full, 1);
+    xa::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      uint32_t it = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        const uint32_t round = it / stages;
+        if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+        uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
+        xa::mbar_expect_tx(full + s, stage_bytes);
+        const int q0 = static_cast<int>(kb * kBlockK);
+        tma_load_2d(a_dst, &map_dy, q0, 0, full + s);
+        for (int t = 0; t < p.n_taps; ++t) tma_load_2d(a_dst + tile_a + t * tile_b, &map_x, q0 + p.shift[t], 0, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer: one accumulator column block per tap
+      const uint32_t idesc = make_idesc(kBlockM, p.C);
+      uint32_t it = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait_wd(full + s, (it / stages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint8_t* base = smem + static_cast<size_t>(s) * stage_bytes;
+        const uint64_t da = make_smem_desc(base);
+        for (int t = 0; t < p.n_taps; ++t) {
+          const uint64_t db = make_smem_desc(base + tile_a + t * tile_b);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_base + t * p.C, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---- epilogue: fp32 partial of this slice
+    const int quad = warp & 3;
+    mbar_wait_wd(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int n = quad * 32 + lane;
+    const int cols = p.n_taps * p.C;
+    float* dst = p.partial + (static_cast<int64_t>(split) * p.n_out + n) * p.ld_out + static_cast<int64_t>(p.tap0) * p.C;
+#pragma unroll 1
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
+      if (n < p.n_out && kb1 > kb0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst + c0)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      } else if (n < p.n_out) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst + c0)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t total,
+                                                            int splits) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.0f;
+    for (int s = 0; s < splits; ++s) acc += partial[static_cast<int64_t>(s) * total + i];
+    dw[i] = acc;
+  }
+}
+
+// dY rows (pixels in natural (b, y, x) order, or in the 2x2 space-to-depth order (b, y/2, x/2, y%2, x%2) of a layer
+// written with out_s2d) -> dYt [N, ld] on the INPUT grid: column q = (b*H + y)*W + x holds dY of output pixel (y, x)
+// or zero when y >= OH or x >= OW.  64 grid pixels x N channels per block through shared memory.
+template <int kN>
+__global__ void __launch_bounds__(256) dy_to_grid_t_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out, int B,
+                                                            int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
+  constexpr int kPitch = kN + 8;
+  constexpr int kVecPerPix = kN / 8;
+  constexpr int kPixPerPass = 256 / kVecPerPix;
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * kPitch];
+  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int64_t Q = static_cast<int64_t>(B) * H * W;
+  const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
+#pragma unroll
+  for (int pass = 0; pass < 64 / kPixPerPass; ++pass) {
+    const int pi = pass * kPixPerPass + prow;
+    const int64_t q = q0 + pi;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q < Q) {
+      const int x = static_cast<int>(q % W), y = static_cast<int>((q / W) % H);
+      const int64_t b = q / (static_cast<int64_t>(W) * H);
+      if (y < OH && x < OW) {
+        const int64_t r = s2d_order ? ((b * (OH / 2) + y / 2) * (OW / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1)
+                                    : (b * OH + y) * OW + x;
+        v = __ldg(reinterpret_cast<const uint4*>(dy + r * kN) + vec);
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < kN / 32; ++pass) {
+    const int ci = pass * 32 + threadIdx.x / 8;
+    const int pg = (threadIdx.x & 7) * 8;
+    const int64_t q = q0 + pg;
+    if (q < ld) {
+      __nv_bfloat16 vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
+      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(ci) * ld + q) = *reinterpret_cast<uint4*>(vals);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int xa_dy_to_grid_t_bf16(const void* dy, void* out, int n_out, int batch, int height, int width, int out_h, int out_w, int64_t ld,
+                         int s2d_order, xa_stream_t stream) {
+  const char* what = "xa_dy_to_grid_t_bf16";
+  XA_REQUIRE(dy && out, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(n_out == 32 || n_out == 64, XA_EINVAL, "%s: n_out=%d (32 or 64 supported)", what, n_out);
+  XA_REQUIRE(batch > 0 && out_h > 0 && out_w > 0 && out_h <= height && out_w <= width, XA_EINVAL, "%s: bad shape", what);
+  const int64_t Q = static_cast<int64_t>(batch) * height * width;
+  XA_REQUIRE(ld >= Q && ld % 8 == 0, XA_EINVAL, "%s: ld=%lld must be a multiple of 8 and >= %lld", what, static_cast<long long>(ld),
+             static_cast<long long>(Q));
+  XA_REQUIRE(!s2d_order || (out_h % 2 == 0 && out_w % 2 == 0), XA_EINVAL, "%s: s2d order needs even output size", what);
+  XA_REQUIRE(xa::aligned(dy, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
+  const unsigned grid = static_cast<unsigned>((ld + 63) / 64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_out == 64)
+    dy_to_grid_t_kernel<64><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(out), batch, height,
+                                                  width, out_h, out_w, ld, s2d_order);
+  else
+    dy_to_grid_t_kernel<32><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(out), batch, height,
+                                                  width, out_h, out_w, ld, s2d_order);
+  return xa::check_launch(what);
+}
+
+int64_t xa_conv_wgrad_workspace_bytes(int n_out, int channels, int kh, int kw) {
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  return static_cast<int64_t>(sms) * n_out * kh * kw * channels * static_cast<int64_t>(sizeof(float));
+}
+
+int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, int channels, int kh, int kw, int width, int64_t q_total,
+                       int64_t ld_dy, int64_t ld_x, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
+  const char* what = "xa_conv_wgrad_bf16";
+  XA_REQUIRE(dyt && xt && dw && workspace, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(n_out > 0 && n_out <= kBlockM && (channels == 64 || channels == 128) && kh > 0 && kw > 0 && kh * kw <= kMaxTaps, XA_EINVAL,
+             "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
+  XA_REQUIRE(q_total > 0 && ld_dy >= q_total && ld_x >= q_total && ld_dy % 8 == 0 && ld_x % 8 == 0, XA_EINVAL, "%s: bad pitches", what);
+  XA_REQUIRE(xa::aligned(dyt, 16) && xa::aligned(xt, 16) && xa::aligned(dw, 16) && xa::aligned(workspace, 16), XA_EALIGN,
+             "%s: 16-byte alignment required", what);
+  XA_REQUIRE(workspace_bytes >= xa_conv_wgrad_workspace_bytes(n_out, channels, kh, kw), XA_ENOSPACE, "%s: workspace too small", what);
+  const int taps = kh * kw, ld_out = taps * channels;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t k_blocks = (q_total + kBlockK - 1) / kBlockK;
+  int splits = static_cast<int>(k_blocks < sms ? k_blocks : sms);
+  const int kb_per = static_cast<int>((k_blocks + splits - 1) / splits);
+  splits = static_cast<int>((k_blocks + kb_per - 1) / kb_per);
+  CUtensorMap mdy, mx;
+  if (int rc = make_map_2d(&mdy, dyt, n_out, ld_dy, kBlockM, what)) return rc;   // 128-row box: rows >= n_out zero-filled
+  if (int rc = make_map_2d(&mx, xt, channels, ld_x, channels, what)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) {
+      xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured_dev = dev;
+  }
+  const int taps_per_launch = 512 / channels;
+  for (int tap0 = 0; tap0 < taps; tap0 += taps_per_launch) {
+    WgradParams p{};
+    p.partial = static_cast<float*>(workspace);
+    p.n_out = n_out, p.C = channels, p.tap0 = tap0, p.ld_out = ld_out, p.q_total = q_total;
+    p.n_taps = taps - tap0 < taps_per_launch ? taps - tap0 : taps_per_launch;
+    p.kb_per_split = kb_per, p.splits = splits;
+    for (int t = 0; t < p.n_taps; ++t) p.shift[t] = ((tap0 + t) / kw) * width + (tap0 + t) % kw;
+    const size_t stage = static_cast<size_t>(kBlockM) * kBlockK * 2 + static_cast<size_t>(p.n_taps) * channels * kBlockK * 2;
+    int stages = static_cast<int>((200 * 1024) / stage);
+    if (stages > 6) stages = 6;
+    XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: stage of %zu bytes does not fit twice in shared memory", what, stage);
+    const size_t smem = stages * stage + 1024 + 256;
+    wgrad_kernel<<<splits, kThreads, smem, s>>>(mdy, mx, p, stages);
+    if (int rc = xa::check_launch(what)) return rc;
+  }
+  const int64_t total = static_cast<int64_t>(n_out) * ld_out;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(static_cast<const float*>(workspace), dw, total, splits);
+  return xa::check_launch(what);
+}
+
+}  // extern "C"

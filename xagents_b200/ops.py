@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'im2col_t_bf16', 'transpose_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -484,3 +484,30 @@ def transpose_bf16(x2d, *, stream=None):
     _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), 1, 1, M, C, 1, 1, ld, 0, 0, _stream(stream))
     _count()
     return out
+
+
+def conv_wgrad_bf16(dy, x, kh, kw, *, s2d_order=False, workspace=None, stream=None):
+    """Weight (and bias) gradient of a stride-1 NHWC convolution on tcgen05 without an im2col matrix.
+    dy: [pixels, N] bf16 rows of the output gradient ((b,y,x) order, or the space-to-depth order of a layer written
+    with out_s2d); x: the layer input [B,H,W,C] bf16.  Returns (dW [N, kh*kw*C] fp32 with K ordered (kh,kw,c), db [N])."""
+    xx, dd = _dev(x, 'bfloat16'), _dev(dy, 'bfloat16')
+    B, H, W, C = xx.shape
+    N = dd.shape[-1]
+    OH, OW = H - kh + 1, W - kw + 1
+    Q = B * H * W
+    ld = -(-Q // 8) * 8
+    dev = _device_of(xx)
+    st = _stream(stream)
+    dyt = torch.empty((N, ld), dtype=torch.bfloat16, device=dev)
+    _ffi.call('xa_dy_to_grid_t_bf16', _ptr(dd), _tptr(dyt), N, B, H, W, OH, OW, ld, int(bool(s2d_order)), st)
+    xt = torch.empty((C, ld), dtype=torch.bfloat16, device=dev)
+    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(xt), 1, 1, Q, C, 1, 1, ld, 0, 0, st)
+    ws_bytes = _ffi.lib().xa_conv_wgrad_workspace_bytes(N, C, kh, kw)
+    if workspace is None or workspace.numel() * workspace.element_size() < ws_bytes:
+        workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    dw = torch.empty((N, kh * kw * C), dtype=torch.float32, device=dev)
+    _ffi.call('xa_conv_wgrad_bf16', _ptr(dyt), _ptr(xt), _tptr(dw), N, C, kh, kw, W, Q, ld, ld, _tptr(workspace),
+              workspace.numel() * workspace.element_size(), st)
+    _count(3 + -(-kh * kw // (512 // C)))
+    db = dyt.sum(1, dtype=torch.float32)                       # zero-padded columns add nothing
+    return dw, db
