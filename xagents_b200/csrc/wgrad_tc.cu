@@ -8,7 +8,10 @@
 //
 //   dW_tap[n, c] = sum_q dYt[n, q] * Xt[c, q + shift_tap]        dYt [N, Q], Xt [C, Q]   (bf16, K-major)
 //
-// every tap is the same K-major GEMM over q with the B operand's TMA window moved by `shift_tap` elements.  One CTA
+// every tap is the same K-major GEMM over q with a shifted TMA window.  TMA wants the window start 16-byte aligned, so
+// the grid rows are padded to a multiple of 8 pixels (kh*W is then aligned) and the kw part of the shift is carried
+// by KW pre-shifted copies of the small operand (dYt_kw[n, q] = dYt[n, q - kw], written by xa_place_on_grid_t_bf16):
+//   dW[n, (kh,kw,c)] = sum_q dYt_kw[n, q] * Xt[c, q + kh*W].  One CTA
 // owns a slice of the q range (split-K over the SMs) and keeps the accumulators of ALL taps in TMEM (taps*C <= 512
 // columns), so dYt is fetched once per slice and the overlapping Xt windows of the taps come out of L2.  Per slice the
 // fp32 partial [N, taps*C] goes to a workspace; a second pass adds the slices in order (deterministic).
@@ -19,23 +22,21 @@ namespace {
 
 using namespace xa_tc;
 
-constexpr int kMaxTaps = 16;
-
 struct WgradParams {
   float* partial;  // [splits, n_out, ld_out]
-  int n_out, C, n_taps, tap0, ld_out;
+  int n_out, C, KW, kh0, n_kh, ld_out;  // this launch covers kernel rows kh0 .. kh0+n_kh-1, all KW columns
+  int grid_w;                           // padded grid width (multiple of 8): row shift of one kernel row
   int64_t q_total;
   int kb_per_split, splits;
-  int shift[kMaxTaps];
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                          const __grid_constant__ CUtensorMap map_x, const WgradParams p, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tile_a = kBlockM * kBlockK * 2;                      // dYt tile: 128 rows (n; rows >= n_out are zero-filled)
-  const uint32_t tile_b = static_cast<uint32_t>(p.C) * kBlockK * 2;   // Xt tile of one tap: C rows
-  const uint32_t stage_bytes = tile_a + p.n_taps * tile_b;
+  const uint32_t tile_a = kBlockM * kBlockK * 2;                      // dYt_kw tile: 128 rows (rows >= n_out are never stored)
+  const uint32_t tile_b = static_cast<uint32_t>(p.C) * kBlockK * 2;   // Xt tile of one kernel row: C rows
+  const uint32_t stage_bytes = p.KW * tile_a + p.n_kh * tile_b;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;
@@ -79,8 +80,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
         xa::mbar_expect_tx(full + s, stage_bytes);
         const int q0 = static_cast<int>(kb * kBlockK);
-        tma_load_2d(a_dst, &map_dy, q0, 0, full + s);
-        for (int t = 0; t < p.n_taps; ++t) tma_load_2d(a_dst + tile_a + t * tile_b, &map_x, q0 + p.shift[t], 0, full + s);
+        for (int kw = 0; kw < p.KW; ++kw) tma_load_2d(a_dst + kw * tile_a, &map_dy, q0, kw * p.n_out, full + s);
+        for (int j = 0; j < p.n_kh; ++j)
+          tma_load_2d(a_dst + p.KW * tile_a + j * tile_b, &map_x, q0 + (p.kh0 + j) * p.grid_w, 0, full + s);
       }
     }
   } else if (warp == 1) {
@@ -92,12 +94,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         mbar_wait_wd(full + s, (it / stages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* base = smem + static_cast<size_t>(s) * stage_bytes;
-        const uint64_t da = make_smem_desc(base);
-        for (int t = 0; t < p.n_taps; ++t) {
-          const uint64_t db = make_smem_desc(base + tile_a + t * tile_b);
+        for (int j = 0; j < p.n_kh; ++j) {
+          const uint64_t db = make_smem_desc(base + p.KW * tile_a + j * tile_b);
+          for (int kw = 0; kw < p.KW; ++kw) {
+            const uint64_t da = make_smem_desc(base + kw * tile_a);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(tmem_base + t * p.C, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(tmem_base + (j * p.KW + kw) * p.C, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+          }
         }
         umma_commit(empty + s);
       }
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     mbar_wait_wd(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int n = quad * 32 + lane;
-    const int cols = p.n_taps * p.C;
-    float* dst = p.partial + (static_cast<int64_t>(split) * p.n_out + n) * p.ld_out + static_cast<int64_t>(p.tap0) * p.C;
+    const int cols = p.n_kh * p.KW * p.C;
+    float* dst = p.partial + (static_cast<int64_t>(split) * p.n_out + n) * p.ld_out + static_cast<int64_t>(p.kh0) * p.KW * p.C;
 #pragma unroll 1
     for (int c0 = 0; c0 < cols; c0 += 32) {
       uint32_t v[32];
@@ -144,17 +148,20 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// dY rows (pixels in natural (b, y, x) order, or in the 2x2 space-to-depth order (b, y/2, x/2, y%2, x%2) of a layer
-// written with out_s2d) -> dYt [N, ld] on the INPUT grid: column q = (b*H + y)*W + x holds dY of output pixel (y, x)
-// or zero when y >= OH or x >= OW.  64 grid pixels x N channels per block through shared memory.
+// Place an NHWC tensor [B, OH, OW, kN] (rows in natural (b, y, x) order, or in the 2x2 space-to-depth order
+// (b, y/2, x/2, y%2, x%2) of a layer written with out_s2d) on a [B, H, W] pixel grid, transposed: out[c, q] with
+// q = (b*H + y)*W + x holds the value of source pixel (y, x - x_off), zero outside the source.  `copies` outputs are
+// written back to back with x_off = 0, 1, ...  64 grid pixels x kN channels per block through shared memory.
 template <int kN>
-__global__ void __launch_bounds__(256) dy_to_grid_t_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out, int B,
-                                                            int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
+__global__ void __launch_bounds__(256) place_on_grid_t_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out, int B,
+                                                               int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
   constexpr int kPitch = kN + 8;
   constexpr int kVecPerPix = kN / 8;
   constexpr int kPixPerPass = 256 / kVecPerPix;
   __shared__ __align__(16) __nv_bfloat16 tile[64 * kPitch];
   const int64_t q0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int x_off = blockIdx.y;
+  out += static_cast<int64_t>(blockIdx.y) * kN * ld;
   const int64_t Q = static_cast<int64_t>(B) * H * W;
   const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
 #pragma unroll
@@ -163,12 +170,12 @@ __global__ void __launch_bounds__(256) dy_to_grid_t_kernel(const __nv_bfloat16* 
     const int64_t q = q0 + pi;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (q < Q) {
-      const int x = static_cast<int>(q % W), y = static_cast<int>((q / W) % H);
+      const int x = static_cast<int>(q % W) - x_off, y = static_cast<int>((q / W) % H);
       const int64_t b = q / (static_cast<int64_t>(W) * H);
-      if (y < OH && x < OW) {
+      if (y < OH && x >= 0 && x < OW) {
         const int64_t r = s2d_order ? ((b * (OH / 2) + y / 2) * (OW / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1)
                                     : (b * OH + y) * OW + x;
-        v = __ldg(reinterpret_cast<const uint4*>(dy + r * kN) + vec);
+        v = __ldg(reinterpret_cast<const uint4*>(src + r * kN) + vec);
       }
     }
     *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
@@ -192,25 +199,28 @@ __global__ void __launch_bounds__(256) dy_to_grid_t_kernel(const __nv_bfloat16* 
 
 extern "C" {
 
-int xa_dy_to_grid_t_bf16(const void* dy, void* out, int n_out, int batch, int height, int width, int out_h, int out_w, int64_t ld,
-                         int s2d_order, xa_stream_t stream) {
-  const char* what = "xa_dy_to_grid_t_bf16";
-  XA_REQUIRE(dy && out, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(n_out == 32 || n_out == 64, XA_EINVAL, "%s: n_out=%d (32 or 64 supported)", what, n_out);
-  XA_REQUIRE(batch > 0 && out_h > 0 && out_w > 0 && out_h <= height && out_w <= width, XA_EINVAL, "%s: bad shape", what);
-  const int64_t Q = static_cast<int64_t>(batch) * height * width;
+int xa_place_on_grid_t_bf16(const void* src, void* out, int channels, int batch, int grid_h, int grid_w, int src_h, int src_w,
+                            int64_t ld, int s2d_order, int copies, xa_stream_t stream) {
+  const char* what = "xa_place_on_grid_t_bf16";
+  XA_REQUIRE(src && out, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(channels == 32 || channels == 64 || channels == 128, XA_EINVAL, "%s: channels=%d (32, 64 or 128 supported)", what, channels);
+  XA_REQUIRE(batch > 0 && src_h > 0 && src_w > 0 && src_h <= grid_h && src_w + copies - 1 <= grid_w && copies > 0 && copies <= 8, XA_EINVAL,
+             "%s: bad shape", what);
+  const int64_t Q = static_cast<int64_t>(batch) * grid_h * grid_w;
   XA_REQUIRE(ld >= Q && ld % 8 == 0, XA_EINVAL, "%s: ld=%lld must be a multiple of 8 and >= %lld", what, static_cast<long long>(ld),
              static_cast<long long>(Q));
-  XA_REQUIRE(!s2d_order || (out_h % 2 == 0 && out_w % 2 == 0), XA_EINVAL, "%s: s2d order needs even output size", what);
-  XA_REQUIRE(xa::aligned(dy, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
-  const unsigned grid = static_cast<unsigned>((ld + 63) / 64);
+  XA_REQUIRE(!s2d_order || (src_h % 2 == 0 && src_w % 2 == 0), XA_EINVAL, "%s: s2d order needs an even source size", what);
+  XA_REQUIRE(xa::aligned(src, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
+  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(copies));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (n_out == 64)
-    dy_to_grid_t_kernel<64><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(out), batch, height,
-                                                  width, out_h, out_w, ld, s2d_order);
+  const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(src);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (channels == 128)
+    place_on_grid_t_kernel<128><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
+  else if (channels == 64)
+    place_on_grid_t_kernel<64><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
   else
-    dy_to_grid_t_kernel<32><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(out), batch, height,
-                                                  width, out_h, out_w, ld, s2d_order);
+    place_on_grid_t_kernel<32><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
   return xa::check_launch(what);
 }
 
@@ -219,25 +229,26 @@ int64_t xa_conv_wgrad_workspace_bytes(int n_out, int channels, int kh, int kw) {
   return static_cast<int64_t>(sms) * n_out * kh * kw * channels * static_cast<int64_t>(sizeof(float));
 }
 
-int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, int channels, int kh, int kw, int width, int64_t q_total,
-                       int64_t ld_dy, int64_t ld_x, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
+int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, int channels, int kh, int kw, int grid_w, int64_t q_total,
+                       int64_t ld, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
   const char* what = "xa_conv_wgrad_bf16";
   XA_REQUIRE(dyt && xt && dw && workspace, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(n_out > 0 && n_out <= kBlockM && (channels == 64 || channels == 128) && kh > 0 && kw > 0 && kh * kw <= kMaxTaps, XA_EINVAL,
-             "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
-  XA_REQUIRE(q_total > 0 && ld_dy >= q_total && ld_x >= q_total && ld_dy % 8 == 0 && ld_x % 8 == 0, XA_EINVAL, "%s: bad pitches", what);
+  XA_REQUIRE(n_out > 0 && n_out <= kBlockM && (channels == 64 || channels == 128) && kh > 0 && kw > 0 && kw <= 8 && kw * channels <= 512,
+             XA_EINVAL, "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
+  XA_REQUIRE(grid_w % 8 == 0, XA_EALIGN, "%s: grid_w=%d must be a multiple of 8 (TMA windows start 16-byte aligned)", what, grid_w);
+  XA_REQUIRE(q_total > 0 && ld >= q_total && ld % 8 == 0, XA_EINVAL, "%s: bad pitch", what);
   XA_REQUIRE(xa::aligned(dyt, 16) && xa::aligned(xt, 16) && xa::aligned(dw, 16) && xa::aligned(workspace, 16), XA_EALIGN,
              "%s: 16-byte alignment required", what);
   XA_REQUIRE(workspace_bytes >= xa_conv_wgrad_workspace_bytes(n_out, channels, kh, kw), XA_ENOSPACE, "%s: workspace too small", what);
-  const int taps = kh * kw, ld_out = taps * channels;
+  const int ld_out = kh * kw * channels;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int64_t k_blocks = (q_total + kBlockK - 1) / kBlockK;
   int splits = static_cast<int>(k_blocks < sms ? k_blocks : sms);
   const int kb_per = static_cast<int>((k_blocks + splits - 1) / splits);
   splits = static_cast<int>((k_blocks + kb_per - 1) / kb_per);
   CUtensorMap mdy, mx;
-  if (int rc = make_map_2d(&mdy, dyt, n_out, ld_dy, kBlockM, what)) return rc;   // 128-row box: rows >= n_out zero-filled
-  if (int rc = make_map_2d(&mx, xt, channels, ld_x, channels, what)) return rc;
+  if (int rc = make_map_2d(&mdy, dyt, static_cast<int64_t>(kw) * n_out, ld, kBlockM, what)) return rc;  // KW shifted copies, stacked
+  if (int rc = make_map_2d(&mx, xt, channels, ld, channels, what)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static thread_local int configured_dev = -1;
   int dev = 0;
@@ -250,15 +261,14 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
     }
     configured_dev = dev;
   }
-  const int taps_per_launch = 512 / channels;
-  for (int tap0 = 0; tap0 < taps; tap0 += taps_per_launch) {
+  const int kh_per_launch = 512 / (kw * channels);  // TMEM: n_kh * KW * C accumulator columns <= 512
+  for (int kh0 = 0; kh0 < kh; kh0 += kh_per_launch) {
     WgradParams p{};
     p.partial = static_cast<float*>(workspace);
-    p.n_out = n_out, p.C = channels, p.tap0 = tap0, p.ld_out = ld_out, p.q_total = q_total;
-    p.n_taps = taps - tap0 < taps_per_launch ? taps - tap0 : taps_per_launch;
+    p.n_out = n_out, p.C = channels, p.KW = kw, p.kh0 = kh0, p.ld_out = ld_out, p.grid_w = grid_w, p.q_total = q_total;
+    p.n_kh = kh - kh0 < kh_per_launch ? kh - kh0 : kh_per_launch;
     p.kb_per_split = kb_per, p.splits = splits;
-    for (int t = 0; t < p.n_taps; ++t) p.shift[t] = ((tap0 + t) / kw) * width + (tap0 + t) % kw;
-    const size_t stage = static_cast<size_t>(kBlockM) * kBlockK * 2 + static_cast<size_t>(p.n_taps) * channels * kBlockK * 2;
+    const size_t stage = static_cast<size_t>(kw) * kBlockM * kBlockK * 2 + static_cast<size_t>(p.n_kh) * channels * kBlockK * 2;
     int stages = static_cast<int>((200 * 1024) / stage);
     if (stages > 6) stages = 6;
     XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: stage of %zu bytes does not fit twice in shared memory", what, stage);

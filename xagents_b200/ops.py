@@ -494,20 +494,21 @@ def conv_wgrad_bf16(dy, x, kh, kw, *, s2d_order=False, workspace=None, stream=No
     B, H, W, C = xx.shape
     N = dd.shape[-1]
     OH, OW = H - kh + 1, W - kw + 1
-    Q = B * H * W
-    ld = -(-Q // 8) * 8
+    Wg = -(-W // 8) * 8                                        # grid rows padded so that kh*Wg is a 16-byte aligned shift
+    Q = B * H * Wg
+    ld = Q
     dev = _device_of(xx)
     st = _stream(stream)
-    dyt = torch.empty((N, ld), dtype=torch.bfloat16, device=dev)
-    _ffi.call('xa_dy_to_grid_t_bf16', _ptr(dd), _tptr(dyt), N, B, H, W, OH, OW, ld, int(bool(s2d_order)), st)
+    dyt = torch.empty((kw, N, ld), dtype=torch.bfloat16, device=dev)          # kw copies, copy j shifted right by j pixels
+    _ffi.call('xa_place_on_grid_t_bf16', _ptr(dd), _tptr(dyt), N, B, H, Wg, OH, OW, ld, int(bool(s2d_order)), kw, st)
     xt = torch.empty((C, ld), dtype=torch.bfloat16, device=dev)
-    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(xt), 1, 1, Q, C, 1, 1, ld, 0, 0, st)
+    _ffi.call('xa_place_on_grid_t_bf16', _ptr(xx), _tptr(xt), C, B, H, Wg, H, W, ld, 0, 1, st)
     ws_bytes = _ffi.lib().xa_conv_wgrad_workspace_bytes(N, C, kh, kw)
     if workspace is None or workspace.numel() * workspace.element_size() < ws_bytes:
         workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
     dw = torch.empty((N, kh * kw * C), dtype=torch.float32, device=dev)
-    _ffi.call('xa_conv_wgrad_bf16', _ptr(dyt), _ptr(xt), _tptr(dw), N, C, kh, kw, W, Q, ld, ld, _tptr(workspace),
+    _ffi.call('xa_conv_wgrad_bf16', _tptr(dyt), _tptr(xt), _tptr(dw), N, C, kh, kw, Wg, Q, ld, _tptr(workspace),
               workspace.numel() * workspace.element_size(), st)
-    _count(3 + -(-kh * kw // (512 // C)))
-    db = dyt.sum(1, dtype=torch.float32)                       # zero-padded columns add nothing
+    _count(3 + -(-kh // max(1, 512 // (kw * C))))
+    db = dyt[0].sum(1, dtype=torch.float32)                    # zero-padded columns add nothing
     return dw, db
