@@ -58,6 +58,9 @@ t('conv1 wgrad: dY^T', lambda: ops.transpose_bf16(dy1.view(-1, 32)))
 t('conv1 wgrad: im2col_t', lambda: ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True, ones_row=True))
 a1, b1 = ops.transpose_bf16(dy1.view(-1, 32)), ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True, ones_row=True)
 t('conv1 wgrad: gemm', lambda: ops.gemm_bf16_tn(a1, b1))
+t('conv3 wgrad: implicit (all)', lambda: ops.conv_wgrad_bf16(dy3.view(-1, 64), x3, 3, 3))
+t('conv2 wgrad: implicit (all)', lambda: ops.conv_wgrad_bf16(dy2.view(-1, 64), x2, 2, 2))
+t('conv1 wgrad: implicit (all)', lambda: ops.conv_wgrad_bf16(dy1.view(-1, 32), x1, 2, 2, s2d_order=True))
 for name, us in rows:
     print(f'{name:28s} {us:9.0f} us')
 print(f'{"total":28s} {sum(u for _, u in rows):9.0f} us')

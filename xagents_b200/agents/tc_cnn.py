@@ -8,7 +8,8 @@ optimiser and the gradient all-reduce are unchanged) and runs every contraction 
   backward   heads/FC: dgrad GEMMs with the ReLU derivative in the epilogue, wgrad GEMMs on transposed operands
              conv3, conv2: data gradient = the same convolution kernel on dY with full zero padding and flipped
              weights (+ ReLU derivative of the layer below in the epilogue)
-             all convs: weight gradient = split-K GEMM  dW = dY^T Xcol  on `xa_im2col_t_bf16` operands
+             all convs: weight gradient = `xa_conv_wgrad_bf16`, the shifted-window GEMM over transposed operands
+             (no im2col matrix), split over the SMs along the pixel axis
   The input layer needs no data gradient.  Bias gradients are column sums (torch reductions).
 
 Strided layers live in space-to-depth form (8x8/4 -> 2x2/1 over 21x21x64, 4x4/2 -> 2x2/1 over 10x10x128); the
@@ -96,16 +97,13 @@ class _NatureCnnFn(torch.autograd.Function):
         d_wf = ops.gemm_bf16_tn(ops.transpose_bf16(dh), ops.transpose_bf16(y3f))                             # [512,3136]
         d_bf = dh.sum(0, dtype=torch.float32)
         dy3 = ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out_dtype=torch.bfloat16).view(B, 7, 7, 64)
-        # convolutions: dW (and, from the row of ones, db) = dY^T [N, M'] x Xcol^T [K+8, M']^T, split along M'
-        g3 = ops.gemm_bf16_tn(ops.transpose_bf16(dy3.view(-1, 64)), ops.im2col_t_bf16(x3, 3, 3, ones_row=True))   # [64,576+8]
-        d_w3, d_b3 = g3[:, :576], g3[:, 576].contiguous()
+        # convolutions: dW by the shifted-window GEMM (no im2col matrix), dX by the padded / flipped convolution
+        d_w3, d_b3 = ops.conv_wgrad_bf16(dy3.view(-1, 64), x3, 3, 3)                                         # [64,576]
         dy2 = ops.conv2d_nhwc_bf16(dy3, op.w3_flip, 3, 3, pad=(2, 2), relu_mask=x3)                          # [B,9,9,64]
-        g2 = ops.gemm_bf16_tn(ops.transpose_bf16(dy2.view(-1, 64)), ops.im2col_t_bf16(x2, 2, 2, ones_row=True))   # [64,512+8]
-        d_w2, d_b2 = g2[:, :512], g2[:, 512].contiguous()
+        d_w2, d_b2 = ops.conv_wgrad_bf16(dy2.view(-1, 64), x2, 2, 2)                                         # [64,512]
         dy1 = ops.conv2d_nhwc_bf16(dy2, op.w2_flip, 2, 2, pad=(1, 1), relu_mask=x2)                          # [B,10,10,128] = dY1 (s2d)
-        # conv1 (rows of dy1 enumerate pixels as (b, y/2, x/2, y%2, x%2): the im2col columns follow the same order)
-        g1 = ops.gemm_bf16_tn(ops.transpose_bf16(dy1.view(-1, 32)), ops.im2col_t_bf16(x1, 2, 2, pixel_s2d=True, ones_row=True))
-        d_w1, d_b1 = g1[:, :256], g1[:, 256].contiguous()
+        # conv1: rows of dy1 enumerate the 20x20 output pixels as (b, y/2, x/2, y%2, x%2)
+        d_w1, d_b1 = ops.conv_wgrad_bf16(dy1.view(-1, 32), x1, 2, 2, s2d_order=True)                         # [32,256]
         # back to torch layouts
         g_w1 = _s2d_kernel_inverse(d_w1, 32, 4, 8, 8, 4)
         g_w2 = _s2d_kernel_inverse(d_w2, 64, 32, 4, 4, 2)
