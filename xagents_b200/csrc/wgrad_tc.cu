@@ -34,9 +34,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap map_x, const WgradParams p, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tile_a = kBlockM * kBlockK * 2;                      // dYt_kw tile: 128 rows (rows >= n_out are never stored)
+  // The KW shifted copies of dYt are stacked row-wise ([KW*n_out, ld]), so one 128-row box holds 128/n_out of them
+  // and ONE MMA (M = 128) produces the gradients of that many kernel columns at once.
+  const int n_abox = (p.KW * p.n_out + kBlockM - 1) / kBlockM;
+  const uint32_t tile_a = kBlockM * kBlockK * 2;
   const uint32_t tile_b = static_cast<uint32_t>(p.C) * kBlockK * 2;   // Xt tile of one kernel row: C rows
-  const uint32_t stage_bytes = p.KW * tile_a + p.n_kh * tile_b;
+  const uint32_t stage_bytes = n_abox * tile_a + p.n_kh * tile_b;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;
@@ -80,9 +83,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
         xa::mbar_expect_tx(full + s, stage_bytes);
         const int q0 = static_cast<int>(kb * kBlockK);
-        for (int kw = 0; kw < p.KW; ++kw) tma_load_2d(a_dst + kw * tile_a, &map_dy, q0, kw * p.n_out, full + s);
+        for (int a = 0; a < n_abox; ++a) tma_load_2d(a_dst + a * tile_a, &map_dy, q0, a * kBlockM, full + s);
         for (int j = 0; j < p.n_kh; ++j)
-          tma_load_2d(a_dst + p.KW * tile_a + j * tile_b, &map_x, q0 + (p.kh0 + j) * p.grid_w, 0, full + s);
+          tma_load_2d(a_dst + n_abox * tile_a + j * tile_b, &map_x, q0 + (p.kh0 + j) * p.grid_w, 0, full + s);
       }
     }
   } else if (warp == 1) {
@@ -95,12 +98,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* base = smem + static_cast<size_t>(s) * stage_bytes;
         for (int j = 0; j < p.n_kh; ++j) {
-          const uint64_t db = make_smem_desc(base + p.KW * tile_a + j * tile_b);
-          for (int kw = 0; kw < p.KW; ++kw) {
-            const uint64_t da = make_smem_desc(base + kw * tile_a);
+          const uint64_t db = make_smem_desc(base + n_abox * tile_a + j * tile_b);
+          for (int a = 0; a < n_abox; ++a) {
+            const uint64_t da = make_smem_desc(base + a * tile_a);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16(tmem_base + (j * p.KW + kw) * p.C, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+              umma_bf16(tmem_base + (a * p.n_kh + j) * p.C, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
         }
         umma_commit(empty + s);
@@ -112,21 +115,24 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     const int quad = warp & 3;
     mbar_wait_wd(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int n = quad * 32 + lane;
-    const int cols = p.n_kh * p.KW * p.C;
-    float* dst = p.partial + (static_cast<int64_t>(split) * p.n_out + n) * p.ld_out + static_cast<int64_t>(p.kh0) * p.KW * p.C;
+    for (int a = 0; a < n_abox; ++a) {
+      const int r = a * kBlockM + quad * 32 + lane;  // stacked row = (kw, n)
+      const int kw = r / p.n_out, n = r - kw * p.n_out;
+      const bool valid = kw < p.KW;
+      for (int j = 0; j < p.n_kh; ++j) {
+        float* dst = p.partial + (static_cast<int64_t>(split) * p.n_out + n) * p.ld_out +
+                     (static_cast<int64_t>(p.kh0 + j) * p.KW + kw) * p.C;
 #pragma unroll 1
-    for (int c0 = 0; c0 < cols; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
-      if (n < p.n_out && kb1 > kb0) {
+        for (int c0 = 0; c0 < p.C; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (a * p.n_kh + j) * p.C + c0, v);
+          if (valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<float4*>(dst + c0)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      } else if (n < p.n_out) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst + c0)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -155,17 +161,19 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 template <int kN>
 __global__ void __launch_bounds__(256) place_on_grid_t_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out, int B,
                                                                int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
+  constexpr int kPix = 256;                   // grid pixels per block: every output row gets a 512-B contiguous run
   constexpr int kPitch = kN + 8;
   constexpr int kVecPerPix = kN / 8;
   constexpr int kPixPerPass = 256 / kVecPerPix;
-  __shared__ __align__(16) __nv_bfloat16 tile[64 * kPitch];
-  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * 64;
+  extern __shared__ __align__(16) uint8_t place_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(place_smem);
+  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * kPix;
   const int x_off = blockIdx.y;
   out += static_cast<int64_t>(blockIdx.y) * kN * ld;
   const int64_t Q = static_cast<int64_t>(B) * H * W;
   const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
-#pragma unroll
-  for (int pass = 0; pass < 64 / kPixPerPass; ++pass) {
+#pragma unroll 1
+  for (int pass = 0; pass < kPix / kPixPerPass; ++pass) {
     const int pi = pass * kPixPerPass + prow;
     const int64_t q = q0 + pi;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -181,10 +189,11 @@ __global__ void __launch_bounds__(256) place_on_grid_t_kernel(const __nv_bfloat1
     *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
   }
   __syncthreads();
-#pragma unroll
-  for (int pass = 0; pass < kN / 32; ++pass) {
-    const int ci = pass * 32 + threadIdx.x / 8;
-    const int pg = (threadIdx.x & 7) * 8;
+  // a warp writes one channel row: 32 lanes x 8 pixels = 256 pixels = 512 contiguous bytes
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int ci = wrp; ci < kN; ci += 8) {
+    const int pg = lane * 8;
     const int64_t q = q0 + pg;
     if (q < ld) {
       __nv_bfloat16 vals[8];
@@ -193,6 +202,20 @@ __global__ void __launch_bounds__(256) place_on_grid_t_kernel(const __nv_bfloat1
       *reinterpret_cast<uint4*>(out + static_cast<int64_t>(ci) * ld + q) = *reinterpret_cast<uint4*>(vals);
     }
   }
+}
+
+template <int kN>
+void launch_place(dim3 grid, cudaStream_t s, const __nv_bfloat16* in, __nv_bfloat16* o, int batch, int grid_h, int grid_w, int src_h,
+                  int src_w, int64_t ld, int s2d_order) {
+  constexpr int smem = 256 * (kN + 8) * 2;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaFuncSetAttribute(place_on_grid_t_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured_dev = dev;
+  }
+  place_on_grid_t_kernel<kN><<<grid, 256, smem, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
 }
 
 }  // namespace
@@ -211,16 +234,16 @@ int xa_place_on_grid_t_bf16(const void* src, void* out, int channels, int batch,
              static_cast<long long>(Q));
   XA_REQUIRE(!s2d_order || (src_h % 2 == 0 && src_w % 2 == 0), XA_EINVAL, "%s: s2d order needs an even source size", what);
   XA_REQUIRE(xa::aligned(src, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
-  const dim3 grid(static_cast<unsigned>((ld + 63) / 64), static_cast<unsigned>(copies));
+  const dim3 grid(static_cast<unsigned>((ld + 255) / 256), static_cast<unsigned>(copies));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (channels == 128)
-    place_on_grid_t_kernel<128><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
+    launch_place<128>(grid, s, in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
   else if (channels == 64)
-    place_on_grid_t_kernel<64><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
+    launch_place<64>(grid, s, in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
   else
-    place_on_grid_t_kernel<32><<<grid, 256, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
+    launch_place<32>(grid, s, in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
   return xa::check_launch(what);
 }
 
@@ -233,7 +256,7 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
                        int64_t ld, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
   const char* what = "xa_conv_wgrad_bf16";
   XA_REQUIRE(dyt && xt && dw && workspace, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(n_out > 0 && n_out <= kBlockM && (channels == 64 || channels == 128) && kh > 0 && kw > 0 && kw <= 8 && kw * channels <= 512,
+  XA_REQUIRE(n_out > 0 && n_out <= kBlockM && (channels == 64 || channels == 128) && kh > 0 && kw > 0 && kw <= 8 && ((kw * n_out + 127) / 128) * channels <= 512,
              XA_EINVAL, "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
   XA_REQUIRE(grid_w % 8 == 0, XA_EALIGN, "%s: grid_w=%d must be a multiple of 8 (TMA windows start 16-byte aligned)", what, grid_w);
   XA_REQUIRE(q_total > 0 && ld >= q_total && ld % 8 == 0, XA_EINVAL, "%s: bad pitch", what);
@@ -261,14 +284,15 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
     }
     configured_dev = dev;
   }
-  const int kh_per_launch = 512 / (kw * channels);  // TMEM: n_kh * KW * C accumulator columns <= 512
+  const int n_abox = (kw * n_out + kBlockM - 1) / kBlockM;
+  const int kh_per_launch = 512 / (n_abox * channels);  // TMEM: n_abox * n_kh * C accumulator columns <= 512
   for (int kh0 = 0; kh0 < kh; kh0 += kh_per_launch) {
     WgradParams p{};
     p.partial = static_cast<float*>(workspace);
     p.n_out = n_out, p.C = channels, p.KW = kw, p.kh0 = kh0, p.ld_out = ld_out, p.grid_w = grid_w, p.q_total = q_total;
     p.n_kh = kh - kh0 < kh_per_launch ? kh - kh0 : kh_per_launch;
     p.kb_per_split = kb_per, p.splits = splits;
-    const size_t stage = static_cast<size_t>(kw) * kBlockM * kBlockK * 2 + static_cast<size_t>(p.n_kh) * channels * kBlockK * 2;
+    const size_t stage = static_cast<size_t>(n_abox) * kBlockM * kBlockK * 2 + static_cast<size_t>(p.n_kh) * channels * kBlockK * 2;
     int stages = static_cast<int>((200 * 1024) / stage);
     if (stages > 6) stages = 6;
     XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: stage of %zu bytes does not fit twice in shared memory", what, stage);
