@@ -156,66 +156,55 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // Place an NHWC tensor [B, OH, OW, kN] (rows in natural (b, y, x) order, or in the 2x2 space-to-depth order
 // (b, y/2, x/2, y%2, x%2) of a layer written with out_s2d) on a [B, H, W] pixel grid, transposed: out[c, q] with
-// q = (b*H + y)*W + x holds the value of source pixel (y, x - x_off), zero outside the source.  `copies` outputs are
-// written back to back with x_off = 0, 1, ...  64 grid pixels x kN channels per block through shared memory.
+// q = (b*H + y)*W + x holds the value of source pixel (y, x - x_off), zero outside the source.  `copies` outputs
+// (blockIdx.y) are written back to back with x_off = 0, 1, ...
+// No shared memory: warp w owns channels 8w..8w+7, lane l owns grid pixels 8l..8l+7 of the block's 256; each thread
+// loads eight 16-B vectors (its 8 pixels x 8 channels), transposes the 8x8 block of bf16 in registers (byte_perm) and
+// stores eight 16-B vectors, so a warp writes 512 contiguous bytes per channel row; the eight warps of a block read
+// the same 128-B pixel rows, which L1 serves.
 template <int kN>
-__global__ void __launch_bounds__(256) place_on_grid_t_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out, int B,
-                                                               int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
-  constexpr int kPix = 256;                   // grid pixels per block: every output row gets a 512-B contiguous run
-  constexpr int kPitch = kN + 8;
-  constexpr int kVecPerPix = kN / 8;
-  constexpr int kPixPerPass = 256 / kVecPerPix;
-  extern __shared__ __align__(16) uint8_t place_smem[];
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(place_smem);
-  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * kPix;
+__global__ void __launch_bounds__(4 * kN) place_on_grid_t_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out,
+                                                                  int B, int H, int W, int OH, int OW, int64_t ld, int s2d_order) {
+  const int lane = threadIdx.x & 31, vec = threadIdx.x >> 5;  // kN / 8 warps
   const int x_off = blockIdx.y;
   out += static_cast<int64_t>(blockIdx.y) * kN * ld;
   const int64_t Q = static_cast<int64_t>(B) * H * W;
-  const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
-#pragma unroll 1
-  for (int pass = 0; pass < kPix / kPixPerPass; ++pass) {
-    const int pi = pass * kPixPerPass + prow;
-    const int64_t q = q0 + pi;
-    uint4 v = make_uint4(0, 0, 0, 0);
+  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * 256 + lane * 8;
+  uint4 rows[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t q = q0 + j;
+    rows[j] = make_uint4(0, 0, 0, 0);
     if (q < Q) {
       const int x = static_cast<int>(q % W) - x_off, y = static_cast<int>((q / W) % H);
       const int64_t b = q / (static_cast<int64_t>(W) * H);
       if (y < OH && x >= 0 && x < OW) {
         const int64_t r = s2d_order ? ((b * (OH / 2) + y / 2) * (OW / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1)
                                     : (b * OH + y) * OW + x;
-        v = __ldg(reinterpret_cast<const uint4*>(src + r * kN) + vec);
+        rows[j] = __ldg(reinterpret_cast<const uint4*>(src + r * kN) + vec);
       }
     }
-    *reinterpret_cast<uint4*>(tile + pi * kPitch + vec * 8) = v;
   }
-  __syncthreads();
-  // a warp writes one channel row: 32 lanes x 8 pixels = 256 pixels = 512 contiguous bytes
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int ci = wrp; ci < kN; ci += 8) {
-    const int pg = lane * 8;
-    const int64_t q = q0 + pg;
-    if (q < ld) {
-      __nv_bfloat16 vals[8];
+  if (q0 >= ld) return;  // ld is a multiple of 8: a group of 8 pixels is all-in or all-out
 #pragma unroll
-      for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
-      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(ci) * ld + q) = *reinterpret_cast<uint4*>(vals);
-    }
+  for (int u = 0; u < 8; ++u) {  // channel 8*vec + u: one bf16 from each of the 8 pixel rows
+    const uint32_t sel = (u & 1) ? 0x7632u : 0x5410u;
+    uint4 o;
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&rows[0]);
+    (void)w0;
+    auto word = [&](int j) { return reinterpret_cast<const uint32_t*>(&rows[j])[u >> 1]; };
+    o.x = __byte_perm(word(0), word(1), sel);
+    o.y = __byte_perm(word(2), word(3), sel);
+    o.z = __byte_perm(word(4), word(5), sel);
+    o.w = __byte_perm(word(6), word(7), sel);
+    *reinterpret_cast<uint4*>(out + static_cast<int64_t>(vec * 8 + u) * ld + q0) = o;
   }
 }
 
 template <int kN>
 void launch_place(dim3 grid, cudaStream_t s, const __nv_bfloat16* in, __nv_bfloat16* o, int batch, int grid_h, int grid_w, int src_h,
                   int src_w, int64_t ld, int s2d_order) {
-  constexpr int smem = 256 * (kN + 8) * 2;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (configured_dev != dev) {
-    cudaFuncSetAttribute(place_on_grid_t_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured_dev = dev;
-  }
-  place_on_grid_t_kernel<kN><<<grid, 256, smem, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
+  place_on_grid_t_kernel<kN><<<grid, 4 * kN, 0, s>>>(in, o, batch, grid_h, grid_w, src_h, src_w, ld, s2d_order);
 }
 
 }  // namespace
