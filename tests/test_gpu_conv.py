@@ -278,3 +278,26 @@ def test_conv_weight_gradient_without_im2col_vs_autograd(B, H, W, C, kh, kw, N, 
     assert torch.equal(dw, again)                                             # split over the SMs, reduced in order
     assert float((dw.double() - want_w).abs().max()) <= 5e-5 * float(want_w.abs().max())
     assert float((db.double() - want_b).abs().max()) <= 1e-5 * float(want_b.abs().max())
+
+
+@pytest.mark.timeout(120)
+def test_graphed_inference_equals_eager_and_follows_weight_updates():
+    from xagents_b200.agents import NatureCNN
+    from xagents_b200.agents.tc_conv import NatureCnnTcForward
+    torch.manual_seed(3)
+    net = NatureCNN(4, 6).cuda()
+    tc = NatureCnnTcForward(net)
+    x = torch.randint(0, 256, (64, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    a0, c0 = tc(x)
+    run = tc.graphed(64)
+    a1, c1 = run(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a0, a1) and torch.equal(c0, c1)
+    with torch.no_grad():                               # an "optimiser step", then refresh: the graph must see the new weights
+        for p in net.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    tc.refresh()
+    a2, c2 = tc(x)
+    a3, c3 = run(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a2, a3) and torch.equal(c2, c3) and not torch.equal(a0, a2)

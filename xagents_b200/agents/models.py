@@ -22,7 +22,7 @@ from .. import ops
 
 class TorchModel:
     def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
-                 comm=None, tensor_core_inference=False):
+                 comm=None, tensor_core_inference=False, graph_inference=True):
         self.module = module
         self.output_is_softmax = output_is_softmax
         self.img_inputs = img_inputs
@@ -54,14 +54,18 @@ class TorchModel:
             mod.refresh()
         # rollout-time policy evaluation (no grad) through the tcgen05 convolution + GEMM pipeline
         self._tc_forward = None
-        if tensor_core_inference:
+        self._graph_inference = graph_inference
+        if tensor_core_inference or getattr(module, 'takes_uint8', False):
             from .tc_conv import NatureCnnTcForward
-            assert isinstance(module, NatureCNN), 'tensor_core_inference is implemented for NatureCNN'
+            assert isinstance(module, NatureCNN), 'tensor-core inference is implemented for NatureCNN'
             self._tc_forward = NatureCnnTcForward(module)
             self._refreshable.append(self._tc_forward)
 
     def forward(self, states, training=True):
         if not training and self._tc_forward is not None and states.dtype == torch.uint8:
+            if self._graph_inference:                             # fixed rollout batch: one graph replay per step
+                a, c = self._tc_forward.graphed(states.shape[0])(states)
+                return a.clone(), c.clone()
             return self._tc_forward(states)
         x = states
         if getattr(self.module, 'takes_uint8', False) and x.dtype == torch.uint8:
