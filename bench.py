@@ -216,6 +216,10 @@ def run_ours(args):
         if comm is not None:
             comm.wait_gradients()
 
+    # clocks are sampled from before the warm-up (nvidia-smi takes ~100 ms to start) to the end of the timed region
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
@@ -233,12 +237,9 @@ def run_ours(args):
         return rc
 
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if comm is not None:
         comm.barrier()
     torch.cuda.synchronize(dev)
-    if sampler:
-        sampler.start()
     start.record(stream)
     for s in range(args.steps):
         cur[0] = s

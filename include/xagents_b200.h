@@ -221,6 +221,13 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
                               int block, int scale_255, xa_stream_t stream);
 
+/* The minibatch gather for the tensor-core network: tf.gather (ppo/agent.py:154) + flatten (base.py:559-564) +
+ * cast/255 (base.py:505-506) + space-to-depth in ONE pass: dst [n_idx, H/s, W/s, s*s*C] bf16 from the time-major uint8
+ * rollout (28 KB read + 56 KB written per frame instead of 56 + 84 for gather then space-to-depth). */
+int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t n_src_rows,
+                          int n_steps, int n_envs, int height, int width, int channels, int block, int scale_255,
+                          xa_stream_t stream);
+
 /* fp32 | bf16 [rows, cols] -> bf16, same orientation (dst pitch ld_dst >= cols) or transposed into
  * [cols, ld_dst >= rows]: operand preparation for the backward products (dW = dY^T X needs both transposed). */
 int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t rows, int64_t cols, int64_t ld_dst,

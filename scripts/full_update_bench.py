@@ -43,14 +43,15 @@ class Autocast:
         return self.inner.backward_and_step(*args)
 
 
-def update_phase(net):
+def update_phase(net, fused_gather=False):
     ret = ops.gae_returns(rewards, values, last_values, dones, 0.99, 0.95)
     offsets = [k * N + m * B for k in range(K) for m in range(M)] + [K * N]
     moments = ops.adv_moments(ret, values, perms.view(-1), offsets, time_major=(T, E))
     for k in range(K):
         for m in range(M):
             idx = perms[k, m * B:(m + 1) * B]
-            states = ops.gather_rows(obs, idx, time_major=(T, E))
+            states = (ops.gather_s2d_u8_bf16(obs, idx, time_major=(T, E)) if fused_gather
+                      else ops.gather_rows(obs, idx, time_major=(T, E)))
             actor, critic = net.forward(states, training=True)
             _, d_actor, d_values, _ = ops.ppo_loss(actor, critic, actions, log_probs, values, ret, idx=idx, time_major=(T, E),
                                                    moments=moments[k * M + m], workspace=workspace)
@@ -71,10 +72,11 @@ def timeit(fn, reps=3):
 
 torch.manual_seed(0)
 rows = []
-for name, net in (('Nature CNN on tcgen05 kernels (bf16 operands, fp32 accumulate)', TorchModel(NatureCnnTc(4, A).cuda())),
+for name, net in (('Nature CNN on tcgen05 kernels, gather fused with /255 + space-to-depth', TorchModel(NatureCnnTc(4, A).cuda())),
+                  ('Nature CNN on tcgen05 kernels (bf16 operands, fp32 accumulate)', TorchModel(NatureCnnTc(4, A).cuda())),
                   ('torch fp32 (cuDNN / cuBLAS)', TorchModel(NatureCNN(4, A).cuda())),
                   ('torch bf16 autocast', Autocast(TorchModel(NatureCNN(4, A).cuda())))):
-    ms = timeit(lambda: update_phase(net))
+    ms = timeit(lambda: update_phase(net, fused_gather='fused' in name))
     rows.append((name, ms))
 print('| network path | ms per update phase (16 minibatches of 8192) | env-steps/s through the update phase |')
 print('|---|---|---|')

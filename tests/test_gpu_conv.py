@@ -301,3 +301,15 @@ def test_graphed_inference_equals_eager_and_follows_weight_updates():
     a3, c3 = run(x)
     torch.cuda.synchronize()
     assert torch.equal(a2, a3) and torch.equal(c2, c3) and not torch.equal(a0, a2)
+
+
+@pytest.mark.timeout(60)
+def test_gather_fused_with_scale_and_space_to_depth():
+    T, E = 6, 5
+    obs = torch.randint(0, 256, (T, E, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    idx = torch.randperm(T * E, device=DEV).to(torch.int32)[:17]
+    got = ops.gather_s2d_u8_bf16(obs, idx, time_major=(T, E))
+    want = ops.space_to_depth_u8_bf16(ops.gather_rows(obs, idx, time_major=(T, E)), 4)
+    assert torch.equal(got, want)
+    flat = obs.reshape(T * E, 84, 84, 4)
+    assert torch.equal(ops.gather_s2d_u8_bf16(flat, idx), ops.space_to_depth_u8_bf16(flat[idx.long()], 4))

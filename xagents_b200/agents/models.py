@@ -68,7 +68,7 @@ class TorchModel:
                 return a.clone(), c.clone()
             return self._tc_forward(states)
         x = states
-        if getattr(self.module, 'takes_uint8', False) and x.dtype == torch.uint8:
+        if getattr(self.module, 'takes_uint8', False) and x.dtype in (torch.uint8, torch.bfloat16):
             pass                                                  # the tensor-core network scales inside its first kernel
         else:
             scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)

@@ -69,7 +69,8 @@ class _Operands:
 class _NatureCnnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, frames, op, w1, b1, w2, b2, w3, b3, wf, bf_, wa, ba, wc, bc):
-        x1 = ops.space_to_depth_u8_bf16(frames.contiguous(), 4)                                    # [B,21,21,64]
+        # uint8 frames, or the output of ops.gather_s2d_u8_bf16 (minibatch gather fused with /255 + space-to-depth)
+        x1 = frames if frames.dtype == torch.bfloat16 else ops.space_to_depth_u8_bf16(frames.contiguous(), 4)   # [B,21,21,64]
         x2 = ops.conv2d_nhwc_bf16(x1, op.w1, 2, 2, bias=op.b1, relu=True, out_s2d=True)           # [B,10,10,128]
         x3 = ops.conv2d_nhwc_bf16(x2, op.w2, 2, 2, bias=op.b2, relu=True)                         # [B,9,9,64]
         y3 = ops.conv2d_nhwc_bf16(x3, op.w3, 3, 3, bias=op.b3, relu=True)                         # [B,7,7,64]
@@ -115,7 +116,7 @@ class _NatureCnnFn(torch.autograd.Function):
 
 class NatureCnnTc(NatureCNN):
     """NatureCNN whose forward and backward run on the tcgen05 kernels.  Takes uint8 NHWC frames directly."""
-    takes_uint8 = True
+    takes_uint8 = True          # ... or the bf16 space-to-depth tensor of ops.gather_s2d_u8_bf16
 
     def __init__(self, in_channels=4, n_actions=6):
         assert in_channels == 4, 'the space-to-depth layouts are built for 84x84x4 frames'

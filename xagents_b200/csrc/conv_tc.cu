@@ -226,8 +226,11 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const uint8_t* __re
 // Fast path for block*C == 16 (84x84x4 frames, block 4): one thread moves the 16 contiguous input bytes of one
 // (output pixel, dy) -- (dx, c) for dx = 0..3 -- into 16 bf16 = 32 contiguous output bytes.  Reads are 16-B
 // vectors along input rows, writes are fully coalesced (a pixel's 64 channels = 4 threads x 32 B).
+// With `idx` the kernel is also the minibatch gather (PPO.get_mini_batches, ppo/agent.py:149-154, fused with the flatten
+// of base.py:559-564 and the cast/255 of base.py:505-506): output image b is frame row(idx[b]) of the time-major rollout.
 __global__ void __launch_bounds__(256) space_to_depth16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B,
-                                                                int H, int W, int s, int scale) {
+                                                                int H, int W, int s, int scale, const int32_t* __restrict__ idx,
+                                                                int n_steps, int n_envs) {
   const int OH = H / s, OW = W / s;
   const int64_t total = static_cast<int64_t>(B) * OH * OW * s;   // (pixel, dy) pairs
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(256) space_to_depth16_kernel(const uint8_t* __
     const int dy = static_cast<int>(i % s);
     const int64_t pix = i / s;
     const int ox = static_cast<int>(pix % OW), oy = static_cast<int>((pix / OW) % OH);
-    const int64_t b = pix / (static_cast<int64_t>(OW) * OH);
+    int64_t b = pix / (static_cast<int64_t>(OW) * OH);
+    if (idx != nullptr) b = xa::sample_row(__ldg(idx + b), n_steps, n_envs);
     const uint4 in = __ldg(reinterpret_cast<const uint4*>(src + ((b * H + oy * s + dy) * W + static_cast<int64_t>(ox) * s) * (16 / s)));
     const uint32_t words[4] = {in.x, in.y, in.z, in.w};
     __nv_bfloat162 out[8];
@@ -343,12 +347,31 @@ int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int heig
   if (block * channels == 16 && xa::aligned(src, 16) && xa::aligned(dst, 16) && (width * channels) % 16 == 0) {
     const int64_t want16 = (total / 16 + 255) / 256;
     space_to_depth16_kernel<<<static_cast<unsigned>(want16 < cap ? want16 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, static_cast<__nv_bfloat16*>(dst), batch, height, width, block, scale_255);
+        src, static_cast<__nv_bfloat16*>(dst), batch, height, width, block, scale_255, nullptr, 0, 0);
     return xa::check_launch("xa_space_to_depth_u8_bf16");
   }
   space_to_depth_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), batch, height, width, channels, block, scale_255);
   return xa::check_launch("xa_space_to_depth_u8_bf16");
+}
+
+int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t n_src_rows, int n_steps, int n_envs,
+                          int height, int width, int channels, int block, int scale_255, xa_stream_t stream) {
+  const char* what = "xa_gather_s2d_u8_bf16";
+  XA_REQUIRE(n_idx >= 0 && n_src_rows > 0 && n_src_rows <= INT32_MAX, XA_EINVAL, "%s: bad sizes", what);
+  if (n_idx == 0) return XA_OK;
+  XA_REQUIRE(src && idx && dst, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(block * channels == 16 && height % block == 0 && width % block == 0 && (width * channels) % 16 == 0, XA_EINVAL,
+             "%s: built for block*channels == 16 (84x84x4 frames, block 4)", what);
+  XA_REQUIRE(n_steps >= 0 && n_envs >= 0 && (n_steps == 0 || static_cast<int64_t>(n_steps) * n_envs == n_src_rows), XA_EINVAL,
+             "%s: n_steps*n_envs must equal n_src_rows", what);
+  XA_REQUIRE(xa::aligned(src, 16) && xa::aligned(dst, 16) && xa::aligned(idx, 4), XA_EALIGN, "%s: alignment", what);
+  const int64_t total = n_idx * height * width * channels / 16;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(sms) * 32;
+  space_to_depth16_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), static_cast<int>(n_idx), height, width, block, scale_255, idx, n_steps, n_envs);
+  return xa::check_launch(what);
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -512,3 +512,19 @@ def conv_wgrad_bf16(dy, x, kh, kw, *, s2d_order=False, workspace=None, stream=No
     _count(3 + -(-kh // max(1, 512 // (kw * C))))
     db = dyt[0].sum(1, dtype=torch.float32)                    # zero-padded columns add nothing
     return dw, db
+
+
+def gather_s2d_u8_bf16(frames, idx, block=4, *, time_major=None, scale_255=True, out=None, stream=None):
+    """Minibatch gather + /255 + space-to-depth in one pass: frames [T,E,H,W,C] (time_major=(T,E)) or [rows,H,W,C] uint8,
+    idx env-major sample ids -> bf16 [n, H/s, W/s, s*s*C], the first-layer input of the tensor-core network."""
+    f, i = _dev(frames, 'uint8'), _dev(idx, 'int32')
+    T, E = _layout(time_major)
+    H, W, C = f.shape[-3:]
+    n_rows = f.shape[0] * (f.shape[1] if T else 1)
+    n = i.size
+    y = out if out is not None else torch.empty((n, H // block, W // block, block * block * C), dtype=torch.bfloat16,
+                                                 device=_device_of(f))
+    _ffi.call('xa_gather_s2d_u8_bf16', _ptr(f), _ptr(i), _tptr(y), n, n_rows, T, E, H, W, C, block, int(bool(scale_255)),
+              _stream(stream))
+    _count()
+    return y
