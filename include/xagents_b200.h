@@ -221,6 +221,16 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
                               int block, int scale_255, xa_stream_t stream);
 
+/* Weight and bias gradient of a stride-1 NHWC convolution from the NATURAL tensors (no transposes, no im2col):
+ * x [q_total, channels] bf16 with q = (b*H + y)*grid_w + x the pixels of the INPUT grid, dy_grid [q_total, n_out] bf16
+ * = dY placed on that same grid (zero where there is no output pixel; xa_conv2d_nhwc_bf16_ex / xa_gemm_bf16_tn_ex
+ * write it there).  dw [n_out, kh*kw*channels] fp32 (K ordered kh, kw, c), db [n_out] fp32 (may be NULL).
+ * n_out 32 or 64, channels a multiple of 64; both operands are read once (MN-major UMMA operands, csrc/wgrad_mn_tc.cu). */
+int64_t xa_conv_wgrad_nhwc_workspace_bytes(int n_out, int channels, int kh, int kw);
+int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float* db, int n_out, int channels, int kh,
+                            int kw, int grid_w, int64_t q_total, void* workspace, int64_t workspace_bytes,
+                            xa_stream_t stream);
+
 /* The minibatch gather for the tensor-core network: tf.gather (ppo/agent.py:154) + flatten (base.py:559-564) +
  * cast/255 (base.py:505-506) + space-to-depth in ONE pass: dst [n_idx, H/s, W/s, s*s*C] bf16 from the time-major uint8
  * rollout (28 KB read + 56 KB written per frame instead of 56 + 84 for gather then space-to-depth). */

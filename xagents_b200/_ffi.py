@@ -81,6 +81,8 @@ PROTOTYPES = {
     'xa_conv_wgrad_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int] * 5 + [ctypes.c_int64] * 2 +
                            [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_space_to_depth_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [c_stream]),
+    'xa_conv_wgrad_nhwc_workspace_bytes': (ctypes.c_int64, [ctypes.c_int] * 4),
+    'xa_conv_wgrad_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gather_s2d_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64] +
                               [ctypes.c_int] * 7 + [c_stream]),
     'xa_to_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
   };
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer
+    if (elect_one()) {  // ---- TMA producer
       uint32_t it = 0;
       const uint32_t stage_bytes = static_cast<uint32_t>(rows) * 128u + S::kStageB;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer
+    if (elect_one()) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {

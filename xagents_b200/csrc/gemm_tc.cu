@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
+    if (elect_one()) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
       uint32_t it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item % n_tiles, split = item / n_tiles;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer
+    if (elect_one()) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
       uint32_t it = 0, lt = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {

@@ -31,6 +31,14 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas then knows the branch is single-threaded and
+// issues tcgen05 / TMA instructions straight from uniform registers instead of wrapping each in an elect-broadcast loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -52,10 +60,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// MN-major shared-memory matrix descriptor: the operand is stored [K rows][MN contiguous], rows of 128 B
+// (SWIZZLE_128B, 64 bf16) or 64 B (SWIZZLE_64B, 32 bf16).  In 16-byte units the canonical layout is
+// ((8|4, n), (8, k)) : ((1, LBO), (8|4, SBO)): LBO = distance between 64(32)-element groups along MN, SBO = distance
+// between 8-row groups along K (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, bool sw64,
+                                                      uint32_t base_offset = 0) {
+  uint64_t d = 0;
+  d |= (addr >> 4) & 0x3FFF;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(sw64 ? 4 : 2) << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: bf16 x bf16 -> f32; bits 15 / 16 select MN-major A / B
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ | (a_mn ? (1u << 15) : 0u) |
+         (b_mn ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -123,6 +147,23 @@ inline int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (rows=%lld k=%lld)", what, static_cast<int>(r),
              static_cast<long long>(rows), static_cast<long long>(k));
+  return XA_OK;
+}
+
+// 2-D bf16 row-major [rows, cols] -> boxes of box_rows x box_cols (box_cols * 2 = the swizzle span: 128 or 64 bytes)
+inline int make_map_2d_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int box_cols, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+  XA_REQUIRE(box_cols == 64 || box_cols == 32, XA_EINVAL, "%s: box of %d columns", what, box_cols);
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld)", what, static_cast<int>(r),
+             static_cast<long long>(rows), static_cast<long long>(cols));
   return XA_OK;
 }
 

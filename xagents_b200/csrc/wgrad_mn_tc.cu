@@ -1,0 +1,299 @@
+// Convolution weight (and bias) gradient on the tensor cores straight from the NATURAL NHWC tensors -- no transposed
+// copies, no im2col matrix.
+//
+//   dW[n, (kh, kw, c)] = sum over output pixels (b, y, x) of  dY[b, y, x, n] * X[b, y + kh, x + kw, c]
+//
+// dY lives on the INPUT pixel grid (zero where y >= OH or x >= OW; the kernels that produce it write it there, see
+// xa_conv2d_nhwc_bf16_ex / xa_gemm_bf16_tn_ex) and pixels are flattened as q = (b*H + y)*W + x, so a kernel tap is a
+// shift of the pixel index, q -> q + kh*W + kw (where the shift would wrap into the next row or image dY is zero):
+//
+//   dW_tap[c, n] = sum_q X[q + shift_tap, c] * dYg[q, n]          X [Q, C], dYg [Q, N]  bf16, pixel-major
+//
+// Both operands are "MN-major" for tcgen05 (the contraction index q is the slow one), which the UMMA descriptors
+// support for bf16: a TMA box of 64 pixels x 64 channels (128-B rows, SWIZZLE_128B) IS the canonical MN-major tile, and
+// the tap shift is a shift of the box's ROW coordinate, which TMA does not need aligned.  The kw shifts of one kernel row
+// are not even loaded separately: one box of 72 rows per kernel row is fetched and the tap is selected by advancing the
+// descriptor's start address by kw * 128 B (the 128-B swizzle is a function of the absolute shared-memory address, so
+// a row-shifted window of a swizzled tile is still a valid swizzled operand).
+//   A (M = 128)  two (tap, 64-channel) groups of X, LBO = their distance in shared memory
+//   B (N = n_out) the dYg tile
+//   D            TMEM lanes = (group, c), columns = n; one accumulator column block per group pair, all resident
+// One extra group of constant ones yields the bias gradient db[n] = sum_q dYg[q, n] from the same pass.
+// The pixel range is split over the SMs (split-K); fp32 partials are added in split order (deterministic).
+// HBM traffic: (C + N) * Q * 2 bytes, each operand read once.
+#include "tc_common.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+using namespace xa_tc;
+
+constexpr int kMaxGroups = 20;
+constexpr int kMaxBoxes = 20;
+
+struct WgradMnParams {
+  float* partial;  // [splits, n_out, ld_p]
+  int n_out, n_groups, n_boxes, box_rows, ld_p;
+  int kb_per_split;
+  int64_t k_blocks;
+  uint32_t stage_bytes, b_off, tmem_cols;
+  int box_shift[kMaxBoxes];   // pixel shift of the box's first row
+  int box_col[kMaxBoxes];     // first channel of the box
+  int box_off[kMaxBoxes];     // byte offset inside the stage
+  int group_off[kMaxGroups];  // byte offset of the group's first row inside the stage; -1 = the ones tile
+  int group_col[kMaxGroups];  // column of the group's channel 0 in a partial row
+};
+
+template <int kMB>  // accumulator column blocks = ceil(groups / 2): descriptors of one K block live in registers
+__global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_dy,
+                                                            const __grid_constant__ WgradMnParams p, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + static_cast<size_t>(stages) * p.stage_bytes;  // 64 rows x 128 B of bf16 1.0
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + 8192);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* desc_tab = acc_full + 2;  // [stages][kMB]: A descriptor of (stage, column block) at K step 0
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int64_t kb0 = static_cast<int64_t>(split) * p.kb_per_split;
+  const int64_t kb1 = kb0 + p.kb_per_split < p.k_blocks ? kb0 + p.kb_per_split : p.k_blocks;
+  constexpr int n_mblocks = kMB;
+
+  for (int i = threadIdx.x; i < 8192 / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  for (int i = threadIdx.x; i < stages * kMB; i += kThreads) {
+    const int s = i / kMB, mb = i - s * kMB;
+    const uint32_t base = xa::smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes), ones_addr = xa::smem_u32(ones);
+    const int g0 = 2 * mb, g1 = 2 * mb + 1 < p.n_groups ? 2 * mb + 1 : 2 * mb;
+    const uint32_t a0 = p.group_off[g0] < 0 ? ones_addr : base + p.group_off[g0];
+    const uint32_t a1 = p.group_off[g1] < 0 ? ones_addr : base + p.group_off[g1];
+    desc_tab[i] = make_smem_desc_mn(a0, a1 - a0, 1024, false);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      xa::mbar_init(full + s, 1);
+      xa::mbar_init(empty + s, 1);
+    }
+    xa::mbar_init(acc_full, 1);
+    xa::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {  // ---- TMA producer
+      uint32_t it = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        const uint32_t round = it / stages;
+        if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+        uint8_t* dst = smem + static_cast<size_t>(s) * p.stage_bytes;
+        xa::mbar_expect_tx(full + s, p.stage_bytes);
+        const int q0 = static_cast<int>(kb * kBlockK);
+        tma_load_2d(dst + p.b_off, &map_dy, 0, q0, full + s);
+        for (int b = 0; b < p.n_boxes; ++b) tma_load_2d(dst + p.box_off[b], &map_x, p.box_col[b], q0 + p.box_shift[b], full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {  // ---- MMA issuer
+      const uint32_t idesc = make_idesc(kBlockM, p.n_out, true, true);
+      const bool sw64 = p.n_out == 32;                // dYg rows of 64 B
+      const uint32_t b_kstep = sw64 ? 1024u : 2048u;  // 16 pixel rows
+      const uint64_t db_proto = make_smem_desc_mn(0, 0, sw64 ? 512 : 1024, sw64);
+      uint32_t it = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        uint64_t da[kMB];
+#pragma unroll
+        for (int mb = 0; mb < kMB; ++mb) da[mb] = desc_tab[s * kMB + mb];
+        const uint32_t b_addr = xa::smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes) + p.b_off;
+        mbar_wait_wd(full + s, (it / stages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int mb = 0; mb < kMB; ++mb) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)  // 16 pixel rows further: +2048 B in the start-address field
+            umma_bf16(tmem_base + mb * p.n_out, da[mb] + k * (2048u >> 4), db_proto | ((b_addr + k * b_kstep) >> 4), idesc,
+                      (kb > kb0) || (k != 0));
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---- epilogue: lanes = (group, channel), columns = n  ->  partial[split][n][group_col + channel]
+    const int quad = warp & 3;
+    mbar_wait_wd(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int mb = 0; mb < n_mblocks; ++mb) {
+      const int g = 2 * mb + (quad >> 1);
+      const int c = (quad & 1) * 32 + lane;
+      const bool is_ones = g < p.n_groups && p.group_off[g] < 0;
+      const bool valid = g < p.n_groups && (!is_ones || c == 0);
+      float* dst = p.partial + static_cast<int64_t>(split) * p.n_out * p.ld_p + (g < p.n_groups ? p.group_col[g] : 0) + c;
+#pragma unroll 1
+      for (int n0 = 0; n0 < p.n_out; n0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mb * p.n_out + n0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[static_cast<int64_t>(n0 + j) * p.ld_p] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// dw[n, col] = sum_s partial[s][n][col] for col < ld_out; db[n] = the column after them
+__global__ void __launch_bounds__(256) wgrad_mn_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
+                                                               int n_out, int ld_out, int ld_p, int splits) {
+  const int64_t total = static_cast<int64_t>(n_out) * (ld_out + 1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / (ld_out + 1)), col = static_cast<int>(i - static_cast<int64_t>(n) * (ld_out + 1));
+    float acc = 0.0f;
+    for (int s = 0; s < splits; ++s) acc += partial[(static_cast<int64_t>(s) * n_out + n) * ld_p + col];
+    if (col < ld_out)
+      dw[static_cast<int64_t>(n) * ld_out + col] = acc;
+    else if (db != nullptr)
+      db[n] = acc;
+  }
+}
+
+template <int kMB>
+int launch_wgrad_mn(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradMnParams& p, int stages, int splits, size_t smem, cudaStream_t s,
+                    const char* what) {
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_mn_kernel<kMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) {
+      xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured_dev = dev;
+  }
+  wgrad_mn_kernel<kMB><<<splits, kThreads, smem, s>>>(mx, mdy, p, stages);
+  return xa::check_launch(what);
+}
+
+int wgrad_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("XA_WGRAD_MODE");
+    mode = e ? std::atoi(e) : 0;
+  }
+  return mode;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t xa_conv_wgrad_nhwc_workspace_bytes(int n_out, int channels, int kh, int kw) {
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  return static_cast<int64_t>(sms) * n_out * (kh * kw * channels + 8) * static_cast<int64_t>(sizeof(float));
+}
+
+int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float* db, int n_out, int channels, int kh, int kw,
+                            int grid_w, int64_t q_total, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
+  const char* what = "xa_conv_wgrad_nhwc_bf16";
+  XA_REQUIRE(x && dy_grid && dw && workspace, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE((n_out == 32 || n_out == 64) && channels > 0 && channels % 64 == 0 && kh > 0 && kw > 0 && kw <= 8 && grid_w >= kw, XA_EINVAL,
+             "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
+  const int cg = channels / 64;
+  const int n_groups = kh * kw * cg + 1;  // + the ones group (bias gradient)
+  const int n_mblocks = (n_groups + 1) / 2;
+  XA_REQUIRE(n_groups <= kMaxGroups && n_mblocks * n_out <= 512, XA_EINVAL, "%s: %d taps x %d channels exceed the TMEM accumulator", what,
+             kh * kw, channels);
+  XA_REQUIRE(q_total > 0 && q_total < (int64_t(1) << 31) - 4096, XA_EOVERFLOW, "%s: q_total out of range", what);
+  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(dy_grid, 16) && xa::aligned(dw, 16) && xa::aligned(workspace, 16), XA_EALIGN,
+             "%s: 16-byte alignment required", what);
+  XA_REQUIRE(workspace_bytes >= xa_conv_wgrad_nhwc_workspace_bytes(n_out, channels, kh, kw), XA_ENOSPACE, "%s: workspace too small", what);
+  const int mode = wgrad_mode();  // 0: one box per kernel row, taps by descriptor shift; 2: one box per tap
+  WgradMnParams p{};
+  p.partial = static_cast<float*>(workspace);
+  p.n_out = n_out, p.n_groups = n_groups;
+  p.ld_p = kh * kw * channels + 8;
+  const bool per_tap = mode == 2;
+  p.box_rows = per_tap ? 64 : 64 + ((kw - 1 + 7) / 8) * 8;
+  const int box_bytes = p.box_rows * 128;
+  int nb = 0, ng = 0;
+  for (int i = 0; i < kh; ++i) {
+    for (int g = 0; g < cg; ++g) {
+      if (per_tap) {
+        for (int j = 0; j < kw; ++j, ++nb, ++ng) {
+          p.box_shift[nb] = i * grid_w + j, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
+          p.group_off[ng] = p.box_off[nb], p.group_col[ng] = (i * kw + j) * channels + g * 64;
+        }
+      } else {
+        p.box_shift[nb] = i * grid_w, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
+        for (int j = 0; j < kw; ++j, ++ng) p.group_off[ng] = p.box_off[nb] + j * 128, p.group_col[ng] = (i * kw + j) * channels + g * 64;
+        ++nb;
+      }
+    }
+  }
+  XA_REQUIRE(nb <= kMaxBoxes, XA_EINVAL, "%s: too many boxes", what);
+  p.group_off[ng] = -1, p.group_col[ng] = kh * kw * channels;
+  p.n_boxes = nb;
+  p.b_off = static_cast<uint32_t>(nb) * box_bytes;
+  p.stage_bytes = p.b_off + (n_out == 64 ? 8192u : 4096u);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(n_mblocks * n_out)) cols *= 2;
+  p.tmem_cols = cols;
+  int stages = static_cast<int>((214 * 1024 - 8192) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: a stage of %u bytes does not fit twice in shared memory", what, p.stage_bytes);
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  p.k_blocks = (q_total + kBlockK - 1) / kBlockK;
+  int splits = static_cast<int>(p.k_blocks < sms ? p.k_blocks : sms);
+  p.kb_per_split = static_cast<int>((p.k_blocks + splits - 1) / splits);
+  splits = static_cast<int>((p.k_blocks + p.kb_per_split - 1) / p.kb_per_split);
+  CUtensorMap mx, mdy;
+  if (int rc = make_map_2d_box(&mx, x, q_total, channels, p.box_rows, 64, what)) return rc;
+  if (int rc = make_map_2d_box(&mdy, dy_grid, q_total, n_out, 64, n_out, what)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(stages) * p.stage_bytes + 8192 + 1024 + 1024;
+  int rc = XA_EINVAL;
+  switch (n_mblocks) {
+#define XA_WGRAD_CASE(MB) \
+  case MB:                \
+    rc = launch_wgrad_mn<MB>(mx, mdy, p, stages, splits, smem, s, what); \
+    break;
+    XA_WGRAD_CASE(1) XA_WGRAD_CASE(2) XA_WGRAD_CASE(3) XA_WGRAD_CASE(4) XA_WGRAD_CASE(5)
+    XA_WGRAD_CASE(6) XA_WGRAD_CASE(7) XA_WGRAD_CASE(8) XA_WGRAD_CASE(9) XA_WGRAD_CASE(10)
+#undef XA_WGRAD_CASE
+    default:
+      xa::set_error("%s: %d accumulator blocks", what, n_mblocks);
+  }
+  if (rc) return rc;
+  const int ld_out = kh * kw * channels;
+  const int64_t total = static_cast<int64_t>(n_out) * (ld_out + 1);
+  wgrad_mn_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(static_cast<const float*>(workspace), dw, db, n_out, ld_out,
+                                                                                     p.ld_p, splits);
+  return xa::check_launch(what);
+}
+
+}  // extern "C"

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer
+    if (elect_one()) {  // ---- TMA producer
       uint32_t it = 0;
       for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % stages;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer: one accumulator column block per tap
+    if (elect_one()) {  // ---- MMA issuer: one accumulator column block per tap
       const uint32_t idesc = make_idesc(kBlockM, p.C);
       uint32_t it = 0;
       for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {

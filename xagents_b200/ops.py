@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -528,3 +528,28 @@ def gather_s2d_u8_bf16(frames, idx, block=4, *, time_major=None, scale_255=True,
               _stream(stream))
     _count()
     return y
+
+
+_wgrad_nhwc_ws = {}
+
+
+def conv_wgrad_nhwc_bf16(x, dy_grid, kh, kw, *, stream=None):
+    """dW [N, kh*kw*C] and db [N] (fp32) of a stride-1 convolution from the natural NHWC tensors: x [B,H,W,C] bf16 and
+    dy_grid [B,H,W,N] bf16 = dY on the input grid (zero outside the [OH, OW] corner).  No transposed copies."""
+    xx, dd = _dev(x, 'bfloat16'), _dev(dy_grid, 'bfloat16')
+    B, H, W, C = xx.shape
+    N = dd.shape[-1]
+    if tuple(dd.shape[:3]) != (B, H, W):
+        raise ValueError(f'dy_grid {tuple(dd.shape)} is not on the grid of x {tuple(xx.shape)}')
+    dev = _device_of(xx)
+    key = (dev, N, C, kh, kw)
+    ws = _wgrad_nhwc_ws.get(key)
+    if ws is None:
+        nbytes = _ffi.lib().xa_conv_wgrad_nhwc_workspace_bytes(N, C, kh, kw)
+        ws = _wgrad_nhwc_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dw = torch.empty((N, kh * kw * C), dtype=torch.float32, device=dev)
+    db = torch.empty((N,), dtype=torch.float32, device=dev)
+    _ffi.call('xa_conv_wgrad_nhwc_bf16', _ptr(xx), _ptr(dd), _tptr(dw), _tptr(db), N, C, kh, kw, W, B * H * W, _tptr(ws),
+              ws.numel(), _stream(stream))
+    _count(2)
+    return dw, db
