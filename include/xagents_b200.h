@@ -181,6 +181,14 @@ int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* nois
 int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n,
                     int64_t k, int64_t ldc, int out_bf16, int relu, const void* relu_mask, void* workspace,
                     int64_t workspace_bytes, xa_stream_t stream);
+
+/* xa_gemm_bf16_tn with an output column map and a separate mask pitch: with col_group > 0 (a multiple of 32) column j
+ * of the product is stored at c[row*ldc + (j / col_group) * col_group_pitch + j % col_group], which writes a
+ * [B, h*w*ch] gradient straight onto a zero-bordered [B, H, W, ch] grid (col_group = w*ch, col_group_pitch = W*ch,
+ * ldc = H*W*ch) -- the layout xa_conv_wgrad_nhwc_bf16 reads.  relu_mask is [m, mask_ld] in PRODUCT columns. */
+int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
+                       int64_t ldc, int out_bf16, int relu, const void* relu_mask, int64_t mask_ld, int64_t col_group,
+                       int64_t col_group_pitch, void* workspace, int64_t workspace_bytes, xa_stream_t stream);
 /* Scratch for split-K (few output tiles, long K: the weight-gradient products); 0 when the shape does not split.
  * Passing workspace = NULL simply disables splitting.  relu_mask: optional bf16 [m, ldc], c *= (mask > 0). */
 int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
@@ -195,6 +203,19 @@ int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int batch, int height,
                         int width, int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu,
                         int out_s2d, const void* relu_mask, xa_stream_t stream);
+
+/* xa_conv2d_nhwc_bf16 with an explicit output extent and output pixel grid (what the backward pass needs to keep every
+ * gradient on the zero-bordered grid xa_conv_wgrad_nhwc_bf16 reads):
+ *   out_h, out_w            > 0: compute only the top-left out_h x out_w corner of the padded output
+ *   out_grid_h, out_grid_w  > 0: pixel (y, x) is stored at ((b*out_grid_h + y)*out_grid_w + x); pixels outside the
+ *                           written extent are left untouched (the caller zero-fills the buffer once)
+ *   out_mode                0 natural; 1 pack 2x2 pixels into channels (the old out_s2d); 2 unpack: the n_out channels
+ *                           are (dy, dx, n_out/4) and land on pixels (2y+dy, 2x+dx) of a [B, grid_h, grid_w, n_out/4] grid
+ * relu_mask always has the natural compact [B, out_h, out_w, n_out] layout. */
+int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width,
+                           int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode,
+                           const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w,
+                           xa_stream_t stream);
 /* Transposed im2col for the weight-gradient product: x [B,H,W,C] bf16 -> out [kh*kw*C, ld] bf16 with
  * out[(kh,kw,c), m] = x[b, y+kh, x+kw, c], m = output pixel (ld >= B*OH*OW, even; columns past M are written 0).
  * pixel_s2d: pixels enumerated (b, y/2, x/2, y%2, x%2).  dW = dY^T Xcol = xa_gemm_bf16_tn(dY^T, out).

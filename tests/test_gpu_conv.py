@@ -313,3 +313,59 @@ def test_gather_fused_with_scale_and_space_to_depth():
     assert torch.equal(got, want)
     flat = obs.reshape(T * E, 84, 84, 4)
     assert torch.equal(ops.gather_s2d_u8_bf16(flat, idx), ops.space_to_depth_u8_bf16(flat[idx.long()], 4))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('B,H,W,C,kh,kw,N', [(3, 9, 9, 64, 3, 3, 64), (5, 10, 10, 128, 2, 2, 64), (2, 21, 21, 64, 2, 2, 32),
+                                             (37, 9, 9, 64, 3, 3, 64), (1, 12, 7, 64, 3, 2, 64), (300, 10, 10, 128, 2, 2, 64)])
+def test_conv_weight_gradient_from_natural_nhwc_tensors(B, H, W, C, kh, kw, N):
+    """xa_conv_wgrad_nhwc_bf16 (MN-major UMMA operands, dY on the zero-bordered input grid) against fp64 autograd."""
+    torch.manual_seed(B + C)
+    OH, OW = H - kh + 1, W - kw + 1
+    x = torch.randn(B, H, W, C, device=DEV).to(torch.bfloat16)
+    dy = torch.randn(B, OH, OW, N, device=DEV).to(torch.bfloat16)
+    grid = torch.zeros(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    grid[:, :OH, :OW] = dy
+    dw, db = ops.conv_wgrad_nhwc_bf16(x, grid, kh, kw)
+    w = torch.zeros(N, C, kh, kw, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w)
+    y.backward(dy.double().permute(0, 3, 1, 2))
+    want = w.grad.permute(0, 2, 3, 1).reshape(N, -1)                       # [N, (kh, kw, c)]
+    assert (dw.double() - want).norm() / want.norm() < 2e-5               # bf16 products are exact in fp32; only summation order differs
+    want_b = dy.double().sum((0, 1, 2))
+    assert (db.double() - want_b).norm() / want_b.norm() < 2e-5
+
+
+@pytest.mark.timeout(120)
+def test_gradients_written_straight_onto_zero_bordered_grids():
+    """The backward producers: GEMM column groups, conv output grid, conv unpack -- against the compact result placed by torch."""
+    torch.manual_seed(3)
+    B = 19
+    # FC data gradient [B, 7*7*64] -> 7x7 corner of a [B, 9, 9, 64] grid, with the ReLU mask in compact layout
+    dh = torch.randn(B, 512, device=DEV).to(torch.bfloat16)
+    wt = (torch.randn(3136, 512, device=DEV) * 0.05).to(torch.bfloat16)
+    mask = torch.randn(B, 3136, device=DEV).to(torch.bfloat16)
+    compact = ops.gemm_bf16_tn(dh, wt, relu_mask=mask, out_dtype=torch.bfloat16)
+    grid = torch.zeros(B, 9, 9, 64, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16_tn(dh, wt, relu_mask=mask, out=grid.view(B, -1), col_group=(7 * 64, 9 * 64))
+    want = torch.zeros_like(grid)
+    want[:, :7, :7] = compact.view(B, 7, 7, 64)
+    assert torch.equal(grid, want)
+    # conv3 data gradient read from that grid, 9x9 result written on a 10x10 grid
+    w3 = (torch.randn(64, 3 * 3 * 64, device=DEV) * 0.05).to(torch.bfloat16)
+    m3 = torch.randn(B, 9, 9, 64, device=DEV).to(torch.bfloat16)
+    ref = ops.conv2d_nhwc_bf16(compact.view(B, 7, 7, 64), w3, 3, 3, pad=(2, 2), relu_mask=m3)             # [B,9,9,64]
+    g2 = torch.zeros(B, 10, 10, 64, device=DEV, dtype=torch.bfloat16)
+    ops.conv2d_nhwc_bf16(grid, w3, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=m3, out=g2)
+    want2 = torch.zeros_like(g2)
+    want2[:, :9, :9] = ref
+    assert torch.equal(g2, want2)
+    # conv2 data gradient [B,10,10,(dy,dx,32)] unpacked to 20x20 pixels of a 21x21 grid
+    w2 = (torch.randn(128, 2 * 2 * 64, device=DEV) * 0.05).to(torch.bfloat16)
+    m2 = torch.randn(B, 10, 10, 128, device=DEV).to(torch.bfloat16)
+    ref1 = ops.conv2d_nhwc_bf16(ref, w2, 2, 2, pad=(1, 1), relu_mask=m2)                                   # [B,10,10,128]
+    g1 = torch.zeros(B, 21, 21, 32, device=DEV, dtype=torch.bfloat16)
+    ops.conv2d_nhwc_bf16(g2, w2, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=m2, out=g1, unpack_s2d=True)
+    want1 = torch.zeros_like(g1)
+    want1[:, :20, :20] = ref1.view(B, 10, 10, 2, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(B, 20, 20, 32)
+    assert torch.equal(g1, want1)

@@ -8,9 +8,12 @@ optimiser and the gradient all-reduce are unchanged) and runs every contraction 
   backward   heads/FC: dgrad GEMMs with the ReLU derivative in the epilogue, wgrad GEMMs on transposed operands
              conv3, conv2: data gradient = the same convolution kernel on dY with full zero padding and flipped
              weights (+ ReLU derivative of the layer below in the epilogue)
-             all convs: weight gradient = `xa_conv_wgrad_bf16`, the shifted-window GEMM over transposed operands
-             (no im2col matrix), split over the SMs along the pixel axis
-  The input layer needs no data gradient.  Bias gradients are column sums (torch reductions).
+             all convs: weight + bias gradient = `xa_conv_wgrad_nhwc_bf16`: a shifted-window GEMM over the NATURAL
+             NHWC tensors (MN-major UMMA operands: no transposes, no im2col matrix), split over the SMs along the
+             pixel axis.  For that every dY is kept on the zero-bordered pixel grid of its layer's INPUT, which the
+             producing kernels write directly (column-group map of the FC data-gradient GEMM, output grid / unpack
+             options of the data-gradient convolutions)
+  The input layer needs no data gradient.
 
 Strided layers live in space-to-depth form (8x8/4 -> 2x2/1 over 21x21x64, 4x4/2 -> 2x2/1 over 10x10x128); the
 layout maps between torch's [N, C, KH, KW] and the kernels' [N, (kh, kw, c)] are applied to the (tiny) weight and
@@ -64,6 +67,17 @@ class _Operands:
         hb[:self.n_actions] = a.bias
         hb[self.n_actions] = c.bias[0]
         self.bh = hb
+        self._grids = m._grids
+
+    def grids(self, batch):
+        """dY3 / dY2 / dY1 on the pixel grids of their layers' inputs.  Allocated zeroed once per batch size: the kernels
+        only ever write the valid corner, so the borders stay zero."""
+        g = self._grids.get(batch)
+        if g is None:
+            dev = self.w1.device
+            g = self._grids[batch] = tuple(torch.zeros((batch, h, h, n), dtype=torch.bfloat16, device=dev)
+                                           for h, n in ((9, 64), (10, 64), (21, 32)))
+        return g
 
 
 class _NatureCnnFn(torch.autograd.Function):
@@ -97,14 +111,16 @@ class _NatureCnnFn(torch.autograd.Function):
         y3f = y3.view(B, -1)
         d_wf = ops.gemm_bf16_tn(ops.transpose_bf16(dh), ops.transpose_bf16(y3f))                             # [512,3136]
         d_bf = dh.sum(0, dtype=torch.float32)
-        dy3 = ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out_dtype=torch.bfloat16).view(B, 7, 7, 64)
-        # convolutions: dW by the shifted-window GEMM (no im2col matrix), dX by the padded / flipped convolution
-        d_w3, d_b3 = ops.conv_wgrad_bf16(dy3.view(-1, 64), x3, 3, 3)                                         # [64,576]
-        dy2 = ops.conv2d_nhwc_bf16(dy3, op.w3_flip, 3, 3, pad=(2, 2), relu_mask=x3)                          # [B,9,9,64]
-        d_w2, d_b2 = ops.conv_wgrad_bf16(dy2.view(-1, 64), x2, 2, 2)                                         # [64,512]
-        dy1 = ops.conv2d_nhwc_bf16(dy2, op.w2_flip, 2, 2, pad=(1, 1), relu_mask=x2)                          # [B,10,10,128] = dY1 (s2d)
-        # conv1: rows of dy1 enumerate the 20x20 output pixels as (b, y/2, x/2, y%2, x%2)
-        d_w1, d_b1 = ops.conv_wgrad_bf16(dy1.view(-1, 32), x1, 2, 2, s2d_order=True)                         # [32,256]
+        g3, g2, g1 = op.grids(B)
+        ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out=g3.view(B, -1), col_group=(7 * 64, 9 * 64))         # 7x7 on the 9x9 grid
+        # convolutions: dW, db by the shifted-window GEMM over natural NHWC tensors; dX by the padded / flipped convolution,
+        # written straight onto the next layer's zero-bordered grid
+        d_w3, d_b3 = ops.conv_wgrad_nhwc_bf16(x3, g3, 3, 3)                                                  # [64,576]
+        ops.conv2d_nhwc_bf16(g3, op.w3_flip, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=x3, out=g2)          # 9x9 on the 10x10 grid
+        d_w2, d_b2 = ops.conv_wgrad_nhwc_bf16(x2, g2, 2, 2)                                                  # [64,512]
+        ops.conv2d_nhwc_bf16(g2, op.w2_flip, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=x2, out=g1,        # [B,10,10,128] unpacked
+                             unpack_s2d=True)                                                                # to 20x20 on the 21x21 grid
+        d_w1, d_b1 = ops.conv_wgrad_nhwc_bf16(x1, g1, 2, 2)                                                  # [32,256]
         # back to torch layouts
         g_w1 = _s2d_kernel_inverse(d_w1, 32, 4, 8, 8, 4)
         g_w2 = _s2d_kernel_inverse(d_w2, 64, 32, 4, 4, 2)
@@ -122,6 +138,7 @@ class NatureCnnTc(NatureCNN):
         assert in_channels == 4, 'the space-to-depth layouts are built for 84x84x4 frames'
         super().__init__(in_channels, n_actions)
         self._op = None
+        self._grids = {}
 
     def refresh(self):
         self._op = _Operands(self)

@@ -22,7 +22,8 @@ struct ConvParams {
   const float* bias;
   int B, H, W, C, KH, KW, N, OH, OW;
   int bx, by, bb;  // tile box over (x, y, image)
-  int relu, out_s2d;
+  int relu, out_s2d;  // out_s2d: 0 natural, 1 pack 2x2 pixels into channels, 2 unpack channels into 2x2 pixels
+  int PH, PW;         // pixel grid the output is written on (>= the written extent; the rest is left untouched)
   int pad_y, pad_x;
   const __nv_bfloat16* mask;  // optional, output layout: result *= (mask > 0)
 };
@@ -150,12 +151,15 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
       const int oy = ty * p.by + (r / p.bx) % p.by;
       const int ob = tb * p.bb + r / (p.bx * p.by);
       const bool valid = r < rows && oy < p.OH && ob < p.B;
-      int64_t out_off = 0;
+      int64_t out_off = 0, mask_off = 0;
       if (valid) {
-        if (p.out_s2d)  // [B, OH/2, OW/2, 4N], channel block (oy%2, ox%2): the next layer's space-to-depth input
+        mask_off = ((static_cast<int64_t>(ob) * p.OH + oy) * p.OW + ox) * p.N;  // the mask has the natural compact layout
+        if (p.out_s2d == 1)  // [B, OH/2, OW/2, 4N], channel block (oy%2, ox%2): the next layer's space-to-depth input
           out_off = ((static_cast<int64_t>(ob) * (p.OH / 2) + oy / 2) * (p.OW / 2) + ox / 2) * (4 * p.N) + ((oy & 1) * 2 + (ox & 1)) * p.N;
+        else if (p.out_s2d == 2)  // [B, PH, PW, N/4]: channel block (dy, dx) of pixel (oy, ox) is pixel (2oy+dy, 2ox+dx)
+          out_off = ((static_cast<int64_t>(ob) * p.PH + 2 * oy) * p.PW + 2 * ox) * (p.N / 4);
         else
-          out_off = ((static_cast<int64_t>(ob) * p.OH + oy) * p.OW + ox) * p.N;
+          out_off = ((static_cast<int64_t>(ob) * p.PH + oy) * p.PW + ox) * p.N;
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -163,8 +167,13 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
         const int col0 = tn * BN + c0;
         if (valid && col0 < p.N) {
-          uint4* dst = reinterpret_cast<uint4*>(p.y + out_off + col0);
-          const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(p.mask + out_off + col0) : nullptr;
+          int64_t off = out_off + col0;
+          if (p.out_s2d == 2) {
+            const int n4 = p.N / 4, sub = col0 / n4;
+            off = out_off + (static_cast<int64_t>(sub >> 1) * p.PW + (sub & 1)) * n4 + (col0 - sub * n4);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.y + off);
+          const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(p.mask + mask_off + col0) : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 h[4];
@@ -282,7 +291,15 @@ extern "C" {
 int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels,
                         int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_s2d, const void* relu_mask,
                         xa_stream_t stream) {
+  return xa_conv2d_nhwc_bf16_ex(x, w, bias, y, batch, height, width, channels, kh, kw, n_out, pad_y, pad_x, relu, out_s2d, relu_mask, 0, 0,
+                                0, 0, stream);
+}
+
+int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels,
+                           int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int out_h,
+                           int out_w, int out_grid_h, int out_grid_w, xa_stream_t stream) {
   const char* what = "xa_conv2d_nhwc_bf16";
+  const int out_s2d = out_mode;
   XA_REQUIRE(x && w && y, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(batch > 0 && channels > 0 && kh > 0 && kw > 0 && n_out > 0 && pad_y >= 0 && pad_x >= 0 && pad_y < kh && pad_x < kw,
              XA_EINVAL, "%s: bad shape", what);
@@ -297,10 +314,20 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
   p.B = batch, p.H = height, p.W = width, p.C = channels, p.KH = kh, p.KW = kw, p.N = n_out;
   p.pad_y = pad_y, p.pad_x = pad_x;
   p.OH = height + 2 * pad_y - kh + 1, p.OW = width + 2 * pad_x - kw + 1;
+  XA_REQUIRE(out_h >= 0 && out_w >= 0 && out_h <= p.OH && out_w <= p.OW, XA_EINVAL, "%s: out_h/out_w exceed the padded output %dx%d", what,
+             p.OH, p.OW);
+  if (out_h > 0) p.OH = out_h;  // only the top-left corner of the padded output (a data gradient read from a zero-bordered grid)
+  if (out_w > 0) p.OW = out_w;
+  XA_REQUIRE(out_mode >= 0 && out_mode <= 2, XA_EINVAL, "%s: out_mode=%d", what, out_mode);
+  const int mul = out_mode == 2 ? 2 : 1;
+  p.PH = out_grid_h > 0 ? out_grid_h : mul * p.OH, p.PW = out_grid_w > 0 ? out_grid_w : mul * p.OW;
+  XA_REQUIRE(p.PH >= mul * p.OH && p.PW >= mul * p.OW && (out_mode != 1 || (out_grid_h == 0 && out_grid_w == 0)), XA_EINVAL,
+             "%s: output grid %dx%d smaller than the output", what, p.PH, p.PW);
+  XA_REQUIRE(out_mode != 2 || (n_out % 128 == 0), XA_EINVAL, "%s: unpacking needs n_out %% 128 == 0", what);
   p.relu = relu, p.out_s2d = out_s2d;
   p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
   XA_REQUIRE(p.OW <= kBlockM, XA_EINVAL, "%s: output width %d exceeds one tile (128)", what, p.OW);
-  XA_REQUIRE(!out_s2d || (p.OH % 2 == 0 && p.OW % 2 == 0 && relu_mask == nullptr), XA_EINVAL,
+  XA_REQUIRE(out_s2d != 1 || (p.OH % 2 == 0 && p.OW % 2 == 0 && relu_mask == nullptr), XA_EINVAL,
              "%s: out_s2d needs even output height/width and no mask", what);
   // tile box: whole output rows (bx = OW), by rows (a divisor of OH), bb images; maximise filled GEMM rows <= 128
   p.bx = p.OW;

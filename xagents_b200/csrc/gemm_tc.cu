@@ -32,7 +32,9 @@ struct GemmParams {
   int splits;                  // > 1: split-K, fp32 partial tiles go to `partial` [splits, m, n]
   int kb_per_split;
   float* partial;
-  const __nv_bfloat16* mask;   // optional [m, ldc]: result *= (mask > 0)  (ReLU derivative in a backward product)
+  const __nv_bfloat16* mask;   // optional [m, mask_ld]: result *= (mask > 0)  (ReLU derivative in a backward product)
+  int64_t mask_ld;
+  int64_t col_group, col_group_pitch;  // col_group > 0: output column j lands at (j / col_group) * col_group_pitch + j % col_group
 };
 
 template <int BN>
@@ -163,12 +165,14 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
         }
         if (row < p.m && col0 < p.n) {
           float f[32];
+          // grouped output columns (a [B, h*w*c] gradient written onto a zero-bordered [B, H, W, c] grid)
+          const int64_t ocol0 = p.col_group > 0 ? (col0 / p.col_group) * p.col_group_pitch + col0 % p.col_group : col0;
           // ReLU-derivative mask: four 16-B loads per 32 columns when the layout allows, scalar otherwise
           uint4 mraw[4];
-          const bool mvec = p.mask != nullptr && col0 + 32 <= p.n && (p.ldc % 8) == 0 && xa::aligned(p.mask, 16);
+          const bool mvec = p.mask != nullptr && col0 + 32 <= p.n && (p.mask_ld % 8) == 0 && xa::aligned(p.mask, 16);
           if (mvec) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) mraw[q] = __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.ldc + col0) + q);
+            for (int q = 0; q < 4; ++q) mraw[q] = __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + col0) + q);
           }
           const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(mraw);
 #pragma unroll
@@ -177,14 +181,14 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
             if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
             if (p.relu) x = fmaxf(x, 0.0f);
             if (p.mask != nullptr && col0 + j < p.n) {
-              const float mval = mvec ? __bfloat162float(mv[j]) : __bfloat162float(p.mask[row * p.ldc + col0 + j]);
+              const float mval = mvec ? __bfloat162float(mv[j]) : __bfloat162float(p.mask[row * p.mask_ld + col0 + j]);
               if (!(mval > 0.0f)) x = 0.0f;
             }
             f[j] = x;
           }
           if (vec_ok && col0 + 32 <= p.n) {
             if (kOutBf16) {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col0);
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + ocol0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 __nv_bfloat162 h[4];
@@ -193,16 +197,16 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
                 dst[j] = *reinterpret_cast<uint4*>(h);
               }
             } else {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + col0);
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + ocol0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
           } else {
             for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
               if (kOutBf16)
-                static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + col0 + j] = __float2bfloat16_rn(f[j]);
+                static_cast<__nv_bfloat16*>(p.c)[row * p.ldc + ocol0 + j] = __float2bfloat16_rn(f[j]);
               else
-                static_cast<float*>(p.c)[row * p.ldc + col0 + j] = f[j];
+                static_cast<float*>(p.c)[row * p.ldc + ocol0 + j] = f[j];
             }
           }
         }
@@ -291,8 +295,19 @@ extern "C" int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k) {
 extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
                                int64_t ldc, int out_bf16, int relu, const void* relu_mask, void* workspace,
                                int64_t workspace_bytes, xa_stream_t stream) {
+  return xa_gemm_bf16_tn_ex(a, b, c, bias, m, n, k, ldc, out_bf16, relu, relu_mask, ldc, 0, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
+                                  int64_t ldc, int out_bf16, int relu, const void* relu_mask, int64_t mask_ld, int64_t col_group,
+                                  int64_t col_group_pitch, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
   const char* what = "xa_gemm_bf16_tn";
   XA_REQUIRE(a && b && c, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(col_group >= 0 && (col_group == 0 || (col_group % 32 == 0 && col_group_pitch >= col_group &&
+                                                   ((n + col_group - 1) / col_group - 1) * col_group_pitch + col_group <= ldc)),
+             XA_EINVAL, "%s: col_group=%lld (multiple of 32) / col_group_pitch=%lld do not fit ldc=%lld", what,
+             static_cast<long long>(col_group), static_cast<long long>(col_group_pitch), static_cast<long long>(ldc));
+  XA_REQUIRE(relu_mask == nullptr || mask_ld >= n, XA_EINVAL, "%s: mask_ld=%lld < n", what, static_cast<long long>(mask_ld));
   XA_REQUIRE(m > 0 && n > 0 && k > 0 && ldc >= n, XA_EINVAL, "%s: m=%lld n=%lld k=%lld ldc=%lld", what, static_cast<long long>(m),
              static_cast<long long>(n), static_cast<long long>(k), static_cast<long long>(ldc));
   XA_REQUIRE(k % 8 == 0, XA_EALIGN, "%s: k=%lld must be a multiple of 8 (16-byte row pitch for TMA)", what, static_cast<long long>(k));
@@ -305,9 +320,10 @@ extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const floa
   GemmParams p{};
   p.c = c, p.bias = bias, p.m = m, p.n = n, p.k = k, p.ldc = ldc, p.relu = relu;
   p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+  p.mask_ld = mask_ld, p.col_group = col_group, p.col_group_pitch = col_group_pitch;
   const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
   int splits = workspace != nullptr ? gemm_auto_splits(m, n, k) : 1;
-  if (splits > 1 && relu_mask == nullptr && workspace_bytes >= static_cast<int64_t>(splits) * m * n * 4) {
+  if (splits > 1 && relu_mask == nullptr && col_group == 0 && workspace_bytes >= static_cast<int64_t>(splits) * m * n * 4) {
     p.kb_per_split = static_cast<int>((k_blocks + splits - 1) / splits);
     p.splits = static_cast<int>((k_blocks + p.kb_per_split - 1) / p.kb_per_split);  // every split owns >= 1 block
     p.partial = static_cast<float*>(workspace);

@@ -379,11 +379,14 @@ def clip_adam(param, grad, m, v, step, *, workspace=None, lr=7e-4, beta1=0.9, be
 
 
 # ------------------------------------------------------------------------------------------ tensor-core GEMM
-def gemm_bf16_tn(a, b, *, bias=None, relu=False, relu_mask=None, out_dtype=torch.float32, out=None, split_k=True, stream=None):
+def gemm_bf16_tn(a, b, *, bias=None, relu=False, relu_mask=None, out_dtype=torch.float32, out=None, split_k=True, col_group=None,
+                 stream=None):
     """C[M,N] = A[M,K] @ B[N,K]^T (+ bias) (ReLU) on tcgen05 tensor cores: bf16 operands, fp32 accumulate.
     The Dense layers of the policy/value network (utils/common.py:239-258), y = x W^T + b, and their backward
     products; shapes with few output tiles and a long K (weight gradients) are split along K over the SMs and
-    reduced in a second, deterministic pass.  `relu_mask` [M,N] bf16 zeroes C where mask <= 0."""
+    reduced in a second, deterministic pass.  `relu_mask` [M,N] bf16 zeroes C where mask <= 0.  `col_group` =
+    (group, pitch) stores product column j at out[:, (j // group) * pitch + j % group] (`out` required): a [B, h*w*c]
+    gradient written straight onto a zero-bordered [B, H, W, c] grid."""
     aa, bb = _dev(a, 'bfloat16'), _dev(b, 'bfloat16')
     (m, k), (n, k2) = aa.shape, bb.shape
     if k != k2:
@@ -393,12 +396,15 @@ def gemm_bf16_tn(a, b, *, bias=None, relu=False, relu_mask=None, out_dtype=torch
     bias_a = _dev(bias, 'float32') if bias is not None else None
     mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
     ws, ws_bytes = None, 0
-    if split_k and mask_a is None:
+    if split_k and mask_a is None and col_group is None:
         ws_bytes = _ffi.lib().xa_gemm_workspace_bytes(m, n, k)
         if ws_bytes:
             ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-    _ffi.call('xa_gemm_bf16_tn', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
-              int(bool(relu)), _ptr(mask_a), _tptr(ws), ws_bytes, _stream(stream))
+    if col_group is not None and out is None:
+        raise ValueError('col_group needs a preallocated `out` (the zero-bordered grid)')
+    group, pitch = col_group if col_group is not None else (0, 0)
+    _ffi.call('xa_gemm_bf16_tn_ex', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
+              int(bool(relu)), _ptr(mask_a), n, int(group), int(pitch), _tptr(ws), ws_bytes, _stream(stream))
     _count(2 if ws is not None else 1)
     return c
 
@@ -422,24 +428,32 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
     return dst
 
 
-def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=(0, 0), relu_mask=None, out=None, stream=None):
+def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=(0, 0), relu_mask=None, out=None, out_hw=None,
+                     unpack_s2d=False, stream=None):
     """Stride-1 NHWC convolution on tcgen05 (implicit GEMM, no im2col).  x [B,H,W,C] bf16; w [N, kh*kw*C] bf16
     with K ordered (kh, kw, c); zero padding `pad`=(py, px).  Returns y [B,OH,OW,N] bf16, or its 2x2
-    space-to-depth form [B,OH/2,OW/2,4N].  `relu_mask` (same layout as y) zeroes y where mask <= 0."""
+    space-to-depth form [B,OH/2,OW/2,4N].  `relu_mask` (compact [B,OH,OW,N]) zeroes y where mask <= 0.
+    Backward-pass options: `out_hw` computes only that top-left corner of the padded output; a preallocated `out`
+    [B,GH,GW,N] larger than the output is a zero-bordered grid written in place; `unpack_s2d` spreads the N = (dy,dx,N/4)
+    channels over pixels (2y+dy, 2x+dx) of `out` [B,GH,GW,N/4]."""
     xx, ww = _dev(x, 'bfloat16'), _dev(w, 'bfloat16')
     B, H, W, C = xx.shape
     N = ww.shape[0]
     if ww.shape[1] != kh * kw * C:
         raise ValueError(f'weights {ww.shape} do not match kh*kw*C = {kh * kw * C}')
-    OH, OW = H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1
-    shape = (B, OH // 2, OW // 2, 4 * N) if out_s2d else (B, OH, OW, N)
+    OH, OW = out_hw if out_hw is not None else (H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1)
+    shape = (B, OH // 2, OW // 2, 4 * N) if out_s2d else ((B, 2 * OH, 2 * OW, N // 4) if unpack_s2d else (B, OH, OW, N))
     y = out if out is not None else torch.empty(shape, dtype=torch.bfloat16, device=_device_of(xx))
+    if y.shape[0] != B or y.shape[-1] != shape[-1] or y.shape[1] < shape[1] or y.shape[2] < shape[2] or not y.is_contiguous():
+        raise ValueError(f'out {tuple(y.shape)} cannot hold an output of {shape}')
+    gh, gw = (y.shape[1], y.shape[2]) if tuple(y.shape) != shape else (0, 0)
     bias_a = _dev(bias, 'float32') if bias is not None else None
     mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
-    if mask_a is not None and mask_a.size != y.numel():
-        raise ValueError('relu_mask must have the output layout')
-    _ffi.call('xa_conv2d_nhwc_bf16', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
-              int(bool(relu)), int(bool(out_s2d)), _ptr(mask_a), _stream(stream))
+    if mask_a is not None and mask_a.size != B * OH * OW * N:
+        raise ValueError('relu_mask must have the compact output layout [B, OH, OW, N]')
+    _ffi.call('xa_conv2d_nhwc_bf16_ex', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
+              int(bool(relu)), 2 if unpack_s2d else int(bool(out_s2d)), _ptr(mask_a), int(OH) if out_hw is not None else 0,
+              int(OW) if out_hw is not None else 0, int(gh), int(gw), _stream(stream))
     _count()
     return y
 
