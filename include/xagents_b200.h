@@ -242,6 +242,14 @@ int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, in
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
                               int block, int scale_255, xa_stream_t stream);
 
+/* c [m, n] fp32 (pitch ldc) = a^T b for ROW-MAJOR a [k, m] and b [k, n] bf16: the Dense weight gradient dW = dY^T X
+ * with dY [batch, out] and X [batch, in] as the other kernels leave them -- no transposed copies (MN-major UMMA
+ * operands, csrc/gemm_atb_tc.cu).  m and n multiples of 8.  workspace (xa_gemm_atb_workspace_bytes, may be NULL)
+ * enables the deterministic split over k for shapes with few output tiles. */
+int64_t xa_gemm_atb_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int xa_gemm_bf16_atb(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int64_t ldc, void* workspace,
+                     int64_t workspace_bytes, xa_stream_t stream);
+
 /* Weight and bias gradient of a stride-1 NHWC convolution from the NATURAL tensors (no transposes, no im2col):
  * x [q_total, channels] bf16 with q = (b*H + y)*grid_w + x the pixels of the INPUT grid, dy_grid [q_total, n_out] bf16
  * = dY placed on that same grid (zero where there is no output pixel; xa_conv2d_nhwc_bf16_ex / xa_gemm_bf16_tn_ex

@@ -132,3 +132,18 @@ def test_gemm_relu_mask_epilogue():
     got = ops.gemm_bf16_tn(a, b, relu_mask=mask)
     want = (a.double() @ b.double().t()) * (mask > 0)
     assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('k,m,n', [(64, 8, 8), (200, 128, 64), (8192, 512, 3136), (8192, 8, 512), (1000, 72, 136), (37, 512, 8)])
+def test_gemm_atb_from_row_major_operands(k, m, n):
+    """C = A^T B with both operands row-major [K, *] (MN-major UMMA descriptors) against fp64."""
+    torch.manual_seed(k + m)
+    a = torch.randn(k, m, device=DEV).to(torch.bfloat16)
+    b = torch.randn(k, n, device=DEV).to(torch.bfloat16)
+    got = ops.gemm_bf16_atb(a, b)
+    want = a.double().t() @ b.double()
+    assert got.shape == (m, n)
+    assert float((got.double() - want).abs().max()) <= 2e-5 * float(want.abs().max()) * max(1.0, (k / 1000) ** 0.5)
+    one = ops.gemm_bf16_atb(a, b, split_k=False)
+    assert float((one.double() - want).abs().max()) <= 2e-3 * float(want.abs().max())

@@ -5,7 +5,8 @@ optimiser and the gradient all-reduce are unchanged) and runs every contraction 
 `xa_conv2d_nhwc_bf16` / `xa_gemm_bf16_tn` (bf16 operands, fp32 accumulation in TMEM):
 
   forward    frames -s2d-> conv1 -> conv2 -> conv3 -> FC512 -> heads                     (tc_conv.py's pipeline)
-  backward   heads/FC: dgrad GEMMs with the ReLU derivative in the epilogue, wgrad GEMMs on transposed operands
+  backward   heads/FC: dgrad GEMMs with the ReLU derivative in the epilogue, wgrad = `xa_gemm_bf16_atb` (dY^T X from the
+             natural row-major tensors, MN-major UMMA operands)
              conv3, conv2: data gradient = the same convolution kernel on dY with full zero padding and flipped
              weights (+ ReLU derivative of the layer below in the epilogue)
              all convs: weight + bias gradient = `xa_conv_wgrad_nhwc_bf16`: a shifted-window GEMM over the NATURAL
@@ -104,12 +105,12 @@ class _NatureCnnFn(torch.autograd.Function):
         d_out[:, A] = d_critic.reshape(-1)
         # heads
         d_out16 = ops.to_bf16(d_out)
-        d_wh = ops.gemm_bf16_tn(ops.to_bf16(d_out, transpose=True), ops.transpose_bf16(h))                   # [8,512]
+        d_wh = ops.gemm_bf16_atb(d_out16, h)                                                                 # [8,512] = d_out^T h
         d_bh = d_out.sum(0)
         dh = ops.gemm_bf16_tn(d_out16, op.wh_t, relu_mask=h, out_dtype=torch.bfloat16)                       # [B,512]
         # FC512
         y3f = y3.view(B, -1)
-        d_wf = ops.gemm_bf16_tn(ops.transpose_bf16(dh), ops.transpose_bf16(y3f))                             # [512,3136]
+        d_wf = ops.gemm_bf16_atb(dh, y3f)                                                                    # [512,3136] = dh^T y3
         d_bf = dh.sum(0, dtype=torch.float32)
         g3, g2, g1 = op.grids(B)
         ops.gemm_bf16_tn(dh, op.wf_t, relu_mask=y3f, out=g3.view(B, -1), col_group=(7 * 64, 9 * 64))         # 7x7 on the 9x9 grid

@@ -5,9 +5,8 @@ run through `xa_gemm_bf16_tn` -- bf16 operands, fp32 accumulation in TMEM:
 
     forward   y  = x  W^T (+ b) (ReLU fused in the epilogue)        A = x [M,K],      B = W   [N,K]
     backward  dx = dy W                                            A = dy [M,N],     B = W^T [K,N]
-              dW = dy^T x                                          A = dy^T [N,M'],  B = x^T [K,M']
+              dW = dy^T x       `xa_gemm_bf16_atb`: dy [M,N] and x [M,K] as they are (MN-major UMMA operands)
 
-The transposed bf16 copies come from `xa_to_bf16` (zero-padded so the contraction length is a multiple of 8).
 bf16 copies of the weights are refreshed by `refresh()` after every optimiser step (the fused clip+Adam kernel
 writes the fp32 master in place).  Convolutions still go through the framework's library path; the
 implicit-GEMM convolutions are the next slice of this row.
@@ -38,9 +37,10 @@ class _TcLinearFn(torch.autograd.Function):
         pad = (-n) % 8
         dy16 = ops.to_bf16(dy2) if pad == 0 else torch.nn.functional.pad(dy2, (0, pad)).to(torch.bfloat16)
         dx = ops.gemm_bf16_tn(dy16, wt16, out_dtype=torch.float32)                  # [M, K]
-        dyt = ops.to_bf16(dy2, transpose=True)                                      # [N, M']
-        xt = ops.to_bf16(x16, transpose=True)                                       # [K, M']
-        dw = ops.gemm_bf16_tn(dyt, xt, out_dtype=torch.float32)                     # [N, K]
+        if x16.shape[1] % 8 == 0:
+            dw = ops.gemm_bf16_atb(dy16, x16)[:n]                                   # dy^T x from the natural layouts
+        else:
+            dw = ops.gemm_bf16_tn(ops.to_bf16(dy2, transpose=True), ops.to_bf16(x16, transpose=True), out_dtype=torch.float32)
         db = dy2.sum(0) if ctx.has_bias else None
         return dx.reshape(ctx.x_shape).to(ctx.x_dtype), dw, db, None, None, None
 

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -567,3 +567,22 @@ def conv_wgrad_nhwc_bf16(x, dy_grid, kh, kw, *, stream=None):
               ws.numel(), _stream(stream))
     _count(2)
     return dw, db
+
+
+def gemm_bf16_atb(a, b, *, split_k=True, stream=None):
+    """C[M,N] fp32 = A^T B for row-major A [K,M] and B [K,N] bf16 -- the Dense weight gradient dW = dY^T X from the
+    tensors as the forward / data-gradient kernels leave them (no transposed copies)."""
+    aa, bb = _dev(a, 'bfloat16'), _dev(b, 'bfloat16')
+    (k, m), (k2, n) = aa.shape, bb.shape
+    if k != k2:
+        raise ValueError(f'contraction lengths differ: A {aa.shape}, B {bb.shape}')
+    dev = _device_of(aa)
+    c = torch.empty((m, n), dtype=torch.float32, device=dev)
+    ws, ws_bytes = None, 0
+    if split_k:
+        ws_bytes = _ffi.lib().xa_gemm_atb_workspace_bytes(m, n, k)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    _ffi.call('xa_gemm_bf16_atb', _ptr(aa), _ptr(bb), _tptr(c), m, n, k, n, _tptr(ws), ws_bytes, _stream(stream))
+    _count(2 if ws is not None else 1)
+    return c
