@@ -34,11 +34,17 @@ struct ConvSmem {
   static constexpr int kStageB = BN * kBlockK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (160 * 1024) / kStage > 8 ? 8 : (160 * 1024) / kStage;
-  static constexpr int kBytes = kStages * kStage + 1024 + 256;
+  static constexpr int kBytes = kStages * kStage + 1024 + 256 + 2048 /*bias*/;
 };
 
+// 2 + 8 warps: TMA producer, MMA issuer, and TWO epilogue groups of four warps (one per TMEM lane quadrant).  Group g
+// drains accumulator g, i.e. every other tile, so two tiles' epilogues are in flight per SM: with one warp per
+// scheduler the epilogue of these short-K convolutions was a chain of exposed latencies (tcgen05.ld -> mask/bias loads
+// -> stores) and bounded the kernel at ~10 % tensor-pipe utilisation.
+constexpr int kConvThreads = 64 + 8 * 32;
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
+__global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
                                                              const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
   using S = ConvSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -48,9 +54,11 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
   uint64_t* acc_full = empty + S::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStage + 256);  // [N <= 512]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.N; i += kConvThreads) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   const int kc_blocks = p.C / kBlockK;        // 64-channel K blocks per kernel tap
   const int k_blocks = p.KH * p.KW * kc_blocks;
   const int tiles_y = (p.OH + p.by - 1) / p.by;
@@ -136,20 +144,22 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
       }
     }
   } else {
-    // ---- epilogue
-    const int quad = warp & 3;
-    uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+    // ---- epilogue: group `grp` (warps 2-5 / 6-9) owns accumulator `grp` = the CTA's tiles of that parity
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
+    const uint32_t grp = (warp - 2) >> 2;
+    // GEMM row r of a tile = pixel (x, y, image) in box order (x fastest): the same for every tile of this thread
+    const int r = quad * 32 + lane;
+    const int ox = r % p.bx;
+    const int ry = (r / p.bx) % p.by;
+    const int rb = r / (p.bx * p.by);
+    for (uint32_t lt = grp;; lt += 2) {
+      const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
+      if (tile >= n_tiles) break;
       int tn, tb, ty;
       decode(tile, tn, tb, ty);
-      const uint32_t acc = lt & 1;
-      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // GEMM row r of the tile = pixel (x, y, image) in box order (x fastest)
-      const int r = quad * 32 + lane;
-      const int ox = r % p.bx;
-      const int oy = ty * p.by + (r / p.bx) % p.by;
-      const int ob = tb * p.bb + r / (p.bx * p.by);
+      const uint32_t acc = grp;
+      const int oy = ty * p.by + ry;
+      const int ob = tb * p.bb + rb;
       const bool valid = r < rows && oy < p.OH && ob < p.B;
       int64_t out_off = 0, mask_off = 0;
       if (valid) {
@@ -161,7 +171,17 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
         else
           out_off = ((static_cast<int64_t>(ob) * p.PH + oy) * p.PW + ox) * p.N;
       }
-#pragma unroll 1
+      // the ReLU-derivative mask does not depend on the accumulator: fetch this row's BN values before waiting for it
+      uint4 mraw[BN / 8];
+      const bool use_mask = p.mask != nullptr && valid;
+      if (use_mask) {
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j)
+          if (tn * BN + j * 8 < p.N) mraw[j] = __ldg(reinterpret_cast<const uint4*>(p.mask + mask_off + tn * BN) + j);
+      }
+      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
@@ -173,25 +193,21 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(const __grid_constan
             off = out_off + (static_cast<int64_t>(sub >> 1) * p.PW + (sub & 1)) * n4 + (col0 - sub * n4);
           }
           uint4* dst = reinterpret_cast<uint4*>(p.y + off);
-          const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(p.mask + mask_off + col0) : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 h[4];
-            uint4 mraw = make_uint4(0, 0, 0, 0);
-            if (msk) mraw = __ldg(msk + j);
-            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw);
+            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw[c0 / 8 + j]);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j + 4);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float a = __uint_as_float(v[8 * j + 2 * q]), b = __uint_as_float(v[8 * j + 2 * q + 1]);
-              if (p.bias != nullptr) {
-                a += __ldg(p.bias + col0 + 8 * j + 2 * q);
-                b += __ldg(p.bias + col0 + 8 * j + 2 * q + 1);
-              }
+              float a = __uint_as_float(v[8 * j + 2 * q]) + bv[2 * q], b = __uint_as_float(v[8 * j + 2 * q + 1]) + bv[2 * q + 1];
               if (p.relu) {
                 a = fmaxf(a, 0.0f);
                 b = fmaxf(b, 0.0f);
               }
-              if (msk) {  // ReLU derivative of the layer below
+              if (use_mask) {  // ReLU derivative of the layer below
                 if (!(__low2float(mk[q]) > 0.0f)) a = 0.0f;
                 if (!(__high2float(mk[q]) > 0.0f)) b = 0.0f;
               }
@@ -280,7 +296,7 @@ int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& 
   }
   const int64_t tiles = static_cast<int64_t>((p.OH + p.by - 1) / p.by) * ((p.B + p.bb - 1) / p.bb) * ((p.N + BN - 1) / BN);
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  kernel<<<static_cast<unsigned>(tiles < sms ? tiles : sms), kThreads, ConvSmem<BN>::kBytes, stream>>>(mx, mw, p);
+  kernel<<<static_cast<unsigned>(tiles < sms ? tiles : sms), kConvThreads, ConvSmem<BN>::kBytes, stream>>>(mx, mw, p);
   return xa::check_launch(what);
 }
 
@@ -305,7 +321,7 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
              XA_EINVAL, "%s: bad shape", what);
   XA_REQUIRE(height + 2 * pad_y >= kh && width + 2 * pad_x >= kw, XA_EINVAL, "%s: kernel larger than the padded image", what);
   XA_REQUIRE(channels % kBlockK == 0, XA_EINVAL, "%s: channels=%d must be a multiple of 64 (one K block per tap)", what, channels);
-  XA_REQUIRE(n_out % 32 == 0, XA_EINVAL, "%s: n_out=%d must be a multiple of 32", what, n_out);
+  XA_REQUIRE(n_out % 32 == 0 && n_out <= 512, XA_EINVAL, "%s: n_out=%d must be a multiple of 32, at most 512", what, n_out);
   XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(w, 16) && xa::aligned(y, 16) && xa::aligned(relu_mask, 16), XA_EALIGN,
              "%s: 16-byte alignment required", what);
   ConvParams p{};
