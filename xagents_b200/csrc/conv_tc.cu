@@ -101,28 +101,34 @@ __global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(const __grid_con
 
   if (warp == 0) {
     if (elect_one()) {  // ---- TMA producer
-      uint32_t it = 0;
+      // No division or modulo in the per-K-block path: this single thread feeds the whole pipeline, and three runtime
+      // divisions per K block (tap / channel block / stage) cost more cycles than the four MMAs the block feeds.
+      uint32_t s = 0, round = 0;
       const uint32_t stage_bytes = static_cast<uint32_t>(rows) * 128u + S::kStageB;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int tn, tb, ty;
         decode(tile, tn, tb, ty);
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int tap = kb / kc_blocks, kc = kb - tap * kc_blocks;
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          const int s = it % S::kStages;
-          const uint32_t round = it / S::kStages;
+        const int y0 = ty * p.by - p.pad_y, b0 = tb * p.bb, n0 = tn * BN;
+        int kh = 0, kw = 0, kc = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
           if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
           uint8_t* a_dst = smem + s * S::kStage;
           xa::mbar_expect_tx(full + s, stage_bytes);
-          tma_load_4d(a_dst, &map_x, kc * kBlockK, kw - p.pad_x, ty * p.by + kh - p.pad_y, tb * p.bb, full + s);
-          tma_load_2d(a_dst + S::kStageA, &map_w, kb * kBlockK, tn * BN, full + s);
+          tma_load_4d(a_dst, &map_x, kc * kBlockK, kw - p.pad_x, y0 + kh, b0, full + s);
+          tma_load_2d(a_dst + S::kStageA, &map_w, kb * kBlockK, n0, full + s);
+          if (++kc == kc_blocks) {
+            kc = 0;
+            if (++kw == p.KW) kw = 0, ++kh;
+          }
+          if (++s == S::kStages) s = 0, ++round;
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
-      uint32_t it = 0, lt = 0;
+      uint32_t s = 0, phase = 0, lt = 0;
+      const uint64_t desc0 = make_smem_desc(smem);  // descriptor of stage 0; stage s adds s * kStage to the address field
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt & 1, use = lt >> 1;
         if (use > 0) {
@@ -130,15 +136,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(const __grid_con
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int s = it % S::kStages;
-          mbar_wait_wd(full + s, (it / S::kStages) & 1);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait_wd(full + s, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc(smem + s * S::kStage);
-          const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
+          const uint64_t da = desc0 + static_cast<uint64_t>(s * (S::kStage >> 4));
+          const uint64_t db = da + (S::kStageA >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           umma_commit(empty + s);
+          if (++s == S::kStages) s = 0, phase ^= 1;
         }
         umma_commit(acc_full + acc);
       }

@@ -96,17 +96,17 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (elect_one()) {  // ---- TMA producer
-      uint32_t it = 0;
-      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % stages;
-        const uint32_t round = it / stages;
+    if (elect_one()) {  // ---- TMA producer (no division / modulo per K block: `stages` is a run-time value)
+      int s = 0;
+      uint32_t round = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
         if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
         uint8_t* dst = smem + static_cast<size_t>(s) * p.stage_bytes;
         xa::mbar_expect_tx(full + s, p.stage_bytes);
         const int q0 = static_cast<int>(kb * kBlockK);
         tma_load_2d(dst + p.b_off, &map_dy, 0, q0, full + s);
         for (int b = 0; b < p.n_boxes; ++b) tma_load_2d(dst + p.box_off[b], &map_x, p.box_col[b], q0 + p.box_shift[b], full + s);
+        if (++s == stages) s = 0, ++round;
       }
     }
   } else if (warp == 1) {
@@ -115,23 +115,27 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
       const bool sw64 = p.n_out == 32;                // dYg rows of 64 B
       const uint32_t b_kstep = sw64 ? 1024u : 2048u;  // 16 pixel rows
       const uint64_t db_proto = make_smem_desc_mn(0, 0, sw64 ? 512 : 1024, sw64);
-      uint32_t it = 0;
-      for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % stages;
+      int s = 0;
+      uint32_t phase = 0;
+      const uint32_t b_addr0 = xa::smem_u32(smem) + p.b_off;
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
         uint64_t da[kMB];
 #pragma unroll
         for (int mb = 0; mb < kMB; ++mb) da[mb] = desc_tab[s * kMB + mb];
-        const uint32_t b_addr = xa::smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes) + p.b_off;
-        mbar_wait_wd(full + s, (it / stages) & 1);
+        const uint32_t b_addr = b_addr0 + static_cast<uint32_t>(s) * p.stage_bytes;
+        mbar_wait_wd(full + s, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // K step outer, accumulator inner: consecutive MMAs write DIFFERENT accumulators, so the tensor pipe never waits
+        // for the previous instruction's accumulation (back-to-back MMAs on one accumulator serialise at ~150 cycles)
 #pragma unroll
-        for (int mb = 0; mb < kMB; ++mb) {
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {  // 16 pixel rows further: +2048 B in the start-address field
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)  // 16 pixel rows further: +2048 B in the start-address field
+          for (int mb = 0; mb < kMB; ++mb)
             umma_bf16(tmem_base + mb * p.n_out, da[mb] + k * (2048u >> 4), db_proto | ((b_addr + k * b_kstep) >> 4), idesc,
                       (kb > kb0) || (k != 0));
         }
         umma_commit(empty + s);
+        if (++s == stages) s = 0, phase ^= 1;
       }
       umma_commit(acc_full);
     }
