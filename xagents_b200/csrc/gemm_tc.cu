@@ -46,8 +46,12 @@ struct Smem {
   static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// 2 + 8 warps: TMA producer, MMA issuer, two epilogue groups of four warps; group g drains accumulator g (every other
+// tile of the CTA), so two epilogues are in flight per SM and their latencies (tcgen05.ld, mask loads) overlap.
+constexpr int kGemmThreads = 64 + 8 * 32;
+
 template <int BN, bool kOutBf16>
-__global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -93,27 +97,29 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
 
   if (warp == 0) {
     if (elect_one()) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t round = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item % n_tiles, split = item / n_tiles;
         const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
         const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % S::kStages;
-          const uint32_t round = it / S::kStages;
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
           uint8_t* a_dst = smem + s * S::kStage;
           uint8_t* b_dst = a_dst + S::kStageA;
           xa::mbar_expect_tx(full + s, S::kStage);
           tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
           tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+          if (++s == S::kStages) s = 0, ++round;
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
-      uint32_t it = 0, lt = 0;
+      uint32_t lt = 0, phase = 0;
+      int s = 0;
+      const uint64_t desc0 = make_smem_desc(smem);  // stage 0; stage s adds s * kStage to the address field
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
         const int split = item / n_tiles;
         const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
@@ -123,65 +129,84 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % S::kStages;
-          mbar_wait_wd(full + s, (it / S::kStages) & 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_wd(full + s, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc(smem + s * S::kStage);
-          const uint64_t db = make_smem_desc(smem + s * S::kStage + S::kStageA);
+          const uint64_t da = desc0 + static_cast<uint64_t>(s * (S::kStage >> 4));
+          const uint64_t db = da + (S::kStageA >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
           umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
+          if (++s == S::kStages) s = 0, phase ^= 1;
         }
         umma_commit(acc_full + acc);  // accumulator complete
       }
     }
   } else {
-    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); group (w-2)/4 owns accumulator (w-2)/4
     const int quad = warp & 3;
+    const uint32_t grp = (warp - 2) >> 2;
     const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16);
-    uint32_t lt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+    constexpr int kChunks = BN < 32 ? 1 : BN / 32;
+    for (uint32_t lt = grp;; lt += 2) {
+      const int item = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
+      if (item >= n_items) break;
       const int tile = item % n_tiles, split = item / n_tiles;
       const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
-      const uint32_t acc = lt & 1;
-      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = grp;
       const int64_t row = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + lane;
+      // The ReLU-derivative mask does not depend on the accumulator: chunks 0 and 1 are fetched before the wait, chunk
+      // ci + 2 while chunk ci is processed (three rotating register sets; the chunk loop stays rolled -- unrolled, the
+      // eight epilogue warps run ~200 KB of code and their instruction-cache misses stall the producer / issuer warps).
+      const int64_t colt = static_cast<int64_t>(tile_n) * BN;
+      const bool mvec = p.mask != nullptr && p.splits == 1 && row < p.m && (p.mask_ld % 8) == 0 && xa::aligned(p.mask, 16);
+      const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + (mvec ? row * p.mask_ld + colt : 0));
+      uint4 m0[4], m1[4], m2[4];
+      auto load_mask = [&](uint4 (&m)[4], int chunk) {
+        if (mvec && chunk < kChunks && colt + chunk * 32 + 32 <= p.n) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = __ldg(mrow + chunk * 4 + q);
+        }
+      };
+      load_mask(m0, 0);
+      load_mask(m1, 1);
+      mbar_wait_backoff(acc_full + acc, (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int c0 = ci * 32;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
-        const int64_t col0 = static_cast<int64_t>(tile_n) * BN + c0;
+        load_mask(m2, ci + 2);
+        const int64_t col0 = colt + c0;
         if (p.splits > 1) {  // raw fp32 partial tile; bias / ReLU / conversion happen in the reduction pass
           if (row < p.m && col0 < p.n) {
             float* dstp = p.partial + (static_cast<int64_t>(split) * p.m + row) * p.n + col0;
-            for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
+            if (col0 + 32 <= p.n && (p.n % 4) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(dstp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
+            }
           }
-          continue;
-        }
-        if (row < p.m && col0 < p.n) {
+        } else if (row < p.m && col0 < p.n) {
           float f[32];
           // grouped output columns (a [B, h*w*c] gradient written onto a zero-bordered [B, H, W, c] grid)
           const int64_t ocol0 = p.col_group > 0 ? (col0 / p.col_group) * p.col_group_pitch + col0 % p.col_group : col0;
-          // ReLU-derivative mask: four 16-B loads per 32 columns when the layout allows, scalar otherwise
-          uint4 mraw[4];
-          const bool mvec = p.mask != nullptr && col0 + 32 <= p.n && (p.mask_ld % 8) == 0 && xa::aligned(p.mask, 16);
-          if (mvec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mraw[q] = __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + col0) + q);
-          }
-          const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(mraw);
+          const bool mv_ok = mvec && col0 + 32 <= p.n;
+          const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(m0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(v[j]);
             if (p.bias != nullptr && col0 + j < p.n) x += __ldg(p.bias + col0 + j);
             if (p.relu) x = fmaxf(x, 0.0f);
             if (p.mask != nullptr && col0 + j < p.n) {
-              const float mval = mvec ? __bfloat162float(mv[j]) : __bfloat162float(p.mask[row * p.mask_ld + col0 + j]);
+              const float mval = mv_ok ? __bfloat162float(mv[j]) : __bfloat162float(p.mask[row * p.mask_ld + col0 + j]);
               if (!(mval > 0.0f)) x = 0.0f;
             }
             f[j] = x;
@@ -210,6 +235,8 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_tn_kernel(const __grid_con
             }
           }
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m0[q] = m1[q], m1[q] = m2[q];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -260,7 +287,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   const int64_t items = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN) * p.splits;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);  // persistent: at most one CTA per SM
-  kernel<<<grid, kThreads, Smem<BN>::kBytes, stream>>>(ma, mb, p);
+  kernel<<<grid, kGemmThreads, Smem<BN>::kBytes, stream>>>(ma, mb, p);
   if (int rc = xa::check_launch(what)) return rc;
   if (p.splits > 1) {
     const int64_t want = (p.m * p.n + 255) / 256;

@@ -39,6 +39,25 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// The same wait for warps that wait LONG (epilogue warps waiting for a whole tile's MMAs): back off between polls so
+// that eight polling warps do not compete with the producer / issuer for issue slots and the mbarrier unit.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = xa::smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+    if (++spins > (kWatchdog >> 4)) __trap();
+  }
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
