@@ -211,10 +211,14 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
  *                           written extent are left untouched (the caller zero-fills the buffer once)
  *   out_mode                0 natural; 1 pack 2x2 pixels into channels (the old out_s2d); 2 unpack: the n_out channels
  *                           are (dy, dx, n_out/4) and land on pixels (2y+dy, 2x+dx) of a [B, grid_h, grid_w, n_out/4] grid
+ *   flags                   XA_CONV_INPUT_ZERO_BORDER: the caller guarantees that the last pad_x columns and pad_y rows
+ *                           of every input image are zero (a gradient on a zero-bordered grid); padded convolutions
+ *                           may then use the flat kernel that fetches every input pixel once (csrc/conv_flat_tc.cu)
  * relu_mask always has the natural compact [B, out_h, out_w, n_out] layout. */
+#define XA_CONV_INPUT_ZERO_BORDER 1
 int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width,
                            int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode,
-                           const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w,
+                           const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w, int flags,
                            xa_stream_t stream);
 /* Transposed im2col for the weight-gradient product: x [B,H,W,C] bf16 -> out [kh*kw*C, ld] bf16 with
  * out[(kh,kw,c), m] = x[b, y+kh, x+kw, c], m = output pixel (ld >= B*OH*OW, even; columns past M are written 0).

@@ -360,6 +360,9 @@ def test_gradients_written_straight_onto_zero_bordered_grids():
     want2 = torch.zeros_like(g2)
     want2[:, :9, :9] = ref
     assert torch.equal(g2, want2)
+    g2f = torch.zeros_like(g2)                                        # the flat kernel (every input pixel fetched once)
+    ops.conv2d_nhwc_bf16(grid, w3, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=m3, out=g2f, zero_border=True)
+    assert torch.equal(g2f, want2)
     # conv2 data gradient [B,10,10,(dy,dx,32)] unpacked to 20x20 pixels of a 21x21 grid
     w2 = (torch.randn(128, 2 * 2 * 64, device=DEV) * 0.05).to(torch.bfloat16)
     m2 = torch.randn(B, 10, 10, 128, device=DEV).to(torch.bfloat16)
@@ -369,3 +372,6 @@ def test_gradients_written_straight_onto_zero_bordered_grids():
     want1 = torch.zeros_like(g1)
     want1[:, :20, :20] = ref1.view(B, 10, 10, 2, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(B, 20, 20, 32)
     assert torch.equal(g1, want1)
+    g1f = torch.zeros_like(g1)
+    ops.conv2d_nhwc_bf16(g2, w2, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=m2, out=g1f, unpack_s2d=True, zero_border=True)
+    assert torch.equal(g1f, want1)

@@ -73,7 +73,7 @@ PROTOTYPES = {
     'xa_gemm_bf16_tn_ex': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p] +
                            [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_conv2d_nhwc_bf16_ex': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
-                               [ctypes.c_void_p] + [ctypes.c_int] * 4 + [c_stream]),
+                               [ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_stream]),
     'xa_gemm_atb_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_gemm_bf16_atb': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),

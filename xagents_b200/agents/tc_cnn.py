@@ -117,10 +117,10 @@ class _NatureCnnFn(torch.autograd.Function):
         # convolutions: dW, db by the shifted-window GEMM over natural NHWC tensors; dX by the padded / flipped convolution,
         # written straight onto the next layer's zero-bordered grid
         d_w3, d_b3 = ops.conv_wgrad_nhwc_bf16(x3, g3, 3, 3)                                                  # [64,576]
-        ops.conv2d_nhwc_bf16(g3, op.w3_flip, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=x3, out=g2)          # 9x9 on the 10x10 grid
+        ops.conv2d_nhwc_bf16(g3, op.w3_flip, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=x3, out=g2, zero_border=True)          # 9x9 on the 10x10 grid
         d_w2, d_b2 = ops.conv_wgrad_nhwc_bf16(x2, g2, 2, 2)                                                  # [64,512]
         ops.conv2d_nhwc_bf16(g2, op.w2_flip, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=x2, out=g1,        # [B,10,10,128] unpacked
-                             unpack_s2d=True)                                                                # to 20x20 on the 21x21 grid
+                             unpack_s2d=True, zero_border=True)                                                                # to 20x20 on the 21x21 grid
         d_w1, d_b1 = ops.conv_wgrad_nhwc_bf16(x1, g1, 2, 2)                                                  # [32,256]
         # back to torch layouts
         g_w1 = _s2d_kernel_inverse(d_w1, 32, 4, 8, 8, 4)

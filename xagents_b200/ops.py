@@ -429,13 +429,15 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
 
 
 def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=(0, 0), relu_mask=None, out=None, out_hw=None,
-                     unpack_s2d=False, stream=None):
+                     unpack_s2d=False, zero_border=False, stream=None):
     """Stride-1 NHWC convolution on tcgen05 (implicit GEMM, no im2col).  x [B,H,W,C] bf16; w [N, kh*kw*C] bf16
     with K ordered (kh, kw, c); zero padding `pad`=(py, px).  Returns y [B,OH,OW,N] bf16, or its 2x2
     space-to-depth form [B,OH/2,OW/2,4N].  `relu_mask` (compact [B,OH,OW,N]) zeroes y where mask <= 0.
     Backward-pass options: `out_hw` computes only that top-left corner of the padded output; a preallocated `out`
     [B,GH,GW,N] larger than the output is a zero-bordered grid written in place; `unpack_s2d` spreads the N = (dy,dx,N/4)
-    channels over pixels (2y+dy, 2x+dx) of `out` [B,GH,GW,N/4]."""
+    channels over pixels (2y+dy, 2x+dx) of `out` [B,GH,GW,N/4]; `zero_border` promises that the last pad columns / rows
+    of every input image are zero (a gradient on a zero-bordered grid), which lets a padded convolution use the flat
+    kernel that fetches every input pixel once."""
     xx, ww = _dev(x, 'bfloat16'), _dev(w, 'bfloat16')
     B, H, W, C = xx.shape
     N = ww.shape[0]
@@ -453,7 +455,7 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
         raise ValueError('relu_mask must have the compact output layout [B, OH, OW, N]')
     _ffi.call('xa_conv2d_nhwc_bf16_ex', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
               int(bool(relu)), 2 if unpack_s2d else int(bool(out_s2d)), _ptr(mask_a), int(OH) if out_hw is not None else 0,
-              int(OW) if out_hw is not None else 0, int(gh), int(gw), _stream(stream))
+              int(OW) if out_hw is not None else 0, int(gh), int(gw), int(bool(zero_border)), _stream(stream))
     _count()
     return y
 
