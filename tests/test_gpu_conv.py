@@ -77,6 +77,10 @@ def test_space_to_depth_u8():
     got = ops.space_to_depth_u8_bf16(x, 4)
     want = (x.float() / 255.0).reshape(5, 21, 4, 21, 4, 4).permute(0, 1, 3, 2, 4, 5).reshape(5, 21, 21, 64).to(torch.bfloat16)
     assert torch.equal(got, want)
+    # every byte value: the kernel's x * (1/255) must round to the same bf16 as the reference's true division (base.py:505-506)
+    ramp = (torch.arange(84 * 84 * 4, device=DEV) % 256).to(torch.uint8).reshape(1, 84, 84, 4)
+    assert torch.equal(ops.space_to_depth_u8_bf16(ramp, 4).reshape(-1).sort().values,
+                       (ramp.float() / 255.0).to(torch.bfloat16).reshape(-1).sort().values)
     got = ops.space_to_depth_u8_bf16(x, 2, scale_255=False)
     want = x.float().reshape(5, 42, 2, 42, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(5, 42, 42, 16).to(torch.bfloat16)
     assert torch.equal(got, want)

@@ -265,36 +265,54 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const uint8_t* __re
 // vectors along input rows, writes are fully coalesced (a pixel's 64 channels = 4 threads x 32 B).
 // With `idx` the kernel is also the minibatch gather (PPO.get_mini_batches, ppo/agent.py:149-154, fused with the flatten
 // of base.py:559-564 and the cast/255 of base.py:505-506): output image b is frame row(idx[b]) of the time-major rollout.
+// Blocks walk over frames; the 16-byte pieces of one frame are spread over the block's threads, all loads of a thread
+// are issued before the first conversion (seven in flight), and the index arithmetic is 32-bit and per-frame.  x/255
+// is computed as x * (1/255): for all 256 byte values the bf16 result is bit-identical to the rounded true division
+// (tests/test_gpu_conv.py checks every value), without sixteen IEEE divisions per thread.
 __global__ void __launch_bounds__(256) space_to_depth16_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B,
                                                                 int H, int W, int s, int scale, const int32_t* __restrict__ idx,
                                                                 int n_steps, int n_envs) {
   const int OH = H / s, OW = W / s;
-  const int64_t total = static_cast<int64_t>(B) * OH * OW * s;   // (pixel, dy) pairs
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int dy = static_cast<int>(i % s);
-    const int64_t pix = i / s;
-    const int ox = static_cast<int>(pix % OW), oy = static_cast<int>((pix / OW) % OH);
-    int64_t b = pix / (static_cast<int64_t>(OW) * OH);
-    if (idx != nullptr) b = xa::sample_row(__ldg(idx + b), n_steps, n_envs);
-    const uint4 in = __ldg(reinterpret_cast<const uint4*>(src + ((b * H + oy * s + dy) * W + static_cast<int64_t>(ox) * s) * (16 / s)));
-    const uint32_t words[4] = {in.x, in.y, in.z, in.w};
-    __nv_bfloat162 out[8];
+  const int per_frame = OH * OW * s;  // (pixel, dy) pairs = 16-byte input pieces of one frame
+  const int in_pitch = W * (16 / s);  // bytes per input row
+  const float mul = scale ? 1.0f / 255.0f : 1.0f;
+  constexpr int kUnroll = 7;          // 84x84x4: 1764 pieces = 6.9 x 256
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t row = idx != nullptr ? xa::sample_row(__ldg(idx + b), n_steps, n_envs) : b;
+    const uint8_t* frame = src + row * (static_cast<int64_t>(H) * in_pitch);
+    __nv_bfloat16* out_frame = dst + static_cast<int64_t>(b) * per_frame * 16;
+    for (int t0 = threadIdx.x; t0 < per_frame; t0 += kUnroll * 256) {
+      uint4 in[kUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float a = static_cast<float>((words[k] >> (16 * h)) & 0xFF), c = static_cast<float>((words[k] >> (16 * h + 8)) & 0xFF);
-        if (scale) {
-          a = __fdiv_rn(a, 255.0f);
-          c = __fdiv_rn(c, 255.0f);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int t = t0 + u * 256;
+        if (t < per_frame) {
+          const int dy = t % s, pix = t / s;
+          const int ox = pix % OW, oy = pix / OW;
+          in[u] = __ldg(reinterpret_cast<const uint4*>(frame + (oy * s + dy) * in_pitch + ox * 16));
         }
-        out[2 * k + h] = __floats2bfloat162_rn(a, c);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int t = t0 + u * 256;
+        if (t < per_frame) {
+          const uint32_t words[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
+          __nv_bfloat162 out[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float a = static_cast<float>((words[k] >> (16 * h)) & 0xFF) * mul;
+              const float c = static_cast<float>((words[k] >> (16 * h + 8)) & 0xFF) * mul;
+              out[2 * k + h] = __floats2bfloat162_rn(a, c);
+            }
+          }
+          uint4* d = reinterpret_cast<uint4*>(out_frame + static_cast<int64_t>(t) * 16);
+          d[0] = *reinterpret_cast<uint4*>(out);
+          d[1] = *reinterpret_cast<uint4*>(out + 4);
+        }
       }
     }
-    uint4* d = reinterpret_cast<uint4*>(dst + i * 16);
-    d[0] = *reinterpret_cast<uint4*>(out);
-    d[1] = *reinterpret_cast<uint4*>(out + 4);
   }
 }
 
@@ -408,7 +426,7 @@ int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int heig
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int64_t cap = static_cast<int64_t>(sms) * 32;
   if (block * channels == 16 && xa::aligned(src, 16) && xa::aligned(dst, 16) && (width * channels) % 16 == 0) {
-    const int64_t want16 = (total / 16 + 255) / 256;
+    const int64_t want16 = batch;  // one frame per block iteration
     space_to_depth16_kernel<<<static_cast<unsigned>(want16 < cap ? want16 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, static_cast<__nv_bfloat16*>(dst), batch, height, width, block, scale_255, nullptr, 0, 0);
     return xa::check_launch("xa_space_to_depth_u8_bf16");
@@ -431,7 +449,8 @@ int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int
   XA_REQUIRE(xa::aligned(src, 16) && xa::aligned(dst, 16) && xa::aligned(idx, 4), XA_EALIGN, "%s: alignment", what);
   const int64_t total = n_idx * height * width * channels / 16;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(sms) * 32;
+  (void)total;
+  const int64_t want = n_idx, cap = static_cast<int64_t>(sms) * 32;  // one frame per block iteration
   space_to_depth16_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), static_cast<int>(n_idx), height, width, block, scale_255, idx, n_steps, n_envs);
   return xa::check_launch(what);
