@@ -220,27 +220,7 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
                            int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode,
                            const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w, int flags,
                            xa_stream_t stream);
-/* Transposed im2col for the weight-gradient product: x [B,H,W,C] bf16 -> out [kh*kw*C, ld] bf16 with
- * out[(kh,kw,c), m] = x[b, y+kh, x+kw, c], m = output pixel (ld >= B*OH*OW, even; columns past M are written 0).
- * pixel_s2d: pixels enumerated (b, y/2, x/2, y%2, x%2).  dW = dY^T Xcol = xa_gemm_bf16_tn(dY^T, out).
- * ones_row: out has one more row, all ones, so the product's extra column is the bias gradient.  C % 32 == 0,
- * ld % 8 == 0.  A 1x1 kernel makes this a plain [M, C] -> [C, ld] transpose. */
-int xa_im2col_t_bf16(const void* x, void* out, int batch, int height, int width, int channels, int kh, int kw,
-                     int64_t ld, int pixel_s2d, int ones_row, xa_stream_t stream);
-/* Convolution weight gradient with NO im2col matrix: with both operands placed on the (row-padded) input pixel grid
- * and transposed to pixel-contiguous form, every kernel tap is the same K-major GEMM over the flattened pixel index
- * with a shifted TMA window (csrc/wgrad_tc.cu).
- *   xa_place_on_grid_t_bf16: src [pixels, C] bf16 of a [B, src_h, src_w] image (natural (b,y,x) row order, or the
- *     (b, y/2, x/2, y%2, x%2) order of a layer written with out_s2d) -> out [copies][C, ld] on the grid_h x grid_w
- *     grid (grid_w % 8 == 0), copy j shifted right by j pixels, zero outside the source.
- *   xa_conv_wgrad_bf16: dw [n_out, kh*kw*C] fp32 (K ordered kh, kw, c) from dyt = kw shifted copies [kw][n_out, ld]
- *     of the output gradient and xt [C, ld] = the layer input, both from xa_place_on_grid_t_bf16; q_total = B*H*grid_w.
- *     Split over the SMs along the pixel axis, reduced deterministically through `workspace`. */
-int xa_place_on_grid_t_bf16(const void* src, void* out, int channels, int batch, int grid_h, int grid_w, int src_h,
-                            int src_w, int64_t ld, int s2d_order, int copies, xa_stream_t stream);
-int64_t xa_conv_wgrad_workspace_bytes(int n_out, int channels, int kh, int kw);
-int xa_conv_wgrad_bf16(const void* dyt, const void* xt, float* dw, int n_out, int channels, int kh, int kw, int grid_w,
-                       int64_t q_total, int64_t ld, void* workspace, int64_t workspace_bytes, xa_stream_t stream);
+
 /* uint8 NHWC frames -> bf16 (optionally /255, xagents/base.py:505-506) rearranged block x block -> channels:
  * dst[b, y/s, x/s, (y%s, x%s, c)]. */
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,

@@ -259,31 +259,6 @@ def test_ppo_fit_with_the_tensor_core_network():
     assert np.isfinite(losses).all()
 
 
-@pytest.mark.timeout(240)
-@pytest.mark.parametrize('B,H,W,C,kh,kw,N,s2d', [(5, 9, 9, 64, 3, 3, 64, False), (6, 10, 10, 128, 2, 2, 64, False),
-                                                 (7, 21, 21, 64, 2, 2, 32, True), (400, 9, 9, 64, 3, 3, 64, False),
-                                                 (333, 21, 21, 64, 2, 2, 32, True)])
-def test_conv_weight_gradient_without_im2col_vs_autograd(B, H, W, C, kh, kw, N, s2d):
-    """dW / db from the shifted-window GEMM (no im2col matrix) against torch autograd in fp64 on the same operands."""
-    g = torch.Generator(device=DEV)
-    g.manual_seed(B * 3 + C)
-    x = torch.randn((B, H, W, C), device=DEV, generator=g).to(torch.bfloat16)
-    OH, OW = H - kh + 1, W - kw + 1
-    dy = torch.randn((B, OH, OW, N), device=DEV, generator=g).to(torch.bfloat16)
-    want_w = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (N, C, kh, kw), dy.double().permute(0, 3, 1, 2))
-    want_w = want_w.permute(0, 2, 3, 1).reshape(N, -1)                       # [N, (kh, kw, c)]
-    want_b = dy.double().sum((0, 1, 2))
-    rows = dy.reshape(-1, N)
-    if s2d:                                                                   # rows in the order an out_s2d layer holds them
-        rows = dy.reshape(B, OH // 2, 2, OW // 2, 2, N).permute(0, 1, 3, 2, 4, 5).reshape(-1, N).contiguous()
-    dw, db = ops.conv_wgrad_bf16(rows, x, kh, kw, s2d_order=s2d)
-    again, _ = ops.conv_wgrad_bf16(rows, x, kh, kw, s2d_order=s2d)
-    torch.cuda.synchronize()
-    assert torch.equal(dw, again)                                             # split over the SMs, reduced in order
-    assert float((dw.double() - want_w).abs().max()) <= 5e-5 * float(want_w.abs().max())
-    assert float((db.double() - want_b).abs().max()) <= 1e-5 * float(want_b.abs().max())
-
-
 @pytest.mark.timeout(120)
 def test_graphed_inference_equals_eager_and_follows_weight_updates():
     from xagents_b200.agents import NatureCNN

@@ -79,13 +79,6 @@ PROTOTYPES = {
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_conv2d_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                             [ctypes.c_void_p, c_stream]),
-    'xa_im2col_t_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
-                                                                                                   c_stream]),
-    'xa_place_on_grid_t_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_int64, ctypes.c_int,
-                                                                                                      ctypes.c_int, c_stream]),
-    'xa_conv_wgrad_workspace_bytes': (ctypes.c_int64, [ctypes.c_int] * 4),
-    'xa_conv_wgrad_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int] * 5 + [ctypes.c_int64] * 2 +
-                           [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_space_to_depth_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [c_stream]),
     'xa_conv_wgrad_nhwc_workspace_bytes': (ctypes.c_int64, [ctypes.c_int] * 4),
     'xa_conv_wgrad_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),

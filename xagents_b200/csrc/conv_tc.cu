@@ -457,115 +457,3 @@ int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int
 }
 
 }  // extern "C"
-
-// ---------------------------------------------------------------------------------------------- weight gradient operand
-// Transposed im2col: X [B,H,W,C] bf16 -> Xcol^T [K = KH*KW*C, ld] with ld >= M = B*OH*OW (caller zero-fills the
-// padding), column m = output pixel, row k = (kh, kw, c):  Xcol^T[k, m] = X[b, y+kh, x+kw, c].  This is the B
-// operand (K-major, M contiguous) of the weight-gradient product dW = dY^T Xcol run by xa_gemm_bf16_tn with
-// split-K.  pixel_s2d: columns enumerate pixels as (b, y/2, x/2, y%2, x%2), the order in which a layer whose
-// output was written with out_s2d holds its dY rows.  64 pixels x 64 channels per block through shared memory:
-// 128-B reads along channels, 128-B writes along pixels.
-// ones_row appends a row K of ones, so that the same GEMM also returns the bias gradient sum_m dY[m, n] as its
-// extra output column (deterministically).  With a 1x1 kernel this is simply a fast [M, C] -> [C, M] transpose.
-// (Materialising Xcol^T costs K*M*2 bytes of traffic; reading NHWC tiles as MN-major UMMA operands is the
-// replacement planned for the next round.)
-namespace {
-
-// kCB = channels per block (64 or 32).  Loads: 16-B vectors along channels (a pixel's kCB channels are contiguous);
-// stores: 16-B vectors along pixels (8 pixels of one channel), through a padded shared tile.
-template <int kCB>
-__global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H,
-                                                        int W, int C, int KH, int KW, int OH, int OW, int64_t M, int64_t ld,
-                                                        int pixel_s2d, int ones_row) {
-  constexpr int kPitch = kCB + 8;              // bf16 elements; keeps 16-B alignment and spreads banks
-  constexpr int kVecPerPix = kCB / 8;          // 16-B vectors per pixel
-  constexpr int kPixPerPass = 256 / kVecPerPix;
-  __shared__ __align__(16) __nv_bfloat16 tile[64 * kPitch];
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
-  const int cblocks = C / kCB;
-  const int taps = KH * KW;
-  if (ones_row) {  // the row of ones (bias gradient for free)
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
-    for (int i = threadIdx.x; i < 64; i += 256) {
-      const int64_t m = m0 + i;
-      if (m < ld) out[static_cast<int64_t>(taps) * C * ld + m] = m < M ? one : zero;
-    }
-  }
-  // pixel coordinates of this thread's load row(s) are the same for every tap: decode once
-  const int vec = threadIdx.x % kVecPerPix, prow = threadIdx.x / kVecPerPix;
-  constexpr int kPasses = 64 / kPixPerPass;
-  int64_t base[kPasses];
-#pragma unroll
-  for (int pass = 0; pass < kPasses; ++pass) {
-    const int64_t m = m0 + pass * kPixPerPass + prow;
-    base[pass] = -1;
-    if (m < M) {
-      int ox, oy;
-      int64_t b;
-      if (pixel_s2d) {
-        const int sub = static_cast<int>(m & 3);
-        const int64_t q = m >> 2;
-        const int X2 = static_cast<int>(q % (OW / 2)), Y2 = static_cast<int>((q / (OW / 2)) % (OH / 2));
-        b = q / (static_cast<int64_t>(OW / 2) * (OH / 2));
-        oy = Y2 * 2 + (sub >> 1), ox = X2 * 2 + (sub & 1);
-      } else {
-        ox = static_cast<int>(m % OW), oy = static_cast<int>((m / OW) % OH);
-        b = m / (static_cast<int64_t>(OW) * OH);
-      }
-      base[pass] = ((b * H + oy) * W + ox) * C;
-    }
-  }
-  // one block walks every (tap, channel block) of its 64 pixels: the taps re-read the same few input rows, which are
-  // still in L1/L2, so the activation comes from HBM once instead of KH*KW times
-  for (int blk = 0; blk < taps * cblocks; ++blk) {
-    const int tap = blk / cblocks, c0 = (blk - tap * cblocks) * kCB;
-    const int kh = tap / KW, kw = tap - kh * KW;
-#pragma unroll
-    for (int pass = 0; pass < kPasses; ++pass) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (base[pass] >= 0) v = __ldg(reinterpret_cast<const uint4*>(x + base[pass] + (static_cast<int64_t>(kh) * W + kw) * C + c0) + vec);
-      *reinterpret_cast<uint4*>(tile + (pass * kPixPerPass + prow) * kPitch + vec * 8) = v;
-    }
-    __syncthreads();
-    // 8 threads per channel row, each packs 8 pixels of that channel into one 16-B store
-    constexpr int kRowsPerPass = 256 / 8;
-#pragma unroll
-    for (int pass = 0; pass < kCB / kRowsPerPass; ++pass) {
-      const int ci = pass * kRowsPerPass + threadIdx.x / 8;
-      const int pg = (threadIdx.x & 7) * 8;
-      const int64_t m = m0 + pg;
-      if (m < ld) {  // ld is a multiple of 8, so a group of 8 pixels is all-in or all-out
-        __nv_bfloat16 vals[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vals[j] = tile[(pg + j) * kPitch + ci];
-        *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * C + c0 + ci) * ld + m) = *reinterpret_cast<uint4*>(vals);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-}  // namespace
-
-extern "C" int xa_im2col_t_bf16(const void* x, void* out, int batch, int height, int width, int channels, int kh, int kw,
-                                int64_t ld, int pixel_s2d, int ones_row, xa_stream_t stream) {
-  const char* what = "xa_im2col_t_bf16";
-  XA_REQUIRE(x && out, XA_EINVAL, "%s: null pointer", what);
-  XA_REQUIRE(batch > 0 && height >= kh && width >= kw && kh > 0 && kw > 0 && channels % 32 == 0, XA_EINVAL, "%s: bad shape", what);
-  const int OH = height - kh + 1, OW = width - kw + 1;
-  const int64_t M = static_cast<int64_t>(batch) * OH * OW;
-  XA_REQUIRE(ld >= M && ld % 8 == 0, XA_EINVAL, "%s: ld=%lld must be a multiple of 8 and >= %lld", what, static_cast<long long>(ld),
-             static_cast<long long>(M));
-  XA_REQUIRE(!pixel_s2d || (OH % 2 == 0 && OW % 2 == 0), XA_EINVAL, "%s: pixel_s2d needs even output size", what);
-  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(out, 16), XA_EALIGN, "%s: 16-byte alignment required", what);
-  const int cb = channels % 64 == 0 ? 64 : 32;
-  const dim3 grid(static_cast<unsigned>((ld + 63) / 64));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* xs = static_cast<const __nv_bfloat16*>(x);
-  __nv_bfloat16* os = static_cast<__nv_bfloat16*>(out);
-  if (cb == 64)
-    im2col_t_kernel<64><<<grid, 256, 0, s>>>(xs, os, batch, height, width, channels, kh, kw, OH, OW, M, ld, pixel_s2d, ones_row);
-  else
-    im2col_t_kernel<32><<<grid, 256, 0, s>>>(xs, os, batch, height, width, channels, kh, kw, OH, OW, M, ld, pixel_s2d, ones_row);
-  return xa::check_launch(what);
-}

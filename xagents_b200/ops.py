@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb', 'im2col_t_bf16', 'transpose_bf16', 'conv_wgrad_bf16',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -469,65 +469,6 @@ def space_to_depth_u8_bf16(frames, block, *, scale_255=True, out=None, stream=No
     _ffi.call('xa_space_to_depth_u8_bf16', _ptr(f), _tptr(y), B, H, W, C, block, int(bool(scale_255)), _stream(stream))
     _count()
     return y
-
-
-def im2col_t_bf16(x, kh, kw, *, pixel_s2d=False, ones_row=False, pad_to=8, stream=None):
-    """x [B,H,W,C] bf16 -> Xcol^T [kh*kw*C (+8 with ones_row), M'] (M' = B*OH*OW rounded up to 8, zero-filled):
-    the K-major operand of the weight-gradient product dW = gemm_bf16_tn(dY^T, Xcol^T).  With ones_row, row
-    kh*kw*C is all ones (the product's column kh*kw*C is then the bias gradient) and 7 zero rows follow."""
-    xx = _dev(x, 'bfloat16')
-    B, H, W, C = xx.shape
-    M = B * (H - kh + 1) * (W - kw + 1)
-    ld = -(-M // pad_to) * pad_to
-    K = kh * kw * C
-    if ones_row:
-        out = torch.empty((K + 8, ld), dtype=torch.bfloat16, device=_device_of(xx))
-        out[K + 1:].zero_()
-    else:
-        out = torch.empty((K, ld), dtype=torch.bfloat16, device=_device_of(xx))
-    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), B, H, W, C, kh, kw, ld, int(bool(pixel_s2d)), int(bool(ones_row)),
-              _stream(stream))
-    _count()
-    return out
-
-
-def transpose_bf16(x2d, *, stream=None):
-    """[M, C] bf16 (C % 32 == 0) -> [C, M'] bf16, M' = M rounded up to 8 (zero-filled): the fast path of to_bf16(transpose=True)."""
-    xx = _dev(x2d, 'bfloat16')
-    M, C = xx.shape
-    ld = -(-M // 8) * 8
-    out = torch.empty((C, ld), dtype=torch.bfloat16, device=_device_of(xx))
-    _ffi.call('xa_im2col_t_bf16', _ptr(xx), _tptr(out), 1, 1, M, C, 1, 1, ld, 0, 0, _stream(stream))
-    _count()
-    return out
-
-
-def conv_wgrad_bf16(dy, x, kh, kw, *, s2d_order=False, workspace=None, stream=None):
-    """Weight (and bias) gradient of a stride-1 NHWC convolution on tcgen05 without an im2col matrix.
-    dy: [pixels, N] bf16 rows of the output gradient ((b,y,x) order, or the space-to-depth order of a layer written
-    with out_s2d); x: the layer input [B,H,W,C] bf16.  Returns (dW [N, kh*kw*C] fp32 with K ordered (kh,kw,c), db [N])."""
-    xx, dd = _dev(x, 'bfloat16'), _dev(dy, 'bfloat16')
-    B, H, W, C = xx.shape
-    N = dd.shape[-1]
-    OH, OW = H - kh + 1, W - kw + 1
-    Wg = -(-W // 8) * 8                                        # grid rows padded so that kh*Wg is a 16-byte aligned shift
-    Q = B * H * Wg
-    ld = Q
-    dev = _device_of(xx)
-    st = _stream(stream)
-    dyt = torch.empty((kw, N, ld), dtype=torch.bfloat16, device=dev)          # kw copies, copy j shifted right by j pixels
-    _ffi.call('xa_place_on_grid_t_bf16', _ptr(dd), _tptr(dyt), N, B, H, Wg, OH, OW, ld, int(bool(s2d_order)), kw, st)
-    xt = torch.empty((C, ld), dtype=torch.bfloat16, device=dev)
-    _ffi.call('xa_place_on_grid_t_bf16', _ptr(xx), _tptr(xt), C, B, H, Wg, H, W, ld, 0, 1, st)
-    ws_bytes = _ffi.lib().xa_conv_wgrad_workspace_bytes(N, C, kh, kw)
-    if workspace is None or workspace.numel() * workspace.element_size() < ws_bytes:
-        workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-    dw = torch.empty((N, kh * kw * C), dtype=torch.float32, device=dev)
-    _ffi.call('xa_conv_wgrad_bf16', _tptr(dyt), _tptr(xt), _tptr(dw), N, C, kh, kw, Wg, Q, ld, _tptr(workspace),
-              workspace.numel() * workspace.element_size(), st)
-    _count(3 + -(-kh // max(1, 512 // (kw * C))))
-    db = dyt[0].sum(1, dtype=torch.float32)                    # zero-padded columns add nothing
-    return dw, db
 
 
 def gather_s2d_u8_bf16(frames, idx, block=4, *, time_major=None, scale_255=True, out=None, stream=None):
