@@ -72,20 +72,51 @@ def workload_of(args, world):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled WHILE the bench runs.  NVML in a thread (a query takes well under
+    a millisecond, so a 25 ms timed region still gets a dozen samples); `nvidia-smi -lms` if NVML cannot be loaded."""
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
-    def __init__(self, gpu_index):
-        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, period_s=0.002):
+        self.gpu_index, self.period_s = gpu_index, period_s
+        self.proc, self.thread, self.lines, self.samples, self.stop_flag, self.source = None, None, [], [], False, None
+
+    def _nvml_loop(self, nv, handle, masks):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                power = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(sm), power, [n for n, m in masks if bits & m]))
+            except Exception:
+                pass
+            time.sleep(self.period_s)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            masks = [('hw_slowdown', nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ('hw_thermal_slowdown', nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ('sw_thermal_slowdown', nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ('sw_power_cap', nv.nvmlClocksThrottleReasonSwPowerCap)]
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle, masks), daemon=True)
+            self.thread.start()
+            self.source = 'nvml'
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = 'nvidia-smi'
         except Exception:
             self.proc = None
 
@@ -93,7 +124,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken from here on are the ones reported (call right before the timed region)."""
+        self.first = len(self.samples)
+
     def stop(self):
+        if self.source == 'nvml':
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            first = getattr(self, 'first', 0)
+            used = self.samples[first:] or self.samples[-1:]
+            sm = [x[0] for x in used]
+            reasons = sorted({r for x in used for r in x[2]})
+            return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.sm_max,
+                    'power_w_max': max((x[1] for x in used), default=None), 'samples': len(sm), 'reasons': reasons,
+                    'source': 'nvml, sampled every %.0f ms from the start of the timed region' % (self.period_s * 1e3)}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -103,7 +148,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in self.lines:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 8:
@@ -114,11 +158,12 @@ class ClockSampler:
                 power.append(float(parts[3]))
             except ValueError:
                 continue
-            for name, flag in zip(names, parts[4:8]):
+            for name, flag in zip(self.NAMES, parts[4:8]):
                 if flag.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons),
+                'source': 'nvidia-smi -lms 100'}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -216,7 +261,8 @@ def run_ours(args):
         if comm is not None:
             comm.wait_gradients()
 
-    # clocks are sampled from before the warm-up (nvidia-smi takes ~100 ms to start) to the end of the timed region
+    # the sampler starts before the warm-up (nvidia-smi, the fallback, takes ~100 ms to start); with NVML only the samples
+    # taken inside the timed region are reported
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -240,6 +286,8 @@ def run_ours(args):
     if comm is not None:
         comm.barrier()
     torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.mark()
     start.record(stream)
     for s in range(args.steps):
         cur[0] = s
