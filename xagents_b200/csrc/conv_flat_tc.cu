@@ -21,6 +21,26 @@ namespace {
 using namespace xa_tc;
 
 constexpr int kFlatThreads = 64 + 8 * 32;
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int64_t lds_i64(uint32_t a) {
+  int64_t v;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_i64(uint32_t a, int64_t v) { asm volatile("st.shared.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 constexpr int kMaxEntries = 40;
 
 struct FlatParams {
@@ -57,6 +77,7 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
   uint32_t* s_a = reinterpret_cast<uint32_t*>(tail + 256);  // [kMaxEntries]
   uint32_t* s_b = s_a + kMaxEntries;
   float* s_bias = reinterpret_cast<float*>(tail + 256 + 2 * kMaxEntries * 4);  // [N <= 128]
+  uint8_t* epi_stage = tail + 2048;  // 8 warps x (32 rows x (2 BN + 16) bytes + 512)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,77 +158,110 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
       }
     }
   } else {
-    // ---- epilogue: group `grp` (warps 2-5 / 6-9) owns accumulator `grp` = the CTA's tiles of that parity
+    // ---- epilogue: group `grp` (warps 2-5 / 6-9) owns accumulator `grp` = the CTA's tiles of that parity.
+    // tcgen05.ld hands every thread one ROW (32 consecutive columns): stored directly, a warp-wide 16-byte access touches
+    // 32 different lines, and those load/store wavefronts -- not the tensor pipe, not HBM -- bounded the data-gradient
+    // layers (ncu: LSU 80 % busy).  So each warp transposes through its own padded shared-memory tile: phase 1 writes
+    // rows as they come out of TMEM (thread = row), phase 2 moves 16-byte pieces with consecutive lanes on consecutive
+    // pieces of a row, so that mask loads and output stores are coalesced (4 wavefronts per access instead of 32).
     const int quad = warp & 3;
     const uint32_t grp = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t hw = static_cast<uint32_t>(p.H) * p.W;
+    constexpr int kPitch = BN * 2 + 16;   // bytes; +16 keeps 16-byte accesses of 32 rows conflict-free
+    constexpr int kPieces = BN / 8;       // 16-byte pieces per row
+    uint8_t* my_stage = epi_stage + static_cast<size_t>(warp - 2) * (32 * kPitch + 512);
+    // explicit shared-state-space accesses: through the aligned-up base pointer the compiler only sees generic addresses
+    const uint32_t my_stage_u32 = xa::smem_u32(my_stage), s_bias_u32 = xa::smem_u32(s_bias);
+    const uint32_t row_out_u32 = my_stage_u32 + 32 * kPitch;  // [32] int64 output offset of the row, -1 = dropped
+    const uint32_t row_msk_u32 = row_out_u32 + 256;            // [32] int64 mask offset of the row
+    // phase-2 coordinates: iteration `it` moves 32 consecutive 16-byte pieces = kRowsPerIt rows, so a thread keeps its
+    // piece (column group) for the whole kernel and only its row advances -- all per-iteration address arithmetic is
+    // an add of a compile-time constant.
+    constexpr int kRowsPerIt = 32 / kPieces;
+    const int piece = lane % kPieces, row0 = lane / kPieces;
+    int col_delta = piece * 8;  // element offset of my piece inside the output row
+    if (p.out_mode == 2) {      // (dy, dx, c) channel blocks land on pixels (2y+dy, 2x+dx): see xa_conv2d_nhwc_bf16_ex
+      constexpr int kN4 = BN / 4;
+      const int sub = col_delta / kN4;
+      col_delta = ((sub >> 1) * p.PW + (sub & 1)) * kN4 + (col_delta - sub * kN4);
+    }
+    const uint32_t my_piece_u32 = my_stage_u32 + row0 * kPitch + piece * 16;
     for (uint32_t lt = grp;; lt += 2) {
       const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
       if (tile >= n_tiles) break;
       const uint32_t acc = grp;
-      const int64_t q = static_cast<int64_t>(tile) * kBlockM + r;
-      const uint32_t qq = static_cast<uint32_t>(q < p.Q ? q : 0);
-      const int ob = static_cast<int>(qq / hw);
-      const uint32_t rem = qq - static_cast<uint32_t>(ob) * hw;
-      const int oy = static_cast<int>(rem / p.W), ox = static_cast<int>(rem - (rem / p.W) * p.W);
-      const bool valid = q < p.Q && oy < p.OH && ox < p.OW;
-      int64_t out_off = 0, mask_off = 0;
-      if (valid) {
-        mask_off = ((static_cast<int64_t>(ob) * p.OH + oy) * p.OW + ox) * p.N;
-        if (p.out_mode == 1)
-          out_off = ((static_cast<int64_t>(ob) * (p.OH / 2) + oy / 2) * (p.OW / 2) + ox / 2) * (4 * p.N) + ((oy & 1) * 2 + (ox & 1)) * p.N;
-        else if (p.out_mode == 2)
-          out_off = ((static_cast<int64_t>(ob) * p.PH + 2 * oy) * p.PW + 2 * ox) * (p.N / 4);
-        else
-          out_off = ((static_cast<int64_t>(ob) * p.PH + oy) * p.PW + ox) * p.N;
+      {  // phase 0: where does my row go?
+        const int64_t q = static_cast<int64_t>(tile) * kBlockM + r;
+        const uint32_t qq = static_cast<uint32_t>(q < p.Q ? q : 0);
+        const int ob = static_cast<int>(qq / hw);
+        const uint32_t rem = qq - static_cast<uint32_t>(ob) * hw;
+        const int oy = static_cast<int>(rem / p.W), ox = static_cast<int>(rem - (rem / p.W) * p.W);
+        const bool valid = q < p.Q && oy < p.OH && ox < p.OW;
+        int64_t out_off = -1, mask_off = 0;
+        if (valid) {
+          mask_off = ((static_cast<int64_t>(ob) * p.OH + oy) * p.OW + ox) * p.N;
+          if (p.out_mode == 1)
+            out_off = ((static_cast<int64_t>(ob) * (p.OH / 2) + oy / 2) * (p.OW / 2) + ox / 2) * (4 * p.N) + ((oy & 1) * 2 + (ox & 1)) * p.N;
+          else if (p.out_mode == 2)
+            out_off = ((static_cast<int64_t>(ob) * p.PH + 2 * oy) * p.PW + 2 * ox) * (p.N / 4);
+          else
+            out_off = ((static_cast<int64_t>(ob) * p.PH + oy) * p.PW + ox) * p.N;
+        }
+        sts_i64(row_out_u32 + lane * 8, out_off);
+        sts_i64(row_msk_u32 + lane * 8, mask_off);
       }
-      uint4 mraw[BN / 8];
-      const bool use_mask = p.mask != nullptr && valid;
-      if (use_mask) {
+      __syncwarp();
+      // the ReLU-derivative mask does not depend on the accumulator: fetch it (coalesced) before waiting
+      uint4 mraw[kPieces];
+      if (p.mask != nullptr) {
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) mraw[j] = __ldg(reinterpret_cast<const uint4*>(p.mask + mask_off) + j);
+        for (int it = 0; it < kPieces; ++it) {
+          const int row = it * kRowsPerIt + row0;
+          if (lds_i64(row_out_u32 + row * 8) >= 0)
+            mraw[it] = __ldg(reinterpret_cast<const uint4*>(p.mask + lds_i64(row_msk_u32 + row * 8)) + piece);
+        }
       }
       mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float lo = p.relu ? 0.0f : -INFINITY;  // ReLU as one max per element, no per-element branch on the flag
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {  // phase 1: TMEM -> (+bias, ReLU) -> bf16 rows in shared memory
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
-        if (valid) {
-          int64_t off = out_off + c0;
-          if (p.out_mode == 2) {
-            const int n4 = p.N / 4, sub = c0 / n4;
-            off = out_off + (static_cast<int64_t>(sub >> 1) * p.PW + (sub & 1)) * n4 + (c0 - sub * n4);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.y + off);
+        const uint32_t dst = my_stage_u32 + lane * kPitch + c0 * 2;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h[4];
-            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw[c0 / 8 + j]);
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * j + 4);
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float a = __uint_as_float(v[8 * j + 2 * t]) + bv[2 * t], b = __uint_as_float(v[8 * j + 2 * t + 1]) + bv[2 * t + 1];
-              if (p.relu) {
-                a = fmaxf(a, 0.0f);
-                b = fmaxf(b, 0.0f);
-              }
-              if (use_mask) {
-                if (!(__low2float(mk[t]) > 0.0f)) a = 0.0f;
-                if (!(__high2float(mk[t]) > 0.0f)) b = 0.0f;
-              }
-              h[t] = __floats2bfloat162_rn(a, b);
-            }
-            dst[j] = *reinterpret_cast<uint4*>(h);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = lds_f4(s_bias_u32 + (c0 + 8 * j) * 4), b1 = lds_f4(s_bias_u32 + (c0 + 8 * j + 4) * 4);
+          __nv_bfloat162 h[4];
+          h[0] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, lo));
+          h[1] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, lo));
+          h[2] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, lo));
+          h[3] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, lo));
+          sts_u4(dst + j * 16, *reinterpret_cast<uint4*>(h));
         }
       }
+      // the accumulator is drained: hand it back before the global stores
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+#pragma unroll
+      for (int it = 0; it < kPieces; ++it) {  // phase 2: coalesced mask application and stores
+        const int64_t off0 = lds_i64(row_out_u32 + (it * kRowsPerIt + row0) * 8);
+        if (off0 >= 0) {
+          uint4 val = lds_u4(my_piece_u32 + it * (kRowsPerIt * kPitch));
+          if (p.mask != nullptr) {  // ReLU derivative of the layer below: zero where its activation was <= 0
+            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw[it]);
+            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
+            val.x &= __hgt2_mask(mk[0], zero);
+            val.y &= __hgt2_mask(mk[1], zero);
+            val.z &= __hgt2_mask(mk[2], zero);
+            val.w &= __hgt2_mask(mk[3], zero);
+          }
+          *reinterpret_cast<uint4*>(p.y + off0 + col_delta) = val;
+        }
+      }
+      __syncwarp();  // the tile's staging rows are free again
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -256,7 +310,8 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   FlatParams p{};
   p.w_bytes = static_cast<uint32_t>(n_entries) * n_out * 128u;
   p.stage_bytes = static_cast<uint32_t>(kc_blocks) * win_rows * 128u;
-  const int64_t budget = 227 * 1024 - 1024 /*alignment*/ - 2048 /*barriers, tables, bias*/ - p.w_bytes;
+  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 512);  // the epilogue warps' transposing tiles
+  const int64_t budget = 227 * 1024 - 1024 /*alignment*/ - 2048 /*barriers, tables, bias*/ - epi_bytes - p.w_bytes;
   int stages = static_cast<int>(budget / p.stage_bytes);
   if (stages < 2) return 1;
   if (stages > 6) stages = 6;
@@ -276,7 +331,7 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   CUtensorMap mx, mw;
   if (int rc = make_map_2d_box(&mx, x, Q, channels, win_rows, 64, what)) return rc;
   if (int rc = make_map_2d(&mw, w, n_out, static_cast<int64_t>(kh) * kw * channels, n_out, what)) return rc;
-  const size_t smem = 1024 + p.w_bytes + static_cast<size_t>(stages) * p.stage_bytes + 2048;
+  const size_t smem = 1024 + p.w_bytes + static_cast<size_t>(stages) * p.stage_bytes + 2048 + epi_bytes;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n_out == 128) return launch_flat<128>(mx, mw, p, smem, s, what);
   if (n_out == 64) return launch_flat<64>(mx, mw, p, smem, s, what);
