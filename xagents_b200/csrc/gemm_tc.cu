@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
     // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); group (w-2)/4 owns accumulator (w-2)/4
     const int quad = warp & 3;
     const uint32_t grp = (warp - 2) >> 2;
-    const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16);
+    const bool vec_ok = (p.ldc % (kOutBf16 ? 8 : 4)) == 0 && xa::aligned(p.c, 16) && (p.col_group % 8) == 0 && (p.col_group_pitch % 8) == 0;
+    const bool bias_vec = xa::aligned(p.bias, 16);
     constexpr int kChunks = BN < 32 ? 1 : BN / 32;
     for (uint32_t lt = grp;; lt += 2) {
       const int item = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
@@ -193,6 +194,45 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
             } else {
               for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
             }
+          }
+        } else if (row < p.m && col0 + 32 <= p.n && vec_ok && bias_vec && (p.mask == nullptr || (mvec && kOutBf16))) {
+          // Fast path (a full chunk of 32 columns, vector-aligned): the epilogue of the short-K products is bounded by its
+          // instruction count, so no per-element flag tests here -- bias by vector loads, ReLU as one max, the mask as a
+          // packed bf16 compare that yields a bit mask.
+          const int64_t ocol0 = p.col_group > 0 ? (col0 / p.col_group) * p.col_group_pitch + col0 % p.col_group : col0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(bp + q);
+              f[4 * q] += b.x, f[4 * q + 1] += b.y, f[4 * q + 2] += b.z, f[4 * q + 3] += b.w;
+            }
+          }
+          const float lo = p.relu ? 0.0f : -INFINITY;
+          if (kOutBf16) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + ocol0);
+            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(fmaxf(f[8 * j + 2 * q], lo), fmaxf(f[8 * j + 2 * q + 1], lo));
+              uint4 o = *reinterpret_cast<uint4*>(h);
+              if (p.mask != nullptr) {
+                const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&m0[j]);
+                o.x &= __hgt2_mask(mk[0], zero), o.y &= __hgt2_mask(mk[1], zero);
+                o.z &= __hgt2_mask(mk[2], zero), o.w &= __hgt2_mask(mk[3], zero);
+              }
+              dst[j] = o;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + ocol0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(fmaxf(f[4 * j], lo), fmaxf(f[4 * j + 1], lo), fmaxf(f[4 * j + 2], lo), fmaxf(f[4 * j + 3], lo));
           }
         } else if (row < p.m && col0 < p.n) {
           float f[32];
