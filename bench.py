@@ -171,6 +171,14 @@ def cpu_reference(args, sample_envs, steps, warmup):
     """The reference's CPU path (oracle port; TF is not installable here) on a bounded sample."""
     import torch
 
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1, which would make the N>1 reference arm 4x slower
+    # than the N=1 one for no reason of the reference's
+    try:
+        n_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_threads))
+
     from oracle import cpu_path
     from xagents_b200 import synthetic
     ro = synthetic.make_rollout(args.n_steps, sample_envs, epochs=4)
@@ -416,6 +424,9 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever NCCL wants to say (a box may export NCCL_DEBUG=VERSION)
+    # goes to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     if args.impl == 'reference':
         run_reference(args)
     else:
