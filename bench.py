@@ -213,7 +213,7 @@ def run_reference(args):
         'e2e': {'value': res['env_steps_per_sec'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -419,14 +419,30 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         _, base = cpu_reference(args, args.cpu_sample_envs, 3, 1)
         line['cpu_baseline'] = base
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    global _RESULT_FD
     args = parse_args()
-    # stdout carries the ONE JSON line and nothing else: whatever NCCL wants to say (a box may export NCCL_DEBUG=VERSION)
-    # goes to stderr
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL announces its version on
+    # stdout when a communicator is created) are pointed at stderr for the whole run
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
