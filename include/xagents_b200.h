@@ -193,8 +193,11 @@ int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias,
  * Passing workspace = NULL simply disables splitting.  relu_mask: optional bf16 [m, ldc], c *= (mask > 0). */
 int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
-/* Stride-1 NHWC convolution as an implicit GEMM on tcgen05 (no im2col buffer: per kernel tap TMA fetches the
- * shifted box of the activation, zero-filled outside the image): the network's convolutional trunk
+/* Stride-1 NHWC convolution as an implicit GEMM on tcgen05, no im2col buffer.  Two kernels behind one entry point:
+ * the flat kernel (csrc/conv_flat_tc.cu: pixels flattened, one window per 128-pixel tile, each tap a row-shifted view
+ * of it, weights resident in shared memory) for unpadded layers and zero-bordered full-padding gradients with
+ * n_out in {32, 64, 128}; otherwise the per-tap kernel (csrc/conv_tc.cu: per kernel tap TMA fetches the shifted box
+ * of the activation, zero-filled outside the image).  This is the network's convolutional trunk
  * (ppo/models/cnn-actor-critic.cfg:1-21) after space-to-depth turns its strided layers into stride-1 ones, and,
  * with pad = k-1 and flipped weights, its data-gradient (relu_mask, output layout, applies the ReLU derivative of
  * the layer below).  x [B,H,W,C] bf16, w [n_out, kh*kw*C] bf16 with K ordered (kh, kw, c), y [B,OH,OW,n_out] bf16

@@ -354,3 +354,19 @@ def test_gradients_written_straight_onto_zero_bordered_grids():
     g1f = torch.zeros_like(g1)
     ops.conv2d_nhwc_bf16(g2, w2, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=m2, out=g1f, unpack_s2d=True, zero_border=True)
     assert torch.equal(g1f, want1)
+
+
+@pytest.mark.timeout(120)
+def test_same_padding_with_zero_border_falls_back_to_the_per_tap_kernel():
+    """A 3x3 convolution with pad 1 reads below/right of the image for its last output row/column: the flat kernel cannot
+    express that as a row shift, so the zero-border promise must not route it there."""
+    torch.manual_seed(5)
+    B, H, W, C, N = 6, 9, 9, 64, 64
+    x = torch.zeros(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    x[:, :H - 1, :W - 1] = torch.randn(B, H - 1, W - 1, C, device=DEV).to(torch.bfloat16)     # zero last row / column
+    w = (torch.randn(N, 3 * 3 * C, device=DEV) * 0.05).to(torch.bfloat16)
+    plain = ops.conv2d_nhwc_bf16(x, w, 3, 3, pad=(1, 1))
+    promised = ops.conv2d_nhwc_bf16(x, w, 3, 3, pad=(1, 1), zero_border=True)
+    assert torch.equal(plain, promised)
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().reshape(N, 3, 3, C).permute(0, 3, 1, 2), padding=1)
+    assert float((plain.float() - want.permute(0, 2, 3, 1)).abs().max()) <= 4e-3 * float(want.abs().max())

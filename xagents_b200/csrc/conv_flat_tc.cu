@@ -299,7 +299,11 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
                      xa_stream_t stream) {
   const char* what = "xa_conv2d_nhwc_bf16";
   if (!(n_out == 32 || n_out == 64 || n_out == 128)) return 1;
-  if (OH > height || OW > width) return 1;  // output pixels are indexed on the input grid
+  // Output pixels are indexed on the input grid, and a kept output (y < OH, x < OW) must never read below / right of its
+  // image -- there the flattened index would run into the next row / image instead of padding.  True for unpadded
+  // convolutions and for full padding (pad = k - 1, the data gradients); 'same'-style padding goes to the per-tap kernel.
+  if (OH > height || OW > width) return 1;
+  if (OH > height + pad_y - kh + 1 || OW > width + pad_x - kw + 1) return 1;
   const int kc_blocks = channels / kBlockK;
   const int n_entries = kh * kw * kc_blocks;
   if (n_entries > kMaxEntries) return 1;
