@@ -194,3 +194,30 @@ def test_fit_with_a_torch_model_trains_on_device():
     assert net.n_params == 1_687_719 - 0 or net.n_params > 1_600_000      # Nature CNN @84x84x4, 6 actions
     losses = torch.stack(agent.loss_history).cpu().numpy()
     assert np.isfinite(losses).all()
+
+
+@pytest.mark.timeout(240)
+def test_ppo_fit_with_the_as_coded_conv1d_network_on_the_tensor_core_dense_path():
+    """The .cfg as ModelReader actually builds it (Conv1D trunk, 19.3 M parameters): same agent, loss kernels and fused
+    optimiser; its 37 632 -> 512 Dense layer runs on the tcgen05 GEMM."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    from xagents_b200.agents import PPO, AsCodedConv1dCNN, TorchModel
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    T, E, A = 8, 4, 6
+    rng = np.random.default_rng(3)
+    obs, rewards, dones, resets = mg._streams(rng, 3 * T, E, (84, 84, 4), True, 0.1)
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+    torch.manual_seed(0)
+    net = TorchModel(AsCodedConv1dCNN(4, A, tensor_core_dense=True).cuda())
+    assert net.n_params == 19_293_351
+    before = net.flat_param.clone()
+    agent = PPO(envs, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=5)
+    agent.fit(max_steps=2 * T * E)
+    torch.cuda.synchronize()
+    assert agent.steps == 2 * T * E and net.step == 2 * 2 * 4
+    assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)

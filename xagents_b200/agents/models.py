@@ -173,3 +173,37 @@ class NatureCNN(torch.nn.Module):
     def forward(self, x):                                          # x: [n, 84, 84, C] channels-last like the reference
         h = self.trunk(x.permute(0, 3, 1, 2))
         return self.actor(h), self.critic(h)
+
+
+class AsCodedConv1dCNN(torch.nn.Module):
+    """The same `.cfg` as the reference's ModelReader ACTUALLY builds it: the conv sections become
+    `Conv1D` layers (utils/common.py:17,231-237), which Keras applies to the 4-D frame batch with the image rows as an
+    extended batch dimension -- 1-D convolutions along the width, 32x8/4 -> 64x4/2 -> 64x3/1 on [n, 84, 84, C], then
+    flatten (84*7*64 = 37 632) -> FC512 -> heads: 19.3 M parameters against the documented Conv2D network's 1.69 M.
+    The 1-D convolutions (4/32/64 channels, a few MFLOP per frame) run through the framework's library path; the FC
+    layer that holds 99.6 % of the parameters and most of the flops runs on the tcgen05 GEMM (`TcLinear`) when
+    `tensor_core_dense` is set.  Both architectures go through the same agents, loss kernels and fused optimiser."""
+
+    def __init__(self, in_channels=4, n_actions=6, tensor_core_dense=False):
+        super().__init__()
+        nn = torch.nn
+        if tensor_core_dense:
+            from .tc_dense import TcLinear
+            fc = [TcLinear(84 * 7 * 64, 512, relu=True)]
+            self.actor, self.critic = TcLinear(512, n_actions), TcLinear(512, 1)
+        else:
+            fc = [nn.Linear(84 * 7 * 64, 512), nn.ReLU()]
+            self.actor, self.critic = nn.Linear(512, n_actions), nn.Linear(512, 1)
+        conv = lambda cin, cout, k, s: nn.Conv2d(cin, cout, (1, k), (1, s))       # Conv1D over an extended batch of rows
+        self.trunk = nn.Sequential(conv(in_channels, 32, 8, 4), nn.ReLU(), conv(32, 64, 4, 2), nn.ReLU(), conv(64, 64, 3, 1), nn.ReLU())
+        self.fc = nn.Sequential(*fc)
+        mods = [m for m in self.trunk if hasattr(m, 'weight')] + [m for m in self.fc if hasattr(m, 'weight')]
+        for mod, gain in [(m, 2 ** 0.5) for m in mods] + [(self.actor, 0.01), (self.critic, 1.0)]:
+            nn.init.orthogonal_(mod.weight, gain)
+            nn.init.zeros_(mod.bias)
+
+    def forward(self, x):                                          # x: [n, 84, 84, C] channels-last like the reference
+        h = self.trunk(x.permute(0, 3, 1, 2))                      # [n, 64, 84, 7]
+        h = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)          # Keras flatten order (row, position, channel)
+        h = self.fc(h)
+        return self.actor(h), self.critic(h)
