@@ -229,6 +229,10 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
                               int block, int scale_255, xa_stream_t stream);
 
+/* dst[i] = src[map[i]] as bf16 (out_bf16) or fp32, 0 where map[i] < 0: re-derives every weight layout of the
+ * tensor-core network (all permutations of the fp32 parameters) in one launch after an optimiser step. */
+int xa_gather_cast_f32(const float* src, const int32_t* map, void* dst, int64_t n, int out_bf16, xa_stream_t stream);
+
 /* c [m, n] fp32 (pitch ldc) = a^T b for ROW-MAJOR a [k, m] and b [k, n] bf16: the Dense weight gradient dW = dY^T X
  * with dY [batch, out] and X [batch, in] as the other kernels leave them -- no transposed copies (MN-major UMMA
  * operands, csrc/gemm_atb_tc.cu).  m and n multiples of 8.  workspace (xa_gemm_atb_workspace_bytes, may be NULL)

@@ -74,6 +74,7 @@ PROTOTYPES = {
                            [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_conv2d_nhwc_bf16_ex': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                                [ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_stream]),
+    'xa_gather_cast_f32': (ctypes.c_int, [c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_stream]),
     'xa_gemm_atb_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_gemm_bf16_atb': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),

@@ -24,61 +24,13 @@ import torch
 
 from .. import ops
 from .models import NatureCNN
-from .tc_conv import _s2d_kernel
+from .tc_operands import OperandPack
 
 
 def _s2d_kernel_inverse(g, n, c, kh, kw, s):
     """[N, (kh', kw', dy, dx, c)] -> torch [N, C, KH, KW]."""
     g = g.reshape(n, kh // s, kw // s, s, s, c).permute(0, 1, 3, 2, 4, 5).reshape(n, kh, kw, c)
     return g.permute(0, 3, 1, 2).contiguous()
-
-
-def _flip(w, kh, kw, c):
-    """forward [N, kh*kw*C] -> data-gradient weights [C, kh*kw*N]: W'[c, kh', kw', n] = W[n, KH-1-kh', KW-1-kw', c]."""
-    n = w.shape[0]
-    return w.reshape(n, kh, kw, c).flip(1, 2).permute(3, 1, 2, 0).reshape(c, kh * kw * n).contiguous()
-
-
-class _Operands:
-    """bf16 operand copies of the weights, re-derived after every optimiser step."""
-
-    @torch.no_grad()
-    def __init__(self, m):
-        bf = lambda t: t.to(torch.bfloat16).contiguous()
-        c1, c2, c3 = [x for x in m.trunk if isinstance(x, torch.nn.Conv2d)]
-        fc = [x for x in m.trunk if isinstance(x, torch.nn.Linear)][0]
-        self.w1 = bf(_s2d_kernel(c1.weight, 4))                                   # [32, 2*2*64]
-        self.w2 = bf(_s2d_kernel(c2.weight, 2))                                   # [64, 2*2*128]
-        self.w3 = bf(c3.weight.permute(0, 2, 3, 1).reshape(64, -1))               # [64, 3*3*64]
-        self.w2_flip = _flip(self.w2, 2, 2, 128)                                  # [128, 2*2*64]
-        self.w3_flip = _flip(self.w3, 3, 3, 64)                                   # [64, 3*3*64]
-        wf = fc.weight.reshape(512, 64, 7, 7).permute(0, 2, 3, 1).reshape(512, -1)
-        self.wf = bf(wf)                                                          # [512, 3136] (h, w, c)
-        self.wf_t = bf(wf.t())                                                    # [3136, 512]
-        a, c = m.actor, m.critic
-        self.n_actions = a.weight.shape[0]
-        heads = torch.zeros((8 * ((self.n_actions + 1 + 7) // 8), 512), device=a.weight.device)
-        heads[:self.n_actions] = a.weight
-        heads[self.n_actions] = c.weight[0]
-        self.wh = bf(heads)                                                       # [8, 512]
-        self.wh_t = bf(heads.t())                                                 # [512, 8]
-        self.b1, self.b2, self.b3 = (x.bias.detach().float().contiguous() for x in (c1, c2, c3))
-        self.bf_ = fc.bias.detach().float().contiguous()
-        hb = torch.zeros(heads.shape[0], device=a.weight.device)
-        hb[:self.n_actions] = a.bias
-        hb[self.n_actions] = c.bias[0]
-        self.bh = hb
-        self._grids = m._grids
-
-    def grids(self, batch):
-        """dY3 / dY2 / dY1 on the pixel grids of their layers' inputs.  Allocated zeroed once per batch size: the kernels
-        only ever write the valid corner, so the borders stay zero."""
-        g = self._grids.get(batch)
-        if g is None:
-            dev = self.w1.device
-            g = self._grids[batch] = tuple(torch.zeros((batch, h, h, n), dtype=torch.bfloat16, device=dev)
-                                           for h, n in ((9, 64), (10, 64), (21, 32)))
-        return g
 
 
 class _NatureCnnFn(torch.autograd.Function):
@@ -139,10 +91,13 @@ class NatureCnnTc(NatureCNN):
         assert in_channels == 4, 'the space-to-depth layouts are built for 84x84x4 frames'
         super().__init__(in_channels, n_actions)
         self._op = None
-        self._grids = {}
 
     def refresh(self):
-        self._op = _Operands(self)
+        """bf16 operand layouts of the current weights: two launches (index-map gather + cast, tc_operands.py)."""
+        if self._op is None:
+            self._op = OperandPack(self)
+        else:
+            self._op.refresh()
         return self
 
     def forward(self, frames_u8):

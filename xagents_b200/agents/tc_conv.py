@@ -18,55 +18,31 @@ train step); the backward convolutions are not built yet, so training still diff
 import torch
 
 from .. import ops
-
-
-def _s2d_kernel(w, s):
-    """torch conv weight [N, C, KH, KW] with stride s -> [N, (KH/s)*(KW/s)*(s*s*C)] for the stride-1 conv over the
-    space-to-depth input: K ordered (kh', kw', dy, dx, c)."""
-    n, c, kh, kw = w.shape
-    w = w.permute(0, 2, 3, 1)                                           # [N, KH, KW, C]
-    w = w.reshape(n, kh // s, s, kw // s, s, c).permute(0, 1, 3, 2, 4, 5)   # [N, kh', kw', dy, dx, C]
-    return w.reshape(n, -1).contiguous()
+from .tc_operands import OperandPack
 
 
 class NatureCnnTcForward:
     def __init__(self, module):
         self.module = module
         self._graphs = {}
+        self._pack, self._shared = None, False
         self.refresh()
 
     @torch.no_grad()
     def refresh(self):
-        """Re-derive the bf16 operand copies from the module's fp32 weights (after an optimiser step)."""
-        convs = [m for m in self.module.trunk if isinstance(m, torch.nn.Conv2d)]
-        fc = [m for m in self.module.trunk if hasattr(m, 'weight') and m.weight.dim() == 2][0]
-        bf = lambda t: t.to(torch.bfloat16).contiguous()
-        def keep(name, value):                      # same buffer on every refresh: captured graphs read fixed addresses
-            old = getattr(self, name, None)
-            if old is not None and old.shape == value.shape and old.dtype == value.dtype:
-                old.copy_(value)
-            else:
-                setattr(self, name, value.contiguous().clone())
-
-        keep('w1', bf(_s2d_kernel(convs[0].weight, 4)))
-        keep('b1', convs[0].bias.float())
-        keep('w2', bf(_s2d_kernel(convs[1].weight, 2)))
-        keep('b2', convs[1].bias.float())
-        keep('w3', bf(convs[2].weight.permute(0, 2, 3, 1).reshape(64, -1)))
-        keep('b3', convs[2].bias.float())
-        wf = fc.weight.reshape(fc.weight.shape[0], 64, 7, 7).permute(0, 2, 3, 1).reshape(fc.weight.shape[0], -1)
-        keep('wf', bf(wf))
-        keep('bf_', fc.bias.float())
-        a, c = self.module.actor, self.module.critic
-        heads = torch.zeros((8 * ((a.weight.shape[0] + 1 + 7) // 8), a.weight.shape[1]), device=a.weight.device)
-        heads[:a.weight.shape[0]] = a.weight
-        heads[a.weight.shape[0]] = c.weight[0]
-        hb = torch.zeros(heads.shape[0], device=a.weight.device)
-        hb[:a.weight.shape[0]] = a.bias
-        hb[a.weight.shape[0]] = c.bias[0]
-        keep('wh', bf(heads))
-        keep('bh', hb)
-        self.n_actions = a.weight.shape[0]
+        """Re-derive the bf16 operand copies from the module's fp32 weights (after an optimiser step): two launches into
+        buffers with fixed addresses, so captured graphs stay valid.  A `NatureCnnTc` module shares its own pack."""
+        if self._pack is None:
+            own = getattr(self.module, '_op', None) if hasattr(self.module, 'refresh') else None
+            if own is None and hasattr(self.module, 'refresh'):
+                own = self.module.refresh()._op
+            self._pack = own if own is not None else OperandPack(self.module)
+            self._shared = own is not None
+        elif not self._shared:
+            self._pack.refresh()
+        for name in ('w1', 'b1', 'w2', 'b2', 'w3', 'b3', 'wf', 'bf_', 'wh', 'bh'):
+            setattr(self, name, getattr(self._pack, name))
+        self.n_actions = self._pack.n_actions
         return self
 
     @torch.no_grad()

@@ -1,0 +1,132 @@
+"""bf16 / fp32 operand copies of the Nature CNN's weights in the layouts the tcgen05 kernels read, refreshed in TWO
+launches after every optimiser step.
+
+The layouts (NHWC kernels with K ordered (kh, kw, c); strided layers rewritten for space-to-depth inputs; flipped
+kernels for the data gradients; the FC weight in the (h, w, c) flatten order of the reference's Keras Flatten on NHWC,
+and its transpose; both heads stacked into one zero-padded [8, 512] matrix) are all PERMUTATIONS of the parameters.  So
+the re-layout code below is run once on tensors of parameter INDICES; the resulting index map drives one gather+cast
+kernel (`xa_gather_cast_f32`) per refresh.  Re-deriving the operands with torch ops cost ~30 launches per refresh --
+and there is one refresh per minibatch.
+"""
+import torch
+
+from .. import ops
+
+
+def s2d_kernel(w, s):
+    """torch conv weight [N, C, KH, KW] with stride s -> [N, (KH/s)*(KW/s)*(s*s*C)] for the stride-1 conv over the
+    space-to-depth input: K ordered (kh', kw', dy, dx, c)."""
+    n, c, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)                                           # [N, KH, KW, C]
+    w = w.reshape(n, kh // s, s, kw // s, s, c).permute(0, 1, 3, 2, 4, 5)   # [N, kh', kw', dy, dx, C]
+    return w.reshape(n, -1).contiguous()
+
+
+def flip_kernel(w, kh, kw, c):
+    """forward [N, kh*kw*C] -> data-gradient weights [C, kh*kw*N]: W'[c, kh', kw', n] = W[n, KH-1-kh', KW-1-kw', c]."""
+    n = w.shape[0]
+    return w.reshape(n, kh, kw, c).flip(1, 2).permute(3, 1, 2, 0).reshape(c, kh * kw * n).contiguous()
+
+
+def derive(p, pad):
+    """All operand layouts from the parameters `p` (a dict of tensors: real weights, or their flat indices).  `pad`
+    fills the rows that pad the stacked heads to a multiple of 8 (0 for weights, -1 for indices)."""
+    w1 = s2d_kernel(p['c1w'], 4)                                              # [32, 2*2*64]
+    w2 = s2d_kernel(p['c2w'], 2)                                              # [64, 2*2*128]
+    w3 = p['c3w'].permute(0, 2, 3, 1).reshape(64, -1).contiguous()            # [64, 3*3*64]
+    wf = p['fcw'].reshape(512, 64, 7, 7).permute(0, 2, 3, 1).reshape(512, -1).contiguous()    # [512, 3136] (h, w, c)
+    n_actions = p['aw'].shape[0]
+    rows = 8 * ((n_actions + 1 + 7) // 8)
+    heads = torch.full((rows, 512), pad, dtype=p['aw'].dtype, device=p['aw'].device)
+    heads[:n_actions] = p['aw']
+    heads[n_actions] = p['cw'][0]
+    hb = torch.full((rows,), pad, dtype=p['aw'].dtype, device=p['aw'].device)
+    hb[:n_actions] = p['ab']
+    hb[n_actions] = p['cb'][0]
+    bf16 = dict(w1=w1, w2=w2, w3=w3, w2_flip=flip_kernel(w2, 2, 2, 128), w3_flip=flip_kernel(w3, 3, 3, 64), wf=wf,
+                wf_t=wf.t().contiguous(), wh=heads, wh_t=heads.t().contiguous())
+    f32 = dict(b1=p['c1b'], b2=p['c2b'], b3=p['c3b'], bf_=p['fcb'], bh=hb)
+    return bf16, f32
+
+
+class OperandPack:
+    """`.w1 .w2 .w3 .w2_flip .w3_flip .wf .wf_t .wh .wh_t` (bf16) and `.b1 .b2 .b3 .bf_ .bh` (fp32): views into two flat
+    buffers with fixed addresses (captured CUDA graphs keep reading them), rewritten by `refresh()`."""
+
+    def __init__(self, module):
+        convs = [m for m in module.trunk if isinstance(m, torch.nn.Conv2d)]
+        fc = [m for m in module.trunk if isinstance(m, torch.nn.Linear)][0]
+        self._named = dict(c1w=convs[0].weight, c1b=convs[0].bias, c2w=convs[1].weight, c2b=convs[1].bias, c3w=convs[2].weight,
+                           c3b=convs[2].bias, fcw=fc.weight, fcb=fc.bias, aw=module.actor.weight, ab=module.actor.bias,
+                           cw=module.critic.weight, cb=module.critic.bias)
+        self.n_actions = module.actor.weight.shape[0]
+        self._layout_key = None
+        self._grids = {}
+        self.refresh()
+
+    # ---- index map ---------------------------------------------------------------------------------------------
+    def _source(self):
+        """(flat fp32 tensor holding every parameter, offset of each parameter in it).  The parameters of a TorchModel
+        are views into one flat buffer: used in place; a free-standing module is concatenated (one extra launch)."""
+        params = list(self._named.values())
+        store = params[0].untyped_storage()
+        if all(q.untyped_storage().data_ptr() == store.data_ptr() and q.is_contiguous() for q in params):
+            flat = torch.empty(0, dtype=torch.float32, device=params[0].device).set_(store)
+            return flat, [q.storage_offset() for q in params], ('shared', store.data_ptr())
+        offs, total = [], 0
+        for q in params:
+            offs.append(total)
+            total += q.numel()
+        return None, offs, ('cat',)
+
+    def _build(self, offsets, device):
+        """Index maps (rebuilt when the parameters move, e.g. when TorchModel re-seats them in its flat buffer); the
+        operand buffers are allocated once, so captured CUDA graphs keep reading valid addresses."""
+        ids = {name: torch.arange(off, off + q.numel(), dtype=torch.float64, device=device).view_as(q)
+               for (name, q), off in zip(self._named.items(), offsets)}
+        bf16, f32 = derive(ids, -1.0)
+
+        def pack(parts):
+            views, chunks, pos = {}, [], 0
+            for name, t in parts.items():
+                n = t.numel()
+                padded = -(-n // 64) * 64                                   # every operand starts 128-byte aligned
+                chunk = torch.full((padded,), -1, dtype=torch.int32, device=device)
+                chunk[:n] = t.reshape(-1).to(torch.int32)
+                chunks.append(chunk)
+                views[name] = (pos, n, tuple(t.shape))
+                pos += padded
+            return torch.cat(chunks), views, pos
+
+        self._map16, views16, n16 = pack(bf16)
+        self._map32, views32, n32 = pack(f32)
+        if getattr(self, '_buf16', None) is None:
+            self._buf16 = torch.zeros(n16, dtype=torch.bfloat16, device=device)
+            self._buf32 = torch.zeros(n32, dtype=torch.float32, device=device)
+            for buf, views in ((self._buf16, views16), (self._buf32, views32)):
+                for name, (pos, n, shape) in views.items():
+                    setattr(self, name, buf[pos:pos + n].view(shape))
+
+    @torch.no_grad()
+    def refresh(self):
+        flat, offsets, key = self._source()
+        key = key + tuple(offsets)
+        if key != self._layout_key:
+            self._build(offsets, next(iter(self._named.values())).device)
+            self._layout_key = key
+        if flat is None:
+            flat = torch.cat([q.detach().reshape(-1).float() for q in self._named.values()])
+        ops.gather_cast_f32(flat, self._map16, self._buf16)
+        ops.gather_cast_f32(flat, self._map32, self._buf32)
+        return self
+
+    # ---- scratch the backward pass keeps per batch size ----------------------------------------------------------
+    def grids(self, batch):
+        """dY3 / dY2 / dY1 on the pixel grids of their layers' inputs.  Allocated zeroed once per batch size: the kernels
+        only ever write the valid corner, so the borders stay zero."""
+        g = self._grids.get(batch)
+        if g is None:
+            dev = self.w1.device
+            g = self._grids[batch] = tuple(torch.zeros((batch, h, h, n), dtype=torch.bfloat16, device=dev)
+                                           for h, n in ((9, 64), (10, 64), (21, 32)))
+        return g

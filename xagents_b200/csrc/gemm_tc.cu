@@ -449,3 +449,30 @@ extern "C" int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t ro
                                                         ld_dst, transpose);
   return xa::check_launch("xa_to_bf16");
 }
+
+// dst[i] = src[map[i]] (0 where map[i] < 0), as bf16 or fp32: every weight layout the tensor-core kernels read is a
+// permutation (+ zero padding) of the fp32 parameters, so one launch of this kernel re-derives all of them after an
+// optimiser step (agents/tc_operands.py builds the map once by running the re-layout code on parameter indices).
+namespace {
+__global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, void* __restrict__ dst,
+                                                           int64_t n, int out_bf16) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t j = __ldg(map + i);
+    const float v = j >= 0 ? __ldg(src + j) : 0.0f;
+    if (out_bf16)
+      static_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+    else
+      static_cast<float*>(dst)[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int xa_gather_cast_f32(const float* src, const int32_t* map, void* dst, int64_t n, int out_bf16, xa_stream_t stream) {
+  XA_REQUIRE(n >= 0, XA_EINVAL, "xa_gather_cast_f32: n=%lld", static_cast<long long>(n));
+  if (n == 0) return XA_OK;
+  XA_REQUIRE(src && map && dst, XA_EINVAL, "xa_gather_cast_f32: null pointer");
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t want = (n + 255) / 256, cap = static_cast<int64_t>(sms) * 16;
+  gather_cast_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, map, dst, n, out_bf16);
+  return xa::check_launch("xa_gather_cast_f32");
+}

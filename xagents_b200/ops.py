@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb', 'gather_cast_f32',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -529,3 +529,13 @@ def gemm_bf16_atb(a, b, *, split_k=True, stream=None):
     _ffi.call('xa_gemm_bf16_atb', _ptr(aa), _ptr(bb), _tptr(c), m, n, k, n, _tptr(ws), ws_bytes, _stream(stream))
     _count(2 if ws is not None else 1)
     return c
+
+
+def gather_cast_f32(src, index_map, out, *, stream=None):
+    """out[i] = src[index_map[i]] (0 where the index is negative), cast to out's dtype (bf16 or fp32)."""
+    s_, m_ = _dev(src, 'float32'), _dev(index_map, 'int32')
+    if out.dtype not in (torch.bfloat16, torch.float32) or out.numel() != m_.size:
+        raise ValueError('out must be a bf16/fp32 tensor with one element per map entry')
+    _ffi.call('xa_gather_cast_f32', _ptr(s_), _ptr(m_), _tptr(out), out.numel(), int(out.dtype == torch.bfloat16), _stream(stream))
+    _count()
+    return out
