@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc_path(), *ARCH_FLAGS, '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+    cmd = [nvcc_path(), *ARCH_FLAGS, '--threads', '0', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
            '-I', os.path.join(ROOT, 'include'), '-o', LIB_PATH + '.tmp', *srcs]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
