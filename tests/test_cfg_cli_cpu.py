@@ -1,0 +1,244 @@
+"""Host logic of the drop-in surface around the hot path (SURVEY.md §8b "CLI / factory" row): the `.cfg` network reader,
+the built-in environments and the `train` command line.  No GPU: nothing here launches a kernel."""
+import math
+import os
+import textwrap
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from xagents_b200 import cli, envs
+from xagents_b200.agents import AsCodedConv1dCNN, ModelReader
+
+MODELS = os.path.join(os.path.dirname(os.path.abspath(cli.__file__)), 'agents', 'models')
+CNN = os.path.join(MODELS, 'cnn-actor-critic.cfg')
+ANN = os.path.join(MODELS, 'ann-actor-critic.cfg')
+
+
+def _cfg(tmp_path, text):
+    path = tmp_path / 'net.cfg'
+    path.write_text(textwrap.dedent(text))
+    return str(path)
+
+
+# ---------------------------------------------------------------------- .cfg reader
+def test_default_cnn_cfg_has_the_parameter_counts_of_both_readings():
+    """As coded (Conv1D over the rows): 19 293 351; as documented (Conv2D, README.md:243-259): 1 687 719."""
+    as_coded = ModelReader(CNN, [6, 1], (84, 84, 4)).build_model()
+    documented = ModelReader(CNN, [6, 1], (84, 84, 4), conv_dims=2).build_model()
+    assert sum(p.numel() for p in as_coded.parameters()) == 19_293_351
+    assert sum(p.numel() for p in documented.parameters()) == 1_687_719
+    # README.md:243-259 prints 1 681 575: the same network on AtariWrapper's single-channel frames
+    assert sum(p.numel() for p in ModelReader(CNN, [6, 1], (84, 84, 1), conv_dims=2).build_model().parameters()) == 1_681_575
+    x = torch.rand(3, 84, 84, 4)
+    for net in (as_coded, documented):
+        actor, critic = net(x)
+        assert actor.shape == (3, 6) and critic.shape == (3, 1) and not net.output_is_softmax
+
+
+def test_as_coded_reading_equals_the_hand_written_conv1d_network():
+    """Same weights -> same outputs as agents.AsCodedConv1dCNN (the module the GPU tests train)."""
+    torch.manual_seed(0)
+    net = ModelReader(CNN, [6, 1], (84, 84, 4)).build_model()
+    ref = AsCodedConv1dCNN(4, 6)
+    convs = [m for m in ref.trunk if hasattr(m, 'weight')]
+    with torch.no_grad():
+        for i, conv in enumerate(convs):                           # Conv2d (1, k) kernels <- Conv1d kernels
+            conv.weight.copy_(net.layers[i].weight.unsqueeze(2))
+            conv.bias.copy_(torch.randn_like(conv.bias))
+            net.layers[i].bias.copy_(conv.bias)
+        for mine, theirs in ((net.layers[4], ref.fc[0]), (net.layers[5], ref.actor), (net.layers[6], ref.critic)):
+            theirs.weight.copy_(mine.weight)
+            theirs.bias.copy_(torch.randn_like(theirs.bias))
+            mine.bias.copy_(theirs.bias)
+    x = torch.rand(2, 84, 84, 4)
+    got, want = net(x), ref(x)
+    for g, w in zip(got, want):
+        assert torch.allclose(g, w, rtol=1e-5, atol=1e-6)
+
+
+def test_conv2d_reading_matches_a_channels_last_restatement():
+    net = ModelReader(CNN, [4, 1], (84, 84, 4), conv_dims=2, seed=3).build_model()
+    x = torch.rand(2, 84, 84, 4)
+    h = x.permute(0, 3, 1, 2)
+    for layer, stride in zip(net.layers[:3], (4, 2, 1)):
+        h = torch.relu(torch.nn.functional.conv2d(h, layer.weight, layer.bias, stride))
+    assert h.shape == (2, 64, 7, 7)
+    flat = h.permute(0, 2, 3, 1).reshape(2, -1)                    # Keras flatten order: (row, column, channel)
+    trunk = torch.relu(flat @ net.layers[4].weight.T + net.layers[4].bias)
+    actor, critic = net(x)
+    assert torch.allclose(actor, trunk @ net.layers[5].weight.T + net.layers[5].bias, atol=1e-6)
+    assert torch.allclose(critic, trunk @ net.layers[6].weight.T + net.layers[6].bias, atol=1e-6)
+
+
+def test_ann_cfg_and_initialisers():
+    net = ModelReader(ANN, [2, 1], (4,), seed=7).build_model()
+    assert sum(p.numel() for p in net.parameters()) == 4 * 64 + 64 + 64 * 64 + 64 + 64 * 2 + 2 + 64 + 1
+    again = ModelReader(ANN, [2, 1], (4,), seed=7).build_model()
+    other = ModelReader(ANN, [2, 1], (4,), seed=8).build_model()
+    assert all(torch.equal(a, b) for a, b in zip(net.parameters(), again.parameters()))
+    assert not torch.equal(net.layers[0].weight, other.layers[0].weight)
+    for layer, gain in zip(net.layers, (2 ** 0.5, 2 ** 0.5, 0.01, 1.0)):  # orthogonal(gain): W W^T or W^T W = gain^2 I
+        w = layer.weight.double()
+        gram = w @ w.T if w.shape[0] <= w.shape[1] else w.T @ w
+        assert torch.allclose(gram, gain ** 2 * torch.eye(gram.shape[0], dtype=torch.float64), atol=1e-5)
+        assert torch.count_nonzero(layer.bias) == 0
+    actor, critic = net(torch.rand(5, 4))
+    assert actor.shape == (5, 2) and critic.shape == (5, 1)
+
+
+def test_common_layer_wiring_outputs_and_softmax_detection(tmp_path):
+    """build_model (common.py:257-290): after a `common` layer every later dense layer reads it, not its predecessor."""
+    path = _cfg(tmp_path, """
+        [dense-0]
+        units=8
+        activation=tanh
+        common=1
+        [dense-1]
+        units=5
+        activation=relu
+        output=1
+        [dense-2]
+        activation=softmax
+        output=1
+        [dense-3]
+        output=1
+        """)
+    net = ModelReader(path, [3, 1], (6,)).build_model()
+    assert [layer.linear.in_features for layer in net.layers] == [6, 8, 8, 8]      # dense-2/3 read dense-0, not dense-1
+    outs = net(torch.rand(4, 6))
+    assert [tuple(o.shape) for o in outs] == [(4, 5), (4, 3), (4, 1)]
+    assert torch.allclose(outs[1].sum(-1), torch.ones(4), atol=1e-6)
+    assert net.output_is_softmax                                                    # a2c/agent.py:42-43
+    single = ModelReader(_cfg(tmp_path, '[dense-0]\nunits=3\noutput=1\n'), [], (6,)).build_model()
+    assert single(torch.rand(2, 6)).shape == (2, 3)
+
+
+def test_reader_errors(tmp_path):
+    with pytest.raises(AssertionError, match='Empty model configuration'):
+        ModelReader(_cfg(tmp_path, ''), [2], (4,)).build_model()
+    with pytest.raises(AssertionError, match='Output units given are less than dense layers required'):
+        ModelReader(ANN, [2], (4,)).build_model()
+    with pytest.raises(AssertionError, match='Unsupported activation'):
+        ModelReader(_cfg(tmp_path, '[dense-0]\nunits=3\nactivation=swishy\noutput=1\n'), [], (4,)).build_model()
+    with pytest.raises(AssertionError, match='smaller than the kernel'):
+        ModelReader(CNN, [2, 1], (84, 4, 4)).build_model()
+    reader = ModelReader(ANN, [2, 1], (4,))
+    reader.build_model()
+    assert reader.output_count == 0                                                 # reusable, like the reference's
+
+
+def test_tensor_core_dense_selection():
+    """Dense layers move to the tcgen05 GEMM only where the kernel's operand constraints hold."""
+    from xagents_b200.agents.tc_dense import TcLinear
+    net = ModelReader(CNN, [6, 1], (84, 84, 4), conv_dims=2, tensor_core_dense=True).build_model()
+    assert [isinstance(layer.linear, TcLinear) for layer in net.layers[4:]] == [True, True, True]
+    ann = ModelReader(ANN, [2, 1], (4,), tensor_core_dense=True).build_model()
+    assert [isinstance(layer.linear, TcLinear) for layer in ann.layers] == [False, False, True, True]  # K=4 / tanh stay
+
+
+# ---------------------------------------------------------------------- environments
+def test_cartpole_follows_the_published_dynamics():
+    env = envs.CartPole(seed=5)
+    s = env.reset()
+    assert s.shape == (4,) and s.dtype == np.float32 and np.abs(s).max() <= 0.05
+    x, xd, th, thd = env.state
+    nxt, reward, done, info = env.step(1)
+    total, pml = 1.1, 0.05
+    temp = (10.0 + pml * thd * thd * math.sin(th)) / total
+    th_acc = (9.8 * math.sin(th) - math.cos(th) * temp) / (0.5 * (4.0 / 3.0 - 0.1 * math.cos(th) ** 2 / total))
+    x_acc = temp - pml * th_acc * math.cos(th) / total
+    want = np.array([x + 0.02 * xd, xd + 0.02 * x_acc, th + 0.02 * thd, thd + 0.02 * th_acc], np.float32)
+    assert np.allclose(nxt, want, rtol=1e-6) and reward == 1.0 and not done
+    steps = 1
+    while not done:                                                 # pushing one way only: the pole falls quickly
+        nxt, reward, done, info = env.step(1)
+        steps += 1
+    assert steps < 30 and abs(nxt[2]) > env.THETA_LIMIT
+    a, b = envs.CartPole(seed=9), envs.CartPole(seed=9)
+    assert np.array_equal(a.reset(), b.reset())
+
+
+def test_cartpole_time_limit():
+    env = envs.CartPole(seed=0)
+    env.reset()
+    for t in range(500):                                            # a bang-bang controller on the pole angle keeps it up
+        s, r, done, info = env.step(1 if env.state[2] + 0.5 * env.state[3] > 0 else 0)
+        if done:
+            break
+    assert t == 499 and done and info['TimeLimit.truncated']
+
+
+def test_synthetic_atari_and_create_envs():
+    made = envs.create_envs('SyntheticAtari-v0', 3, preprocess=True)
+    assert len(made) == 3 and made[0].observation_space.shape == (84, 84, 4) and made[0].action_space.n == 6
+    frame = made[0].reset()
+    assert frame.shape == (84, 84, 4) and frame.dtype == np.uint8
+    made[0].seed(1)
+    rewards, dones = zip(*[(made[0].step(0)[1], made[0].step(0)[2]) for _ in range(2000)])
+    assert set(rewards) <= {-1.0, 0.0, 1.0} and 0 < sum(r != 0 for r in rewards) < 200 and 0 < sum(dones) < 100
+    with pytest.raises(AssertionError, match='Cannot use AtariWrapper or --preprocess for non-atari environment CartPole-v1'):
+        envs.create_envs('CartPole-v1', 1, preprocess=True)
+    with pytest.raises(ImportError, match='neither gym nor gymnasium'):
+        envs.create_envs('NoSuchEnv-v0', 1, preprocess=False)
+
+
+# ---------------------------------------------------------------------- command line
+def test_flag_tables_carry_the_reference_defaults():
+    """Defaults of xagents/utils/cli.py and xagents/{a2c,ppo}/cli.py."""
+    ex = cli.Executor()
+    ex.command, ex.agent_id = 'train', 'ppo'
+    agent, general, command = ex.parse_known_args(['train', 'ppo', '--env', 'CartPole-v1', '--max-steps', '10'])
+    assert vars(command) == {'target_reward': None, 'max_steps': 10, 'monitor_session': None}
+    want_agent = dict(reward_buffer_size=100, gamma=0.99, display_precision=2, seed=None, log_frequency=None, checkpoints=None,
+                      history_checkpoint=None, plateau_reduce_factor=0.9, plateau_reduce_patience=10, early_stop_patience=3,
+                      divergence_monitoring_steps=None, quiet=None, model=None, entropy_coef=0.01, value_loss_coef=0.5,
+                      grad_norm=0.5, n_steps=128, lam=0.95, ppo_epochs=4, mini_batches=4, advantage_epsilon=1e-8, clip_norm=0.1)
+    assert vars(agent) == want_agent
+    g = vars(general)
+    assert (g['env'], g['n_envs'], g['lr'], g['opt_epsilon'], g['beta1'], g['beta2'], g['weights']) == \
+        ('CartPole-v1', 1, 7e-4, 1e-7, 0.9, 0.999, None)
+    ex.agent_id = 'a2c'
+    agent, _, _ = ex.parse_known_args(['train', 'a2c', '--env', 'x', '--target-reward', '3', '--n-steps', '7', '--quiet'])
+    assert agent.n_steps == 7 and agent.quiet is True and not hasattr(agent, 'lam')
+    assert cli.a2c_args['n-steps']['default'] == 5
+
+
+def test_command_line_errors_and_help(capsys):
+    with pytest.raises(AssertionError, match='Invalid command `fly`'):
+        cli.execute(['fly'])
+    with pytest.raises(AssertionError, match='Invalid agent `dqn`'):       # off-policy agents are outside the hot path
+        cli.execute(['train', 'dqn'])
+    with pytest.raises(AssertionError, match='train requires --target-reward or --max-steps'):
+        cli.execute(['train', 'ppo', '--env', 'CartPole-v1'])
+    cli.Executor().execute([])
+    assert 'Available commands' in capsys.readouterr().out
+    cli.execute(['train', 'ppo'])
+    out = capsys.readouterr().out
+    for flag in ('--lam', '--mini-batches', '--clip-norm', '--env', '--max-steps', '--grad-norm', '--conv-dims'):
+        assert flag in out
+    ex = cli.Executor()
+    ex.command, ex.agent_id = 'train', 'a2c'
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        ex.parse_known_args(['train', 'a2c', '--env', 'x', '--max-steps', '5', '--no-such-flag'])
+    assert any('--no-such-flag' in str(w.message) for w in caught)
+
+
+def test_registry_shape():
+    """xagents.agents[id] keeps its keys (xagents/__init__.py:18-27; register_models, common.py:312-343)."""
+    from xagents_b200.agents import A2C, PPO
+    assert cli.agents['ppo']['agent'] is PPO and cli.agents['a2c']['agent'] is A2C
+    for agent_id in ('a2c', 'ppo'):
+        assert [os.path.basename(p) for p in cli.agents[agent_id]['model']['cnn']] == ['cnn-actor-critic.cfg']
+        assert [os.path.basename(p) for p in cli.agents[agent_id]['model']['ann']] == ['ann-actor-critic.cfg']
+        assert 'n-steps' in cli.agents[agent_id]['module'].cli_args
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_create_agent_fails_loudly_without_a_gpu():
+    """No CPU fallback: building the agent needs the device."""
+    with pytest.raises((RuntimeError, AssertionError)):
+        cli.execute(['train', 'ppo', '--env', 'CartPole-v1', '--n-envs', '2', '--max-steps', '10', '--quiet'])

@@ -221,3 +221,34 @@ def test_ppo_fit_with_the_as_coded_conv1d_network_on_the_tensor_core_dense_path(
     torch.cuda.synchronize()
     assert agent.steps == 2 * T * E and net.step == 2 * 2 * 4
     assert torch.isfinite(net.flat_param).all() and not torch.equal(before, net.flat_param)
+
+
+@pytest.mark.timeout(300)
+def test_cli_train_ppo_on_cartpole_learns():
+    """BASELINE config C1 end to end through the reference's command line: `xagents train ppo --env CartPole-v1
+    --n-envs 16` (n_steps defaults to 128), default `.cfg` network, every hot-path stage on the device.  A random policy
+    scores ~22 per episode; the mean over the last 100 episodes must clearly exceed that."""
+    from xagents_b200 import cli
+    ex = cli.Executor()
+    ex.execute(['train', 'ppo', '--env', 'CartPole-v1', '--n-envs', '16', '--max-steps', '81920', '--seed', '1', '--quiet'])
+    agent = ex.agent
+    assert type(agent).__name__ == 'PPO' and agent.n_steps == 128 and agent.n_envs == 16 and agent.steps >= 81920
+    assert agent.net.n_params == 4675 and agent.net.step == (81920 // 2048) * 16
+    agent.update_metrics()
+    assert torch.isfinite(agent.net.flat_param).all()
+    assert agent.best_reward > 35.0, f'PPO did not improve on CartPole: best mean reward {agent.best_reward}'
+
+
+@pytest.mark.timeout(300)
+def test_cli_train_a2c_on_synthetic_atari_frames_with_both_cfg_readings():
+    """Config C2's shape through the command line (A2C, 84x84x4 uint8 frames, n_envs=16, n_steps=5), the default `.cfg`
+    read as Conv2D (documented) and as Conv1D (as coded), Dense layers on the tcgen05 GEMM."""
+    from xagents_b200 import cli
+    for dims, n_params in ((2, 1_687_719), (1, 19_293_351)):
+        ex = cli.Executor()
+        ex.execute(['train', 'a2c', '--env', 'SyntheticAtari-v0', '--n-envs', '16', '--max-steps', '400', '--seed', '2', '--quiet',
+                    '--conv-dims', str(dims), '--tensor-core-dense', '--preprocess'])
+        agent = ex.agent
+        assert agent.n_steps == 5 and agent.steps == 400 and agent.net.n_params == n_params and agent.net.step == 5
+        assert agent.ro_states.dtype == torch.uint8 and tuple(agent.ro_states.shape) == (5, 16, 84, 84, 4)
+        assert torch.isfinite(agent.net.flat_param).all()

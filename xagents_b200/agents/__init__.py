@@ -2,8 +2,10 @@
 arithmetic on the B200 through the C ABI."""
 from .a2c import A2C
 from .base import BaseAgent, EnvMajorView, OnPolicy
+from .cfg import CfgNetwork, ModelReader
 from .models import AsCodedConv1dCNN, KerasModel, NatureCNN, TorchModel, adapt
 from .ppo import PPO
 from .tc_cnn import NatureCnnTc
 
-__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'NatureCnnTc', 'AsCodedConv1dCNN', 'adapt']
+__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'NatureCnnTc', 'AsCodedConv1dCNN', 'adapt',
+           'ModelReader', 'CfgNetwork']

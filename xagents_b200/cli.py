@@ -1,0 +1,262 @@
+"""`xagents train <a2c|ppo> ...` on the device path: the reference's command line for the two on-policy agents this
+package mirrors (xagents/cli.py:13-241, xagents/utils/cli.py, xagents/{a2c,ppo}/cli.py) and its factory
+(`create_model(s)` / `create_agent`, xagents/utils/common.py:430-494, 568-624).
+
+    python -m xagents_b200 train ppo --env CartPole-v1 --n-envs 16 --max-steps 200000
+    python -m xagents_b200 train a2c --env SyntheticAtari-v0 --n-envs 16 --max-steps 4000 --conv-dims 2
+
+Flags, defaults, the agent/non-agent/command split and the assertion messages are the reference's.  `play`, `tune`
+and the off-policy agents are outside the hot path and are refused as invalid commands / agents;
+checkpoint, history and wandb flags are accepted by the parser and refused by the agent (agents/base.py).
+Three flags are new: `--conv-dims` (1 = the `.cfg` as the reference's reader builds it, Conv1D; 2 = the documented
+Conv2D network), `--tensor-core-dense` (Dense layers on the tcgen05 GEMM) and `--device`.
+"""
+import argparse
+import sys
+import types
+import warnings
+from pathlib import Path
+
+from . import __version__, envs as _envs
+from .agents import A2C, PPO
+from .agents.cfg import ModelReader
+
+_MODELS = Path(__file__).parent / 'agents' / 'models'
+
+
+def _flag(help, type=None, default=None, action=None, required=None, nargs=None):
+    spec = {'help': help}
+    for key, value in (('type', type), ('default', default), ('action', action), ('required', required), ('nargs', nargs)):
+        if value is not None:
+            spec[key] = value
+    return spec
+
+
+non_agent_args = {
+    'env': _flag('environment id (built-in: CartPole-v1, SyntheticAtari-v0; else gym / gymnasium)', required=True),
+    'n-envs': _flag('Number of environments to create', int, 1),
+    'preprocess': _flag('Treat states as atari frames and preprocess them', action='store_true'),
+    'lr': _flag('Adam learning rate', float, 7e-4),
+    'opt-epsilon': _flag('Adam epsilon', float, 1e-7),
+    'beta1': _flag('Adam beta1', float, 0.9),
+    'beta2': _flag('Adam beta2', float, 0.999),
+    'weights': _flag('Path(s) to model weights (torch state_dict) loaded into the agent output_models', nargs='+'),
+    'max-frame': _flag('Max & skip during preprocessing', action='store_true'),
+    'conv-dims': _flag('1: convolutional sections as the reference reader builds them (Conv1D); 2: Conv2D', int, 1),
+    'tensor-core-dense': _flag('Dense layers on the tcgen05 GEMM', action='store_true'),
+    'device': _flag('CUDA device of this process', default='cuda:0'),
+}
+
+agent_args = {
+    'reward-buffer-size': _flag('Size of the total reward buffer used for the displayed mean reward', int, 100),
+    'gamma': _flag('Discount factor', float, 0.99),
+    'display-precision': _flag('Number of decimals to be displayed', int, 2),
+    'seed': _flag('Random seed', int),
+    'log-frequency': _flag('Log progress every n games', int),
+    'checkpoints': _flag('Path(s) to which checkpoint(s) would be saved (refused: outside the hot path)', nargs='+'),
+    'history-checkpoint': _flag('Path to .parquet training history (refused: outside the hot path)'),
+    'plateau-reduce-factor': _flag('Factor multiplied by the learning rate on a plateau', float, 0.9),
+    'plateau-reduce-patience': _flag('Minimum non-improvements to reduce lr', int, 10),
+    'early-stop-patience': _flag('Minimum plateau reduces to stop training', int, 3),
+    'divergence-monitoring-steps': _flag('Steps after which plateau and early stopping are active', int),
+    'quiet': _flag('No messages by the agent', action='store_true'),
+}
+
+train_args = {
+    'target-reward': _flag('Target reward: training stops when reached', int),
+    'max-steps': _flag('Maximum number of environment steps', int),
+    'monitor-session': _flag('Wandb session name (refused: outside the hot path)'),
+}
+
+a2c_args = {
+    'model': _flag('Path to model .cfg file'),
+    'entropy-coef': _flag('Entropy coefficient of the loss', float, 0.01),
+    'value-loss-coef': _flag('Value loss coefficient of the loss', float, 0.5),
+    'grad-norm': _flag('Global-norm gradient clipping value', float, 0.5),
+    'n-steps': _flag('Transition steps', int, 5),
+}
+
+ppo_args = dict(a2c_args)
+ppo_args.update({
+    'lam': _flag('GAE-Lambda for advantage estimation', float, 0.95),
+    'ppo-epochs': _flag('Gradient updates per training step', int, 4),
+    'mini-batches': _flag('Number of mini-batches per update', int, 4),
+    'advantage-epsilon': _flag('Value added to the advantage standard deviation', float, 1e-8),
+    'clip-norm': _flag('Clipping value of the probability ratio and of the value update', float, 0.1),
+    'n-steps': _flag('Transition steps', int, 128),
+})
+
+
+def _default_models():
+    groups = {'cnn': [], 'ann': []}
+    for cfg in sorted(_MODELS.iterdir()):
+        for kind in groups:
+            if cfg.suffix == '.cfg' and kind in cfg.name:
+                groups[kind].append(cfg.as_posix())
+    return groups
+
+
+# xagents.agents / xagents.commands (xagents/__init__.py:18-40), restricted to what this package mirrors
+agents = {
+    'a2c': {'module': types.SimpleNamespace(cli_args=a2c_args, __file__=str(_MODELS.parent / 'a2c.py')), 'agent': A2C,
+            'model': _default_models()},
+    'ppo': {'module': types.SimpleNamespace(cli_args=ppo_args, __file__=str(_MODELS.parent / 'ppo.py')), 'agent': PPO,
+            'model': _default_models()},
+}
+commands = {'train': (train_args, 'fit', 'Train given an agent and environment')}
+
+
+# ---------------------------------------------------------------------- factory
+def create_model(env, agent_id, model_type, optimizer_kwargs=None, seed=None, model_cfg=None, conv_dims=1,
+                 tensor_core_dense=False, device='cuda:0'):
+    """`.cfg` -> network -> device adapter.  Head widths as in common.py:447-471: n_actions (Discrete) or the action
+    dimension (Box), then 1 for an actor-critic file."""
+    space = env.action_space
+    units = [int(space.n) if hasattr(space, 'n') else int(space.shape[0])]
+    network_type = 'cnn' if len(env.observation_space.shape) == 3 else 'ann'
+    try:
+        model_cfg = model_cfg or agents[agent_id][model_type][network_type][0]
+    except (IndexError, KeyError):
+        model_cfg = None
+    assert model_cfg, (f'You should specify `model_cfg`. No default {network_type.upper()} model found in\n{_MODELS}')
+    name = Path(model_cfg).name
+    if 'actor' in name and 'critic' in name:
+        units.append(1)
+    elif 'critic' in name:
+        units[0] = 1
+    reader = ModelReader(model_cfg, units, env.observation_space.shape, optimizer_kwargs or {}, seed, conv_dims=conv_dims,
+                         tensor_core_dense=tensor_core_dense)
+    return reader.build_adapter(device)
+
+
+def create_models(options, env, agent_id, **kwargs):
+    models = {}
+    for model_type in ('model', 'actor_model', 'critic_model'):
+        if model_type in options:
+            model_cfg = options[model_type]
+            if not isinstance(model_cfg, (str, Path)):
+                model_cfg = None
+            models[model_type] = create_model(env, agent_id, model_type, model_cfg=model_cfg, **kwargs)
+    return models
+
+
+def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
+    """Environments + model + agent from parsed flags (common.py:568-624)."""
+    import torch
+    assert agent_id in agents, f'Invalid agent `{agent_id}`'
+    agent_kwargs = dict(agent_kwargs)
+    if trial is not None:
+        agent_kwargs['trial'] = trial
+    device = non_agent_kwargs.get('device') or 'cuda:0'
+    envs = _envs.create_envs(non_agent_kwargs['env'], non_agent_kwargs['n_envs'], non_agent_kwargs['preprocess'],
+                             max_frame=non_agent_kwargs.get('max_frame'))
+    agent_kwargs['envs'] = envs
+    optimizer_kwargs = {'learning_rate': non_agent_kwargs['lr'], 'beta_1': non_agent_kwargs['beta1'],
+                        'beta_2': non_agent_kwargs['beta2'], 'epsilon': non_agent_kwargs['opt_epsilon']}
+    agent_kwargs.update(create_models(agent_kwargs, envs[0], agent_id, optimizer_kwargs=optimizer_kwargs,
+                                      seed=agent_kwargs.get('seed'), conv_dims=non_agent_kwargs.get('conv_dims', 1),
+                                      tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device))
+    agent = agents[agent_id]['agent'](device=device, **agent_kwargs)
+    if non_agent_kwargs.get('weights'):
+        n_weights, n_models = len(non_agent_kwargs['weights']), len(agent.output_models)
+        assert n_weights == n_models, f'Expected {n_models} weights to load, got {n_weights}'
+        for weight, model in zip(non_agent_kwargs['weights'], agent.output_models):
+            model.module.load_state_dict(torch.load(weight, map_location=device))
+            for mod in getattr(model, '_refreshable', []):
+                mod.refresh()
+    return agent
+
+
+# ---------------------------------------------------------------------- command line
+class Executor:
+    def __init__(self):
+        self.agent_id = None
+        self.command = None
+        self.agent = None
+
+    @staticmethod
+    def display_section(title, cli_args):
+        print(f'\n{title}\n')
+        width = max(len(flag) for flag in cli_args) + 2
+        for flag in sorted(cli_args):
+            spec = cli_args[flag]
+            default = spec.get('default', '-')
+            print(f'  --{flag:<{width}} {spec["help"]}  [default: {default}]')
+
+    def display_commands(self, sections=None):
+        print(f'xagents_b200 {__version__}')
+        print('\nUsage:')
+        print('\txagents <command> <agent> [options] [args]')
+        print('\nAvailable commands:')
+        for command, items in commands.items():
+            print(f'\t{command:<10} {items[2]}')
+        print()
+        print('Use xagents <command> to see more info about a command')
+        print('Use xagents <command> <agent> to see more info about command + agent')
+        for title, cli_args in (sections or {}).items():
+            self.display_section(title, cli_args)
+
+    @staticmethod
+    def add_args(cli_args, parser):
+        for arg, options in cli_args.items():
+            if options.get('action'):
+                parser.add_argument(f'--{arg}', help=options.get('help'), default=options.get('default'),
+                                    action=options['action'])
+            else:
+                parser.add_argument(f'--{arg}', help=options.get('help'), default=options.get('default'),
+                                    type=options.get('type'), required=options.get('required'), nargs=options.get('nargs'))
+
+    def maybe_create_agent(self, argv):
+        to_display = {}
+        if len(argv) == 0:
+            self.display_commands()
+            return
+        command = argv[0]
+        to_display.update(non_agent_args)
+        to_display.update(agent_args)
+        assert command in commands, f'Invalid command `{command}`'
+        to_display.update(commands[command][0])
+        if len(argv) == 1:
+            self.display_commands({command: to_display})
+            return
+        agent_id = argv[1]
+        assert agent_id in agents, f'Invalid agent `{agent_id}`'
+        to_display.update(agents[agent_id]['module'].cli_args)
+        if len(argv) == 2:
+            self.display_commands({f'{command} {agent_id}': to_display})
+            return
+        self.command, self.agent_id = command, agent_id
+
+    def parse_known_args(self, argv):
+        general_parser, agent_parser, command_parser = (argparse.ArgumentParser(add_help=False) for _ in range(3))
+        self.add_args(agent_args, agent_parser)
+        self.add_args(agents[self.agent_id]['module'].cli_args, agent_parser)
+        self.add_args(commands[self.command][0], command_parser)
+        self.add_args(non_agent_args, general_parser)
+        non_agent_known, extra1 = general_parser.parse_known_args(argv)
+        agent_known, extra2 = agent_parser.parse_known_args(argv)
+        command_known, extra3 = command_parser.parse_known_args(argv)
+        unknown_flags = [flag for flag in set(extra1) & set(extra2) & set(extra3)
+                         if flag not in (self.command, self.agent_id) and '--' in flag]
+        if unknown_flags:
+            warnings.warn(f'Got unknown flags {unknown_flags}')
+        if self.command == 'train':
+            assert command_known.target_reward or command_known.max_steps, 'train requires --target-reward or --max-steps'
+        return agent_known, non_agent_known, command_known
+
+    def execute(self, argv):
+        self.maybe_create_agent(argv)
+        if not self.agent_id:
+            return
+        agent_known, non_agent_known, command_known = self.parse_known_args(argv)
+        self.agent = create_agent(self.agent_id, vars(agent_known), vars(non_agent_known))
+        getattr(self.agent, commands[self.command][1])(**vars(command_known))
+
+
+def execute(argv=None):
+    argv = argv or sys.argv[1:]
+    Executor().execute(argv)
+
+
+if __name__ == '__main__':
+    execute()
