@@ -6,6 +6,7 @@ from .cfg import CfgNetwork, ModelReader
 from .models import AsCodedConv1dCNN, KerasModel, NatureCNN, TorchModel, adapt
 from .ppo import PPO
 from .tc_cnn import NatureCnnTc
+from .trpo import TRPO
 
-__all__ = ['A2C', 'PPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'NatureCnnTc', 'AsCodedConv1dCNN', 'adapt',
+__all__ = ['A2C', 'PPO', 'TRPO', 'BaseAgent', 'OnPolicy', 'EnvMajorView', 'TorchModel', 'KerasModel', 'NatureCNN', 'NatureCnnTc', 'AsCodedConv1dCNN', 'adapt',
            'ModelReader', 'CfgNetwork']

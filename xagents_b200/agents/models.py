@@ -22,8 +22,10 @@ from .. import ops
 
 class TorchModel:
     def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
-                 comm=None, tensor_core_inference=False, graph_inference=True):
+                 comm=None, tensor_core_inference=False, graph_inference=True, role='actor_critic'):
+        assert role in ('actor_critic', 'actor', 'critic'), f'unknown model role `{role}`'
         self.module = module
+        self.role = role                                          # 'actor' / 'critic': TRPO's separate single-output networks
         self.output_is_softmax = output_is_softmax
         self.img_inputs = img_inputs
         self.lr, self.beta1, self.beta2, self.epsilon = lr, beta1, beta2, epsilon
@@ -67,25 +69,35 @@ class TorchModel:
                 a, c = self._tc_forward.graphed(states.shape[0])(states)
                 return a.clone(), c.clone()
             return self._tc_forward(states)
+        x = self.scaled(states)
+        with torch.set_grad_enabled(training):
+            out = self.module(x)
+        if self.role == 'actor_critic':
+            actor, critic = out
+        else:
+            out = out[0] if isinstance(out, (tuple, list)) else out
+            actor, critic = (out, None) if self.role == 'actor' else (None, out)
+        if critic is not None:
+            critic = critic.reshape(-1)                           # tf.squeeze, a2c/agent.py:84
+        self._outputs = (actor, critic) if training else None
+        return (None if actor is None else actor.detach().contiguous(),
+                None if critic is None else critic.detach().contiguous())
+
+    def scaled(self, states):
+        """The network's input for a batch of stored observations: fp32, images divided by 255 (base.py:505-506)."""
         x = states
         if getattr(self.module, 'takes_uint8', False) and x.dtype in (torch.uint8, torch.bfloat16):
-            pass                                                  # the tensor-core network scales inside its first kernel
-        else:
-            scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
-            if x.dtype != torch.float32:
-                x = x.float()
-            if scale:
-                x = x / 255.0                                     # base.py:505-506
-        with torch.set_grad_enabled(training):
-            actor, critic = self.module(x)
-        critic = critic.reshape(-1)                               # tf.squeeze, a2c/agent.py:84
-        self._outputs = (actor, critic) if training else None
-        return actor.detach().contiguous(), critic.detach().contiguous()
+            return x                                              # the tensor-core network scales inside its first kernel
+        scale = self.img_inputs if self.img_inputs is not None else (x.dtype == torch.uint8)
+        if x.dtype != torch.float32:
+            x = x.float()
+        return x / 255.0 if scale else x
 
     def backward_and_step(self, d_actor, d_values, grad_norm=None):
         actor, critic = self._outputs
         self.flat_grad.zero_()
-        torch.autograd.backward([actor, critic], [d_actor.view_as(actor), d_values.view_as(critic)])
+        pairs = [(o, g) for o, g in ((actor, d_actor), (critic, d_values)) if o is not None]
+        torch.autograd.backward([o for o, _ in pairs], [g.view_as(o) for o, g in pairs])
         self._outputs = None
         scale = 1.0
         if self.comm is not None and self.comm.world_size > 1:

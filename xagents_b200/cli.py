@@ -1,4 +1,4 @@
-"""`xagents train <a2c|ppo> ...` on the device path: the reference's command line for the two on-policy agents this
+"""`xagents train <a2c|ppo|trpo> ...` on the device path: the reference's command line for the on-policy agents this
 package mirrors (xagents/cli.py:13-241, xagents/utils/cli.py, xagents/{a2c,ppo}/cli.py) and its factory
 (`create_model(s)` / `create_agent`, xagents/utils/common.py:430-494, 568-624).
 
@@ -18,7 +18,7 @@ import warnings
 from pathlib import Path
 
 from . import __version__, envs as _envs
-from .agents import A2C, PPO
+from .agents import A2C, PPO, TRPO
 from .agents.cfg import ModelReader
 
 _MODELS = Path(__file__).parent / 'agents' / 'models'
@@ -86,12 +86,33 @@ ppo_args.update({
     'n-steps': _flag('Transition steps', int, 128),
 })
 
+trpo_args = dict(ppo_args)
+trpo_args.update({
+    'actor-model': _flag('Path to actor model .cfg file'),
+    'critic-model': _flag('Path to critic model .cfg file'),
+    'max-kl': _flag('Maximum KL divergence of an actor update', float, 1e-3),
+    'cg-iterations': _flag('Conjugate-gradient iterations per train step', int, 10),
+    'cg-residual-tolerance': _flag('Conjugate-gradient residual tolerance', float, 1e-10),
+    'cg-damping': _flag('Damping added to the Fisher-vector product', float, 1e-3),
+    'actor-iterations': _flag('Line-search iterations per train step', int, 10),
+    'critic-iterations': _flag('Critic optimisation passes per train step', int, 3),
+    'fvp-n-steps': _flag('Use every n-th state for Fisher-vector products', int, 5),
+    'entropy-coef': _flag('Entropy coefficient of the loss', float, 0),
+    'lam': _flag('GAE-Lambda for advantage estimation', float, 1.0),
+    'n-steps': _flag('Transition steps', int, 512),
+})
+del trpo_args['model']
 
-def _default_models():
+
+def _default_models(role):
+    """Default `.cfg` files by network type, split like register_models (common.py:312-343): files naming both `actor`
+    and `critic` are single-model defaults, the others belong to the role they name."""
     groups = {'cnn': [], 'ann': []}
     for cfg in sorted(_MODELS.iterdir()):
+        has = {'actor': 'actor' in cfg.name, 'critic': 'critic' in cfg.name}
+        mine = (has['actor'] and has['critic']) if role == 'model' else (has[role.split('_')[0]] and sum(has.values()) == 1)
         for kind in groups:
-            if cfg.suffix == '.cfg' and kind in cfg.name:
+            if cfg.suffix == '.cfg' and kind in cfg.name and mine:
                 groups[kind].append(cfg.as_posix())
     return groups
 
@@ -99,9 +120,11 @@ def _default_models():
 # xagents.agents / xagents.commands (xagents/__init__.py:18-40), restricted to what this package mirrors
 agents = {
     'a2c': {'module': types.SimpleNamespace(cli_args=a2c_args, __file__=str(_MODELS.parent / 'a2c.py')), 'agent': A2C,
-            'model': _default_models()},
+            'model': _default_models('model')},
     'ppo': {'module': types.SimpleNamespace(cli_args=ppo_args, __file__=str(_MODELS.parent / 'ppo.py')), 'agent': PPO,
-            'model': _default_models()},
+            'model': _default_models('model')},
+    'trpo': {'module': types.SimpleNamespace(cli_args=trpo_args, __file__=str(_MODELS.parent / 'trpo.py')), 'agent': TRPO,
+             'actor_model': _default_models('actor_model'), 'critic_model': _default_models('critic_model')},
 }
 commands = {'train': (train_args, 'fit', 'Train given an agent and environment')}
 
@@ -124,9 +147,10 @@ def create_model(env, agent_id, model_type, optimizer_kwargs=None, seed=None, mo
         units.append(1)
     elif 'critic' in name:
         units[0] = 1
+    role = {'model': 'actor_critic', 'actor_model': 'actor', 'critic_model': 'critic'}[model_type]
     reader = ModelReader(model_cfg, units, env.observation_space.shape, optimizer_kwargs or {}, seed, conv_dims=conv_dims,
-                         tensor_core_dense=tensor_core_dense)
-    return reader.build_adapter(device)
+                         tensor_core_dense=tensor_core_dense and role != 'actor')
+    return reader.build_adapter(device, role=role)
 
 
 def create_models(options, env, agent_id, **kwargs):
