@@ -227,6 +227,28 @@ def test_command_line_errors_and_help(capsys):
     assert any('--no-such-flag' in str(w.message) for w in caught)
 
 
+def test_trpo_flags_and_default_models():
+    """xagents/trpo/cli.py: PPO's flags plus TRPO's, `model` removed, different defaults for entropy-coef / lam / n-steps."""
+    ex = cli.Executor()
+    ex.command, ex.agent_id = 'train', 'trpo'
+    agent, _, _ = ex.parse_known_args(['train', 'trpo', '--env', 'CartPole-v1', '--max-steps', '10'])
+    a = vars(agent)
+    assert 'model' not in a and a['actor_model'] is None and a['critic_model'] is None
+    assert (a['max_kl'], a['cg_iterations'], a['cg_residual_tolerance'], a['cg_damping'], a['actor_iterations'],
+            a['critic_iterations'], a['fvp_n_steps'], a['entropy_coef'], a['lam'], a['n_steps']) == \
+        (1e-3, 10, 1e-10, 1e-3, 10, 3, 5, 0, 1.0, 512)
+    assert (a['ppo_epochs'], a['mini_batches'], a['clip_norm'], a['grad_norm']) == (4, 4, 0.1, 0.5)
+    assert cli.ppo_args['lam']['default'] == 0.95 and 'model' in cli.ppo_args          # the copies are independent
+    reg = cli.agents['trpo']
+    assert 'model' not in reg
+    assert [os.path.basename(p) for p in reg['actor_model']['ann'] + reg['actor_model']['cnn']] == ['ann-actor.cfg', 'cnn-actor.cfg']
+    assert [os.path.basename(p) for p in reg['critic_model']['ann'] + reg['critic_model']['cnn']] == ['ann-critic.cfg', 'cnn-critic.cfg']
+    actor = ModelReader(reg['actor_model']['cnn'][0], [6], (84, 84, 4)).build_model()
+    critic = ModelReader(reg['critic_model']['ann'][0], [1], (4,)).build_model()
+    assert actor(torch.rand(2, 84, 84, 4)).shape == (2, 6) and critic(torch.rand(3, 4)).shape == (3, 1)
+    assert sum(p.numel() for p in actor.parameters()) == 28224 * 128 + 128 + 128 * 6 + 6
+
+
 def test_registry_shape():
     """xagents.agents[id] keeps its keys (xagents/__init__.py:18-27; register_models, common.py:312-343)."""
     from xagents_b200.agents import A2C, PPO
