@@ -264,3 +264,32 @@ def test_create_agent_fails_loudly_without_a_gpu():
     """No CPU fallback: building the agent needs the device."""
     with pytest.raises((RuntimeError, AssertionError)):
         cli.execute(['train', 'ppo', '--env', 'CartPole-v1', '--n-envs', '2', '--max-steps', '10', '--quiet'])
+
+
+def test_replay_buffer_handles_and_acer_flags():
+    """xagents/utils/buffers.py:8-60 assertions; create_buffers' as_total split (common.py:497-565); xagents/acer/cli.py."""
+    from xagents_b200.buffers import BaseBuffer, ReplayBuffer1, create_buffers
+    for kwargs, message in ((dict(size=0), 'Buffer size should be > 0'), (dict(size=4, initial_size=0), 'Buffer initial size should be > 0'),
+                            (dict(size=4, batch_size=0), 'Buffer batch size should be > 0'),
+                            (dict(size=4, batch_size=5), 'should be <= size'), (dict(size=4, initial_size=5, batch_size=1), 'exceeds max size')):
+        with pytest.raises(AssertionError, match=message):
+            BaseBuffer(**kwargs)
+    with pytest.raises(NotImplementedError):
+        BaseBuffer(4, batch_size=1).get_sample()
+    made = create_buffers('acer', 10000, 32, 16, None)
+    assert len(made) == 16 and all(isinstance(b, ReplayBuffer1) for b in made)
+    assert (made[0].size, made[0].initial_size, made[0].batch_size, made[0].current_size) == (625, 625, 1, 0)
+    assert create_buffers('acer', 100, 32, 4, 20, as_total=False)[0].initial_size == 20
+    ex = cli.Executor()
+    ex.command, ex.agent_id = 'train', 'acer'
+    agent, general, _ = ex.parse_known_args(['train', 'acer', '--env', 'x', '--max-steps', '10'])
+    a, g = vars(agent), vars(general)
+    assert (a['ema_alpha'], a['replay_ratio'], a['epsilon'], a['importance_c'], a['delta'], a['trust_region'], a['n_steps'],
+            a['grad_norm'], a['entropy_coef']) == (0.99, 4, 1e-6, 10.0, 1, None, 20, 10, 0.01)
+    assert (g['buffer_max_size'], g['buffer_initial_size'], g['buffer_batch_size']) == (10000, None, 32)
+    ex.agent_id = 'ppo'
+    _, general, _ = ex.parse_known_args(['train', 'ppo', '--env', 'x', '--max-steps', '10'])
+    assert 'buffer_max_size' not in vars(general)                   # buffer flags only for agents that own a buffer
+    net = ModelReader(cli.agents['acer']['model']['cnn'][0], [6, 6], (84, 84, 4), conv_dims=2).build_model()
+    probs, q = net(torch.rand(2, 84, 84, 4))
+    assert net.output_is_softmax and probs.shape == q.shape == (2, 6) and torch.allclose(probs.sum(-1), torch.ones(2), atol=1e-6)

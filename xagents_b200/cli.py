@@ -1,4 +1,4 @@
-"""`xagents train <a2c|ppo|trpo> ...` on the device path: the reference's command line for the on-policy agents this
+"""`xagents train <a2c|acer|ppo|trpo> ...` on the device path: the reference's command line for the on-policy agents this
 package mirrors (xagents/cli.py:13-241, xagents/utils/cli.py, xagents/{a2c,ppo}/cli.py) and its factory
 (`create_model(s)` / `create_agent`, xagents/utils/common.py:430-494, 568-624).
 
@@ -6,7 +6,8 @@ package mirrors (xagents/cli.py:13-241, xagents/utils/cli.py, xagents/{a2c,ppo}/
     python -m xagents_b200 train a2c --env SyntheticAtari-v0 --n-envs 16 --max-steps 4000 --conv-dims 2
 
 Flags, defaults, the agent/non-agent/command split and the assertion messages are the reference's.  `play`, `tune`
-and the off-policy agents are outside the hot path (SURVEY.md §8) and are refused as invalid commands / agents;
+and the off-policy agents (dqn, ddpg, td3) are outside the hot path and are refused as invalid commands /
+agents;
 checkpoint, history and wandb flags are accepted by the parser and refused by the agent (agents/base.py).
 Three flags are new: `--conv-dims` (1 = the `.cfg` as the reference's reader builds it, Conv1D; 2 = the documented
 Conv2D network), `--tensor-core-dense` (Dense layers on the tcgen05 GEMM) and `--device`.
@@ -17,8 +18,8 @@ import types
 import warnings
 from pathlib import Path
 
-from . import __version__, envs as _envs
-from .agents import A2C, PPO, TRPO
+from . import __version__, buffers as _buffers, envs as _envs
+from .agents import A2C, ACER, PPO, TRPO
 from .agents.cfg import ModelReader
 
 _MODELS = Path(__file__).parent / 'agents' / 'models'
@@ -45,6 +46,12 @@ non_agent_args = {
     'conv-dims': _flag('1: convolutional sections as the reference reader builds them (Conv1D); 2: Conv2D', int, 1),
     'tensor-core-dense': _flag('Dense layers on the tcgen05 GEMM', action='store_true'),
     'device': _flag('CUDA device of this process', default='cuda:0'),
+}
+
+off_policy_args = {
+    'buffer-max-size': _flag('Maximum replay buffer size', int, 10000),
+    'buffer-initial-size': _flag('Replay buffer initial size', int),
+    'buffer-batch-size': _flag('Replay buffer batch size', int, 32),
 }
 
 agent_args = {
@@ -86,6 +93,18 @@ ppo_args.update({
     'n-steps': _flag('Transition steps', int, 128),
 })
 
+acer_args = dict(a2c_args)
+acer_args.update({
+    'ema-alpha': _flag('Decay of the averaged policy network', float, 0.99),
+    'replay-ratio': _flag('Mean of the Poisson number of replay updates per train step', int, 4),
+    'epsilon': _flag('Epsilon used in several calculations during the gradient update', float, 1e-6),
+    'importance-c': _flag('Importance weight truncation parameter', float, 10.0),
+    'delta': _flag('Delta parameter of the trust region update', float, 1),
+    'trust-region': _flag('If specified, trust region updates will be used', action='store_true'),
+    'n-steps': _flag('Transition steps', int, 20),
+    'grad-norm': _flag('Global-norm gradient clipping value', float, 10),
+})
+
 trpo_args = dict(ppo_args)
 trpo_args.update({
     'actor-model': _flag('Path to actor model .cfg file'),
@@ -104,11 +123,11 @@ trpo_args.update({
 del trpo_args['model']
 
 
-def _default_models(role):
+def _default_models(role, folder=_MODELS):
     """Default `.cfg` files by network type, split like register_models (common.py:312-343): files naming both `actor`
     and `critic` are single-model defaults, the others belong to the role they name."""
     groups = {'cnn': [], 'ann': []}
-    for cfg in sorted(_MODELS.iterdir()):
+    for cfg in sorted(folder.iterdir()):
         has = {'actor': 'actor' in cfg.name, 'critic': 'critic' in cfg.name}
         mine = (has['actor'] and has['critic']) if role == 'model' else (has[role.split('_')[0]] and sum(has.values()) == 1)
         for kind in groups:
@@ -121,6 +140,8 @@ def _default_models(role):
 agents = {
     'a2c': {'module': types.SimpleNamespace(cli_args=a2c_args, __file__=str(_MODELS.parent / 'a2c.py')), 'agent': A2C,
             'model': _default_models('model')},
+    'acer': {'module': types.SimpleNamespace(cli_args=acer_args, __file__=str(_MODELS.parent / 'acer.py')), 'agent': ACER,
+             'model': _default_models('model', _MODELS / 'acer')},
     'ppo': {'module': types.SimpleNamespace(cli_args=ppo_args, __file__=str(_MODELS.parent / 'ppo.py')), 'agent': PPO,
             'model': _default_models('model')},
     'trpo': {'module': types.SimpleNamespace(cli_args=trpo_args, __file__=str(_MODELS.parent / 'trpo.py')), 'agent': TRPO,
@@ -143,7 +164,9 @@ def create_model(env, agent_id, model_type, optimizer_kwargs=None, seed=None, mo
         model_cfg = None
     assert model_cfg, (f'You should specify `model_cfg`. No default {network_type.upper()} model found in\n{_MODELS}')
     name = Path(model_cfg).name
-    if 'actor' in name and 'critic' in name:
+    if agent_id == 'acer':                                         # policy head + one critic output per action
+        units.append(units[-1])
+    elif 'actor' in name and 'critic' in name:
         units.append(1)
     elif 'critic' in name:
         units[0] = 1
@@ -180,6 +203,10 @@ def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
     agent_kwargs.update(create_models(agent_kwargs, envs[0], agent_id, optimizer_kwargs=optimizer_kwargs,
                                       seed=agent_kwargs.get('seed'), conv_dims=non_agent_kwargs.get('conv_dims', 1),
                                       tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device))
+    if agent_id == 'acer':
+        agent_kwargs['buffers'] = _buffers.create_buffers(agent_id, non_agent_kwargs['buffer_max_size'],
+                                                          non_agent_kwargs['buffer_batch_size'], non_agent_kwargs['n_envs'],
+                                                          non_agent_kwargs['buffer_initial_size'])
     agent = agents[agent_id]['agent'](device=device, **agent_kwargs)
     if non_agent_kwargs.get('weights'):
         n_weights, n_models = len(non_agent_kwargs['weights']), len(agent.output_models)
@@ -247,6 +274,8 @@ class Executor:
         assert agent_id in agents, f'Invalid agent `{agent_id}`'
         to_display.update(agents[agent_id]['module'].cli_args)
         if len(argv) == 2:
+            if agent_id == 'acer':
+                to_display.update(off_policy_args)
             self.display_commands({f'{command} {agent_id}': to_display})
             return
         self.command, self.agent_id = command, agent_id
@@ -256,6 +285,8 @@ class Executor:
         self.add_args(agent_args, agent_parser)
         self.add_args(agents[self.agent_id]['module'].cli_args, agent_parser)
         self.add_args(commands[self.command][0], command_parser)
+        if self.agent_id == 'acer':
+            self.add_args(off_policy_args, general_parser)
         self.add_args(non_agent_args, general_parser)
         non_agent_known, extra1 = general_parser.parse_known_args(argv)
         agent_known, extra2 = agent_parser.parse_known_args(argv)
