@@ -38,7 +38,9 @@ class _StubMeta(type):
     def __getattr__(cls, name):
         if name.startswith('__'):
             raise AttributeError(name)
-        return _make_stub(f'{cls.__name__}.{name}')
+        value = _make_stub(f'{cls.__name__}.{name}')
+        type.__setattr__(cls, name, value)     # stable identity: `tf.keras.activations.softmax in activations` must work
+        return value
 
     def __call__(cls, *args, **kwargs):
         # decorator use (tf.function): hand the function back untouched
@@ -298,10 +300,10 @@ def _wrap(agent, name, sink):
     setattr(agent, name, recorder)
 
 
-def _build(xagents, kind, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, softmax=False, **kw):
+def _build(xagents, kind, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, softmax=False, box=False, **kw):
     rng = np.random.default_rng(seed)
     obs, rewards, dones, resets = _streams(rng, n_steps, n_envs, obs_shape, image, p_done)
-    space = Discrete(n_actions)
+    space = Box((n_actions,)) if box else Discrete(n_actions)      # Box: n_actions = action dimension k
     envs = [ReplayEnv(obs[i], rewards[i], dones[i], resets[i], space) for i in range(n_envs)]
     model = TinyModel(min(int(np.prod(obs_shape)), 24), n_actions, rng, softmax)
     cls = xagents.PPO if kind == 'ppo' else xagents.A2C
@@ -312,6 +314,7 @@ def _build(xagents, kind, seed, n_steps, n_envs, obs_shape, image, n_actions, p_
 def ppo_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, drift=0.05, **kw):
     for k in RECORD:
         RECORD[k].clear()
+    actor_kind = 'normal' if kw.get('box') else ('probs' if kw.get('softmax') else 'logits')
     agent, model = _build(xagents, 'ppo', seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw)
     rec = {k: [] for k in ('calculate_returns', 'get_batch', 'get_mini_batches', 'update_gradients')}
     for name in rec:
@@ -336,6 +339,7 @@ def ppo_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p
     model.drift = F32(0)
     next_values = np.squeeze(model(_f32(agent.get_states()) / F32(255.0) if image else _f32(agent.get_states()))[1])
     out = dict(
+        actor_kind=actor_kind,
         n_steps=n_steps, n_envs=n_envs, gamma=agent.gamma, lam=agent.lam, clip_norm=agent.clip_norm,
         entropy_coef=agent.entropy_coef, value_loss_coef=agent.value_loss_coef,
         advantage_epsilon=agent.advantage_epsilon, mini_batch_size=agent.mini_batch_size,
@@ -369,6 +373,7 @@ def ppo_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p
 def a2c_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw):
     for k in RECORD:
         RECORD[k].clear()
+    actor_kind = 'normal' if kw.get('box') else ('probs' if kw.get('softmax') else 'logits')
     agent, model = _build(xagents, 'a2c', seed, n_steps, n_envs, obs_shape, image, n_actions, p_done, **kw)
     rec = {k: [] for k in ('calculate_returns', 'np_train_step')}
     for name in rec:
@@ -391,7 +396,7 @@ def a2c_case(xagents, tag, seed, n_steps, n_envs, obs_shape, image, n_actions, p
     next_values = np.squeeze(model(x)[1])
     np.savez_compressed(
         os.path.join(HERE, f'{tag}.npz'),
-        n_steps=n_steps, n_envs=n_envs, gamma=agent.gamma, entropy_coef=agent.entropy_coef,
+        actor_kind=actor_kind, n_steps=n_steps, n_envs=n_envs, gamma=agent.gamma, entropy_coef=agent.entropy_coef,
         value_loss_coef=agent.value_loss_coef, steps_after=agent.steps,
         rewards=rewards, dones=dones, next_values=np.atleast_1d(next_values), returns=returns,
         flat_states=states, flat_returns=flat_returns, flat_actions=actions, flat_values=old_values,
@@ -444,10 +449,24 @@ def acer_case(xagents):
     print('acer_retrace:', np.asarray(out)[:4])
 
 
+def distribution_cases(xagents):
+    """The other two branches of A2C.get_distribution (a2c/agent.py:50-63) through the reference's own train steps:
+    MultivariateNormalDiag for Box action spaces (actions [N, k]) and Categorical(probs=) for softmax-output models."""
+    ppo_case(xagents, 'ppo_box', 15, n_steps=10, n_envs=4, obs_shape=(6,), image=False, n_actions=3, p_done=0.15,
+             mini_batches=4, ppo_epochs=2, box=True)
+    ppo_case(xagents, 'ppo_softmax', 16, n_steps=12, n_envs=6, obs_shape=(5,), image=False, n_actions=5, p_done=0.1,
+             mini_batches=3, ppo_epochs=2, softmax=True)
+    a2c_case(xagents, 'a2c_box', 23, n_steps=6, n_envs=5, obs_shape=(4,), image=False, n_actions=2, p_done=0.2, box=True)
+    a2c_case(xagents, 'a2c_softmax', 24, n_steps=7, n_envs=4, obs_shape=(4,), image=False, n_actions=3, p_done=0.2, softmax=True)
+
+
 def main():
     xagents = _import_reference()
     if '--acer-only' in sys.argv:
         return acer_case(xagents)
+    if '--distributions-only' in sys.argv:                         # added later: leaves the earlier fixtures untouched
+        return distribution_cases(xagents)
+    distribution_cases(xagents)
     acer_case(xagents)
     kat_case(xagents)
     # PPO, image observations (uint8-valued, 8x8x4), 6 actions: Atari-shaped in miniature

@@ -40,11 +40,30 @@ class NumpyModel:
         self.grads.append((d_actor.clone(), d_values.clone()))
 
 
+def _softmax_tiny(mg, in_features, n_actions, rng):
+    """TinyModel(softmax=True) outside the generator: its constructor looks the Keras softmax symbol up in the stubbed
+    tensorflow module, which only exists while make_golden.py runs; the arithmetic needs the flag alone."""
+    import sys
+    import types
+    had = 'tensorflow' in sys.modules
+    if not had:
+        sys.modules['tensorflow'] = types.SimpleNamespace(keras=types.SimpleNamespace(activations=types.SimpleNamespace(softmax='softmax')))
+    try:
+        return mg.TinyModel(in_features, n_actions, rng, softmax=True)
+    finally:
+        if not had:
+            del sys.modules['tensorflow']
+
+
 CASES = {
     'ppo_image': dict(seed=11, T=16, E=8, shape=(8, 8, 4), image=True, A=6, p=0.08, kw=dict(mini_batches=4, ppo_epochs=4), drift=0.05),
     'ppo_cartpole': dict(seed=12, T=128, E=16, shape=(4,), image=False, A=2, p=0.02, kw=dict(mini_batches=4, ppo_epochs=4), drift=0.05),
     'ppo_ragged': dict(seed=13, T=7, E=3, shape=(5,), image=False, A=3, p=0.3, kw=dict(mini_batches=4, ppo_epochs=2, clip_norm=0.02), drift=0.2),
     'ppo_single_env': dict(seed=14, T=9, E=1, shape=(6, 6, 1), image=True, A=4, p=0.2, kw=dict(mini_batches=3, ppo_epochs=2), drift=0.05),
+    'ppo_box': dict(seed=15, T=10, E=4, shape=(6,), image=False, A=3, p=0.15, kw=dict(mini_batches=4, ppo_epochs=2), drift=0.05, box=True),
+    'ppo_softmax': dict(seed=16, T=12, E=6, shape=(5,), image=False, A=5, p=0.1, kw=dict(mini_batches=3, ppo_epochs=2), drift=0.05, softmax=True),
+    'a2c_box': dict(seed=23, T=6, E=5, shape=(4,), image=False, A=2, p=0.2, kw={}, drift=0.05, box=True),
+    'a2c_softmax': dict(seed=24, T=7, E=4, shape=(4,), image=False, A=3, p=0.2, kw={}, drift=0.05, softmax=True),
     'a2c_image': dict(seed=21, T=5, E=16, shape=(8, 8, 4), image=True, A=6, p=0.1, kw={}, drift=0.05),
     'a2c_vector': dict(seed=22, T=12, E=5, shape=(4,), image=False, A=2, p=0.15, kw={}, drift=0.05),
 }
@@ -55,10 +74,12 @@ def build(case, cls):
     c = CASES[case]
     rng = np.random.default_rng(c['seed'])
     obs, rewards, dones, resets = mg._streams(rng, c['T'], c['E'], c['shape'], c['image'], c['p'])
-    space = mg.Discrete(c['A'])
+    space = mg.Box((c['A'],)) if c.get('box') else mg.Discrete(c['A'])
     envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], space) for i in range(c['E'])]
-    tiny = mg.TinyModel(min(int(np.prod(c['shape'])), 24), c['A'], rng)
+    in_features = min(int(np.prod(c['shape'])), 24)
+    tiny = _softmax_tiny(mg, in_features, c['A'], rng) if c.get('softmax') else mg.TinyModel(in_features, c['A'], rng)
     model = NumpyModel(tiny, c['image'])
+    model.output_is_softmax = bool(c.get('softmax'))
     agent = cls(envs, model, n_steps=c['T'], quiet=True, **c['kw'])
     return agent, model, tiny, c
 
@@ -70,15 +91,16 @@ def near(got, want, scale=None):
     assert np.abs(got - want).max() <= REL * max(s, 1e-30)
 
 
-@pytest.mark.parametrize('case', ['ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env'])
+@pytest.mark.parametrize('case', ['ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env', 'ppo_box', 'ppo_softmax'])
 def test_ppo_train_step_matches_the_reference_run(golden, case):
     from xagents_b200.agents import PPO
     g = golden(case)
     agent, model, tiny, c = build(case, PPO)
     T, E = c['T'], c['E']
     tm = lambda flat: np.ascontiguousarray(np.asarray(flat).reshape(E, T).T)
-    golden_actions = tm(g['flat_actions'])
+    golden_actions = np.ascontiguousarray(np.swapaxes(g['flat_actions'].reshape((E, T) + ((c['A'],) if c.get('box') else ())), 0, 1))
     agent.action_source = lambda step, actor_out: golden_actions[step]
+    assert agent.actor_kind == ('normal' if c.get('box') else 'probs' if c.get('softmax') else 'logits')
     agent.permutation_source = lambda epoch: g['shuffles'][epoch]
     inner = agent.run_ppo_epochs
 
@@ -129,13 +151,14 @@ def test_ppo_get_mini_batches_contract(golden):
     assert len(mbs[4][0]) == 1                        # trailing short minibatch: 21 = 4*5 + 1
 
 
-@pytest.mark.parametrize('case', ['a2c_image', 'a2c_vector'])
+@pytest.mark.parametrize('case', ['a2c_image', 'a2c_vector', 'a2c_box', 'a2c_softmax'])
 def test_a2c_train_step_matches_the_reference_run(golden, case):
     from xagents_b200.agents import A2C
     g = golden(case)
     agent, model, tiny, c = build(case, A2C)
     T, E = c['T'], c['E']
-    golden_actions = np.ascontiguousarray(g['flat_actions'].reshape(E, T).T)
+    golden_actions = np.ascontiguousarray(np.swapaxes(g['flat_actions'].reshape((E, T) + ((c['A'],) if c.get('box') else ())), 0, 1))
+    assert agent.actor_kind == ('normal' if c.get('box') else 'probs' if c.get('softmax') else 'logits')
     agent.action_source = lambda step, actor_out: golden_actions[step]
     inner = agent.calculate_returns
 

@@ -33,7 +33,7 @@ def close(got, want, scale=None, rel=REL):
 
 
 # ---------------------------------------------------------------------------------------------- returns
-@pytest.mark.parametrize('case', ['kat_returns', 'ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env'])
+@pytest.mark.parametrize('case', ['kat_returns', 'ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env', 'ppo_box', 'ppo_softmax'])
 def test_gae_sequential_bit_exact_vs_reference_golden(golden, case):
     g = golden(case)
     if case == 'kat_returns':
@@ -52,7 +52,7 @@ def test_gae_sequential_bit_exact_vs_reference_golden(golden, case):
         close(got, want)
 
 
-@pytest.mark.parametrize('case', ['kat_returns', 'a2c_image', 'a2c_vector'])
+@pytest.mark.parametrize('case', ['kat_returns', 'a2c_image', 'a2c_vector', 'a2c_box', 'a2c_softmax'])
 def test_nstep_sequential_bit_exact_vs_reference_golden(golden, case):
     g = golden(case)
     want = g['a2c_returns'] if case == 'kat_returns' else g['returns']
@@ -224,6 +224,82 @@ def test_ppo_loss_vs_reference_golden(golden, case):
                                         advantages=cu(ref_adv), **hp)
         assert abs(sc2.cpu().numpy()[0] - ref_loss) <= REL * scale
         close(da2, dl)
+
+
+def _normal_grads_fp64(actor, critic, actions, old_lp, old_v, ret, adv, clip, ec, vc, ppo=True):
+    """d loss / d(loc, V) for the MultivariateNormalDiag branch by fp64 autograd with TF's tie rules (oracle/torch_ref.py
+    conventions); the closed forms of oracle/hotpath.py cover the two Categorical branches."""
+    from oracle.torch_ref import _tf_clip, _tf_max
+    t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64)
+    loc, v = t(actor).clone().requires_grad_(True), t(critic).clone().requires_grad_(True)
+    a, old_v, ret = t(actions).reshape(loc.shape), t(old_v), t(ret)
+    k = loc.shape[-1]
+    logp = -0.5 * ((a - loc) ** 2).sum(-1) - 0.5 * k * np.log(2 * np.pi)
+    entropy = torch.full_like(logp, 0.5 * k * (1 + np.log(2 * np.pi))).mean()
+    if ppo:
+        old_lp, adv = t(old_lp), t(adv)
+        clipped = old_v + _tf_clip(v - old_v, -clip, clip)
+        vl = 0.5 * _tf_max((v - ret) ** 2, (clipped - ret) ** 2).mean()
+        ratio = torch.exp(logp - old_lp)
+        pg = _tf_max(-adv * ratio, -adv * _tf_clip(ratio, 1 - clip, 1 + clip)).mean()
+    else:
+        vl = ((v - ret) ** 2).mean()
+        pg = -((ret - old_v) * logp).mean()
+    (pg - entropy * ec + vl * vc).backward()
+    return loc.grad.numpy(), v.grad.numpy()
+
+
+@pytest.mark.parametrize('case', ['ppo_box', 'ppo_softmax'])
+def test_ppo_loss_other_distribution_branches_vs_reference_golden(golden, case):
+    """MultivariateNormalDiag (Box actions [N, k]) and Categorical(probs=) (softmax-output model): the other two
+    branches of A2C.get_distribution (a2c/agent.py:50-63), fixtures from the reference's own PPO.train_step."""
+    g = golden(case)
+    kind = str(g['actor_kind'])
+    assert kind == {'ppo_box': 'normal', 'ppo_softmax': 'probs'}[case]
+    hp = dict(clip_norm=float(g['clip_norm']), entropy_coef=float(g['entropy_coef']),
+              value_loss_coef=float(g['value_loss_coef']), advantage_epsilon=float(g['advantage_epsilon']))
+    for k, ref_loss in enumerate(g['losses']):
+        actor, critic = g[f'mb{k}_actor'], g[f'mb{k}_critic'].reshape(-1)
+        actions = g[f'mb{k}_actions'].reshape(actor.shape) if kind == 'normal' else g[f'mb{k}_actions'].reshape(-1)
+        old_lp, old_v, ret = (g[f'mb{k}_{name}'].reshape(-1) for name in ('old_log_probs', 'old_values', 'returns'))
+        sc, d_actor, d_values, adv = ops.ppo_loss(cu(actor), cu(critic), cu(actions), cu(old_lp), cu(old_v), cu(ret),
+                                                 actor_kind=kind, return_advantages=True, **hp)
+        sc = sc.cpu().numpy()
+        _, ref_ent, ref_vl, ref_pg = g['means'][k]
+        scale = max(abs(float(ref_loss)), abs(float(ref_ent)) * hp['entropy_coef'])
+        assert abs(sc[0] - ref_loss) <= REL * scale, (k, sc, ref_loss)
+        assert abs(sc[1] - ref_pg) <= REL * scale and abs(sc[2] - 0.5 * ref_vl) <= REL * scale
+        assert abs(sc[3] - ref_ent) <= REL * max(scale, abs(float(ref_ent)))
+        ref_adv = g[f'mb{k}_advantages'].reshape(-1)
+        close(adv, ref_adv)
+        if kind == 'probs':
+            dl, dv = oracle.ppo_loss_grads(actor, critic, actions, old_v, ret, old_lp, ref_adv, hp['clip_norm'],
+                                           hp['entropy_coef'], hp['value_loss_coef'], is_probs=True)
+        else:
+            dl, dv = _normal_grads_fp64(actor, critic, actions, old_lp, old_v, ret, ref_adv, hp['clip_norm'],
+                                        hp['entropy_coef'], hp['value_loss_coef'])
+        close(d_actor, dl)
+        close(d_values, dv)
+
+
+@pytest.mark.parametrize('case', ['a2c_box', 'a2c_softmax'])
+def test_a2c_loss_other_distribution_branches_vs_reference_golden(golden, case):
+    g = golden(case)
+    kind = str(g['actor_kind'])
+    actor, critic = g['actor'], g['critic'].reshape(-1)
+    actions = g['flat_actions'].reshape(actor.shape) if kind == 'normal' else g['flat_actions'].reshape(-1)
+    old_v, ret = g['flat_values'].reshape(-1), g['flat_returns'].reshape(-1)
+    ec, vc = float(g['entropy_coef']), float(g['value_loss_coef'])
+    sc, d_actor, d_values = ops.a2c_loss(cu(actor), cu(critic), cu(actions), cu(old_v), cu(ret), entropy_coef=ec,
+                                         value_loss_coef=vc, actor_kind=kind)
+    ref = float(g['loss'][0])
+    assert abs(sc.cpu().numpy()[0] - ref) <= REL * abs(ref)
+    if kind == 'probs':
+        dl, dv = oracle.a2c_loss_grads(actor, critic, actions, old_v, ret, ec, vc, is_probs=True)
+    else:
+        dl, dv = _normal_grads_fp64(actor, critic, actions, None, old_v, ret, None, 0.0, ec, vc, ppo=False)
+    close(d_actor, dl)
+    close(d_values, dv)
 
 
 @pytest.mark.parametrize('case', ['a2c_image', 'a2c_vector'])

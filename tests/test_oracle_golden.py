@@ -4,8 +4,20 @@ import pytest
 
 import oracle
 
-PPO_CASES = ['ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env']
-A2C_CASES = ['a2c_image', 'a2c_vector']
+PPO_CASES = ['ppo_image', 'ppo_cartpole', 'ppo_ragged', 'ppo_single_env', 'ppo_box', 'ppo_softmax']
+A2C_CASES = ['a2c_image', 'a2c_vector', 'a2c_box', 'a2c_softmax']
+
+
+def actor_kind(g):
+    """Which branch of A2C.get_distribution produced the fixture (a2c/agent.py:50-63); older fixtures are all logits."""
+    return str(g['actor_kind']) if 'actor_kind' in g.files else 'logits'
+
+
+def logp_entropy(g, actor, actions):
+    kind = actor_kind(g)
+    if kind == 'normal':
+        return oracle.diag_normal_logp_entropy(actor, actions.reshape(actor.shape))[:2]
+    return oracle.categorical_logp_entropy(actor, actions.reshape(-1), kind == 'probs')[:2]
 
 
 def test_kat_returns_bit_exact(golden):
@@ -48,11 +60,11 @@ def test_ppo_minibatches_and_loss(golden, case):
     assert len(mbs) == len(g['losses']) == int(g['ppo_epochs']) * -(-N // B)
     for i, mb in enumerate(mbs):
         assert np.array_equal(mb[0], g[f'mb{i}_states'])
-        r, v, lp, a = mb[2].reshape(-1), mb[3].reshape(-1), mb[4].reshape(-1), mb[1].reshape(-1)
+        r, v, lp, a = mb[2].reshape(-1), mb[3].reshape(-1), mb[4].reshape(-1), mb[1]
         assert np.array_equal(r, g[f'mb{i}_returns'].reshape(-1))
         adv = oracle.normalize_advantages(r, v, float(g['advantage_epsilon']))
         np.testing.assert_allclose(adv, g[f'mb{i}_advantages'].reshape(-1), rtol=1e-6, atol=1e-6)
-        logp, ent, _ = oracle.categorical_logp_entropy(g[f'mb{i}_actor'], a)
+        logp, ent = logp_entropy(g, g[f'mb{i}_actor'], a)
         sc = oracle.ppo_loss(logp, g[f'mb{i}_critic'].reshape(-1), ent, v, r, lp, adv, float(g['clip_norm']),
                              float(g['entropy_coef']), float(g['value_loss_coef']))
         ref_loss = g['losses'][i]
@@ -70,8 +82,7 @@ def test_a2c_path(golden, case):
     got = oracle.nstep_returns(g['rewards'], g['dones'], g['next_values'], float(g['gamma']))
     assert np.array_equal(got, g['returns'])
     assert np.array_equal(oracle.concat_step_batches(got)[0].reshape(-1), g['flat_returns'].reshape(-1))
-    a = g['flat_actions'].reshape(-1)
-    logp, ent, _ = oracle.categorical_logp_entropy(g['actor'], a)
+    logp, ent = logp_entropy(g, g['actor'], g['flat_actions'])
     sc = oracle.a2c_loss(logp, g['critic'].reshape(-1), ent, g['flat_values'].reshape(-1),
                          g['flat_returns'].reshape(-1), float(g['entropy_coef']), float(g['value_loss_coef']))
     assert abs(sc['loss'] - g['loss'][0]) <= 1e-5 * abs(g['loss'][0])
