@@ -262,8 +262,9 @@ def test_ppo_loss_other_distribution_branches_vs_reference_golden(golden, case):
         actor, critic = g[f'mb{k}_actor'], g[f'mb{k}_critic'].reshape(-1)
         actions = g[f'mb{k}_actions'].reshape(actor.shape) if kind == 'normal' else g[f'mb{k}_actions'].reshape(-1)
         old_lp, old_v, ret = (g[f'mb{k}_{name}'].reshape(-1) for name in ('old_log_probs', 'old_values', 'returns'))
+        mom = ops.adv_moments(cu(ret), cu(old_v), None, [0, len(ret)])
         sc, d_actor, d_values, adv = ops.ppo_loss(cu(actor), cu(critic), cu(actions), cu(old_lp), cu(old_v), cu(ret),
-                                                 actor_kind=kind, return_advantages=True, **hp)
+                                                 moments=mom[0], actor_kind=kind, return_advantages=True, **hp)
         sc = sc.cpu().numpy()
         _, ref_ent, ref_vl, ref_pg = g['means'][k]
         scale = max(abs(float(ref_loss)), abs(float(ref_ent)) * hp['entropy_coef'])
