@@ -275,3 +275,29 @@ def test_cli_train_a2c_on_synthetic_atari_frames_with_both_cfg_readings():
         assert agent.n_steps == 5 and agent.steps == 400 and agent.net.n_params == n_params and agent.net.step == 5
         assert agent.ro_states.dtype == torch.uint8 and tuple(agent.ro_states.shape) == (5, 16, 84, 84, 4)
         assert torch.isfinite(agent.net.flat_param).all()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs of one box')
+def test_cli_train_shards_the_environments_over_two_gpus():
+    """torchrun x2: 16 CartPole environments, 8 per rank, NCCL gradient all-reduce per minibatch and job-wide advantage
+    moments.  Every rank must end with bit-identical weights after the same number of optimiser steps."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    root = os.path.dirname(HERE)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(root, 'scripts', 'sharded_train_check.py'), 'train', 'ppo', '--env', 'CartPole-v1',
+           '--n-envs', '16', '--max-steps', '40960', '--seed', '1', '--quiet']
+    done = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=280)
+    assert done.returncode == 0, done.stderr[-3000:]
+    line = [ln for ln in done.stdout.splitlines() if ln.startswith('{')][-1]
+    out = json.loads(line)
+    assert out['world_size'] == 2 and out['n_envs_per_rank'] == 8 and out['job_steps'] == 40960
+    assert out['optimizer_steps'] == (40960 // 2048) * 16
+    assert out['weights_identical_across_ranks'] and out['weights_finite']
+    assert out['mean_reward_last_episodes'] > 25.0

@@ -186,10 +186,18 @@ class BaseAgent:
             self.done_envs = 0
 
     def training_done(self):
-        if self.target_reward is not None and self.mean_reward >= self.target_reward:
-            self.display_message(f'Reward achieved in {self.steps} steps')
+        mean_reward, steps = self.mean_reward, self.steps
+        comm = getattr(self, 'comm', None)
+        if comm is not None and comm.world_size > 1:
+            # sharded environments: every rank must take the same decision at the same train step (the updates contain
+            # collectives), so the stop conditions read the job-wide episode mean and the job-wide step count
+            total, count, steps = comm.sum_over_ranks([float(np.sum(self.total_rewards)), len(self.total_rewards), self.steps])
+            mean_reward = total / count if count else -float('inf')
+            steps = int(steps)
+        if self.target_reward is not None and mean_reward >= self.target_reward:
+            self.display_message(f'Reward achieved in {steps} steps')
             return True
-        if self.max_steps and self.steps >= self.max_steps:
+        if self.max_steps and steps >= self.max_steps:
             self.display_message(f'Maximum steps exceeded')
             return True
         return False

@@ -187,27 +187,63 @@ def create_models(options, env, agent_id, **kwargs):
     return models
 
 
+def _rank_device(local_rank):
+    return f'cuda:{local_rank}'
+
+
 def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
-    """Environments + model + agent from parsed flags (common.py:568-624)."""
+    """Environments + model + agent from parsed flags (common.py:568-624).
+
+    Under `torchrun` (WORLD_SIZE > 1) the job shards its environments: `--n-envs` is the job-wide count, rank g builds
+    and steps only its slice on `cuda:LOCAL_RANK`, the networks start from rank 0's weights and every update averages
+    gradients over the ranks (`dist.ShardComm`, collectives C1 / C2 of SURVEY.md 8e).  The reference is single-process;
+    there is nothing to mirror, only to keep: the flags mean what they meant."""
     import torch
+    from . import dist as xdist
     assert agent_id in agents, f'Invalid agent `{agent_id}`'
     agent_kwargs = dict(agent_kwargs)
     if trial is not None:
         agent_kwargs['trial'] = trial
     device = non_agent_kwargs.get('device') or 'cuda:0'
-    envs = _envs.create_envs(non_agent_kwargs['env'], non_agent_kwargs['n_envs'], non_agent_kwargs['preprocess'],
+    rank, local_rank, world = xdist.init_from_env()
+    comm, n_envs = None, non_agent_kwargs['n_envs']
+    if world > 1:
+        assert agent_id in ('a2c', 'ppo'), (f'`{agent_id}` cannot shard its environments: its updates are not a fixed '
+                                            f'sequence of gradient steps (line search / random replay counts)')
+        assert n_envs % world == 0, f'--n-envs {n_envs} must be a multiple of the {world} ranks'
+        device = _rank_device(local_rank)
+        comm = xdist.ShardComm(device=device)
+        n_envs //= world
+        if rank > 0:
+            agent_kwargs['quiet'] = True
+        if agent_kwargs.get('seed') is not None:                   # different episodes on every rank, same model seed
+            non_agent_kwargs = dict(non_agent_kwargs, env_seed=agent_kwargs['seed'] + 7919 * rank)
+    envs = _envs.create_envs(non_agent_kwargs['env'], n_envs, non_agent_kwargs['preprocess'],
                              max_frame=non_agent_kwargs.get('max_frame'))
     agent_kwargs['envs'] = envs
     optimizer_kwargs = {'learning_rate': non_agent_kwargs['lr'], 'beta_1': non_agent_kwargs['beta1'],
                         'beta_2': non_agent_kwargs['beta2'], 'epsilon': non_agent_kwargs['opt_epsilon']}
-    agent_kwargs.update(create_models(agent_kwargs, envs[0], agent_id, optimizer_kwargs=optimizer_kwargs,
-                                      seed=agent_kwargs.get('seed'), conv_dims=non_agent_kwargs.get('conv_dims', 1),
-                                      tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device))
+    models = create_models(agent_kwargs, envs[0], agent_id, optimizer_kwargs=optimizer_kwargs,
+                           seed=agent_kwargs.get('seed'), conv_dims=non_agent_kwargs.get('conv_dims', 1),
+                           tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device)
+    if comm is not None:
+        for model in models.values():
+            comm.broadcast_(model.flat_param)
+            for mod in model._refreshable:
+                mod.refresh()
+            model.comm = comm
+    agent_kwargs.update(models)
     if agent_id == 'acer':
         agent_kwargs['buffers'] = _buffers.create_buffers(agent_id, non_agent_kwargs['buffer_max_size'],
                                                           non_agent_kwargs['buffer_batch_size'], non_agent_kwargs['n_envs'],
                                                           non_agent_kwargs['buffer_initial_size'])
     agent = agents[agent_id]['agent'](device=device, **agent_kwargs)
+    if comm is not None:
+        agent._rng_offset = rank << 40                             # disjoint Philox counter ranges for the action sampler
+        if 'env_seed' in non_agent_kwargs:
+            for i, env in enumerate(envs):
+                env.seed(non_agent_kwargs['env_seed'] + i)
+            agent.reset_envs()
     if non_agent_kwargs.get('weights'):
         n_weights, n_models = len(non_agent_kwargs['weights']), len(agent.output_models)
         assert n_weights == n_models, f'Expected {n_models} weights to load, got {n_weights}'

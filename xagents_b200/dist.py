@@ -106,6 +106,16 @@ class ShardComm:
             torch.cuda.current_stream(self.device).wait_event(self._pending)
             self._pending = None
 
+    def sum_over_ranks(self, values):
+        """Element-wise sum of a short list of host numbers over all ranks (stop conditions, logging)."""
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=self.device if self.backend == 'nccl' else 'cpu')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.tolist()
+
+    def broadcast_(self, tensor, src=0):
+        dist.broadcast(tensor, src, group=self.group)
+        return tensor
+
     def max_over_ranks(self, value):
         t = torch.tensor([float(value)], dtype=torch.float64, device=self.device if self.backend == 'nccl' else 'cpu')
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
