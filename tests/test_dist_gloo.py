@@ -78,9 +78,23 @@ def _worker(rank, world, port, out_dir):
     comm.all_reduce_gradients_async(grads)
     comm.wait_gradients()
     slowest = comm.max_over_ranks(10.0 * (rank + 1))
+    # job-wide stop conditions of a sharded fit() (agents/base.py: training_done) and the initial weight broadcast
+    from collections import deque
+    from xagents_b200.agents.base import BaseAgent
+    agent = object.__new__(BaseAgent)
+    agent.comm, agent.quiet = comm, True
+    agent.total_rewards = deque([10.0, 20.0] if rank == 0 else [60.0], maxlen=100)
+    agent.mean_reward = float(np.mean(agent.total_rewards))
+    agent.steps = 100 * (rank + 1)
+    decisions = []
+    for target, max_steps in ((25.0, None), (31.0, None), (None, 300), (None, 301)):
+        agent.target_reward, agent.max_steps = target, max_steps
+        decisions.append(agent.training_done())
+    weights = torch.full((5,), float(rank + 7))
+    comm.broadcast_(weights)
     comm.barrier()
     np.savez(os.path.join(out_dir, f'rank{rank}.npz'), returns=returns, perms=np.stack(perms), gathered=gathered.numpy(),
-             grads=grads.numpy(), slowest=slowest)
+             grads=grads.numpy(), slowest=slowest, decisions=np.array(decisions), weights=weights.numpy())
     dist.destroy_process_group()
 
 
@@ -109,3 +123,7 @@ def test_two_rank_sharded_step_equals_single_process(tmp_path):
             np.testing.assert_allclose(got, want, atol=1e-5 * np.abs(want).max())
     for r in ranks:
         assert np.array_equal(r['grads'], np.full(1000, 3.0)) and float(r['slowest']) == 20.0
+        # job-wide mean reward (10 + 20 + 60) / 3 = 30 and step count 300: both ranks decide alike although rank 0 alone
+        # (mean 15, 100 steps) would never have stopped and rank 1 alone (mean 60) would have stopped every time
+        assert r['decisions'].tolist() == [True, False, True, False]
+        assert np.array_equal(r['weights'], np.full(5, 7.0))
