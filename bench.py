@@ -186,8 +186,12 @@ def cpu_reference(args, sample_envs, steps, warmup):
     sample = (f'{steps} timed train steps (after {warmup} warm-up) of n_envs={sample_envs} x n_steps={args.n_steps} '
               f'(= {sample_envs * args.n_steps} samples/step, fp32 observations as the reference stores them), '
               f'4 epochs x 4 minibatches; env-steps/s is size-independent on the CPU')
+    # also with the observations kept uint8 on the host (a quarter of the bytes the reference's fp32 layout
+    # moves) -- the fairest CPU number for the byte movement itself; `value` stays the reference's own layout
+    res_u8 = cpu_path.time_cpu_baseline(ro, steps=max(1, steps // 2), warmup=1, layout='uint8')
     return res, {'value': res['env_steps_per_sec'], 'unit': UNIT, 'cores': res['threads'], 'kind': 'port', 'sample': sample,
-                 'host_cpus': os.cpu_count(), 'torch_threads': torch.get_num_threads()}
+                 'value_uint8_obs': res_u8['env_steps_per_sec'], 'host_cpus': os.cpu_count(),
+                 'torch_threads': torch.get_num_threads()}
 
 
 def run_reference(args):
