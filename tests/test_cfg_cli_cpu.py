@@ -293,3 +293,39 @@ def test_replay_buffer_handles_and_acer_flags():
     net = ModelReader(cli.agents['acer']['model']['cnn'][0], [6, 6], (84, 84, 4), conv_dims=2).build_model()
     probs, q = net(torch.rand(2, 84, 84, 4))
     assert net.output_is_softmax and probs.shape == q.shape == (2, 6) and torch.allclose(probs.sum(-1), torch.ones(2), atol=1e-6)
+
+
+def test_batched_device_environment_keeps_the_step_envs_contract():
+    """envs.BatchedSyntheticAtari behind BaseAgent.step_envs (xagents/base.py:388-426): same outputs and bookkeeping as the
+    per-environment loop -- terminal frame returned, post-reset frame kept, episode sums cut at dones -- as tensors."""
+    from xagents_b200.agents import BaseAgent
+    made = envs.create_envs('SyntheticAtariDevice-v0', 6, preprocess=True, device='cpu')
+    assert made.batched and len(made) == 6 and made[3].observation_space.shape == (84, 84, 4)
+    with pytest.raises(TypeError, match='not a list of environments'):
+        list(made)
+    made.p_done, made.p_reward = 0.3, 0.6
+    agent = BaseAgent(made, None, n_steps=4, quiet=True, seed=4, device='cpu')
+    assert agent.batched and agent.n_envs == 6 and agent.img_inputs and agent.n_actions == 6
+    assert isinstance(agent.get_states(), torch.Tensor) and agent.get_states().dtype == torch.uint8
+    sums, finished, n_done = np.zeros(6), [], 0
+    for step in range(25):
+        before = agent.get_states().clone()
+        previous, actions, rewards, dones, new_states = agent.step_envs(torch.zeros(6), True)
+        assert torch.equal(previous, before) and torch.equal(agent.get_dones(), dones)
+        assert set(rewards.tolist()) <= {-1.0, 0.0, 1.0} and set(dones.tolist()) <= {0.0, 1.0}
+        moved_on = (agent.get_states() != new_states).flatten(1).any(1)
+        assert torch.equal(moved_on, dones.bool())                 # finished envs already hold their post-reset frame
+        sums += rewards.numpy()
+        for e in np.nonzero(dones.numpy())[0]:
+            finished.append(sums[e])
+            sums[e] = 0
+            n_done += 1
+    assert agent.steps == 25 * 6 and agent.games == 0              # bookkeeping is deferred ...
+    from time import perf_counter
+    agent.training_start_time = agent.last_reset_time = perf_counter()      # what fit() sets before its loop
+    agent.check_episodes()                                         # ... to one read-back per train step
+    assert agent.games == n_done > 10 and list(agent.total_rewards) == [float(x) for x in finished][-100:]
+    assert np.allclose(agent._episode_sums.numpy(), sums)
+    agent.update_metrics()
+    assert agent.mean_reward == pytest.approx(np.mean(finished[-100:]))
+    assert agent.step_envs(torch.zeros(6)) == []

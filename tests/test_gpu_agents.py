@@ -301,3 +301,31 @@ def test_cli_train_shards_the_environments_over_two_gpus():
     assert out['optimizer_steps'] == (40960 // 2048) * 16
     assert out['weights_identical_across_ranks'] and out['weights_finite']
     assert out['mean_reward_last_episodes'] > 25.0
+
+
+@pytest.mark.timeout(240)
+def test_ppo_and_acer_on_the_device_resident_batched_environment():
+    """envs.BatchedSyntheticAtari: the rollout never leaves the device (states, rewards, dones are tensors; no per-env loop),
+    episode bookkeeping is read back once per train step and agrees with the done flags the rollout recorded."""
+    from xagents_b200 import cli, envs
+    from xagents_b200.agents import PPO, NatureCNN, TorchModel
+    made = envs.create_envs('SyntheticAtariDevice-v0', 8, preprocess=True, device='cuda:0')
+    made.p_done = 0.2
+    torch.manual_seed(0)
+    net = TorchModel(NatureCNN(4, 6).cuda())
+    agent = PPO(made, net, n_steps=8, mini_batches=4, ppo_epochs=2, quiet=True, seed=3)
+    assert agent.batched and agent.obs_dtype == torch.uint8 and agent.get_states().is_cuda
+    first = agent.get_states().clone()
+    agent.train_step()
+    assert torch.equal(agent.ro_states[0], first) and agent.steps == 64 and agent.games == 0
+    agent.check_episodes() if agent.training_start_time else agent._flush_episode_log()
+    assert agent.games == int(agent.ro_dones[1:].sum().item()) > 0 and len(agent.total_rewards) == agent.games
+    assert torch.equal(agent.ro_dones[8], agent.get_dones()) and set(agent.ro_rewards.unique().tolist()) <= {-1.0, 0.0, 1.0}
+    agent.fit(max_steps=3 * 64)
+    assert agent.steps == 192 and net.step == 3 * 2 * 4 and torch.isfinite(net.flat_param).all()
+    # through the command line, with ACER's device trajectory ring fed by the device environment
+    ex = cli.Executor()
+    ex.execute(['train', 'acer', '--env', 'SyntheticAtariDevice-v0', '--n-envs', '4', '--n-steps', '8', '--max-steps', '96', '--quiet',
+                '--seed', '3', '--buffer-max-size', '16', '--buffer-initial-size', '8', '--conv-dims', '2', '--preprocess'])
+    assert ex.agent.batched and ex.agent.steps == 96 and ex.agent.ring.states.dtype == torch.uint8
+    assert torch.isfinite(ex.agent.net.flat_param).all()

@@ -34,8 +34,8 @@ class A2C(OnPolicy):
     # ------------------------------------------------------------------ buffers
     def _alloc_rollout(self):
         T, E, dev, f32 = self.n_steps, self.n_envs, self.device, torch.float32
-        first = np.asarray(self.states[0])
-        self.obs_dtype = torch.uint8 if (self.img_inputs and first.dtype == np.uint8) else f32
+        first_dtype = self.states.dtype if self.batched else np.asarray(self.states[0]).dtype
+        self.obs_dtype = torch.uint8 if (self.img_inputs and first_dtype in (np.uint8, torch.uint8)) else f32
         self.ro_states = torch.empty((T, E) + self.input_shape, dtype=self.obs_dtype, device=dev)
         self.ro_rewards = torch.empty((T, E), dtype=f32, device=dev)
         self.ro_values = torch.empty((T, E), dtype=f32, device=dev)
@@ -48,8 +48,17 @@ class A2C(OnPolicy):
         self.loss_scalars = torch.zeros(4, dtype=f32, device=dev)
 
     def _to_device(self, array, dtype=None):
+        if isinstance(array, torch.Tensor):                        # batched device environments hand tensors over
+            return array.to(self.device, dtype=dtype)
         t = torch.as_tensor(np.ascontiguousarray(array))
         return t.to(self.device, dtype=dtype, non_blocking=True)
+
+    def _env_actions(self, actions):
+        """What `step_envs` gets: the device tensor itself for a batched environment, host values for a list of envs."""
+        if self.batched:
+            return actions
+        env_actions = actions.cpu().numpy()
+        return env_actions.astype(np.int64) if self.discrete else env_actions
 
     # ------------------------------------------------------------------ distribution (a2c/agent.py:50-94)
     def _log_prob_entropy(self, actor_out, actions):
@@ -100,9 +109,7 @@ class A2C(OnPolicy):
             self.ro_dones[t].copy_(self._to_device(step_dones))
             self.ro_entropies[t].copy_(entropy)
             self.ro_actor[t].copy_(actor_out)
-            env_actions = actions.cpu().numpy()
-            env_actions = env_actions.astype(np.int64) if self.discrete else env_actions
-            *_, step_rewards, step_dones, step_states = self.step_envs(env_actions, True, False)
+            *_, step_rewards, step_dones, step_states = self.step_envs(self._env_actions(actions), True, False)
             self.ro_rewards[t].copy_(self._to_device(step_rewards))
         self.ro_dones[self.n_steps].copy_(self._to_device(step_dones))
         return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,

@@ -71,7 +71,7 @@ class ACER(A2C):
             states[t].copy_(states_d)
             actions[t].copy_(step_actions)
             probs[t].copy_(actor_out)
-            *_, step_rewards, step_dones, step_states = self.step_envs(step_actions.cpu().numpy().astype(np.int64), True, False)
+            *_, step_rewards, step_dones, step_states = self.step_envs(self._env_actions(step_actions), True, False)
             rewards[t].copy_(self._to_device(step_rewards))
             dones[t].copy_(self._to_device(step_dones))
         states[self.n_steps].copy_(self._to_device(self.get_states(), self.obs_dtype))   # acer/agent.py:160

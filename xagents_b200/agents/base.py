@@ -52,6 +52,9 @@ class BaseAgent:
             if value is not None:
                 raise NotImplementedError(f'{name}: checkpoint / history / tuning hooks are outside the hot-path '
                                           f'package (SURVEY.md §2); drive them from the caller')
+        # one device-resident object for all environments (envs.BatchedSyntheticAtari): states, rewards and dones are
+        # device tensors and a rollout step has no host round trip; a list of gym-style environments otherwise
+        self.batched = bool(getattr(envs, 'batched', False))
         self.n_envs = len(envs)
         self.envs = envs
         self.model = model
@@ -78,6 +81,10 @@ class BaseAgent:
         self.mean_reward = -float('inf')
         self.states = [np.array(0)] * self.n_envs
         self.dones = [False] * self.n_envs
+        if self.batched:
+            self.dones = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+            self._episode_sums = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+            self._episode_log = []       # per step: (dones, episode sums at that step), read back once per train step
         self.steps = 0
         self.frame_speed = 0
         self.last_reset_step = 0
@@ -90,7 +97,7 @@ class BaseAgent:
             self.set_seeds(seed)
         self.reset_envs()
         self.set_action_count()
-        self.img_inputs = len(np.shape(self.states[0])) >= 2          # base.py:120
+        self.img_inputs = len(tuple(self.states[0].shape) if self.batched else np.shape(self.states[0])) >= 2   # base.py:120
         self.display_titles = ('time', 'steps', 'games', 'speed', 'mean reward', 'best reward')
 
     # ------------------------------------------------------------------ small helpers
@@ -102,6 +109,9 @@ class BaseAgent:
         torch.manual_seed(seed)
         np.random.seed(seed)
         random.seed(seed)
+        if self.batched:
+            self.envs.seed(seed)
+            return
         for env in self.envs:
             if hasattr(env, 'seed'):
                 env.seed(seed)
@@ -109,6 +119,9 @@ class BaseAgent:
                 env.action_space.seed(seed)
 
     def reset_envs(self):
+        if self.batched:
+            self.states = self.envs.reset_all()
+            return
         for i, env in enumerate(self.envs):
             self.states[i] = env.reset()
 
@@ -122,16 +135,43 @@ class BaseAgent:
             self.n_actions = int(space.shape[0])
 
     def get_states(self):
-        return np.array(self.states)
+        return self.states if self.batched else np.array(self.states)
 
     def get_dones(self):
-        return np.array(self.dones, np.float32)
+        return self.dones if self.batched else np.array(self.dones, np.float32)
+
+    def _step_batched(self, actions, get_observation):
+        """step_envs for a device-resident batched environment: same contract, device tensors, no per-env loop.  Episode
+        bookkeeping (total_rewards, games, done_envs) is deferred: the per-step done flags and episode sums stay on the
+        device and are read back once per train step by `_flush_episode_log`."""
+        previous = self.states
+        new_states, rewards, dones = self.envs.step_all(actions)
+        self.states, self.dones = self.envs.states, dones
+        self._episode_sums += rewards
+        self._episode_log.append((dones, self._episode_sums.clone()))
+        self._episode_sums *= 1.0 - dones
+        self.steps += self.n_envs
+        return [previous, actions, rewards, dones, new_states] if get_observation else []
+
+    def _flush_episode_log(self):
+        if not self.batched or not self._episode_log:
+            return
+        dones = torch.stack([d for d, _ in self._episode_log]).cpu().numpy()
+        sums = torch.stack([s for _, s in self._episode_log]).cpu().numpy()
+        self._episode_log.clear()
+        for step_dones, step_sums in zip(dones, sums):             # in step order, envs in index order: the loop's order
+            for total in step_sums[step_dones > 0]:
+                self.done_envs += 1
+                self.total_rewards.append(float(total))
+                self.games += 1
 
     # ------------------------------------------------------------------ environments
     def step_envs(self, actions, get_observation=False, store_in_buffers=False):
         """Step every environment once (xagents/base.py:388-426 semantics: the returned new_state of a
         finished episode is the terminal one while `self.states[i]` already holds the reset state)."""
         assert not store_in_buffers, 'replay buffers belong to the off-policy agents (out of scope)'
+        if self.batched:
+            return self._step_batched(actions, get_observation)
         columns = [[] for _ in range(5)]
         for i, (env, action) in enumerate(zip(self.envs, actions)):
             previous = self.states[i]
@@ -167,10 +207,12 @@ class BaseAgent:
 
     # ------------------------------------------------------------------ driver
     def update_metrics(self):
+        self._flush_episode_log()
         self.mean_reward = float(np.mean(self.total_rewards)) if self.total_rewards else -float('inf')
         self.best_reward = max(self.best_reward, self.mean_reward)
         now = perf_counter()
-        self.frame_speed = (self.steps - self.last_reset_step) / max(now - self.last_reset_time, 1e-9)
+        since = self.last_reset_time if self.last_reset_time is not None else now        # metrics asked for outside fit()
+        self.frame_speed = (self.steps - self.last_reset_step) / max(now - since, 1e-9)
         self.last_reset_step, self.last_reset_time = self.steps, now
 
     def display_metrics(self):
@@ -180,12 +222,14 @@ class BaseAgent:
         self.display_message(', '.join(f'{t}: {v}' for t, v in zip(self.display_titles, values)))
 
     def check_episodes(self):
+        self._flush_episode_log()
         if self.done_envs >= self.log_frequency:
             self.update_metrics()
             self.display_metrics()
             self.done_envs = 0
 
     def training_done(self):
+        self._flush_episode_log()
         mean_reward, steps = self.mean_reward, self.steps
         comm = getattr(self, 'comm', None)
         if comm is not None and comm.world_size > 1:

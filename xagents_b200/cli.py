@@ -34,7 +34,8 @@ def _flag(help, type=None, default=None, action=None, required=None, nargs=None)
 
 
 non_agent_args = {
-    'env': _flag('environment id (built-in: CartPole-v1, SyntheticAtari-v0; else gym / gymnasium)', required=True),
+    'env': _flag('environment id (built-in: CartPole-v1, SyntheticAtari-v0, SyntheticAtariDevice-v0; else gym / gymnasium)',
+                 required=True),
     'n-envs': _flag('Number of environments to create', int, 1),
     'preprocess': _flag('Treat states as atari frames and preprocess them', action='store_true'),
     'lr': _flag('Adam learning rate', float, 7e-4),
@@ -219,7 +220,7 @@ def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
         if agent_kwargs.get('seed') is not None:                   # different episodes on every rank, same model seed
             non_agent_kwargs = dict(non_agent_kwargs, env_seed=agent_kwargs['seed'] + 7919 * rank)
     envs = _envs.create_envs(non_agent_kwargs['env'], n_envs, non_agent_kwargs['preprocess'],
-                             max_frame=non_agent_kwargs.get('max_frame'))
+                             max_frame=non_agent_kwargs.get('max_frame'), device=device)
     agent_kwargs['envs'] = envs
     optimizer_kwargs = {'learning_rate': non_agent_kwargs['lr'], 'beta_1': non_agent_kwargs['beta1'],
                         'beta_2': non_agent_kwargs['beta2'], 'epsilon': non_agent_kwargs['opt_epsilon']}
@@ -241,8 +242,11 @@ def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
     if comm is not None:
         agent._rng_offset = rank << 40                             # disjoint Philox counter ranges for the action sampler
         if 'env_seed' in non_agent_kwargs:
-            for i, env in enumerate(envs):
-                env.seed(non_agent_kwargs['env_seed'] + i)
+            if getattr(envs, 'batched', False):
+                envs.seed(non_agent_kwargs['env_seed'])
+            else:
+                for i, env in enumerate(envs):
+                    env.seed(non_agent_kwargs['env_seed'] + i)
             agent.reset_envs()
     if non_agent_kwargs.get('weights'):
         n_weights, n_models = len(non_agent_kwargs['weights']), len(agent.output_models)

@@ -8,6 +8,8 @@ environments BASELINE.json's configs name ship here in the gym API the reference
 * `CartPole-v1` -- the classic cart-pole balance task (Barto, Sutton & Anderson 1983) with the standard
   constants (Euler integration at 0.02 s, 12 degrees / 2.4 m limits, 500-step episodes, reward 1 per step):
   config C1 runs end to end and learns.
+* `SyntheticAtariDevice-v0` -- the same frames as ONE device-resident batched environment (`BatchedSyntheticAtari`):
+  rollouts without host round trips.
 * `SyntheticAtari-v0` (aliases `SyntheticPong-v0`, and any `*NoFrameskip-v4` id when ALE is absent and
   `XAGENTS_B200_SYNTHETIC_ATARI=1`) -- 84x84xC uint8 frames drawn i.i.d., sparse +-1 rewards, geometric
   episode lengths: the "synthetic Atari frames" of configs C2-C4 behind the env interface.
@@ -142,6 +144,68 @@ class SyntheticAtari:
         pass
 
 
+class BatchedSyntheticAtari:
+    """All `n` synthetic-frame environments as ONE object whose state lives on the device (SURVEY.md 8f-3 taken to the
+    environment side): `reset_all()` / `step_all(actions)` take and return device tensors, so a rollout step is
+    network -> sampler -> this, with no host round trip, no per-environment Python loop and no H2D copy of frames
+    (256 x 28 KB per step at config C3).  Same distribution as `SyntheticAtari` (i.i.d. uint8 frames from a pool,
+    +-1 rewards w.p. `p_reward`, episode ends w.p. `p_done`), same reset semantics as BaseAgent.step_envs
+    (xagents/base.py:408-426): `step_all` returns the terminal frame of a finished episode while `states` already holds
+    the frame after the reset.  Looks like a sequence of `n` environments to code that reads `len(envs)` or
+    `envs[0].observation_space`; agents detect `batched` and call the two batch methods instead of looping."""
+    batched = True
+
+    def __init__(self, n, env_id='SyntheticAtariDevice-v0', channels=4, n_actions=6, p_done=0.01, p_reward=0.02, seed=None,
+                 pool=256, device='cuda:0'):
+        import torch
+        self.torch, self.n, self.device = torch, int(n), torch.device(device)
+        self.spec = _Spec(env_id)
+        self.observation_space = Box(0, 255, (84, 84, channels), np.uint8)
+        self.action_space = Discrete(n_actions)
+        self.p_done, self.p_reward, self._pool_size = p_done, p_reward, pool
+        self.states = None
+        self.seed(seed)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self
+
+    def __iter__(self):
+        raise TypeError('a batched environment is not a list of environments: call reset_all() / step_all(actions)')
+
+    def seed(self, seed=None):
+        torch = self.torch
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63)))
+        self._pool = torch.randint(0, 256, (self._pool_size,) + self.observation_space.shape, dtype=torch.uint8,
+                                   device=self.device, generator=self._gen)
+        return [seed]
+
+    def _frames(self):
+        idx = self.torch.randint(0, self._pool_size, (self.n,), device=self.device, generator=self._gen)
+        return self._pool.index_select(0, idx)
+
+    def reset_all(self):
+        self.states = self._frames()
+        return self.states
+
+    def step_all(self, actions):
+        """-> (new_states [n,84,84,C] uint8, rewards [n] fp32, dones [n] fp32), all on the device."""
+        torch = self.torch
+        u = torch.rand((3, self.n), device=self.device, generator=self._gen)
+        rewards = torch.where(u[0] < self.p_reward, torch.where(u[1] < 0.5, 1.0, -1.0), 0.0)
+        dones = (u[2] < self.p_done).float()
+        new_states = self._frames()
+        after_reset = self._frames()
+        self.states = torch.where(dones.bool().view(-1, 1, 1, 1), after_reset, new_states)
+        return new_states, rewards, dones
+
+    def close(self):
+        pass
+
+
 class _Gymnasium4Tuple:
     """gymnasium (reset -> (obs, info); step -> 5-tuple) behind the 4-tuple API of the gym version the reference pins."""
 
@@ -170,6 +234,8 @@ class _Gymnasium4Tuple:
         self.env.close()
 
 
+BATCHED = {'SyntheticAtariDevice-v0': BatchedSyntheticAtari}
+
 BUILTIN = {
     'CartPole-v1': CartPole,
     'CartPole-v0': CartPole,
@@ -197,6 +263,8 @@ def create_envs(env_name, n=1, preprocess=True, *args, **kwargs):
     """`n` environments of one id (common.py:145-167).  `preprocess` asks for the reference's AtariWrapper (grayscale +
     84x84 resize + frame skip over raw ALE frames): the built-in synthetic frames are already in the processed
     shape, so it is a no-op for them and an assertion for non-image environments, as in the reference."""
+    if env_name in BATCHED:                                        # one device-resident object for all n environments
+        return BATCHED[env_name](n, env_name, device=kwargs.get('device') or 'cuda:0')
     envs = [make(env_name) for _ in range(n)]
     if preprocess:
         shape = envs[0].observation_space.shape
