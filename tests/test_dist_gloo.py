@@ -82,7 +82,7 @@ def _worker(rank, world, port, out_dir):
     from collections import deque
     from xagents_b200.agents.base import BaseAgent
     agent = object.__new__(BaseAgent)
-    agent.comm, agent.quiet = comm, True
+    agent.comm, agent.quiet, agent.batched = comm, True, False
     agent.total_rewards = deque([10.0, 20.0] if rank == 0 else [60.0], maxlen=100)
     agent.mean_reward = float(np.mean(agent.total_rewards))
     agent.steps = 100 * (rank + 1)
