@@ -329,3 +329,42 @@ def test_batched_device_environment_keeps_the_step_envs_contract():
     agent.update_metrics()
     assert agent.mean_reward == pytest.approx(np.mean(finished[-100:]))
     assert agent.step_envs(torch.zeros(6)) == []
+
+
+def test_batched_cartpole_integrates_like_the_per_environment_cartpole():
+    """envs.BatchedCartPole against envs.CartPole from identical states under identical actions: same trajectories,
+    same termination steps, time limit included; finished episodes restart inside the initial-state box."""
+    made = envs.create_envs('CartPoleDevice-v1', 5, preprocess=False, device='cpu')
+    made.seed(11)
+    first = made.reset_all()
+    assert first.shape == (5, 4) and first.dtype == torch.float32 and first.abs().max() <= 0.05
+    singles = [envs.CartPole() for _ in range(5)]
+    for i, env in enumerate(singles):
+        env.reset()
+        env.state = made.state[i].numpy().copy()
+    rng = np.random.default_rng(0)
+    alive, finished = [True] * 5, 0
+    for step in range(120):
+        actions = rng.integers(0, 2, 5)
+        new_states, rewards, dones = made.step_all(torch.as_tensor(actions, dtype=torch.float32))
+        assert torch.equal(rewards, torch.ones(5))
+        for i, env in enumerate(singles):
+            if not alive[i]:
+                continue
+            want, reward, done, _ = env.step(int(actions[i]))
+            assert np.allclose(new_states[i].numpy(), want, rtol=0, atol=1e-6) and bool(dones[i]) == done
+            if done:                                                # the batched env restarted it; stop following this one
+                alive[i], finished = False, finished + 1
+                assert made.states[i].abs().max() <= 0.05 and int(made.t[i]) == 0
+                assert not torch.equal(made.states[i], new_states[i])
+            else:
+                assert torch.equal(made.states[i], new_states[i])
+    assert finished == 5                                            # random actions drop every pole well within 120 steps
+    made.reset_all()                                                # time limit: a bang-bang controller holds for 500 steps
+    for t in range(500):
+        s = made.state
+        _, _, dones = made.step_all((s[:, 2] + 0.5 * s[:, 3] > 0).float())
+        assert bool(dones.any()) == (t == 499)
+    assert bool(dones.all())
+    with pytest.raises(AssertionError, match='Cannot use AtariWrapper or --preprocess for non-atari environment CartPoleDevice-v1'):
+        envs.create_envs('CartPoleDevice-v1', 2, preprocess=True, device='cpu')

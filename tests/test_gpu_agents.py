@@ -329,3 +329,16 @@ def test_ppo_and_acer_on_the_device_resident_batched_environment():
                 '--seed', '3', '--buffer-max-size', '16', '--buffer-initial-size', '8', '--conv-dims', '2', '--preprocess'])
     assert ex.agent.batched and ex.agent.steps == 96 and ex.agent.ring.states.dtype == torch.uint8
     assert torch.isfinite(ex.agent.net.flat_param).all()
+
+
+@pytest.mark.timeout(300)
+def test_cli_train_ppo_on_the_device_resident_cartpole_learns():
+    """Config C1 with the environments integrated on the device (envs.BatchedCartPole): no host round trip in the rollout."""
+    from xagents_b200 import cli
+    ex = cli.Executor()
+    ex.execute(['train', 'ppo', '--env', 'CartPoleDevice-v1', '--n-envs', '16', '--max-steps', '81920', '--seed', '1', '--quiet'])
+    agent = ex.agent
+    assert agent.batched and agent.obs_dtype == torch.float32 and tuple(agent.ro_states.shape) == (128, 16, 4)
+    assert agent.steps >= 81920 and agent.net.step == (81920 // 2048) * 16
+    agent.update_metrics()
+    assert agent.games > 100 and agent.best_reward > 35.0, f'PPO did not improve: best mean reward {agent.best_reward}'

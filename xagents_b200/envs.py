@@ -8,8 +8,8 @@ environments BASELINE.json's configs name ship here in the gym API the reference
 * `CartPole-v1` -- the classic cart-pole balance task (Barto, Sutton & Anderson 1983) with the standard
   constants (Euler integration at 0.02 s, 12 degrees / 2.4 m limits, 500-step episodes, reward 1 per step):
   config C1 runs end to end and learns.
-* `SyntheticAtariDevice-v0` -- the same frames as ONE device-resident batched environment (`BatchedSyntheticAtari`):
-  rollouts without host round trips.
+* `SyntheticAtariDevice-v0`, `CartPoleDevice-v1` -- the same two tasks as ONE device-resident batched environment each
+  (`BatchedSyntheticAtari`, `BatchedCartPole`): rollouts without host round trips.
 * `SyntheticAtari-v0` (aliases `SyntheticPong-v0`, and any `*NoFrameskip-v4` id when ALE is absent and
   `XAGENTS_B200_SYNTHETIC_ATARI=1`) -- 84x84xC uint8 frames drawn i.i.d., sparse +-1 rewards, geometric
   episode lengths: the "synthetic Atari frames" of configs C2-C4 behind the env interface.
@@ -206,6 +206,73 @@ class BatchedSyntheticAtari:
         pass
 
 
+class BatchedCartPole:
+    """`n` cart-poles integrated together on the device (id `CartPoleDevice-v1`): the dynamics, limits and time limit of
+    `CartPole`, one tensor expression per step instead of `n` Python calls, states / rewards / dones handed to the agent as
+    device tensors (float64 state inside, float32 observations out, like gym's).  Same batch protocol as
+    `BatchedSyntheticAtari`; config C1 (PPO on CartPole, n_envs=16, n_steps=128) then runs without a host round trip in
+    the rollout."""
+    batched = True
+
+    def __init__(self, n, env_id='CartPoleDevice-v1', seed=None, device='cuda:0'):
+        import torch
+        self.torch, self.n, self.device = torch, int(n), torch.device(device)
+        self.spec = _Spec(env_id)
+        c = CartPole
+        high = np.array([2 * c.X_LIMIT, np.finfo(np.float32).max, 2 * c.THETA_LIMIT, np.finfo(np.float32).max], np.float32)
+        self.observation_space = Box(-high, high, (4,), np.float32)
+        self.action_space = Discrete(2)
+        self.state = self.t = self.states = None
+        self.seed(seed)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self
+
+    def __iter__(self):
+        raise TypeError('a batched environment is not a list of environments: call reset_all() / step_all(actions)')
+
+    def seed(self, seed=None):
+        self._gen = self.torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63)))
+        return [seed]
+
+    def _initial(self, count):
+        torch = self.torch
+        return torch.rand((count, 4), dtype=torch.float64, device=self.device, generator=self._gen) * 0.1 - 0.05
+
+    def reset_all(self):
+        self.state = self._initial(self.n)
+        self.t = self.torch.zeros(self.n, dtype=self.torch.int64, device=self.device)
+        self.states = self.state.float()
+        return self.states
+
+    def step_all(self, actions):
+        """-> (new_states [n,4] fp32, rewards [n] fp32 (all ones), dones [n] fp32) on the device."""
+        torch, c = self.torch, CartPole
+        assert self.state is not None, 'Cannot call step_all() before calling reset_all()'
+        x, x_dot, th, th_dot = self.state.unbind(1)
+        force = torch.where(actions.to(self.device).reshape(-1) >= 0.5, c.FORCE, -c.FORCE).to(torch.float64)
+        cos, sin = torch.cos(th), torch.sin(th)
+        total, pml = c.CART_MASS + c.POLE_MASS, c.POLE_MASS * c.HALF_LENGTH
+        temp = (force + pml * th_dot * th_dot * sin) / total
+        th_acc = (c.GRAVITY * sin - cos * temp) / (c.HALF_LENGTH * (4.0 / 3.0 - c.POLE_MASS * cos * cos / total))
+        x_acc = temp - pml * th_acc * cos / total
+        state = torch.stack([x + c.TAU * x_dot, x_dot + c.TAU * x_acc, th + c.TAU * th_dot, th_dot + c.TAU * th_acc], 1)
+        self.t += 1
+        done = (state[:, 0].abs() > c.X_LIMIT) | (state[:, 2].abs() > c.THETA_LIMIT) | (self.t >= c.MAX_STEPS)
+        new_states = state.float()
+        self.state = torch.where(done.view(-1, 1), self._initial(self.n), state)      # finished episodes start over
+        self.t = torch.where(done, torch.zeros_like(self.t), self.t)
+        self.states = self.state.float()
+        return new_states, torch.ones(self.n, dtype=torch.float32, device=self.device), done.float()
+
+    def close(self):
+        pass
+
+
 class _Gymnasium4Tuple:
     """gymnasium (reset -> (obs, info); step -> 5-tuple) behind the 4-tuple API of the gym version the reference pins."""
 
@@ -234,7 +301,7 @@ class _Gymnasium4Tuple:
         self.env.close()
 
 
-BATCHED = {'SyntheticAtariDevice-v0': BatchedSyntheticAtari}
+BATCHED = {'SyntheticAtariDevice-v0': BatchedSyntheticAtari, 'CartPoleDevice-v1': BatchedCartPole}
 
 BUILTIN = {
     'CartPole-v1': CartPole,
@@ -264,7 +331,12 @@ def create_envs(env_name, n=1, preprocess=True, *args, **kwargs):
     84x84 resize + frame skip over raw ALE frames): the built-in synthetic frames are already in the processed
     shape, so it is a no-op for them and an assertion for non-image environments, as in the reference."""
     if env_name in BATCHED:                                        # one device-resident object for all n environments
-        return BATCHED[env_name](n, env_name, device=kwargs.get('device') or 'cuda:0')
+        made = BATCHED[env_name](n, env_name, device=kwargs.get('device') or 'cuda:0')
+        if preprocess:
+            shape = made.observation_space.shape
+            assert len(shape) == 3, (f'Cannot use AtariWrapper or --preprocess for non-atari environment '
+                                     f'{made.spec.id}, with input shape {shape}')
+        return made
     envs = [make(env_name) for _ in range(n)]
     if preprocess:
         shape = envs[0].observation_space.shape
