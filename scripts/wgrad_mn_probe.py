@@ -1,5 +1,6 @@
 """Correctness + timing probe for xa_conv_wgrad_nhwc_bf16 (XA_WGRAD_MODE = 0 | 1 | 2 picks the operand addressing)."""
-import os, sys, time
+import os
+import sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from xagents_b200 import ops

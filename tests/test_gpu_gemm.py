@@ -1,7 +1,6 @@
 """tcgen05 GEMM (dense layers of the policy/value network) against a plain torch fp32 reference of the
 same op on the same bf16-rounded operands.  fp32 accumulation on both sides: tolerance 1e-5 of max|C|
 plus bf16 rounding when the output is bf16."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,10 +1,7 @@
 """Host logic of the prepared pipeline, checked without a GPU: minibatch slicing (incl. the trailing short one),
 launch schedules, staging placement and the pointer arithmetic of the launch tables.  Nothing is launched -- and
 trying to is an error, not a fallback."""
-import ctypes
-
 import pytest
-import torch
 
 from xagents_b200 import _ffi
 from xagents_b200.hotpath import PPOHotPath
