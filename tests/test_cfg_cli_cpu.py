@@ -368,3 +368,31 @@ def test_batched_cartpole_integrates_like_the_per_environment_cartpole():
     assert bool(dones.all())
     with pytest.raises(AssertionError, match='Cannot use AtariWrapper or --preprocess for non-atari environment CartPoleDevice-v1'):
         envs.create_envs('CartPoleDevice-v1', 2, preprocess=True, device='cpu')
+
+
+def test_step_envs_columns_for_a_list_of_environments():
+    """BaseAgent.step_envs(get_observation=True) -> [state, action, reward, done, new_state] (xagents/base.py:388-426): the
+    terminal frame is returned while the agent already holds the reset frame; uint8 frames stay uint8, everything else is
+    float32 like the reference's columns."""
+    from xagents_b200.agents import BaseAgent
+    made = envs.create_envs('SyntheticAtari-v0', 5, preprocess=True)
+    for i, env in enumerate(made):
+        env.seed(i)
+        env.p_done = 0.4
+    agent = BaseAgent(made, None, n_steps=3, quiet=True, device='cpu')
+    finished = 0
+    for _ in range(12):
+        before = agent.get_states()
+        state, action, reward, done, new_state = agent.step_envs(np.arange(5) % 6, True)
+        assert [c.dtype for c in (state, action, reward, done, new_state)] == [np.uint8, np.float32, np.float32, np.float32, np.uint8]
+        assert np.array_equal(state, before) and np.array_equal(action, np.arange(5, dtype=np.float32))
+        held = agent.get_states()
+        for e in range(5):
+            assert bool(done[e]) == agent.dones[e]
+            if done[e]:
+                finished += 1
+            else:
+                assert np.array_equal(held[e], new_state[e])
+    assert agent.games == finished > 5 and agent.steps == 60 and len(agent.total_rewards) == finished
+    vector = BaseAgent(envs.create_envs('CartPole-v1', 3, preprocess=False), None, quiet=True, device='cpu')
+    assert [c.dtype for c in vector.step_envs(np.zeros(3, np.int64), True)] == [np.float32] * 5
