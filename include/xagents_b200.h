@@ -81,12 +81,13 @@ int xa_gather_rows(const void* src, const int32_t* idx, void* dst, int64_t n_idx
                    int64_t n_src_rows, int n_steps, int n_envs, int mode, xa_stream_t stream);
 
 /* Same gather for up to XA_MAX_FIELDS fp32 scalar-per-sample fields at once (actions, returns,
- * old values, old log-probs).  src/dst: HOST arrays of n_fields device pointers. */
+ * old values, old log-probs: the four scalar tf.gather calls of xagents/ppo/agent.py:149-154).  src/dst: HOST arrays of n_fields device pointers. */
 #define XA_MAX_FIELDS 8
 int xa_gather_fields_f32(const float* const* src, float* const* dst, int n_fields, const int32_t* idx,
                          int64_t n_idx, int n_steps, int n_envs, xa_stream_t stream);
 
-/* One launch for a whole minibatch (or epoch): observation rows + scalar fields. */
+/* One launch for a whole minibatch (or epoch): observation rows + scalar fields -- everything one iteration of the
+ * loop in PPO.get_mini_batches produces (xagents/ppo/agent.py:139-155). */
 int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, int64_t n_src_rows,
                         const float* const* field_src, float* const* field_dst, int n_fields,
                         const int32_t* idx, int64_t n_idx, int n_steps, int n_envs, int mode,
@@ -182,7 +183,8 @@ int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const float* bias, in
                     int64_t k, int64_t ldc, int out_bf16, int relu, const void* relu_mask, void* workspace,
                     int64_t workspace_bytes, xa_stream_t stream);
 
-/* xa_gemm_bf16_tn with an output column map and a separate mask pitch: with col_group > 0 (a multiple of 32) column j
+/* Backward of a Keras Dense layer (the tape's part of xagents/ppo/agent.py:134): xa_gemm_bf16_tn with an output column
+ * map and a separate mask pitch: with col_group > 0 (a multiple of 32) column j
  * of the product is stored at c[row*ldc + (j / col_group) * col_group_pitch + j % col_group], which writes a
  * [B, h*w*ch] gradient straight onto a zero-bordered [B, H, W, ch] grid (col_group = w*ch, col_group_pitch = W*ch,
  * ldc = H*W*ch) -- the layout xa_conv_wgrad_nhwc_bf16 reads.  relu_mask is [m, mask_ld] in PRODUCT columns. */
@@ -229,11 +231,13 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
                               int block, int scale_255, xa_stream_t stream);
 
-/* dst[i] = src[map[i]] as bf16 (out_bf16) or fp32, 0 where map[i] < 0: re-derives every weight layout of the
+/* After optimizer.apply_gradients (xagents/ppo/agent.py:137) the kernels' operand copies must follow the fp32 weights:
+ * dst[i] = src[map[i]] as bf16 (out_bf16) or fp32, 0 where map[i] < 0: re-derives every weight layout of the
  * tensor-core network (all permutations of the fp32 parameters) in one launch after an optimiser step. */
 int xa_gather_cast_f32(const float* src, const int32_t* map, void* dst, int64_t n, int out_bf16, xa_stream_t stream);
 
 /* c [m, n] fp32 (pitch ldc) = a^T b for ROW-MAJOR a [k, m] and b [k, n] bf16: the Dense weight gradient dW = dY^T X
+ * (Dense layers of the .cfg model, xagents/utils/common.py:239-258; gradient taken at xagents/ppo/agent.py:134)
  * with dY [batch, out] and X [batch, in] as the other kernels leave them -- no transposed copies (MN-major UMMA
  * operands, csrc/gemm_atb_tc.cu).  m and n multiples of 8.  workspace (xa_gemm_atb_workspace_bytes, may be NULL)
  * enables the deterministic split over k for shapes with few output tiles. */
@@ -241,7 +245,8 @@ int64_t xa_gemm_atb_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int xa_gemm_bf16_atb(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int64_t ldc, void* workspace,
                      int64_t workspace_bytes, xa_stream_t stream);
 
-/* Weight and bias gradient of a stride-1 NHWC convolution from the NATURAL tensors (no transposes, no im2col):
+/* Weight and bias gradient of a stride-1 NHWC convolution (conv sections of the .cfg model, xagents/utils/common.py:
+ * 218-237, read as Conv2D: README.md:243-259) from the NATURAL tensors (no transposes, no im2col):
  * x [q_total, channels] bf16 with q = (b*H + y)*grid_w + x the pixels of the INPUT grid, dy_grid [q_total, n_out] bf16
  * = dY placed on that same grid (zero where there is no output pixel; xa_conv2d_nhwc_bf16_ex / xa_gemm_bf16_tn_ex
  * write it there).  dw [n_out, kh*kw*channels] fp32 (K ordered kh, kw, c), db [n_out] fp32 (may be NULL).
@@ -258,7 +263,8 @@ int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int
                           int n_steps, int n_envs, int height, int width, int channels, int block, int scale_255,
                           xa_stream_t stream);
 
-/* fp32 | bf16 [rows, cols] -> bf16, same orientation (dst pitch ld_dst >= cols) or transposed into
+/* Operand preparation for the Dense / convolution products above (no reference counterpart: the reference computes in
+ * fp32 throughout).  fp32 | bf16 [rows, cols] -> bf16, same orientation (dst pitch ld_dst >= cols) or transposed into
  * [cols, ld_dst >= rows]: operand preparation for the backward products (dW = dY^T X needs both transposed). */
 int xa_to_bf16(const void* src, int src_is_f32, void* dst, int64_t rows, int64_t cols, int64_t ld_dst,
                int transpose, xa_stream_t stream);
