@@ -449,9 +449,18 @@ def acer_case(xagents):
     print('acer_retrace:', np.asarray(out)[:4])
 
 
+def _reset_rngs():
+    """The shuffle / sampling streams are module-wide and consumed case after case; groups of cases added later start from
+    the initial seeds again so that they do not depend on (or disturb) the cases generated before them."""
+    global _SHUFFLE_RNG, _SAMPLE_RNG
+    _SHUFFLE_RNG = np.random.default_rng(4321)
+    _SAMPLE_RNG = np.random.default_rng(99)
+
+
 def distribution_cases(xagents):
     """The other two branches of A2C.get_distribution (a2c/agent.py:50-63) through the reference's own train steps:
     MultivariateNormalDiag for Box action spaces (actions [N, k]) and Categorical(probs=) for softmax-output models."""
+    _reset_rngs()
     ppo_case(xagents, 'ppo_box', 15, n_steps=10, n_envs=4, obs_shape=(6,), image=False, n_actions=3, p_done=0.15,
              mini_batches=4, ppo_epochs=2, box=True)
     ppo_case(xagents, 'ppo_softmax', 16, n_steps=12, n_envs=6, obs_shape=(5,), image=False, n_actions=5, p_done=0.1,
@@ -466,7 +475,6 @@ def main():
         return acer_case(xagents)
     if '--distributions-only' in sys.argv:                         # added later: leaves the earlier fixtures untouched
         return distribution_cases(xagents)
-    distribution_cases(xagents)
     acer_case(xagents)
     kat_case(xagents)
     # PPO, image observations (uint8-valued, 8x8x4), 6 actions: Atari-shaped in miniature
@@ -485,6 +493,7 @@ def main():
              n_actions=6, p_done=0.1)
     a2c_case(xagents, 'a2c_vector', 22, n_steps=12, n_envs=5, obs_shape=(4,), image=False,
              n_actions=2, p_done=0.15)
+    distribution_cases(xagents)
 
 
 if __name__ == '__main__':
