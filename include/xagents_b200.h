@@ -282,6 +282,49 @@ int xa_clip_adam_f32(float* param, const float* grad, float* m, float* v, int64_
                      const void* workspace, double lr, double beta1, double beta2, double eps,
                      double clip_norm, int64_t step, double grad_scale, xa_stream_t stream);
 
+/* ---- collective C1 fused with the optimiser over NVLink peer memory (SURVEY.md 8e + 8f-2) --------- */
+/* Replaces ncclAllReduce(gradients) + xa_grad_sumsq_f32 + xa_clip_adam_f32 by one cooperative kernel per update:
+ * reduce-scatter by P2P loads (rank r sums shard r over every rank's gradient buffer, in rank order), global norm
+ * from G exchanged partial sums, clip + Keras Adam on the owned shard (m, v exist only for it), all-gather by P2P
+ * stores of the updated weights into every rank's parameter buffer.  The reference's step is
+ * tf.clip_by_global_norm + Adam.apply_gradients (xagents/ppo/agent.py:135-137) in one process; averaging over ranks
+ * is the data-parallel extension.  grad[r], param[r], sumsq[r], flags[r] are THIS process's mappings of rank r's
+ * buffers (entries >= world unused): grad/param [world * shard_len] floats, sumsq [XA_MAX_PEERS] doubles, flags
+ * xa_peer_adam_flag_bytes() bytes, zero-filled before the first call.  m, v: local [shard_len]; workspace: local,
+ * xa_peer_adam_workspace_bytes(), zero-filled once.  `epoch` must be the same on every rank and increase by one per
+ * call (it is what the peers' flags are compared with).  Every rank must call with the same step / hyper-parameters;
+ * waits are bounded (~2 s) and a timeout is reported in workspace word 2 (status: 0 = ok, 1..3 = phase that timed out). */
+#define XA_MAX_PEERS 8
+typedef struct xa_peer_adam_args {
+  void* grad[XA_MAX_PEERS];
+  void* param[XA_MAX_PEERS];
+  void* sumsq[XA_MAX_PEERS];
+  void* flags[XA_MAX_PEERS];
+  float* m;
+  float* v;
+  void* workspace;
+  int64_t shard_len;
+  int32_t rank, world;
+  uint32_t epoch;
+  float lr_t, beta1, beta2, eps, clip, inv_world; /* filled by the call */
+} xa_peer_adam_args;
+/* Peer-mappable device memory through CUDA IPC (zero-filled cudaMalloc + a 64-byte handle; the peers open the handle). */
+int xa_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int xa_ipc_open(const unsigned char* handle64, void** ptr);
+int xa_ipc_close(void* ptr);
+int xa_ipc_free(void* ptr);
+int64_t xa_peer_adam_workspace_bytes(void);
+int64_t xa_peer_adam_flag_bytes(void);
+int xa_peer_allreduce_adam_f32(const xa_peer_adam_args* args, double lr, double beta1, double beta2, double eps,
+                               double clip_norm, int64_t step, xa_stream_t stream);
+
+/* Benchmark stand-in for the network backward (bench.py): grad[j] = d_actor[j mod n*A] + 0.5 * d_values[j mod n].  The reference
+ * obtains the parameter gradients from its tape (xagents/ppo/agent.py:134); the headline metric excludes the network, so
+ * this kernel supplies what the gradient all-reduce and the optimiser need from it: a flat gradient that depends on this
+ * minibatch's loss outputs. */
+int xa_grad_from_outputs_f32(const float* d_actor, const float* d_values, int64_t n, int n_actions,
+                             float* grad, int64_t n_params, xa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,11 +46,25 @@ def ppo_train_step_cpu(ro, mini_batches=4, layout='reference', gamma=0.99, lam=0
     return time.perf_counter() - t0, float(loss)
 
 
-def time_cpu_baseline(ro, steps=1, warmup=0, **kw):
+def a2c_train_step_cpu(ro, layout='reference', gamma=0.99, entropy_coef=0.01, value_loss_coef=0.5):
+    """A2C.train_step on the host (xagents/a2c/agent.py:173-218): np.asarray of the rollout, the n-step returns loop,
+    concat_step_batches (the env-major flatten COPY of states, returns, actions, values), then the loss and its tape
+    gradient over all T*E samples.  Model outputs are inputs, as on the GPU arm."""
+    t0 = time.perf_counter()
+    states = np.asarray(ro.obs, np.float32) if layout == 'reference' else np.asarray(ro.obs)
+    returns = hotpath.nstep_returns(ro.rewards, ro.dones, ro.last_values, gamma)
+    flat_states, flat_returns, flat_actions, flat_values = hotpath.concat_step_batches(states, returns, ro.actions, ro.values)
+    loss, _, _ = torch_ref.a2c_loss_autograd(ro.new_logits, ro.new_values, flat_actions, flat_values, flat_returns, entropy_coef,
+                                             value_loss_coef)
+    return time.perf_counter() - t0, float(loss['loss'])
+
+
+def time_cpu_baseline(ro, steps=1, warmup=0, algo='ppo', **kw):
     """Median seconds per train step over `steps` runs (after `warmup`), env-steps/s, threads used."""
+    step = a2c_train_step_cpu if algo == 'a2c' else ppo_train_step_cpu
     for _ in range(warmup):
-        ppo_train_step_cpu(ro, **kw)
-    times = [ppo_train_step_cpu(ro, **kw)[0] for _ in range(steps)]
+        step(ro, **kw)
+    times = [step(ro, **kw)[0] for _ in range(steps)]
     sec = float(np.median(times))
     return dict(seconds_per_step=sec, env_steps_per_sec=ro.n_steps * ro.n_envs / sec, threads=torch.get_num_threads(),
                 times=times)

@@ -144,11 +144,13 @@ def categorical_logp_entropy(actor_output, actions, is_probs=False, dtype=np.flo
     """
     x = np.asarray(actor_output, dtype)
     # probs= : tfp takes logits = log(probs) and still normalises through log_softmax
-    lsm = _log_softmax(np.log(x)) if is_probs else _log_softmax(x)
-    a = np.asarray(actions).astype(np.int64).reshape(-1)
-    logp = np.take_along_axis(lsm, a[:, None], axis=-1)[:, 0]
-    p = np.exp(lsm)
-    ent = -(p * lsm).sum(axis=-1, dtype=dtype)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        lsm = _log_softmax(np.log(x)) if is_probs else _log_softmax(x)
+        a = np.asarray(actions).astype(np.int64).reshape(-1)
+        logp = np.take_along_axis(lsm, a[:, None], axis=-1)[:, 0]
+        p = np.exp(lsm)
+        # tfp's Categorical.entropy uses multiply_no_nan: a probability of exactly 0 contributes 0 (not 0 * -inf)
+        ent = -np.where(p > 0, p * lsm, dtype(0)).sum(axis=-1, dtype=dtype)
     return logp, ent, lsm
 
 

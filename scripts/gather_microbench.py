@@ -3,6 +3,7 @@
 XA_GATHER_* knobs, random vs identity permutation, bulk vs vector path, and a torch copy_ for scale."""
 import itertools
 import os
+os.environ.setdefault('XA_TUNING', '1')    # the XA_GATHER_* knobs are honoured only in tuning mode
 import sys
 
 import torch

@@ -2,6 +2,7 @@
 """Finer sweep of bytes-in-flight per SM for the bulk gather (stages x chunk), 20 reps each."""
 import itertools
 import os
+os.environ.setdefault('XA_TUNING', '1')    # the XA_GATHER_* knobs are honoured only in tuning mode
 import sys
 
 import torch

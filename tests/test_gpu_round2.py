@@ -1,0 +1,263 @@
+"""Round-2 parity cases: the C3-sized prepared pipeline against the oracle, the agents on the prepared pipelines, rollouts
+fed from host memory, devices other than cuda:0, the zero-probability branch of Categorical(probs=), the debug index
+check, and the fused peer-memory gradient all-reduce + Adam (2 GPUs)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from xagents_b200 import ops, synthetic
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+DEV = 'cuda:0'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(600)
+def test_hotpath_at_c3_size_vs_oracle():
+    """BASELINE config C3 itself (n_envs=256, n_steps=128, 4 epochs x 4 minibatches of 8192 frames, default launch
+    schedule [8, 4, 3, 1]) -- the exact object bench.py times -- against oracle.ppo_train_step: returns bit-exact, every
+    minibatch's loss / pg / value / entropy <= 1e-5, three sampled minibatches' gathered frames bit-exact."""
+    from xagents_b200.hotpath import PPOHotPath
+    T, E, K, M = 128, 256, 4, 4
+    ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=K, p_done=0.01)
+    want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
+                                 ro.permutations, ro.new_logits, ro.new_values, mini_batches=M, keep_states=False)
+    hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=M, device=DEV)
+    assert hp.group_sizes == [8, 4, 3, 1] and hp.B == 8192 and hp.n_mb == 16
+    hp.load(ro)
+    hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
+    for i, w in enumerate(want['minibatches']):
+        hp.actor_out[i].copy_(torch.as_tensor(ro.new_logits[w['idx']]))
+        hp.critic_out[i].copy_(torch.as_tensor(ro.new_values[w['idx']]))
+    hp.prepare()
+    sampled, kept = (0, 9, 15), {}
+
+    def after_loss(i):
+        if i in sampled:
+            kept[i] = hp.minibatch_views(i)[0].clone()
+
+    hp.run(after_loss=after_loss)
+    torch.cuda.synchronize()
+    assert np.array_equal(hp.returns.cpu().numpy(), want['returns'])
+    sc = hp.scalars.cpu().numpy()
+    for i, w in enumerate(want['minibatches']):
+        scale = max(abs(float(w[name])) for name in ('loss', 'pg', 'vl', 'entropy'))
+        for j, name in enumerate(('loss', 'pg', 'vl', 'entropy')):
+            assert abs(sc[i, j] - w[name]) <= REL * scale, (i, name, sc[i, j], w[name])
+    flat_obs = oracle.concat_step_batches(ro.obs)[0]                 # the reference's env-major flatten copy (base.py:559-564)
+    for i in sampled:
+        assert np.array_equal(kept[i].cpu().numpy(), flat_obs[want['minibatches'][i]['idx']])
+
+
+def _replay_agent(cls, T=16, E=8, A=6, shape=(8, 8, 4), seed=5, **kw):
+    """An agent over replayed environments and a tiny torch network (both deterministic)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(ROOT, 'tests', 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    from xagents_b200.agents import TorchModel
+    rng = np.random.default_rng(seed)
+    obs, rewards, dones, resets = mg._streams(rng, 4 * T, E, shape, True, 0.1)
+    envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Linear(int(np.prod(shape)), 32)
+            self.actor, self.critic = torch.nn.Linear(32, A), torch.nn.Linear(32, 1)
+
+        def forward(self, x):
+            h = torch.tanh(self.body(x.flatten(1)))
+            return self.actor(h), self.critic(h)
+
+    torch.manual_seed(seed)
+    net = TorchModel(Tiny().cuda())
+    return cls(envs, net, n_steps=T, quiet=True, seed=3, **kw), net
+
+
+def test_ppo_pipeline_equals_the_literal_minibatch_loop():
+    """run_ppo_epochs on the prepared pipeline (PPOHotPath in place over the agent's buffers) and the reference's literal loop
+    (a subclass overriding update_gradients falls back to it) train the same network to the same weights."""
+    from xagents_b200.agents import PPO
+
+    class Literal(PPO):
+        def update_gradients(self, *args):
+            return super().update_gradients(*args)
+
+    results = []
+    for cls in (PPO, Literal):
+        agent, net = _replay_agent(cls, mini_batches=4, ppo_epochs=2)
+        perms = [np.random.default_rng(k).permutation(agent.batch_size).astype(np.int32) for k in range(2)]
+        agent.permutation_source = lambda epoch: perms[epoch]
+        assert agent._pipeline_applies(*[None] * 5) is False
+        agent.train_step()
+        torch.cuda.synchronize()
+        assert (agent._pipeline is not None) == (cls is PPO)
+        results.append((net.flat_param.clone(), torch.stack(list(agent.loss_history)).cpu().numpy(), agent.ro_returns.clone()))
+    (p0, l0, r0), (p1, l1, r1) = results
+    assert torch.equal(r0, r1)
+    assert np.abs(l0 - l1).max() <= REL * np.abs(l1).max()
+    assert float((p0 - p1).abs().max()) <= 2e-5
+
+
+def test_train_step_fed_from_host_rollouts():
+    """feeds.HostRolloutFeed as rollout_source: PPO.train_step() and A2C.train_step() on rollouts uploaded from pinned host
+    buffers give what the oracle gives for those rollouts; agent.steps advances by n_steps * n_envs per step."""
+    from xagents_b200 import feeds
+    from xagents_b200.agents import A2C, PPO
+
+    class Table:                                    # model outputs are inputs (precomputed per sample, env-major ids)
+        output_is_softmax, comm = False, None
+
+        def __init__(self):
+            self.calls = []
+
+        def forward(self, states, training=True):
+            raise AssertionError('fed rollouts need no rollout-time forward')
+
+        def backward_and_step(self, d_actor, d_values, grad_norm=None):
+            self.calls.append((d_actor.clone(), d_values.clone()))
+
+    T, E, A, K, M = 12, 6, 5, 2, 3
+    rollouts = [synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), n_actions=A, epochs=K, p_done=0.1, seed=100 + k) for k in range(3)]
+    host = []
+    for ro in rollouts:
+        d = {k: torch.as_tensor(getattr(ro, k)).pin_memory() for k in ('obs', 'rewards', 'values', 'dones', 'actions', 'log_probs', 'last_values')}
+        host.append(d)
+    envs = feeds.FedEnvs(E, (84, 84, 4), torch.uint8, A, device=DEV)
+    model = Table()
+    agent = PPO(envs, model, n_steps=T, ppo_epochs=K, mini_batches=M, quiet=True)
+    feed = feeds.HostRolloutFeed(agent, lambda k: host[k] if k < len(host) else None)
+    agent.rollout_source = feed
+    state = {'k': 0}
+    agent.permutation_source = lambda epoch: rollouts[state['k']].permutations[epoch]
+
+    def forward_into(states, actor_dst, critic_dst, i):
+        ro = rollouts[state['k']]
+        idx = ro.permutations[i // M][(i % M) * (T * E // M):(i % M + 1) * (T * E // M)]
+        got = states.cpu().numpy()
+        assert np.array_equal(got, oracle.concat_step_batches(ro.obs)[0][idx])       # the staged frames are this minibatch's
+        actor_dst.copy_(torch.as_tensor(ro.new_logits[idx]))
+        critic_dst.copy_(torch.as_tensor(ro.new_values[idx]))
+    model.forward_into = forward_into
+    for k, ro in enumerate(rollouts):
+        state['k'] = k
+        agent.train_step()
+        torch.cuda.synchronize()
+        assert agent.steps == (k + 1) * T * E
+        want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
+                                     ro.permutations, ro.new_logits, ro.new_values, mini_batches=M)
+        assert np.array_equal(agent.ro_returns.cpu().numpy(), want['returns'])
+        for sc, w in zip(agent.loss_history, want['minibatches']):
+            scale = max(abs(float(w[name])) for name in ('loss', 'pg', 'vl', 'entropy'))
+            assert abs(float(sc[0]) - w['loss']) <= REL * scale
+    assert len(model.calls) == 3 * K * M
+    # A2C on the same feed mechanism
+    ro = rollouts[0]
+    model2 = Table()
+    a2c = A2C(feeds.FedEnvs(E, (84, 84, 4), torch.uint8, A, device=DEV), model2, n_steps=T, quiet=True)
+    a2c.rollout_source = feeds.HostRolloutFeed(a2c, lambda k: host[0])
+    tm_logits = np.ascontiguousarray(ro.new_logits.reshape(E, T, A).swapaxes(0, 1).reshape(T * E, A))     # env-major -> time-major
+    tm_values = np.ascontiguousarray(ro.new_values.reshape(E, T).T.reshape(-1))
+    model2.forward_into = lambda s, a, c, i: (a.copy_(torch.as_tensor(tm_logits)), c.copy_(torch.as_tensor(tm_values)))
+    a2c.train_step()
+    torch.cuda.synchronize()
+    ret = oracle.nstep_returns(ro.rewards, ro.dones, ro.last_values, 0.99)
+    assert np.array_equal(a2c.ro_returns.cpu().numpy(), ret)
+    logp, ent, _ = oracle.categorical_logp_entropy(tm_logits, ro.actions.reshape(-1))
+    want = oracle.a2c_loss(logp, tm_values, ent, ro.values.reshape(-1), ret.reshape(-1), 0.01, 0.5)
+    assert abs(float(a2c.loss_scalars[0]) - float(want['loss'])) <= REL * abs(float(want['loss']))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs of one box')
+def test_ops_and_pipeline_on_a_device_that_is_not_current():
+    """Tensors on cuda:1 while the process's current device stays cuda:0: launches follow the tensors' device."""
+    from xagents_b200.hotpath import PPOHotPath
+    assert torch.cuda.current_device() == 0
+    dev = 'cuda:1'
+    T, E = 16, 8
+    ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=1, p_done=0.05)
+    d = {k: torch.as_tensor(getattr(ro, k)).to(dev) for k in ('obs', 'rewards', 'values', 'last_values', 'dones')}
+    ret = ops.gae_returns(d['rewards'], d['values'], d['last_values'], d['dones'], 0.99, 0.95, mode='sequential')
+    want = oracle.gae_returns(ro.rewards, ro.dones, ro.values, ro.last_values, 0.99, 0.95)
+    assert ret.device == torch.device(dev) and np.array_equal(ret.cpu().numpy(), want)
+    idx = torch.as_tensor(ro.permutations[0]).to(dev)
+    rows = ops.gather_rows(d['obs'], idx, time_major=(T, E), mode='bulk')
+    assert np.array_equal(rows.cpu().numpy(), oracle.concat_step_batches(ro.obs)[0][ro.permutations[0]])
+    hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=1, mini_batches=4, device=dev)
+    hp.load(ro)
+    hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
+    hp.actor_out.normal_()
+    hp.critic_out.normal_()
+    hp.run()
+    torch.cuda.synchronize(dev)
+    assert torch.cuda.current_device() == 0 and np.array_equal(hp.returns.cpu().numpy(), want)
+    assert torch.isfinite(hp.scalars).all()
+
+
+def test_zero_probability_rows_stay_finite():
+    """Categorical(probs=) with a saturated softmax row (a probability of exactly 0): tfp's entropy uses multiply_no_nan;
+    the loss scalars, d_actor and the rollout sampler's entropy stay finite and agree with the oracle."""
+    n, A = 64, 4
+    rng = np.random.default_rng(3)
+    probs = rng.dirichlet(np.ones(A), n).astype(np.float32)
+    probs[::4] = np.eye(A, dtype=np.float32)[rng.integers(0, A, len(probs[::4]))]          # one-hot rows
+    actions = probs.argmax(-1).astype(np.float32)                                           # the taken action has p > 0
+    values, old_values, returns = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    old_logp = np.log(probs[np.arange(n), actions.astype(int)]) - 0.05
+    adv = rng.standard_normal(n).astype(np.float32)
+    cu = lambda x: torch.as_tensor(x).to(DEV)
+    sc, d_actor, d_values, _ = ops.ppo_loss(cu(probs), cu(values), cu(actions), cu(old_logp), cu(old_values), cu(returns),
+                                            advantages=cu(adv), actor_kind='probs')
+    logp, ent, _ = oracle.categorical_logp_entropy(probs, actions, True)
+    want = oracle.ppo_loss(logp, values, ent, old_values, returns, old_logp, adv, 0.1, 0.01, 0.5)
+    assert torch.isfinite(sc).all() and torch.isfinite(d_actor).all() and np.isfinite(ent).all()
+    scale = max(abs(float(want[k])) for k in ('loss', 'pg', 'vl', 'entropy'))
+    assert abs(float(sc[0]) - want['loss']) <= REL * scale and abs(float(sc[3]) - want['entropy']) <= REL * scale
+    _, _, ent_dev = ops.policy_step(cu(probs), actor_kind='probs', seed=1)
+    assert np.abs(ent_dev.cpu().numpy() - ent).max() <= 1e-5
+
+
+def test_debug_index_check_returns_einval_instead_of_faulting():
+    """XA_DEBUG_INDICES=1 (read once per process): an out-of-range index is reported as XA_EINVAL before the TMA gather runs."""
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from xagents_b200 import ops, _ffi\n"
+        "src = torch.zeros((16, 4096), dtype=torch.uint8, device='cuda')\n"
+        "ok = ops.gather_rows(src, torch.tensor([0, 15, 3], dtype=torch.int32, device='cuda'), mode='bulk')\n"
+        "try:\n"
+        "    ops.gather_rows(src, torch.tensor([0, 16, 3], dtype=torch.int32, device='cuda'), mode='bulk')\n"
+        "except _ffi.XAError as e:\n"
+        "    print('XAERR', e.code, e.message)\n"
+        "torch.cuda.synchronize(); print('ALIVE', int(torch.ones(1, device='cuda').item()))\n" % ROOT)
+    done = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, XA_DEBUG_INDICES='1'), capture_output=True, text=True, timeout=120)
+    assert done.returncode == 0, done.stderr[-2000:]
+    assert 'XAERR -1' in done.stdout and 'outside [0, 16)' in done.stdout and 'ALIVE 1' in done.stdout
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs of one box')
+def test_fused_peer_allreduce_adam_two_ranks():
+    """csrc/peer_adam.cu under torchrun x2: equals the oracle's clip_by_global_norm + Adam on the rank-averaged gradient,
+    weights bit-identical on both ranks, no wait timed out."""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(_free_port()), os.path.join(ROOT, 'scripts', 'peer_adam_check.py')]
+    done = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=280)
+    assert done.returncode == 0, done.stderr[-3000:]
+    out = json.loads([ln for ln in done.stdout.splitlines() if ln.startswith('{')][-1])
+    assert out['transport'] in ('symm', 'ipc'), out
+    assert out['parity_ok'] and out['weights_identical_across_ranks'] and out['status'] == 0 and out['status_after_timing'] == 0, out

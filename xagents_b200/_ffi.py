@@ -39,6 +39,19 @@ class LossArgs(ctypes.Structure):
     ]
 
 
+XA_MAX_PEERS = 8
+
+
+class PeerAdamArgs(ctypes.Structure):
+    """struct xa_peer_adam_args"""
+    _fields_ = [('grad', ctypes.c_void_p * XA_MAX_PEERS), ('param', ctypes.c_void_p * XA_MAX_PEERS),
+                ('sumsq', ctypes.c_void_p * XA_MAX_PEERS), ('flags', ctypes.c_void_p * XA_MAX_PEERS),
+                ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('workspace', ctypes.c_void_p), ('shard_len', ctypes.c_int64),
+                ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('epoch', ctypes.c_uint32), ('lr_t', ctypes.c_float),
+                ('beta1', ctypes.c_float), ('beta2', ctypes.c_float), ('eps', ctypes.c_float), ('clip', ctypes.c_float),
+                ('inv_world', ctypes.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/xagents_b200.h declares
 PROTOTYPES = {
     'xa_version': (ctypes.c_int, []),
@@ -89,6 +102,14 @@ PROTOTYPES = {
                                   ctypes.c_int, c_stream]),
     'xa_clip_adam_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64]),
     'xa_grad_sumsq_f32': (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_ipc_alloc': (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    'xa_ipc_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'xa_ipc_close': (ctypes.c_int, [ctypes.c_void_p]),
+    'xa_ipc_free': (ctypes.c_int, [ctypes.c_void_p]),
+    'xa_peer_adam_workspace_bytes': (ctypes.c_int64, []),
+    'xa_peer_adam_flag_bytes': (ctypes.c_int64, []),
+    'xa_peer_allreduce_adam_f32': (ctypes.c_int, [ctypes.POINTER(PeerAdamArgs)] + [ctypes.c_double] * 5 + [ctypes.c_int64, c_stream]),
+    'xa_grad_from_outputs_f32': (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int64, ctypes.c_int, c_f32p, ctypes.c_int64, c_stream]),
     'xa_clip_adam_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
                                                        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                                        ctypes.c_double, c_stream]),

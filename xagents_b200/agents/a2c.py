@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..hotpath import A2CHotPath
 from .base import OnPolicy
 from .models import adapt
 
@@ -29,6 +30,10 @@ class A2C(OnPolicy):
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(self.seed) if self.seed else 0)
         self._rng_offset = 0             # Philox counter offset of the in-kernel sampler
+        self.rollout_source = None       # rollouts produced elsewhere (feeds.HostRolloutFeed): callable(agent) that leaves a
+        #                                  complete rollout in the ro_* buffers and returns the bootstrap values [E]
+        self._fed_last_values = None
+        self._a2c_pipeline = None
         self._alloc_rollout()
 
     # ------------------------------------------------------------------ buffers
@@ -45,6 +50,7 @@ class A2C(OnPolicy):
         a_shape = (T, E) if self.discrete else (T, E, self.n_actions)
         self.ro_actions = torch.empty(a_shape, dtype=f32, device=dev)
         self.ro_actor = torch.empty((T, E, self.n_actions), dtype=f32, device=dev)
+        self.ro_returns = torch.empty((T, E), dtype=f32, device=dev)
         self.loss_scalars = torch.zeros(4, dtype=f32, device=dev)
 
     def _to_device(self, array, dtype=None):
@@ -69,7 +75,8 @@ class A2C(OnPolicy):
             return logp, torch.full_like(logp, 0.5 * k * (1.0 + log2pi))
         lsm = torch.log_softmax(torch.log(actor_out) if self.output_is_softmax else actor_out, dim=-1)
         logp = lsm.gather(-1, actions.long().view(-1, 1)).squeeze(-1)
-        return logp, -(lsm.exp() * lsm).sum(-1)
+        p = lsm.exp()
+        return logp, -torch.where(p > 0, p * lsm, torch.zeros_like(p)).sum(-1)     # multiply_no_nan (tfp Categorical.entropy)
 
     def sample_actions(self, actor_out):
         if not self.discrete:
@@ -98,6 +105,13 @@ class A2C(OnPolicy):
     def get_batch(self):
         """Run the environments for n_steps; returns the time-major device buffers
         [states, rewards, actions, critic_output, dones, log_probs, entropies, actor_output]."""
+        if self.rollout_source is not None:
+            # the rollout was produced elsewhere (host-side actors, a replay of recorded data): the feed uploads it into
+            # the time-major buffers and supplies the bootstrap values that `get_states()` would have been evaluated for
+            self._fed_last_values = self.rollout_source(self)
+            self.steps += self.n_steps * self.n_envs               # what step_envs counts (base.py:425)
+            return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
+                    self.ro_entropies, self.ro_actor]
         step_states, step_dones = self.get_states(), self.get_dones()
         for t in range(self.n_steps):
             states_d = self._to_device(step_states, self.obs_dtype)
@@ -116,13 +130,16 @@ class A2C(OnPolicy):
                 self.ro_entropies, self.ro_actor]
 
     def _bootstrap_values(self):
+        if self.rollout_source is not None:
+            return self._fed_last_values
         return self.get_model_outputs(self.get_states(), training=False, actions=self.ro_actions[0])[2]
 
     def calculate_returns(self, rewards, dones, values=None, selected_critic_logits=None, selected_importance=None):
         """n-step returns [T, E] (a2c/agent.py:141-171): bootstrap from the current states, then the scan kernel."""
         rewards = rewards if isinstance(rewards, torch.Tensor) else self._to_device(rewards, torch.float32)
         dones = dones if isinstance(dones, torch.Tensor) else self._to_device(dones, torch.float32)
-        return ops.nstep_returns(rewards, dones, self._bootstrap_values(), self.gamma)
+        out = self.ro_returns if tuple(rewards.shape) == tuple(self.ro_returns.shape) else None
+        return ops.nstep_returns(rewards, dones, self._bootstrap_values(), self.gamma, out=out)
 
     def np_train_step(self):
         states, rewards, actions, critic_output, dones, *_ = self.get_batch()
@@ -130,13 +147,41 @@ class A2C(OnPolicy):
         return self.concat_step_batches(states, returns, actions, critic_output)
 
     # ------------------------------------------------------------------ update (a2c/agent.py:190-218)
+    def hot_path(self):
+        """The agent's A2CHotPath (returns scan + fused loss, launch arguments resolved once) over the `ro_*` buffers."""
+        bound = dict(rewards=self.ro_rewards, values=self.ro_values, dones=self.ro_dones, actions=self.ro_actions,
+                     returns=self.ro_returns)
+        hp = self._a2c_pipeline
+        if hp is None:
+            hp = self._a2c_pipeline = A2CHotPath(self.n_steps, self.n_envs, self.n_actions, gamma=self.gamma,
+                                                 entropy_coef=self.entropy_coef, value_loss_coef=self.value_loss_coef,
+                                                 actor_kind=self.actor_kind, device=self.device, buffers=bound)
+        else:
+            moved = {name: t for name, t in bound.items() if getattr(hp, name).data_ptr() != t.data_ptr()}
+            if moved:
+                hp.bind(**moved)
+        stream = torch.cuda.current_stream(self.device)
+        if hp._args is None or hp.stream != stream:
+            hp.prepare(stream)
+        return hp
+
     def train_step(self):
         states, rewards, actions, old_values, dones, *_ = self.get_batch()
         returns = self.calculate_returns(rewards, dones)
+        if not isinstance(returns, torch.Tensor):
+            returns = self._to_device(returns, torch.float32)
+        if returns.data_ptr() != self.ro_returns.data_ptr():       # an overriding calculate_returns made its own tensor
+            self.ro_returns = returns.contiguous()
+        hp = self.hot_path()
         n = self.n_steps * self.n_envs
-        actor_out, critic = self.net.forward(states.reshape((n,) + self.input_shape), training=True)
-        flat_actions = actions.reshape(n) if self.discrete else actions.reshape(n, self.n_actions)
-        _, d_actor, d_values = ops.a2c_loss(actor_out, critic, flat_actions, old_values.reshape(n), returns.reshape(n),
-                                            entropy_coef=self.entropy_coef, value_loss_coef=self.value_loss_coef,
-                                            actor_kind=self.actor_kind, out=(self.loss_scalars, None, None, None))
-        self.net.backward_and_step(d_actor, d_values, self.grad_norm)
+        forward_into = getattr(self.net, 'forward_into', None)
+        flat_states = states.reshape((n,) + self.input_shape)
+        if forward_into is not None:
+            forward_into(flat_states, hp.actor_out, hp.critic_out, 0)
+        else:
+            actor_out, critic = self.net.forward(flat_states, training=True)
+            hp.actor_out.copy_(actor_out.reshape(n, -1))
+            hp.critic_out.copy_(critic.reshape(n))
+        hp.run(returns=False)                                      # fused loss forward + backward (a2c/agent.py:202-215)
+        self.loss_scalars = hp.scalars
+        self.net.backward_and_step(hp.d_actor, hp.d_values, self.grad_norm)

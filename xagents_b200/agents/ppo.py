@@ -1,13 +1,22 @@
 """PPO with the reference's surface (xagents/ppo/agent.py:6-225), hot path on the device.
 
 train_step() = get_batch() (rollout into time-major device buffers -> GAE kernel -> env-major *views*)
-followed by run_ppo_epochs() (per minibatch: permute-gather kernel, advantage moments + normalisation,
-model forward, fused loss forward+backward, model backward, fused clip+Adam).  Every replacement point of
-SURVEY.md §8b keeps its name and argument order, so subclasses that override one of them still compose.
+followed by run_ppo_epochs().  run_ppo_epochs() drives the prepared pipeline `hotpath.PPOHotPath` IN PLACE over the
+agent's own rollout buffers -- the pipeline bench.py measures: one advantage-moments launch for all K*M minibatches,
+the permute-gathers back to back on a data stream (double-buffered staging, several minibatches per launch), and per
+minibatch [model forward -> fused loss forward+backward reading the rollout scalars through the permutation ->
+model backward -> collective C1 -> fused clip+Adam] on the caller's stream, so the HBM-bound byte movement runs under
+the network instead of in front of it.
+
+Every replacement point of SURVEY.md §8b keeps its name and argument order.  A subclass (or instance) that overrides
+`get_mini_batches`, `update_gradients` or `_normalized_advantages`, or a caller that hands `run_ppo_epochs` arrays
+other than the agent's own rollout views, gets the reference's literal loop (`_run_ppo_epochs_generic`: per minibatch
+gather -> normalise -> update_gradients) on the same kernels.
 """
 import torch
 
 from .. import ops
+from ..hotpath import PPOHotPath
 from .a2c import A2C
 from .base import EnvMajorView
 
@@ -28,13 +37,16 @@ class PPO(A2C):
         self.permutation_source = None   # tests / parity runs: callable(epoch) -> int32 permutation of range(N)
         self.loss_history = []           # device tensors [4] = loss, pg, value loss, entropy per update
         self._workspace = ops.loss_workspace(self.mini_batch_size + self.mini_batches, self.device)
+        self.pipeline_options = {}       # PPOHotPath keywords (gather_mode, gather_chunk, staging, ...) for tuning runs
+        self._pipeline = None
 
     # ------------------------------------------------------------------ returns (ppo/agent.py:48-94)
     def calculate_returns(self, rewards, dones, values=None, selected_critic_logits=None, selected_importance=None):
         dev = lambda x: x if isinstance(x, torch.Tensor) else self._to_device(x, torch.float32)
         rewards, dones, values = dev(rewards), dev(dones), dev(values)
         values = values.reshape(rewards.shape)
-        return ops.gae_returns(rewards, values, self._bootstrap_values(), dones, self.gamma, self.lam)
+        out = self.ro_returns if tuple(rewards.shape) == tuple(self.ro_returns.shape) else None
+        return ops.gae_returns(rewards, values, self._bootstrap_values(), dones, self.gamma, self.lam, out=out)
 
     # ------------------------------------------------------------------ minibatches (ppo/agent.py:139-155)
     def _next_permutation(self, epoch):
@@ -86,7 +98,64 @@ class PPO(A2C):
             moments = moments[0]
         return ops.normalize_advantages(returns_mb, old_values_mb, self.advantage_epsilon, moments=moments)
 
+    # ---- the prepared pipeline (hotpath.PPOHotPath) over the agent's own buffers
+    _ROLLOUT_BINDINGS = (('obs', 'ro_states'), ('rewards', 'ro_rewards'), ('values', 'ro_values'), ('dones', 'ro_dones'),
+                         ('actions', 'ro_actions'), ('log_probs', 'ro_log_probs'), ('returns', 'ro_returns'))
+
+    def hot_path(self):
+        """The agent's PPOHotPath, bound to the current `ro_*` tensors and prepared on torch's current stream."""
+        bound = {name: getattr(self, attr) for name, attr in self._ROLLOUT_BINDINGS}
+        hp = self._pipeline
+        if hp is None:
+            hp = self._pipeline = PPOHotPath(
+                self.n_steps, self.n_envs, self.input_shape, self.n_actions, ppo_epochs=self.ppo_epochs,
+                mini_batches=self.mini_batches, gamma=self.gamma, lam=self.lam, clip_norm=self.clip_norm,
+                entropy_coef=self.entropy_coef, value_loss_coef=self.value_loss_coef,
+                advantage_epsilon=self.advantage_epsilon, actor_kind=self.actor_kind, device=self.device, comm=self.comm,
+                buffers=bound, **self.pipeline_options)
+        else:
+            moved = {name: t for name, t in bound.items() if getattr(hp, name).data_ptr() != t.data_ptr()}
+            if moved:                                              # a rollout feed swapped buffers (double-buffered uploads)
+                hp.bind(**moved)
+        stream = torch.cuda.current_stream(self.device)
+        if hp._calls is None or hp.compute_stream != stream:
+            hp.prepare(stream)
+        return hp
+
+    def _pipeline_applies(self, *batch):
+        names = ('get_mini_batches', 'update_gradients', '_normalized_advantages')
+        if any(getattr(type(self), n) is not getattr(PPO, n) or n in self.__dict__ for n in names):
+            return False
+        buffers = (self.ro_states, self.ro_actions, self.ro_returns, self.ro_values, self.ro_log_probs)
+        return len(batch) == 5 and all(isinstance(v, EnvMajorView) and v.tensor.data_ptr() == b.data_ptr()
+                                       and v.time_major == (self.n_steps, self.n_envs) for v, b in zip(batch, buffers))
+
     def run_ppo_epochs(self, states, actions, returns, old_values, old_log_probs):
+        if not self._pipeline_applies(states, actions, returns, old_values, old_log_probs):
+            return self._run_ppo_epochs_generic(states, actions, returns, old_values, old_log_probs)
+        hp, net = self.hot_path(), self.net
+        for epoch in range(self.ppo_epochs):                       # every epoch's shuffle up front: one moments launch
+            hp.perms[epoch].copy_(self._next_permutation(epoch))
+        forward_into = getattr(net, 'forward_into', None)
+
+        def forward(i):                                            # minibatch i is staged: model forward on it
+            n = hp.mb_rows[i]
+            states_mb = hp.mb_obs[hp._mb_place[i][1], hp._mb_place[i][2]:hp._mb_place[i][2] + n]
+            if forward_into is not None:
+                forward_into(states_mb, hp.actor_out[i, :n], hp.critic_out[i, :n], i)
+                return
+            actor_out, critic = net.forward(states_mb, training=True)
+            hp.actor_out[i, :n].copy_(actor_out.reshape(n, -1))
+            hp.critic_out[i, :n].copy_(critic.reshape(n))
+
+        def backward(i):                                           # loss i is queued: back-propagate its output gradients
+            n = hp.mb_rows[i]
+            net.backward_and_step(hp.d_actor[:n], hp.d_values[:n], self.grad_norm)
+
+        hp.run(gae=False, before_loss=forward, after_loss=backward)
+        self.loss_history[:] = [hp.scalars[i] for i in range(hp.n_mb)]
+
+    def _run_ppo_epochs_generic(self, states, actions, returns, old_values, old_log_probs):
         self.loss_history.clear()
         for states_mb, actions_mb, returns_mb, old_values_mb, old_log_probs_mb in self.get_mini_batches(
                 states, actions, returns, old_values, old_log_probs):
@@ -98,8 +167,11 @@ class PPO(A2C):
         """[states, actions, returns, values, log probs], env-major, as views over the time-major buffers."""
         states, rewards, actions, values, dones, log_probs, *_ = super().get_batch()
         returns = self.calculate_returns(rewards, dones, values)
-        self.ro_returns = returns
-        return self.concat_step_batches(states, actions, returns, values, log_probs)
+        if not isinstance(returns, torch.Tensor):
+            returns = self._to_device(returns, torch.float32)
+        if returns.data_ptr() != self.ro_returns.data_ptr():       # an overriding calculate_returns made its own tensor
+            self.ro_returns = returns.contiguous()
+        return self.concat_step_batches(states, actions, self.ro_returns, values, log_probs)
 
     def train_step(self):
         batch = self.get_batch()

@@ -37,6 +37,7 @@ struct GatherParams {
   int stages;
   int load_hint, store_hint;  // L2 evict-first policy on the bulk loads / stores
   // scalar fields riding along
+  int64_t n_src_rows;  // host-side checks only
   int n_fields;
   const float* fsrc[XA_MAX_FIELDS];
   float* fdst[XA_MAX_FIELDS];
@@ -188,6 +189,80 @@ __global__ void __launch_bounds__(256) gather_scaled_kernel(const GatherParams p
 }
 
 // ------------------------------------------------------------------------------------------ host
+// Tuning knobs of the bulk path (scripts/gather_microbench2.py sweeps them): honoured only when the process was started
+// with XA_TUNING=1 (checked once); the product path never calls getenv on a launch.
+struct BulkTuning {
+  int64_t max_chunk = 16 * 1024;        // rows are cut into equal 16-B-multiple chunks of at most this many bytes
+  int64_t target_inflight = 56 * 1024;  // bytes in flight per SM (ring size)
+  int stages = 0;                       // 0 = derived from target_inflight
+  int load_hint = 1, store_hint = 1;    // L2 evict-first on both sides (hinting only the loads measured 2 % slower)
+  int ctas_per_sm = 1;
+  explicit BulkTuning(bool from_env) {
+    if (!from_env) return;
+    if (const char* e = getenv("XA_GATHER_CHUNK")) max_chunk = atoll(e) > 0 ? atoll(e) : max_chunk;
+    if (const char* e = getenv("XA_GATHER_INFLIGHT")) target_inflight = atoll(e) > 0 ? atoll(e) : target_inflight;
+    if (const char* e = getenv("XA_GATHER_STAGES")) stages = atoi(e) > 0 && atoi(e) <= kMaxStages ? atoi(e) : 0;
+    if (const char* e = getenv("XA_GATHER_LOAD_HINT")) load_hint = atoi(e);
+    if (const char* e = getenv("XA_GATHER_STORE_HINT")) store_hint = atoi(e);
+    if (const char* e = getenv("XA_GATHER_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
+  }
+};
+
+struct GatherEnv {  // the two switches, read once (thread-safe static initialisation)
+  bool tuning = false, debug_indices = false;
+  GatherEnv() {
+    if (const char* e = getenv("XA_TUNING")) tuning = atoi(e) != 0;
+    if (const char* e = getenv("XA_DEBUG_INDICES")) debug_indices = atoi(e) != 0;
+  }
+};
+
+const GatherEnv& gather_env() {
+  static const GatherEnv e;
+  return e;
+}
+
+BulkTuning bulk_tuning() {  // tuning mode re-reads the knobs on every launch (the sweep scripts change them in-process)
+  return BulkTuning(gather_env().tuning);
+}
+
+// cudaFuncSetAttribute is per device: remember which devices already allow the bulk kernel its dynamic shared memory
+int allow_bulk_smem(const char* what) {
+  constexpr int kMaxDevices = 64;
+  static bool done[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (dev >= 0 && dev < kMaxDevices && done[dev]) return XA_OK;
+  cudaError_t e = cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (e != cudaSuccess) {
+    xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  if (dev >= 0 && dev < kMaxDevices) done[dev] = true;  // racing threads set the same attribute twice: harmless
+  return XA_OK;
+}
+
+// Debug aid (XA_DEBUG_INDICES=1): one bad index is an out-of-bounds TMA read and a sticky context error, so the check
+// runs as its own tiny kernel and the call returns XA_EINVAL instead of launching the gather.  Synchronises the stream.
+__global__ void check_indices_kernel(const int32_t* idx, int64_t n, int64_t n_rows, int* bad) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (idx[i] < 0 || idx[i] >= n_rows) atomicAdd(bad, 1);
+}
+
+int debug_check_indices(const int32_t* idx, int64_t n, int64_t n_rows, cudaStream_t stream, const char* what) {
+  int* bad = nullptr;
+  if (cudaMallocAsync(&bad, sizeof(int), stream) != cudaSuccess) return XA_OK;  // cannot check: do not block the caller
+  cudaMemsetAsync(bad, 0, sizeof(int), stream);
+  const int64_t want = (n + 255) / 256;
+  check_indices_kernel<<<static_cast<unsigned>(want < 1184 ? want : 1184), 256, 0, stream>>>(idx, n, n_rows, bad);
+  int host = 0;
+  cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  cudaStreamSynchronize(stream);
+  cudaFreeAsync(bad, stream);
+  XA_REQUIRE(host == 0, XA_EINVAL, "%s: %d of %lld indices are outside [0, %lld)", what, host, static_cast<long long>(n),
+             static_cast<long long>(n_rows));
+  return XA_OK;
+}
+
 int widest_vector(const GatherParams& p) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(p.src) | reinterpret_cast<uintptr_t>(p.dst) |
                          static_cast<uintptr_t>(p.row_bytes);
@@ -230,6 +305,8 @@ bool bulk_eligible(const GatherParams& p) {
 
 int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what) {
   if (p.n_idx == 0) return XA_OK;
+  if (gather_env().debug_indices)
+    if (int rc = debug_check_indices(p.idx, p.n_idx, p.n_src_rows, stream, what)) return rc;
   const bool can_bulk = bulk_eligible(p);
   if (mode == XA_GATHER_BULK)
     XA_REQUIRE(can_bulk, XA_EALIGN, "%s: XA_GATHER_BULK needs 16-byte aligned src, dst and row_bytes (row_bytes=%lld)", what,
@@ -240,41 +317,27 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
     // gather_microbench2.py, 32768 rows of 28224 B, random permutation) ~55 KB per SM peaks at 6.45 TB/s
     // (98 % of a plain copy) while 110-226 KB per SM falls to 5.9-6.0 TB/s.  So rows are cut into equal
     // 16-B-multiple chunks of <= 16 KB and the ring holds ~56 KB: 4 stages of half a frame for 84x84x4.
-    // (XA_GATHER_* environment variables are tuning knobs for the microbenchmarks.)
-    int64_t max_chunk = 16 * 1024;
-    int64_t target_inflight = 56 * 1024;
-    if (const char* e = getenv("XA_GATHER_CHUNK")) max_chunk = atoll(e) > 0 ? atoll(e) : max_chunk;
-    if (const char* e = getenv("XA_GATHER_INFLIGHT")) target_inflight = atoll(e) > 0 ? atoll(e) : target_inflight;
-    p.chunks_per_row = static_cast<int>((p.row_bytes + max_chunk - 1) / max_chunk);
+    // (XA_GATHER_* environment variables are tuning knobs for the microbenchmarks, honoured only under XA_TUNING=1.)
+    const BulkTuning tune = bulk_tuning();
+    p.chunks_per_row = static_cast<int>((p.row_bytes + tune.max_chunk - 1) / tune.max_chunk);
     int64_t chunk = (p.row_bytes + p.chunks_per_row - 1) / p.chunks_per_row;
     chunk = (chunk + 15) & ~int64_t(15);
     p.chunk_bytes = static_cast<uint32_t>(chunk);
-    int stages = static_cast<int>((target_inflight + chunk / 2) / chunk);
+    int stages = static_cast<int>((tune.target_inflight + chunk / 2) / chunk);
     if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
     while (stages > 1 && static_cast<int64_t>(stages) * chunk + 8 * kMaxStages > kSmemBudget) --stages;
-    if (const char* e = getenv("XA_GATHER_STAGES")) stages = atoi(e) > 0 && atoi(e) <= kMaxStages ? atoi(e) : stages;
+    if (tune.stages > 0 && static_cast<int64_t>(tune.stages) * chunk + 8 * kMaxStages <= kSmemBudget) stages = tune.stages;
     p.stages = stages;
-    p.load_hint = 1;   // evict-first on both sides (hinting only the loads measured 2 % slower than both or neither)
-    p.store_hint = 1;
-    if (const char* e = getenv("XA_GATHER_LOAD_HINT")) p.load_hint = atoi(e);
-    if (const char* e = getenv("XA_GATHER_STORE_HINT")) p.store_hint = atoi(e);
+    p.load_hint = tune.load_hint;
+    p.store_hint = tune.store_hint;
     const size_t smem = static_cast<size_t>(stages) * chunk + 8 * kMaxStages;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-      if (e != cudaSuccess) {
-        xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-        return static_cast<int>(e);
-      }
-      configured = kSmemBudget;
-    }
+    if (int rc = allow_bulk_smem(what)) return rc;
     const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
     const int ctas_per_sm = static_cast<int>(kSmemBudget / (smem + 1024)) > 0 ? static_cast<int>(kSmemBudget / (smem + 1024)) : 1;
     const int64_t items = p.n_idx * p.chunks_per_row;
     int64_t grid = (items + stages - 1) / stages;
-    int cta_cap = 1;
-    if (const char* e = getenv("XA_GATHER_CTAS")) cta_cap = atoi(e) > 0 && atoi(e) <= ctas_per_sm ? atoi(e) : cta_cap;
+    const int cta_cap = tune.ctas_per_sm <= ctas_per_sm ? tune.ctas_per_sm : ctas_per_sm;
     const int64_t cap = static_cast<int64_t>(sms) * cta_cap;
     if (grid > cap) grid = cap;
     gather_bulk_kernel<<<static_cast<unsigned>(grid), 32 * (stages + 1), smem, stream>>>(p);
@@ -310,6 +373,7 @@ int fill_common(GatherParams& p, const char* what, const void* src, const int32_
   p.row_bytes = row_bytes;
   p.n_steps = n_steps;
   p.n_envs = n_envs;
+  p.n_src_rows = n_src_rows;
   return XA_OK;
 }
 

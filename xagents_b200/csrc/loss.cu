@@ -112,6 +112,10 @@ __global__ void __launch_bounds__(256) normalize_adv_kernel(const NormParams p) 
   }
 }
 
+// p * x with tfp's multiply_no_nan rule (Categorical.entropy): a probability of exactly 0 -- a saturated softmax-output
+// model, Categorical(probs=) -- contributes 0, not 0 * (-inf) = NaN
+__device__ __forceinline__ float plogp(float p, float x) { return p > 0.0f ? p * x : 0.0f; }
+
 struct LossWorkspace {  // layout of xa_loss_args.workspace
   unsigned int ticket;
   unsigned int pad[3];
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const xa_loss_args a
         for (int j = 0; j < kRegActions; ++j)
           if (j < A) {
             lsm[j] = (lsm[j] - zmax) - lse;
-            ent -= expf(lsm[j]) * lsm[j];
+            ent -= plogp(expf(lsm[j]), lsm[j]);
             if (j == act) logp = lsm[j];
           }
       } else {
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const xa_loss_args a
         logp = 0.0f;
         for (int j = 0; j < A; ++j) {
           const float l = ((kActorKind == XA_ACTOR_PROBS ? logf(actor[j]) : actor[j]) - zmax) - lse;
-          ent -= expf(l) * l;
+          ent -= plogp(expf(l), l);
           if (j == act) logp = l;
         }
       }
@@ -253,16 +257,16 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const xa_loss_args a
           if (j < A) {
             const float pj = expf(lsm[j]);
             // g*(onehot - p) + c_e * p * (lsm + H)        
-            float g = (g_logp * ((j == act ? 1.0f : 0.0f) - pj) + a.ent_coef * pj * (lsm[j] + ent)) * inv_n;
-            if (kActorKind == XA_ACTOR_PROBS) g = __fdiv_rn(g, actor[j]);  // chain through logits = log(probs)
+            float g = (g_logp * ((j == act ? 1.0f : 0.0f) - pj) + a.ent_coef * plogp(pj, lsm[j] + ent)) * inv_n;
+            if (kActorKind == XA_ACTOR_PROBS) g = actor[j] > 0.0f ? __fdiv_rn(g, actor[j]) : 0.0f;  // chain through logits = log(probs)
             d_actor[j] = g;
           }
       } else {
         for (int j = 0; j < A; ++j) {
           const float l = ((kActorKind == XA_ACTOR_PROBS ? logf(actor[j]) : actor[j]) - zmax) - lse;
           const float pj = expf(l);
-          float g = (g_logp * ((j == act ? 1.0f : 0.0f) - pj) + a.ent_coef * pj * (l + ent)) * inv_n;
-          if (kActorKind == XA_ACTOR_PROBS) g = __fdiv_rn(g, actor[j]);
+          float g = (g_logp * ((j == act ? 1.0f : 0.0f) - pj) + a.ent_coef * plogp(pj, l + ent)) * inv_n;
+          if (kActorKind == XA_ACTOR_PROBS) g = actor[j] > 0.0f ? __fdiv_rn(g, actor[j]) : 0.0f;
           d_actor[j] = g;
         }
       }

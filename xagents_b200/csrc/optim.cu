@@ -98,6 +98,20 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a)
     adam_one(a.param[i], a.grad[i], a.m[i], a.v[i], a, scale);
 }
 
+// Benchmark stand-in for the network's backward pass (bench.py; the metric excludes the network contractions): every
+// "parameter gradient" is a fixed combination of the loss kernel's outputs, so the flat gradient buffer -- the input of
+// collective C1 and of the optimiser -- is PRODUCED by a kernel that consumes d loss / d(actor_out, critic_out) of this
+// minibatch, as in training.  6.75 MB written per call for the Nature CNN's 1.69 M parameters.
+__global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float* __restrict__ d_actor, const float* __restrict__ d_values,
+                                                                     int64_t n, int n_actions, float* __restrict__ grad, int64_t n_params) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const int64_t na = n * n_actions;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < n_params; j += stride) {
+    const float a = __ldg(d_actor + j % na), v = __ldg(d_values + j % n);
+    grad[j] = a + 0.5f * v;
+  }
+}
+
 unsigned blocks_for(int64_t n) {
   const int64_t want = (n + kThreads * kVec - 1) / (kThreads * kVec);
   return static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
@@ -119,6 +133,17 @@ int xa_grad_sumsq_f32(const float* grads, int64_t n, void* workspace, int64_t wo
   XA_REQUIRE(xa::aligned(grads, 16) && xa::aligned(workspace, 16), XA_EALIGN, "xa_grad_sumsq_f32: 16-byte alignment required");
   grad_sumsq_kernel<<<blocks_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(grads, n, static_cast<OptimWorkspace*>(workspace));
   return xa::check_launch("xa_grad_sumsq_f32");
+}
+
+int xa_grad_from_outputs_f32(const float* d_actor, const float* d_values, int64_t n, int n_actions, float* grad, int64_t n_params,
+                             xa_stream_t stream) {
+  XA_REQUIRE(d_actor && d_values && grad, XA_EINVAL, "xa_grad_from_outputs_f32: null pointer");
+  XA_REQUIRE(n > 0 && n_actions > 0 && n_params > 0, XA_EINVAL, "xa_grad_from_outputs_f32: n=%lld n_actions=%d n_params=%lld",
+             static_cast<long long>(n), n_actions, static_cast<long long>(n_params));
+  const int64_t want = (n_params + kThreads - 1) / kThreads;
+  grad_from_outputs_kernel<<<static_cast<unsigned>(want > kMaxBlocks ? kMaxBlocks : want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_actor, d_values, n, n_actions, grad, n_params);
+  return xa::check_launch("xa_grad_from_outputs_f32");
 }
 
 int xa_clip_adam_f32(float* param, const float* grad, float* m, float* v, int64_t n, const void* workspace, double lr,

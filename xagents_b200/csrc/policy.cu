@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) 
   int arg = 0;
   for (int j = 0; j < A; ++j) {
     const float l = ((kActorKind == XA_ACTOR_PROBS ? logf(row[j]) : row[j]) - zmax) - lse;
-    ent -= expf(l) * l;
+    const float pl = expf(l);
+    ent -= pl > 0.0f ? pl * l : 0.0f;  // tfp's multiply_no_nan: a probability of exactly 0 contributes 0, not NaN
     const float u = p.noise ? p.noise[i * A + j] : u01(draw(j));
     const float score = l - logf(-logf(u));  // Gumbel-max
     if (score > best) {

@@ -46,9 +46,12 @@ class PPOHotPath:
     def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
                  gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
                  actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
-                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None):
+                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None):
+        """`buffers`: existing time-major device tensors to run on instead of allocating (any of ROLLOUT_FIELDS and
+        'returns') -- the agents pass their own `ro_*` rollout buffers, so the pipeline works in place (no copies)."""
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
         self.N = self.T * self.E
+        obs_dtype = buffers['obs'].dtype if buffers and 'obs' in buffers else obs_dtype
         self.K, self.M = int(ppo_epochs), int(mini_batches)
         self.B = self.N // self.M                                  # mini_batch_size (ppo/agent.py:42-46)
         assert self.B > 0, f'Invalid batch size to mini-batch size ratio {self.N}: {self.M}'
@@ -60,6 +63,8 @@ class PPOHotPath:
         self.value_loss_coef, self.advantage_epsilon = float(value_loss_coef), float(advantage_epsilon)
         self.actor_kind = actor_kind
         self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.gather_mode, self.scan_mode = gather_mode, scan_mode
         self.comm = comm
         self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
@@ -99,15 +104,19 @@ class PPOHotPath:
         self.cap = max(self.group_rows)
         dev, f32 = self.device, torch.float32
         T, E, N, B, A = self.T, self.E, self.N, self.B, self.A
+        if comm is not None and comm.world_size > 1:
+            # equal shards: the loss divides by the LOCAL minibatch size and the gradients are averaged over ranks (a mean
+            # of per-rank means is the global mean only then), and every rank must issue the same number of collectives
+            assert comm.max_over_ranks(N) == N and comm.max_over_ranks(-N) == -N, (
+                f'sharded PPO needs the same n_steps * n_envs on every rank (this rank: {N})')
         # rollout, time-major (what the rollout loop writes step by step)
-        self.obs = torch.empty((T, E) + self.obs_shape, dtype=obs_dtype, device=dev)
-        self.rewards = torch.empty((T, E), dtype=f32, device=dev)
-        self.values = torch.empty((T, E), dtype=f32, device=dev)
-        self.last_values = torch.empty((E,), dtype=f32, device=dev)
-        self.dones = torch.empty((T + 1, E), dtype=f32, device=dev)
-        self.actions = torch.empty((T, E), dtype=f32, device=dev)
-        self.log_probs = torch.empty((T, E), dtype=f32, device=dev)
-        self.returns = torch.empty((T, E), dtype=f32, device=dev)
+        shapes = {'obs': ((T, E) + self.obs_shape, obs_dtype), 'rewards': ((T, E), f32), 'values': ((T, E), f32),
+                  'last_values': ((E,), f32), 'dones': ((T + 1, E), f32), 'actions': ((T, E), f32), 'log_probs': ((T, E), f32),
+                  'returns': ((T, E), f32)}
+        for name, (shape, dtype) in shapes.items():
+            setattr(self, name, torch.empty(shape, dtype=dtype, device=dev) if not (buffers and name in buffers) else None)
+        if buffers:
+            self.bind(**buffers)
         # permutations of env-major flat sample ids, one row per epoch
         self.perms = torch.empty((self.K, N), dtype=torch.int32, device=dev)
         # minibatch staging
@@ -127,6 +136,7 @@ class PPOHotPath:
         nbytes = _ffi.lib().xa_loss_workspace_bytes(B)
         self.workspace = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
         self._calls = None
+        self.on_gather = None          # default `on_gather` hook of run() (bench.py times the gather launches through it)
         self.row_bytes = self.obs.element_size()
         for k in self.obs_shape:
             self.row_bytes *= k
@@ -139,6 +149,26 @@ class PPOHotPath:
         return n
 
     # ---------------------------------------------------------------------------------- data in
+    def bind(self, **buffers):
+        """Run on the caller's rollout tensors (time-major, contiguous, on this device).  Continuous actions may be
+        [T, E, k] (read through the permutation by the loss; they cannot ride along as a gathered scalar field)."""
+        T, E = self.T, self.E
+        for name, t in buffers.items():
+            assert name in self.ROLLOUT_FIELDS + ('returns',), f'unknown rollout field `{name}`'
+            assert t.is_contiguous() and t.device == self.device, f'{name}: need a contiguous tensor on {self.device}'
+            lead = (E,) if name == 'last_values' else ((T + 1, E) if name == 'dones' else (T, E))
+            assert tuple(t.shape[:len(lead)]) == lead, f'{name}: shape {tuple(t.shape)} is not time-major {lead}'
+            if name == 'obs':
+                assert tuple(t.shape[2:]) == self.obs_shape, f'obs rows {tuple(t.shape[2:])} != {self.obs_shape}'
+            elif name == 'actions':
+                assert t.dim() == 2 or self.fuse_fields, 'vector actions need fuse_fields=True'
+                assert t.dtype == torch.float32
+            else:
+                assert t.dtype == torch.float32 and t.dim() == len(lead), f'{name}: need fp32 {lead}'
+            setattr(self, name, t)
+        self._calls = None
+        return self
+
     ROLLOUT_FIELDS = ('obs', 'rewards', 'values', 'last_values', 'dones', 'actions', 'log_probs')
 
     def load(self, rollout, stream=None, non_blocking=True):
@@ -237,28 +267,36 @@ class PPOHotPath:
         if rc != 0:
             raise _ffi.XAError(tag, rc, _ffi.lib().xa_last_error().decode('utf-8', 'replace'))
 
-    def run(self, on_gather=None, after_loss=None):
+    def run(self, on_gather=None, after_loss=None, before_loss=None, gae=True):
         """Issue one train step.  `on_gather(i, fn, args)` may wrap gather i (bench timing, on
-        `self.data_stream`); `after_loss(i)` runs after minibatch i's loss was enqueued on the compute
-        stream (model backward / collective C1)."""
+        `self.data_stream`); `before_loss(i)` runs on the compute stream once minibatch i is staged and must
+        leave the model outputs in `actor_out[i]` / `critic_out[i]` (model forward); `after_loss(i)` runs after
+        minibatch i's loss was enqueued (model backward from `d_actor` / `d_values`, collective C1, optimiser).
+        `gae=False`: `returns` already holds this rollout's returns (the agents' `calculate_returns` wrote them)."""
         if self._calls is None:
             self.prepare()
+        if self.device.type == 'cuda' and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):                    # launches go to the CUDA runtime's current device
+                return self.run(on_gather, after_loss, before_loss, gae)
         cs, ds = self.compute_stream, self.data_stream
         two = ds is not cs
+        on_gather = on_gather if on_gather is not None else self.on_gather
         # the data stream joins after everything already queued on the compute stream (rollout writes,
         # the previous step) -- and after GAE only when the gathers carry the returns field
         if two and self.fuse_fields:
             self._fork.record(cs)
             ds.wait_event(self._fork)
-        fn, args = self._gae
-        self._check('gae', fn(*args))
+        if gae:
+            fn, args = self._gae
+            self._check('gae', fn(*args))
         if two and not self.fuse_fields:
             self._fork.record(cs)
             ds.wait_event(self._fork)
         fn, args = self._moments
         self._check('moments', fn(*args))
         if self.comm is not None and self.comm.world_size > 1:
-            self.comm.all_gather_moments(self.all_moments, self.moments)        # collective C2
+            with torch.cuda.stream(cs):                                         # ordered between the moments and the losses
+                self.comm.all_gather_moments(self.all_moments, self.moments)    # collective C2
         for g in range(self.n_groups):
             fn, args = self._gathers[g]
             if two and g >= self.staging:
@@ -268,6 +306,8 @@ class PPOHotPath:
                 self._gather_done[g].record(ds)
                 cs.wait_event(self._gather_done[g])
             for i in range(self.group_first[g], self.group_first[g] + self.group_sizes[g]):
+                if before_loss is not None:
+                    before_loss(i)
                 fn, args = self._losses[i]
                 self._check('loss', fn(*args))
                 if after_loss is not None:
@@ -333,20 +373,22 @@ class A2CHotPath:
     over the batch, so the env-major flatten of np_train_step changes nothing but the summation order).
     Two launches per train step."""
 
+    FIELDS = ('rewards', 'values', 'last_values', 'dones', 'actions', 'returns')
+
     def __init__(self, n_steps, n_envs, n_actions, *, gamma=0.99, entropy_coef=0.01, value_loss_coef=0.5, actor_kind='logits',
-                 device='cuda:0', scan_mode='auto'):
+                 device='cuda:0', scan_mode='auto', buffers=None):
+        """`buffers`: the caller's time-major rollout tensors (any of FIELDS) to work on in place, as in PPOHotPath."""
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
         self.N = self.T * self.E
         self.gamma, self.entropy_coef, self.value_loss_coef = float(gamma), float(entropy_coef), float(value_loss_coef)
         self.actor_kind, self.scan_mode = actor_kind, scan_mode
         self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         dev, f32, T, E, N, A = self.device, torch.float32, self.T, self.E, self.N, self.A
-        self.rewards = torch.empty((T, E), dtype=f32, device=dev)
-        self.values = torch.empty((T, E), dtype=f32, device=dev)
-        self.last_values = torch.empty((E,), dtype=f32, device=dev)
-        self.dones = torch.empty((T + 1, E), dtype=f32, device=dev)
-        self.actions = torch.empty((T, E), dtype=f32, device=dev)
-        self.returns = torch.empty((T, E), dtype=f32, device=dev)
+        shapes = {'rewards': (T, E), 'values': (T, E), 'last_values': (E,), 'dones': (T + 1, E), 'actions': (T, E), 'returns': (T, E)}
+        for name, shape in shapes.items():
+            setattr(self, name, torch.empty(shape, dtype=f32, device=dev) if not (buffers and name in buffers) else None)
         self.actor_out = torch.empty((N, A), dtype=f32, device=dev)       # forward pass outputs, time-major sample order
         self.critic_out = torch.empty((N,), dtype=f32, device=dev)
         self.scalars = torch.zeros(4, dtype=f32, device=dev)
@@ -356,6 +398,17 @@ class A2CHotPath:
         self.workspace = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
         self.kernel_launches_per_step = 2
         self._args = None
+        if buffers:
+            self.bind(**buffers)
+
+    def bind(self, **buffers):
+        for name, t in buffers.items():
+            assert name in self.FIELDS, f'unknown rollout field `{name}`'
+            assert t.is_contiguous() and t.device == self.device and t.dtype == torch.float32, (
+                f'{name}: need a contiguous fp32 tensor on {self.device}')
+            setattr(self, name, t)
+        self._args = None
+        return self
 
     def prepare(self, stream=None):
         lib = _ffi.lib()
@@ -375,10 +428,17 @@ class A2CHotPath:
         self._loss = (lib.xa_a2c_loss_f32, (ctypes.byref(a), s))
         return self
 
-    def run(self):
+    def run(self, returns=True, loss=True):
+        """`returns=False`: `self.returns` is already filled (the agent's `calculate_returns` wrote it); `loss=False`: only the
+        returns scan (the model forward, which the loss needs, comes after it in A2C.train_step)."""
         if self._args is None:
             self.prepare()
-        for tag, (fn, args) in (('nstep_returns', self._returns), ('a2c_loss', self._loss)):
+        if self.device.type == 'cuda' and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.run(returns, loss)
+        for tag, on, (fn, args) in (('nstep_returns', returns, self._returns), ('a2c_loss', loss, self._loss)):
+            if not on:
+                continue
             rc = fn(*args)
             if rc != 0:
                 raise _ffi.XAError(tag, rc, _ffi.lib().xa_last_error().decode('utf-8', 'replace'))

@@ -15,7 +15,7 @@ from ._ffi import (XA_ACTOR_LOGITS, XA_ACTOR_NORMAL, XA_ACTOR_PROBS, XA_GATHER_A
                    XA_MAX_FIELDS, XA_MOMENT_STRIDE, XA_SCAN_AUTO, XA_SCAN_CHUNKED, XA_SCAN_SEQUENTIAL)
 
 __all__ = ['gae_returns', 'nstep_returns', 'retrace_returns', 'gather_rows', 'gather_fields', 'gather_minibatch', 'gather_rows_scaled',
-           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb', 'gather_cast_f32',
+           'policy_step', 'adv_moments', 'normalize_advantages', 'ppo_loss', 'a2c_loss', 'loss_workspace', 'grad_sumsq', 'grad_from_outputs', 'clip_adam', 'optim_workspace', 'gemm_bf16_tn', 'to_bf16', 'conv2d_nhwc_bf16', 'space_to_depth_u8_bf16', 'gather_s2d_u8_bf16', 'conv_wgrad_nhwc_bf16', 'gemm_bf16_atb', 'gather_cast_f32',
            'launch_count', 'reset_launch_count']
 
 SCAN_MODES = {'auto': XA_SCAN_AUTO, 'sequential': XA_SCAN_SEQUENTIAL, 'chunked': XA_SCAN_CHUNKED}
@@ -39,10 +39,22 @@ def _count(n=1):
     _launches += n
 
 
-def _stream(stream):
+def _stream(stream, device=None):
     if stream is None:
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(device).cuda_stream
     return getattr(stream, 'cuda_stream', stream)
+
+
+def _call(arr, fn_name, *args):
+    """Launch on the device that owns `arr` (a DeviceArray): the kernels go to the CUDA runtime's CURRENT device, so a tensor
+    on cuda:1 in a process whose current device is cuda:0 needs the switch (and that device's current stream).  The last
+    argument is the caller's `stream` (None = torch's current stream on that device)."""
+    index = arr.device_id
+    stream = args[-1]
+    if index == torch.cuda.current_device():
+        return _ffi.call(fn_name, *args[:-1], _stream(stream, index))
+    with torch.cuda.device(index):
+        return _ffi.call(fn_name, *args[:-1], _stream(stream, index))
 
 
 def _dev(x, dtype=None):
@@ -79,8 +91,8 @@ def gae_returns(rewards, values, last_values, dones, gamma, lam, *, mode='auto',
     dev = _device_of(r)
     ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=dev)
     adv = torch.empty((T, E), dtype=torch.float32, device=dev) if with_advantages else None
-    _ffi.call('xa_gae_f32', _ptr(r), _ptr(v), _ptr(lv), _ptr(d), _tptr(ret), _tptr(adv), T, E, float(gamma), float(lam),
-              SCAN_MODES[mode], _stream(stream))
+    _call(r, 'xa_gae_f32', _ptr(r), _ptr(v), _ptr(lv), _ptr(d), _tptr(ret), _tptr(adv), T, E, float(gamma), float(lam),
+              SCAN_MODES[mode], stream)
     _count()
     return (ret, adv) if with_advantages else ret
 
@@ -94,8 +106,8 @@ def nstep_returns(rewards, dones, last_values, gamma, *, mode='auto', out=None, 
     if lv.size != E or d.size != (T + 1) * E:
         raise ValueError(f'shape mismatch: rewards {r.shape}, last_values {lv.shape}, dones {d.shape}')
     ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=_device_of(r))
-    _ffi.call('xa_nstep_returns_f32', _ptr(r), _ptr(d), _ptr(lv), _tptr(ret), T, E, float(gamma), SCAN_MODES[mode],
-              _stream(stream))
+    _call(r, 'xa_nstep_returns_f32', _ptr(r), _ptr(d), _ptr(lv), _tptr(ret), T, E, float(gamma), SCAN_MODES[mode],
+              stream)
     _count()
     return ret
 
@@ -107,7 +119,7 @@ def retrace_returns(rewards, dones, values, last_values, q_selected, importance,
     if arrs[1].size != (T + 1) * E or arrs[3].size != E or any(a.size != T * E for a in (arrs[2], arrs[4], arrs[5])):
         raise ValueError('shape mismatch: [T,E] fields, dones [T+1,E], last_values [E]')
     ret = out if out is not None else torch.empty((T, E), dtype=torch.float32, device=_device_of(arrs[0]))
-    _ffi.call('xa_retrace_f32', *[_ptr(a) for a in arrs], _tptr(ret), T, E, float(gamma), _stream(stream))
+    _call(arrs[0], 'xa_retrace_f32', *[_ptr(a) for a in arrs], _tptr(ret), T, E, float(gamma), stream)
     _count()
     return ret
 
@@ -142,7 +154,7 @@ def gather_rows(src, idx, *, time_major=None, mode='auto', out=None, stream=None
         row_bytes *= k
     n = i.size
     dst = out if out is not None else torch.empty((n,) + tuple(row_shape), dtype=_torch_dtype(s.dtype), device=_device_of(s))
-    _ffi.call('xa_gather_rows', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, GATHER_MODES[mode], _stream(stream))
+    _call(s, 'xa_gather_rows', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, GATHER_MODES[mode], stream)
     _count()
     return dst
 
@@ -163,7 +175,7 @@ def gather_fields(fields, idx, *, time_major=None, out=None, stream=None):
     i = _dev(idx, 'int32')
     T, E = _layout(time_major)
     arrs, outs, src, dst = _field_tables(fields, out, i.size, _device_of(i))
-    _ffi.call('xa_gather_fields_f32', src, dst, len(arrs), _ptr(i), i.size, T, E, _stream(stream))
+    _call(i, 'xa_gather_fields_f32', src, dst, len(arrs), _ptr(i), i.size, T, E, stream)
     _count()
     return outs
 
@@ -182,8 +194,8 @@ def gather_minibatch(obs, fields, idx, *, time_major=None, mode='auto', out_obs=
     dev = _device_of(s)
     dst = out_obs if out_obs is not None else torch.empty((n,) + tuple(row_shape), dtype=_torch_dtype(s.dtype), device=dev)
     arrs, outs, fsrc, fdst = _field_tables(fields, out_fields, n, dev)
-    _ffi.call('xa_gather_minibatch', _ptr(s), _tptr(dst), row_bytes, n_rows, fsrc, fdst, len(arrs), _ptr(i), n, T, E,
-              GATHER_MODES[mode], _stream(stream))
+    _call(s, 'xa_gather_minibatch', _ptr(s), _tptr(dst), row_bytes, n_rows, fsrc, fdst, len(arrs), _ptr(i), n, T, E,
+              GATHER_MODES[mode], stream)
     # bulk path: one kernel; vector path: rows kernel + fields kernel
     _count(1 if (mode == 'bulk' or (mode == 'auto' and row_bytes >= 2048 and row_bytes % 16 == 0)) else 1 + (len(arrs) > 0))
     return dst, outs
@@ -201,7 +213,7 @@ def gather_rows_scaled(src_u8, idx, *, time_major=None, out=None, stream=None):
         row_bytes *= k
     n = i.size
     dst = out if out is not None else torch.empty((n,) + tuple(row_shape), dtype=torch.float32, device=_device_of(s))
-    _ffi.call('xa_gather_rows_u8_scaled_f32', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, _stream(stream))
+    _call(s, 'xa_gather_rows_u8_scaled_f32', _ptr(s), _ptr(i), _tptr(dst), n, row_bytes, n_rows, T, E, stream)
     _count()
     return dst
 
@@ -221,8 +233,8 @@ def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0,
     if ent is None:
         ent = torch.empty((n,), dtype=torch.float32, device=dev)
     nz = _dev(noise, 'float32') if noise is not None else None
-    _ffi.call('xa_policy_step_f32', _ptr(ao), ACTOR_KINDS[actor_kind], _ptr(nz), int(seed), int(offset), _tptr(actions),
-              _tptr(logp), _tptr(ent), n, A, _stream(stream))
+    _call(ao, 'xa_policy_step_f32', _ptr(ao), ACTOR_KINDS[actor_kind], _ptr(nz), int(seed), int(offset), _tptr(actions),
+              _tptr(logp), _tptr(ent), n, A, stream)
     _count()
     return actions, logp, ent
 
@@ -237,7 +249,7 @@ def adv_moments(returns, old_values, idx, mb_offsets, *, time_major=None, out=No
     n_mb = len(mb_offsets) - 1
     offs = (ctypes.c_int64 * (n_mb + 1))(*[int(o) for o in mb_offsets])
     mom = out if out is not None else torch.empty((n_mb, XA_MOMENT_STRIDE), dtype=torch.float64, device=_device_of(r))
-    _ffi.call('xa_adv_moments_f32', _ptr(r), _ptr(v), _ptr(i), offs, n_mb, T, E, _tptr(mom), _stream(stream))
+    _call(r, 'xa_adv_moments_f32', _ptr(r), _ptr(v), _ptr(i), offs, n_mb, T, E, _tptr(mom), stream)
     _count((n_mb + 63) // 64)
     return mom
 
@@ -255,8 +267,8 @@ def normalize_advantages(returns_mb, old_values_mb, advantage_epsilon=1e-8, *, i
     mom = _dev(moments, 'float64')
     parts = 1 if len(mom.shape) == 1 else mom.shape[0]
     adv = out if out is not None else torch.empty((n,), dtype=torch.float32, device=_device_of(r))
-    _ffi.call('xa_normalize_adv_f32', _ptr(r), _ptr(v), _ptr(i), n, T, E, _ptr(mom), parts, mom.shape[-1] if parts > 1 else 0,
-              float(advantage_epsilon), _tptr(adv), _stream(stream))
+    _call(r, 'xa_normalize_adv_f32', _ptr(r), _ptr(v), _ptr(i), n, T, E, _ptr(mom), parts, mom.shape[-1] if parts > 1 else 0,
+              float(advantage_epsilon), _tptr(adv), stream)
     _count()
     return adv
 
@@ -321,7 +333,7 @@ def _loss(fn, ppo, actor_out, values, actions, old_log_probs, old_values, return
     args.out_scalars, args.d_actor, args.d_values = scalars.data_ptr(), _tptr(d_actor), _tptr(d_values)
     args.advantages_out = _tptr(adv_out)
     args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
-    _ffi.call(fn, ctypes.byref(args), _stream(stream))
+    _call(ao, fn, ctypes.byref(args), stream)
     _count()
     return scalars, d_actor, d_values, adv_out
 
@@ -360,7 +372,7 @@ def optim_workspace(device):
 
 def grad_sumsq(grads, workspace, *, stream=None):
     g = _dev(grads, 'float32')
-    _ffi.call('xa_grad_sumsq_f32', _ptr(g), g.size, workspace.data_ptr(), workspace.numel() * 8, _stream(stream))
+    _call(g, 'xa_grad_sumsq_f32', _ptr(g), g.size, workspace.data_ptr(), workspace.numel() * 8, stream)
     _count()
 
 
@@ -373,8 +385,15 @@ def clip_adam(param, grad, m, v, step, *, workspace=None, lr=7e-4, beta1=0.9, be
         if workspace is None:
             raise ValueError('clip_norm needs the workspace that grad_sumsq filled')
         grad_sumsq(grad, workspace, stream=stream)
-    _ffi.call('xa_clip_adam_f32', _ptr(p), _ptr(g), _ptr(mm), _ptr(vv), p.size, _tptr(workspace), float(lr), float(beta1),
-              float(beta2), float(eps), clip, int(step), float(grad_scale), _stream(stream))
+    _call(p, 'xa_clip_adam_f32', _ptr(p), _ptr(g), _ptr(mm), _ptr(vv), p.size, _tptr(workspace), float(lr), float(beta1),
+              float(beta2), float(eps), clip, int(step), float(grad_scale), stream)
+    _count()
+
+
+def grad_from_outputs(d_actor, d_values, grad, *, stream=None):
+    """Benchmark stand-in for the network backward: fills the flat gradient from the loss's output gradients."""
+    da, dv, g = _dev(d_actor, 'float32'), _dev(d_values, 'float32'), _dev(grad, 'float32')
+    _call(g, 'xa_grad_from_outputs_f32', _ptr(da), _ptr(dv), dv.size, da.size // dv.size, _ptr(g), g.size, stream)
     _count()
 
 
@@ -403,8 +422,8 @@ def gemm_bf16_tn(a, b, *, bias=None, relu=False, relu_mask=None, out_dtype=torch
     if col_group is not None and out is None:
         raise ValueError('col_group needs a preallocated `out` (the zero-bordered grid)')
     group, pitch = col_group if col_group is not None else (0, 0)
-    _ffi.call('xa_gemm_bf16_tn_ex', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
-              int(bool(relu)), _ptr(mask_a), n, int(group), int(pitch), _tptr(ws), ws_bytes, _stream(stream))
+    _call(aa, 'xa_gemm_bf16_tn_ex', _ptr(aa), _ptr(bb), _tptr(c), _ptr(bias_a), m, n, k, c.stride(0), int(c.dtype == torch.bfloat16),
+              int(bool(relu)), _ptr(mask_a), n, int(group), int(pitch), _tptr(ws), ws_bytes, stream)
     _count(2 if ws is not None else 1)
     return c
 
@@ -423,7 +442,7 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
     else:
         ld = cols
         dst = torch.empty((rows, cols), dtype=torch.bfloat16, device=dev)
-    _ffi.call('xa_to_bf16', _ptr(a), int(a.dtype == 'float32'), _tptr(dst), rows, cols, ld, int(transpose), _stream(stream))
+    _call(a, 'xa_to_bf16', _ptr(a), int(a.dtype == 'float32'), _tptr(dst), rows, cols, ld, int(transpose), stream)
     _count()
     return dst
 
@@ -453,9 +472,9 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
     mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
     if mask_a is not None and mask_a.size != B * OH * OW * N:
         raise ValueError('relu_mask must have the compact output layout [B, OH, OW, N]')
-    _ffi.call('xa_conv2d_nhwc_bf16_ex', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
+    _call(xx, 'xa_conv2d_nhwc_bf16_ex', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
               int(bool(relu)), 2 if unpack_s2d else int(bool(out_s2d)), _ptr(mask_a), int(OH) if out_hw is not None else 0,
-              int(OW) if out_hw is not None else 0, int(gh), int(gw), int(bool(zero_border)), _stream(stream))
+              int(OW) if out_hw is not None else 0, int(gh), int(gw), int(bool(zero_border)), stream)
     _count()
     return y
 
@@ -466,7 +485,7 @@ def space_to_depth_u8_bf16(frames, block, *, scale_255=True, out=None, stream=No
     B, H, W, C = f.shape
     y = out if out is not None else torch.empty((B, H // block, W // block, block * block * C), dtype=torch.bfloat16,
                                                  device=_device_of(f))
-    _ffi.call('xa_space_to_depth_u8_bf16', _ptr(f), _tptr(y), B, H, W, C, block, int(bool(scale_255)), _stream(stream))
+    _call(f, 'xa_space_to_depth_u8_bf16', _ptr(f), _tptr(y), B, H, W, C, block, int(bool(scale_255)), stream)
     _count()
     return y
 
@@ -481,8 +500,8 @@ def gather_s2d_u8_bf16(frames, idx, block=4, *, time_major=None, scale_255=True,
     n = i.size
     y = out if out is not None else torch.empty((n, H // block, W // block, block * block * C), dtype=torch.bfloat16,
                                                  device=_device_of(f))
-    _ffi.call('xa_gather_s2d_u8_bf16', _ptr(f), _ptr(i), _tptr(y), n, n_rows, T, E, H, W, C, block, int(bool(scale_255)),
-              _stream(stream))
+    _call(f, 'xa_gather_s2d_u8_bf16', _ptr(f), _ptr(i), _tptr(y), n, n_rows, T, E, H, W, C, block, int(bool(scale_255)),
+              stream)
     _count()
     return y
 
@@ -506,8 +525,8 @@ def conv_wgrad_nhwc_bf16(x, dy_grid, kh, kw, *, stream=None):
         ws = _wgrad_nhwc_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     dw = torch.empty((N, kh * kw * C), dtype=torch.float32, device=dev)
     db = torch.empty((N,), dtype=torch.float32, device=dev)
-    _ffi.call('xa_conv_wgrad_nhwc_bf16', _ptr(xx), _ptr(dd), _tptr(dw), _tptr(db), N, C, kh, kw, W, B * H * W, _tptr(ws),
-              ws.numel(), _stream(stream))
+    _call(xx, 'xa_conv_wgrad_nhwc_bf16', _ptr(xx), _ptr(dd), _tptr(dw), _tptr(db), N, C, kh, kw, W, B * H * W, _tptr(ws),
+              ws.numel(), stream)
     _count(2)
     return dw, db
 
@@ -526,7 +545,7 @@ def gemm_bf16_atb(a, b, *, split_k=True, stream=None):
         ws_bytes = _ffi.lib().xa_gemm_atb_workspace_bytes(m, n, k)
         if ws_bytes:
             ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-    _ffi.call('xa_gemm_bf16_atb', _ptr(aa), _ptr(bb), _tptr(c), m, n, k, n, _tptr(ws), ws_bytes, _stream(stream))
+    _call(aa, 'xa_gemm_bf16_atb', _ptr(aa), _ptr(bb), _tptr(c), m, n, k, n, _tptr(ws), ws_bytes, stream)
     _count(2 if ws is not None else 1)
     return c
 
@@ -536,6 +555,6 @@ def gather_cast_f32(src, index_map, out, *, stream=None):
     s_, m_ = _dev(src, 'float32'), _dev(index_map, 'int32')
     if out.dtype not in (torch.bfloat16, torch.float32) or out.numel() != m_.size:
         raise ValueError('out must be a bf16/fp32 tensor with one element per map entry')
-    _ffi.call('xa_gather_cast_f32', _ptr(s_), _ptr(m_), _tptr(out), out.numel(), int(out.dtype == torch.bfloat16), _stream(stream))
+    _call(s_, 'xa_gather_cast_f32', _ptr(s_), _ptr(m_), _tptr(out), out.numel(), int(out.dtype == torch.bfloat16), stream)
     _count()
     return out
