@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--gather-mode', default='auto', choices=['auto', 'bulk', 'vector'])
     ap.add_argument('--no-overlap', action='store_true', help='gathers on the compute stream instead of a data stream')
     ap.add_argument('--staging', type=int, default=2)
+    ap.add_argument('--sync', default='auto', choices=['auto', 'event', 'progress'], help='how losses learn their minibatch is staged (hotpath.PPOHotPath)')
     ap.add_argument('--gather-chunk', type=int, default=None, help='minibatches per gather launch (default: tapered schedule)')
     ap.add_argument('--gather-schedule', default=None, help='explicit launch schedule, e.g. 4,4,4,3,1')
     ap.add_argument('--c1', default='auto', choices=['auto', 'nccl', 'fused', 'none'],
@@ -275,25 +276,32 @@ class SyntheticNetwork:
     output_is_softmax = False
 
     def __init__(self, device, comm, n_params, optimizer=True, c1='nccl', lr=7e-4):
+        import ctypes
+
         import torch
 
-        from xagents_b200 import ops
+        from xagents_b200 import _ffi, ops
+        from xagents_b200.optim import FlatAdam
         self.torch, self.ops, self.comm, self.optimizer, self.c1, self.lr = torch, ops, comm, optimizer, c1, lr
+        self.device = torch.device(device)
         n = n_params + (-n_params) % 4
         self.n_params = n_params
         self.step = 0
         self.tables = None               # (actor [n_mb, B, A], critic [n_mb, B]) uploaded per rollout (e2e); None: already in place
-        self.fused = None
+        self.fused = self.opt = None
         if c1 == 'fused' and comm is not None and comm.world_size > 1:
             from xagents_b200 import peer
             self.fused = peer.FusedAllReduceAdam(comm, n_params, lr=lr)
             self.flat_grad, self.flat_param = self.fused.grad, self.fused.param       # peer-mapped buffers; m, v: this rank's shard
         else:
             self.flat_param = torch.zeros(n, dtype=torch.float32, device=device)
-            self.m, self.v = torch.zeros_like(self.flat_param), torch.zeros_like(self.flat_param)
             self.flat_grad = torch.zeros_like(self.flat_param)
-            self.workspace = ops.optim_workspace(device)
+            self.opt = FlatAdam(self.flat_param, self.flat_grad, lr=lr)
         self.launches_per_update = 0 if not optimizer else (2 if self.fused is not None else 3)
+        # the stand-in backward as a prepared C-ABI call (fixed gradient buffer; the loss outputs' pointers come per call)
+        self._grad_fn, self._check, self._count = _ffi.lib().xa_grad_from_outputs_f32, _ffi.check, ops._count
+        self._grad_tail = (ctypes.c_void_p(self.flat_grad.data_ptr()), self.flat_grad.numel())
+        self._vp = ctypes.c_void_p
 
     def forward(self, states, training=True):
         raise RuntimeError('the benchmark feeds complete rollouts: there is no rollout-time forward')
@@ -307,19 +315,23 @@ class SyntheticNetwork:
     def backward_and_step(self, d_actor, d_values, grad_norm=None):
         if not self.optimizer:
             return
-        ops, comm = self.ops, self.comm
-        ops.grad_from_outputs(d_actor, d_values, self.flat_grad)
+        comm, vp = self.comm, self._vp
+        stream = vp(self.torch.cuda.current_stream(self.device).cuda_stream)
+        n = d_values.shape[0]
+        self._check('xa_grad_from_outputs_f32', self._grad_fn(vp(d_actor.data_ptr()), vp(d_values.data_ptr()), n, d_actor.shape[1],
+                                                             *self._grad_tail, stream))
+        self._count()
         self.step += 1
         if self.fused is not None:
             self.fused.step(self.step, grad_norm)
+            self._count()
             return
         scale = 1.0
         if comm is not None and comm.world_size > 1 and self.c1 != 'none':
             comm.all_reduce_gradients_async(self.flat_grad)         # collective C1 (comm stream, high priority) ...
             comm.wait_gradients()                                   # ... and the optimiser waits for it
             scale = 1.0 / comm.world_size
-        ops.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.step, workspace=self.workspace, lr=self.lr,
-                      clip_norm=grad_norm, grad_scale=scale)
+        self.opt.step(grad_norm, scale)
 
 
 def synthetic_host_rollout(T, E, shape, dtype, A, K, M, seed):
@@ -352,7 +364,7 @@ def build_ppo(args, dev, comm, E, T, shape, dtype, A, n_params, rank, c1, networ
     else:
         net = SyntheticNetwork(dev, comm, n_params, optimizer=not args.no_optimizer, c1=c1)
     agent = PPO(envs, net, n_steps=T, quiet=True, device=dev)
-    opts = dict(gather_mode=args.gather_mode, staging=args.staging, overlap=not args.no_overlap)
+    opts = dict(gather_mode=args.gather_mode, staging=args.staging, overlap=not args.no_overlap, sync=args.sync)
     if args.gather_schedule:
         opts['gather_chunk'] = [int(x) for x in args.gather_schedule.split(',')]
     elif args.gather_chunk:
@@ -372,8 +384,9 @@ def build_ppo(args, dev, comm, E, T, shape, dtype, A, n_params, rank, c1, networ
     N = T * E
     perms = torch.stack([torch.randperm(N, device=dev, generator=gen).to(torch.int32) for _ in range(agent.ppo_epochs)])
     agent.rollout_source = lambda ag: last_values                 # the rollout is already in the agent's buffers
-    agent.permutation_source = lambda epoch: perms[epoch]         # identical permutation indices on every step
     hp = agent.hot_path()
+    hp.perms.copy_(perms)
+    agent.permutation_source = lambda epoch: hp.perms[epoch]      # identical permutation indices on every step, resident
     if network == 'stand-in':
         hp.actor_out.copy_(torch.randn(hp.actor_out.shape, device=dev, generator=gen))
         hp.critic_out.copy_(torch.randn(hp.critic_out.shape, device=dev, generator=gen))
@@ -564,7 +577,20 @@ def run_ppo(args):
     ms_per_step = elapsed_ms / args.steps
     value = total_envs * T * args.steps / (elapsed_ms * 1e-3)
     assert agent.steps == (warmup + args.steps) * N, 'train_step() must advance agent.steps by n_steps * n_envs'
-    launches = wrapper_launches + args.steps * (hp.kernel_launches_per_step - 1)       # GAE is counted by the ops wrapper
+    agent.steps = 0
+    launches = wrapper_launches                                  # every C-ABI launch goes through ops' counter (pipeline included)
+
+    # ---- the metric's three stages alone (round-1 definition: nothing after the loss), for continuity ----------------
+    bare = None
+    if world == 1 and args.network == 'stand-in' and not args.no_optimizer:
+        net.optimizer = False
+        for _ in range(3):
+            agent.train_step()
+        ms_b, per_b = timed_steps(lambda s: agent.train_step(), stream, args.steps, None, dev)
+        net.optimizer = True
+        bare = {'value': total_envs * T * args.steps / (ms_b * 1e-3), 'ms_per_step': ms_b / args.steps,
+                'ms_per_step_median': statistics.median(per_b),
+                'what': 'the same train_step() with nothing after each loss (no gradient stand-in, no optimiser): GAE + gathers + losses only'}
 
     # ---- end to end: PPO.train_step() fed HOST rollouts ---------------------------------------------
     # feeds.HostRolloutFeed: every step's rollout, permutations and model outputs come from pinned host memory; rollout s+1
@@ -720,6 +746,8 @@ def run_ppo(args):
         'gpu_launches': launches,
         'clocks': clocks,
     }
+    if bare is not None:
+        line['gae_gather_loss_only'] = bare
     if graph_us is not None:
         line['graph_replay_us_per_step'] = graph_us
         line['eager_us_per_step'] = ms_per_step * 1e3
@@ -840,7 +868,7 @@ def run_a2c(args):
     steps = max(args.steps, 200)
     ops.reset_launch_count()
     elapsed_ms, per_step = timed_steps(lambda s: agent.train_step(), stream, steps, None, dev, sampler)
-    launches = ops.launch_count() + steps * 1
+    launches = ops.launch_count()
     clocks = sampler.stop()
     N = T * E
     # the bare two-launch pipeline as a CUDA-graph replay (what a captured training loop would pay)

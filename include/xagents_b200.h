@@ -93,6 +93,19 @@ int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, i
                         const int32_t* idx, int64_t n_idx, int n_steps, int n_envs, int mode,
                         xa_stream_t stream);
 
+/* Gather with fine-grained completion, for pipelines that consume minibatches while one long launch is still moving the
+ * later ones (the reference materialises every minibatch before the first update, xagents/ppo/agent.py:149-155).  TMA bulk
+ * path only (16-byte aligned src/dst/row_bytes).  Destination row i belongs to minibatch
+ *   m = e * ceil(rows_per_epoch / mb_rows) + (g - e * rows_per_epoch) / mb_rows,  g = row_offset + i, e = g / rows_per_epoch
+ * and progress[m] (device uint32, never reset: cyclic) grows by xa_gather_progress_units(row_bytes) per finished row, after
+ * the row's bytes are written.  A consumer orders its stream after minibatch m of the s-th launch over these counters with
+ * xa_stream_wait_geq_u32(stream, progress + m, s * rows_in_m * units)  (cuStreamWaitValue32, cyclic >=). */
+int xa_gather_progress_units(int64_t row_bytes);
+int xa_gather_rows_progress(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes,
+                            int64_t n_src_rows, int n_steps, int n_envs, uint32_t* progress, int64_t row_offset,
+                            int64_t rows_per_epoch, int64_t mb_rows, xa_stream_t stream);
+int xa_stream_wait_geq_u32(xa_stream_t stream, const uint32_t* addr, uint32_t value);
+
 /* BaseAgent.get_model_outputs image scaling, xagents/base.py:505-506, fused behind the gather:
  * dst fp32 [n_idx, row_bytes] = float(src u8) / 255.0f (true division). */
 int xa_gather_rows_u8_scaled_f32(const uint8_t* src, const int32_t* idx, float* dst, int64_t n_idx,

@@ -113,6 +113,9 @@ def _reduce_std(x):
 
 
 class _Tape:
+    def __init__(self, *args, **kwargs):
+        pass
+
     def __enter__(self):
         return self
 
@@ -142,6 +145,10 @@ class Categorical:
 
     def entropy(self):
         return -(np.exp(self.lsm) * self.lsm).sum(axis=-1, dtype=F32)
+
+    def kl_divergence(self, other):
+        """KL(self || other) = sum softmax(a) * (log_softmax(a) - log_softmax(b)) (tfp's Categorical-Categorical KL)."""
+        return (np.exp(self.lsm) * (self.lsm - other.lsm)).sum(axis=-1, dtype=F32)
 
     def sample(self, seed=None):
         g = _SAMPLE_RNG.gumbel(size=self.lsm.shape)
@@ -199,7 +206,13 @@ def _populate(module):
         module.reshape = lambda t, shape: np.reshape(np.asarray(t), shape)
         module.split = lambda t, n, axis=0: np.split(np.asarray(t), n, axis)
         module.stack = lambda items, axis=0: np.stack([np.asarray(i) for i in items], axis)
-        module.cast = lambda x, dtype: _f32(x)
+        module.cast = lambda x, dtype: np.asarray(x).astype(np.int64) if dtype == 'int64' else _f32(x)
+        module.int64, module.int32, module.newaxis = 'int64', 'int32', None
+        module.reduce_sum = lambda x, axis=None: np.asarray(x).sum(axis=axis, dtype=F32)
+        module.stop_gradient = lambda x: x
+        module.concat = lambda items, axis=0: np.concatenate([np.asarray(i) for i in items], axis)
+        module.gather_nd = lambda params, idx: np.asarray(params)[tuple(np.asarray(idx).T)]
+        module.tensordot = lambda a, b, axes: np.tensordot(a, b, axes)
         module.GradientTape = _Tape
         module.clip_by_global_norm = lambda grads, norm: (grads, F32(0))
     elif name == 'tensorflow.random':
@@ -207,6 +220,8 @@ def _populate(module):
         module.set_seed = lambda s: None
     elif name == 'tensorflow.math':
         module.reduce_std = _reduce_std
+        module.log = np.log
+        module.sqrt = np.sqrt
     elif name == 'tensorflow_probability.python.distributions':
         module.Categorical = Categorical
         module.MultivariateNormalDiag = MultivariateNormalDiag
@@ -469,10 +484,210 @@ def distribution_cases(xagents):
     a2c_case(xagents, 'a2c_softmax', 24, n_steps=7, n_envs=4, obs_shape=(4,), image=False, n_actions=3, p_done=0.2, softmax=True)
 
 
+def _set_precision(dtype):
+    """The shim computes in `F32`; numerical differentiation of the reference's own functions needs it in float64."""
+    global F32
+    F32 = dtype
+
+
+class _KerasModelBase:
+    """What `isinstance(models, tf.keras.models.Model)` (base.py:507) is pointed at while the update cases run."""
+
+
+def _set_model_base(tf, value):
+    holder = tf.keras.models
+    (setattr if isinstance(holder, types.ModuleType) else type.__setattr__)(holder, 'Model', value)
+
+
+def _install_model_base(tf):
+    previous = tf.keras.models.Model
+    _set_model_base(tf, _KerasModelBase)
+    return previous
+
+
+def _bare(cls, **attrs):
+    a = object.__new__(cls)
+    for k, v in attrs.items():
+        setattr(a, k, v)
+    return a
+
+
+def acer_update_case(xagents, tag, trust_region, seed=51):
+    """The reference's own ACER.update_gradients (acer/agent.py:262-339) end to end -- model outputs -> values -> clip_last_step ->
+    gather_nd -> importance weights -> Retrace -> calculate_losses -> calculate_grads (trust-region projection) -- under the shim
+    in float64.  The one thing a NumPy shim cannot give is the tape: `tape.gradient(loss, action_probs)` is answered by central
+    differences of the REFERENCE'S calculate_losses (fp64, h = 1e-6), so the gradient too is the reference's, not a restatement;
+    what the tape is then asked to push into the network (`output_grads`) is recorded."""
+    import tensorflow as tf
+    _set_precision(np.float64)
+    previous_model_base = _install_model_base(tf)
+    try:
+        T, E, A, Fdim = 7, 6, 4, 5
+        N = T * E
+        rng = np.random.default_rng(seed)
+
+        class Net(_KerasModelBase):
+            def __init__(self, wa, wc):
+                self.wa, self.wc = wa, wc
+                self.trainable_variables = []
+                self.optimizer = types.SimpleNamespace(apply_gradients=lambda pairs: None)
+
+            def __call__(self, x, training=True):
+                x = np.asarray(x, F32)
+                return [np.exp(_log_softmax(x @ self.wa)), x @ self.wc]
+
+        wa, wc, wavg = (rng.standard_normal((Fdim, A)) * 0.8 for _ in range(3))
+        agent = _bare(xagents.ACER, n_steps=T, n_envs=E, n_actions=A, gamma=0.99, epsilon=1e-6, importance_c=10.0, delta=1,
+                      trust_region=trust_region, entropy_coef=0.01, value_loss_coef=0.5, grad_norm=None, img_inputs=False,
+                      output_is_softmax=True, seed=None, distribution_type=Categorical, model=Net(wa, wc), avg_model=Net(wavg, wc),
+                      ema=types.SimpleNamespace(apply=lambda v: None), batch_indices=np.arange(N, dtype=np.int64)[:, None])
+        agent.update_avg_weights = lambda: None
+        states = rng.standard_normal((E * (T + 1), Fdim))                  # env-major, T+1 steps per env (acer/agent.py:146-162)
+        rewards = rng.standard_normal(N)
+        actions = rng.integers(0, A, N).astype(np.int32)
+        dones = (rng.random(N) < 0.15).astype(np.float64)
+        previous = np.exp(_log_softmax(rng.standard_normal((N, A))))
+        rec = {'calculate_losses': [], 'calculate_grads': [], 'calculate_returns': []}
+        inner_losses = agent.calculate_losses
+        for name in rec:
+            _wrap(agent, name, rec[name])
+        pushed = {}
+
+        class Tape(_Tape):
+            def gradient(self, target, sources, output_gradients=None):
+                if output_gradients is not None:                          # tape.gradient(action_probs, variables, output_grads)
+                    pushed['output_grads'] = np.asarray(output_gradients).copy()
+                    return []
+                if isinstance(sources, np.ndarray) and sources.ndim == 2:  # tape.gradient(loss, action_probs)
+                    (probs, values, returns, _, sel_imp, sel_q), _ = rec['calculate_losses'][-1]
+                    return _fd_probs(inner_losses, probs, actions, values, returns, sel_imp, sel_q)
+                return []
+
+        tf.GradientTape, saved = Tape, tf.GradientTape
+        try:
+            agent.update_gradients(states, rewards, actions, dones, previous)
+        finally:
+            tf.GradientTape = saved
+        (probs, values, returns, sel_probs, sel_imp, sel_q), losses = rec['calculate_losses'][0]
+        (_, _, _, avg_probs), _ = rec['calculate_grads'][0]
+        full_probs, full_q = agent.model(states)
+        out = dict(n_steps=T, n_envs=E, n_actions=A, gamma=0.99, epsilon=1e-6, importance_c=10.0, delta=1, trust_region=trust_region,
+                   entropy_coef=0.01, value_loss_coef=0.5, rewards=rewards, actions=actions, dones=dones, previous_action_probs=previous,
+                   full_action_probs=full_probs, full_critic_logits=full_q, full_avg_action_probs=agent.avg_model(states)[0],
+                   action_probs=np.asarray(probs), avg_action_probs=np.asarray(avg_probs), values=np.asarray(values),
+                   returns=np.asarray(returns), selected_probs=np.asarray(sel_probs), selected_importance=np.asarray(sel_imp),
+                   selected_critic_logits=np.asarray(sel_q))
+        # gradients of the reference's loss w.r.t. the two model outputs, by central differences of the reference's function
+        g = _fd_probs(inner_losses, probs, actions, values, returns, sel_imp, sel_q)
+        dq = _fd_selected_q(inner_losses, probs, values, returns, sel_probs, sel_imp, sel_q, trust_region)
+        d_critic = np.zeros((N, A))
+        d_critic[np.arange(N), actions] = dq
+        if trust_region:
+            out.update(loss=float(losses[0]), value_loss=float(losses[1]), d_loss_d_action_probs=g,
+                       output_grads=pushed['output_grads'], d_value_loss_d_critic_logits=d_critic)
+        else:
+            out.update(loss=float(losses), d_loss_d_action_probs=g, d_loss_d_critic_logits=d_critic)
+        np.savez_compressed(os.path.join(HERE, f'{tag}.npz'), **out)
+        print(f'{tag}: loss={out["loss"]:.6f} |g|max={np.abs(g).max():.4f}')
+    finally:
+        _set_precision(np.float32)
+        _set_model_base(tf, previous_model_base)
+
+
+def _fd_probs(calculate_losses, probs, actions, values, returns, sel_imp, sel_q, h=1e-6):
+    """d loss / d action_probs[i, j] of the reference's calculate_losses; selected_probs follows action_probs (gather_nd)."""
+    probs = np.asarray(probs, np.float64)
+    n, a = probs.shape
+    idx = np.arange(n)
+
+    def f(p):
+        out = calculate_losses(p, values, returns, p[idx, actions], sel_imp, sel_q)
+        return float(out[0]) if isinstance(out, tuple) else float(out)
+    g = np.zeros_like(probs)
+    for i in range(n):
+        for j in range(a):
+            up, dn = probs.copy(), probs.copy()
+            up[i, j] += h
+            dn[i, j] -= h
+            g[i, j] = (f(up) - f(dn)) / (2 * h)
+    return g
+
+
+def _fd_selected_q(calculate_losses, probs, values, returns, sel_probs, sel_imp, sel_q, trust_region, h=1e-6):
+    sel_q = np.asarray(sel_q, np.float64)
+
+    def f(q):
+        out = calculate_losses(probs, values, returns, sel_probs, sel_imp, q)
+        return float(out[1]) if trust_region else float(out)
+    g = np.zeros_like(sel_q)
+    for i in range(len(sel_q)):
+        up, dn = sel_q.copy(), sel_q.copy()
+        up[i] += h
+        dn[i] -= h
+        g[i] = (f(up) - f(dn)) / (2 * h)
+    return g
+
+
+def trpo_case(xagents):
+    """The reference's own TRPO.calculate_losses / calculate_kl_divergence (trpo/agent.py:179-224) and update_critic_weights
+    (:279-297) on linear NumPy networks: surrogate objective, mean KL(old || new), the critic's value loss per shuffled minibatch."""
+    import tensorflow as tf
+    _reset_rngs()
+    for k in RECORD:
+        RECORD[k].clear()
+    T, E, A, Fdim = 9, 4, 5, 6
+    N = T * E
+    rng = np.random.default_rng(61)
+
+    previous_model_base = _install_model_base(tf)
+
+    class Linear(_KerasModelBase):
+        def __init__(self, w):
+            self.w = w
+            self.trainable_variables = []
+            self.optimizer = types.SimpleNamespace(apply_gradients=lambda pairs: None)
+
+        def __call__(self, x, training=True):
+            return _f32(x) @ self.w
+
+    w_new, w_old = (rng.standard_normal((Fdim, A)) * 0.6).astype(F32), None
+    w_old = (w_new + 0.05 * rng.standard_normal((Fdim, A))).astype(F32)
+    w_critic = (rng.standard_normal((Fdim, 1)) * 0.6).astype(F32)
+    actor, old_actor, critic = Linear(w_new), Linear(w_old), Linear(w_critic)
+    agent = _bare(xagents.TRPO, n_steps=T, n_envs=E, entropy_coef=0.01, img_inputs=False, output_is_softmax=False, seed=None,
+                  distribution_type=Categorical, actor=actor, old_actor=old_actor, critic=critic, output_models=[actor, critic],
+                  critic_iterations=2, ppo_epochs=2, mini_batches=3, batch_size=N, mini_batch_size=N // 3)
+    states = rng.standard_normal((N, Fdim)).astype(F32)
+    actions = rng.integers(0, A, N).astype(F32)
+    raw_adv = rng.standard_normal(N).astype(F32)
+    advantages = ((raw_adv - raw_adv.mean(dtype=F32)) / _reduce_std(raw_adv)).astype(F32)        # trpo/agent.py:316-319
+    surrogate, kl = xagents.TRPO.calculate_losses(agent, states, actions, advantages)
+    returns = rng.standard_normal(N).astype(F32)
+    RECORD['losses'].clear()
+    RECORD['shuffles'].clear()
+    xagents.TRPO.update_critic_weights(agent, states, returns)
+    np.savez_compressed(os.path.join(HERE, 'trpo_losses.npz'), n_steps=T, n_envs=E, n_actions=A, entropy_coef=0.01, w_actor=w_new,
+                        w_old_actor=w_old, w_critic=w_critic, states=states, actions=actions, raw_advantages=raw_adv,
+                        advantages=advantages, surrogate_loss=F32(surrogate), kl_divergence=F32(kl), returns=returns,
+                        critic_iterations=2, ppo_epochs=2, mini_batches=3, critic_value_losses=np.asarray(RECORD['losses'], F32),
+                        critic_shuffles=np.stack(RECORD['shuffles']))
+    _set_model_base(tf, previous_model_base)
+    print(f'trpo_losses: surrogate={float(surrogate):.6f} kl={float(kl):.6e} value losses={len(RECORD["losses"])}')
+
+
+def update_cases(xagents):
+    acer_update_case(xagents, 'acer_update_trust_region', True)
+    acer_update_case(xagents, 'acer_update_plain', False)
+    trpo_case(xagents)
+
+
+
 def main():
     xagents = _import_reference()
     if '--acer-only' in sys.argv:
         return acer_case(xagents)
+    if '--updates-only' in sys.argv:                               # round 2: leaves the earlier fixtures untouched
+        return update_cases(xagents)
     if '--distributions-only' in sys.argv:                         # added later: leaves the earlier fixtures untouched
         return distribution_cases(xagents)
     acer_case(xagents)
@@ -494,6 +709,7 @@ def main():
     a2c_case(xagents, 'a2c_vector', 22, n_steps=12, n_envs=5, obs_shape=(4,), image=False,
              n_actions=2, p_done=0.15)
     distribution_cases(xagents)
+    update_cases(xagents)
 
 
 if __name__ == '__main__':

@@ -154,3 +154,41 @@ def test_cli_train_acer(tmp_path):
     assert agent.net.step > agent.buffer_current_size               # replay updates happened on top of the on-policy ones
     agent.update_metrics()
     assert torch.isfinite(agent.net.flat_param).all() and agent.games > 100 and np.isfinite(agent.mean_reward)
+
+
+@pytest.mark.parametrize('case', ['acer_update_trust_region', 'acer_update_plain'])
+def test_update_gradients_vs_the_reference_run(golden, case):
+    """The whole ACER.update_gradients on the device -- values, clip_last_step, importance weights, the Retrace kernel, losses,
+    trust-region projection -- against the fixture made by the REFERENCE'S OWN update_gradients (acer/agent.py:262-339; float64
+    shim, tape answered by central differences of the reference's calculate_losses: tests/golden/make_golden.py).  The network is
+    replaced by the fixture's model outputs; layouts are converted env-major (reference) -> time-major (this repo)."""
+    g = golden(case)
+    T, E, A = int(g['n_steps']), int(g['n_envs']), int(g['n_actions'])
+    n = T * E
+    agent, net = _agent(T=T, E=E, A=A, trust_region=bool(g['trust_region']), delta=float(g['delta']), grad_norm=None)
+    assert (agent.epsilon, agent.importance_c, agent.entropy_coef, agent.value_loss_coef, agent.gamma) == (
+        float(g['epsilon']), float(g['importance_c']), float(g['entropy_coef']), float(g['value_loss_coef']), float(g['gamma']))
+    cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda()
+    full_tm = lambda x: cu(x.reshape(E, T + 1, A).swapaxes(0, 1).reshape((T + 1) * E, A))        # [E(T+1), A] env-major -> [(T+1)E, A]
+    steps_tm = lambda x: cu(x.reshape((E, T) + x.shape[1:]).swapaxes(0, 1))                    # [E T, ...] -> [T, E, ...]
+    probs_full, q_full, avg_full = full_tm(g['full_action_probs']), full_tm(g['full_critic_logits']), full_tm(g['full_avg_action_probs'])
+    net.forward = lambda states, training=True: (probs_full, q_full)
+    agent._avg_outputs = lambda states: avg_full
+    seen = {}
+    net.backward_and_step = lambda da, dq, gn: seen.update(p=da.clone(), q=dq.clone())
+    states = torch.zeros((T + 1, E) + agent.input_shape, dtype=agent.ring.states.dtype if hasattr(agent, 'ring') else torch.float32, device='cuda')
+    agent.update_gradients(states, steps_tm(g['rewards']), steps_tm(g['actions'].astype(np.float32)), steps_tm(g['dones']),
+                           steps_tm(g['previous_action_probs']))
+    torch.cuda.synchronize()
+    to_env_major = lambda x: x[:n].view(T, E, A).transpose(0, 1).reshape(n, A).double().cpu().numpy()
+    want_p = g['output_grads'] if bool(g['trust_region']) else g['d_loss_d_action_probs']
+    want_q = g['d_value_loss_d_critic_logits'] if bool(g['trust_region']) else g['d_loss_d_critic_logits']
+    for got, want in ((to_env_major(seen['p']), want_p), (to_env_major(seen['q']), want_q)):
+        assert np.abs(got - want).max() <= REL * np.abs(want).max()
+    assert torch.count_nonzero(seen['p'][n:]) == 0 and torch.count_nonzero(seen['q'][n:]) == 0     # clip_last_step
+    losses = agent.last_losses
+    if bool(g['trust_region']):
+        assert abs(float(losses[0]) - float(g['loss'])) <= REL * abs(float(g['loss']))
+        assert abs(float(losses[1]) - float(g['value_loss'])) <= REL * abs(float(g['value_loss']))
+    else:
+        assert abs(float(losses) - float(g['loss'])) <= REL * max(abs(float(g['loss'])), 1.0)

@@ -504,6 +504,18 @@ def test_clip_adam_vs_oracle(n, clip):
 def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
     """The prepared two-stream pipeline (what bench.py times) against the oracle's PPO.train_step,
     including the trailing short minibatch (7*3 % 4 != 0) and every staging / granularity layout."""
+    _check_pipeline(T, E, mb, fuse, chunk, overlap, staging, 'event')
+
+
+@pytest.mark.parametrize('chunk,staging', [(None, 2), (3, 2), (1, 1), ('schedule', 2), (5, 3)])
+@pytest.mark.parametrize('T,E,mb', [(16, 8, 4), (7, 3, 4)])
+def test_hotpath_progress_sync_vs_oracle(T, E, mb, chunk, staging):
+    """The same pipeline with per-minibatch completion counters (sync='progress': the gather kernel publishes finished rows,
+    the compute stream waits on its minibatch's counter with cuStreamWaitValue32) instead of one event per gather launch."""
+    _check_pipeline(T, E, mb, True, chunk, True, staging, 'progress')
+
+
+def _check_pipeline(T, E, mb, fuse, chunk, overlap, staging, sync):
     from xagents_b200.hotpath import PPOHotPath
     K = 2
     ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=K, p_done=0.05, seed=T + E)
@@ -513,7 +525,8 @@ def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
         n_mb = K * -(-(T * E) // ((T * E) // mb))
         chunk = [3, 1, 2] + [n_mb - 6]
     hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=mb, device=DEV, fuse_fields=fuse,
-                    gather_chunk=chunk, overlap=overlap, staging=staging, scan_mode='sequential')
+                    gather_chunk=chunk, overlap=overlap, staging=staging, scan_mode='sequential', sync=sync)
+    assert hp.sync == sync
     hp.load(ro)
     hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
     for i, w in enumerate(want['minibatches']):                       # the "forward pass" outputs per minibatch
@@ -529,7 +542,7 @@ def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
         seen[i] = (hp.d_actor[:n].clone(), hp.d_values[:n].clone(), states.clone(),
                    [f.clone() for f in hp.minibatch_views(i)[1:]])
 
-    for _ in range(2):                                                # twice: buffers and tickets must be reusable
+    for _ in range(3):                                                # repeatedly: buffers, tickets and counters must be reusable
         seen.clear()
         hp.run(after_loss=after_loss)
         torch.cuda.synchronize()

@@ -29,15 +29,15 @@ def _free_port():
 @pytest.mark.timeout(600)
 def test_hotpath_at_c3_size_vs_oracle():
     """BASELINE config C3 itself (n_envs=256, n_steps=128, 4 epochs x 4 minibatches of 8192 frames, default launch
-    schedule [8, 4, 3, 1]) -- the exact object bench.py times -- against oracle.ppo_train_step: returns bit-exact, every
+    schedule: one gather launch with per-minibatch completion counters) -- the exact object bench.py times -- against oracle.ppo_train_step: returns bit-exact, every
     minibatch's loss / pg / value / entropy <= 1e-5, three sampled minibatches' gathered frames bit-exact."""
     from xagents_b200.hotpath import PPOHotPath
     T, E, K, M = 128, 256, 4, 4
     ro = synthetic.make_rollout(T, E, obs_shape=(84, 84, 4), epochs=K, p_done=0.01)
     want = oracle.ppo_train_step(ro.obs, ro.rewards, ro.dones, ro.values, ro.last_values, ro.actions, ro.log_probs,
                                  ro.permutations, ro.new_logits, ro.new_values, mini_batches=M, keep_states=False)
-    hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=M, device=DEV)
-    assert hp.group_sizes == [8, 4, 3, 1] and hp.B == 8192 and hp.n_mb == 16
+    hp = PPOHotPath(T, E, (84, 84, 4), ro.n_actions, ppo_epochs=K, mini_batches=M, device=DEV, scan_mode='sequential')
+    assert hp.sync == 'progress' and hp.group_sizes == [16] and hp.B == 8192 and hp.n_mb == 16      # one launch, per-minibatch counters
     hp.load(ro)
     hp.perms.copy_(torch.as_tensor(np.stack(ro.permutations)))
     for i, w in enumerate(want['minibatches']):
@@ -52,12 +52,15 @@ def test_hotpath_at_c3_size_vs_oracle():
 
     hp.run(after_loss=after_loss)
     torch.cuda.synchronize()
-    assert np.array_equal(hp.returns.cpu().numpy(), want['returns'])
+    assert np.array_equal(hp.returns.cpu().numpy(), want['returns'])          # sequential scan: the reference's operation order
     sc = hp.scalars.cpu().numpy()
     for i, w in enumerate(want['minibatches']):
         scale = max(abs(float(w[name])) for name in ('loss', 'pg', 'vl', 'entropy'))
         for j, name in enumerate(('loss', 'pg', 'vl', 'entropy')):
             assert abs(sc[i, j] - w[name]) <= REL * scale, (i, name, sc[i, j], w[name])
+    # the default scan (`auto`: T split over warps at this shape, carries re-associated) stays within 1e-5 of max|returns|
+    auto = ops.gae_returns(hp.rewards, hp.values, hp.last_values, hp.dones, 0.99, 0.95).cpu().numpy()
+    assert np.abs(auto - want['returns']).max() <= REL * np.abs(want['returns']).max()
     flat_obs = oracle.concat_step_batches(ro.obs)[0]                 # the reference's env-major flatten copy (base.py:559-564)
     for i in sampled:
         assert np.array_equal(kept[i].cpu().numpy(), flat_obs[want['minibatches'][i]['idx']])
@@ -177,7 +180,7 @@ def test_train_step_fed_from_host_rollouts():
     a2c.train_step()
     torch.cuda.synchronize()
     ret = oracle.nstep_returns(ro.rewards, ro.dones, ro.last_values, 0.99)
-    assert np.array_equal(a2c.ro_returns.cpu().numpy(), ret)
+    assert np.abs(a2c.ro_returns.cpu().numpy() - ret).max() <= REL * np.abs(ret).max()
     logp, ent, _ = oracle.categorical_logp_entropy(tm_logits, ro.actions.reshape(-1))
     want = oracle.a2c_loss(logp, tm_values, ent, ro.values.reshape(-1), ret.reshape(-1), 0.01, 0.5)
     assert abs(float(a2c.loss_scalars[0]) - float(want['loss'])) <= REL * abs(float(want['loss']))

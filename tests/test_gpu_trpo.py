@@ -144,3 +144,50 @@ def test_cli_train_trpo_on_cartpole_and_on_synthetic_frames():
     agent = ex.agent
     assert agent.ro_states.dtype == torch.uint8 and agent.actor.n_params == 28224 * 128 + 128 + 128 * 6 + 6
     assert agent.steps == 128 and torch.isfinite(agent.actor.flat_param).all() and torch.isfinite(agent.critic.flat_param).all()
+
+
+def test_losses_kl_and_critic_minibatches_vs_the_reference_run(golden):
+    """Surrogate objective and mean KL(old || new) against the REFERENCE'S OWN TRPO.calculate_losses / calculate_kl_divergence
+    (trpo/agent.py:179-224) on linear networks, and the critic's value loss per shuffled minibatch against the reference's own
+    update_critic_weights (:279-297) -- fixture tests/golden/trpo_losses.npz (make_golden.py --updates-only)."""
+    from xagents_b200.agents import TRPO
+    g = golden('trpo_losses')
+    T, E, A = int(g['n_steps']), int(g['n_envs']), int(g['n_actions'])
+    n, f_dim = T * E, g['states'].shape[1]
+    mg = _golden_module()
+    rng = np.random.default_rng(0)
+    obs_s, rewards, dones, resets = mg._streams(rng, 2 * T, E, (f_dim,), False, 0.1)
+    envs = [mg.ReplayEnv(obs_s[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+
+    def linear(w):
+        m = torch.nn.Linear(w.shape[0], w.shape[1], bias=False)
+        with torch.no_grad():
+            m.weight.copy_(torch.as_tensor(w.T))
+        return m.cuda()
+
+    agent = TRPO(envs, linear(g['w_actor']), linear(g['w_critic']), n_steps=T, quiet=True, entropy_coef=float(g['entropy_coef']),
+                 critic_iterations=int(g['critic_iterations']), ppo_epochs=int(g['ppo_epochs']), mini_batches=int(g['mini_batches']))
+    agent.old_actor_flat[:A * f_dim].copy_(torch.as_tensor(np.ascontiguousarray(g['w_old_actor'].T).reshape(-1)).cuda())   # the "old" actor
+    cu = lambda x: torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    states, actions, advantages = cu(g['states']), cu(g['actions']), cu(g['advantages'])
+    with torch.no_grad():
+        surrogate, kl = agent.calculate_losses(states, actions, advantages)
+    assert abs(float(surrogate) - float(g['surrogate_loss'])) <= 1e-5 * max(abs(float(g['surrogate_loss'])), float(np.abs(g['advantages']).mean()))
+    assert abs(float(kl) - float(g['kl_divergence'])) <= 1e-4 * float(g['kl_divergence'])      # a difference of log-probabilities ~1e-3: fp32
+    # whole-batch advantage normalisation (trpo/agent.py:316-319) as the reference's shim evaluated it
+    raw = g['raw_advantages']
+    from xagents_b200 import ops
+    zeros = torch.zeros(n, device='cuda')
+    got = ops.normalize_advantages(cu(raw), zeros, 0.0).cpu().numpy()
+    assert np.abs(got - g['advantages']).max() <= 1e-5 * np.abs(g['advantages']).max()
+    # the critic's minibatches: same shuffles -> same value losses, in the same order
+    shuffles = [s for s in g['critic_shuffles']]
+    agent.permutation_source = lambda epoch, it=iter(shuffles): next(it)
+    returns = cu(g['returns'])
+    losses = []
+    for _ in range(agent.critic_iterations):
+        for states_mb, returns_mb in agent.get_mini_batches(states, returns):
+            _, values = agent.critic.forward(states_mb, training=False)
+            losses.append(float(((values - returns_mb) ** 2).mean()))
+    want = g['critic_value_losses']
+    assert len(losses) == len(want) and np.abs(np.asarray(losses) - want).max() <= 1e-5 * np.abs(want).max()

@@ -18,6 +18,7 @@ TensorFlow is not installable here; it is imported lazily).
 import torch
 
 from .. import ops
+from ..optim import FlatAdam
 
 
 class TorchModel:
@@ -39,9 +40,8 @@ class TorchModel:
         pad = (-n) % 4                                            # float4 path of the optimiser kernel
         self.flat_param = torch.zeros(n + pad, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros_like(self.flat_param)
-        self.m = torch.zeros_like(self.flat_param)
-        self.v = torch.zeros_like(self.flat_param)
-        self.workspace = ops.optim_workspace(dev)
+        self.optimizer = FlatAdam(self.flat_param, self.flat_grad, lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
+        self.m, self.v, self.workspace = self.optimizer.m, self.optimizer.v, self.optimizer.workspace
         off = 0
         for p in params:                                          # re-seat parameters and grads as views
             k = p.numel()
@@ -105,8 +105,9 @@ class TorchModel:
             self.comm.wait_gradients()
             scale = 1.0 / self.comm.world_size
         self.step += 1
-        ops.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.step, workspace=self.workspace, lr=self.lr,
-                      beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, clip_norm=grad_norm, grad_scale=scale)
+        opt = self.optimizer
+        opt.t, opt.lr = self.step - 1, self.lr                    # `step` and `lr` stay the attributes callers may set
+        opt.step(grad_norm, scale)
         for mod in self._refreshable:                             # bf16 operand copies of tensor-core layers
             mod.refresh()
 

@@ -135,7 +135,9 @@ class PPO(A2C):
             return self._run_ppo_epochs_generic(states, actions, returns, old_values, old_log_probs)
         hp, net = self.hot_path(), self.net
         for epoch in range(self.ppo_epochs):                       # every epoch's shuffle up front: one moments launch
-            hp.perms[epoch].copy_(self._next_permutation(epoch))
+            perm = self._next_permutation(epoch)
+            if perm.data_ptr() != hp.perms[epoch].data_ptr():      # a source may hand out rows of `hot_path().perms` itself
+                hp.perms[epoch].copy_(perm)
         forward_into = getattr(net, 'forward_into', None)
 
         def forward(i):                                            # minibatch i is staged: model forward on it

@@ -38,6 +38,9 @@ struct GatherParams {
   int load_hint, store_hint;  // L2 evict-first policy on the bulk loads / stores
   // scalar fields riding along
   int64_t n_src_rows;  // host-side checks only
+  // fine-grained completion (bulk path): progress[m] += chunks finished, m = the minibatch a destination row belongs to
+  uint32_t* progress;
+  uint32_t row_offset, rows_per_epoch, mb_rows, mbs_per_epoch;
   int n_fields;
   const float* fsrc[XA_MAX_FIELDS];
   float* fdst[XA_MAX_FIELDS];
@@ -63,12 +66,48 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
     int64_t k = static_cast<int64_t>(blockIdx.x) * stages + warp;
     uint32_t parity = 0;
     int32_t b = k < n_items ? p.idx[k / p.chunks_per_row] : 0;
+    // Fine-grained completion: this warp's items ascend, so the minibatch they belong to only moves forward.  `mb_end` is
+    // the first item (row * chunks_per_row, launch-relative) past the current minibatch; when an item crosses it, what the
+    // warp finished of the previous minibatch is published one iteration LATER, after `wait_group 1` (every store but the
+    // newest has been written) -- by then the older store has long completed, so the wait costs nothing.
+    uint32_t cur_mb = 0, cur_count = 0, pend_mb = 0, pend_count = 0;
+    int64_t mb_end = 0;
+    uint32_t ep = 0, in_ep = 0;  // epoch and minibatch-within-epoch of cur_mb
+    if (p.progress) {
+      const uint32_t g0 = p.row_offset;
+      ep = g0 / p.rows_per_epoch;
+      in_ep = (g0 - ep * p.rows_per_epoch) / p.mb_rows;
+      cur_mb = ep * p.mbs_per_epoch + in_ep;
+      uint32_t end_in_ep = (in_ep + 1) * p.mb_rows;
+      if (end_in_ep > p.rows_per_epoch) end_in_ep = p.rows_per_epoch;
+      mb_end = (static_cast<int64_t>(ep) * p.rows_per_epoch + end_in_ep - g0) * p.chunks_per_row;
+    }
     for (; k < n_items; k += stride) {
       const int64_t i = k / p.chunks_per_row;
       const int64_t off = (k - i * p.chunks_per_row) * static_cast<int64_t>(p.chunk_bytes);
       const int64_t left = p.row_bytes - off;
       const uint32_t bytes = left < static_cast<int64_t>(p.chunk_bytes) ? static_cast<uint32_t>(left) : p.chunk_bytes;
       const int64_t row = xa::sample_row(b, p.n_steps, p.n_envs);
+      if (p.progress && k >= mb_end) {
+        if (pend_count) {  // a minibatch this warp barely touched: its publication is still pending -- drain and publish now
+          xa::bulk_wait_all<0>();
+          __threadfence();
+          atomicAdd(p.progress + pend_mb, pend_count);
+        }
+        pend_mb = cur_mb;
+        pend_count = cur_count;
+        cur_count = 0;
+        while (k >= mb_end) {  // advance to the minibatch of item k
+          if (++in_ep == p.mbs_per_epoch) {
+            in_ep = 0;
+            ++ep;
+          }
+          ++cur_mb;
+          uint32_t end_in_ep = (in_ep + 1) * p.mb_rows;
+          if (end_in_ep > p.rows_per_epoch) end_in_ep = p.rows_per_epoch;
+          mb_end = (static_cast<int64_t>(ep) * p.rows_per_epoch + end_in_ep - p.row_offset) * p.chunks_per_row;
+        }
+      }
       xa::mbar_expect_tx(bar, bytes);
       if (p.load_hint)
         xa::bulk_g2s(buf, p.src + row * p.row_bytes + off, bytes, bar, policy);
@@ -83,9 +122,21 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
       else
         xa::bulk_s2g(p.dst + i * p.row_bytes + off, buf, bytes);
       xa::bulk_commit();
+      ++cur_count;
+      if (pend_count) {
+        xa::bulk_wait_all<1>();  // everything but the store just committed has been WRITTEN: the previous minibatch's rows are out
+        __threadfence();
+        atomicAdd(p.progress + pend_mb, pend_count);
+        pend_count = 0;
+      }
       xa::bulk_wait_read<0>();  // the engine has read the stage out: it may be refilled
     }
     xa::bulk_wait_all<0>();
+    if (p.progress) {
+      __threadfence();
+      if (pend_count) atomicAdd(p.progress + pend_mb, pend_count);
+      if (cur_count) atomicAdd(p.progress + cur_mb, cur_count);
+    }
     return;
   }
 
@@ -124,7 +175,9 @@ __device__ __forceinline__ void store_vec<int4>(int4* p, const int4& v) {
 constexpr int kVecThreads = 256;
 constexpr int kVecUnroll = 8;
 
-// threads_per_row (power of two <= 256) lanes cooperate on a row; 256/threads_per_row rows per block pass
+// threads_per_row (power of two <= 256) lanes cooperate on a row; 256/threads_per_row rows per block pass.  gridDim.y > 1
+// cuts every row into that many segments (few long rows: 80 frames of 28 KB would otherwise occupy 80 of 148 SMs with one
+// block each and leave the latency of 7 dependent 16-B loads per thread exposed).
 template <typename V>
 __global__ void __launch_bounds__(kVecThreads) gather_vector_kernel(const GatherParams p, int threads_per_row_log2) {
   const int tpr = 1 << threads_per_row_log2;
@@ -132,22 +185,25 @@ __global__ void __launch_bounds__(kVecThreads) gather_vector_kernel(const Gather
   const int sub = threadIdx.x >> threads_per_row_log2;
   const int lane = threadIdx.x & (tpr - 1);
   const int64_t n_vec = p.row_bytes / static_cast<int64_t>(sizeof(V));
+  const int64_t seg_len = (n_vec + gridDim.y - 1) / gridDim.y;
+  const int64_t seg_lo = seg_len * blockIdx.y;
+  const int64_t seg_hi = seg_lo + seg_len < n_vec ? seg_lo + seg_len : n_vec;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * rows_per_block + sub; i < p.n_idx;
        i += static_cast<int64_t>(gridDim.x) * rows_per_block) {
     const int64_t row = xa::sample_row(p.idx[i], p.n_steps, p.n_envs);
     const V* s = reinterpret_cast<const V*>(p.src + row * p.row_bytes);
     V* d = reinterpret_cast<V*>(p.dst + i * p.row_bytes);
-    for (int64_t base = lane; base < n_vec; base += static_cast<int64_t>(tpr) * kVecUnroll) {
+    for (int64_t base = seg_lo + lane; base < seg_hi; base += static_cast<int64_t>(tpr) * kVecUnroll) {
       V regs[kVecUnroll];
 #pragma unroll
       for (int u = 0; u < kVecUnroll; ++u) {
         const int64_t v = base + static_cast<int64_t>(u) * tpr;
-        if (v < n_vec) regs[u] = load_vec(s + v);
+        if (v < seg_hi) regs[u] = load_vec(s + v);
       }
 #pragma unroll
       for (int u = 0; u < kVecUnroll; ++u) {
         const int64_t v = base + static_cast<int64_t>(u) * tpr;
-        if (v < n_vec) store_vec(d + v, regs[u]);
+        if (v < seg_hi) store_vec(d + v, regs[u]);
       }
     }
   }
@@ -288,7 +344,16 @@ void launch_vector(const GatherParams& p, cudaStream_t stream) {
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int64_t cap = static_cast<int64_t>(sms) * 8 * 4;  // a few waves of 8 resident blocks per SM
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  gather_vector_kernel<V><<<grid, kVecThreads, 0, stream>>>(p, tpr_log2);
+  // fewer blocks than ~4 per SM: cut the rows into segments (each at least one pass of the block wide, i.e. tpr vectors)
+  int64_t segments = 1;
+  if (want < static_cast<int64_t>(sms) * 4) {
+    segments = (static_cast<int64_t>(sms) * 4 + want - 1) / want;
+    const int64_t max_seg = (n_vec + (int64_t(1) << tpr_log2) - 1) >> tpr_log2;
+    if (segments > max_seg) segments = max_seg;
+    if (segments > 64) segments = 64;
+    if (segments < 1) segments = 1;
+  }
+  gather_vector_kernel<V><<<dim3(grid, static_cast<unsigned>(segments)), kVecThreads, 0, stream>>>(p, tpr_log2);
 }
 
 int launch_fields(const GatherParams& p, cudaStream_t stream) {
@@ -298,6 +363,8 @@ int launch_fields(const GatherParams& p, cudaStream_t stream) {
   gather_fields_kernel<<<grid, 256, 0, stream>>>(p);
   return xa::check_launch("xa_gather_fields_f32");
 }
+
+int chunks_per_row_for(int64_t row_bytes, int64_t max_chunk) { return static_cast<int>((row_bytes + max_chunk - 1) / max_chunk); }
 
 bool bulk_eligible(const GatherParams& p) {
   return ((reinterpret_cast<uintptr_t>(p.src) | reinterpret_cast<uintptr_t>(p.dst) | static_cast<uintptr_t>(p.row_bytes)) & 15) == 0;
@@ -311,7 +378,10 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
   if (mode == XA_GATHER_BULK)
     XA_REQUIRE(can_bulk, XA_EALIGN, "%s: XA_GATHER_BULK needs 16-byte aligned src, dst and row_bytes (row_bytes=%lld)", what,
                static_cast<long long>(p.row_bytes));
-  const bool use_bulk = mode == XA_GATHER_BULK || (mode == XA_GATHER_AUTO && can_bulk && p.row_bytes >= 2048);
+  // AUTO: TMA bulk copies for long aligned rows once there is enough work to fill the ring on every SM; a few rows (the
+  // 80-frame env-major reorder of config C2) finish sooner on the segmented vector path
+  const bool enough = p.n_idx * p.row_bytes >= (int64_t(16) << 20);
+  const bool use_bulk = mode == XA_GATHER_BULK || (mode == XA_GATHER_AUTO && can_bulk && p.row_bytes >= 2048 && enough);
   if (use_bulk) {
     // Bytes in flight per SM decide the rate, and more is NOT better: measured on B200 (scripts/
     // gather_microbench2.py, 32768 rows of 28224 B, random permutation) ~55 KB per SM peaks at 6.45 TB/s
@@ -319,7 +389,7 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
     // 16-B-multiple chunks of <= 16 KB and the ring holds ~56 KB: 4 stages of half a frame for 84x84x4.
     // (XA_GATHER_* environment variables are tuning knobs for the microbenchmarks, honoured only under XA_TUNING=1.)
     const BulkTuning tune = bulk_tuning();
-    p.chunks_per_row = static_cast<int>((p.row_bytes + tune.max_chunk - 1) / tune.max_chunk);
+    p.chunks_per_row = chunks_per_row_for(p.row_bytes, tune.max_chunk);
     int64_t chunk = (p.row_bytes + p.chunks_per_row - 1) / p.chunks_per_row;
     chunk = (chunk + 15) & ~int64_t(15);
     p.chunk_bytes = static_cast<uint32_t>(chunk);
@@ -425,6 +495,54 @@ int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, i
   XA_REQUIRE(mode >= XA_GATHER_AUTO && mode <= XA_GATHER_VECTOR, XA_EINVAL, "xa_gather_minibatch: unknown mode %d", mode);
   if (int rc = fill_fields(p, "xa_gather_minibatch", field_src, field_dst, n_fields)) return rc;
   return launch_rows(p, mode, static_cast<cudaStream_t>(stream), "xa_gather_minibatch");
+}
+
+int xa_gather_progress_units(int64_t row_bytes) {
+  if (row_bytes <= 0) return 0;
+  return chunks_per_row_for(row_bytes, bulk_tuning().max_chunk);
+}
+
+int xa_gather_rows_progress(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src_rows,
+                            int n_steps, int n_envs, uint32_t* progress, int64_t row_offset, int64_t rows_per_epoch, int64_t mb_rows,
+                            xa_stream_t stream) {
+  GatherParams p;
+  if (int rc = fill_common(p, "xa_gather_rows_progress", src, idx, dst, n_idx, row_bytes, n_src_rows, n_steps, n_envs)) return rc;
+  XA_REQUIRE(progress != nullptr && xa::aligned(progress, 4), XA_EINVAL, "xa_gather_rows_progress: progress must be a 4-byte aligned device pointer");
+  XA_REQUIRE(rows_per_epoch > 0 && mb_rows > 0 && mb_rows <= rows_per_epoch && row_offset >= 0, XA_EINVAL,
+             "xa_gather_rows_progress: rows_per_epoch=%lld mb_rows=%lld row_offset=%lld", static_cast<long long>(rows_per_epoch),
+             static_cast<long long>(mb_rows), static_cast<long long>(row_offset));
+  XA_REQUIRE(row_offset + n_idx < (int64_t(1) << 32), XA_EOVERFLOW, "xa_gather_rows_progress: row_offset + n_idx exceeds 32 bits");
+  p.progress = progress;
+  p.row_offset = static_cast<uint32_t>(row_offset);
+  p.rows_per_epoch = static_cast<uint32_t>(rows_per_epoch);
+  p.mb_rows = static_cast<uint32_t>(mb_rows);
+  p.mbs_per_epoch = static_cast<uint32_t>((rows_per_epoch + mb_rows - 1) / mb_rows);
+  return launch_rows(p, XA_GATHER_BULK, static_cast<cudaStream_t>(stream), "xa_gather_rows_progress");
+}
+
+// cuStreamWaitValue32(stream, addr, value, GEQ): the stream's later work starts once *addr - value >= 0 (cyclic 32-bit compare).
+// Resolved through the runtime (no link-time dependency on libcuda).
+int xa_stream_wait_geq_u32(xa_stream_t stream, const uint32_t* addr, uint32_t value) {
+  typedef int (*wait_fn)(void*, unsigned long long, unsigned int, unsigned int);
+  static wait_fn fn = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<wait_fn>(sym);
+    else
+      cudaGetLastError();
+    looked = true;
+  }
+  XA_REQUIRE(fn != nullptr, XA_EINVAL, "xa_stream_wait_geq_u32: the driver does not export cuStreamWaitValue32");
+  XA_REQUIRE(addr != nullptr && xa::aligned(addr, 4), XA_EINVAL, "xa_stream_wait_geq_u32: bad address");
+  const int rc = fn(stream, reinterpret_cast<unsigned long long>(addr), value, 1u /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (rc != 0) {
+    xa::set_error("xa_stream_wait_geq_u32: cuStreamWaitValue32 failed with CUresult %d", rc);
+    return rc;
+  }
+  return XA_OK;
 }
 
 int xa_gather_rows_u8_scaled_f32(const uint8_t* src, const int32_t* idx, float* dst, int64_t n_idx, int64_t row_bytes,

@@ -103,12 +103,25 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a)
 // collective C1 and of the optimiser -- is PRODUCED by a kernel that consumes d loss / d(actor_out, critic_out) of this
 // minibatch, as in training.  6.75 MB written per call for the Nature CNN's 1.69 M parameters.
 __global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float* __restrict__ d_actor, const float* __restrict__ d_values,
-                                                                     int64_t n, int n_actions, float* __restrict__ grad, int64_t n_params) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-  const int64_t na = n * n_actions;
-  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < n_params; j += stride) {
-    const float a = __ldg(d_actor + j % na), v = __ldg(d_values + j % n);
-    grad[j] = a + 0.5f * v;
+                                                                     uint32_t n, uint32_t na, float* __restrict__ grad, int64_t n_params) {
+  // one float4 of "parameter gradients" per thread and pass; 32-bit index arithmetic (n_params, n * A < 2^31 are checked)
+  const uint32_t n4 = static_cast<uint32_t>(n_params / 4);
+  const uint32_t stride = gridDim.x * kThreads;
+  for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n4; q += stride) {
+    const uint32_t j = q * 4u;
+    uint32_t ia = j % na, iv = j % n;
+    float out[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      out[c] = __ldg(d_actor + ia) + 0.5f * __ldg(d_values + iv);
+      ia = ia + 1 == na ? 0 : ia + 1;
+      iv = iv + 1 == n ? 0 : iv + 1;
+    }
+    reinterpret_cast<float4*>(grad)[q] = make_float4(out[0], out[1], out[2], out[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < static_cast<uint32_t>(n_params % 4)) {
+    const uint32_t j = n4 * 4u + threadIdx.x;
+    grad[j] = __ldg(d_actor + j % na) + 0.5f * __ldg(d_values + j % n);
   }
 }
 
@@ -140,9 +153,12 @@ int xa_grad_from_outputs_f32(const float* d_actor, const float* d_values, int64_
   XA_REQUIRE(d_actor && d_values && grad, XA_EINVAL, "xa_grad_from_outputs_f32: null pointer");
   XA_REQUIRE(n > 0 && n_actions > 0 && n_params > 0, XA_EINVAL, "xa_grad_from_outputs_f32: n=%lld n_actions=%d n_params=%lld",
              static_cast<long long>(n), n_actions, static_cast<long long>(n_params));
-  const int64_t want = (n_params + kThreads - 1) / kThreads;
-  grad_from_outputs_kernel<<<static_cast<unsigned>(want > kMaxBlocks ? kMaxBlocks : want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_actor, d_values, n, n_actions, grad, n_params);
+  XA_REQUIRE(n_params < (int64_t(1) << 31) && n * n_actions < (int64_t(1) << 31), XA_EOVERFLOW, "xa_grad_from_outputs_f32: sizes exceed 32-bit indices");
+  XA_REQUIRE(xa::aligned(grad, 16), XA_EALIGN, "xa_grad_from_outputs_f32: grad must be 16-byte aligned");
+  const int64_t want = (n_params / 4 + kThreads - 1) / kThreads;
+  const unsigned grid = static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
+  grad_from_outputs_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_actor, d_values, static_cast<uint32_t>(n), static_cast<uint32_t>(n * n_actions), grad, n_params);
   return xa::check_launch("xa_grad_from_outputs_f32");
 }
 

@@ -33,7 +33,7 @@ import torch
 
 from . import _ffi
 from ._ffi import XA_MOMENT_STRIDE
-from .ops import ACTOR_KINDS, GATHER_MODES, SCAN_MODES
+from .ops import ACTOR_KINDS, GATHER_MODES, SCAN_MODES, _count
 
 
 def _p(t):
@@ -46,7 +46,7 @@ class PPOHotPath:
     def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
                  gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
                  actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
-                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None):
+                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None, sync='auto'):
         """`buffers`: existing time-major device tensors to run on instead of allocating (any of ROLLOUT_FIELDS and
         'returns') -- the agents pass their own `ro_*` rollout buffers, so the pipeline works in place (no copies)."""
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
@@ -68,6 +68,18 @@ class PPOHotPath:
         self.gather_mode, self.scan_mode = gather_mode, scan_mode
         self.comm = comm
         self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
+        # How the losses learn that their minibatch is staged.  'event': one CUDA event per gather launch (a loss waits for its
+        # whole launch).  'progress': the gather kernel counts finished rows per minibatch in device memory and the compute
+        # stream waits on the counter of ITS minibatch (cuStreamWaitValue32), so one long launch -- full HBM rate, no launch
+        # gaps -- feeds the per-minibatch chain loss -> backward -> all-reduce -> Adam as soon as each minibatch is complete.
+        # 'auto' = 'progress' whenever the rows go through the TMA bulk path and the scalar fields are fused into the loss.
+        assert sync in ('auto', 'event', 'progress'), f'unknown sync mode `{sync}`'
+        row_b = self._row_bytes(obs_shape, obs_dtype)
+        bulk_ok = gather_mode != 'vector' and row_b % 16 == 0 and self.fuse_fields and self.overlap and self.device.type == 'cuda'
+        if sync == 'progress':
+            assert bulk_ok, 'progress sync needs 16-byte aligned rows (TMA bulk path), fused fields, the data stream and a CUDA device'
+        worthwhile = row_b >= 2048 and self.B * row_b >= (16 << 20)          # where the gather's AUTO mode picks the bulk path
+        self.sync = 'progress' if (sync == 'progress' or (sync == 'auto' and bulk_ok and worthwhile)) else 'event'
         # minibatches moved per gather launch.  An int = fixed group size (1 = per minibatch, K*M = the whole
         # step, which is what get_mini_batches does: everything materialised before the first update); a list
         # = explicit schedule.  Default on one GPU: a taper -- half of what is left per launch, then (rest-1, 1):
@@ -76,7 +88,14 @@ class PPOHotPath:
         # one launch per epoch).  With ranks > 1: per epoch, the last epoch per minibatch, so that a single
         # loss + gradient all-reduce trails (measured at 8 GPUs: four trailing all-reduces cost ~10 %).
         per_epoch = len(self.slices)
-        if gather_chunk is None:
+        if gather_chunk is None and self.sync == 'progress':
+            # as few launches as memory allows: <= 16 GB per staging slot; everything in one launch / one slot when it fits
+            limit = max(1, int((16 << 30) // max(1, self.B * row_b)))
+            sizes, rest = [], self.n_mb
+            while rest > 0:
+                sizes.append(min(rest, limit))
+                rest -= sizes[-1]
+        elif gather_chunk is None:
             if comm is not None and comm.world_size > 1:
                 sizes = [per_epoch] * (self.K - 1) + [1] * per_epoch
             else:
@@ -216,14 +235,28 @@ class PPOHotPath:
             self._field_dst.append((ctypes.c_void_p * 4)(*[base + j * fsz for j in range(4)]))
         flat_off = list(self._offsets)                       # start of every minibatch in perms.view(-1)
         self._mb_place = []                                  # minibatch -> (group, slot, first row in the slot)
+        self._progress_sync = self.sync == 'progress' and self.device.type == 'cuda' and not getattr(self, '_capturing', False)
+        if self._progress_sync:
+            if getattr(self, 'progress', None) is None:
+                self.progress = torch.zeros(self.n_mb, dtype=torch.int32, device=self.device)      # cyclic counters, never reset
+                self._step_no = 0
+            self._units = lib.xa_gather_progress_units(self.row_bytes)
+            self._wait = lib.xa_stream_wait_geq_u32
+            self._wait_addr = [ctypes.c_void_p(self.progress.data_ptr() + 4 * i) for i in range(self.n_mb)]
+            self._wait_stream = sc
         for g in range(self.n_groups):
             first, slot = self.group_first[g], g % self.staging
             idx_addr = self.perms.data_ptr() + 4 * flat_off[first]
             obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * self.cap * self.row_bytes)
-            self._gathers.append((lib.xa_gather_minibatch,
-                                  (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
-                                   n_fields, ctypes.c_void_p(idx_addr), self.group_rows[g], T, E,
-                                   GATHER_MODES[self.gather_mode], sd)))
+            if self._progress_sync:
+                self._gathers.append((lib.xa_gather_rows_progress,
+                                      (_p(self.obs), ctypes.c_void_p(idx_addr), obs_dst, self.group_rows[g], self.row_bytes, N, T, E,
+                                       _p(self.progress), flat_off[first], N, B, sd)))
+            else:
+                self._gathers.append((lib.xa_gather_minibatch,
+                                      (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
+                                       n_fields, ctypes.c_void_p(idx_addr), self.group_rows[g], T, E,
+                                       GATHER_MODES[self.gather_mode], sd)))
             for mb in range(first, first + self.group_sizes[g]):
                 self._mb_place.append((g, slot, flat_off[mb] - flat_off[first]))
         for mb in range(self.n_mb):
@@ -286,6 +319,7 @@ class PPOHotPath:
         if two and self.fuse_fields:
             self._fork.record(cs)
             ds.wait_event(self._fork)
+        _count(self.kernel_launches_per_step - (0 if gae else 1))
         if gae:
             fn, args = self._gae
             self._check('gae', fn(*args))
@@ -297,6 +331,9 @@ class PPOHotPath:
         if self.comm is not None and self.comm.world_size > 1:
             with torch.cuda.stream(cs):                                         # ordered between the moments and the losses
                 self.comm.all_gather_moments(self.all_moments, self.moments)    # collective C2
+        progress = self._progress_sync
+        if progress:
+            self._step_no += 1
         for g in range(self.n_groups):
             fn, args = self._gathers[g]
             if two and g >= self.staging:
@@ -304,8 +341,12 @@ class PPOHotPath:
             self._check('gather', on_gather(g, fn, args) if on_gather is not None else fn(*args))
             if two:
                 self._gather_done[g].record(ds)
-                cs.wait_event(self._gather_done[g])
+                if not progress:
+                    cs.wait_event(self._gather_done[g])
             for i in range(self.group_first[g], self.group_first[g] + self.group_sizes[g]):
+                if progress:     # minibatch i is staged once its counter reached (launches so far) x (its rows) x (units per row)
+                    target = (self._step_no * self.mb_rows[i] * self._units) & 0xffffffff
+                    self._check('wait', self._wait(self._wait_stream, self._wait_addr[i], target))
                 if before_loss is not None:
                     before_loss(i)
                 fn, args = self._losses[i]
@@ -314,6 +355,8 @@ class PPOHotPath:
                     after_loss(i)
             if two:
                 self._loss_done[g].record(cs)
+        if progress:
+            cs.wait_event(self._gather_done[self.n_groups - 1])                 # formal join: the gather KERNELS are done too
 
     # ---------------------------------------------------------------------------------- CUDA graph
     def capture(self):
@@ -328,6 +371,7 @@ class PPOHotPath:
         graph = torch.cuda.CUDAGraph()
         capture_stream = torch.cuda.Stream(self.device)
         eager_streams = (self.compute_stream, self.data_stream)
+        self._capturing = True                               # a captured step orders by events (no stream memory ops in the graph)
         with torch.cuda.stream(capture_stream):
             self.prepare(capture_stream)                    # re-resolve the launches onto the capturing stream
             self.run()                                      # warm-up outside the capture (lazy module loading)
@@ -335,6 +379,7 @@ class PPOHotPath:
             with torch.cuda.graph(graph, stream=capture_stream):
                 self.run()
         self._graph = graph                                  # keep alive
+        self._capturing = False
         self.prepare(eager_streams[0])                       # eager path stays usable
         return graph.replay
 
@@ -439,6 +484,7 @@ class A2CHotPath:
         for tag, on, (fn, args) in (('nstep_returns', returns, self._returns), ('a2c_loss', loss, self._loss)):
             if not on:
                 continue
+            _count()
             rc = fn(*args)
             if rc != 0:
                 raise _ffi.XAError(tag, rc, _ffi.lib().xa_last_error().decode('utf-8', 'replace'))

@@ -197,7 +197,8 @@ def gather_minibatch(obs, fields, idx, *, time_major=None, mode='auto', out_obs=
     _call(s, 'xa_gather_minibatch', _ptr(s), _tptr(dst), row_bytes, n_rows, fsrc, fdst, len(arrs), _ptr(i), n, T, E,
               GATHER_MODES[mode], stream)
     # bulk path: one kernel; vector path: rows kernel + fields kernel
-    _count(1 if (mode == 'bulk' or (mode == 'auto' and row_bytes >= 2048 and row_bytes % 16 == 0)) else 1 + (len(arrs) > 0))
+    bulk = mode == 'bulk' or (mode == 'auto' and row_bytes >= 2048 and row_bytes % 16 == 0 and n * row_bytes >= (16 << 20))
+    _count(1 if bulk else 1 + (len(arrs) > 0))
     return dst, outs
 
 
