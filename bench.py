@@ -48,7 +48,9 @@ def parse_args():
     ap.add_argument('--gather-mode', default='auto', choices=['auto', 'bulk', 'vector'])
     ap.add_argument('--no-overlap', action='store_true', help='gathers on the compute stream instead of a data stream')
     ap.add_argument('--staging', type=int, default=2)
-    ap.add_argument('--sync', default='auto', choices=['auto', 'event', 'progress'], help='how losses learn their minibatch is staged (hotpath.PPOHotPath)')
+    ap.add_argument('--static-gather', action='store_true', help='deal the gather items statically instead of through a work counter')
+    ap.add_argument('--late-fork', action='store_true', help='start the data stream after GAE + moments instead of beside them')
+    ap.add_argument('--sync', default='auto', choices=['auto', 'event', 'progress', 'progress-memop'], help='how losses learn their minibatch is staged (hotpath.PPOHotPath)')
     ap.add_argument('--gather-chunk', type=int, default=None, help='minibatches per gather launch (default: tapered schedule)')
     ap.add_argument('--gather-schedule', default=None, help='explicit launch schedule, e.g. 4,4,4,3,1')
     ap.add_argument('--c1', default='auto', choices=['auto', 'nccl', 'fused', 'none'],
@@ -57,6 +59,7 @@ def parse_args():
     ap.add_argument('--network', default='stand-in', choices=['stand-in', 'nature-tc'],
                     help='nature-tc: the real Nature CNN forward/backward on the tcgen05 kernels inside the step (secondary metric)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-clock-sampler', action='store_true', help='diagnostic: no NVML polling thread beside the timed region')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-single-gpu-compare', action='store_true', help='N>1: skip the 1-GPU runs at the same per-GPU n_envs / at C4')
     ap.add_argument('--no-parity-check', action='store_true', help='N>1: skip the sharded-vs-oracle check before timing')
@@ -110,9 +113,10 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mem = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_MEM)
                 power = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
                 bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
-                self.samples.append((float(sm), power, [n for n, m in masks if bits & m]))
+                self.samples.append((float(sm), power, [n for n, m in masks if bits & m], float(mem)))
             except Exception:
                 pass
             time.sleep(self.period_s)
@@ -159,8 +163,11 @@ class ClockSampler:
             used = self.samples[first:] or self.samples[-1:]
             sm = [x[0] for x in used]
             reasons = sorted({r for x in used for r in x[2]})
-            return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.sm_max,
-                    'power_w_max': max((x[1] for x in used), default=None), 'samples': len(sm), 'reasons': reasons,
+            mem = [x[3] for x in used]
+            return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.sm_max, 'sm_min_mhz_seen': min(sm) if sm else None,
+                    'mem_mhz': statistics.median(mem) if mem else None, 'mem_min_mhz_seen': min(mem) if mem else None,
+                    'power_w_max': max((x[1] for x in used), default=None),
+                    'power_w_median': statistics.median([x[1] for x in used]) if used else None, 'samples': len(sm), 'reasons': reasons,
                     'source': 'nvml, sampled every %.0f ms from the start of the timed region' % (self.period_s * 1e3)}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -364,7 +371,8 @@ def build_ppo(args, dev, comm, E, T, shape, dtype, A, n_params, rank, c1, networ
     else:
         net = SyntheticNetwork(dev, comm, n_params, optimizer=not args.no_optimizer, c1=c1)
     agent = PPO(envs, net, n_steps=T, quiet=True, device=dev)
-    opts = dict(gather_mode=args.gather_mode, staging=args.staging, overlap=not args.no_overlap, sync=args.sync)
+    opts = dict(gather_mode=args.gather_mode, staging=args.staging, overlap=not args.no_overlap, sync=args.sync,
+                dynamic=not args.static_gather, late_fork=args.late_fork)
     if args.gather_schedule:
         opts['gather_chunk'] = [int(x) for x in args.gather_schedule.split(',')]
     elif args.gather_chunk:
@@ -543,7 +551,7 @@ def run_ppo(args):
 
     # the sampler starts before the warm-up (nvidia-smi, the fallback, takes ~100 ms to start); with NVML only the samples
     # taken inside the timed region are reported
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clock_sampler) else None
     if sampler:
         sampler.start()
     warmup = max(args.warmup, 3)
@@ -712,6 +720,7 @@ def run_ppo(args):
         'metric': METRIC if args.network == 'stand-in' else 'ppo_env_steps_per_sec_update_phase_with_network',
         'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
         'ms_per_step': ms_per_step, 'ms_per_step_median': med, 'ms_per_step_min': min(per_step), 'ms_per_step_max': max(per_step),
+        'ms_per_step_each': [round(x, 4) for x in per_step], 'gather_launch_ms_each': [round(x, 3) for x in gather_ms],
         'value_at_median_step': N * 1e3 / med * world if world == 1 else None,
         'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong',
         'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars' if dtype == 'uint8' else 'f32', 'data': 'synthetic',

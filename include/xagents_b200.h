@@ -99,12 +99,19 @@ int xa_gather_minibatch(const void* obs_src, void* obs_dst, int64_t row_bytes, i
  *   m = e * ceil(rows_per_epoch / mb_rows) + (g - e * rows_per_epoch) / mb_rows,  g = row_offset + i, e = g / rows_per_epoch
  * and progress[m] (device uint32, never reset: cyclic) grows by xa_gather_progress_units(row_bytes) per finished row, after
  * the row's bytes are written.  A consumer orders its stream after minibatch m of the s-th launch over these counters with
- * xa_stream_wait_geq_u32(stream, progress + m, s * rows_in_m * units)  (cuStreamWaitValue32, cyclic >=). */
+ * xa_stream_wait_geq_u32(stream, progress + m, s * rows_in_m * units)  (cuStreamWaitValue32, cyclic >=).  `progress`
+ * may be NULL (no counters).  `work` (NULL, or two zero-filled device uint32 words that the kernel leaves zeroed again, not
+ * shared by launches that can run concurrently) switches from static dealing of the copy items to a work counter: the launch
+ * then no longer runs at the pace of its slowest CTA when other kernels share the SMs. */
 int xa_gather_progress_units(int64_t row_bytes);
 int xa_gather_rows_progress(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes,
                             int64_t n_src_rows, int n_steps, int n_envs, uint32_t* progress, int64_t row_offset,
-                            int64_t rows_per_epoch, int64_t mb_rows, xa_stream_t stream);
+                            int64_t rows_per_epoch, int64_t mb_rows, uint32_t* work, xa_stream_t stream);
 int xa_stream_wait_geq_u32(xa_stream_t stream, const uint32_t* addr, uint32_t value);
+/* The same wait as a one-warp spin kernel on `stream` (bounded, ~2 s: on expiry *status -- device int, may be NULL -- is set
+ * to 1 and the stream goes on).  Wakes within a microsecond of the publication; the front-end wait above re-polls long waits
+ * only every few milliseconds on B200. */
+int xa_wait_progress_u32(const uint32_t* addr, uint32_t target, int* status, xa_stream_t stream);
 
 /* BaseAgent.get_model_outputs image scaling, xagents/base.py:505-506, fused behind the gather:
  * dst fp32 [n_idx, row_bytes] = float(src u8) / 255.0f (true division). */

@@ -35,7 +35,7 @@ def run(T, E, epochs, reps=10, sampler=False, gap_ms=0.0, progress=False):
 
     def launch():
         if progress:
-            rc = lib.xa_gather_rows_progress(P(obs), P(perms), P(dst), rows, F, N, T, E, P(prog), 0, N, max(1, N // 4), st)
+            rc = lib.xa_gather_rows_progress(P(obs), P(perms), P(dst), rows, F, N, T, E, P(prog), 0, N, max(1, N // 4), None, st)
         else:
             rc = lib.xa_gather_rows(P(obs), P(perms), P(dst), rows, F, N, T, E, 1, st)
         assert rc == 0, lib.xa_last_error()

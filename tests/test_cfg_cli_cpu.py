@@ -327,7 +327,7 @@ def test_batched_device_environment_keeps_the_step_envs_contract():
     assert agent.games == n_done > 10 and list(agent.total_rewards) == [float(x) for x in finished][-100:]
     assert np.allclose(agent._episode_sums.numpy(), sums)
     agent.update_metrics()
-    assert agent.mean_reward == pytest.approx(np.mean(finished[-100:]))
+    assert agent.mean_reward == pytest.approx(np.around(np.mean(finished[-100:]), 2))      # rounded like base.py:289-291
     assert agent.step_envs(torch.zeros(6)) == []
 
 
@@ -396,3 +396,34 @@ def test_step_envs_columns_for_a_list_of_environments():
     assert agent.games == finished > 5 and agent.steps == 60 and len(agent.total_rewards) == finished
     vector = BaseAgent(envs.create_envs('CartPole-v1', 3, preprocess=False), None, quiet=True, device='cpu')
     assert [c.dtype for c in vector.step_envs(np.zeros(3, np.int64), True)] == [np.float32] * 5
+
+
+def test_plateau_learning_rate_reduction_and_early_stop_follow_the_reference():
+    """base.py:213-230, 270-291, 333-335: under `divergence_monitoring_steps` a mean reward that does not beat the best one
+    counts towards a plateau; `plateau_reduce_patience` plateaus scale the learning rate by `plateau_reduce_factor` and count
+    towards early stopping; a new best reward resets both counters."""
+    import types
+
+    from xagents_b200.agents import BaseAgent
+    made = envs.create_envs('SyntheticAtariDevice-v0', 2, preprocess=True, device='cpu')
+    model = types.SimpleNamespace(lr=1e-3)
+    agent = BaseAgent(made, model, n_steps=4, quiet=True, device='cpu', divergence_monitoring_steps=10, plateau_reduce_factor=0.5,
+                      plateau_reduce_patience=2, early_stop_patience=2)
+    agent.max_steps = 10 ** 9
+    agent.steps = 5
+    agent.total_rewards.extend([1.0, 3.0])
+    agent.update_metrics()                                         # below divergence_monitoring_steps: nothing counts
+    assert (agent.plateau_count, agent.early_stop_count, agent.mean_reward, model.lr) == (0, 0, 2.0, 1e-3)
+    agent.steps = 20
+    agent.update_metrics()                                         # mean 2.0 becomes the best reward: counters reset
+    assert agent.best_reward == 2.0 and agent.plateau_count == 1   # ... and mean <= best already counts (the reference's order)
+    agent.update_metrics()
+    assert agent.plateau_count == 0 and agent.early_stop_count == 1 and model.lr == pytest.approx(5e-4)
+    assert not agent.training_done()
+    agent.update_metrics()
+    agent.update_metrics()
+    assert agent.early_stop_count == 2 and model.lr == pytest.approx(2.5e-4) and agent.training_done()
+    agent.total_rewards.extend([50.0] * 100)                       # a better mean arrives: both counters start over
+    agent.update_metrics()                                         # (this call still sees the old mean ...)
+    agent.update_metrics()                                         # (... the next one the new best)
+    assert agent.best_reward == 50.0 and agent.early_stop_count == 0 and not agent.training_done()

@@ -507,12 +507,13 @@ def test_hotpath_pipeline_vs_oracle(T, E, mb, fuse, chunk, overlap, staging):
     _check_pipeline(T, E, mb, fuse, chunk, overlap, staging, 'event')
 
 
+@pytest.mark.parametrize('sync', ['progress', 'progress-memop'])
 @pytest.mark.parametrize('chunk,staging', [(None, 2), (3, 2), (1, 1), ('schedule', 2), (5, 3)])
 @pytest.mark.parametrize('T,E,mb', [(16, 8, 4), (7, 3, 4)])
-def test_hotpath_progress_sync_vs_oracle(T, E, mb, chunk, staging):
-    """The same pipeline with per-minibatch completion counters (sync='progress': the gather kernel publishes finished rows,
-    the compute stream waits on its minibatch's counter with cuStreamWaitValue32) instead of one event per gather launch."""
-    _check_pipeline(T, E, mb, True, chunk, True, staging, 'progress')
+def test_hotpath_progress_sync_vs_oracle(T, E, mb, chunk, staging, sync):
+    """The same pipeline with per-minibatch completion counters (the gather kernel publishes finished rows; the compute stream
+    waits on its minibatch's counter with a one-warp spin kernel, or with cuStreamWaitValue32) instead of one event per launch."""
+    _check_pipeline(T, E, mb, True, chunk, True, staging, sync)
 
 
 def _check_pipeline(T, E, mb, fuse, chunk, overlap, staging, sync):
@@ -546,6 +547,7 @@ def _check_pipeline(T, E, mb, fuse, chunk, overlap, staging, sync):
         seen.clear()
         hp.run(after_loss=after_loss)
         torch.cuda.synchronize()
+        assert getattr(hp, 'wait_status', None) is None or int(hp.wait_status.item()) == 0      # no device-side wait gave up
         assert np.array_equal(hp.returns.cpu().numpy(), want['returns'])
         sc = hp.scalars.cpu().numpy()
         assert len(want['minibatches']) == hp.n_mb

@@ -72,7 +72,8 @@ PROTOTYPES = {
                                            c_stream]),
     'xa_gather_progress_units': (ctypes.c_int, [ctypes.c_int64]),
     'xa_gather_rows_progress': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_stream]),
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, c_stream]),
+    'xa_wait_progress_u32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, c_stream]),
     'xa_stream_wait_geq_u32': (ctypes.c_int, [c_stream, ctypes.c_void_p, ctypes.c_uint32]),
     'xa_gather_rows_u8_scaled_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                     ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_stream]),

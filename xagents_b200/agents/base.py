@@ -93,6 +93,8 @@ class BaseAgent:
         self.games = 0
         self.episode_rewards = np.zeros(self.n_envs)
         self.done_envs = 0
+        self.plateau_count = 0
+        self.early_stop_count = 0
         if seed:
             self.set_seeds(seed)
         self.reset_envs()
@@ -214,13 +216,33 @@ class BaseAgent:
 
     # ------------------------------------------------------------------ driver
     def update_metrics(self):
+        """base.py:213-230, 260-291: best reward follows the mean (the reference's `checkpoint()`; saving weights is out of
+        scope), plateau / early-stop counters under `divergence_monitoring_steps`, learning-rate reduction on a plateau, frame
+        speed, then the new mean reward -- in the reference's order, so the plateau test sees the PREVIOUS mean."""
         self._flush_episode_log()
-        self.mean_reward = float(np.mean(self.total_rewards)) if self.total_rewards else -float('inf')
-        self.best_reward = max(self.best_reward, self.mean_reward)
+        if self.mean_reward > self.best_reward:
+            self.plateau_count = 0
+            self.early_stop_count = 0
+            self.display_message(f'Best reward updated: {self.best_reward} -> {self.mean_reward}')
+        self.best_reward = max(self.mean_reward, self.best_reward)
+        if (self.divergence_monitoring_steps and self.steps >= self.divergence_monitoring_steps
+                and self.mean_reward <= self.best_reward):
+            self.plateau_count += 1
+        if self.plateau_count >= self.plateau_reduce_patience:
+            for model in self.output_models:                       # adapters carry the optimiser's learning rate as `.lr`
+                net = getattr(self, 'net', None) if not hasattr(model, 'lr') else model
+                if net is not None and hasattr(net, 'lr'):
+                    new_lr = net.lr * self.plateau_reduce_factor
+                    self.display_message(f'Learning rate reduced {net.lr} -> {new_lr}')
+                    net.lr = new_lr
+            self.plateau_count = 0
+            self.early_stop_count += 1
         now = perf_counter()
         since = self.last_reset_time if self.last_reset_time is not None else now        # metrics asked for outside fit()
         self.frame_speed = (self.steps - self.last_reset_step) / max(now - since, 1e-9)
         self.last_reset_step, self.last_reset_time = self.steps, now
+        self.mean_reward = (float(np.around(np.mean(self.total_rewards), self.display_precision)) if self.total_rewards
+                            else -float('inf'))
 
     def display_metrics(self):
         elapsed = perf_counter() - self.training_start_time
@@ -245,6 +267,9 @@ class BaseAgent:
             total, count, steps = comm.sum_over_ranks([float(np.sum(self.total_rewards)), len(self.total_rewards), self.steps])
             mean_reward = total / count if count else -float('inf')
             steps = int(steps)
+        if self.early_stop_count >= self.early_stop_patience:      # base.py:333-335
+            self.display_message('Early stopping')
+            return True
         if self.target_reward is not None and mean_reward >= self.target_reward:
             self.display_message(f'Reward achieved in {steps} steps')
             return True

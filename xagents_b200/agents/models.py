@@ -23,7 +23,11 @@ from ..optim import FlatAdam
 
 class TorchModel:
     def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
-                 comm=None, tensor_core_inference=False, graph_inference=True, role='actor_critic'):
+                 comm=None, tensor_core_inference=False, graph_inference=True, role='actor_critic', fused_c1='auto'):
+        """`fused_c1` (sharded training, comm.world_size > 1): 'auto' / True = the gradient all-reduce, the global-norm clip
+        and Adam run as ONE kernel over NVLink peer memory (xagents_b200/peer.py) when the box can map peer memory -- the flat
+        parameter and gradient buffers then live in peer-mapped memory and Adam's m, v exist only for this rank's shard;
+        False = NCCL all-reduce + the two-launch clip+Adam."""
         assert role in ('actor_critic', 'actor', 'critic'), f'unknown model role `{role}`'
         self.module = module
         self.role = role                                          # 'actor' / 'critic': TRPO's separate single-output networks
@@ -38,10 +42,21 @@ class TorchModel:
         assert dev.type == 'cuda', 'the model must live on the GPU: xagents_b200 has no CPU path'
         n = sum(p.numel() for p in params)
         pad = (-n) % 4                                            # float4 path of the optimiser kernel
-        self.flat_param = torch.zeros(n + pad, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros_like(self.flat_param)
-        self.optimizer = FlatAdam(self.flat_param, self.flat_grad, lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
-        self.m, self.v, self.workspace = self.optimizer.m, self.optimizer.v, self.optimizer.workspace
+        self.fused = None
+        if fused_c1 and comm is not None and comm.world_size > 1:
+            from .. import peer
+            if peer.available(comm):
+                self.fused = peer.FusedAllReduceAdam(comm, n, lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
+            else:
+                assert fused_c1 == 'auto', f'no peer-memory transport on this box: {peer.probe_errors()}'
+        if self.fused is not None:
+            self.flat_param, self.flat_grad = self.fused.param, self.fused.grad      # peer-mapped, padded to world * shard
+            self.optimizer, self.m, self.v, self.workspace = None, self.fused.m, self.fused.v, None
+        else:
+            self.flat_param = torch.zeros(n + pad, dtype=torch.float32, device=dev)
+            self.flat_grad = torch.zeros_like(self.flat_param)
+            self.optimizer = FlatAdam(self.flat_param, self.flat_grad, lr=lr, beta1=beta1, beta2=beta2, eps=epsilon)
+            self.m, self.v, self.workspace = self.optimizer.m, self.optimizer.v, self.optimizer.workspace
         off = 0
         for p in params:                                          # re-seat parameters and grads as views
             k = p.numel()
@@ -99,12 +114,18 @@ class TorchModel:
         pairs = [(o, g) for o, g in ((actor, d_actor), (critic, d_values)) if o is not None]
         torch.autograd.backward([o for o, _ in pairs], [g.view_as(o) for o, g in pairs])
         self._outputs = None
+        self.step += 1
+        if self.fused is not None:                                # collective C1 + clip + Adam: one kernel over peer memory
+            self.fused.lr = self.lr
+            self.fused.step(self.step, grad_norm)
+            for mod in self._refreshable:
+                mod.refresh()
+            return
         scale = 1.0
         if self.comm is not None and self.comm.world_size > 1:
-            self.comm.all_reduce_gradients_async(self.flat_grad)  # collective C1
-            self.comm.wait_gradients()
+            self.comm.all_reduce_gradients_async(self.flat_grad)  # collective C1 (NCCL, comm stream) ...
+            self.comm.wait_gradients()                            # ... which the optimiser has to wait for
             scale = 1.0 / self.comm.world_size
-        self.step += 1
         opt = self.optimizer
         opt.t, opt.lr = self.step - 1, self.lr                    # `step` and `lr` stay the attributes callers may set
         opt.step(grad_norm, scale)

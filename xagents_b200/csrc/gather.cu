@@ -41,6 +41,9 @@ struct GatherParams {
   // fine-grained completion (bulk path): progress[m] += chunks finished, m = the minibatch a destination row belongs to
   uint32_t* progress;
   uint32_t row_offset, rows_per_epoch, mb_rows, mbs_per_epoch;
+  // dynamic work distribution (bulk path): work[0] = next item to hand out, work[1] = lanes that have finished; both zero at
+  // launch, and the last lane to finish zeroes them again.  nullptr: items are dealt statically (item k -> CTA k mod grid).
+  uint32_t* work;
   int n_fields;
   const float* fsrc[XA_MAX_FIELDS];
   float* fdst[XA_MAX_FIELDS];
@@ -63,7 +66,11 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
     const uint64_t policy = xa::policy_evict_first();
     const int64_t n_items = p.n_idx * p.chunks_per_row;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * stages;
-    int64_t k = static_cast<int64_t>(blockIdx.x) * stages + warp;
+    // Static dealing makes the launch as slow as its slowest CTA: when other kernels hold SMs at launch time the block
+    // scheduler doubles gather CTAs up on the free SMs for the whole persistent launch, and kernels that come and go beside
+    // it (losses, optimiser) slow the CTAs they share an SM with.  With a work counter every lane takes the next item when it
+    // is ready for one (the ticket for item k+1 is drawn while item k's copy is in flight, so its latency is hidden).
+    int64_t k = p.work ? static_cast<int64_t>(atomicAdd(p.work, 1u)) : static_cast<int64_t>(blockIdx.x) * stages + warp;
     uint32_t parity = 0;
     int32_t b = k < n_items ? p.idx[k / p.chunks_per_row] : 0;
     // Fine-grained completion: this warp's items ascend, so the minibatch they belong to only moves forward.  `mb_end` is
@@ -113,8 +120,8 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
         xa::bulk_g2s(buf, p.src + row * p.row_bytes + off, bytes, bar, policy);
       else
         xa::bulk_g2s_nohint(buf, p.src + row * p.row_bytes + off, bytes, bar);
-      const int64_t kn = k + stride;
-      if (kn < n_items) b = p.idx[kn / p.chunks_per_row];  // next index travels under the copy
+      const int64_t kn = p.work ? static_cast<int64_t>(atomicAdd(p.work, 1u)) : k + stride;
+      if (kn < n_items) b = p.idx[kn / p.chunks_per_row];  // next ticket and next index travel under the copy
       xa::mbar_wait(bar, parity);
       parity ^= 1u;
       if (p.store_hint)
@@ -130,12 +137,17 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1)) gather_bulk_kernel(cons
         pend_count = 0;
       }
       xa::bulk_wait_read<0>();  // the engine has read the stage out: it may be refilled
+      if (p.work) k = kn - stride;  // the loop increment adds `stride` back: k becomes the ticket drawn above
     }
     xa::bulk_wait_all<0>();
     if (p.progress) {
       __threadfence();
       if (pend_count) atomicAdd(p.progress + pend_mb, pend_count);
       if (cur_count) atomicAdd(p.progress + cur_mb, cur_count);
+    }
+    if (p.work && atomicAdd(p.work + 1, 1u) == gridDim.x * static_cast<unsigned>(stages) - 1u) {
+      p.work[0] = 0;  // every lane has drawn its last ticket: leave the counter ready for the next launch
+      p.work[1] = 0;
     }
     return;
   }
@@ -253,6 +265,7 @@ struct BulkTuning {
   int stages = 0;                       // 0 = derived from target_inflight
   int load_hint = 1, store_hint = 1;    // L2 evict-first on both sides (hinting only the loads measured 2 % slower)
   int ctas_per_sm = 1;
+  int spread = 1;                       // pad the CTA's shared memory so that two gather CTAs never share an SM
   explicit BulkTuning(bool from_env) {
     if (!from_env) return;
     if (const char* e = getenv("XA_GATHER_CHUNK")) max_chunk = atoll(e) > 0 ? atoll(e) : max_chunk;
@@ -261,6 +274,7 @@ struct BulkTuning {
     if (const char* e = getenv("XA_GATHER_LOAD_HINT")) load_hint = atoi(e);
     if (const char* e = getenv("XA_GATHER_STORE_HINT")) store_hint = atoi(e);
     if (const char* e = getenv("XA_GATHER_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char* e = getenv("XA_GATHER_SPREAD")) spread = atoi(e);
   }
 };
 
@@ -401,10 +415,18 @@ int launch_rows(GatherParams p, int mode, cudaStream_t stream, const char* what)
     p.stages = stages;
     p.load_hint = tune.load_hint;
     p.store_hint = tune.store_hint;
-    const size_t smem = static_cast<size_t>(stages) * chunk + 8 * kMaxStages;
+    size_t smem = static_cast<size_t>(stages) * chunk + 8 * kMaxStages;
+    // One CTA per SM is the design (grid = SM count), but the block scheduler does not promise it: launched while other kernels
+    // are resident, the 148 CTAs were seen packed two per SM on half of the SMs for the whole persistent launch (measured: 3.7
+    // instead of 6.5 TB/s -- the per-SM load/store path, not HBM, then bounds it).  Asking for more than half of an SM's shared
+    // memory makes a second gather CTA on the same SM impossible.
+    const size_t spread_smem = 116 * 1024;
+    if (tune.spread && tune.ctas_per_sm <= 1 && smem < spread_smem) smem = spread_smem;
     if (int rc = allow_bulk_smem(what)) return rc;
     const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-    const int ctas_per_sm = static_cast<int>(kSmemBudget / (smem + 1024)) > 0 ? static_cast<int>(kSmemBudget / (smem + 1024)) : 1;
+    const int ctas_per_sm = static_cast<int>(kSmemBudget / (static_cast<size_t>(stages) * chunk + 8 * kMaxStages + 1024)) > 0
+                                ? static_cast<int>(kSmemBudget / (static_cast<size_t>(stages) * chunk + 8 * kMaxStages + 1024))
+                                : 1;
     const int64_t items = p.n_idx * p.chunks_per_row;
     int64_t grid = (items + stages - 1) / stages;
     const int cta_cap = tune.ctas_per_sm <= ctas_per_sm ? tune.ctas_per_sm : ctas_per_sm;
@@ -504,20 +526,44 @@ int xa_gather_progress_units(int64_t row_bytes) {
 
 int xa_gather_rows_progress(const void* src, const int32_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src_rows,
                             int n_steps, int n_envs, uint32_t* progress, int64_t row_offset, int64_t rows_per_epoch, int64_t mb_rows,
-                            xa_stream_t stream) {
+                            uint32_t* work, xa_stream_t stream) {
   GatherParams p;
   if (int rc = fill_common(p, "xa_gather_rows_progress", src, idx, dst, n_idx, row_bytes, n_src_rows, n_steps, n_envs)) return rc;
-  XA_REQUIRE(progress != nullptr && xa::aligned(progress, 4), XA_EINVAL, "xa_gather_rows_progress: progress must be a 4-byte aligned device pointer");
+  XA_REQUIRE(progress == nullptr || xa::aligned(progress, 4), XA_EALIGN, "xa_gather_rows_progress: progress must be 4-byte aligned");
   XA_REQUIRE(rows_per_epoch > 0 && mb_rows > 0 && mb_rows <= rows_per_epoch && row_offset >= 0, XA_EINVAL,
              "xa_gather_rows_progress: rows_per_epoch=%lld mb_rows=%lld row_offset=%lld", static_cast<long long>(rows_per_epoch),
              static_cast<long long>(mb_rows), static_cast<long long>(row_offset));
   XA_REQUIRE(row_offset + n_idx < (int64_t(1) << 32), XA_EOVERFLOW, "xa_gather_rows_progress: row_offset + n_idx exceeds 32 bits");
+  XA_REQUIRE(work == nullptr || xa::aligned(work, 8), XA_EALIGN, "xa_gather_rows_progress: work must be 8-byte aligned (two uint32 words)");
+  XA_REQUIRE(work == nullptr || n_idx * chunks_per_row_for(row_bytes, bulk_tuning().max_chunk) < (int64_t(1) << 31), XA_EOVERFLOW,
+             "xa_gather_rows_progress: too many items for a 32-bit work counter");
+  p.work = work;
   p.progress = progress;
   p.row_offset = static_cast<uint32_t>(row_offset);
   p.rows_per_epoch = static_cast<uint32_t>(rows_per_epoch);
   p.mb_rows = static_cast<uint32_t>(mb_rows);
   p.mbs_per_epoch = static_cast<uint32_t>((rows_per_epoch + mb_rows - 1) / mb_rows);
   return launch_rows(p, XA_GATHER_BULK, static_cast<cudaStream_t>(stream), "xa_gather_rows_progress");
+}
+
+// Device-side wait: a one-warp kernel that spins (nanosleep back-off) until *addr - target >= 0 (cyclic), so that the stream's
+// next kernel starts within a microsecond of the producer's publication.  cuStreamWaitValue32 does the same in the front-end,
+// but on B200 a wait that lasts more than ~0.5 ms is re-evaluated only every ~3 ms (measured: n_envs=2048, 0.6 ms per
+// minibatch -> steps of 9.1 or 12.2 ms), which is useless for a pipeline.  Bounded (~2 s): a producer that never publishes
+// sets *status = 1 instead of hanging the GPU.
+__global__ void wait_progress_kernel(const uint32_t* addr, uint32_t target, int* status) {
+  if (threadIdx.x != 0) return;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    if (static_cast<int32_t>(v - target) >= 0) return;
+    if (clock64() - t0 > 4000000000LL) {
+      if (status) atomicExch(status, 1);
+      return;
+    }
+    __nanosleep(100);
+  }
 }
 
 // cuStreamWaitValue32(stream, addr, value, GEQ): the stream's later work starts once *addr - value >= 0 (cyclic 32-bit compare).
@@ -543,6 +589,12 @@ int xa_stream_wait_geq_u32(xa_stream_t stream, const uint32_t* addr, uint32_t va
     return rc;
   }
   return XA_OK;
+}
+
+int xa_wait_progress_u32(const uint32_t* addr, uint32_t target, int* status, xa_stream_t stream) {
+  XA_REQUIRE(addr != nullptr && xa::aligned(addr, 4), XA_EINVAL, "xa_wait_progress_u32: bad address");
+  wait_progress_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(addr, target, status);
+  return xa::check_launch("xa_wait_progress_u32");
 }
 
 int xa_gather_rows_u8_scaled_f32(const uint8_t* src, const int32_t* idx, float* dst, int64_t n_idx, int64_t row_bytes,

@@ -46,7 +46,7 @@ class PPOHotPath:
     def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
                  gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
                  actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
-                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None, sync='auto'):
+                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None, sync='auto', dynamic=True, late_fork=False):
         """`buffers`: existing time-major device tensors to run on instead of allocating (any of ROLLOUT_FIELDS and
         'returns') -- the agents pass their own `ro_*` rollout buffers, so the pipeline works in place (no copies)."""
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
@@ -70,16 +70,21 @@ class PPOHotPath:
         self.fuse_fields, self.staging, self.overlap = bool(fuse_fields), max(1, int(staging)), bool(overlap)
         # How the losses learn that their minibatch is staged.  'event': one CUDA event per gather launch (a loss waits for its
         # whole launch).  'progress': the gather kernel counts finished rows per minibatch in device memory and the compute
-        # stream waits on the counter of ITS minibatch (cuStreamWaitValue32), so one long launch -- full HBM rate, no launch
+        # stream waits on the counter of ITS minibatch (a one-warp spin kernel; 'progress-memop': cuStreamWaitValue32, which
+        # B200 re-polls only every ~3 ms once a wait has lasted ~0.5 ms), so one long launch -- full HBM rate, no launch
         # gaps -- feeds the per-minibatch chain loss -> backward -> all-reduce -> Adam as soon as each minibatch is complete.
         # 'auto' = 'progress' whenever the rows go through the TMA bulk path and the scalar fields are fused into the loss.
-        assert sync in ('auto', 'event', 'progress'), f'unknown sync mode `{sync}`'
+        assert sync in ('auto', 'event', 'progress', 'progress-memop'), f'unknown sync mode `{sync}`'
+        # `dynamic` (progress mode): the gather's copy items are handed out through a device work counter instead of being
+        # dealt statically, so the launch does not run at the pace of the CTAs that share an SM with the loss / optimiser
+        # kernels.  `late_fork`: the data stream starts after GAE and the moments instead of beside them.
+        self.dynamic, self.late_fork = bool(dynamic), bool(late_fork)
         row_b = self._row_bytes(obs_shape, obs_dtype)
         bulk_ok = gather_mode != 'vector' and row_b % 16 == 0 and self.fuse_fields and self.overlap and self.device.type == 'cuda'
-        if sync == 'progress':
+        if sync.startswith('progress'):
             assert bulk_ok, 'progress sync needs 16-byte aligned rows (TMA bulk path), fused fields, the data stream and a CUDA device'
         worthwhile = row_b >= 2048 and self.B * row_b >= (16 << 20)          # where the gather's AUTO mode picks the bulk path
-        self.sync = 'progress' if (sync == 'progress' or (sync == 'auto' and bulk_ok and worthwhile)) else 'event'
+        self.sync = sync if sync.startswith('progress') else ('progress' if (sync == 'auto' and bulk_ok and worthwhile) else 'event')
         # minibatches moved per gather launch.  An int = fixed group size (1 = per minibatch, K*M = the whole
         # step, which is what get_mini_batches does: everything materialised before the first update); a list
         # = explicit schedule.  Default on one GPU: a taper -- half of what is left per launch, then (rest-1, 1):
@@ -88,7 +93,7 @@ class PPOHotPath:
         # one launch per epoch).  With ranks > 1: per epoch, the last epoch per minibatch, so that a single
         # loss + gradient all-reduce trails (measured at 8 GPUs: four trailing all-reduces cost ~10 %).
         per_epoch = len(self.slices)
-        if gather_chunk is None and self.sync == 'progress':
+        if gather_chunk is None and self.sync.startswith('progress'):
             # as few launches as memory allows: <= 16 GB per staging slot; everything in one launch / one slot when it fits
             limit = max(1, int((16 << 30) // max(1, self.B * row_b)))
             sizes, rest = [], self.n_mb
@@ -235,15 +240,21 @@ class PPOHotPath:
             self._field_dst.append((ctypes.c_void_p * 4)(*[base + j * fsz for j in range(4)]))
         flat_off = list(self._offsets)                       # start of every minibatch in perms.view(-1)
         self._mb_place = []                                  # minibatch -> (group, slot, first row in the slot)
-        self._progress_sync = self.sync == 'progress' and self.device.type == 'cuda' and not getattr(self, '_capturing', False)
+        self._progress_sync = self.sync.startswith('progress') and self.device.type == 'cuda' and not getattr(self, '_capturing', False)
         if self._progress_sync:
             if getattr(self, 'progress', None) is None:
                 self.progress = torch.zeros(self.n_mb, dtype=torch.int32, device=self.device)      # cyclic counters, never reset
                 self._step_no = 0
             self._units = lib.xa_gather_progress_units(self.row_bytes)
-            self._wait = lib.xa_stream_wait_geq_u32
+            self._wait_memop = self.sync == 'progress-memop'
+            self._wait = lib.xa_stream_wait_geq_u32 if self._wait_memop else lib.xa_wait_progress_u32
+            if getattr(self, 'wait_status', None) is None:
+                self.wait_status = torch.zeros(1, dtype=torch.int32, device=self.device)     # 1 = a wait gave up after ~2 s
+            self._wait_status = _p(self.wait_status)
             self._wait_addr = [ctypes.c_void_p(self.progress.data_ptr() + 4 * i) for i in range(self.n_mb)]
             self._wait_stream = sc
+            if self.dynamic and getattr(self, 'work', None) is None:
+                self.work = torch.zeros(2 * self.n_groups, dtype=torch.int32, device=self.device)   # per launch: next item, lanes done
         for g in range(self.n_groups):
             first, slot = self.group_first[g], g % self.staging
             idx_addr = self.perms.data_ptr() + 4 * flat_off[first]
@@ -251,7 +262,8 @@ class PPOHotPath:
             if self._progress_sync:
                 self._gathers.append((lib.xa_gather_rows_progress,
                                       (_p(self.obs), ctypes.c_void_p(idx_addr), obs_dst, self.group_rows[g], self.row_bytes, N, T, E,
-                                       _p(self.progress), flat_off[first], N, B, sd)))
+                                       _p(self.progress), flat_off[first], N, B,
+                                       ctypes.c_void_p(self.work.data_ptr() + 8 * g) if self.dynamic else ctypes.c_void_p(None), sd)))
             else:
                 self._gathers.append((lib.xa_gather_minibatch,
                                       (_p(self.obs), obs_dst, self.row_bytes, N, self._field_src, self._field_dst[slot],
@@ -316,7 +328,8 @@ class PPOHotPath:
         on_gather = on_gather if on_gather is not None else self.on_gather
         # the data stream joins after everything already queued on the compute stream (rollout writes,
         # the previous step) -- and after GAE only when the gathers carry the returns field
-        if two and self.fuse_fields:
+        early = two and self.fuse_fields and not self.late_fork
+        if early:
             self._fork.record(cs)
             ds.wait_event(self._fork)
         _count(self.kernel_launches_per_step - (0 if gae else 1))
@@ -328,6 +341,9 @@ class PPOHotPath:
             ds.wait_event(self._fork)
         fn, args = self._moments
         self._check('moments', fn(*args))
+        if two and self.fuse_fields and self.late_fork:
+            self._fork.record(cs)
+            ds.wait_event(self._fork)
         if self.comm is not None and self.comm.world_size > 1:
             with torch.cuda.stream(cs):                                         # ordered between the moments and the losses
                 self.comm.all_gather_moments(self.all_moments, self.moments)    # collective C2
@@ -346,7 +362,10 @@ class PPOHotPath:
             for i in range(self.group_first[g], self.group_first[g] + self.group_sizes[g]):
                 if progress:     # minibatch i is staged once its counter reached (launches so far) x (its rows) x (units per row)
                     target = (self._step_no * self.mb_rows[i] * self._units) & 0xffffffff
-                    self._check('wait', self._wait(self._wait_stream, self._wait_addr[i], target))
+                    if self._wait_memop:
+                        self._check('wait', self._wait(self._wait_stream, self._wait_addr[i], target))
+                    else:
+                        self._check('wait', self._wait(self._wait_addr[i], target, self._wait_status, self._wait_stream))
                 if before_loss is not None:
                     before_loss(i)
                 fn, args = self._losses[i]
