@@ -192,6 +192,11 @@ int xa_a2c_loss_f32(const xa_loss_args* args, xa_stream_t stream);
 int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* noise, uint64_t seed,
                        uint64_t offset, float* actions, float* log_probs, float* entropies, int64_t n,
                        int n_actions, xa_stream_t stream);
+/* The same step with the Philox offset in DEVICE memory (*offset_dev is read by the kernel, then advanced by `advance` by a
+ * one-thread kernel behind it): a CUDA graph that captured a whole rollout draws fresh noise on every replay. */
+int xa_policy_step_counter_f32(const float* actor_out, int actor_kind, uint64_t seed, uint64_t* offset_dev,
+                               uint64_t advance, float* actions, float* log_probs, float* entropies, int64_t n,
+                               int n_actions, xa_stream_t stream);
 
 /* ---- dense contractions on the tensor cores (row "next": the policy/value network) ------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU), bf16 operands, fp32 accumulation in TMEM (tcgen05),

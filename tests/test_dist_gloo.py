@@ -83,6 +83,7 @@ def _worker(rank, world, port, out_dir):
     from xagents_b200.agents.base import BaseAgent
     agent = object.__new__(BaseAgent)
     agent.comm, agent.quiet, agent.batched = comm, True, False
+    agent.early_stop_count, agent.early_stop_patience = 0, 3
     agent.total_rewards = deque([10.0, 20.0] if rank == 0 else [60.0], maxlen=100)
     agent.mean_reward = float(np.mean(agent.total_rewards))
     agent.steps = 100 * (rank + 1)

@@ -264,3 +264,52 @@ def test_fused_peer_allreduce_adam_two_ranks():
     out = json.loads([ln for ln in done.stdout.splitlines() if ln.startswith('{')][-1])
     assert out['transport'] in ('symm', 'ipc'), out
     assert out['parity_ok'] and out['weights_identical_across_ranks'] and out['status'] == 0 and out['status_after_timing'] == 0, out
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('env_id,network', [('SyntheticAtariDevice-v0', 'torch'), ('SyntheticAtariDevice-v0', 'tcgen05'), ('CartPoleDevice-v1', 'mlp')])
+def test_rollout_as_one_cuda_graph_equals_the_eager_loop(env_id, network):
+    """graph_rollout: the n_steps x (policy evaluation, in-kernel sampler, device environment step, row writes) captured once
+    and replayed -- same environment generator stream (registered with the graph), same Philox offsets (device counter), so the
+    rollout buffers, the episode bookkeeping and agent.steps equal the eager loop's, rollout after rollout."""
+    from xagents_b200 import envs
+    from xagents_b200.agents import PPO, NatureCNN, TorchModel
+    T, E = 6, 8
+    agents = []
+    for graph in (True, False):
+        made = envs.create_envs(env_id, E, preprocess=True, device=DEV)
+        made.seed(5)
+        if hasattr(made, 'p_done'):
+            made.p_done = 0.2
+        made.reset_all()
+        torch.manual_seed(0)
+        if network == 'mlp':
+            class Mlp(torch.nn.Module):
+                def __init__(self):
+                    super().__init__()
+                    self.body, self.actor, self.critic = torch.nn.Linear(4, 16), torch.nn.Linear(16, 2), torch.nn.Linear(16, 1)
+
+                def forward(self, x):
+                    h = torch.tanh(self.body(x))
+                    return self.actor(h), self.critic(h)
+            net = TorchModel(Mlp().cuda())
+        else:
+            net = TorchModel(NatureCNN(4, 6).cuda(), tensor_core_inference=(network == 'tcgen05'))
+        agent = PPO(made, net, n_steps=T, mini_batches=4, ppo_epochs=1, quiet=True, seed=3)
+        agent.graph_rollout = graph
+        agents.append(agent)
+    g, e = agents
+    for rollout in range(3):
+        for a in (g, e):
+            a.get_batch()
+            a._flush_episode_log()
+        torch.cuda.synchronize()
+        assert (g._rollout_graph is not None and g._rollout_graph is not False) and not e._rollout_graph
+        for name in ('ro_states', 'ro_actions', 'ro_rewards', 'ro_dones', 'ro_values', 'ro_log_probs', 'ro_entropies', 'ro_actor'):
+            assert torch.equal(getattr(g, name), getattr(e, name)), (rollout, name)
+        assert torch.equal(g.get_states(), e.get_states()) and torch.equal(g.get_dones(), e.get_dones())
+        assert g.steps == e.steps == (rollout + 1) * T * E and g.games == e.games and list(g.total_rewards) == list(e.total_rewards)
+    assert g.games > 0 or env_id.startswith('CartPole')
+    g.train_step()                                                 # and a whole train step on top of a replayed rollout
+    torch.cuda.synchronize()
+    assert g.steps == 4 * T * E and torch.isfinite(g.net.flat_param).all()

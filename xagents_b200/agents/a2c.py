@@ -34,6 +34,12 @@ class A2C(OnPolicy):
         #                                  complete rollout in the ro_* buffers and returns the bootstrap values [E]
         self._fed_last_values = None
         self._a2c_pipeline = None
+        # The rollout as ONE CUDA graph (`graph_rollout`): with a device-resident batched environment the n_steps x (policy
+        # evaluation, sampler, environment step, row writes) are ~20 launches per step of a few microseconds each -- launch-
+        # bound.  'auto' captures them once (Philox offset in device memory, the environment's generator registered with the
+        # graph) when everything in the loop lives on the device; False keeps the eager loop.
+        self.graph_rollout = 'auto'
+        self._rollout_graph = None
         self._alloc_rollout()
 
     # ------------------------------------------------------------------ buffers
@@ -91,7 +97,8 @@ class A2C(OnPolicy):
         actor_out, critic = self.net.forward(x, training=training)
         if actions is None and self.action_source is None:
             # sample + log_prob + entropy in one kernel (Philox stream keyed by the agent seed)
-            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind,
+            counter = getattr(self, '_philox', None) if getattr(self.net, 'capturing', False) else None
+            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind, counter=counter,
                                                      seed=int(self.seed) if self.seed else 0, offset=self._rng_offset)
             self._rng_offset += 2 * self.n_actions
             return actions, logp, critic, entropy, actor_out
@@ -112,6 +119,20 @@ class A2C(OnPolicy):
             self.steps += self.n_steps * self.n_envs               # what step_envs counts (base.py:425)
             return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
                     self.ro_entropies, self.ro_actor]
+        if self._rollout_graph is None and self._can_graph_rollout():
+            self._capture_rollout()
+        if self._rollout_graph:
+            self._flush_episode_log()                              # the replay overwrites the rows the pending log entries view
+            self._rollout_graph.replay()                           # the whole rollout: one launch
+            self.steps += self.n_steps * self.n_envs
+            self._episode_log = [(self.ro_dones[t + 1], self._ro_sums[t]) for t in range(self.n_steps)]
+        else:
+            self._rollout_loop()
+        return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
+                self.ro_entropies, self.ro_actor]
+
+    def _rollout_loop(self, capturing=False):
+        """n_steps x (model outputs -> row t of the rollout buffers -> environment step), a2c/agent.py:113-139."""
         step_states, step_dones = self.get_states(), self.get_dones()
         for t in range(self.n_steps):
             states_d = self._to_device(step_states, self.obs_dtype)
@@ -125,9 +146,69 @@ class A2C(OnPolicy):
             self.ro_actor[t].copy_(actor_out)
             *_, step_rewards, step_dones, step_states = self.step_envs(self._env_actions(actions), True, False)
             self.ro_rewards[t].copy_(self._to_device(step_rewards))
+            if capturing:                                          # episode sums at the moment of each done flag
+                self._ro_sums[t].copy_(self._episode_log.pop()[1])
         self.ro_dones[self.n_steps].copy_(self._to_device(step_dones))
-        return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
-                self.ro_entropies, self.ro_actor]
+
+    # ------------------------------------------------------------------ the rollout as one CUDA graph
+    def _can_graph_rollout(self):
+        if self.graph_rollout is False or self._rollout_graph is False or self.device.type != 'cuda':
+            return False
+        from .models import TorchModel
+        ok = (self.batched and hasattr(self.envs, 'GRAPH_STATE') and hasattr(self.envs, '_gen') and self.action_source is None
+              and isinstance(self.net, TorchModel) and (self.graph_rollout is True or type(self).__name__ in ('A2C', 'PPO')))
+        if not ok:
+            assert self.graph_rollout is not True, 'graph_rollout=True needs a batched device environment and a TorchModel'
+            self._rollout_graph = False
+        return ok
+
+    def _capture_rollout(self):
+        envs, dev = self.envs, self.device
+        self._ro_sums = torch.empty((self.n_steps, self.n_envs), dtype=torch.float32, device=dev)
+        self._philox = torch.full((1,), self._rng_offset, dtype=torch.int64, device=dev)
+        # fixed-address homes for everything the loop reads on entry and replaces on exit
+        home = {name: getattr(envs, name).clone() for name in envs.GRAPH_STATE}
+        home['agent.dones'], home['agent.sums'] = self.dones.clone(), self._episode_sums.clone()
+
+        def enter():                                               # point the live objects at the homes
+            for name in envs.GRAPH_STATE:
+                setattr(envs, name, home[name])
+            self.states, self.dones, self._episode_sums = envs.states, home['agent.dones'], home['agent.sums']
+
+        def leave():                                               # what the loop left behind goes back into the homes
+            final = {name: getattr(envs, name) for name in envs.GRAPH_STATE}
+            final['agent.dones'], final['agent.sums'] = self.dones, self._episode_sums
+            for name, t in final.items():
+                if t.data_ptr() != home[name].data_ptr():
+                    home[name].copy_(t)
+            enter()
+
+        saved = {k: v.clone() for k, v in home.items()}
+        gen_state, steps, log, rng_offset = envs._gen.get_state(), self.steps, list(self._episode_log), self._rng_offset
+        self.net.capturing = True                                  # no nested graph replays inside the capture
+        stream = torch.cuda.Stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        try:
+            with torch.cuda.stream(stream):
+                enter()
+                self._rollout_loop(capturing=True)                 # warm-up outside the capture (module loading, allocator, cuDNN)
+                stream.synchronize()
+                for k, v in saved.items():                         # ... undone: same states, same random streams as before
+                    home[k].copy_(v)
+                envs._gen.set_state(gen_state)
+                self._rng_offset = rng_offset
+                self._philox.fill_(rng_offset)
+                enter()
+                graph = torch.cuda.CUDAGraph()
+                graph.register_generator_state(envs._gen)
+                with torch.cuda.graph(graph, stream=stream):
+                    self._rollout_loop(capturing=True)
+                    leave()
+        finally:
+            self.net.capturing = False
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        self.steps, self._episode_log = steps, log
+        self._rollout_graph = graph
 
     def _bootstrap_values(self):
         if self.rollout_source is not None:

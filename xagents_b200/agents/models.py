@@ -71,6 +71,7 @@ class TorchModel:
             mod.refresh()
         # rollout-time policy evaluation (no grad) through the tcgen05 convolution + GEMM pipeline
         self._tc_forward = None
+        self.capturing = False                                    # set by a caller that is capturing a CUDA graph around forward()
         self._graph_inference = graph_inference
         if tensor_core_inference or getattr(module, 'takes_uint8', False):
             from .tc_conv import NatureCnnTcForward
@@ -80,7 +81,7 @@ class TorchModel:
 
     def forward(self, states, training=True):
         if not training and self._tc_forward is not None and states.dtype == torch.uint8:
-            if self._graph_inference:                             # fixed rollout batch: one graph replay per step
+            if self._graph_inference and not self.capturing:      # fixed rollout batch: one graph replay per step
                 a, c = self._tc_forward.graphed(states.shape[0])(states)
                 return a.clone(), c.clone()
             return self._tc_forward(states)

@@ -30,6 +30,7 @@ struct PolicyParams {
   const float* actor_out;
   const float* noise;
   uint64_t seed, offset;
+  const uint64_t* offset_ptr;  // when set, the Philox offset is read from device memory (a replayed CUDA graph must not repeat its draws)
   float* actions;
   float* log_probs;
   float* entropies;
@@ -44,11 +45,12 @@ __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) 
   const int A = p.n_actions;
   const float* row = p.actor_out + i * A;
   const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+  const uint64_t offset = p.offset_ptr ? *p.offset_ptr : p.offset;
   uint4 rnd = make_uint4(0, 0, 0, 0);
   auto draw = [&](int j) -> uint32_t {  // j-th 32-bit word of this sample's Philox stream
     if ((j & 3) == 0)
       rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32),
-                                     static_cast<uint32_t>(p.offset + (j >> 2)), static_cast<uint32_t>((p.offset + (j >> 2)) >> 32)),
+                                     static_cast<uint32_t>(offset + (j >> 2)), static_cast<uint32_t>((offset + (j >> 2)) >> 32)),
                           key);
     const int k = j & 3;
     return k == 0 ? rnd.x : (k == 1 ? rnd.y : (k == 2 ? rnd.z : rnd.w));
@@ -98,7 +100,34 @@ __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) 
   if (p.entropies) p.entropies[i] = ent;
 }
 
+__global__ void bump_u64_kernel(uint64_t* p, uint64_t delta) { *p += delta; }
+
+int launch_policy(const PolicyParams& p, int actor_kind, cudaStream_t s, const char* what) {
+  const unsigned grid = static_cast<unsigned>((p.n + 127) / 128);
+  switch (actor_kind) {
+    case XA_ACTOR_LOGITS: policy_step_kernel<XA_ACTOR_LOGITS><<<grid, 128, 0, s>>>(p); break;
+    case XA_ACTOR_PROBS: policy_step_kernel<XA_ACTOR_PROBS><<<grid, 128, 0, s>>>(p); break;
+    default: policy_step_kernel<XA_ACTOR_NORMAL><<<grid, 128, 0, s>>>(p); break;
+  }
+  return xa::check_launch(what);
+}
+
 }  // namespace
+
+// The same step with the Philox offset held in DEVICE memory: the kernel reads *offset_dev and a one-thread kernel behind it
+// adds `advance`, so a CUDA graph that captured the call draws fresh noise on every replay.
+extern "C" int xa_policy_step_counter_f32(const float* actor_out, int actor_kind, uint64_t seed, uint64_t* offset_dev, uint64_t advance,
+                                          float* actions, float* log_probs, float* entropies, int64_t n, int n_actions, xa_stream_t stream) {
+  XA_REQUIRE(n > 0 && n_actions > 0, XA_EINVAL, "xa_policy_step_counter_f32: n=%lld n_actions=%d", static_cast<long long>(n), n_actions);
+  XA_REQUIRE(actor_out && actions && log_probs && offset_dev, XA_EINVAL, "xa_policy_step_counter_f32: null pointer");
+  XA_REQUIRE(xa::aligned(offset_dev, 8), XA_EALIGN, "xa_policy_step_counter_f32: offset_dev must be 8-byte aligned");
+  XA_REQUIRE(actor_kind >= XA_ACTOR_LOGITS && actor_kind <= XA_ACTOR_NORMAL, XA_EINVAL, "xa_policy_step_counter_f32: unknown actor_kind %d", actor_kind);
+  PolicyParams p{actor_out, nullptr, seed, 0, offset_dev, actions, log_probs, entropies, n, n_actions};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = launch_policy(p, actor_kind, s, "xa_policy_step_counter_f32")) return rc;
+  bump_u64_kernel<<<1, 1, 0, s>>>(offset_dev, advance);
+  return xa::check_launch("xa_policy_step_counter_f32");
+}
 
 extern "C" int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* noise, uint64_t seed, uint64_t offset,
                                   float* actions, float* log_probs, float* entropies, int64_t n, int n_actions,
@@ -108,13 +137,6 @@ extern "C" int xa_policy_step_f32(const float* actor_out, int actor_kind, const 
   XA_REQUIRE(actor_out && actions && log_probs, XA_EINVAL, "xa_policy_step_f32: null pointer");
   XA_REQUIRE(actor_kind >= XA_ACTOR_LOGITS && actor_kind <= XA_ACTOR_NORMAL, XA_EINVAL, "xa_policy_step_f32: unknown actor_kind %d",
              actor_kind);
-  PolicyParams p{actor_out, noise, seed, offset, actions, log_probs, entropies, n, n_actions};
-  const unsigned grid = static_cast<unsigned>((n + 127) / 128);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (actor_kind) {
-    case XA_ACTOR_LOGITS: policy_step_kernel<XA_ACTOR_LOGITS><<<grid, 128, 0, s>>>(p); break;
-    case XA_ACTOR_PROBS: policy_step_kernel<XA_ACTOR_PROBS><<<grid, 128, 0, s>>>(p); break;
-    default: policy_step_kernel<XA_ACTOR_NORMAL><<<grid, 128, 0, s>>>(p); break;
-  }
-  return xa::check_launch("xa_policy_step_f32");
+  PolicyParams p{actor_out, noise, seed, offset, nullptr, actions, log_probs, entropies, n, n_actions};
+  return launch_policy(p, actor_kind, static_cast<cudaStream_t>(stream), "xa_policy_step_f32");
 }

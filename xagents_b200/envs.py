@@ -191,6 +191,10 @@ class BatchedSyntheticAtari:
         self.states = self._frames()
         return self.states
 
+    # everything `step_all` reads and replaces, by attribute name: what a captured rollout (CUDA graph) must find at fixed
+    # addresses on entry and what it hands back on exit; `_gen` is the generator the graph has to register
+    GRAPH_STATE = ('states',)
+
     def step_all(self, actions):
         """-> (new_states [n,84,84,C] uint8, rewards [n] fp32, dones [n] fp32), all on the device."""
         torch = self.torch
@@ -249,6 +253,8 @@ class BatchedCartPole:
         self.states = self.state.float()
         return self.states
 
+    GRAPH_STATE = ('state', 't', 'states')       # see BatchedSyntheticAtari.GRAPH_STATE
+
     def step_all(self, actions):
         """-> (new_states [n,4] fp32, rewards [n] fp32 (all ones), dones [n] fp32) on the device."""
         torch, c = self.torch, CartPole
@@ -261,7 +267,7 @@ class BatchedCartPole:
         th_acc = (c.GRAVITY * sin - cos * temp) / (c.HALF_LENGTH * (4.0 / 3.0 - c.POLE_MASS * cos * cos / total))
         x_acc = temp - pml * th_acc * cos / total
         state = torch.stack([x + c.TAU * x_dot, x_dot + c.TAU * x_acc, th + c.TAU * th_dot, th_dot + c.TAU * th_acc], 1)
-        self.t += 1
+        self.t = self.t + 1
         done = (state[:, 0].abs() > c.X_LIMIT) | (state[:, 2].abs() > c.THETA_LIMIT) | (self.t >= c.MAX_STEPS)
         new_states = state.float()
         self.state = torch.where(done.view(-1, 1), self._initial(self.n), state)      # finished episodes start over

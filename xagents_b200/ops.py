@@ -220,9 +220,10 @@ def gather_rows_scaled(src_u8, idx, *, time_major=None, out=None, stream=None):
 
 
 # ------------------------------------------------------------------------------------------ rollout-time policy
-def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0, out=None, stream=None):
+def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0, out=None, stream=None, counter=None):
     """sample() + log_prob() + entropy() of A2C.get_model_outputs (a2c/agent.py:80-94) for one env step.
-    Returns (actions, log_probs, entropies); `out` may hold row views of the rollout buffers."""
+    Returns (actions, log_probs, entropies); `out` may hold row views of the rollout buffers.  `counter`: a device int64 [1]
+    holding the Philox offset (read by the kernel, advanced behind it) instead of the host-side `offset` -- for captured graphs."""
     ao = _dev(actor_out, 'float32')
     n, A = ao.shape[0], ao.shape[-1]
     dev = _device_of(ao)
@@ -233,6 +234,12 @@ def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0,
         logp = torch.empty((n,), dtype=torch.float32, device=dev)
     if ent is None:
         ent = torch.empty((n,), dtype=torch.float32, device=dev)
+    if counter is not None:
+        assert noise is None and counter.dtype == torch.int64 and counter.is_cuda
+        _call(ao, 'xa_policy_step_counter_f32', _ptr(ao), ACTOR_KINDS[actor_kind], int(seed), _tptr(counter), 2 * A, _tptr(actions),
+              _tptr(logp), _tptr(ent), n, A, stream)
+        _count(2)
+        return actions, logp, ent
     nz = _dev(noise, 'float32') if noise is not None else None
     _call(ao, 'xa_policy_step_f32', _ptr(ao), ACTOR_KINDS[actor_kind], _ptr(nz), int(seed), int(offset), _tptr(actions),
               _tptr(logp), _tptr(ent), n, A, stream)
