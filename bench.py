@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument('--network', default='stand-in', choices=['stand-in', 'nature-tc'],
                     help='nature-tc: the real Nature CNN forward/backward on the tcgen05 kernels inside the step (secondary metric)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--time-updates', action='store_true', help='diagnostic: CUDA events around every gradient stand-in + C1 + optimiser update')
     ap.add_argument('--no-clock-sampler', action='store_true', help='diagnostic: no NVML polling thread beside the timed region')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-single-gpu-compare', action='store_true', help='N>1: skip the 1-GPU runs at the same per-GPU n_envs / at C4')
@@ -309,6 +310,7 @@ class SyntheticNetwork:
         self._grad_fn, self._check, self._count = _ffi.lib().xa_grad_from_outputs_f32, _ffi.check, ops._count
         self._grad_tail = (ctypes.c_void_p(self.flat_grad.data_ptr()), self.flat_grad.numel())
         self._vp = ctypes.c_void_p
+        self.update_events = None        # list of (start, end) CUDA events per update when --time-updates
 
     def forward(self, states, training=True):
         raise RuntimeError('the benchmark feeds complete rollouts: there is no rollout-time forward')
@@ -322,6 +324,16 @@ class SyntheticNetwork:
     def backward_and_step(self, d_actor, d_values, grad_norm=None):
         if not self.optimizer:
             return
+        if self.update_events is not None:
+            a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            a.record()
+            self._update(d_actor, d_values, grad_norm)
+            b.record()
+            self.update_events.append((a, b))
+            return
+        self._update(d_actor, d_values, grad_norm)
+
+    def _update(self, d_actor, d_values, grad_norm):
         comm, vp = self.comm, self._vp
         stream = vp(self.torch.cuda.current_stream(self.device).cuda_stream)
         n = d_values.shape[0]
@@ -411,9 +423,11 @@ def timed_steps(step, stream, n_steps, comm, dev, sampler=None):
     if sampler:
         sampler.mark()
     marks[0].record(stream)
+    t0 = time.perf_counter()
     for s in range(n_steps):
         step(s)
         marks[s + 1].record(stream)
+    timed_steps.host_ms_per_step = (time.perf_counter() - t0) * 1e3 / n_steps      # time the HOST needed to issue a step
     torch.cuda.synchronize(dev)
     if comm is not None:
         comm.barrier()
@@ -576,9 +590,16 @@ def run_ppo(args):
         agent.train_step()
 
     hp.on_gather = timed_gather
+    if args.time_updates and hasattr(net, 'update_events'):
+        net.update_events = []
     ops.reset_launch_count()
     elapsed_ms, per_step = timed_steps(step, stream, args.steps, comm, dev, sampler)
+    host_ms = timed_steps.host_ms_per_step
     hp.on_gather = None
+    update_ms = None
+    if getattr(net, 'update_events', None):
+        update_ms = [a.elapsed_time(b) for a, b in net.update_events]
+        net.update_events = None
     wrapper_launches = ops.launch_count()
     clocks = sampler.stop() if sampler else None
     gather_ms = [a.elapsed_time(b) for row in ev for (a, b) in row]
@@ -720,7 +741,7 @@ def run_ppo(args):
         'metric': METRIC if args.network == 'stand-in' else 'ppo_env_steps_per_sec_update_phase_with_network',
         'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
         'ms_per_step': ms_per_step, 'ms_per_step_median': med, 'ms_per_step_min': min(per_step), 'ms_per_step_max': max(per_step),
-        'ms_per_step_each': [round(x, 4) for x in per_step], 'gather_launch_ms_each': [round(x, 3) for x in gather_ms],
+        'host_issue_ms_per_step': host_ms, 'ms_per_step_each': [round(x, 4) for x in per_step], 'gather_launch_ms_each': [round(x, 3) for x in gather_ms],
         'value_at_median_step': N * 1e3 / med * world if world == 1 else None,
         'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong',
         'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars' if dtype == 'uint8' else 'f32', 'data': 'synthetic',
@@ -755,6 +776,9 @@ def run_ppo(args):
         'gpu_launches': launches,
         'clocks': clocks,
     }
+    if update_ms:
+        line['update_ms'] = {'mean': statistics.mean(update_ms), 'median': statistics.median(update_ms), 'max': max(update_ms), 'n': len(update_ms),
+                             'what': 'gradient stand-in + collective C1 + clip/Adam per minibatch, CUDA events on the compute stream inside the timed region'}
     if bare is not None:
         line['gae_gather_loss_only'] = bare
     if graph_us is not None:

@@ -343,6 +343,21 @@ int64_t xa_peer_adam_flag_bytes(void);
 int xa_peer_allreduce_adam_f32(const xa_peer_adam_args* args, double lr, double beta1, double beta2, double eps,
                                double clip_norm, int64_t step, xa_stream_t stream);
 
+/* Collective C2 over peer memory: all-gather of a small fp64 block per rank (the per-minibatch advantage moments of
+ * xagents/ppo/agent.py:180-183, so that normalisation uses the statistics of the GLOBAL minibatch).  recv[r] / flags[r]: this
+ * process's mappings of rank r's receive buffer (2 generations x world x n_per_rank doubles) and flag words (XA_MAX_PEERS
+ * uint32), zero-filled before the first call; `epoch` as in xa_peer_allreduce_adam_f32 (same on every rank, +1 per call);
+ * status: optional local device int set to 1 if a wait gave up (~2 s).  out: local [world * n_per_rank] doubles. */
+typedef struct xa_peer_gather_args {
+  void* recv[XA_MAX_PEERS];
+  void* flags[XA_MAX_PEERS];
+  int* status;
+  int64_t n_per_rank;
+  int32_t rank, world;
+  uint32_t epoch;
+} xa_peer_gather_args;
+int xa_peer_allgather_f64(const xa_peer_gather_args* args, const double* src, double* out, xa_stream_t stream);
+
 /* Benchmark stand-in for the network backward (bench.py): grad[j] = d_actor[j mod n*A] + 0.5 * d_values[j mod n].  The reference
  * obtains the parameter gradients from its tape (xagents/ppo/agent.py:134); the headline metric excludes the network, so
  * this kernel supplies what the gradient all-reduce and the optimiser need from it: a flat gradient that depends on this

@@ -58,6 +58,18 @@ def main():
     out['status'] = fused.status()
     out['parity_ok'] = worst <= 1e-5 and out['weights_identical_across_ranks'] and out['status'] == 0
 
+    # ---- collective C2 through peer memory: 4 all-gathers (both generations twice) against torch.distributed ---------------
+    gather = peer.PeerAllGather(comm, 16 * 4)
+    ok_c2 = True
+    for call in range(4):
+        local = torch.randn(16, 4, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(100 * call + rank))
+        got = torch.empty((world, 16, 4), dtype=torch.float64, device=dev)
+        gather.gather(local, got)
+        want = [torch.empty_like(local) for _ in range(world)]
+        torch.distributed.all_gather(want, local)
+        ok_c2 = ok_c2 and torch.equal(got, torch.stack(want))
+    out['peer_allgather_ok'] = bool(ok_c2) and gather.status() == 0
+
     # ---- timing at the Nature CNN's size ------------------------------------------------------------------------
     n = 1_687_719
     big = peer.FusedAllReduceAdam(comm, n)

@@ -264,6 +264,7 @@ def test_fused_peer_allreduce_adam_two_ranks():
     out = json.loads([ln for ln in done.stdout.splitlines() if ln.startswith('{')][-1])
     assert out['transport'] in ('symm', 'ipc'), out
     assert out['parity_ok'] and out['weights_identical_across_ranks'] and out['status'] == 0 and out['status_after_timing'] == 0, out
+    assert out['peer_allgather_ok'], out
 
 
 @pytest.mark.timeout(300)

@@ -52,6 +52,12 @@ class PeerAdamArgs(ctypes.Structure):
                 ('inv_world', ctypes.c_float)]
 
 
+class PeerGatherArgs(ctypes.Structure):
+    """struct xa_peer_gather_args"""
+    _fields_ = [('recv', ctypes.c_void_p * XA_MAX_PEERS), ('flags', ctypes.c_void_p * XA_MAX_PEERS), ('status', ctypes.c_void_p),
+                ('n_per_rank', ctypes.c_int64), ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('epoch', ctypes.c_uint32)]
+
+
 # name -> (restype, argtypes); every symbol include/xagents_b200.h declares
 PROTOTYPES = {
     'xa_version': (ctypes.c_int, []),
@@ -113,6 +119,7 @@ PROTOTYPES = {
     'xa_ipc_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     'xa_ipc_close': (ctypes.c_int, [ctypes.c_void_p]),
     'xa_ipc_free': (ctypes.c_int, [ctypes.c_void_p]),
+    'xa_peer_allgather_f64': (ctypes.c_int, [ctypes.POINTER(PeerGatherArgs), ctypes.c_void_p, ctypes.c_void_p, c_stream]),
     'xa_peer_adam_workspace_bytes': (ctypes.c_int64, []),
     'xa_peer_adam_flag_bytes': (ctypes.c_int64, []),
     'xa_peer_allreduce_adam_f32': (ctypes.c_int, [ctypes.POINTER(PeerAdamArgs)] + [ctypes.c_double] * 5 + [ctypes.c_int64, c_stream]),

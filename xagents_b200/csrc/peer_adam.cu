@@ -191,9 +191,60 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_adam_kernel(const xa_
   wait_all(my_flags + 2 * XA_MAX_PEERS, G, a.epoch, 3, ws);
 }
 
+// Collective C2: the per-minibatch advantage moments of every rank, once per train step -- a few hundred bytes.
+// One small CTA: store this rank's block into every peer's receive buffer (P2P stores), raise this rank's flag at every peer,
+// wait for every peer's flag here, copy the complete table into the caller's private output.  NCCL's kernels (up to 640 threads
+// x 96 registers per CTA) cannot share an SM with a gather CTA and queue until the persistent gather has finished -- measured:
+// the whole per-minibatch chain then runs AFTER the gathers instead of under them; this kernel is 128 threads.
+// The receive buffer holds two generations (epoch parity): a rank can run at most one all-gather ahead of the slowest peer
+// (it cannot finish generation e+1 before every peer has entered it), so generation e+2 never overwrites data still in use.
+__global__ void __launch_bounds__(128) peer_allgather_kernel(const xa_peer_gather_args a, const double* __restrict__ src, double* __restrict__ out) {
+  PeerWorkspace* ws = nullptr;
+  (void)ws;
+  const int me = a.rank, G = a.world;
+  const int64_t n = a.n_per_rank;
+  const int64_t gen = static_cast<int64_t>(a.epoch & 1u) * G * n;
+  for (int r = 0; r < G; ++r) {
+    double* dst = static_cast<double*>(a.recv[r]) + gen + static_cast<int64_t>(me) * n;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < G) st_release_sys(static_cast<uint32_t*>(a.flags[threadIdx.x]) + me, a.epoch);
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const uint32_t* mine = static_cast<const uint32_t*>(a.flags[me]) + threadIdx.x;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
+      if (clock64() - t0 > kTimeoutCycles) {
+        s_ok = 0;
+        if (a.status) atomicExch(a.status, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const volatile double* table = static_cast<const double*>(a.recv[me]) + gen;
+  for (int64_t i = threadIdx.x; i < n * G; i += blockDim.x) out[i] = table[i];
+}
+
 }  // namespace
 
 extern "C" {
+
+int xa_peer_allgather_f64(const xa_peer_gather_args* args, const double* src, double* out, xa_stream_t stream) {
+  XA_REQUIRE(args != nullptr && src != nullptr && out != nullptr, XA_EINVAL, "xa_peer_allgather_f64: null pointer");
+  const xa_peer_gather_args& a = *args;
+  XA_REQUIRE(a.world >= 1 && a.world <= XA_MAX_PEERS && a.rank >= 0 && a.rank < a.world, XA_EINVAL, "xa_peer_allgather_f64: rank %d of %d", a.rank, a.world);
+  XA_REQUIRE(a.n_per_rank > 0 && a.epoch > 0, XA_EINVAL, "xa_peer_allgather_f64: n_per_rank=%lld epoch=%u", static_cast<long long>(a.n_per_rank), a.epoch);
+  for (int r = 0; r < a.world; ++r)
+    XA_REQUIRE(a.recv[r] && a.flags[r] && xa::aligned(a.recv[r], 8) && xa::aligned(a.flags[r], 4), XA_EINVAL, "xa_peer_allgather_f64: bad peer pointer for rank %d", r);
+  peer_allgather_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, src, out);
+  return xa::check_launch("xa_peer_allgather_f64");
+}
 
 // Peer-mappable allocations by CUDA IPC (the transport used when torch's symmetric-memory rendezvous is not possible on a
 // box): cudaMalloc + cudaIpcGetMemHandle here, cudaIpcOpenMemHandle in the peers (lazy peer-access enabling).

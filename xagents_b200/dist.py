@@ -73,10 +73,23 @@ class ShardComm:
         self.comm_stream = (torch.cuda.Stream(device, priority=-1)
                             if (device is not None and torch.device(device).type == 'cuda') else None)
         self._pending = None
+        self.peer_c2 = 'auto'            # 'auto': C2 through NVLink peer memory when the box can map it (peer.PeerAllGather); False: NCCL
+        self._peer_gathers = {}
 
     # C2 ------------------------------------------------------------------------------------------
     def all_gather_moments(self, out, local):
         """out [G, n_mb, 4] <- every rank's local [n_mb, 4] moments (fp64), on the current stream."""
+        if self.peer_c2 and self.backend == 'nccl' and local.is_cuda:
+            # NCCL's kernels cannot share an SM with the persistent gather's CTAs (register file) and would run after it -- with
+            # the whole per-minibatch chain behind them; a 128-thread P2P kernel does not have that problem
+            from . import peer
+            if peer.available(self):
+                key = local.numel()
+                if key not in self._peer_gathers:
+                    self._peer_gathers[key] = peer.PeerAllGather(self, key)
+                self._peer_gathers[key].gather(local, out)
+                return out
+            self.peer_c2 = False
         if self.backend == 'gloo':
             parts = [torch.empty_like(local) for _ in range(self.world_size)]
             dist.all_gather(parts, local, group=self.group)

@@ -145,3 +145,38 @@ class FusedAllReduceAdam:
     def status(self):
         """0 = every wait so far completed; 1..3 = the phase whose wait timed out (synchronises)."""
         return int(self._ws.view(torch.int32)[2].item())
+
+
+class PeerAllGather:
+    """Collective C2 without NCCL: every rank's small fp64 block lands in every rank's table through P2P stores (one 128-thread
+    kernel per call, csrc/peer_adam.cu).  `gather(local, out)`: out [world, ...] <- every rank's `local`, on the current stream."""
+
+    def __init__(self, comm, n_per_rank, via=None):
+        G, dev = comm.world_size, torch.device(comm.device)
+        via = via or transport(comm)
+        assert via in _TRANSPORTS, f'no peer-memory transport on this box ({probe_errors()})'
+        self.comm, self.device, self.n = comm, dev, int(n_per_rank)
+        words = 2 * (2 * G * self.n) + _ffi.XA_MAX_PEERS            # two generations of [G, n] doubles, then the flags
+        self._buf, ptrs, self._keep = _TRANSPORTS[via](comm, words)
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        a = self._args = _ffi.PeerGatherArgs()
+        for r, base in enumerate(ptrs):
+            a.recv[r] = base
+            a.flags[r] = base + 8 * (2 * G * self.n)
+        a.status, a.n_per_rank, a.rank, a.world = self._status.data_ptr(), self.n, comm.rank, G
+        self.epoch = 0
+        torch.cuda.synchronize(dev)
+        comm.barrier()
+
+    def gather(self, local, out, stream=None):
+        assert local.dtype == torch.float64 and out.dtype == torch.float64 and local.numel() == self.n
+        assert out.numel() == self.n * self.comm.world_size and local.is_contiguous() and out.is_contiguous()
+        self.epoch += 1
+        self._args.epoch = self.epoch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _ffi.call('xa_peer_allgather_f64', ctypes.byref(self._args), ctypes.c_void_p(local.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                  ctypes.c_void_p(s.cuda_stream))
+        return out
+
+    def status(self):
+        return int(self._status.item())
