@@ -23,11 +23,12 @@ E, T, A = int(os.environ.get('N_ENVS', 256)), int(os.environ.get('N_STEPS', 128)
 STEPS = int(os.environ.get('TRAIN_STEPS', 3))
 
 
-def run(env_id, tensor_cores):
+def run(env_id, tensor_cores, graph_rollout='auto'):
     torch.manual_seed(0)
     made = xenvs.create_envs(env_id, E, preprocess=True, device='cuda:0')
     net = TorchModel((NatureCnnTc if tensor_cores else NatureCNN)(4, A).cuda())
     agent = PPO(made, net, n_steps=T, mini_batches=4, ppo_epochs=4, quiet=True, seed=1)
+    agent.graph_rollout = graph_rollout
     phases = {'rollout': 0.0, 'update': 0.0}
     inner_batch, inner_epochs = agent.get_batch, agent.run_ppo_epochs
 
@@ -51,17 +52,18 @@ def run(env_id, tensor_cores):
     torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / STEPS
     return {'env': env_id, 'network': 'tcgen05 kernels (bf16 operands, fp32 accumulate)' if tensor_cores else 'torch fp32',
-            'n_envs': E, 'n_steps': T, 'train_steps_timed': STEPS, 'ms_per_train_step': sec * 1e3,
+            'rollout': 'one CUDA graph' if agent._rollout_graph else 'eager loop', 'n_envs': E, 'n_steps': T, 'train_steps_timed': STEPS, 'ms_per_train_step': sec * 1e3,
             'rollout_ms': phases['rollout'] / STEPS * 1e3, 'update_ms': phases['update'] / STEPS * 1e3,
             'env_steps_per_sec': T * E / sec, 'hot_path_kernel_launches_per_train_step': ops.launch_count() // STEPS,
             'finite': bool(torch.isfinite(net.flat_param).all())}
 
 
-rows = [run('SyntheticAtariDevice-v0', True), run('SyntheticAtariDevice-v0', False), run('SyntheticAtari-v0', True)]
-print('| environments | network | ms / train step | rollout ms | update ms | env-steps/s (whole training) |')
-print('|---|---|---|---|---|---|')
+rows = [run('SyntheticAtariDevice-v0', True), run('SyntheticAtariDevice-v0', True, graph_rollout=False), run('SyntheticAtariDevice-v0', False),
+        run('SyntheticAtari-v0', True)]
+print('| environments | network | rollout | ms / train step | rollout ms | update ms | env-steps/s (whole training) |')
+print('|---|---|---|---|---|---|---|')
 for r in rows:
-    print(f"| {r['env']} x {r['n_envs']} | {r['network']} | {r['ms_per_train_step']:.1f} | {r['rollout_ms']:.1f} | {r['update_ms']:.1f} | "
+    print(f"| {r['env']} x {r['n_envs']} | {r['network']} | {r['rollout']} | {r['ms_per_train_step']:.1f} | {r['rollout_ms']:.1f} | {r['update_ms']:.1f} | "
           f"{r['env_steps_per_sec'] / 1e3:.0f} k |")
 for r in rows:
     print(json.dumps(r))

@@ -675,6 +675,98 @@ def trpo_case(xagents):
     print(f'trpo_losses: surrogate={float(surrogate):.6f} kl={float(kl):.6e} value losses={len(RECORD["losses"])}')
 
 
+class _PerturbableModel(TinyModel):
+    """TinyModel whose outputs can be nudged entry by entry: central differences of the reference's own loss w.r.t. the
+    model outputs stand in for the tape (the shim has none)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.delta_actor = self.delta_critic = None
+
+    def __call__(self, inputs, training=True):
+        actor, critic = super().__call__(inputs, training)
+        if self.delta_actor is not None:
+            actor = actor + self.delta_actor
+        if self.delta_critic is not None:
+            critic = critic + self.delta_critic.reshape(critic.shape)
+        return [actor, critic]
+
+
+def loss_gradient_case(xagents, tag, kind, seed, softmax=False, box=False, n_actions=4, h=1e-6):
+    """d loss / d(actor_output, critic_output) of the REFERENCE'S OWN PPO.update_gradients (ppo/agent.py:96-134) and
+    A2C.train_step loss (a2c/agent.py:202-214): the reference code runs under the shim in float64 and its recorded loss is
+    differenced centrally (h = 1e-6) over every entry of the model outputs.  This pins the gradients the CUDA loss kernels
+    return (ties of maximum / clip_by_value are a set of measure zero for these inputs)."""
+    _set_precision(np.float64)
+    try:
+        T, E, Fdim = 6, 4, 5
+        N = T * E
+        rng = np.random.default_rng(seed)
+        obs, rewards, dones, resets = _streams(rng, T, E, (Fdim,), False, 0.1)
+        space = Box((n_actions,)) if box else Discrete(n_actions)
+        envs = [ReplayEnv(obs[i], rewards[i], dones[i], resets[i], space) for i in range(E)]
+        model = _PerturbableModel(Fdim, n_actions, rng, softmax)
+        model.wa, model.wc = model.wa.astype(np.float64), model.wc.astype(np.float64)
+        cls = xagents.PPO if kind == 'ppo' else xagents.A2C
+        kw = dict(mini_batches=1, ppo_epochs=1) if kind == 'ppo' else {}
+        agent = cls(envs, model, n_steps=T, quiet=True, **kw)
+        states = rng.standard_normal((N, Fdim))
+        base_actor, base_critic = TinyModel.__call__(model, states)
+        if box:
+            actions = base_actor + rng.standard_normal((N, n_actions))
+        else:
+            actions = rng.integers(0, n_actions, N).astype(np.float64)
+        old_values = np.squeeze(base_critic) + 0.08 * rng.standard_normal(N)        # both sides of the value clip (0.1)
+        returns = rng.standard_normal(N)
+        dist = agent.get_distribution(base_actor)
+        old_log_probs = np.asarray(dist.log_prob(actions)) + 0.08 * rng.standard_normal(N)   # ratios on both sides of the clip band
+        advantages = rng.standard_normal(N)
+
+        def loss_of():
+            RECORD['losses'].clear()
+            if kind == 'ppo':
+                agent.update_gradients(states, actions, old_values, returns, old_log_probs, advantages)
+            else:                                                  # A2C.train_step's loss block, fed the same batch
+                agent.np_train_step = lambda: (states, returns, actions, old_values)
+                agent.train_step()
+            return float(RECORD['losses'][-1])
+
+        loss = loss_of()
+        d_actor, d_critic = np.zeros((N, n_actions)), np.zeros(N)
+        for i in range(N):
+            for j in range(n_actions):
+                model.delta_actor = np.zeros((N, n_actions))
+                model.delta_actor[i, j] = h
+                up = loss_of()
+                model.delta_actor[i, j] = -h
+                d_actor[i, j] = (up - loss_of()) / (2 * h)
+            model.delta_actor = None
+            model.delta_critic = np.zeros(N)
+            model.delta_critic[i] = h
+            up = loss_of()
+            model.delta_critic[i] = -h
+            d_critic[i] = (up - loss_of()) / (2 * h)
+            model.delta_critic = None
+        np.savez_compressed(os.path.join(HERE, f'{tag}.npz'), kind=kind, actor_kind='normal' if box else ('probs' if softmax else 'logits'),
+                            n_actions=n_actions, clip_norm=getattr(agent, 'clip_norm', 0.0), entropy_coef=agent.entropy_coef,
+                            value_loss_coef=agent.value_loss_coef, actor_output=base_actor, critic_output=np.squeeze(base_critic),
+                            actions=actions, old_values=old_values, returns=returns, old_log_probs=old_log_probs, advantages=advantages,
+                            loss=loss, d_actor=d_actor, d_critic=d_critic)
+        print(f'{tag}: loss={loss:.6f} |d_actor|max={np.abs(d_actor).max():.5f} |d_critic|max={np.abs(d_critic).max():.5f}')
+    finally:
+        _set_precision(np.float32)
+
+
+def gradient_cases(xagents):
+    _reset_rngs()
+    loss_gradient_case(xagents, 'grad_ppo_logits', 'ppo', 71)
+    loss_gradient_case(xagents, 'grad_ppo_probs', 'ppo', 72, softmax=True)
+    loss_gradient_case(xagents, 'grad_ppo_normal', 'ppo', 73, box=True, n_actions=3)
+    loss_gradient_case(xagents, 'grad_a2c_logits', 'a2c', 74)
+    loss_gradient_case(xagents, 'grad_a2c_probs', 'a2c', 75, softmax=True)
+    loss_gradient_case(xagents, 'grad_a2c_normal', 'a2c', 76, box=True, n_actions=3)
+
+
 def update_cases(xagents):
     acer_update_case(xagents, 'acer_update_trust_region', True)
     acer_update_case(xagents, 'acer_update_plain', False)
@@ -686,6 +778,8 @@ def main():
     xagents = _import_reference()
     if '--acer-only' in sys.argv:
         return acer_case(xagents)
+    if '--gradients-only' in sys.argv:                             # round 2: leaves the earlier fixtures untouched
+        return gradient_cases(xagents)
     if '--updates-only' in sys.argv:                               # round 2: leaves the earlier fixtures untouched
         return update_cases(xagents)
     if '--distributions-only' in sys.argv:                         # added later: leaves the earlier fixtures untouched
@@ -710,6 +804,7 @@ def main():
              n_actions=2, p_done=0.15)
     distribution_cases(xagents)
     update_cases(xagents)
+    gradient_cases(xagents)
 
 
 if __name__ == '__main__':

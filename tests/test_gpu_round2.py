@@ -314,3 +314,24 @@ def test_rollout_as_one_cuda_graph_equals_the_eager_loop(env_id, network):
     g.train_step()                                                 # and a whole train step on top of a replayed rollout
     torch.cuda.synchronize()
     assert g.steps == 4 * T * E and torch.isfinite(g.net.flat_param).all()
+
+
+@pytest.mark.parametrize('case', ['grad_ppo_logits', 'grad_ppo_probs', 'grad_ppo_normal', 'grad_a2c_logits', 'grad_a2c_probs', 'grad_a2c_normal'])
+def test_loss_kernel_gradients_vs_differences_of_the_reference_loss(golden, case):
+    """d loss / d(actor_output, critic_output) returned by xa_ppo_loss_f32 / xa_a2c_loss_f32 against central differences of the
+    loss the REFERENCE'S OWN PPO.update_gradients / A2C.train_step computes (float64 shim; tests/golden/make_golden.py
+    --gradients-only) -- the three distribution branches of a2c/agent.py:50-63."""
+    g = golden(case)
+    kind, actor_kind = str(g['kind']), str(g['actor_kind'])
+    cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(DEV)
+    common = dict(entropy_coef=float(g['entropy_coef']), value_loss_coef=float(g['value_loss_coef']), actor_kind=actor_kind)
+    if kind == 'ppo':
+        sc, d_actor, d_values, _ = ops.ppo_loss(cu(g['actor_output']), cu(g['critic_output']), cu(g['actions']), cu(g['old_log_probs']),
+                                                cu(g['old_values']), cu(g['returns']), advantages=cu(g['advantages']),
+                                                clip_norm=float(g['clip_norm']), **common)
+    else:
+        sc, d_actor, d_values = ops.a2c_loss(cu(g['actor_output']), cu(g['critic_output']), cu(g['actions']), cu(g['old_values']),
+                                             cu(g['returns']), **common)
+    assert abs(float(sc[0]) - float(g['loss'])) <= REL * max(abs(float(g['loss'])), 1.0)
+    assert np.abs(d_actor.cpu().numpy() - g['d_actor']).max() <= REL * np.abs(g['d_actor']).max()
+    assert np.abs(d_values.cpu().numpy() - g['d_critic']).max() <= REL * np.abs(g['d_critic']).max()

@@ -44,3 +44,27 @@ def test_acer_losses_and_output_gradients_vs_the_reference_run(golden, case):
     if a.trust_region:                                             # the projection acted on some rows of this fixture
         free = -g['d_loss_d_action_probs'] / n
         assert (np.abs(free - want_p).max(-1) > 1e-6).sum() >= 5
+
+
+GRAD_CASES = ['grad_ppo_logits', 'grad_ppo_probs', 'grad_ppo_normal', 'grad_a2c_logits', 'grad_a2c_probs', 'grad_a2c_normal']
+
+
+@pytest.mark.parametrize('case', GRAD_CASES)
+def test_oracle_loss_gradients_vs_differences_of_the_reference_loss(golden, case):
+    """The closed-form d loss / d(actor_output, critic_output) of the oracle (what the CUDA loss kernels are compared with)
+    against central differences of the loss computed by the REFERENCE'S OWN PPO.update_gradients / A2C.train_step under the
+    float64 shim (make_golden.py --gradients-only): the gradients are pinned to the reference, not to a restatement."""
+    import oracle
+    g = golden(case)
+    kind, actor_kind = str(g['kind']), str(g['actor_kind'])
+    f64 = np.float64
+    if actor_kind == 'normal':
+        pytest.skip('the oracle keeps closed forms for the categorical heads; the normal head is checked on the device')
+    args = (g['actor_output'], g['critic_output'], g['actions'], g['old_values'], g['returns'])
+    if kind == 'ppo':
+        d_actor, d_values = oracle.ppo_loss_grads(*args, g['old_log_probs'], g['advantages'], float(g['clip_norm']), float(g['entropy_coef']),
+                                                  float(g['value_loss_coef']), actor_kind == 'probs', f64)
+    else:
+        d_actor, d_values = oracle.a2c_loss_grads(*args, float(g['entropy_coef']), float(g['value_loss_coef']), actor_kind == 'probs', f64)
+    assert np.abs(d_actor - g['d_actor']).max() <= 1e-6 * np.abs(g['d_actor']).max()
+    assert np.abs(d_values - g['d_critic']).max() <= 1e-6 * np.abs(g['d_critic']).max()
