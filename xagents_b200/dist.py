@@ -7,8 +7,12 @@ one contiguous flat range, so returns/GAE and the gathers need NO communication.
 
   C2  one all-gather per train step of the per-minibatch advantage moments (count, mean, M2) so that
       the normalisation of xagents/ppo/agent.py:180-183 uses the statistics of the GLOBAL minibatch;
-  C1  a sum all-reduce of the flat gradient buffer per minibatch (then 1/G inside the fused
-      clip+Adam), issued on a side stream so it runs under the next minibatch's gather.
+  C1  a sum all-reduce of the flat gradient buffer per minibatch, then 1/G, global-norm clip and Adam.
+
+On a box whose GPUs can map each other's memory both run as small kernels of this library over NVLink peer memory
+(xagents_b200/peer.py, csrc/peer_adam.cu: C1 fused with the optimiser; C2 a 128-thread kernel), because NCCL's kernels
+cannot share an SM with the persistent gather and would run after it.  This module keeps the NCCL versions (the fallback and
+the measured baseline: all-reduce on a high-priority side stream, waited for by the optimiser) and the host-side plumbing.
 
 One process per GPU, torch.distributed for the plumbing (NCCL over NVLink on the box, gloo in CPU tests).
 """

@@ -9,23 +9,23 @@ train step of the reference --
                           advantage normalisation            xagents/ppo/agent.py:180-183
     PPO.update_gradients: clipped surrogate+value+entropy    xagents/ppo/agent.py:96-134
 
--- into 2 + 2*K*M kernel launches through the C ABI: one GAE scan, one moments launch for all K*M
-minibatches, then per minibatch one gather (observation rows by TMA bulk copy + the four scalar
-fields) and one fused loss forward+backward.  Launch arguments are resolved once (`prepare`), so a
-step is a tight loop of ctypes calls on fixed device pointers: the host stays far ahead of the GPU
-and the sequence is CUDA-graph capturable.
+-- into a handful of prepared launches through the C ABI: one GAE scan, one moments launch for all K*M minibatches, ONE
+gather launch for all K*M minibatches (observation rows by TMA bulk copy; as few launches as fit the staging slots when
+they do not fit one), and per minibatch a device-side wait for ITS rows plus one fused loss forward+backward.  Launch
+arguments are resolved once (`prepare`), so a step is a tight loop of ctypes calls on fixed device pointers.
 
-Two streams: the caller's stream carries the arithmetic (GAE -> moments -> loss_0 .. loss_{KM-1}); a
-side "data" stream carries the gathers back to back, double-buffered through `staging` minibatch
-buffers, so the HBM-bound byte movement never waits for the latency-bound scalar kernels (in training,
-for the model's forward/backward of the previous minibatch).  With `fuse_fields=True` (default) the loss
-reads the four per-sample rollout scalars straight through the permutation (no scalar gather launch,
-no dependence of the gathers on GAE); `fuse_fields=False` materialises them like the reference does.
+Two streams: a "data" stream carries the gather; the caller's stream carries the arithmetic (GAE -> moments -> [C2] ->
+wait_0, forward_0, loss_0, backward_0 + C1 + optimiser_0, wait_1, ...).  The gather kernel counts the rows it has finished per
+minibatch in device memory (`progress`), and the compute stream waits on the counter of the minibatch it is about to consume
+(`sync='progress'`), so a long launch at full HBM rate feeds the per-minibatch chain without launch gaps; `sync='event'` (one
+CUDA event per gather launch, several minibatches per launch on a tapered schedule) is the capturable alternative.  The loss
+reads the four per-sample rollout scalars straight through the permutation (`fuse_fields=True`: no scalar gather, no
+dependence of the gathers on GAE); `fuse_fields=False` materialises them like the reference does.
 
-With a `dist.ShardComm` the environments are sharded across ranks (each rank owns a contiguous
-env-major range), the per-minibatch advantage moments are all-gathered once per step (collective C2)
-so normalisation uses the GLOBAL minibatch statistics as the single-process reference does, and a
-gradient all-reduce per minibatch (collective C1) runs on a side stream under the next gather.
+With a `dist.ShardComm` the environments are sharded across ranks (each rank owns a contiguous env-major range), the
+per-minibatch advantage moments are all-gathered once per step (collective C2) so normalisation uses the GLOBAL minibatch
+statistics as the single-process reference does; collective C1 belongs to the model adapter's `backward_and_step`
+(`after_loss` hook).  The agents bind this pipeline in place to their own rollout buffers (`buffers=`, `bind`).
 """
 import ctypes
 
