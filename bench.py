@@ -855,6 +855,8 @@ def gather_row_times(T, E, dev, reps):
     out = {}
     for mode, code in (('bulk', 1), ('vector', 2)):
         def call(s, code=code):
+            if os.environ.get('XA_BENCH_TRACE'):
+                print(f'gather_row_times T={T} E={E} mode={mode}', file=sys.stderr, flush=True)
             rc = lib.xa_gather_rows(P(obs), P(perm), P(dst), N, 28224, N, T, E, code, ctypes.c_void_p(s.cuda_stream))
             assert rc == 0, lib.xa_last_error()
         out[mode] = graph_us(call, reps, dev)

@@ -122,3 +122,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_ffi, '_lib', None)
     with pytest.raises(ImportError, match='no CPU or framework fallback'):
         _ffi.lib()
+
+
+def test_bench_reference_arm_runs_the_stated_small_workloads_on_the_host():
+    """`bench.py --impl reference --workload c1|c2`: the reference's CPU path (oracle port) on the host, one JSON line with the
+    contract's keys; no GPU involved."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for workload, metric in (('c1', 'ppo_env_steps_per_sec_gae_gather_loss'), ('c2', 'a2c_env_steps_per_sec_returns_loss')):
+        done = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', workload, '--steps', '3',
+                               '--warmup', '1'], capture_output=True, text=True, timeout=300, cwd=root)
+        assert done.returncode == 0, done.stderr[-2000:]
+        line = json.loads(done.stdout.strip().splitlines()[-1])
+        assert line['impl'] == 'reference' and line['metric'] == metric and line['value'] > 0 and line['steps'] == 3
+        assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == 1 and workload in line['config']['workload']
+        assert line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0

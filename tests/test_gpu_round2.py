@@ -278,7 +278,7 @@ def test_rollout_as_one_cuda_graph_equals_the_eager_loop(env_id, network):
     T, E = 6, 8
     agents = []
     for graph in (True, False):
-        made = envs.create_envs(env_id, E, preprocess=True, device=DEV)
+        made = envs.create_envs(env_id, E, preprocess=env_id.startswith('Synthetic'), device=DEV)
         made.seed(5)
         if hasattr(made, 'p_done'):
             made.p_done = 0.2

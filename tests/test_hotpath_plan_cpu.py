@@ -78,3 +78,28 @@ def test_there_is_no_cpu_path():
     hp = plan(4, 2, mini_batches=2, ppo_epochs=1)
     with pytest.raises(_ffi.XAError):
         hp.run()
+
+
+def test_pipeline_binds_to_the_callers_rollout_buffers_in_place():
+    """`buffers=` / `bind`: the agents hand their own `ro_*` tensors over, nothing is copied; shapes and dtypes are checked."""
+    import pytest
+    import torch
+    T, E = 6, 4
+    mine = {'obs': torch.zeros((T, E, 5), dtype=torch.float32), 'rewards': torch.zeros((T, E)), 'dones': torch.zeros((T + 1, E)),
+            'actions': torch.zeros((T, E, 3)), 'returns': torch.zeros((T, E))}
+    hp = PPOHotPath(T, E, (5,), 3, device='cpu', mini_batches=4, actor_kind='normal', buffers=mine)
+    for name, t in mine.items():
+        assert getattr(hp, name).data_ptr() == t.data_ptr()
+    assert hp.values.shape == (T, E) and hp.obs.dtype == torch.float32 and hp.sync == 'event'       # no CUDA device: event sync
+    other = torch.zeros((T, E))
+    hp.prepare()
+    hp.bind(rewards=other)
+    assert hp.rewards.data_ptr() == other.data_ptr() and hp._calls is None                          # launches are re-resolved
+    with pytest.raises(AssertionError, match='time-major'):
+        hp.bind(dones=torch.zeros((T, E)))
+    with pytest.raises(AssertionError, match='unknown rollout field'):
+        hp.bind(nonsense=other)
+    with pytest.raises(AssertionError, match='vector actions need fuse_fields'):
+        PPOHotPath(T, E, (5,), 3, device='cpu', mini_batches=4, fuse_fields=False, buffers={'actions': mine['actions']})
+    with pytest.raises(AssertionError, match='progress sync needs'):
+        PPOHotPath(T, E, (5,), 3, device='cpu', mini_batches=4, sync='progress')
