@@ -821,6 +821,7 @@ def graph_us(fn, reps, dev):
     import torch
     s = torch.cuda.Stream(dev)
     g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize(dev)          # the inputs were produced on the caller's stream: the side stream must not race them
     with torch.cuda.stream(s):
         fn(s)
         s.synchronize()
