@@ -1032,17 +1032,17 @@ def run_sweep(args):
             'e2e': None, 'e2e_note': 'kernel sweep: no host-facing call'}
     if args.out:
         with open(args.out, 'w') as f:
-            f.write('# C5 sweep: returns/GAE scan and permute-gather (python bench.py --workload c5)\\n\\n')
-            f.write(f'Peak = {peak:.1f} GB/s ({peak_src}).  Device time per launch (CUDA-graph replay of prepared C-ABI calls).\\n\\n')
-            f.write('| T | E | MB | auto us | GB/s | frac | sequential (bit-exact) us | n-step us | CPU oracle ms | speed-up | note |\\n|---|---|---|---|---|---|---|---|---|---|---|\\n')
+            f.write('# C5 sweep: returns/GAE scan and permute-gather (python bench.py --workload c5)\n\n')
+            f.write(f'Peak = {peak:.1f} GB/s ({peak_src}).  Device time per launch (CUDA-graph replay of prepared C-ABI calls).\n\n')
+            f.write('| T | E | MB | auto us | GB/s | frac | sequential (bit-exact) us | n-step us | CPU oracle ms | speed-up | note |\n|---|---|---|---|---|---|---|---|---|---|---|\n')
             for r in gae_rows:
                 f.write(f"| {r['T']} | {r['E']} | {r['MB']:.2f} | {r['auto_us']:.1f} | {r['GBs']:.0f} | {r['frac']:.2f} | {r['sequential_bit_exact_us']:.1f} | "
                         f"{r['nstep_us']:.1f} | {r['cpu_oracle_ms']:.2f} | {r['cpu_oracle_ms'] * 1e3 / r['auto_us']:.0f}x | "
-                        f"{'' if r['meaningful'] else 'L2-resident, latency-bound'} |\\n")
-            f.write('\\n| rows | MB moved | bulk us | bulk GB/s | frac | vector us | torch index_select us | best vs torch | note |\\n|---|---|---|---|---|---|---|---|---|\\n')
+                        f"{'' if r['meaningful'] else 'L2-resident, latency-bound'} |\n")
+            f.write('\n| rows | MB moved | bulk us | bulk GB/s | frac | vector us | torch index_select us | best vs torch | note |\n|---|---|---|---|---|---|---|---|---|\n')
             for r in gather_rows:
                 f.write(f"| {r['rows']} | {r['MB']:.1f} | {r['bulk_us']:.1f} | {r['bulk_GBs']:.0f} | {r['frac']:.2f} | {r['vector_us']:.1f} | "
-                        f"{r['torch_index_select_us']:.1f} | {r['speedup_vs_torch']:.2f}x | {'' if r['meaningful'] else 'fits L2, latency-bound'} |\\n")
+                        f"{r['torch_index_select_us']:.1f} | {r['speedup_vs_torch']:.2f}x | {'' if r['meaningful'] else 'fits L2, latency-bound'} |\n")
     emit(line)
 
 
