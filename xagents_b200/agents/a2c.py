@@ -98,7 +98,10 @@ class A2C(OnPolicy):
         if actions is None and self.action_source is None:
             # sample + log_prob + entropy in one kernel (Philox stream keyed by the agent seed)
             counter = getattr(self, '_philox', None) if getattr(self.net, 'capturing', False) else None
-            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind, counter=counter,
+            rows = None
+            if step is not None and getattr(self, '_rollout_rows', False):     # the rollout loop: write row `step` of the buffers directly
+                rows = (self.ro_actions[step], self.ro_log_probs[step], self.ro_entropies[step])
+            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind, counter=counter, out=rows,
                                                      seed=int(self.seed) if self.seed else 0, offset=self._rng_offset)
             self._rng_offset += 2 * self.n_actions
             return actions, logp, critic, entropy, actor_out
@@ -134,21 +137,23 @@ class A2C(OnPolicy):
     def _rollout_loop(self, capturing=False):
         """n_steps x (model outputs -> row t of the rollout buffers -> environment step), a2c/agent.py:113-139."""
         step_states, step_dones = self.get_states(), self.get_dones()
+        self._rollout_rows = True                                  # the sampler writes its three rows in place
         for t in range(self.n_steps):
             states_d = self._to_device(step_states, self.obs_dtype)
             actions, logp, values, entropy, actor_out = self.get_model_outputs(states_d, training=False, step=t)
             self.ro_states[t].copy_(states_d)
-            self.ro_actions[t].copy_(actions)
+            for row, value in ((self.ro_actions[t], actions), (self.ro_log_probs[t], logp), (self.ro_entropies[t], entropy)):
+                if value.data_ptr() != row.data_ptr():             # an `action_source` / a subclass produced them elsewhere
+                    row.copy_(value)
             self.ro_values[t].copy_(values)
-            self.ro_log_probs[t].copy_(logp)
             self.ro_dones[t].copy_(self._to_device(step_dones))
-            self.ro_entropies[t].copy_(entropy)
             self.ro_actor[t].copy_(actor_out)
             *_, step_rewards, step_dones, step_states = self.step_envs(self._env_actions(actions), True, False)
             self.ro_rewards[t].copy_(self._to_device(step_rewards))
             if capturing:                                          # episode sums at the moment of each done flag
                 self._ro_sums[t].copy_(self._episode_log.pop()[1])
         self.ro_dones[self.n_steps].copy_(self._to_device(step_dones))
+        self._rollout_rows = False
 
     # ------------------------------------------------------------------ the rollout as one CUDA graph
     def _can_graph_rollout(self):
