@@ -288,6 +288,76 @@ int xa_gather_s2d_u8_bf16(const uint8_t* src, const int32_t* idx, void* dst, int
                           int n_steps, int n_envs, int height, int width, int channels, int block, int scale_255,
                           xa_stream_t stream);
 
+/* Split partials only (no reduction pass): xa_conv_wgrad_nhwc_bf16 / xa_gemm_bf16_atb leave fp32 partial sums
+ * [splits, n_out, ld_partial] (column kh*kw*channels of a row = the bias gradient) / [splits, m, n] for the caller's own
+ * reduction -- xa_grad_finalize_f32 adds the partials of every layer of the network in one launch.  The *_plan calls
+ * return the split count (host out-params) for given sizes on the current device. */
+int xa_conv_wgrad_nhwc_plan(int n_out, int channels, int kh, int kw, int64_t q_total, int* splits, int* ld_partial);
+int xa_conv_wgrad_nhwc_bf16_partial(const void* x, const void* dy_grid, int n_out, int channels, int kh, int kw,
+                                    int grid_w, int64_t q_total, float* partial, int64_t partial_bytes,
+                                    xa_stream_t stream);
+int xa_gemm_atb_plan(int64_t m, int64_t n, int64_t k, int* splits);
+int xa_gemm_bf16_atb_partial(const void* a, const void* b, int64_t m, int64_t n, int64_t k, float* partial,
+                             int64_t partial_bytes, xa_stream_t stream);
+
+/* The actor / critic heads (two Dense layers on the 512-wide trunk output, ppo/models/cnn-actor-critic.cfg:30-42) in one
+ * pass over h each way.  wh [8, hidden] bf16 = both heads stacked (rows n_actions+1.. zero), bh [8] fp32.
+ * forward:  actor [batch, n_actions], critic [batch] fp32 (tf.squeeze'd, a2c/agent.py:84).
+ * backward: d_actor / d_critic fp32 from the loss kernel -> dh [batch, hidden] bf16 = (d_out wh) * (h > 0), and per-CTA
+ * partial blocks [xa_heads_backward_blocks(batch)][10][hidden] fp32: rows 0-7 dW_heads, row 8 db of the layer that
+ * produced h (column sums of dh), row 9 db_heads in its first 8 entries.  hidden must be 512, n_actions <= 7. */
+int xa_heads_backward_blocks(int batch);
+int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float* actor, float* critic, int batch,
+                          int hidden, int n_actions, xa_stream_t stream);
+int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const void* h, const void* wh, void* dh,
+                           float* partial, int64_t partial_floats, int batch, int hidden, int n_actions,
+                           xa_stream_t stream);
+
+/* tape.gradient's results into the flat gradient buffer of the optimiser step (xagents/ppo/agent.py:134-137):
+ * grad[j] = sum_{s < splits} src[map[j] + s*split_stride] (0 where map[j] < 0) with splits / split_stride constant over
+ * segments of consecutive j (segment i covers [dest_begin_i, dest_begin_{i+1}); the first starts at 0, the last ends at
+ * n).  `wide` segments (many splits) are summed by four lanes per output.  segments: HOST array. */
+#define XA_MAX_GRAD_SEGMENTS 16
+typedef struct xa_grad_segment_t {
+  int64_t dest_begin;
+  int64_t split_stride;
+  int32_t splits;
+  int32_t wide;
+} xa_grad_segment_t;
+int xa_grad_finalize_f32(const float* src, const int32_t* map, const xa_grad_segment_t* segments, int n_segments,
+                         float* grad, int64_t n, xa_stream_t stream);
+
+/* The documented PPO/A2C network (README.md:243-259; ppo/models/cnn-actor-critic.cfg) as two calls: every launch of the
+ * forward / backward pass issued from native code over buffers the caller owns (HOST struct of device pointers).
+ *   operands     bf16 weight layouts and fp32 biases (agents/tc_operands.py)
+ *   activations  x1 [B,21,21,64] (space-to-depth input; unused when the frames arrive in that form), x2 [B,10,10,128],
+ *                x3 [B,9,9,64], y3 [B,7,7,64], h [B,512] bf16; actor [B,A], critic [B] fp32
+ *   gradients    dh [B,512], g3 [B,9,9,64], g2 [B,10,10,64], g1 [B,21,21,32] bf16 (the g* zero-filled once by the caller:
+ *                only their valid corners are ever written); scratch: fp32 partial sums at the given offsets
+ *   grad_map / segments   for xa_grad_finalize_f32 over `scratch`
+ * forward: frames uint8 [B,84,84,4] (frames_s2d = 0) or bf16 [B,21,21,64] already scaled and space-to-depth'd (1).
+ * backward: d_actor [B,A], d_critic [B] fp32 -> flat_grad [n_grad] fp32, every element written. */
+typedef struct xa_nature_cnn_t {
+  int32_t batch, n_actions;
+  const void *w1, *w2, *w3, *w2_flip, *w3_flip, *wf, *wf_t, *wh;
+  const float *b1, *b2, *b3, *bf, *bh;
+  void *x1, *x2, *x3, *y3, *h;
+  float *actor, *critic;
+  void *dh, *g3, *g2, *g1;
+  void* gemm_ws; /* optional split-K scratch of the FC forward product (small batches) */
+  int64_t gemm_ws_bytes;
+  float* scratch;
+  int64_t scratch_floats;
+  int64_t off_c1, off_c2, off_c3, off_fc, off_heads; /* float offsets into scratch */
+  const int32_t* grad_map;
+  xa_grad_segment_t segments[XA_MAX_GRAD_SEGMENTS];
+  int32_t n_segments, reserved;
+  int64_t n_grad;
+} xa_nature_cnn_t;
+int xa_nature_cnn_forward(const xa_nature_cnn_t* net, const void* frames, int frames_s2d, xa_stream_t stream);
+int xa_nature_cnn_backward(const xa_nature_cnn_t* net, const void* frames_s2d_or_null, const float* d_actor,
+                           const float* d_critic, float* flat_grad, xa_stream_t stream);
+
 /* Operand preparation for the Dense / convolution products above (no reference counterpart: the reference computes in
  * fp32 throughout).  fp32 | bf16 [rows, cols] -> bf16, same orientation (dst pitch ld_dst >= cols) or transposed into
  * [cols, ld_dst >= rows]: operand preparation for the backward products (dW = dY^T X needs both transposed). */

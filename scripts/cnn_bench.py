@@ -84,3 +84,29 @@ t_bf16 = timeit(lambda: torch_step(True), 5)
 fl = 3 * 18.7e6 * B
 print(f'\nforward+backward at B={B}: ours {t_ours:.0f} us ({fl / t_ours / 1e6:.0f} TFLOP/s), torch fp32 {t_fp32:.0f} us, '
       f'torch bf16 autocast {t_bf16:.0f} us  -> {t_bf16 / t_ours:.1f}x / {t_fp32 / t_ours:.1f}x')
+
+# ---- the same step through the native plan (two C calls per minibatch, agents/tc_plan.py): what TorchModel runs
+from xagents_b200.agents import TorchModel  # noqa: E402
+
+tm = TorchModel(NatureCnnTc(4, 6).cuda())
+plan = tm.module.plan(B, tm.flat_param, tm.flat_grad.numel())
+
+
+def plan_step():
+    plan.forward(x)
+    plan.backward(da, dc, tm.flat_grad)
+
+
+t_plan = timeit(plan_step, 20)
+t_fwd = timeit(lambda: plan.forward(x), 20)
+x_s2d = ops.space_to_depth_u8_bf16(x, 4)
+
+
+def plan_step_s2d():
+    plan.forward(x_s2d)
+    plan.backward(da, dc, tm.flat_grad)
+
+
+t_plan_s2d = timeit(plan_step_s2d, 20)
+print(f'native plan at B={B}: forward+backward {t_plan:.0f} us ({fl / t_plan / 1e6:.0f} TFLOP/s), forward alone {t_fwd:.0f} us, '
+      f'forward+backward from space-to-depth input (the fused gather\'s output) {t_plan_s2d:.0f} us')

@@ -82,6 +82,24 @@ def test_loss_args_struct_matches_the_header_layout():
     assert _ffi.LossArgs.n.offset == 96 and _ffi.LossArgs.out_scalars.offset == 128
 
 
+def test_network_plan_structs_match_the_header_layout(tmp_path):
+    """xa_nature_cnn_t / xa_grad_segment_t as gcc lays them out from the header vs the ctypes mirrors."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "xagents_b200.h"\nint main(void) {\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(xa_grad_segment_t), sizeof(xa_nature_cnn_t), offsetof(xa_nature_cnn_t, w1),\n'
+                   'offsetof(xa_nature_cnn_t, gemm_ws_bytes), offsetof(xa_nature_cnn_t, grad_map), offsetof(xa_nature_cnn_t, segments),\n'
+                   'offsetof(xa_nature_cnn_t, n_grad)); return 0; }\n')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    n = _ffi.NatureCnn
+    assert got == [ctypes.sizeof(_ffi.GradSegment), ctypes.sizeof(n), n.w1.offset, n.gemm_ws_bytes.offset, n.grad_map.offset,
+                   n.segments.offset, n.n_grad.offset]
+
+
 def test_dlpack_reader_is_zero_copy_and_consumes_the_capsule():
     t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
     arr = _dlpack.as_device_array(t, 'float32', allow_host=True)

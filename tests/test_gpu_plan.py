@@ -1,0 +1,174 @@
+"""The native two-call form of the policy/value network (csrc/nature_net.cu, heads.cu, grad_finalize.cu; agents/tc_plan.py):
+heads kernels and the gradient finalisation against plain fp32 torch, the plan against the autograd form of the same
+pipeline and against the bf16-emulating fp64 reference of test_gpu_conv.py."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _call(name, *args):
+    from xagents_b200 import _ffi
+    _ffi.check(name, getattr(_ffi.lib(), name)(*args))
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (256, 4), (8192, 7)])
+def test_heads_forward_vs_torch(B, A):
+    torch.manual_seed(B)
+    h = torch.randn(B, 512, device=DEV).relu().bfloat16()
+    wh = torch.zeros(8, 512, device=DEV)
+    wh[:A + 1] = torch.randn(A + 1, 512, device=DEV) * 0.05
+    wh16 = wh.bfloat16()
+    bh = torch.zeros(8, device=DEV)
+    bh[:A + 1] = torch.randn(A + 1, device=DEV)
+    actor = torch.full((B, A), float('nan'), device=DEV)
+    critic = torch.full((B,), float('nan'), device=DEV)
+    _call('xa_heads_forward_bf16', _p(h), _p(wh16), _p(bh), _p(actor), _p(critic), B, 512, A, _s())
+    ref = h.float() @ wh16.float().t() + bh
+    torch.testing.assert_close(actor, ref[:, :A], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(critic, ref[:, A], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (100, 3), (8192, 6)])
+def test_heads_backward_vs_torch(B, A):
+    from xagents_b200 import _ffi
+    torch.manual_seed(B + 1)
+    h = torch.randn(B, 512, device=DEV).relu().bfloat16()
+    wh = torch.zeros(8, 512, device=DEV)
+    wh[:A + 1] = torch.randn(A + 1, 512, device=DEV) * 0.05
+    wh16 = wh.bfloat16()
+    d_actor, d_critic = torch.randn(B, A, device=DEV) / B, torch.randn(B, device=DEV) / B
+    blocks = _ffi.lib().xa_heads_backward_blocks(B)
+    assert blocks == -(-B // 64)
+    partial = torch.full((blocks, 10, 512), float('nan'), device=DEV)
+    dh = torch.full((B, 512), float('nan'), device=DEV, dtype=torch.bfloat16)
+    _call('xa_heads_backward_bf16', _p(d_actor), _p(d_critic), _p(h), _p(wh16), _p(dh), _p(partial), partial.numel(), B, 512, A, _s())
+    d_out = torch.zeros(B, 8, device=DEV)
+    d_out[:, :A], d_out[:, A] = d_actor, d_critic
+    ref_dh = ((d_out @ wh16.float()) * (h > 0)).bfloat16()
+    # one fma order against torch's: ties of the bf16 rounding may flip
+    assert ((dh.float() - ref_dh.float()).abs() <= 1e-2 * ref_dh.float().abs() + 1e-9).all()
+    assert (dh != ref_dh).float().mean() < 2e-2
+    torch.testing.assert_close(partial[:, :8].sum(0), d_out.t() @ h.float(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(partial[:, 8].sum(0), dh.float().sum(0), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(partial[:, 9, :8].sum(0), d_out.sum(0), rtol=1e-4, atol=1e-7)
+
+
+def test_grad_finalize_adds_splits_in_order_and_permutes():
+    from xagents_b200 import _ffi
+    torch.manual_seed(3)
+    # three segments: 1000 outputs x 37 splits (wide), 5000 outputs x 1 split through a permutation, 300 outputs x 2 splits;
+    # 4 padding outputs without a source
+    n = 1000 + 5000 + 300 + 4
+    src = torch.randn(37 * 1000 + 5000 + 2 * 300, device=DEV)
+    gmap = torch.full((n,), -1, dtype=torch.int32, device=DEV)
+    gmap[:1000] = torch.randperm(1000, device=DEV).int()
+    gmap[1000:6000] = 37000 + torch.randperm(5000, device=DEV).int()
+    gmap[6000:6300] = 42000 + torch.arange(300, device=DEV).int()
+    segs = (_ffi.GradSegment * 3)()
+    for s, (begin, stride, splits, wide) in zip(segs, ((0, 1000, 37, 1), (1000, 0, 1, 0), (6000, 300, 2, 0))):
+        s.dest_begin, s.split_stride, s.splits, s.wide = begin, stride, splits, wide
+    grad = torch.full((n,), float('nan'), device=DEV)
+    _call('xa_grad_finalize_f32', _p(src), _p(gmap), segs, 3, _p(grad), n, _s())
+    a = src[:37000].view(37, 1000)[:, gmap[:1000].long()]
+    # four lanes, each a contiguous quarter of the splits in order, then (q0 + q1) + (q2 + q3)
+    quarters = []
+    for q in range(4):
+        acc = torch.zeros(1000, device=DEV)
+        for k in range(q * 10, min(37, q * 10 + 10)):
+            acc = acc + a[k]
+        quarters.append(acc)
+    assert torch.equal(grad[:1000], (quarters[0] + quarters[1]) + (quarters[2] + quarters[3]))
+    assert torch.equal(grad[1000:6000], src[gmap[1000:6000].long()])
+    b = src[42000:].view(2, 300)
+    assert torch.equal(grad[6000:6300], b[0] + b[1])
+    assert torch.equal(grad[6300:], torch.zeros(4, device=DEV))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('B,s2d_input', [(37, False), (512, True), (1000, False)])
+def test_native_plan_matches_the_autograd_pipeline_and_the_emulated_reference(B, s2d_input):
+    """TorchModel with the native plan against (a) the same network through torch autograd around the same kernels and
+    (b) the fp64 reference that rounds to bf16 where the pipeline does."""
+    from test_gpu_conv import _emulated_backward
+    from xagents_b200 import ops
+    from xagents_b200.agents import NatureCNN, NatureCnnTc, TorchModel
+    torch.manual_seed(4)
+    mods = [NatureCnnTc(4, 6).cuda() for _ in range(2)]
+    with torch.no_grad():
+        for p in mods[0].parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn_like(p) * 0.05)
+        mods[0].actor.weight.mul_(30)
+    mods[1].load_state_dict(mods[0].state_dict())
+    ref = NatureCNN(4, 6).cuda()
+    ref.load_state_dict(mods[0].state_dict())
+    native, auto = TorchModel(mods[0], native_plan=True), TorchModel(mods[1], native_plan=False)
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    d_actor, d_critic = torch.randn((B, 6), device=DEV) / B, torch.randn(B, device=DEV) / B
+    frames = ops.space_to_depth_u8_bf16(x, 4) if s2d_input else x
+    outs = []
+    for m in (native, auto):
+        a, c = m.forward(frames, training=True)
+        outs.append((a.clone(), c.clone()))
+        m.lr = 0.0                                                       # keep the weights: only the gradients are compared
+        m.backward_and_step(d_actor, d_critic, grad_norm=None)
+    torch.cuda.synchronize()
+    assert native._native_plan and not auto._native_plan
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=2e-3, atol=2e-3)     # the heads product: fp32 fma order vs the GEMM's
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=2e-3, atol=2e-3)
+    with torch.no_grad():
+        emu = _emulated_backward(ref, x, d_actor, d_critic)
+    for (name, p), q in zip(mods[0].named_parameters(), mods[1].parameters()):
+        g, r, e = p.grad.flatten().double(), q.grad.flatten().double(), emu[name].flatten()
+        rel_auto, rel_emu = float((g - r).norm() / r.norm()), float((g - e).norm() / e.norm())
+        print(f'{name:18s} vs autograd pipeline rel-L2 {rel_auto:.5f} | vs bf16-emulated fp64 rel-L2 {rel_emu:.5f}')
+        # the autograd pipeline rounds d_out to bf16 before the heads products; the plan keeps it in fp32
+        assert rel_auto < 2e-2, f'{name}: {rel_auto:.5f} against the autograd pipeline'
+        assert rel_emu < 2e-2, f'{name}: {rel_emu:.5f} against the bf16-emulated reference'
+    assert torch.isfinite(native.flat_grad).all()
+    # a second minibatch through the same plan: buffers are reused, nothing accumulates
+    g1 = native.flat_grad.clone()
+    native.forward(frames, training=True)
+    native.backward_and_step(d_actor, d_critic, grad_norm=None)
+    torch.cuda.synchronize()
+    assert torch.equal(g1, native.flat_grad), 'the native backward is deterministic and overwrites its outputs'
+
+
+@pytest.mark.timeout(300)
+def test_ppo_train_step_through_the_native_plan_matches_the_autograd_pipeline():
+    """Two PPO agents on the same replayed environments and seeds, one per network path: the same losses to bf16 accuracy."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    from xagents_b200.agents import PPO, NatureCnnTc, TorchModel
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    T, E, A = 8, 4, 6
+    losses = []
+    for native in (True, False):
+        rng = np.random.default_rng(11)
+        obs, rewards, dones, resets = mg._streams(rng, 4 * T, E, (84, 84, 4), True, 0.1)
+        envs = [mg.ReplayEnv(obs[i], rewards[i], dones[i], resets[i], mg.Discrete(A)) for i in range(E)]
+        torch.manual_seed(0)
+        net = TorchModel(NatureCnnTc(4, A).cuda(), native_plan=native)
+        agent = PPO(envs, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=5)
+        agent.fit(max_steps=2 * T * E)
+        torch.cuda.synchronize()
+        assert net.step == 2 * 2 * 4 and torch.isfinite(net.flat_param).all()
+        losses.append(torch.stack(agent.loss_history).cpu().numpy())
+    assert np.isfinite(losses[0]).all()
+    np.testing.assert_allclose(losses[0][:4], losses[1][:4], rtol=5e-2, atol=5e-3)

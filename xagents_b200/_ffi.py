@@ -58,6 +58,25 @@ class PeerGatherArgs(ctypes.Structure):
                 ('n_per_rank', ctypes.c_int64), ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('epoch', ctypes.c_uint32)]
 
 
+XA_MAX_GRAD_SEGMENTS = 16
+
+
+class GradSegment(ctypes.Structure):
+    """struct xa_grad_segment_t"""
+    _fields_ = [('dest_begin', ctypes.c_int64), ('split_stride', ctypes.c_int64), ('splits', ctypes.c_int32), ('wide', ctypes.c_int32)]
+
+
+class NatureCnn(ctypes.Structure):
+    """struct xa_nature_cnn_t"""
+    _fields_ = ([('batch', ctypes.c_int32), ('n_actions', ctypes.c_int32)] +
+                [(name, ctypes.c_void_p) for name in ('w1', 'w2', 'w3', 'w2_flip', 'w3_flip', 'wf', 'wf_t', 'wh', 'b1', 'b2', 'b3', 'bf', 'bh',
+                                                      'x1', 'x2', 'x3', 'y3', 'h', 'actor', 'critic', 'dh', 'g3', 'g2', 'g1', 'gemm_ws')] +
+                [('gemm_ws_bytes', ctypes.c_int64), ('scratch', ctypes.c_void_p), ('scratch_floats', ctypes.c_int64)] +
+                [(name, ctypes.c_int64) for name in ('off_c1', 'off_c2', 'off_c3', 'off_fc', 'off_heads')] +
+                [('grad_map', ctypes.c_void_p), ('segments', GradSegment * XA_MAX_GRAD_SEGMENTS), ('n_segments', ctypes.c_int32),
+                 ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64)])
+
+
 # name -> (restype, argtypes); every symbol include/xagents_b200.h declares
 PROTOTYPES = {
     'xa_version': (ctypes.c_int, []),
@@ -109,6 +128,17 @@ PROTOTYPES = {
     'xa_space_to_depth_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [c_stream]),
     'xa_conv_wgrad_nhwc_workspace_bytes': (ctypes.c_int64, [ctypes.c_int] * 4),
     'xa_conv_wgrad_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_conv_wgrad_nhwc_plan': (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    'xa_conv_wgrad_nhwc_bf16_partial': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_gemm_atb_plan': (ctypes.c_int, [ctypes.c_int64] * 3 + [ctypes.POINTER(ctypes.c_int)]),
+    'xa_gemm_bf16_atb_partial': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
+    'xa_heads_backward_blocks': (ctypes.c_int, [ctypes.c_int]),
+    'xa_heads_forward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [c_stream]),
+    'xa_heads_backward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 3 + [c_stream]),
+    'xa_grad_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GradSegment), ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int64, c_stream]),
+    'xa_nature_cnn_forward': (ctypes.c_int, [ctypes.POINTER(NatureCnn), ctypes.c_void_p, ctypes.c_int, c_stream]),
+    'xa_nature_cnn_backward': (ctypes.c_int, [ctypes.POINTER(NatureCnn)] + [ctypes.c_void_p] * 4 + [c_stream]),
     'xa_gather_s2d_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64] +
                               [ctypes.c_int] * 7 + [c_stream]),
     'xa_to_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

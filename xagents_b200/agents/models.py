@@ -23,11 +23,13 @@ from ..optim import FlatAdam
 
 class TorchModel:
     def __init__(self, module, lr=7e-4, beta1=0.9, beta2=0.999, epsilon=1e-7, img_inputs=None, output_is_softmax=False,
-                 comm=None, tensor_core_inference=False, graph_inference=True, role='actor_critic', fused_c1='auto'):
+                 comm=None, tensor_core_inference=False, graph_inference=True, role='actor_critic', fused_c1='auto', native_plan=True):
         """`fused_c1` (sharded training, comm.world_size > 1): 'auto' / True = the gradient all-reduce, the global-norm clip
         and Adam run as ONE kernel over NVLink peer memory (xagents_b200/peer.py) when the box can map peer memory -- the flat
         parameter and gradient buffers then live in peer-mapped memory and Adam's m, v exist only for this rank's shard;
-        False = NCCL all-reduce + the two-launch clip+Adam."""
+        False = NCCL all-reduce + the two-launch clip+Adam.
+        `native_plan`: a module that offers `plan()` (NatureCnnTc) trains through its two native calls per minibatch, the backward
+        writing the flat gradient buffer directly (agents/tc_plan.py); False keeps torch autograd around the same kernels."""
         assert role in ('actor_critic', 'actor', 'critic'), f'unknown model role `{role}`'
         self.module = module
         self.role = role                                          # 'actor' / 'critic': TRPO's separate single-output networks
@@ -66,6 +68,7 @@ class TorchModel:
             off += k
         self.n_params = n
         self._outputs = None
+        self._native_plan = bool(native_plan) and role == 'actor_critic' and hasattr(module, 'plan')
         self._refreshable = [m for m in module.modules() if hasattr(m, 'refresh')]
         for mod in self._refreshable:
             mod.refresh()
@@ -86,6 +89,10 @@ class TorchModel:
                 return a.clone(), c.clone()
             return self._tc_forward(states)
         x = self.scaled(states)
+        if training and self._native_plan and x.dtype in (torch.uint8, torch.bfloat16):
+            plan = self.module.plan(x.shape[0], self.flat_param, self.flat_grad.numel())
+            self._outputs = plan
+            return plan.forward(x.contiguous())
         with torch.set_grad_enabled(training):
             out = self.module(x)
         if self.role == 'actor_critic':
@@ -110,10 +117,13 @@ class TorchModel:
         return x / 255.0 if scale else x
 
     def backward_and_step(self, d_actor, d_values, grad_norm=None):
-        actor, critic = self._outputs
-        self.flat_grad.zero_()
-        pairs = [(o, g) for o, g in ((actor, d_actor), (critic, d_values)) if o is not None]
-        torch.autograd.backward([o for o, _ in pairs], [g.view_as(o) for o, g in pairs])
+        if self._native_plan and not isinstance(self._outputs, tuple):
+            self._outputs.backward(d_actor, d_values, self.flat_grad)      # writes every element: no zero-fill
+        else:
+            actor, critic = self._outputs
+            self.flat_grad.zero_()
+            pairs = [(o, g) for o, g in ((actor, d_actor), (critic, d_values)) if o is not None]
+            torch.autograd.backward([o for o, _ in pairs], [g.view_as(o) for o, g in pairs])
         self._outputs = None
         self.step += 1
         if self.fused is not None:                                # collective C1 + clip + Adam: one kernel over peer memory

@@ -91,6 +91,7 @@ class NatureCnnTc(NatureCNN):
         assert in_channels == 4, 'the space-to-depth layouts are built for 84x84x4 frames'
         super().__init__(in_channels, n_actions)
         self._op = None
+        self._plans = {}
 
     def refresh(self):
         """bf16 operand layouts of the current weights: two launches (index-map gather + cast, tc_operands.py)."""
@@ -99,6 +100,21 @@ class NatureCnnTc(NatureCNN):
         else:
             self._op.refresh()
         return self
+
+    def plan(self, batch, flat_param=None, n_grad=None):
+        """The native two-call form of this network for one batch size (tc_plan.NaturePlan).  With `flat_param` (the flat fp32
+        buffer the parameters are views of, e.g. TorchModel.flat_param) the plan also back-propagates, writing straight into a
+        flat gradient buffer of `n_grad` elements laid out like it."""
+        if self._op is None:
+            self.refresh()
+        key = (int(batch), None if flat_param is None else flat_param.data_ptr(), n_grad)
+        plan = self._plans.get(key)
+        if plan is None:
+            from .tc_plan import NaturePlan
+            if len(self._plans) >= 4:                              # minibatch / rollout / bootstrap sizes; do not hoard activations
+                self._plans.pop(next(iter(self._plans)))
+            plan = self._plans[key] = NaturePlan(self._op, self._op._named, flat_param, batch, n_grad=n_grad, backward=flat_param is not None)
+        return plan
 
     def forward(self, frames_u8):
         if self._op is None:

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kThreads) gemm_atb_kernel(const __grid_constan
   const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
   const int k_blocks = static_cast<int>((p.k + kBlockK - 1) / kBlockK);
   const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // a power of two
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -149,20 +149,37 @@ __global__ void __launch_bounds__(256) atb_reduce_kernel(const AtbParams p) {
   }
 }
 
-int atb_tile_n(int64_t n) { return n > 64 ? 128 : 64; }
-
-int atb_splits(int64_t m, int64_t n, int64_t k) {
-  const int bn = atb_tile_n(n);
-  const int64_t tiles = ((m + kBlockM - 1) / kBlockM) * ((n + bn - 1) / bn);
+// Tile width and K split by a small cost model (cycles of the slowest CTA x waves): a 128 x BN x 16 MMA with both operands in
+// shared memory costs max(BN / 2, 32 + BN / 4) cycles (math vs operand fetch, scripts/umma_microbench.cu), a CTA adds ~3000
+// cycles of prologue + epilogue, and a launch should fill the SMs once.  The FC weight gradient of the network
+// (512 x 3136 x 8192) lands on BN = 192 with 2 splits: 136 CTAs of 64 K blocks instead of 100 CTAs of 128.
+struct AtbPlan {
+  int bn, splits;
+};
+AtbPlan atb_plan(int64_t m, int64_t n, int64_t k, bool may_split) {
   const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  int64_t splits = sms / tiles;  // one wave
-  if (splits > k_blocks / 8) splits = k_blocks / 8;
-  return splits < 2 ? 1 : static_cast<int>(splits);
+  AtbPlan best{n > 64 ? 128 : 64, 1};
+  double best_cost = 1e30;
+  const int widths[3] = {64, 128, 192};
+  for (int bn : widths) {
+    if (bn > 64 && n <= bn - 64) continue;   // a narrower tile already covers n
+    const int64_t tiles = ((m + kBlockM - 1) / kBlockM) * ((n + bn - 1) / bn);
+    const int max_splits = may_split ? static_cast<int>(k_blocks / 8 > 16 ? 16 : (k_blocks / 8 < 1 ? 1 : k_blocks / 8)) : 1;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int64_t per = (k_blocks + sp - 1) / sp;
+      const int64_t ctas = tiles * ((k_blocks + per - 1) / per);
+      const int64_t waves = (ctas + sms - 1) / sms;
+      const double mma = bn / 2 > 32 + bn / 4 ? bn / 2 : 32 + bn / 4;
+      const double cost = static_cast<double>(waves) * (static_cast<double>(per) * 4.0 * mma + 3000.0) + (sp > 1 ? 1500.0 + 40.0 * sp : 0.0);
+      if (cost < best_cost) best_cost = cost, best = AtbPlan{bn, static_cast<int>((k_blocks + per - 1) / per)};
+    }
+  }
+  return best;
 }
 
 template <int BN>
-int launch_atb(const CUtensorMap& ma, const CUtensorMap& mb, const AtbParams& p, cudaStream_t s, const char* what) {
+int launch_atb(const CUtensorMap& ma, const CUtensorMap& mb, const AtbParams& p, cudaStream_t s, const char* what, bool reduce) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -177,7 +194,7 @@ int launch_atb(const CUtensorMap& ma, const CUtensorMap& mb, const AtbParams& p,
   const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN);
   gemm_atb_kernel<BN><<<static_cast<unsigned>(tiles * p.splits), kThreads, AtbSmem<BN>::kBytes, s>>>(ma, mb, p);
   if (int rc = xa::check_launch(what)) return rc;
-  if (p.splits > 1) {
+  if (p.splits > 1 && reduce) {
     const int64_t want = (p.m * p.n + 255) / 256;
     atb_reduce_kernel<<<static_cast<unsigned>(want < 4096 ? want : 4096), 256, 0, s>>>(p);
     return xa::check_launch(what);
@@ -190,13 +207,18 @@ int launch_atb(const CUtensorMap& ma, const CUtensorMap& mb, const AtbParams& p,
 extern "C" {
 
 int64_t xa_gemm_atb_workspace_bytes(int64_t m, int64_t n, int64_t k) {
-  const int splits = atb_splits(m, n, k);
+  const int splits = atb_plan(m, n, k, true).splits;
   return splits > 1 ? static_cast<int64_t>(splits) * m * n * static_cast<int64_t>(sizeof(float)) : 0;
 }
 
-int xa_gemm_bf16_atb(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int64_t ldc, void* workspace,
-                     int64_t workspace_bytes, xa_stream_t stream) {
-  const char* what = "xa_gemm_bf16_atb";
+int xa_gemm_atb_plan(int64_t m, int64_t n, int64_t k, int* splits) {
+  XA_REQUIRE(m > 0 && n > 0 && k > 0, XA_EINVAL, "xa_gemm_atb_plan: non-positive size");
+  if (splits) *splits = atb_plan(m, n, k, true).splits;
+  return XA_OK;
+}
+
+static int atb_run(const char* what, const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int64_t ldc, void* workspace,
+                   int64_t workspace_bytes, bool reduce, xa_stream_t stream) {
   XA_REQUIRE(a && b && c, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(m > 0 && n > 0 && k > 0 && ldc >= n, XA_EINVAL, "%s: m=%lld n=%lld k=%lld ldc=%lld", what, static_cast<long long>(m),
              static_cast<long long>(n), static_cast<long long>(k), static_cast<long long>(ldc));
@@ -210,16 +232,40 @@ int xa_gemm_bf16_atb(const void* a, const void* b, float* c, int64_t m, int64_t 
   AtbParams p{};
   p.c = c, p.m = m, p.n = n, p.k = k, p.ldc = ldc;
   const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
-  const int splits = workspace != nullptr ? atb_splits(m, n, k) : 1;
-  if (splits > 1 && workspace_bytes >= static_cast<int64_t>(splits) * m * n * 4) {
-    p.kb_per_split = static_cast<int>((k_blocks + splits - 1) / splits);
+  AtbPlan plan = atb_plan(m, n, k, workspace != nullptr);
+  if (plan.splits > 1 && workspace_bytes < static_cast<int64_t>(plan.splits) * m * n * 4) plan = atb_plan(m, n, k, false);
+  if (plan.splits > 1) {
+    p.kb_per_split = static_cast<int>((k_blocks + plan.splits - 1) / plan.splits);
     p.splits = static_cast<int>((k_blocks + p.kb_per_split - 1) / p.kb_per_split);
     p.partial = static_cast<float*>(workspace);
   } else {
     p.splits = 1, p.kb_per_split = static_cast<int>(k_blocks);
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return atb_tile_n(n) == 128 ? launch_atb<128>(ma, mb, p, s, what) : launch_atb<64>(ma, mb, p, s, what);
+  switch (plan.bn) {
+    case 192:
+      return launch_atb<192>(ma, mb, p, s, what, reduce);
+    case 128:
+      return launch_atb<128>(ma, mb, p, s, what, reduce);
+    default:
+      return launch_atb<64>(ma, mb, p, s, what, reduce);
+  }
+}
+
+int xa_gemm_bf16_atb(const void* a, const void* b, float* c, int64_t m, int64_t n, int64_t k, int64_t ldc, void* workspace,
+                     int64_t workspace_bytes, xa_stream_t stream) {
+  return atb_run("xa_gemm_bf16_atb", a, b, c, m, n, k, ldc, workspace, workspace_bytes, true, stream);
+}
+
+/* The same product left as split partials [splits, m, n] (splits from xa_gemm_atb_plan; with splits == 1 the product itself
+ * lands in `partial`): the caller's own reduction (xa_grad_finalize_f32) adds them. */
+int xa_gemm_bf16_atb_partial(const void* a, const void* b, int64_t m, int64_t n, int64_t k, float* partial, int64_t partial_bytes,
+                             xa_stream_t stream) {
+  const char* what = "xa_gemm_bf16_atb_partial";
+  XA_REQUIRE(partial != nullptr, XA_EINVAL, "%s: null pointer", what);
+  const int splits = atb_plan(m > 0 ? m : 1, n > 0 ? n : 1, k > 0 ? k : 1, true).splits;
+  XA_REQUIRE(partial_bytes >= static_cast<int64_t>(splits) * m * n * 4, XA_ENOSPACE, "%s: partial buffer too small", what);
+  return atb_run(what, a, b, partial, m, n, k, n, splits > 1 ? partial : nullptr, partial_bytes, false, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,121 @@
+// Last kernel of the network's backward pass: every weight / bias gradient goes from where its kernel left it (split
+// partial sums, kernel-friendly layouts) to its place in the ONE flat fp32 gradient buffer the fused clip + Adam step reads
+// (tape.gradient -> clip_by_global_norm -> apply_gradients, xagents/ppo/agent.py:134-137).
+//
+//   grad[j] = sum over s < splits(j) of  src[map[j] + s * stride(j)]        (0 where map[j] < 0)
+//
+// `map` is the permutation between the parameter layouts (torch / Keras order) and the kernels' operand layouts, built
+// once on the host from index tensors (agents/tc_plan.py); splits / stride are constant over a SEGMENT of consecutive j
+// (one segment per parameter tensor).  Splits are added in order with a fixed association, so the result is
+// deterministic.  This one launch replaces three split reductions, four layout copies, two torch bias reductions, the
+// zero-fill of the gradient buffer and autograd's twelve accumulation kernels.
+#include "xa_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct FinalizeParams {
+  const float* src;
+  const int32_t* map;
+  float* grad;
+  int64_t n;
+  int n_segments;
+  int64_t wide_total;       // outputs handled by four lanes each
+  xa_grad_segment_t seg[XA_MAX_GRAD_SEGMENTS];
+  int64_t wide_begin[XA_MAX_GRAD_SEGMENTS + 1];   // prefix sums of the wide segments' lengths
+};
+
+__device__ __forceinline__ int find_segment(const FinalizeParams& p, int64_t j) {
+  int s = 0;
+#pragma unroll 1
+  while (s + 1 < p.n_segments && j >= p.seg[s + 1].dest_begin) ++s;
+  return s;
+}
+
+// blocks [0, narrow_blocks): one thread per output of a segment with few splits; the remaining blocks: four lanes per
+// output of the segments with many splits (each lane a contiguous quarter of the splits, combined by a fixed tree)
+__global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_constant__ FinalizeParams p, int narrow_blocks) {
+  if (static_cast<int>(blockIdx.x) < narrow_blocks) {
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < p.n; j += static_cast<int64_t>(narrow_blocks) * kThreads) {
+      const xa_grad_segment_t& sg = p.seg[find_segment(p, j)];
+      if (sg.wide) continue;
+      const int32_t m = p.map[j];
+      float acc = 0.0f;
+      if (m >= 0) {
+        const float* s = p.src + m;
+        for (int k = 0; k < sg.splits; ++k) acc += s[k * sg.split_stride];
+      }
+      p.grad[j] = acc;
+    }
+    return;
+  }
+  const int part = threadIdx.x & 3;
+  const int64_t first = (static_cast<int64_t>(blockIdx.x - narrow_blocks) * kThreads + threadIdx.x) >> 2;
+  const int64_t step = (static_cast<int64_t>(gridDim.x - narrow_blocks) * kThreads) >> 2;
+  const int64_t padded = ((p.wide_total + 7) / 8) * 8;   // whole warps reach the shuffles together
+  for (int64_t i = first; i < padded; i += step) {
+    float acc = 0.0f;
+    int64_t j = -1;
+    if (i < p.wide_total) {
+      int w = 0;
+      while (i >= p.wide_begin[w + 1]) ++w;
+      // the w-th wide segment
+      int s = 0, seen = -1;
+#pragma unroll 1
+      for (; s < p.n_segments; ++s) {
+        if (p.seg[s].wide && ++seen == w) break;
+      }
+      const xa_grad_segment_t& sg = p.seg[s];
+      j = sg.dest_begin + (i - p.wide_begin[w]);
+      const int32_t m = p.map[j];
+      if (m >= 0) {
+        const int per = (sg.splits + 3) / 4;
+        const int k0 = part * per, k1 = k0 + per < sg.splits ? k0 + per : sg.splits;
+        const float* src = p.src + m;
+        for (int k = k0; k < k1; ++k) acc += src[k * sg.split_stride];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0 && j >= 0) p.grad[j] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int xa_grad_finalize_f32(const float* src, const int32_t* map, const xa_grad_segment_t* segments, int n_segments, float* grad,
+                                    int64_t n, xa_stream_t stream) {
+  const char* what = "xa_grad_finalize_f32";
+  XA_REQUIRE(src && map && segments && grad, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(n > 0 && n_segments > 0 && n_segments <= XA_MAX_GRAD_SEGMENTS, XA_EINVAL, "%s: n=%lld n_segments=%d (at most %d)", what,
+             static_cast<long long>(n), n_segments, XA_MAX_GRAD_SEGMENTS);
+  FinalizeParams p{};
+  p.src = src, p.map = map, p.grad = grad, p.n = n, p.n_segments = n_segments;
+  int64_t wide = 0, narrow = 0;
+  int n_wide = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    const xa_grad_segment_t& sg = segments[s];   // host memory
+    const int64_t end = s + 1 < n_segments ? segments[s + 1].dest_begin : n;
+    XA_REQUIRE(sg.dest_begin >= 0 && sg.dest_begin <= end && (s > 0 || sg.dest_begin == 0) && sg.splits >= 1 && sg.split_stride >= 0, XA_EINVAL,
+               "%s: segment %d (dest_begin=%lld splits=%d) out of order or empty", what, s, static_cast<long long>(sg.dest_begin), sg.splits);
+    p.seg[s] = sg;
+    if (sg.wide) {
+      p.wide_begin[n_wide++] = wide;
+      wide += end - sg.dest_begin;
+    } else {
+      narrow += end - sg.dest_begin;
+    }
+  }
+  p.wide_begin[n_wide] = wide;
+  for (int w = n_wide + 1; w <= XA_MAX_GRAD_SEGMENTS; ++w) p.wide_begin[w] = INT64_MAX;
+  p.wide_total = wide;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  int64_t nb = (n + kThreads - 1) / kThreads;
+  if (nb > 8 * sms) nb = 8 * sms;
+  int64_t wb = (wide * 4 + kThreads - 1) / kThreads;
+  if (wb > 16 * sms) wb = 16 * sms;
+  (void)narrow;
+  grad_finalize_kernel<<<static_cast<unsigned>(nb + wb), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<int>(nb));
+  return xa::check_launch(what);
+}

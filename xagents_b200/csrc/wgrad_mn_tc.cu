@@ -235,10 +235,22 @@ int64_t xa_conv_wgrad_nhwc_workspace_bytes(int n_out, int channels, int kh, int 
   return static_cast<int64_t>(sms) * n_out * (kh * kw * channels + 8) * static_cast<int64_t>(sizeof(float));
 }
 
-int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float* db, int n_out, int channels, int kh, int kw,
-                            int grid_w, int64_t q_total, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
-  const char* what = "xa_conv_wgrad_nhwc_bf16";
-  XA_REQUIRE(x && dy_grid && dw && workspace, XA_EINVAL, "%s: null pointer", what);
+int xa_conv_wgrad_nhwc_plan(int n_out, int channels, int kh, int kw, int64_t q_total, int* splits, int* ld_partial) {
+  const char* what = "xa_conv_wgrad_nhwc_plan";
+  XA_REQUIRE(n_out > 0 && channels > 0 && kh > 0 && kw > 0 && q_total > 0, XA_EINVAL, "%s: non-positive size", what);
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t k_blocks = (q_total + kBlockK - 1) / kBlockK;
+  int s = static_cast<int>(k_blocks < sms ? k_blocks : sms);
+  const int64_t per = (k_blocks + s - 1) / s;
+  s = static_cast<int>((k_blocks + per - 1) / per);
+  if (splits) *splits = s;
+  if (ld_partial) *ld_partial = kh * kw * channels + 8;
+  return XA_OK;
+}
+
+static int wgrad_run(const char* what, const void* x, const void* dy_grid, float* dw, float* db, int n_out, int channels, int kh, int kw,
+                     int grid_w, int64_t q_total, void* workspace, int64_t workspace_bytes, bool reduce, xa_stream_t stream) {
+  XA_REQUIRE(x && dy_grid && (dw || !reduce) && workspace, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE((n_out == 32 || n_out == 64) && channels > 0 && channels % 64 == 0 && kh > 0 && kw > 0 && kw <= 8 && grid_w >= kw, XA_EINVAL,
              "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
   const int cg = channels / 64;
@@ -247,29 +259,42 @@ int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float
   XA_REQUIRE(n_groups <= kMaxGroups && n_mblocks * n_out <= 512, XA_EINVAL, "%s: %d taps x %d channels exceed the TMEM accumulator", what,
              kh * kw, channels);
   XA_REQUIRE(q_total > 0 && q_total < (int64_t(1) << 31) - 4096, XA_EOVERFLOW, "%s: q_total out of range", what);
-  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(dy_grid, 16) && xa::aligned(dw, 16) && xa::aligned(workspace, 16), XA_EALIGN,
+  XA_REQUIRE(xa::aligned(x, 16) && xa::aligned(dy_grid, 16) && (!reduce || xa::aligned(dw, 16)) && xa::aligned(workspace, 16), XA_EALIGN,
              "%s: 16-byte alignment required", what);
   XA_REQUIRE(workspace_bytes >= xa_conv_wgrad_nhwc_workspace_bytes(n_out, channels, kh, kw), XA_ENOSPACE, "%s: workspace too small", what);
-  const int mode = wgrad_mode();  // 0: one box per kernel row, taps by descriptor shift; 2: one box per tap
+  // 0: ONE window per 64-channel block (64 + (kh-1)*W + (kw-1) pixel rows), every tap a descriptor shifted by whole rows --
+  //    each input pixel crosses L2 -> shared memory once per K block (these kernels were bound by that traffic, ~8 TB/s
+  //    chip-wide, when every kernel row had its own box); 1: one box per kernel row; 2: one box per tap
+  const int mode = wgrad_mode();
   WgradMnParams p{};
   p.partial = static_cast<float*>(workspace);
   p.n_out = n_out, p.n_groups = n_groups;
   p.ld_p = kh * kw * channels + 8;
   const bool per_tap = mode == 2;
-  p.box_rows = per_tap ? 64 : 64 + ((kw - 1 + 7) / 8) * 8;
+  const int window_rows = ((64 + (kh - 1) * grid_w + (kw - 1) + 7) / 8) * 8;
+  const bool window = mode == 0 && window_rows <= 256;
+  p.box_rows = per_tap ? 64 : window ? window_rows : 64 + ((kw - 1 + 7) / 8) * 8;
   const int box_bytes = p.box_rows * 128;
   int nb = 0, ng = 0;
-  for (int i = 0; i < kh; ++i) {
-    for (int g = 0; g < cg; ++g) {
-      if (per_tap) {
-        for (int j = 0; j < kw; ++j, ++nb, ++ng) {
-          p.box_shift[nb] = i * grid_w + j, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
-          p.group_off[ng] = p.box_off[nb], p.group_col[ng] = (i * kw + j) * channels + g * 64;
+  if (window) {
+    for (int g = 0; g < cg; ++g, ++nb) p.box_shift[nb] = 0, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
+    for (int i = 0; i < kh; ++i)
+      for (int g = 0; g < cg; ++g)
+        for (int j = 0; j < kw; ++j, ++ng)
+          p.group_off[ng] = p.box_off[g] + (i * grid_w + j) * 128, p.group_col[ng] = (i * kw + j) * channels + g * 64;
+  } else {
+    for (int i = 0; i < kh; ++i) {
+      for (int g = 0; g < cg; ++g) {
+        if (per_tap) {
+          for (int j = 0; j < kw; ++j, ++nb, ++ng) {
+            p.box_shift[nb] = i * grid_w + j, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
+            p.group_off[ng] = p.box_off[nb], p.group_col[ng] = (i * kw + j) * channels + g * 64;
+          }
+        } else {
+          p.box_shift[nb] = i * grid_w, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
+          for (int j = 0; j < kw; ++j, ++ng) p.group_off[ng] = p.box_off[nb] + j * 128, p.group_col[ng] = (i * kw + j) * channels + g * 64;
+          ++nb;
         }
-      } else {
-        p.box_shift[nb] = i * grid_w, p.box_col[nb] = g * 64, p.box_off[nb] = nb * box_bytes;
-        for (int j = 0; j < kw; ++j, ++ng) p.group_off[ng] = p.box_off[nb] + j * 128, p.group_col[ng] = (i * kw + j) * channels + g * 64;
-        ++nb;
       }
     }
   }
@@ -306,12 +331,24 @@ int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float
     default:
       xa::set_error("%s: %d accumulator blocks", what, n_mblocks);
   }
-  if (rc) return rc;
+  if (rc || !reduce) return rc;
   const int ld_out = kh * kw * channels;
   const int64_t total = static_cast<int64_t>(n_out) * (ld_out + 1);
   wgrad_mn_reduce_kernel<<<static_cast<unsigned>((total * 4 + 255) / 256), 256, 0, s>>>(static_cast<const float*>(workspace), dw, db, n_out, ld_out,
                                                                                      p.ld_p, splits);
   return xa::check_launch(what);
+}
+
+int xa_conv_wgrad_nhwc_bf16(const void* x, const void* dy_grid, float* dw, float* db, int n_out, int channels, int kh, int kw,
+                            int grid_w, int64_t q_total, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
+  return wgrad_run("xa_conv_wgrad_nhwc_bf16", x, dy_grid, dw, db, n_out, channels, kh, kw, grid_w, q_total, workspace, workspace_bytes, true,
+                   stream);
+}
+
+int xa_conv_wgrad_nhwc_bf16_partial(const void* x, const void* dy_grid, int n_out, int channels, int kh, int kw, int grid_w, int64_t q_total,
+                                    float* partial, int64_t partial_bytes, xa_stream_t stream) {
+  return wgrad_run("xa_conv_wgrad_nhwc_bf16_partial", x, dy_grid, nullptr, nullptr, n_out, channels, kh, kw, grid_w, q_total, partial,
+                   partial_bytes, false, stream);
 }
 
 }  // extern "C"
