@@ -251,6 +251,17 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
                            const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w, int flags,
                            xa_stream_t stream);
 
+/* The first (4x4-strided) layer straight from the uint8 frames: cast + /255 (xagents/base.py:505-506), space-to-depth and the
+ * convolution in one kernel -- raw uint8 windows arrive by TMA, converter warps write the bf16 SWIZZLE_128B operand tiles
+ * the tensor core reads, so the bf16 space-to-depth tensor (2x the frames' bytes) never exists in HBM.  frames
+ * [B, height, width, 4] uint8; a kh x kw stride-1 kernel over the 4x4 space-to-depth grid (the 8x8/4 layer: kh = kw = 2);
+ * w [n_out, kh*kw*64] bf16, K ordered (kh, kw, dy, dx, c); y as xa_conv2d_nhwc_bf16.  x_s2d_out (may be NULL): the converted
+ * tiles are also stored as the bf16 [B, height/4, width/4, 64] space-to-depth tensor (what xa_conv_wgrad_nhwc_bf16 reads
+ * in the backward pass), from shared memory, without a second pass over the frames.  Results are bit-identical to
+ * xa_space_to_depth_u8_bf16 followed by xa_conv2d_nhwc_bf16. */
+int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch,
+                          int height, int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream);
+
 /* uint8 NHWC frames -> bf16 (optionally /255, xagents/base.py:505-506) rearranged block x block -> channels:
  * dst[b, y/s, x/s, (y%s, x%s, c)]. */
 int xa_space_to_depth_u8_bf16(const uint8_t* src, void* dst, int batch, int height, int width, int channels,
@@ -314,9 +325,11 @@ int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const vo
                            xa_stream_t stream);
 
 /* tape.gradient's results into the flat gradient buffer of the optimiser step (xagents/ppo/agent.py:134-137):
- * grad[j] = sum_{s < splits} src[map[j] + s*split_stride] (0 where map[j] < 0) with splits / split_stride constant over
- * segments of consecutive j (segment i covers [dest_begin_i, dest_begin_{i+1}); the first starts at 0, the last ends at
- * n).  `wide` segments (many splits) are summed by four lanes per output.  segments: HOST array. */
+ * grad[dest[j]] = sum_{s < splits} src[map[j] + s*split_stride] (0 where map[j] < 0; dest = NULL: grad[j]) with splits /
+ * split_stride constant over segments of consecutive j (segment i covers [dest_begin_i, dest_begin_{i+1}); the first
+ * starts at 0, the last ends at n).  Enumerate each segment in the order of its sources (map ascending) so that the
+ * partial sums are read coalesced.  `wide` segments (many splits) are summed by four lanes per output.
+ * segments: HOST array. */
 #define XA_MAX_GRAD_SEGMENTS 16
 typedef struct xa_grad_segment_t {
   int64_t dest_begin;
@@ -324,8 +337,8 @@ typedef struct xa_grad_segment_t {
   int32_t splits;
   int32_t wide;
 } xa_grad_segment_t;
-int xa_grad_finalize_f32(const float* src, const int32_t* map, const xa_grad_segment_t* segments, int n_segments,
-                         float* grad, int64_t n, xa_stream_t stream);
+int xa_grad_finalize_f32(const float* src, const int32_t* map, const int32_t* dest, const xa_grad_segment_t* segments,
+                         int n_segments, float* grad, int64_t n, xa_stream_t stream);
 
 /* The documented PPO/A2C network (README.md:243-259; ppo/models/cnn-actor-critic.cfg) as two calls: every launch of the
  * forward / backward pass issued from native code over buffers the caller owns (HOST struct of device pointers).
@@ -349,7 +362,8 @@ typedef struct xa_nature_cnn_t {
   float* scratch;
   int64_t scratch_floats;
   int64_t off_c1, off_c2, off_c3, off_fc, off_heads; /* float offsets into scratch */
-  const int32_t* grad_map;
+  const int32_t* grad_map;  /* source offset of enumeration index j ... */
+  const int32_t* grad_dest; /* ... and its place in flat_grad */
   xa_grad_segment_t segments[XA_MAX_GRAD_SEGMENTS];
   int32_t n_segments, reserved;
   int64_t n_grad;

@@ -110,3 +110,9 @@ def plan_step_s2d():
 t_plan_s2d = timeit(plan_step_s2d, 20)
 print(f'native plan at B={B}: forward+backward {t_plan:.0f} us ({fl / t_plan / 1e6:.0f} TFLOP/s), forward alone {t_fwd:.0f} us, '
       f'forward+backward from space-to-depth input (the fused gather\'s output) {t_plan_s2d:.0f} us')
+t_u8 = timeit(lambda: ops.conv2d_u8_s2d_bf16(x, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True), 20)
+print(f'first layer straight from uint8 frames at B={B}: {t_u8:.0f} us (space-to-depth {t0:.0f} + conv1 {t1:.0f} = {t0 + t1:.0f} us before); '
+      f'{B * (28224 + 400 * 32 * 2) / t_u8 / 1e3:.0f} GB/s of frames + output')
+x1_out = torch.empty((B, 21, 21, 64), dtype=torch.bfloat16, device=dev)
+t_u8s = timeit(lambda: ops.conv2d_u8_s2d_bf16(x, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True, x_s2d_out=x1_out), 20)
+print(f'... and also storing the bf16 space-to-depth tensor for the backward pass: {t_u8s:.0f} us')

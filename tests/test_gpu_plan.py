@@ -80,7 +80,7 @@ def test_grad_finalize_adds_splits_in_order_and_permutes():
     for s, (begin, stride, splits, wide) in zip(segs, ((0, 1000, 37, 1), (1000, 0, 1, 0), (6000, 300, 2, 0))):
         s.dest_begin, s.split_stride, s.splits, s.wide = begin, stride, splits, wide
     grad = torch.full((n,), float('nan'), device=DEV)
-    _call('xa_grad_finalize_f32', _p(src), _p(gmap), segs, 3, _p(grad), n, _s())
+    _call('xa_grad_finalize_f32', _p(src), _p(gmap), None, segs, 3, _p(grad), n, _s())
     a = src[:37000].view(37, 1000)[:, gmap[:1000].long()]
     # four lanes, each a contiguous quarter of the splits in order, then (q0 + q1) + (q2 + q3)
     quarters = []
@@ -94,6 +94,11 @@ def test_grad_finalize_adds_splits_in_order_and_permutes():
     b = src[42000:].view(2, 300)
     assert torch.equal(grad[6000:6300], b[0] + b[1])
     assert torch.equal(grad[6300:], torch.zeros(4, device=DEV))
+    # the same sums stored through a destination permutation
+    dest = torch.randperm(n, device=DEV).int()
+    out = torch.full((n,), float('nan'), device=DEV)
+    _call('xa_grad_finalize_f32', _p(src), _p(gmap), _p(dest), segs, 3, _p(out), n, _s())
+    assert torch.equal(out[dest.long()], grad)
 
 
 @pytest.mark.timeout(300)
@@ -172,3 +177,27 @@ def test_ppo_train_step_through_the_native_plan_matches_the_autograd_pipeline():
         losses.append(torch.stack(agent.loss_history).cpu().numpy())
     assert np.isfinite(losses[0]).all()
     np.testing.assert_allclose(losses[0][:4], losses[1][:4], rtol=5e-2, atol=5e-3)
+
+
+@pytest.mark.parametrize('B', [1, 3, 37, 256, 1000])
+@pytest.mark.parametrize('N,out_s2d', [(32, True), (32, False), (64, False)])
+def test_first_layer_from_uint8_frames_is_bit_identical_to_space_to_depth_then_convolution(B, N, out_s2d):
+    from xagents_b200 import ops
+    torch.manual_seed(B * 7 + N)
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    w = (torch.randn(N, 256, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV) * 0.1
+    want = ops.conv2d_nhwc_bf16(ops.space_to_depth_u8_bf16(x, 4), w, 2, 2, bias=bias, relu=True, out_s2d=out_s2d)
+    got = ops.conv2d_u8_s2d_bf16(x, w, 2, 2, bias=bias, relu=True, out_s2d=out_s2d)
+    x1 = torch.full((B, 21, 21, 64), float('nan'), dtype=torch.bfloat16, device=DEV)
+    got2 = ops.conv2d_u8_s2d_bf16(x, w, 2, 2, bias=bias, relu=True, out_s2d=out_s2d, x_s2d_out=x1)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16)) and torch.equal(got2.view(torch.int16), want.view(torch.int16))
+    assert torch.equal(x1.view(torch.int16), ops.space_to_depth_u8_bf16(x, 4).view(torch.int16)), 'the stored space-to-depth tensor'
+
+    # extreme byte values in every position of a window
+    for fill in (0, 255):
+        xf = torch.full_like(x[:2], fill)
+        assert torch.equal(ops.conv2d_u8_s2d_bf16(xf, w, 2, 2, bias=bias, relu=False).view(torch.int16),
+                           ops.conv2d_nhwc_bf16(ops.space_to_depth_u8_bf16(xf, 4), w, 2, 2, bias=bias, relu=False).view(torch.int16))

@@ -73,7 +73,7 @@ class NatureCnn(ctypes.Structure):
                                                       'x1', 'x2', 'x3', 'y3', 'h', 'actor', 'critic', 'dh', 'g3', 'g2', 'g1', 'gemm_ws')] +
                 [('gemm_ws_bytes', ctypes.c_int64), ('scratch', ctypes.c_void_p), ('scratch_floats', ctypes.c_int64)] +
                 [(name, ctypes.c_int64) for name in ('off_c1', 'off_c2', 'off_c3', 'off_fc', 'off_heads')] +
-                [('grad_map', ctypes.c_void_p), ('segments', GradSegment * XA_MAX_GRAD_SEGMENTS), ('n_segments', ctypes.c_int32),
+                [('grad_map', ctypes.c_void_p), ('grad_dest', ctypes.c_void_p), ('segments', GradSegment * XA_MAX_GRAD_SEGMENTS), ('n_segments', ctypes.c_int32),
                  ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64)])
 
 
@@ -125,6 +125,7 @@ PROTOTYPES = {
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_conv2d_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                             [ctypes.c_void_p, c_stream]),
+    'xa_conv2d_u8_s2d_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 8 + [c_stream]),
     'xa_space_to_depth_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [c_stream]),
     'xa_conv_wgrad_nhwc_workspace_bytes': (ctypes.c_int64, [ctypes.c_int] * 4),
     'xa_conv_wgrad_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_stream]),
@@ -135,7 +136,7 @@ PROTOTYPES = {
     'xa_heads_backward_blocks': (ctypes.c_int, [ctypes.c_int]),
     'xa_heads_forward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [c_stream]),
     'xa_heads_backward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 3 + [c_stream]),
-    'xa_grad_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GradSegment), ctypes.c_int, ctypes.c_void_p,
+    'xa_grad_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GradSegment), ctypes.c_int, ctypes.c_void_p,
                                             ctypes.c_int64, c_stream]),
     'xa_nature_cnn_forward': (ctypes.c_int, [ctypes.POINTER(NatureCnn), ctypes.c_void_p, ctypes.c_int, c_stream]),
     'xa_nature_cnn_backward': (ctypes.c_int, [ctypes.POINTER(NatureCnn)] + [ctypes.c_void_p] * 4 + [c_stream]),

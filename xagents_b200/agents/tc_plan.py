@@ -3,7 +3,7 @@
 `NaturePlan` owns, for one batch size, every activation and gradient tensor of the tensor-core network, the fp32 scratch its
 split partial sums land in, and the index map + segment table of `xa_grad_finalize_f32`, the last launch of the backward
 pass, which adds the partials and writes every parameter gradient at its place in the model's flat gradient buffer (torch
-layouts) -- so one train-step minibatch is `forward()` (6 launches), the loss kernel, `backward()` (9 launches) and the fused
+layouts) -- so one train-step minibatch is `forward()` (6 launches: the first layer reads the uint8 frames directly), the loss kernel, `backward()` (9 launches) and the fused
 clip + Adam (xagents/ppo/agent.py:112-137: model call, tape.gradient, clip_by_global_norm, apply_gradients).
 
 The autograd form of the same pipeline (agents/tc_cnn.py `_NatureCnnFn`) stays as the checker: tests compare the two.
@@ -101,11 +101,23 @@ class NaturePlan:
         put(lay32['bh'], heads_off + (HEAD_ROWS + 1) * HIDDEN + ar(rows))
         assert bool((gmap[:n_params] >= 0).all()), 'a parameter has no gradient source'
         assert int(gmap.max()) < 2 ** 31
-        self.grad_map = gmap.to(torch.int32)
-        net.grad_map, net.n_grad = self.grad_map.data_ptr(), n_grad
+        # enumerate every parameter's elements in SOURCE order (coalesced reads of the partial sums; the one result per
+        # element is the scattered store): (grad_map[j], grad_dest[j]) = (source offset, index in flat_grad)
+        order = sorted(named, key=lambda name: offsets[name])
+        dest = torch.arange(n_grad, dtype=torch.int64, device=dev)
+        for i, name in enumerate(order):
+            lo = offsets[name]
+            hi = offsets[order[i + 1]] if i + 1 < len(order) else n_grad
+            assert hi >= lo + named[name].numel(), 'parameters overlap in the flat buffer'
+            key = gmap[lo:hi].clone()
+            key[key < 0] = 2 ** 40                                   # padding (no source) last
+            perm = torch.argsort(key, stable=True)
+            dest[lo:hi] = lo + perm
+        self.grad_map = gmap[dest].to(torch.int32)
+        self.grad_dest = dest.to(torch.int32)
+        net.grad_map, net.grad_dest, net.n_grad = self.grad_map.data_ptr(), self.grad_dest.data_ptr(), n_grad
 
         seg_of = dict(c1w=('c1',), c1b=('c1',), c2w=('c2',), c2b=('c2',), c3w=('c3',), c3b=('c3',))
-        order = sorted(named, key=lambda name: offsets[name])
         assert len(order) <= _ffi.XA_MAX_GRAD_SEGMENTS
         for i, name in enumerate(order):
             seg = net.segments[i]
@@ -134,17 +146,17 @@ class NaturePlan:
             self._x1_in = frames
         else:
             assert frames.dtype == torch.uint8 and tuple(frames.shape[1:]) == (84, 84, 4)
-            if self.x1 is None:
+            if self.x1 is None and self.has_backward:           # the first layer reads the frames; only the backward needs x1
                 self.x1 = torch.empty((self.batch, 21, 21, 64), dtype=torch.bfloat16, device=self.device)
                 self.net.x1 = self.x1.data_ptr()
             self._x1_in = self.x1
         self._launch(self._fwd, 'xa_nature_cnn_forward', ctypes.byref(self.net), ctypes.c_void_p(frames.data_ptr()), int(s2d), self._stream(stream))
-        ops._count(6 if s2d else 7)
+        ops._count(6)
         return self.actor, self.critic
 
     def backward(self, d_actor, d_critic, flat_grad, stream=None):
         """Output gradients (fp32, from the loss kernel) -> every element of `flat_grad` (the model's flat gradient buffer)."""
-        assert self.has_backward and self._x1_in is not None, 'forward() first, on a plan built with backward=True'
+        assert self.has_backward and self._x1_in is not None, 'forward() first, on a plan built with a flat parameter buffer'
         assert d_actor.dtype == torch.float32 and d_actor.is_contiguous() and d_actor.numel() == self.batch * self.pack.n_actions
         assert d_critic.dtype == torch.float32 and d_critic.is_contiguous() and d_critic.numel() == self.batch
         assert flat_grad.dtype == torch.float32 and flat_grad.numel() >= self.net.n_grad

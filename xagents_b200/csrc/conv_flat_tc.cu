@@ -21,6 +21,9 @@ namespace {
 using namespace xa_tc;
 
 constexpr int kFlatThreads = 64 + 8 * 32;
+constexpr int kConvertWarps = 5;                              // uint8 input: five more warps turn raw windows into bf16 operand tiles
+constexpr int kFlatThreadsU8 = kFlatThreads + kConvertWarps * 32;
+constexpr int kRawStages = 4;
 
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 v;
@@ -56,24 +59,37 @@ struct FlatParams {
   int stages;
   int64_t Q;       // B*H*W
   uint32_t w_bytes, stage_bytes;
+  uint32_t raw_stage_bytes, raw_tx_bytes;  // uint8 input: bytes of one raw window stage / of one TMA box
+  uint32_t div_w_magic;                    // (g * div_w_magic) >> 16 == g / W for every pixel index g inside a raw box
+  int store_x1;                            // uint8 input: also write the converted bf16 rows to HBM through map_x1
   uint32_t a_units[kMaxEntries];  // (byte offset of the entry's A operand inside a stage) >> 4
   uint32_t b_units[kMaxEntries];  // (byte offset of the entry's weight tile) >> 4
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_constant__ CUtensorMap map_x,
+// kU8: the input is the raw uint8 frame tensor [B, 4H, 4W, 4] of a 4x4-strided first layer (space-to-depth grid H x W, 64
+// "channels" = (dy, dx, c)).  map_x then covers the frames as image rows ([B*4H rows, 16 W bytes]); a box of 4 nY whole image
+// rows = nY grid rows arrives as they lie in memory (long TMA rows: a box shaped [pixel][dy][16 B] would be fetched in
+// 16-byte requests), and five converter warps pick the 16-byte (dx, c) pieces of every (pixel, dy), scale by 1/255, round
+// to bf16 and write the SWIZZLE_128B operand tile the MMA reads -- the 2x larger bf16 space-to-depth tensor is never written to or read from HBM (xagents/base.py:505-506: the
+// cast and the division of the image batch, fused here into the first layer).
+template <int BN, bool kU8 = false>
+__global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                  const __grid_constant__ CUtensorMap map_w,
+                                                                 const __grid_constant__ CUtensorMap map_x1,
                                                                  const __grid_constant__ FlatParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem + p.w_bytes;  // weights first, then the ring of window stages
-  uint8_t* tail = ring + static_cast<size_t>(p.stages) * p.stage_bytes;
+  uint8_t* raw_ring = ring + static_cast<size_t>(p.stages) * p.stage_bytes;  // kU8 only
+  uint8_t* tail = raw_ring + (kU8 ? static_cast<size_t>(kRawStages) * p.raw_stage_bytes : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + 8;
   uint64_t* acc_full = empty + 8;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* raw_full = w_full + 1;             // [kRawStages]
+  uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
   uint32_t* s_a = reinterpret_cast<uint32_t*>(tail + 256);  // [kMaxEntries]
   uint32_t* s_b = s_a + kMaxEntries;
   float* s_bias = reinterpret_cast<float*>(tail + 256 + 2 * kMaxEntries * 4);  // [N <= 128]
@@ -81,8 +97,8 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.N; i += kFlatThreads) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
-  for (int i = threadIdx.x; i < p.n_entries; i += kFlatThreads) s_a[i] = p.a_units[i], s_b[i] = p.b_units[i];
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < p.n_entries; i += blockDim.x) s_a[i] = p.a_units[i], s_b[i] = p.b_units[i];
   const int n_tiles = static_cast<int>((p.Q + kBlockM - 1) / kBlockM);
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
   constexpr uint32_t kTmemCols = 2 * kAccStride;
@@ -91,7 +107,7 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) {
-      xa::mbar_init(full + s, 1);
+      xa::mbar_init(full + s, kU8 ? kConvertWarps : 1);  // filled by TMA, or by one arrival per converter warp
       xa::mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -99,6 +115,12 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
       xa::mbar_init(acc_empty + a, 4);
     }
     xa::mbar_init(w_full, 1);
+    if (kU8) {
+      for (int s = 0; s < kRawStages; ++s) {
+        xa::mbar_init(raw_full + s, 1);
+        xa::mbar_init(raw_empty + s, kConvertWarps);
+      }
+    }
     xa::fence_barrier_init();
   }
   if (warp == 1) {
@@ -118,13 +140,22 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
       int s = 0;
       uint32_t round = 0;
       const uint32_t blk_bytes = static_cast<uint32_t>(p.win_rows) * 128u;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
-        uint8_t* dst = ring + static_cast<size_t>(s) * p.stage_bytes;
-        xa::mbar_expect_tx(full + s, p.stage_bytes);
-        const int q0 = tile * kBlockM + p.min_shift;  // may be negative: rows before the tensor read as zeros
-        for (int c = 0; c < p.kc_blocks; ++c) tma_load_2d(dst + c * blk_bytes, &map_x, c * kBlockK, q0, full + s);
-        if (++s == p.stages) s = 0, ++round;
+      if (kU8) {  // raw uint8 windows: the nY whole grid rows that contain pixels [q0, q0 + win_rows)
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          if (round > 0) mbar_wait_wd(raw_empty + s, (round - 1) & 1);
+          xa::mbar_expect_tx(raw_full + s, p.raw_tx_bytes);
+          tma_load_2d(raw_ring + static_cast<size_t>(s) * p.raw_stage_bytes, &map_x, 0, 4 * ((tile * kBlockM) / p.W), raw_full + s);
+          if (++s == kRawStages) s = 0, ++round;
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
+          uint8_t* dst = ring + static_cast<size_t>(s) * p.stage_bytes;
+          xa::mbar_expect_tx(full + s, p.stage_bytes);
+          const int q0 = tile * kBlockM + p.min_shift;  // may be negative: rows before the tensor read as zeros
+          for (int c = 0; c < p.kc_blocks; ++c) tma_load_2d(dst + c * blk_bytes, &map_x, c * kBlockK, q0, full + s);
+          if (++s == p.stages) s = 0, ++round;
+        }
       }
     }
   } else if (warp == 1) {
@@ -157,6 +188,81 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
         if (++s == p.stages) s = 0, phase ^= 1;
       }
     }
+  } else if (kU8 && warp >= 10) {
+    // ---- converters (uint8 input): raw window stage -> bf16 operand stage.  A thread owns one window pixel: its four
+    // 16-byte pieces (the (dx, c) bytes of dy = 0..3, one image row apart) become the eight 16-byte chunks of the pixel's
+    // 128-byte operand row, stored where SWIZZLE_128B puts them (chunk ^ (row & 7): stage bases are 1024-byte aligned, so
+    // the row index supplies address bits 7-9).  Consecutive threads take consecutive pixels: reads walk an image row, the
+    // stores of 8 threads hit 8 different chunks.  The kernel is bound by instruction issue (ncu: 4600 warp instructions
+    // per tile before this layout, 58 % of all issue slots), so the address arithmetic is done once per pixel, not per piece.
+    // byte -> float without the (quarter-rate) integer conversion unit: PRMT builds 2^23 + x, one FMA does
+    // (2^23 + x) * m - 2^23 * m = fl(x * m) with m = fl(1/255) -- the product the space-to-depth kernel rounds to bf16
+    // (bit-identical to x / 255 for every byte value, tests/test_gpu_conv.py).
+    // Warp w converts window rows [32 w, 32 w + 32).  With store_x1 the tile's own 128 rows (warps 0-3) also go to HBM as the
+    // [Q, 64] bf16 space-to-depth tensor the weight-gradient kernel reads in the backward pass: each warp's elected lane
+    // TMA-stores its 32 rows from the operand stage (SWIZZLE_128B undone by the store's tensor map) and, before writing
+    // that stage again, waits until the store has read it.
+    const int cw = warp - 10;
+    const float mul = 1.0f / 255.0f, bias23 = -8388608.0f * mul;
+    const uint32_t ring_u32 = xa::smem_u32(ring), raw_u32 = xa::smem_u32(raw_ring);
+    const uint32_t dy_pitch = static_cast<uint32_t>(p.W) * 16u;  // one image row
+    const bool storing = p.store_x1 != 0 && cw < kBlockM / 32;
+    int rs = 0, bs = 0;
+    uint32_t raw_phase = 0, b_round = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int q0 = tile * kBlockM;
+      const int w0 = q0 - (q0 / p.W) * p.W;  // first window pixel inside the first grid row of the box
+      mbar_wait_backoff(raw_full + rs, raw_phase);
+      if (b_round > 0) mbar_wait_backoff(empty + bs, (b_round - 1) & 1);
+      if (storing) {  // at most the two most recent of my stores may still be reading their stages (stages >= 3)
+        if (lane == 0) xa::bulk_wait_read<2>();
+        __syncwarp();
+      }
+      const uint32_t src0 = raw_u32 + static_cast<uint32_t>(rs) * p.raw_stage_bytes;
+      const uint32_t dst0 = ring_u32 + static_cast<uint32_t>(bs) * p.stage_bytes;
+#pragma unroll 1
+      for (int row = cw * 32 + lane; row < p.win_rows; row += kConvertWarps * 32) {
+        const uint32_t g = static_cast<uint32_t>(w0 + row);
+        const uint32_t gy = (g * p.div_w_magic) >> 16, gx = g - gy * p.W;
+        const uint32_t src = src0 + (gy * 4u * p.W + gx) * 16u;
+        uint4 in[4];
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) in[dy] = lds_u4(src + dy * dy_pitch);
+        const uint32_t row_u32 = dst0 + static_cast<uint32_t>(row) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          const uint32_t words[4] = {in[dy].x, in[dy].y, in[dy].z, in[dy].w};
+          __nv_bfloat162 out[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float f0 = fmaf(__uint_as_float(__byte_perm(words[k], 0x4B000000u, 0x7650)), mul, bias23);
+            const float f1 = fmaf(__uint_as_float(__byte_perm(words[k], 0x4B000000u, 0x7651)), mul, bias23);
+            const float f2 = fmaf(__uint_as_float(__byte_perm(words[k], 0x4B000000u, 0x7652)), mul, bias23);
+            const float f3 = fmaf(__uint_as_float(__byte_perm(words[k], 0x4B000000u, 0x7653)), mul, bias23);
+            out[2 * k] = __floats2bfloat162_rn(f0, f1);
+            out[2 * k + 1] = __floats2bfloat162_rn(f2, f3);
+          }
+          sts_u4(row_u32 + ((32u * dy) ^ sw), *reinterpret_cast<uint4*>(out));
+          sts_u4(row_u32 + ((32u * dy + 16u) ^ sw), *reinterpret_cast<uint4*>(out + 4));
+        }
+      }
+      xa::fence_proxy_async();  // generic-proxy stores -> visible to the async proxy (tensor core, TMA store)
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(full + bs)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(raw_empty + rs)) : "memory");
+        if (storing) {  // rows past the end of the tensor are clipped by the tensor map
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_x1), "r"(0),
+                       "r"(q0 + cw * 32), "r"(dst0 + static_cast<uint32_t>(cw) * 4096u)
+                       : "memory");
+          xa::bulk_commit();
+        }
+      }
+      if (++rs == kRawStages) rs = 0, raw_phase ^= 1;
+      if (++bs == p.stages) bs = 0, ++b_round;
+    }
+    if (storing && lane == 0) xa::bulk_wait_all<0>();  // shared memory must outlive the stores
   } else {
     // ---- epilogue: group `grp` (warps 2-5 / 6-9) owns accumulator `grp` = the CTA's tiles of that parity.
     // tcgen05.ld hands every thread one ROW (32 consecutive columns): stored directly, a warp-wide 16-byte access touches
@@ -187,16 +293,21 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
       col_delta = ((sub >> 1) * p.PW + (sub & 1)) * kN4 + (col_delta - sub * kN4);
     }
     const uint32_t my_piece_u32 = my_stage_u32 + row0 * kPitch + piece * 16;
-    for (uint32_t lt = grp;; lt += 2) {
+    // my row's pixel (image ob, position rem inside it) advances by a constant from one of this group's tiles to the next:
+    // two divisions here instead of three per tile (the epilogue's instruction count is what these short-K layers wait for)
+    const uint32_t step_px = 2u * gridDim.x * kBlockM, step_b = step_px / hw, step_rem = step_px - step_b * hw;
+    int64_t q = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x) * kBlockM + r;
+    uint32_t ob_u = static_cast<uint32_t>(q / hw), rem = static_cast<uint32_t>(q - static_cast<int64_t>(ob_u) * hw);
+    for (uint32_t lt = grp;; lt += 2, q += step_px) {
       const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
       if (tile >= n_tiles) break;
       const uint32_t acc = grp;
       {  // phase 0: where does my row go?
-        const int64_t q = static_cast<int64_t>(tile) * kBlockM + r;
-        const uint32_t qq = static_cast<uint32_t>(q < p.Q ? q : 0);
-        const int ob = static_cast<int>(qq / hw);
-        const uint32_t rem = qq - static_cast<uint32_t>(ob) * hw;
-        const int oy = static_cast<int>(rem / p.W), ox = static_cast<int>(rem - (rem / p.W) * p.W);
+        const int ob = static_cast<int>(ob_u);
+        const uint32_t oy_u = p.div_w_magic != 0 ? (rem * p.div_w_magic) >> 16 : rem / p.W;
+        const int oy = static_cast<int>(oy_u), ox = static_cast<int>(rem - oy_u * p.W);
+        ob_u += step_b, rem += step_rem;
+        if (rem >= hw) rem -= hw, ++ob_u;
         const bool valid = q < p.Q && oy < p.OH && ox < p.OW;
         int64_t out_off = -1, mask_off = 0;
         if (valid) {
@@ -222,7 +333,7 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
             mraw[it] = __ldg(reinterpret_cast<const uint4*>(p.mask + lds_i64(row_msk_u32 + row * 8)) + piece);
         }
       }
-      mbar_wait_wd(acc_full + acc, (lt >> 1) & 1);
+      mbar_wait_backoff(acc_full + acc, (lt >> 1) & 1);  // polling eight warps took a sixth of the SM's issue slots (ncu)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float lo = p.relu ? 0.0f : -INFINITY;  // ReLU as one max per element, no per-element branch on the flag
 #pragma unroll
@@ -272,13 +383,14 @@ __global__ void __launch_bounds__(kFlatThreads) conv_flat_kernel(const __grid_co
   }
 }
 
-template <int BN>
-int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const FlatParams& p, size_t smem, cudaStream_t stream, const char* what) {
+template <int BN, bool kU8 = false>
+int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mx1, const FlatParams& p, size_t smem, cudaStream_t stream,
+                const char* what) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -287,7 +399,7 @@ int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const FlatParams& 
   }
   const int64_t tiles = (p.Q + kBlockM - 1) / kBlockM;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  conv_flat_kernel<BN><<<static_cast<unsigned>(tiles < sms ? tiles : sms), kFlatThreads, smem, stream>>>(mx, mw, p);
+  conv_flat_kernel<BN, kU8><<<static_cast<unsigned>(tiles < sms ? tiles : sms), kU8 ? kFlatThreadsU8 : kFlatThreads, smem, stream>>>(mx, mw, mx1, p);
   return xa::check_launch(what);
 }
 
@@ -324,6 +436,9 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   p.relu = relu, p.out_mode = out_mode;
   p.n_entries = n_entries, p.kc_blocks = kc_blocks, p.win_rows = win_rows, p.stages = stages, p.Q = Q;
   p.min_shift = -(pad_y * width + pad_x);
+  p.div_w_magic = (65536u + width - 1) / width;  // (rem * magic) >> 16 == rem / W for every pixel position of an image, else 0
+  for (uint32_t g = 0; g < static_cast<uint32_t>(height * width) && p.div_w_magic != 0; ++g)
+    if (g * static_cast<uint64_t>(p.div_w_magic) >= (uint64_t(1) << 32) || ((g * p.div_w_magic) >> 16) != g / width) p.div_w_magic = 0;
   int e = 0;
   for (int i = 0; i < kh; ++i)
     for (int j = 0; j < kw; ++j)
@@ -337,7 +452,79 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   if (int rc = make_map_2d(&mw, w, n_out, static_cast<int64_t>(kh) * kw * channels, n_out, what)) return rc;
   const size_t smem = 1024 + p.w_bytes + static_cast<size_t>(stages) * p.stage_bytes + 2048 + epi_bytes;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (n_out == 128) return launch_flat<128>(mx, mw, p, smem, s, what);
-  if (n_out == 64) return launch_flat<64>(mx, mw, p, smem, s, what);
-  return launch_flat<32>(mx, mw, p, smem, s, what);
+  if (n_out == 128) return launch_flat<128>(mx, mw, mx, p, smem, s, what);
+  if (n_out == 64) return launch_flat<64>(mx, mw, mx, p, smem, s, what);
+  return launch_flat<32>(mx, mw, mx, p, smem, s, what);
+}
+
+// First layer straight from the uint8 frames (see conv_flat_kernel's kU8 notes): frames [B, height, width, 4] uint8, a
+// kh x kw stride-1 kernel over the 4x4 space-to-depth grid (= a 4kh x 4kw / 4 convolution of the frames), w [n_out, kh*kw*64]
+// bf16 with K ordered (kh, kw, dy, dx, c), x/255 applied on the way in.
+extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height,
+                                     int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+  const char* what = "xa_conv2d_u8_s2d_bf16";
+  XA_REQUIRE(frames && w && y, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(batch > 0 && height > 0 && width > 0 && height % 4 == 0 && width % 4 == 0 && kh > 0 && kw > 0, XA_EINVAL,
+             "%s: batch=%d frames %dx%d kernel %dx%d", what, batch, height, width, kh, kw);
+  XA_REQUIRE(n_out == 32 || n_out == 64, XA_EINVAL, "%s: n_out=%d (32 or 64)", what, n_out);
+  XA_REQUIRE(xa::aligned(frames, 16) && xa::aligned(w, 16) && xa::aligned(y, 16) && xa::aligned(x_s2d_out, 16), XA_EALIGN,
+             "%s: 16-byte alignment required", what);
+  const int H = height / 4, W = width / 4;
+  const int OH = H - kh + 1, OW = W - kw + 1;
+  XA_REQUIRE(OH > 0 && OW > 0 && width <= 256 && (!out_s2d || (OH % 2 == 0 && OW % 2 == 0)), XA_EINVAL, "%s: output %dx%d", what, OH, OW);
+  const int n_entries = kh * kw;
+  const int win_rows = ((kBlockM + (kh - 1) * W + (kw - 1) + 7) / 8) * 8;
+  const int box_rows = (W - 1 + win_rows + W - 1) / W;  // whole grid rows that can hold a window starting anywhere in a row
+  XA_REQUIRE(n_entries <= kMaxEntries && win_rows <= 256 && 4 * box_rows <= 256, XA_EINVAL, "%s: kernel %dx%d on a %d-wide grid does not fit", what,
+             kh, kw, W);
+  const int64_t Q = static_cast<int64_t>(batch) * H * W;
+  XA_REQUIRE(Q < (int64_t(1) << 31) - 4096, XA_EOVERFLOW, "%s: batch too large", what);
+  FlatParams p{};
+  p.w_bytes = static_cast<uint32_t>(n_entries) * n_out * 128u;
+  p.stage_bytes = static_cast<uint32_t>(win_rows) * 128u;
+  p.raw_tx_bytes = static_cast<uint32_t>(box_rows) * W * 64u;
+  p.raw_stage_bytes = ((p.raw_tx_bytes + 1023u) / 1024u) * 1024u;
+  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 512);
+  const int64_t budget = 227 * 1024 - 1024 - 2048 - epi_bytes - p.w_bytes - static_cast<int64_t>(kRawStages) * p.raw_stage_bytes;
+  int stages = static_cast<int>(budget / p.stage_bytes);
+  XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: shared memory does not hold two operand stages", what);
+  if (stages > 6) stages = 6;
+  p.y = static_cast<__nv_bfloat16*>(y), p.bias = bias, p.mask = nullptr;
+  p.B = batch, p.H = H, p.W = W, p.N = n_out, p.OH = OH, p.OW = OW, p.PH = OH, p.PW = OW;
+  p.relu = relu, p.out_mode = out_s2d ? 1 : 0;
+  p.n_entries = n_entries, p.kc_blocks = 1, p.win_rows = win_rows, p.stages = stages, p.Q = Q, p.min_shift = 0;
+  int e = 0;
+  for (int i = 0; i < kh; ++i)
+    for (int j = 0; j < kw; ++j, ++e) {
+      p.a_units[e] = (static_cast<uint32_t>(i * W + j) * 128u) >> 4;
+      p.b_units[e] = (static_cast<uint32_t>(e) * n_out * 128u) >> 4;
+    }
+  p.div_w_magic = (65536u + W - 1) / W;
+  for (uint32_t g = 0; g < static_cast<uint32_t>((box_rows > H ? box_rows : H) * W); ++g)
+    XA_REQUIRE(((g * p.div_w_magic) >> 16) == g / W, XA_EINVAL, "%s: no 16-bit reciprocal for a grid %d wide", what, W);
+  CUtensorMap mx, mw;
+  {
+    EncodeTiledFn fn = encode_fn();
+    XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+    // the frames as image rows of 32-bit words: [batch * height rows, width words]; a box = 4 * box_rows whole rows
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(batch) * height};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * 4};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(width), static_cast<cuuint32_t>(4 * box_rows)};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult r = fn(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(frames), dims, strides, box, elem,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    XA_REQUIRE(r == CUDA_SUCCESS, XA_EINVAL, "%s: cuTensorMapEncodeTiled(frames) failed with %d", what, static_cast<int>(r));
+  }
+  if (int rc = make_map_2d(&mw, w, n_out, static_cast<int64_t>(kh) * kw * 64, n_out, what)) return rc;
+  CUtensorMap mx1 = mx;
+  p.store_x1 = x_s2d_out != nullptr;
+  if (p.store_x1) {
+    XA_REQUIRE(stages >= 3, XA_EINVAL, "%s: storing the space-to-depth tensor needs three operand stages", what);
+    if (int rc = make_map_2d_box(&mx1, x_s2d_out, Q, 64, 32, 64, what)) return rc;
+  }
+  const size_t smem = 1024 + p.w_bytes + static_cast<size_t>(stages) * p.stage_bytes + static_cast<size_t>(kRawStages) * p.raw_stage_bytes + 2048 +
+                      epi_bytes;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return n_out == 64 ? launch_flat<64, true>(mx, mw, mx1, p, smem, s, what) : launch_flat<32, true>(mx, mw, mx1, p, smem, s, what);
 }

@@ -2,11 +2,14 @@
 // partial sums, kernel-friendly layouts) to its place in the ONE flat fp32 gradient buffer the fused clip + Adam step reads
 // (tape.gradient -> clip_by_global_norm -> apply_gradients, xagents/ppo/agent.py:134-137).
 //
-//   grad[j] = sum over s < splits(j) of  src[map[j] + s * stride(j)]        (0 where map[j] < 0)
+//   grad[dest[j]] = sum over s < splits(j) of  src[map[j] + s * stride(j)]        (0 where map[j] < 0; dest = NULL: j itself)
 //
-// `map` is the permutation between the parameter layouts (torch / Keras order) and the kernels' operand layouts, built
-// once on the host from index tensors (agents/tc_plan.py); splits / stride are constant over a SEGMENT of consecutive j
-// (one segment per parameter tensor).  Splits are added in order with a fixed association, so the result is
+// (map, dest) is the permutation between the kernels' operand layouts and the parameter layouts (torch / Keras order),
+// built once on the host from index tensors (agents/tc_plan.py); splits / stride are constant over a SEGMENT of
+// consecutive j (one segment per parameter tensor).  The caller enumerates each segment in SOURCE order: the partial sums
+// are then read with consecutive lanes on consecutive addresses (148 splits x 47 MB in this network) and only the single
+// result per output is a scattered 4-byte store -- enumerated in destination order the same kernel took 57 us instead of
+// ~12, every 4-byte read pulling its own 32-byte sector.  Splits are added in order with a fixed association, so the result is
 // deterministic.  This one launch replaces three split reductions, four layout copies, two torch bias reductions, the
 // zero-fill of the gradient buffer and autograd's twelve accumulation kernels.
 #include "xa_common.cuh"
@@ -18,6 +21,7 @@ constexpr int kThreads = 256;
 struct FinalizeParams {
   const float* src;
   const int32_t* map;
+  const int32_t* dest;
   float* grad;
   int64_t n;
   int n_segments;
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_co
         const float* s = p.src + m;
         for (int k = 0; k < sg.splits; ++k) acc += s[k * sg.split_stride];
       }
-      p.grad[j] = acc;
+      p.grad[p.dest != nullptr ? p.dest[j] : j] = acc;
     }
     return;
   }
@@ -78,20 +82,20 @@ __global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_co
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (part == 0 && j >= 0) p.grad[j] = acc;
+    if (part == 0 && j >= 0) p.grad[p.dest != nullptr ? p.dest[j] : j] = acc;
   }
 }
 
 }  // namespace
 
-extern "C" int xa_grad_finalize_f32(const float* src, const int32_t* map, const xa_grad_segment_t* segments, int n_segments, float* grad,
-                                    int64_t n, xa_stream_t stream) {
+extern "C" int xa_grad_finalize_f32(const float* src, const int32_t* map, const int32_t* dest, const xa_grad_segment_t* segments,
+                                    int n_segments, float* grad, int64_t n, xa_stream_t stream) {
   const char* what = "xa_grad_finalize_f32";
   XA_REQUIRE(src && map && segments && grad, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(n > 0 && n_segments > 0 && n_segments <= XA_MAX_GRAD_SEGMENTS, XA_EINVAL, "%s: n=%lld n_segments=%d (at most %d)", what,
              static_cast<long long>(n), n_segments, XA_MAX_GRAD_SEGMENTS);
   FinalizeParams p{};
-  p.src = src, p.map = map, p.grad = grad, p.n = n, p.n_segments = n_segments;
+  p.src = src, p.map = map, p.dest = dest, p.grad = grad, p.n = n, p.n_segments = n_segments;
   int64_t wide = 0, narrow = 0;
   int n_wide = 0;
   for (int s = 0; s < n_segments; ++s) {

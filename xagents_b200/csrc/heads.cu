@@ -37,7 +37,13 @@ __global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_b
                                                                   const float* __restrict__ bh, float* __restrict__ actor,
                                                                   float* __restrict__ critic, int batch, int n_actions) {
   __shared__ float s_w[kRows][kHidden];
-  for (int i = threadIdx.x; i < kRows * kHidden; i += kFwdThreads) s_w[i / kHidden][i % kHidden] = __bfloat162float(wh[i]);
+  for (int i = threadIdx.x; i < kRows * kHidden / 8; i += kFwdThreads) {   // 512 16-byte pieces, two per thread, both in flight
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(wh) + i), f);
+    float4* dst = reinterpret_cast<float4*>(&s_w[0][0] + 8 * i);
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = gridDim.x * (kFwdThreads / 32);
@@ -202,7 +208,7 @@ int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float*
   XA_REQUIRE(xa::aligned(h, 16) && xa::aligned(wh, 16), XA_EALIGN, "%s: h and wh must be 16-byte aligned", what);
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int want = (batch + kFwdThreads / 32 - 1) / (kFwdThreads / 32);
-  const int grid = want < 4 * sms ? want : 4 * sms;
+  const int grid = want < 2 * sms ? want : 2 * sms;
   heads_forward_kernel<<<grid, kFwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h),
                                                                                    static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch,
                                                                                    n_actions);

@@ -24,14 +24,12 @@ static int check_net(const xa_nature_cnn_t* n, const char* what) {
 int xa_nature_cnn_forward(const xa_nature_cnn_t* n, const void* frames, int frames_s2d, xa_stream_t stream) {
   const char* what = "xa_nature_cnn_forward";
   XA_TRY(check_net(n, what));
-  XA_REQUIRE(frames != nullptr && (frames_s2d || n->x1), XA_EINVAL, "%s: null frames / x1", what);
+  XA_REQUIRE(frames != nullptr, XA_EINVAL, "%s: null frames", what);
   const int B = n->batch;
-  const void* x1 = frames;
-  if (!frames_s2d) {
-    XA_TRY(xa_space_to_depth_u8_bf16(static_cast<const uint8_t*>(frames), n->x1, B, 84, 84, 4, 4, 1, stream));
-    x1 = n->x1;
-  }
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(x1, n->w1, n->b1, n->x2, B, 21, 21, 64, 2, 2, 32, 0, 0, 1, 1, nullptr, 0, 0, 0, 0, 0, stream));
+  if (frames_s2d)
+    XA_TRY(xa_conv2d_nhwc_bf16_ex(frames, n->w1, n->b1, n->x2, B, 21, 21, 64, 2, 2, 32, 0, 0, 1, 1, nullptr, 0, 0, 0, 0, 0, stream));
+  else  // /255 + space-to-depth + conv1 in one kernel; x1 (only the backward pass reads it) is written from shared memory
+    XA_TRY(xa_conv2d_u8_s2d_bf16(static_cast<const uint8_t*>(frames), n->w1, n->b1, n->x2, n->x1, B, 84, 84, 2, 2, 32, 1, 1, stream));
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x2, n->w2, n->b2, n->x3, B, 10, 10, 128, 2, 2, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, 0, stream));
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, 0, stream));
   XA_TRY(xa_gemm_bf16_tn_ex(n->y3, n->wf, n->h, n->bf, B, 512, 3136, 512, 1, 1, nullptr, 512, 0, 0, n->gemm_ws, n->gemm_ws_bytes, stream));
@@ -43,7 +41,7 @@ int xa_nature_cnn_backward(const xa_nature_cnn_t* n, const void* frames_s2d_or_n
   const char* what = "xa_nature_cnn_backward";
   XA_TRY(check_net(n, what));
   XA_REQUIRE(d_actor && d_critic && flat_grad, XA_EINVAL, "%s: null gradient pointer", what);
-  XA_REQUIRE(n->w2_flip && n->w3_flip && n->wf_t && n->dh && n->g3 && n->g2 && n->g1 && n->scratch && n->grad_map, XA_EINVAL,
+  XA_REQUIRE(n->w2_flip && n->w3_flip && n->wf_t && n->dh && n->g3 && n->g2 && n->g1 && n->scratch && n->grad_map && n->grad_dest, XA_EINVAL,
              "%s: null backward buffer", what);
   const void* x1 = frames_s2d_or_null ? frames_s2d_or_null : n->x1;
   XA_REQUIRE(x1 != nullptr, XA_EINVAL, "%s: no first-layer input", what);
@@ -67,7 +65,7 @@ int xa_nature_cnn_backward(const xa_nature_cnn_t* n, const void* frames_s2d_or_n
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->g2, n->w2_flip, nullptr, n->g1, B, 10, 10, 64, 2, 2, 128, 1, 1, 0, 2, n->x2, 10, 10, 21, 21,
                                 XA_CONV_INPUT_ZERO_BORDER, stream));
   XA_TRY(xa_conv_wgrad_nhwc_bf16_partial(x1, n->g1, 32, 64, 2, 2, 21, static_cast<int64_t>(B) * 441, sc + n->off_c1, bytes_from(n->off_c1), stream));
-  return xa_grad_finalize_f32(sc, n->grad_map, n->segments, n->n_segments, flat_grad, n->n_grad, stream);
+  return xa_grad_finalize_f32(sc, n->grad_map, n->grad_dest, n->segments, n->n_segments, flat_grad, n->n_grad, stream);
 }
 
 }  // extern "C"

@@ -487,6 +487,27 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
     return y
 
 
+def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, x_s2d_out=None, stream=None):
+    """The 4x4-strided first layer straight from uint8 frames [B,H,W,4]: /255, space-to-depth and the kh x kw stride-1
+    convolution over the [B,H/4,W/4,64] grid in one kernel (bit-identical to space_to_depth_u8_bf16 + conv2d_nhwc_bf16).
+    `x_s2d_out` [B,H/4,W/4,64] bf16 also receives the scaled space-to-depth tensor (for the weight gradient)."""
+    f, ww = _dev(frames, 'uint8'), _dev(w, 'bfloat16')
+    B, H, W, C = f.shape
+    N = ww.shape[0]
+    if C != 4 or ww.shape[1] != kh * kw * 64:
+        raise ValueError(f'frames {f.shape} / weights {ww.shape}: built for 4-channel frames and K = kh*kw*64')
+    OH, OW = H // 4 - kh + 1, W // 4 - kw + 1
+    shape = (B, OH // 2, OW // 2, 4 * N) if out_s2d else (B, OH, OW, N)
+    y = out if out is not None else torch.empty(shape, dtype=torch.bfloat16, device=_device_of(f))
+    bias_a = _dev(bias, 'float32') if bias is not None else None
+    if x_s2d_out is not None and (x_s2d_out.dtype != torch.bfloat16 or tuple(x_s2d_out.shape) != (B, H // 4, W // 4, 64) or not x_s2d_out.is_contiguous()):
+        raise ValueError(f'x_s2d_out must be a contiguous bf16 [{B}, {H // 4}, {W // 4}, 64] tensor')
+    _call(f, 'xa_conv2d_u8_s2d_bf16', _ptr(f), _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W, kh, kw, N, int(bool(relu)),
+          int(bool(out_s2d)), stream)
+    _count()
+    return y
+
+
 def space_to_depth_u8_bf16(frames, block, *, scale_255=True, out=None, stream=None):
     """uint8 [B,H,W,C] -> bf16 [B,H/s,W/s,s*s*C] (channel order dy, dx, c), optionally divided by 255."""
     f = _dev(frames, 'uint8')
