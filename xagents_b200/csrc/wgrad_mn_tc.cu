@@ -18,7 +18,10 @@
 //   A (M = 128)  two (tap, 64-channel) groups of X, LBO = their distance in shared memory
 //   B (N = n_out) the dYg tile
 //   D            TMEM lanes = (group, c), columns = n; one accumulator column block per group pair, all resident
-// One extra group of constant ones yields the bias gradient db[n] = sum_q dYg[q, n] from the same pass.
+// The bias gradient db[n] = sum_q dYg[q, n] comes from the same pass: the four epilogue warps, idle while the K loop runs,
+// add up the columns of every dYg tile in shared memory (a first version multiplied by a group of constant ones on the
+// tensor core: one more MMA per K step, and these kernels are bound by the shared-memory reads of their MMA operands --
+// 4 KB of A per instruction for N = 32 / 64 -- not by tensor throughput).
 // The pixel range is split over the SMs (split-K); fp32 partials are added in split order (deterministic).
 // HBM traffic: (C + N) * Q * 2 bytes, each operand read once.
 #include "tc_common.cuh"
@@ -34,14 +37,14 @@ constexpr int kMaxBoxes = 20;
 
 struct WgradMnParams {
   float* partial;  // [splits, n_out, ld_p]
-  int n_out, n_groups, n_boxes, box_rows, ld_p;
+  int n_out, n_groups, n_boxes, box_rows, ld_p, db_col;
   int kb_per_split;
   int64_t k_blocks;
   uint32_t stage_bytes, b_off, tmem_cols;
   int box_shift[kMaxBoxes];   // pixel shift of the box's first row
   int box_col[kMaxBoxes];     // first channel of the box
   int box_off[kMaxBoxes];     // byte offset inside the stage
-  int group_off[kMaxGroups];  // byte offset of the group's first row inside the stage; -1 = the ones tile
+  int group_off[kMaxGroups];  // byte offset of the group's first row inside the stage
   int group_col[kMaxGroups];  // column of the group's channel 0 in a partial row
 };
 
@@ -51,8 +54,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
                                                             const __grid_constant__ WgradMnParams p, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ones = smem + static_cast<size_t>(stages) * p.stage_bytes;  // 64 rows x 128 B of bf16 1.0
-  uint64_t* full = reinterpret_cast<uint64_t*>(ones + 8192);
+  float* db_red = reinterpret_cast<float*>(smem + static_cast<size_t>(stages) * p.stage_bytes);  // [4 warps][64] column sums
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(db_red) + 8192);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -65,13 +68,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
   const int64_t kb1 = kb0 + p.kb_per_split < p.k_blocks ? kb0 + p.kb_per_split : p.k_blocks;
   constexpr int n_mblocks = kMB;
 
-  for (int i = threadIdx.x; i < 8192 / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
   for (int i = threadIdx.x; i < stages * kMB; i += kThreads) {
     const int s = i / kMB, mb = i - s * kMB;
-    const uint32_t base = xa::smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes), ones_addr = xa::smem_u32(ones);
+    const uint32_t base = xa::smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+    // an odd group count pairs the last group with itself (LBO = 0): lanes 64-127 of that block are a copy the epilogue skips
     const int g0 = 2 * mb, g1 = 2 * mb + 1 < p.n_groups ? 2 * mb + 1 : 2 * mb;
-    const uint32_t a0 = p.group_off[g0] < 0 ? ones_addr : base + p.group_off[g0];
-    const uint32_t a1 = p.group_off[g1] < 0 ? ones_addr : base + p.group_off[g1];
+    const uint32_t a0 = base + p.group_off[g0], a1 = base + p.group_off[g1];
     desc_tab[i] = make_smem_desc_mn(a0, a1 - a0, 1024, false);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
     for (int s = 0; s < stages; ++s) {
       xa::mbar_init(full + s, 1);
-      xa::mbar_init(empty + s, 1);
+      xa::mbar_init(empty + s, 1 + 4);  // the MMAs' commit + the four column-summing warps
     }
     xa::mbar_init(acc_full, 1);
     xa::fence_barrier_init();
@@ -140,16 +142,60 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
       umma_commit(acc_full);
     }
   } else {
-    // ---- epilogue: lanes = (group, channel), columns = n  ->  partial[split][n][group_col + channel]
+    // ---- while the K loop runs: column sums of every dYg tile (the bias gradient).  Warp `quad` takes 16 of the tile's 64
+    // pixel rows; a lane reads two adjacent columns (4 bytes) per row, un-swizzling by hand: 128-byte rows (n_out = 64)
+    // have their 16-byte chunk index XORed with (row & 7), 64-byte rows (n_out = 32) with ((row >> 1) & 3), lanes 0-15 on
+    // the even row of a pair and lanes 16-31 on the odd one.
     const int quad = warp & 3;
+    float db0 = 0.0f, db1 = 0.0f;
+    {
+      const bool wide = p.n_out == 64;
+      const uint32_t b_addr0 = xa::smem_u32(smem) + p.b_off;
+      const int lane_row = wide ? 0 : lane >> 4;            // which row of a pair (narrow tiles)
+      const uint32_t chunk = wide ? lane >> 2 : (lane & 15) >> 2, within = (lane & 3) * 4u;
+      int s = 0;
+      uint32_t phase = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_backoff(full + s, phase);
+        const uint32_t tile = b_addr0 + static_cast<uint32_t>(s) * p.stage_bytes;
+        if (wide) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t row = quad * 16 + i;
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tile + row * 128u + ((chunk ^ (row & 7u)) << 4) + within));
+            const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+            db0 += f.x, db1 += f.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t row = quad * 16 + 2 * i + lane_row;
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tile + row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4) + within));
+            const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+            db0 += f.x, db1 += f.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(empty + s)) : "memory");
+        if (++s == stages) s = 0, phase ^= 1;
+      }
+      if (!wide) {  // the odd rows' sums join the even rows' (fixed order)
+        db0 += __shfl_xor_sync(0xffffffffu, db0, 16);
+        db1 += __shfl_xor_sync(0xffffffffu, db1, 16);
+      }
+      const int cols2 = p.n_out / 2;  // lanes holding a column pair
+      if (lane < cols2) db_red[quad * 64 + 2 * lane] = db0, db_red[quad * 64 + 2 * lane + 1] = db1;
+    }
+    // ---- epilogue: lanes = (group, channel), columns = n  ->  partial[split][n][group_col + channel]
     mbar_wait_wd(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int mb = 0; mb < n_mblocks; ++mb) {
       const int g = 2 * mb + (quad >> 1);
       const int c = (quad & 1) * 32 + lane;
-      const bool is_ones = g < p.n_groups && p.group_off[g] < 0;
-      const bool valid = g < p.n_groups && (!is_ones || c == 0);
-      float* dst = p.partial + static_cast<int64_t>(split) * p.n_out * p.ld_p + (g < p.n_groups ? p.group_col[g] : 0) + c;
+      const bool valid = g < p.n_groups;
+      float* dst = p.partial + static_cast<int64_t>(split) * p.n_out * p.ld_p + (valid ? p.group_col[g] : 0) + c;
 #pragma unroll 1
       for (int n0 = 0; n0 < p.n_out; n0 += 32) {
         uint32_t v[32];
@@ -159,6 +205,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
           for (int j = 0; j < 32; ++j) dst[static_cast<int64_t>(n0 + j) * p.ld_p] = __uint_as_float(v[j]);
         }
       }
+    }
+    // bias gradient of this split: the four warps' column sums added in warp order -> column `db_col` of the partial rows
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    {
+      const int n = (quad * 32 + lane);
+      if (n < p.n_out)
+        p.partial[(static_cast<int64_t>(split) * p.n_out + n) * p.ld_p + p.db_col] = ((db_red[n] + db_red[64 + n]) + db_red[128 + n]) + db_red[192 + n];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -254,7 +307,7 @@ static int wgrad_run(const char* what, const void* x, const void* dy_grid, float
   XA_REQUIRE((n_out == 32 || n_out == 64) && channels > 0 && channels % 64 == 0 && kh > 0 && kw > 0 && kw <= 8 && grid_w >= kw, XA_EINVAL,
              "%s: n_out=%d channels=%d kernel %dx%d not supported", what, n_out, channels, kh, kw);
   const int cg = channels / 64;
-  const int n_groups = kh * kw * cg + 1;  // + the ones group (bias gradient)
+  const int n_groups = kh * kw * cg;
   const int n_mblocks = (n_groups + 1) / 2;
   XA_REQUIRE(n_groups <= kMaxGroups && n_mblocks * n_out <= 512, XA_EINVAL, "%s: %d taps x %d channels exceed the TMEM accumulator", what,
              kh * kw, channels);
@@ -299,7 +352,7 @@ static int wgrad_run(const char* what, const void* x, const void* dy_grid, float
     }
   }
   XA_REQUIRE(nb <= kMaxBoxes, XA_EINVAL, "%s: too many boxes", what);
-  p.group_off[ng] = -1, p.group_col[ng] = kh * kw * channels;
+  p.db_col = kh * kw * channels;
   p.n_boxes = nb;
   p.b_off = static_cast<uint32_t>(nb) * box_bytes;
   p.stage_bytes = p.b_off + (n_out == 64 ? 8192u : 4096u);
