@@ -43,7 +43,9 @@ struct Smem {
   static constexpr int kStageB = BN * kBlockK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (208 * 1024) / kStage > 8 ? 8 : (208 * 1024) / kStage;
-  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiPitch = 32 * 2 + 16;  // bf16 epilogue: a warp's 32 x 32 chunk, rows padded against bank conflicts
+  static constexpr int kEpiBytes = 8 * 32 * kEpiPitch;
+  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiBytes;
 };
 
 // 2 + 8 warps: TMA producer, MMA issuer, two epilogue groups of four warps; group g drains accumulator g (every other
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
   uint64_t* acc_full = empty + S::kStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* epi_stage = smem + S::kStages * S::kStage + 256;  // [8 warps][32 rows][kEpiPitch]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,13 +170,27 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
       const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + (mvec ? row * p.mask_ld + colt : 0));
       uint4 m0[4], m1[4], m2[4];
       auto load_mask = [&](uint4 (&m)[4], int chunk) {
-        if (mvec && chunk < kChunks && colt + chunk * 32 + 32 <= p.n) {
+        if (!kOutBf16 && mvec && chunk < kChunks && colt + chunk * 32 + 32 <= p.n) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) m[q] = __ldg(mrow + chunk * 4 + q);
         }
       };
       load_mask(m0, 0);
       load_mask(m1, 1);
+      // bf16 output: the mask is fetched in the layout of the transposed stores (lane -> row it*8 + lane/4, 16-byte piece
+      // lane%4 of the chunk's 64 bytes), one chunk ahead
+      const bool fast_mask = kOutBf16 && p.mask != nullptr && p.splits == 1 && (p.mask_ld % 8) == 0 && xa::aligned(p.mask, 16);
+      uint4 cmask[4], cnext[4];
+      auto load_cmask = [&](uint4 (&m)[4], int chunk) {
+        if (fast_mask && chunk < kChunks && colt + chunk * 32 + 32 <= p.n) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t grow = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + it * 8 + (lane >> 2);
+            if (grow < p.m) m[it] = __ldg(reinterpret_cast<const uint4*>(p.mask + grow * p.mask_ld + colt + chunk * 32) + (lane & 3));
+          }
+        }
+      };
+      load_cmask(cmask, 0);
       mbar_wait_backoff(acc_full + acc, (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -182,6 +199,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
         load_mask(m2, ci + 2);
+        load_cmask(cnext, ci + 1);
         const int64_t col0 = colt + c0;
         if (p.splits > 1) {  // raw fp32 partial tile; bias / ReLU / conversion happen in the reduction pass
           if (row < p.m && col0 < p.n) {
@@ -195,7 +213,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
               for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
             }
           }
-        } else if (row < p.m && col0 + 32 <= p.n && vec_ok && bias_vec && (p.mask == nullptr || (mvec && kOutBf16))) {
+        } else if ((kOutBf16 || row < p.m) && col0 + 32 <= p.n && vec_ok && bias_vec && (p.mask == nullptr || fast_mask)) {  // warp-uniform for bf16
           // Fast path (a full chunk of 32 columns, vector-aligned): the epilogue of the short-K products is bounded by its
           // instruction count, so no per-element flag tests here -- bias by vector loads, ReLU as one max, the mask as a
           // packed bf16 compare that yields a bit mask.
@@ -213,21 +231,42 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
           }
           const float lo = p.relu ? 0.0f : -INFINITY;
           if (kOutBf16) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + row * p.ldc + ocol0);
-            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
+            // Thread = row out of TMEM; stored like that, one warp-wide 16-byte access touches 32 different lines, and those
+            // load/store wavefronts (not HBM, not the tensor pipe) set the pace of the short-K products: 8 chunks x 8
+            // accesses x 32 wavefronts per tile and warp against 4096 MMA cycles.  So the chunk goes through a padded
+            // shared-memory tile: rows in, 16-byte pieces out with four consecutive lanes on one row's 64 bytes -- mask
+            // loads and output stores then touch 8 rows x 64 contiguous bytes per access.
+            uint8_t* my_stage = epi_stage + (warp - 2) * (32 * S::kEpiPitch);
+            const uint32_t st = xa::smem_u32(my_stage);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               __nv_bfloat162 h[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(fmaxf(f[8 * j + 2 * q], lo), fmaxf(f[8 * j + 2 * q + 1], lo));
-              uint4 o = *reinterpret_cast<uint4*>(h);
-              if (p.mask != nullptr) {
-                const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&m0[j]);
-                o.x &= __hgt2_mask(mk[0], zero), o.y &= __hgt2_mask(mk[1], zero);
-                o.z &= __hgt2_mask(mk[2], zero), o.w &= __hgt2_mask(mk[3], zero);
-              }
-              dst[j] = o;
+              const uint4 o = *reinterpret_cast<uint4*>(h);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st + lane * S::kEpiPitch + j * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                           : "memory");
             }
+            __syncwarp();
+            const int piece = lane & 3, r0 = lane >> 2;
+            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + r0;
+              const int64_t grow = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + rr;
+              uint4 o;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(st + rr * S::kEpiPitch + piece * 16));
+              if (grow < p.m) {
+                if (p.mask != nullptr) {
+                  const uint4 mk4 = cmask[it];
+                  const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mk4);
+                  o.x &= __hgt2_mask(mk[0], zero), o.y &= __hgt2_mask(mk[1], zero);
+                  o.z &= __hgt2_mask(mk[2], zero), o.w &= __hgt2_mask(mk[3], zero);
+                }
+                *(reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + grow * p.ldc + ocol0) + piece) = o;
+              }
+            }
+            __syncwarp();
           } else {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.c) + row * p.ldc + ocol0);
 #pragma unroll
@@ -238,7 +277,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
           float f[32];
           // grouped output columns (a [B, h*w*c] gradient written onto a zero-bordered [B, H, W, c] grid)
           const int64_t ocol0 = p.col_group > 0 ? (col0 / p.col_group) * p.col_group_pitch + col0 % p.col_group : col0;
-          const bool mv_ok = mvec && col0 + 32 <= p.n;
+          const bool mv_ok = !kOutBf16 && mvec && col0 + 32 <= p.n;
           const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(m0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -276,7 +315,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) m0[q] = m1[q], m1[q] = m2[q];
+        for (int q = 0; q < 4; ++q) m0[q] = m1[q], m1[q] = m2[q], cmask[q] = cnext[q];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
