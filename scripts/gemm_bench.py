@@ -37,3 +37,28 @@ for m, n, k, what in [(8192, 512, 3136, 'fc fwd (B=8192)'), (8192, 3136, 512, 'f
     t_ref = timeit(lambda: torch.matmul(a, bt, out=out))
     fl = 2.0 * m * n * k
     print(f'| {m} | {n} | {k} | {what} | {t_ours:.1f} | {fl/t_ours/1e6:.0f} | {t_ref:.1f} | {fl/t_ref/1e6:.0f} | {t_ref/t_ours:.2f} |')
+
+# the network's own weight-gradient product: dW = dY^T X from the row-major tensors as the other kernels leave them
+# (xa_gemm_bf16_atb, MN-major UMMA operands) against cuBLAS on the transposed view; and the heads as the fused kernel
+import ctypes  # noqa: E402
+from xagents_b200 import _ffi  # noqa: E402
+B = 8192
+dy = torch.randn((B, 512), device=dev).to(torch.bfloat16)
+xx = torch.randn((B, 3136), device=dev).to(torch.bfloat16)
+t_ours = timeit(lambda: ops.gemm_bf16_atb(dy, xx))
+outw = torch.empty((512, 3136), device=dev, dtype=torch.bfloat16)
+t_ref = timeit(lambda: torch.matmul(dy.t(), xx, out=outw))
+fl = 2.0 * B * 512 * 3136
+print(f'| 512 | 3136 | {B} | fc wgrad as the network runs it (A^T B, row-major operands; incl. split reduction) | {t_ours:.1f} | {fl/t_ours/1e6:.0f} | '
+      f'{t_ref:.1f} | {fl/t_ref/1e6:.0f} | {t_ref/t_ours:.2f} |')
+h = torch.randn((B, 512), device=dev).relu().to(torch.bfloat16)
+wh = torch.randn((8, 512), device=dev).to(torch.bfloat16)
+bh = torch.zeros(8, device=dev)
+actor, critic = torch.empty((B, 6), device=dev), torch.empty(B, device=dev)
+lib = _ffi.lib()
+p_ = lambda t: ctypes.c_void_p(t.data_ptr())
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+t_ours = timeit(lambda: lib.xa_heads_forward_bf16(p_(h), p_(wh), p_(bh), p_(actor), p_(critic), B, 512, 6, st))
+o8 = torch.empty((B, 8), device=dev, dtype=torch.bfloat16)
+t_ref = timeit(lambda: torch.matmul(h, wh.t(), out=o8))
+print(f'| {B} | 8 | 512 | heads fwd as the network runs it (fused CUDA-core kernel, fp32 outputs + bias) | {t_ours:.1f} | - | {t_ref:.1f} | - | {t_ref/t_ours:.2f} |')

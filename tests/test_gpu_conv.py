@@ -267,16 +267,16 @@ def test_graphed_inference_equals_eager_and_follows_weight_updates():
     net = NatureCNN(4, 6).cuda()
     tc = NatureCnnTcForward(net)
     x = torch.randint(0, 256, (64, 84, 84, 4), dtype=torch.uint8, device=DEV)
-    a0, c0 = tc(x)
+    a0, c0 = [t.clone() for t in tc(x)]                  # the outputs are the plan's buffers for this batch size: reused by every call
     run = tc.graphed(64)
-    a1, c1 = run(x)
+    a1, c1 = [t.clone() for t in run(x)]
     torch.cuda.synchronize()
     assert torch.equal(a0, a1) and torch.equal(c0, c1)
     with torch.no_grad():                               # an "optimiser step", then refresh: the graph must see the new weights
         for p in net.parameters():
             p.add_(0.01 * torch.randn_like(p))
     tc.refresh()
-    a2, c2 = tc(x)
+    a2, c2 = [t.clone() for t in tc(x)]
     a3, c3 = run(x)
     torch.cuda.synchronize()
     assert torch.equal(a2, a3) and torch.equal(c2, c3) and not torch.equal(a0, a2)

@@ -87,7 +87,8 @@ class TorchModel:
             if self._graph_inference and not self.capturing:      # fixed rollout batch: one graph replay per step
                 a, c = self._tc_forward.graphed(states.shape[0])(states)
                 return a.clone(), c.clone()
-            return self._tc_forward(states)
+            a, c = self._tc_forward(states)                       # the plan's own buffers: handed out as they are only inside a
+            return (a, c) if self.capturing else (a.clone(), c.clone())   # captured rollout, whose next kernels consume them
         x = self.scaled(states)
         if training and self._native_plan and x.dtype in (torch.uint8, torch.bfloat16):
             plan = self.module.plan(x.shape[0], self.flat_param, self.flat_grad.numel())
@@ -105,6 +106,21 @@ class TorchModel:
         self._outputs = (actor, critic) if training else None
         return (None if actor is None else actor.detach().contiguous(),
                 None if critic is None else critic.detach().contiguous())
+
+    def forward_into(self, states, actor_dst, critic_dst, i=0):
+        """Training forward with the outputs written into the caller's tensors (the prepared pipelines' per-minibatch output
+        rows): no copies with the native plan, forward() + two copies otherwise."""
+        x = self.scaled(states)
+        if self._native_plan and x.dtype in (torch.uint8, torch.bfloat16):
+            plan = self.module.plan(x.shape[0], self.flat_param, self.flat_grad.numel())
+            self._outputs = plan
+            plan.forward(x if x.is_contiguous() else x.contiguous(), out=(actor_dst, critic_dst))
+            return
+        actor, critic = self.forward(states, training=True)
+        if actor is not None:
+            actor_dst.copy_(actor.reshape(actor_dst.shape))
+        if critic is not None:
+            critic_dst.copy_(critic.reshape(critic_dst.shape))
 
     def scaled(self, states):
         """The network's input for a batch of stored observations: fp32, images divided by 255 (base.py:505-506)."""

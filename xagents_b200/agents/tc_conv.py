@@ -6,14 +6,13 @@ strided layers rewritten as stride-1 layers over space-to-depth inputs (8x8/4 ->
 4x4/2 -> 2x2/1 on 10x10x128), the FC weight permuted from (c, h, w) to (h, w, c) flatten order (which is the
 order the reference's Keras Flatten uses on NHWC), both heads stacked into one [8, 512] matrix.
 
-    uint8 frames --xa_space_to_depth_u8_bf16 (/255)--> [B,21,21,64]
-      --xa_conv2d_nhwc_bf16 (2x2, ReLU, out_s2d)-->    [B,10,10,128]
+    uint8 frames --xa_conv2d_u8_s2d_bf16 (/255, space-to-depth, 2x2 conv, ReLU, out_s2d: one kernel)--> [B,10,10,128]
       --xa_conv2d_nhwc_bf16 (2x2, ReLU)-->             [B,9,9,64]
       --xa_conv2d_nhwc_bf16 (3x3, ReLU)-->             [B,7,7,64] = [B,3136]
-      --xa_gemm_bf16_tn (ReLU)--> [B,512] --xa_gemm_bf16_tn--> logits [B,A], value [B]
+      --xa_gemm_bf16_tn (ReLU)--> [B,512] --xa_heads_forward_bf16--> logits [B,A], value [B]
 
 Inference only (rollout-time policy evaluation and the bootstrap value: T+1 of the T+1+K*M forward passes of a
-train step); the backward convolutions are not built yet, so training still differentiates the torch trunk.
+train step); training runs the same kernels plus the backward pass through `NatureCnnTc` (tc_cnn.py, tc_plan.py).
 """
 import torch
 
@@ -25,6 +24,7 @@ class NatureCnnTcForward:
     def __init__(self, module):
         self.module = module
         self._graphs = {}
+        self._plans = {}                                          # batch size -> NaturePlan (kept: captured graphs read their buffers)
         self._pack, self._shared = None, False
         self.refresh()
 
@@ -74,11 +74,12 @@ class NatureCnnTcForward:
 
     @torch.no_grad()
     def __call__(self, frames_u8):
-        """uint8 [B,84,84,4] -> (actor_out [B,A] fp32, critic [B] fp32)."""
-        x = ops.space_to_depth_u8_bf16(frames_u8.contiguous(), 4)
-        x = ops.conv2d_nhwc_bf16(x, self.w1, 2, 2, bias=self.b1, relu=True, out_s2d=True)
-        x = ops.conv2d_nhwc_bf16(x, self.w2, 2, 2, bias=self.b2, relu=True)
-        x = ops.conv2d_nhwc_bf16(x, self.w3, 3, 3, bias=self.b3, relu=True)
-        h = ops.gemm_bf16_tn(x.view(x.shape[0], -1), self.wf, bias=self.bf_, relu=True, out_dtype=torch.bfloat16)
-        out = ops.gemm_bf16_tn(h, self.wh, bias=self.bh, out_dtype=torch.float32)
-        return out[:, :self.n_actions].contiguous(), out[:, self.n_actions].contiguous()
+        """uint8 [B,84,84,4] -> (actor_out [B,A] fp32, critic [B] fp32): one native call, six launches (csrc/nature_net.cu; the
+        first layer reads the frames directly).  The outputs are the plan's own buffers for this batch size, valid until the
+        next call with it."""
+        batch = frames_u8.shape[0]
+        plan = self._plans.get(batch)
+        if plan is None:
+            from .tc_plan import NaturePlan
+            plan = self._plans[batch] = NaturePlan(self._pack, self._pack._named, None, batch, backward=False)
+        return plan.forward(frames_u8 if frames_u8.is_contiguous() else frames_u8.contiguous())

@@ -8,9 +8,11 @@ the re-layout code below is run once on tensors of parameter INDICES; the result
 kernel (`xa_gather_cast_f32`) per refresh.  Re-deriving the operands with torch ops cost ~30 launches per refresh --
 and there is one refresh per minibatch.
 """
+import ctypes
+
 import torch
 
-from .. import ops
+from .. import _ffi, ops
 
 
 def s2d_kernel(w, s):
@@ -108,7 +110,23 @@ class OperandPack:
                     setattr(self, name, buf[pos:pos + n].view(shape))
 
     @torch.no_grad()
-    def refresh(self):
+    def refresh(self, stream=None):
+        """One refresh happens per minibatch, so the steady state is two prepared C calls on fixed pointers; the layout
+        (index maps) is re-derived only when the parameters moved (their first tensor's address is the cheap witness)."""
+        first = next(iter(self._named.values()))
+        fast = getattr(self, '_fast', None)
+        if fast is not None and fast[0] == first.data_ptr() and fast[1] == first.device:
+            dev = fast[1]
+            s = ctypes.c_void_p((stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream)
+            if dev.index != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    for args in fast[2]:
+                        _ffi.check('xa_gather_cast_f32', fast[3](*args, s))
+            else:
+                for args in fast[2]:
+                    _ffi.check('xa_gather_cast_f32', fast[3](*args, s))
+            ops._count(2)
+            return self
         flat, offsets, key = self._source()
         key = key + tuple(offsets)
         if key != self._layout_key:
@@ -116,8 +134,16 @@ class OperandPack:
             self._layout_key = key
         if flat is None:
             flat = torch.cat([q.detach().reshape(-1).float() for q in self._named.values()])
-        ops.gather_cast_f32(flat, self._map16, self._buf16)
-        ops.gather_cast_f32(flat, self._map32, self._buf32)
+        ops.gather_cast_f32(flat, self._map16, self._buf16, stream=stream)
+        ops.gather_cast_f32(flat, self._map32, self._buf32, stream=stream)
+        self._fast = None
+        if key[0] == 'shared' and first.is_cuda:                    # the source is the parameters' own storage: fixed pointers
+            vp = ctypes.c_void_p
+            self._flat_keepalive = flat
+            self._fast = (first.data_ptr(), first.device,
+                          [(vp(flat.data_ptr()), vp(self._map16.data_ptr()), vp(self._buf16.data_ptr()), self._buf16.numel(), 1),
+                           (vp(flat.data_ptr()), vp(self._map32.data_ptr()), vp(self._buf32.data_ptr()), self._buf32.numel(), 0)],
+                          _ffi.lib().xa_gather_cast_f32)
         return self
 
     # ---- scratch the backward pass keeps per batch size ----------------------------------------------------------

@@ -136,10 +136,15 @@ class NaturePlan:
     def _stream(self, stream):
         return ctypes.c_void_p((stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream)
 
-    def forward(self, frames, stream=None):
+    def forward(self, frames, stream=None, out=None):
         """uint8 [B,84,84,4] frames, or the bf16 [B,21,21,64] output of ops.gather_s2d_u8_bf16 -> (actor [B,A], critic [B]) fp32:
-        the plan's own buffers, valid until the next forward()."""
+        the plan's own buffers, valid until the next forward(), or the caller's `out` = (actor, critic) tensors."""
         assert frames.is_cuda and frames.is_contiguous() and frames.shape[0] == self.batch, (tuple(frames.shape), self.batch)
+        actor, critic = out if out is not None else (self.actor, self.critic)
+        if out is not None:
+            assert actor.dtype == torch.float32 and actor.is_contiguous() and actor.numel() == self.actor.numel() and actor.device == self.device
+            assert critic.dtype == torch.float32 and critic.is_contiguous() and critic.numel() == self.batch and critic.device == self.device
+        self.net.actor, self.net.critic = actor.data_ptr(), critic.data_ptr()
         s2d = frames.dtype == torch.bfloat16
         if s2d:
             assert tuple(frames.shape[1:]) == (21, 21, 64)
@@ -152,7 +157,7 @@ class NaturePlan:
             self._x1_in = self.x1
         self._launch(self._fwd, 'xa_nature_cnn_forward', ctypes.byref(self.net), ctypes.c_void_p(frames.data_ptr()), int(s2d), self._stream(stream))
         ops._count(6)
-        return self.actor, self.critic
+        return actor, critic
 
     def backward(self, d_actor, d_critic, flat_grad, stream=None):
         """Output gradients (fp32, from the loss kernel) -> every element of `flat_grad` (the model's flat gradient buffer)."""

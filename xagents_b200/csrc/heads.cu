@@ -208,7 +208,7 @@ int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float*
   XA_REQUIRE(xa::aligned(h, 16) && xa::aligned(wh, 16), XA_EALIGN, "%s: h and wh must be 16-byte aligned", what);
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int want = (batch + kFwdThreads / 32 - 1) / (kFwdThreads / 32);
-  const int grid = want < 2 * sms ? want : 2 * sms;
+  const int grid = want < 8 * sms ? want : 8 * sms;  // one frame per warp up to a full wave of 8 CTAs per SM: the kernel is latency-bound
   heads_forward_kernel<<<grid, kFwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h),
                                                                                    static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch,
                                                                                    n_actions);
