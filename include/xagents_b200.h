@@ -192,11 +192,25 @@ int xa_a2c_loss_f32(const xa_loss_args* args, xa_stream_t stream);
 int xa_policy_step_f32(const float* actor_out, int actor_kind, const float* noise, uint64_t seed,
                        uint64_t offset, float* actions, float* log_probs, float* entropies, int64_t n,
                        int n_actions, xa_stream_t stream);
-/* The same step with the Philox offset in DEVICE memory (*offset_dev is read by the kernel, then advanced by `advance` by a
- * one-thread kernel behind it): a CUDA graph that captured a whole rollout draws fresh noise on every replay. */
+/* The same step with the Philox offset in DEVICE memory: the kernel draws at *offset_dev + offset; when `advance` is not zero a
+ * one-thread kernel behind it adds `advance` to *offset_dev: a CUDA graph that captured a whole rollout draws fresh noise on
+ * every replay (its steps pass offset = t * step, advance = 0, and one xa_bump_u64 closes the rollout). */
 int xa_policy_step_counter_f32(const float* actor_out, int actor_kind, uint64_t seed, uint64_t* offset_dev,
-                               uint64_t advance, float* actions, float* log_probs, float* entropies, int64_t n,
+                               uint64_t offset, uint64_t advance, float* actions, float* log_probs, float* entropies, int64_t n,
                                int n_actions, xa_stream_t stream);
+
+/* *counter += delta, in stream order (counter: device memory, 8-byte aligned). */
+int xa_bump_u64(uint64_t* counter, uint64_t delta, xa_stream_t stream);
+
+/* One step of `n_envs` device-resident synthetic Atari environments (SURVEY.md 8d's synthetic distribution behind the env
+ * interface) fused with the bookkeeping BaseAgent.step_envs does around env.step / env.reset, xagents/base.py:408-426:
+ * new_states[e] (may be NULL) = the frame the step returns -- the terminal frame of a finished episode --, states[e] = the frame
+ * the environment holds afterwards (after the reset when done), rewards / dones [n_envs] fp32, episode_sums (may be NULL)
+ * += reward, copied to sums_log (may be NULL), then cut at dones.  Frames are rows of `row_bytes` drawn from `pool`
+ * [pool_size rows]; draws are Philox4x32-10 keyed by seed at counter (e, *offset_dev + offset) (offset_dev may be NULL). */
+int xa_synth_env_step_u8(const uint8_t* pool, int pool_size, int64_t row_bytes, uint8_t* states, uint8_t* new_states,
+                         float* rewards, float* dones, float* episode_sums, float* sums_log, int n_envs, float p_reward,
+                         float p_done, uint64_t seed, const uint64_t* offset_dev, uint64_t offset, xa_stream_t stream);
 
 /* ---- dense contractions on the tensor cores (row "next": the policy/value network) ------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU), bf16 operands, fp32 accumulation in TMEM (tcgen05),

@@ -1,6 +1,6 @@
 #!/bin/bash
 # session evidence run: full GPU test suite, bench lines, network tables, launch list of one forward+backward
-O=gpurun_out/s10; mkdir -p $O
+O=gpurun_out/s12; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "rc=$?" >> $O/smoke.log
 timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "rc=$?" >> $O/bench_n1.err

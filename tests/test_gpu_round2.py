@@ -335,3 +335,87 @@ def test_loss_kernel_gradients_vs_differences_of_the_reference_loss(golden, case
     assert abs(float(sc[0]) - float(g['loss'])) <= REL * max(abs(float(g['loss'])), 1.0)
     assert np.abs(d_actor.cpu().numpy() - g['d_actor']).max() <= REL * np.abs(g['d_actor']).max()
     assert np.abs(d_values.cpu().numpy() - g['d_critic']).max() <= REL * np.abs(g['d_critic']).max()
+
+
+def test_native_synthetic_environment_step():
+    """csrc/synth_env.cu (one launch per step of envs.BatchedSyntheticAtari on the GPU): the step_envs contract of
+    xagents/base.py:408-426 -- the returned frame is the terminal one, the held frame the post-reset one, episode sums cut at
+    dones --, every frame a row of the pool, rewards / dones at the configured rates, draws a function of (seed, counter + offset)."""
+    from xagents_b200 import envs
+    E = 512
+    made = envs.create_envs('SyntheticAtariDevice-v0', E, preprocess=True, device=DEV)
+    made.seed(9)
+    made.p_done, made.p_reward = 0.25, 0.5
+    made.reset_all()
+    assert made.native_step
+    pool = made._pool.flatten(1)
+    sums, log = torch.zeros(E, device=DEV), torch.empty(E, device=DEV)
+    want_sums = np.zeros(E)
+    n_done = n_reward = n_plus = 0
+    for step in range(6):
+        new_states, rewards, dones = (torch.empty_like(made.states), torch.empty(E, device=DEV), torch.empty(E, device=DEV))
+        made.step_into(new_states, rewards, dones, sums, log)
+        r, d = rewards.cpu().numpy(), dones.cpu().numpy()
+        assert set(np.unique(r)) <= {-1.0, 0.0, 1.0} and set(np.unique(d)) <= {0.0, 1.0}
+        moved_on = (made.states != new_states).flatten(1).any(1)
+        assert not bool((moved_on & ~dones.bool()).any())          # finished environments already hold another frame ...
+        assert int((dones.bool() & ~moved_on).sum()) <= 6          # ... (the same pool row again w.p. 1/256)
+        for frames in (new_states, made.states):                   # every frame is a row of the pool
+            rows = frames.flatten(1)[::37]
+            assert bool((rows[:, None, :64] == pool[None, :, :64]).all(-1).any(-1).all())
+        want_sums += r
+        assert np.array_equal(log.cpu().numpy(), want_sums.astype(np.float32))
+        want_sums[d > 0] = 0
+        assert np.array_equal(sums.cpu().numpy(), want_sums.astype(np.float32))
+        n_done, n_reward, n_plus = n_done + int(d.sum()), n_reward + int((r != 0).sum()), n_plus + int((r > 0).sum())
+    n = 6 * E
+    assert abs(n_done / n - 0.25) < 0.04 and abs(n_reward / n - 0.5) < 0.04 and abs(n_plus / max(n_reward, 1) - 0.5) < 0.06
+    # same (seed, counter + offset) -> same step; the device counter and the host offset add up
+    outs = []
+    for counter, offset in ((0, 5), (5, 0), (2, 3), (0, 6)):
+        made._counter.fill_(counter)
+        made._host_offset = offset
+        new_states, rewards, dones = made.step_all(None)
+        outs.append((new_states.clone(), rewards.clone(), dones.clone(), made.states.clone()))
+    for other in outs[1:3]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], other))
+    assert not torch.equal(outs[0][0], outs[3][0])
+    assert ops.launch_count() >= 0
+    with pytest.raises(Exception, match='different buffers'):
+        made.step_into(made.states, rewards, dones)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('network', ['torch', 'tcgen05'])
+def test_fused_rollout_steps_equal_the_generic_loop(network):
+    """A2C._rollout_loop_fused (network, sampler and environment kernel write rows t / t+1 of the rollout buffers in place: three
+    native calls per step) against the generic loop of a2c/agent.py:113-139 on the same environment and seeds: identical buffers,
+    states, dones and episode bookkeeping, rollout after rollout."""
+    from xagents_b200 import envs
+    from xagents_b200.agents import PPO, NatureCNN, TorchModel
+    T, E = 5, 16
+    agents = []
+    for fused in (True, False):
+        made = envs.create_envs('SyntheticAtariDevice-v0', E, preprocess=True, device=DEV)
+        made.seed(5)
+        made.p_done = 0.2
+        made.reset_all()
+        torch.manual_seed(0)
+        net = TorchModel(NatureCNN(4, 6).cuda(), tensor_core_inference=(network == 'tcgen05'))
+        agent = PPO(made, net, n_steps=T, mini_batches=4, ppo_epochs=1, quiet=True, seed=3)
+        agent.graph_rollout = False
+        if not fused:
+            agent._fused_rollout_applies = lambda: False
+        agents.append(agent)
+    f, g = agents
+    assert f._fused_rollout_applies()
+    for rollout in range(3):
+        for a in (f, g):
+            a.get_batch()
+            a._flush_episode_log()
+        torch.cuda.synchronize()
+        for name in ('ro_states', 'ro_actions', 'ro_rewards', 'ro_dones', 'ro_values', 'ro_log_probs', 'ro_entropies', 'ro_actor', 'ro_returns'):
+            assert torch.equal(getattr(f, name), getattr(g, name)), (rollout, name)
+        assert torch.equal(f.get_states(), g.get_states()) and torch.equal(f.get_dones(), g.get_dones())
+        assert f.steps == g.steps == (rollout + 1) * T * E and f.games == g.games and list(f.total_rewards) == list(g.total_rewards)
+    assert f.games > 0

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libxagents_b200.so')
-SOURCES = ['capi.cu', 'returns_scan.cu', 'gather.cu', 'loss.cu', 'optim.cu', 'peer_adam.cu', 'policy.cu', 'gemm_tc.cu', 'conv_tc.cu', 'conv_flat_tc.cu', 'wgrad_mn_tc.cu', 'gemm_atb_tc.cu', 'heads.cu', 'grad_finalize.cu', 'nature_net.cu']
+SOURCES = ['capi.cu', 'returns_scan.cu', 'gather.cu', 'loss.cu', 'optim.cu', 'peer_adam.cu', 'policy.cu', 'synth_env.cu', 'gemm_tc.cu', 'conv_tc.cu', 'conv_flat_tc.cu', 'wgrad_mn_tc.cu', 'gemm_atb_tc.cu', 'heads.cu', 'grad_finalize.cu', 'nature_net.cu']
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

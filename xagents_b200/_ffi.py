@@ -111,8 +111,11 @@ PROTOTYPES = {
     'xa_a2c_loss_f32': (ctypes.c_int, [ctypes.POINTER(LossArgs), c_stream]),
     'xa_policy_step_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_uint64, ctypes.c_uint64, c_f32p, c_f32p, c_f32p,
                                           ctypes.c_int64, ctypes.c_int, c_stream]),
-    'xa_policy_step_counter_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, c_f32p, c_f32p, c_f32p,
-                                                  ctypes.c_int64, ctypes.c_int, c_stream]),
+    'xa_policy_step_counter_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_f32p, c_f32p,
+                                                  c_f32p, ctypes.c_int64, ctypes.c_int, c_stream]),
+    'xa_bump_u64': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, c_stream]),
+    'xa_synth_env_step_u8': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                            ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, c_stream]),
     'xa_gemm_bf16_tn': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                                                                 ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gemm_bf16_tn_ex': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p] +

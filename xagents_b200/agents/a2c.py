@@ -97,19 +97,28 @@ class A2C(OnPolicy):
         actor_out, critic = self.net.forward(x, training=training)
         if actions is None and self.action_source is None:
             # sample + log_prob + entropy in one kernel (Philox stream keyed by the agent seed)
-            counter = getattr(self, '_philox', None) if getattr(self.net, 'capturing', False) else None
             rows = None
             if step is not None and getattr(self, '_rollout_rows', False):     # the rollout loop: write row `step` of the buffers directly
                 rows = (self.ro_actions[step], self.ro_log_probs[step], self.ro_entropies[step])
-            actions, logp, entropy = ops.policy_step(actor_out, actor_kind=self.actor_kind, counter=counter, out=rows,
-                                                     seed=int(self.seed) if self.seed else 0, offset=self._rng_offset)
-            self._rng_offset += 2 * self.n_actions
+            actions, logp, entropy = self._sample(actor_out, rows)
             return actions, logp, critic, entropy, actor_out
         if actions is None:
             actions = self.action_source(step, actor_out)
             actions = actions if isinstance(actions, torch.Tensor) else self._to_device(actions, torch.float32)
         logp, entropy = self._log_prob_entropy(actor_out, actions)
         return actions, logp, critic, entropy, actor_out
+
+    def _sample(self, actor_out, rows=None):
+        """sample + log_prob + entropy in one kernel (Philox stream keyed by the agent seed).  Inside a captured rollout the offset
+        is `_philox` (device memory) + the steps taken since the capture began; the counter is advanced once, at the rollout's end."""
+        capturing = getattr(self.net, 'capturing', False) and getattr(self, '_philox', None) is not None
+        if capturing:
+            out = ops.policy_step(actor_out, actor_kind=self.actor_kind, counter=self._philox, offset=self._rng_offset - self._philox_base,
+                                  advance=0, out=rows, seed=int(self.seed) if self.seed else 0)
+        else:
+            out = ops.policy_step(actor_out, actor_kind=self.actor_kind, out=rows, seed=int(self.seed) if self.seed else 0, offset=self._rng_offset)
+        self._rng_offset += 2 * self.n_actions
+        return out
 
     # ------------------------------------------------------------------ rollout (a2c/agent.py:96-139)
     def get_batch(self):
@@ -134,8 +143,43 @@ class A2C(OnPolicy):
         return [self.ro_states, self.ro_rewards, self.ro_actions, self.ro_values, self.ro_dones, self.ro_log_probs,
                 self.ro_entropies, self.ro_actor]
 
+    def _fused_rollout_applies(self):
+        """Every rollout step as  network -> sampler -> environment  with all three writing the rollout rows in place: needs the
+        native batched environment, a model that can write its outputs into given tensors, and the stock step / sampling code."""
+        from .base import BaseAgent
+        cls = type(self)
+        return (self.batched and getattr(self.envs, 'native_step', False) and self.action_source is None and self.obs_dtype == torch.uint8
+                and hasattr(self.net, 'infer_into') and cls.get_model_outputs is A2C.get_model_outputs
+                and cls.step_envs is BaseAgent.step_envs and cls._rollout_loop is A2C._rollout_loop)
+
+    def _rollout_loop_fused(self, capturing=False):
+        """The same rollout (a2c/agent.py:113-139 around base.py:408-426) in three native calls per step: the network writes
+        actor / value rows t, the sampler the action / log-prob / entropy rows t, the environment kernel the frame row t + 1
+        (the frames a step returns are the next step's input), the reward row t and the done row t + 1, and keeps the episode
+        sums -- no copies, no elementwise launches.  Bit-identical buffers to `_rollout_loop` on the same environment."""
+        T, envs = self.n_steps, self.envs
+        if getattr(self, '_ro_sums', None) is None:
+            self._ro_sums = torch.empty((T, self.n_envs), dtype=torch.float32, device=self.device)
+        if getattr(self, '_ro_spare', None) is None:
+            self._ro_spare = torch.empty_like(self.ro_states[0])
+        if not capturing:
+            self._flush_episode_log()                              # pending entries view rows this rollout overwrites
+        self.ro_states[0].copy_(envs.states)
+        self.ro_dones[0].copy_(self.dones)
+        for t in range(T):
+            self.net.infer_into(self.ro_states[t], self.ro_actor[t], self.ro_values[t])
+            self._sample(self.ro_actor[t], (self.ro_actions[t], self.ro_log_probs[t], self.ro_entropies[t]))
+            envs.step_into(self.ro_states[t + 1] if t + 1 < T else self._ro_spare, self.ro_rewards[t], self.ro_dones[t + 1],
+                           self._episode_sums, self._ro_sums[t])
+        self.dones.copy_(self.ro_dones[T])
+        self.states = envs.states
+        self.steps += T * self.n_envs
+        self._episode_log = [(self.ro_dones[t + 1], self._ro_sums[t]) for t in range(T)]
+
     def _rollout_loop(self, capturing=False):
         """n_steps x (model outputs -> row t of the rollout buffers -> environment step), a2c/agent.py:113-139."""
+        if self._fused_rollout_applies():
+            return self._rollout_loop_fused(capturing)
         step_states, step_dones = self.get_states(), self.get_dones()
         self._rollout_rows = True                                  # the sampler writes its three rows in place
         for t in range(self.n_steps):
@@ -160,7 +204,7 @@ class A2C(OnPolicy):
         if self.graph_rollout is False or self._rollout_graph is False or self.device.type != 'cuda':
             return False
         from .models import TorchModel
-        ok = (self.batched and hasattr(self.envs, 'GRAPH_STATE') and hasattr(self.envs, '_gen') and self.action_source is None
+        ok = (self.batched and hasattr(self.envs, 'GRAPH_STATE') and hasattr(self.envs, 'register_graph') and self.action_source is None
               and isinstance(self.net, TorchModel) and (self.graph_rollout is True or type(self).__name__ in ('A2C', 'PPO')))
         if not ok:
             assert self.graph_rollout is not True, 'graph_rollout=True needs a batched device environment and a TorchModel'
@@ -169,8 +213,11 @@ class A2C(OnPolicy):
 
     def _capture_rollout(self):
         envs, dev = self.envs, self.device
+        self._flush_episode_log()
         self._ro_sums = torch.empty((self.n_steps, self.n_envs), dtype=torch.float32, device=dev)
         self._philox = torch.full((1,), self._rng_offset, dtype=torch.int64, device=dev)
+        self._philox_base = self._rng_offset
+        envs.sync_rng()                                            # the captured steps count from the device counter alone
         # fixed-address homes for everything the loop reads on entry and replaces on exit
         home = {name: getattr(envs, name).clone() for name in envs.GRAPH_STATE}
         home['agent.dones'], home['agent.sums'] = self.dones.clone(), self._episode_sums.clone()
@@ -189,7 +236,7 @@ class A2C(OnPolicy):
             enter()
 
         saved = {k: v.clone() for k, v in home.items()}
-        gen_state, steps, log, rng_offset = envs._gen.get_state(), self.steps, list(self._episode_log), self._rng_offset
+        gen_state, steps, log, rng_offset = envs.rng_state(), self.steps, list(self._episode_log), self._rng_offset
         self.net.capturing = True                                  # no nested graph replays inside the capture
         stream = torch.cuda.Stream(dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
@@ -200,14 +247,16 @@ class A2C(OnPolicy):
                 stream.synchronize()
                 for k, v in saved.items():                         # ... undone: same states, same random streams as before
                     home[k].copy_(v)
-                envs._gen.set_state(gen_state)
+                envs.set_rng_state(gen_state)
                 self._rng_offset = rng_offset
                 self._philox.fill_(rng_offset)
                 enter()
                 graph = torch.cuda.CUDAGraph()
-                graph.register_generator_state(envs._gen)
+                envs.register_graph(graph)
                 with torch.cuda.graph(graph, stream=stream):
                     self._rollout_loop(capturing=True)
+                    ops.bump_u64(self._philox, self._rng_offset - rng_offset)   # the sampler's and the environment's Philox
+                    envs.sync_rng()                                             # counters advance once per replay
                     leave()
         finally:
             self.net.capturing = False

@@ -107,6 +107,16 @@ class TorchModel:
         return (None if actor is None else actor.detach().contiguous(),
                 None if critic is None else critic.detach().contiguous())
 
+    def infer_into(self, states, actor_dst, critic_dst):
+        """Rollout-time forward (training=False) with the outputs written into the caller's tensors -- rows of the rollout
+        buffers: in place through the tensor-core inference plan, forward() + two copies otherwise."""
+        if self._tc_forward is not None and states.dtype == torch.uint8:
+            self._tc_forward(states, out=(actor_dst, critic_dst))
+            return
+        actor, critic = self.forward(states, training=False)
+        actor_dst.copy_(actor.reshape(actor_dst.shape))
+        critic_dst.copy_(critic.reshape(critic_dst.shape))
+
     def forward_into(self, states, actor_dst, critic_dst, i=0):
         """Training forward with the outputs written into the caller's tensors (the prepared pipelines' per-minibatch output
         rows): no copies with the native plan, forward() + two copies otherwise."""

@@ -73,13 +73,13 @@ class NatureCnnTcForward:
         return run
 
     @torch.no_grad()
-    def __call__(self, frames_u8):
+    def __call__(self, frames_u8, out=None):
         """uint8 [B,84,84,4] -> (actor_out [B,A] fp32, critic [B] fp32): one native call, six launches (csrc/nature_net.cu; the
         first layer reads the frames directly).  The outputs are the plan's own buffers for this batch size, valid until the
-        next call with it."""
+        next call with it -- or the caller's `out` = (actor, critic) tensors (rows of the rollout buffers)."""
         batch = frames_u8.shape[0]
         plan = self._plans.get(batch)
         if plan is None:
             from .tc_plan import NaturePlan
             plan = self._plans[batch] = NaturePlan(self._pack, self._pack._named, None, batch, backward=False)
-        return plan.forward(frames_u8 if frames_u8.is_contiguous() else frames_u8.contiguous())
+        return plan.forward(frames_u8 if frames_u8.is_contiguous() else frames_u8.contiguous(), out=out)

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) 
   const int A = p.n_actions;
   const float* row = p.actor_out + i * A;
   const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
-  const uint64_t offset = p.offset_ptr ? *p.offset_ptr : p.offset;
+  const uint64_t offset = (p.offset_ptr ? *p.offset_ptr : 0) + p.offset;
   uint4 rnd = make_uint4(0, 0, 0, 0);
   auto draw = [&](int j) -> uint32_t {  // j-th 32-bit word of this sample's Philox stream
     if ((j & 3) == 0)
@@ -114,17 +114,20 @@ int launch_policy(const PolicyParams& p, int actor_kind, cudaStream_t s, const c
 
 }  // namespace
 
-// The same step with the Philox offset held in DEVICE memory: the kernel reads *offset_dev and a one-thread kernel behind it
-// adds `advance`, so a CUDA graph that captured the call draws fresh noise on every replay.
-extern "C" int xa_policy_step_counter_f32(const float* actor_out, int actor_kind, uint64_t seed, uint64_t* offset_dev, uint64_t advance,
-                                          float* actions, float* log_probs, float* entropies, int64_t n, int n_actions, xa_stream_t stream) {
+// The same step with the Philox offset held in DEVICE memory: the kernel draws at *offset_dev + offset and, when `advance` is
+// not zero, a one-thread kernel behind it adds `advance` to *offset_dev, so a CUDA graph that captured the call draws fresh
+// noise on every replay.  A captured rollout passes offset = t * step and advance = 0 for its steps and advances the counter
+// once at its end (xa_bump_u64): one launch per step instead of two.
+extern "C" int xa_policy_step_counter_f32(const float* actor_out, int actor_kind, uint64_t seed, uint64_t* offset_dev, uint64_t offset,
+                                          uint64_t advance, float* actions, float* log_probs, float* entropies, int64_t n, int n_actions, xa_stream_t stream) {
   XA_REQUIRE(n > 0 && n_actions > 0, XA_EINVAL, "xa_policy_step_counter_f32: n=%lld n_actions=%d", static_cast<long long>(n), n_actions);
   XA_REQUIRE(actor_out && actions && log_probs && offset_dev, XA_EINVAL, "xa_policy_step_counter_f32: null pointer");
   XA_REQUIRE(xa::aligned(offset_dev, 8), XA_EALIGN, "xa_policy_step_counter_f32: offset_dev must be 8-byte aligned");
   XA_REQUIRE(actor_kind >= XA_ACTOR_LOGITS && actor_kind <= XA_ACTOR_NORMAL, XA_EINVAL, "xa_policy_step_counter_f32: unknown actor_kind %d", actor_kind);
-  PolicyParams p{actor_out, nullptr, seed, 0, offset_dev, actions, log_probs, entropies, n, n_actions};
+  PolicyParams p{actor_out, nullptr, seed, offset, offset_dev, actions, log_probs, entropies, n, n_actions};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int rc = launch_policy(p, actor_kind, s, "xa_policy_step_counter_f32")) return rc;
+  if (advance == 0) return XA_OK;
   bump_u64_kernel<<<1, 1, 0, s>>>(offset_dev, advance);
   return xa::check_launch("xa_policy_step_counter_f32");
 }

@@ -177,10 +177,17 @@ class BatchedSyntheticAtari:
 
     def seed(self, seed=None):
         torch = self.torch
+        self._seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63))
         self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63)))
+        self._gen.manual_seed(self._seed)
         self._pool = torch.randint(0, 256, (self._pool_size,) + self.observation_space.shape, dtype=torch.uint8,
                                    device=self.device, generator=self._gen)
+        # On the GPU a step is ONE kernel (csrc/synth_env.cu) drawing from Philox at (seed, *counter + host offset): the
+        # counter lives in device memory so that a captured rollout draws fresh numbers on every replay.
+        self.native_step = self.device.type == 'cuda'
+        if self.native_step:
+            self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._host_offset = 0
         return [seed]
 
     def _frames(self):
@@ -192,12 +199,50 @@ class BatchedSyntheticAtari:
         return self.states
 
     # everything `step_all` reads and replaces, by attribute name: what a captured rollout (CUDA graph) must find at fixed
-    # addresses on entry and what it hands back on exit; `_gen` is the generator the graph has to register
+    # addresses on entry and what it hands back on exit
     GRAPH_STATE = ('states',)
+
+    # ---- random streams around a captured rollout (agents/a2c.py:_capture_rollout) ----
+    def rng_state(self):
+        state = {'gen': self._gen.get_state()}
+        if self.native_step:
+            state['counter'], state['host_offset'] = int(self._counter.item()), self._host_offset
+        return state
+
+    def set_rng_state(self, state):
+        self._gen.set_state(state['gen'])
+        if self.native_step:
+            self._counter.fill_(state['counter'])
+            self._host_offset = state['host_offset']
+
+    def sync_rng(self):
+        """Fold the host-side step count into the device counter, in stream order: before a capture (the captured steps then
+        count from the counter alone) and as the captured rollout's last node (every replay advances the stream)."""
+        if self.native_step and self._host_offset:
+            from . import ops
+            ops.bump_u64(self._counter, self._host_offset)
+            self._host_offset = 0
+
+    def register_graph(self, graph):
+        if not self.native_step:
+            graph.register_generator_state(self._gen)
+
+    def step_into(self, new_states, rewards, dones, episode_sums=None, sums_log=None):
+        """The native step writing into the caller's tensors (rows of the rollout buffers); `self.states` is updated in place."""
+        from . import ops
+        ops.synth_env_step(self._pool, self.states, new_states, rewards, dones, p_reward=self.p_reward, p_done=self.p_done, seed=self._seed,
+                           counter=self._counter, offset=self._host_offset, episode_sums=episode_sums, sums_log=sums_log)
+        self._host_offset += 1
 
     def step_all(self, actions):
         """-> (new_states [n,84,84,C] uint8, rewards [n] fp32, dones [n] fp32), all on the device."""
         torch = self.torch
+        if self.native_step:
+            new_states, rewards = torch.empty_like(self.states), torch.empty(self.n, dtype=torch.float32, device=self.device)
+            dones = torch.empty_like(rewards)
+            self.states = torch.empty_like(new_states)             # a fresh tensor: callers may still hold the previous states
+            self.step_into(new_states, rewards, dones)
+            return new_states, rewards, dones
         u = torch.rand((3, self.n), device=self.device, generator=self._gen)
         rewards = torch.where(u[0] < self.p_reward, torch.where(u[1] < 0.5, 1.0, -1.0), 0.0)
         dones = (u[2] < self.p_done).float()
@@ -254,6 +299,18 @@ class BatchedCartPole:
         return self.states
 
     GRAPH_STATE = ('state', 't', 'states')       # see BatchedSyntheticAtari.GRAPH_STATE
+
+    def rng_state(self):
+        return {'gen': self._gen.get_state()}
+
+    def set_rng_state(self, state):
+        self._gen.set_state(state['gen'])
+
+    def sync_rng(self):
+        pass
+
+    def register_graph(self, graph):
+        graph.register_generator_state(self._gen)
 
     def step_all(self, actions):
         """-> (new_states [n,4] fp32, rewards [n] fp32 (all ones), dones [n] fp32) on the device."""

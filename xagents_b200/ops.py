@@ -220,10 +220,11 @@ def gather_rows_scaled(src_u8, idx, *, time_major=None, out=None, stream=None):
 
 
 # ------------------------------------------------------------------------------------------ rollout-time policy
-def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0, out=None, stream=None, counter=None):
+def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0, out=None, stream=None, counter=None, advance=None):
     """sample() + log_prob() + entropy() of A2C.get_model_outputs (a2c/agent.py:80-94) for one env step.
     Returns (actions, log_probs, entropies); `out` may hold row views of the rollout buffers.  `counter`: a device int64 [1]
-    holding the Philox offset (read by the kernel, advanced behind it) instead of the host-side `offset` -- for captured graphs."""
+    holding the Philox offset base; the kernel draws at counter + `offset` and the counter is advanced behind it by `advance`
+    (default 2A; 0 = not at all, the caller bumps it once per rollout with `bump_u64`) -- for captured graphs."""
     ao = _dev(actor_out, 'float32')
     n, A = ao.shape[0], ao.shape[-1]
     dev = _device_of(ao)
@@ -236,15 +237,40 @@ def policy_step(actor_out, *, actor_kind='logits', noise=None, seed=0, offset=0,
         ent = torch.empty((n,), dtype=torch.float32, device=dev)
     if counter is not None:
         assert noise is None and counter.dtype == torch.int64 and counter.is_cuda
-        _call(ao, 'xa_policy_step_counter_f32', _ptr(ao), ACTOR_KINDS[actor_kind], int(seed), _tptr(counter), 2 * A, _tptr(actions),
-              _tptr(logp), _tptr(ent), n, A, stream)
-        _count(2)
+        advance = 2 * A if advance is None else int(advance)
+        _call(ao, 'xa_policy_step_counter_f32', _ptr(ao), ACTOR_KINDS[actor_kind], int(seed), _tptr(counter), int(offset), advance,
+              _tptr(actions), _tptr(logp), _tptr(ent), n, A, stream)
+        _count(2 if advance else 1)
         return actions, logp, ent
     nz = _dev(noise, 'float32') if noise is not None else None
     _call(ao, 'xa_policy_step_f32', _ptr(ao), ACTOR_KINDS[actor_kind], _ptr(nz), int(seed), int(offset), _tptr(actions),
               _tptr(logp), _tptr(ent), n, A, stream)
     _count()
     return actions, logp, ent
+
+
+def bump_u64(counter, delta, *, stream=None):
+    """counter[0] += delta in stream order (a device int64 [1]: the Philox offsets a captured rollout reads)."""
+    assert counter.dtype == torch.int64 and counter.is_cuda and counter.numel() == 1
+    _call(_dev(counter), 'xa_bump_u64', _tptr(counter), int(delta), stream)
+    _count()
+
+
+def synth_env_step(pool, states, new_states, rewards, dones, *, p_reward, p_done, seed, counter=None, offset=0, episode_sums=None,
+                   sums_log=None, stream=None):
+    """One step of the device-resident synthetic Atari environments with the step_envs bookkeeping (base.py:408-426) in ONE launch:
+    `new_states` (or None) <- the frames the step returns, `states` <- the frames the environments hold afterwards (post-reset where
+    done), `rewards` / `dones` [n] fp32, `episode_sums` += rewards -> `sums_log`, then cut at dones.  All torch CUDA tensors, written in place."""
+    assert pool.is_cuda and pool.dtype == torch.uint8 and pool.is_contiguous() and states.dtype == torch.uint8 and states.is_contiguous()
+    n = states.shape[0]
+    row_bytes = states[0].numel()
+    assert pool[0].numel() == row_bytes and rewards.numel() == n and dones.numel() == n
+    for t in (new_states, rewards, dones, episode_sums, sums_log):
+        assert t is None or (t.is_cuda and t.is_contiguous() and t.device == states.device)
+    assert rewards.dtype == dones.dtype == torch.float32
+    _call(_dev(states), 'xa_synth_env_step_u8', _tptr(pool), pool.shape[0], row_bytes, _tptr(states), _tptr(new_states), _tptr(rewards), _tptr(dones),
+          _tptr(episode_sums), _tptr(sums_log), n, float(p_reward), float(p_done), int(seed) & (2 ** 64 - 1), _tptr(counter), int(offset), stream)
+    _count()
 
 
 # ------------------------------------------------------------------------------------------ moments + losses
