@@ -342,7 +342,8 @@ int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const vo
  * grad[dest[j]] = sum_{s < splits} src[map[j] + s*split_stride] (0 where map[j] < 0; dest = NULL: grad[j]) with splits /
  * split_stride constant over segments of consecutive j (segment i covers [dest_begin_i, dest_begin_{i+1}); the first
  * starts at 0, the last ends at n).  Enumerate each segment in the order of its sources (map ascending) so that the
- * partial sums are read coalesced.  `wide` segments (many splits) are summed by four lanes per output.
+ * partial sums are read coalesced.  `wide` = lanes per output: 0 one thread, 4 / 8 / 16 / 32 lanes each adding a contiguous
+ * share of the splits, combined by a fixed tree (1 = 4); use 32 for few outputs with hundreds of splits.
  * segments: HOST array. */
 #define XA_MAX_GRAD_SEGMENTS 16
 typedef struct xa_grad_segment_t {

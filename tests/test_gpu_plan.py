@@ -40,7 +40,7 @@ def test_heads_forward_vs_torch(B, A):
     torch.testing.assert_close(critic, ref[:, A], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (100, 3), (8192, 6)])
+@pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (100, 3), (8192, 6), (40001, 6)])
 def test_heads_backward_vs_torch(B, A):
     from xagents_b200 import _ffi
     torch.manual_seed(B + 1)
@@ -50,7 +50,9 @@ def test_heads_backward_vs_torch(B, A):
     wh16 = wh.bfloat16()
     d_actor, d_critic = torch.randn(B, A, device=DEV) / B, torch.randn(B, device=DEV) / B
     blocks = _ffi.lib().xa_heads_backward_blocks(B)
-    assert blocks == -(-B // 64)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rows_per_cta = min(64, max(2, (-(-B // (2 * sms)) + 1) // 2 * 2))       # an even count that keeps every CTA resident (two per SM)
+    assert blocks == -(-B // rows_per_cta)
     partial = torch.full((blocks, 10, 512), float('nan'), device=DEV)
     dh = torch.full((B, 512), float('nan'), device=DEV, dtype=torch.bfloat16)
     _call('xa_heads_backward_bf16', _p(d_actor), _p(d_critic), _p(h), _p(wh16), _p(dh), _p(partial), partial.numel(), B, 512, A, _s())
@@ -99,6 +101,22 @@ def test_grad_finalize_adds_splits_in_order_and_permutes():
     out = torch.full((n,), float('nan'), device=DEV)
     _call('xa_grad_finalize_f32', _p(src), _p(gmap), _p(dest), segs, 3, _p(out), n, _s())
     assert torch.equal(out[dest.long()], grad)
+    # eight lanes per output (few outputs, hundreds of splits: the heads kernel's per-CTA blocks): contiguous eighths of the
+    # splits in order, then ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7))
+    src8 = torch.randn(300 * 100, device=DEV)
+    map8 = torch.randperm(100, device=DEV).int()
+    seg8 = (_ffi.GradSegment * 1)()
+    seg8[0].dest_begin, seg8[0].split_stride, seg8[0].splits, seg8[0].wide = 0, 100, 300, 8
+    got8 = torch.full((100,), float('nan'), device=DEV)
+    _call('xa_grad_finalize_f32', _p(src8), _p(map8), None, seg8, 1, _p(got8), 100, _s())
+    a8 = src8.view(300, 100)[:, map8.long()]
+    parts = []
+    for q in range(8):
+        acc = torch.zeros(100, device=DEV)
+        for k in range(q * 38, min(300, q * 38 + 38)):
+            acc = acc + a8[k]
+        parts.append(acc)
+    assert torch.equal(got8, ((parts[0] + parts[1]) + (parts[2] + parts[3])) + ((parts[4] + parts[5]) + (parts[6] + parts[7])))
 
 
 @pytest.mark.timeout(300)

@@ -129,7 +129,7 @@ class NaturePlan:
                 seg.splits, seg.split_stride = fc_splits, HIDDEN * 3136
             else:                                                  # fcb, aw, ab, cw, cb: per-CTA blocks of the heads kernel
                 seg.splits, seg.split_stride = heads_blocks, (HEAD_ROWS + 2) * HIDDEN
-            seg.wide = int(seg.splits >= 8)
+            seg.wide = 0 if seg.splits < 8 else (8 if seg.splits >= 64 and name not in seg_of and name != 'fcw' else 4)
         net.n_segments = len(order)
 
     # ---- the two calls ------------------------------------------------------------------------------------------

@@ -24,10 +24,12 @@ struct FinalizeParams {
   const int32_t* dest;
   float* grad;
   int64_t n;
-  int n_segments;
-  int64_t wide_total;       // outputs handled by four lanes each
+  int n_segments, n_wide;
+  int64_t wide_slots;       // lane slots of all wide segments (each padded to whole warps)
   xa_grad_segment_t seg[XA_MAX_GRAD_SEGMENTS];
-  int64_t wide_begin[XA_MAX_GRAD_SEGMENTS + 1];   // prefix sums of the wide segments' lengths
+  int32_t wide_seg[XA_MAX_GRAD_SEGMENTS];         // the w-th wide segment's index in seg
+  int64_t wide_begin[XA_MAX_GRAD_SEGMENTS + 1];   // prefix sums of the wide segments' lane slots
+  int64_t seg_len[XA_MAX_GRAD_SEGMENTS];
 };
 
 __device__ __forceinline__ int find_segment(const FinalizeParams& p, int64_t j) {
@@ -37,8 +39,12 @@ __device__ __forceinline__ int find_segment(const FinalizeParams& p, int64_t j) 
   return s;
 }
 
-// blocks [0, narrow_blocks): one thread per output of a segment with few splits; the remaining blocks: four lanes per
-// output of the segments with many splits (each lane a contiguous quarter of the splits, combined by a fixed tree)
+// blocks [0, narrow_blocks): one thread per output of a segment with few splits; the remaining blocks: `wide` (4, 8, 16 or 32)
+// lanes per output of the segments with many splits -- each lane a contiguous share of the splits, combined by a fixed
+// shuffle tree.  A segment's lane slots are padded to whole warps, so a warp works on one segment with one lane count.
+// More lanes are for segments with few outputs and very many splits (the heads kernel's ~300 per-CTA blocks: at four lanes the
+// 74 loads per lane of those 4 600 outputs were the tail of the whole kernel); lanes of one output read different splits, so a
+// warp-wide load touches 32 / lanes consecutive outputs per sector: eight lanes keep half of every sector useful.
 __global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_constant__ FinalizeParams p, int narrow_blocks) {
   if (static_cast<int>(blockIdx.x) < narrow_blocks) {
     for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < p.n; j += static_cast<int64_t>(narrow_blocks) * kThreads) {
@@ -54,34 +60,31 @@ __global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_co
     }
     return;
   }
-  const int part = threadIdx.x & 3;
-  const int64_t first = (static_cast<int64_t>(blockIdx.x - narrow_blocks) * kThreads + threadIdx.x) >> 2;
-  const int64_t step = (static_cast<int64_t>(gridDim.x - narrow_blocks) * kThreads) >> 2;
-  const int64_t padded = ((p.wide_total + 7) / 8) * 8;   // whole warps reach the shuffles together
-  for (int64_t i = first; i < padded; i += step) {
+  const int64_t first = static_cast<int64_t>(blockIdx.x - narrow_blocks) * kThreads + threadIdx.x;
+  const int64_t step = static_cast<int64_t>(gridDim.x - narrow_blocks) * kThreads;
+  for (int64_t t = first; t < p.wide_slots; t += step) {   // wide_slots is a multiple of 32: whole warps reach the shuffles
+    int w = 0;
+    while (t >= p.wide_begin[w + 1]) ++w;
+    const int si = p.wide_seg[w];
+    const xa_grad_segment_t& sg = p.seg[si];
+    const int lanes = sg.wide;
+    const int64_t local = t - p.wide_begin[w];
+    const int64_t i = local / lanes;
+    const int part = static_cast<int>(local - i * lanes);
     float acc = 0.0f;
     int64_t j = -1;
-    if (i < p.wide_total) {
-      int w = 0;
-      while (i >= p.wide_begin[w + 1]) ++w;
-      // the w-th wide segment
-      int s = 0, seen = -1;
-#pragma unroll 1
-      for (; s < p.n_segments; ++s) {
-        if (p.seg[s].wide && ++seen == w) break;
-      }
-      const xa_grad_segment_t& sg = p.seg[s];
-      j = sg.dest_begin + (i - p.wide_begin[w]);
+    if (i < p.seg_len[si]) {
+      j = sg.dest_begin + i;
       const int32_t m = p.map[j];
       if (m >= 0) {
-        const int per = (sg.splits + 3) / 4;
+        const int per = (sg.splits + lanes - 1) / lanes;
         const int k0 = part * per, k1 = k0 + per < sg.splits ? k0 + per : sg.splits;
         const float* src = p.src + m;
-        for (int k = k0; k < k1; ++k) acc += src[k * sg.split_stride];
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) acc += src[k * sg.split_stride];   // loads do not depend on acc: eight in flight
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    for (int o = 1; o < lanes; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // ((q0 + q1) + (q2 + q3)) + ...
     if (part == 0 && j >= 0) p.grad[p.dest != nullptr ? p.dest[j] : j] = acc;
   }
 }
@@ -96,30 +99,33 @@ extern "C" int xa_grad_finalize_f32(const float* src, const int32_t* map, const 
              static_cast<long long>(n), n_segments, XA_MAX_GRAD_SEGMENTS);
   FinalizeParams p{};
   p.src = src, p.map = map, p.dest = dest, p.grad = grad, p.n = n, p.n_segments = n_segments;
-  int64_t wide = 0, narrow = 0;
+  int64_t slots = 0;
   int n_wide = 0;
   for (int s = 0; s < n_segments; ++s) {
     const xa_grad_segment_t& sg = segments[s];   // host memory
     const int64_t end = s + 1 < n_segments ? segments[s + 1].dest_begin : n;
     XA_REQUIRE(sg.dest_begin >= 0 && sg.dest_begin <= end && (s > 0 || sg.dest_begin == 0) && sg.splits >= 1 && sg.split_stride >= 0, XA_EINVAL,
                "%s: segment %d (dest_begin=%lld splits=%d) out of order or empty", what, s, static_cast<long long>(sg.dest_begin), sg.splits);
+    XA_REQUIRE(sg.wide == 0 || sg.wide == 1 || sg.wide == 4 || sg.wide == 8 || sg.wide == 16 || sg.wide == 32, XA_EINVAL,
+               "%s: segment %d: wide=%d (lanes per output: 0, 4, 8, 16 or 32; 1 = 4)", what, s, sg.wide);
     p.seg[s] = sg;
+    p.seg_len[s] = end - sg.dest_begin;
     if (sg.wide) {
-      p.wide_begin[n_wide++] = wide;
-      wide += end - sg.dest_begin;
-    } else {
-      narrow += end - sg.dest_begin;
+      if (sg.wide == 1) p.seg[s].wide = 4;
+      p.wide_seg[n_wide] = s;
+      p.wide_begin[n_wide++] = slots;
+      slots += (((end - sg.dest_begin) * p.seg[s].wide + 31) / 32) * 32;
     }
   }
-  p.wide_begin[n_wide] = wide;
+  p.n_wide = n_wide;
+  p.wide_begin[n_wide] = slots;
   for (int w = n_wide + 1; w <= XA_MAX_GRAD_SEGMENTS; ++w) p.wide_begin[w] = INT64_MAX;
-  p.wide_total = wide;
+  p.wide_slots = slots;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   int64_t nb = (n + kThreads - 1) / kThreads;
   if (nb > 8 * sms) nb = 8 * sms;
-  int64_t wb = (wide * 4 + kThreads - 1) / kThreads;
+  int64_t wb = (slots + kThreads - 1) / kThreads;
   if (wb > 16 * sms) wb = 16 * sms;
-  (void)narrow;
   grad_finalize_kernel<<<static_cast<unsigned>(nb + wb), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<int>(nb));
   return xa::check_launch(what);
 }

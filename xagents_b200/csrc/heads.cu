@@ -19,8 +19,9 @@ constexpr int kHidden = 512;
 constexpr int kRows = 8;           // stacked head rows: n_actions + 1 <= 8 (the rest are zero)
 constexpr int kFwdThreads = 256;
 constexpr int kBwdThreads = 256;
-constexpr int kBwdRowsPerCta = 64;
-constexpr int kChunkThreads = kHidden / 8;   // 64 threads cover one row of h with 16-byte loads
+constexpr int kBwdGroups = 2;                  // row groups of a backward CTA
+constexpr int kBwdMaxRowsPerCta = 64;
+constexpr int kChunkThreads = kHidden / 4;     // 128 threads cover one row of h with 8-byte loads
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -30,13 +31,21 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[2 * i] = t.x, f[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y;
+}
 
-// One warp per frame: lane l holds columns [8l, 8l+8) and [256 + 8l, ...) of h; the stacked head matrix sits in shared
-// memory as fp32 (16 KB, conflict-free 32-byte reads); R dot products are reduced with a butterfly.
+// One warp per PAIR of frames: lane l holds columns [128 j + 4 l, 128 j + 4 l + 4), j = 0..3, of h (8-byte loads, a warp
+// reads 256 contiguous bytes); the stacked head matrix sits in shared memory as fp32 and is read as 16-byte vectors at
+// stride 16 bytes across the lanes (conflict-free: the first version's 32-byte lane stride made every read a 2-way
+// conflict, and with 32 vector reads per frame the kernel was bound by shared-memory wavefronts -- ncu: 2.7 M of them, 10 us),
+// each weight vector feeding both frames; R dot products are reduced with a butterfly.
 __global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ wh,
                                                                   const float* __restrict__ bh, float* __restrict__ actor,
                                                                   float* __restrict__ critic, int batch, int n_actions) {
-  __shared__ float s_w[kRows][kHidden];
+  __shared__ __align__(16) float s_w[kRows][kHidden];
   for (int i = threadIdx.x; i < kRows * kHidden / 8; i += kFwdThreads) {   // 512 16-byte pieces, two per thread, both in flight
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(wh) + i), f);
@@ -48,55 +57,63 @@ __global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_b
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = gridDim.x * (kFwdThreads / 32);
   const float my_bias = lane < kRows && lane <= n_actions ? bh[lane] : 0.0f;
-  for (int row = blockIdx.x * (kFwdThreads / 32) + warp; row < batch; row += warps) {
-    const uint4* hr = reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * kHidden);
-    const uint4 v0 = __ldg(hr + lane), v1 = __ldg(hr + 32 + lane);
-    float x[16];
-    unpack8(v0, *reinterpret_cast<float(*)[8]>(x));
-    unpack8(v1, *reinterpret_cast<float(*)[8]>(x + 8));
-    float acc[kRows];
+  for (int row = 2 * (blockIdx.x * (kFwdThreads / 32) + warp); row < batch; row += 2 * warps) {
+    const bool two = row + 1 < batch;
+    const uint2* h0 = reinterpret_cast<const uint2*>(h + static_cast<int64_t>(row) * kHidden);
+    const uint2* h1 = reinterpret_cast<const uint2*>(h + static_cast<int64_t>(row + (two ? 1 : 0)) * kHidden);
+    uint2 v0[4], v1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v0[j] = __ldg(h0 + 32 * j + lane), v1[j] = __ldg(h1 + 32 * j + lane);
+    float x0[4][4], x1[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack4(v0[j], x0[j]), unpack4(v1[j], x1[j]);
+    float acc0[kRows], acc1[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const float4* w0 = reinterpret_cast<const float4*>(&s_w[r][8 * lane]);
-      const float4* w1 = reinterpret_cast<const float4*>(&s_w[r][256 + 8 * lane]);
-      const float4 a = w0[0], b = w0[1], c = w1[0], d = w1[1];
-      float s = x[0] * a.x;
-      s = fmaf(x[1], a.y, s), s = fmaf(x[2], a.z, s), s = fmaf(x[3], a.w, s);
-      s = fmaf(x[4], b.x, s), s = fmaf(x[5], b.y, s), s = fmaf(x[6], b.z, s), s = fmaf(x[7], b.w, s);
-      s = fmaf(x[8], c.x, s), s = fmaf(x[9], c.y, s), s = fmaf(x[10], c.z, s), s = fmaf(x[11], c.w, s);
-      s = fmaf(x[12], d.x, s), s = fmaf(x[13], d.y, s), s = fmaf(x[14], d.z, s), s = fmaf(x[15], d.w, s);
-      acc[r] = s;
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // columns in ascending order within the lane, as before
+        const float4 w = *reinterpret_cast<const float4*>(&s_w[r][128 * j + 4 * lane]);
+        s0 = fmaf(x0[j][0], w.x, s0), s0 = fmaf(x0[j][1], w.y, s0), s0 = fmaf(x0[j][2], w.z, s0), s0 = fmaf(x0[j][3], w.w, s0);
+        s1 = fmaf(x1[j][0], w.x, s1), s1 = fmaf(x1[j][1], w.y, s1), s1 = fmaf(x1[j][2], w.z, s1), s1 = fmaf(x1[j][3], w.w, s1);
+      }
+      acc0[r] = s0, acc1[r] = s1;
     }
-    float mine = 0.0f;
+    float mine0 = 0.0f, mine1 = 0.0f;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      float s = acc[r];
+      float s0 = acc0[r], s1 = acc1[r];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == r) mine = s;
+      for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o), s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      if (lane == r) mine0 = s0, mine1 = s1;
     }
-    if (lane < n_actions)
-      actor[static_cast<int64_t>(row) * n_actions + lane] = mine + my_bias;
-    else if (lane == n_actions)
-      critic[row] = mine + my_bias;
+    if (lane < n_actions) {
+      actor[static_cast<int64_t>(row) * n_actions + lane] = mine0 + my_bias;
+      if (two) actor[static_cast<int64_t>(row + 1) * n_actions + lane] = mine1 + my_bias;
+    } else if (lane == n_actions) {
+      critic[row] = mine0 + my_bias;
+      if (two) critic[row + 1] = mine1 + my_bias;
+    }
   }
 }
 
-// 256 threads = 4 row groups x 64 column chunks (8 columns each); a CTA owns 64 consecutive frames, row group g the frames
-// g, g+4, ...  Per frame and thread: 8 x 8 FMAs for dh, 8 x 8 for dW_heads; the four row groups are then added in order
+// 256 threads = 2 row groups x 128 column chunks (4 columns each); a CTA owns `rows_per_cta` consecutive frames (chosen so that
+// all CTAs are resident at once: two per SM), row group g the frames g, g+2, ...  Per frame and thread: 8 x 4 FMAs for dh,
+// 8 x 4 for dW_heads.  (The first version gave a thread 8 columns of 16 frames: 1024 warps in all, 7 per SM, 170 registers --
+// bound by instruction issue at that occupancy, 14 us for 16 MB of traffic.)  The two row groups are then added in order
 // through shared memory and the CTA writes one partial block [kRows + 2, 512]:
 //   rows 0..7  dW_heads        row 8  db_fc (column sums of the bf16-rounded dh, what the FC weight gradient also sees)
 //   row 9      db_heads in its first 8 entries
-__global__ void __launch_bounds__(kBwdThreads) heads_backward_kernel(const float* __restrict__ d_actor, const float* __restrict__ d_critic,
-                                                                   const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ wh,
-                                                                   __nv_bfloat16* __restrict__ dh, float* __restrict__ partial, int batch,
-                                                                   int n_actions) {
-  __shared__ float s_d[kBwdRowsPerCta][kRows];
-  __shared__ float s_red[kRows + 1][8][kChunkThreads];   // one row group's accumulators at a time (18 KB)
+__global__ void __launch_bounds__(kBwdThreads, 2) heads_backward_kernel(const float* __restrict__ d_actor, const float* __restrict__ d_critic,
+                                                                      const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ wh,
+                                                                      __nv_bfloat16* __restrict__ dh, float* __restrict__ partial, int batch,
+                                                                      int n_actions, int rows_per_cta) {
+  __shared__ __align__(16) float s_d[kBwdMaxRowsPerCta][kRows];
+  __shared__ float s_red[kRows + 1][4][kChunkThreads];   // row group 1's accumulators (18 KB)
   const int chunk = threadIdx.x % kChunkThreads, grp = threadIdx.x / kChunkThreads;
-  const int row0 = blockIdx.x * kBwdRowsPerCta;
-  const int rows = min(kBwdRowsPerCta, batch - row0);
-  for (int i = threadIdx.x; i < kBwdRowsPerCta * kRows; i += kBwdThreads) {
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, batch - row0);
+  for (int i = threadIdx.x; i < rows_per_cta * kRows; i += kBwdThreads) {
     const int r = i / kRows, c = i % kRows;
     float v = 0.0f;
     if (r < rows) {
@@ -107,37 +124,37 @@ __global__ void __launch_bounds__(kBwdThreads) heads_backward_kernel(const float
     }
     s_d[r][c] = v;
   }
-  float w[kRows][8];
+  float w[kRows][4];
 #pragma unroll
-  for (int r = 0; r < kRows; ++r) unpack8(__ldg(reinterpret_cast<const uint4*>(wh + r * kHidden) + chunk), w[r]);
-  float dw[kRows][8], dbf[8];
+  for (int r = 0; r < kRows; ++r) unpack4(__ldg(reinterpret_cast<const uint2*>(wh + r * kHidden) + chunk), w[r]);
+  float dw[kRows][4], dbf[4];
 #pragma unroll
   for (int r = 0; r < kRows; ++r)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dw[r][e] = 0.0f;
+    for (int e = 0; e < 4; ++e) dw[r][e] = 0.0f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) dbf[e] = 0.0f;
+  for (int e = 0; e < 4; ++e) dbf[e] = 0.0f;
   __syncthreads();
 
-  constexpr int kPerGroup = kBwdRowsPerCta / 4;   // 16 frames per row group, loads issued four at a time
-  for (int i0 = 0; i0 < kPerGroup; i0 += 4) {
-    uint4 hv[4];
+  const int per_group = (rows_per_cta + kBwdGroups - 1) / kBwdGroups;   // loads issued four at a time
+  for (int i0 = 0; i0 < per_group; i0 += 4) {
+    uint2 hv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = (i0 + u) * 4 + grp;
-      hv[u] = r < rows ? __ldg(reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row0 + r) * kHidden) + chunk) : make_uint4(0, 0, 0, 0);
+      const int r = (i0 + u) * kBwdGroups + grp;
+      hv[u] = r < rows ? __ldg(reinterpret_cast<const uint2*>(h + static_cast<int64_t>(row0 + r) * kHidden) + chunk) : make_uint2(0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = (i0 + u) * 4 + grp;
+      const int r = (i0 + u) * kBwdGroups + grp;
       if (r >= rows) continue;
-      float x[8], d[kRows];
-      unpack8(hv[u], x);
+      float x[4], d[kRows];
+      unpack4(hv[u], x);
+      const float4 d_lo = *reinterpret_cast<const float4*>(&s_d[r][0]), d_hi = *reinterpret_cast<const float4*>(&s_d[r][4]);
+      d[0] = d_lo.x, d[1] = d_lo.y, d[2] = d_lo.z, d[3] = d_lo.w, d[4] = d_hi.x, d[5] = d_hi.y, d[6] = d_hi.z, d[7] = d_hi.w;
+      __nv_bfloat162 out[2];
 #pragma unroll
-      for (int q = 0; q < kRows; ++q) d[q] = s_d[r][q];
-      __nv_bfloat162 out[4];
-#pragma unroll
-      for (int e = 0; e < 8; e += 2) {
+      for (int e = 0; e < 4; e += 2) {
         float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
         for (int q = 0; q < kRows; ++q) s0 = fmaf(d[q], w[q][e], s0), s1 = fmaf(d[q], w[q][e + 1], s1);
@@ -147,57 +164,57 @@ __global__ void __launch_bounds__(kBwdThreads) heads_backward_kernel(const float
         const float2 back = __bfloat1622float2(out[e / 2]);
         dbf[e] += back.x, dbf[e + 1] += back.y;
       }
-      reinterpret_cast<uint4*>(dh + static_cast<int64_t>(row0 + r) * kHidden)[chunk] = *reinterpret_cast<uint4*>(out);
+      reinterpret_cast<uint2*>(dh + static_cast<int64_t>(row0 + r) * kHidden)[chunk] = *reinterpret_cast<uint2*>(out);
 #pragma unroll
       for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dw[q][e] = fmaf(d[q], x[e], dw[q][e]);
+        for (int e = 0; e < 4; ++e) dw[q][e] = fmaf(d[q], x[e], dw[q][e]);
     }
   }
-  // row groups 1..3 are added onto group 0 in order (fixed association: the result does not depend on timing)
-  for (int g = 1; g < 4; ++g) {
-    __syncthreads();
-    if (grp == g) {
+  // row group 1 is added onto group 0 (fixed association: the result does not depend on timing)
+  if (grp == 1) {
 #pragma unroll
-      for (int q = 0; q < kRows; ++q)
+    for (int q = 0; q < kRows; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s_red[q][e][chunk] = dw[q][e];
+      for (int e = 0; e < 4; ++e) s_red[q][e][chunk] = dw[q][e];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s_red[kRows][e][chunk] = dbf[e];
-    }
-    __syncthreads();
-    if (grp == 0) {
-#pragma unroll
-      for (int q = 0; q < kRows; ++q)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dw[q][e] += s_red[q][e][chunk];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dbf[e] += s_red[kRows][e][chunk];
-    }
+    for (int e = 0; e < 4; ++e) s_red[kRows][e][chunk] = dbf[e];
   }
+  __syncthreads();
   float* mine = partial + static_cast<int64_t>(blockIdx.x) * (kRows + 2) * kHidden;
   if (grp == 0) {
 #pragma unroll
-    for (int q = 0; q < kRows; ++q) {
-      float4* dst = reinterpret_cast<float4*>(mine + q * kHidden + 8 * chunk);
-      dst[0] = make_float4(dw[q][0], dw[q][1], dw[q][2], dw[q][3]);
-      dst[1] = make_float4(dw[q][4], dw[q][5], dw[q][6], dw[q][7]);
-    }
-    float4* dst = reinterpret_cast<float4*>(mine + kRows * kHidden + 8 * chunk);
-    dst[0] = make_float4(dbf[0], dbf[1], dbf[2], dbf[3]);
-    dst[1] = make_float4(dbf[4], dbf[5], dbf[6], dbf[7]);
-  } else if (grp == 1 && chunk < kRows) {   // db_heads[c] = sum of d_out[:, c] over this CTA's frames, in frame order
+    for (int q = 0; q < kRows; ++q)
+      *reinterpret_cast<float4*>(mine + q * kHidden + 4 * chunk) =
+          make_float4(dw[q][0] + s_red[q][0][chunk], dw[q][1] + s_red[q][1][chunk], dw[q][2] + s_red[q][2][chunk], dw[q][3] + s_red[q][3][chunk]);
+    *reinterpret_cast<float4*>(mine + kRows * kHidden + 4 * chunk) = make_float4(
+        dbf[0] + s_red[kRows][0][chunk], dbf[1] + s_red[kRows][1][chunk], dbf[2] + s_red[kRows][2][chunk], dbf[3] + s_red[kRows][3][chunk]);
+  } else if (chunk < kRows) {   // db_heads[c] = sum of d_out[:, c] over this CTA's frames, in frame order
     float s = 0.0f;
     for (int r = 0; r < rows; ++r) s += s_d[r][chunk];
     mine[(kRows + 1) * kHidden + chunk] = s;
   }
 }
 
+// frames per backward CTA: all CTAs resident at once (two per SM), an even count of at most kBwdMaxRowsPerCta
+int bwd_rows_per_cta(int batch) {
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  int rows = (batch + 2 * sms - 1) / (2 * sms);
+  rows = (rows + 1) & ~1;
+  if (rows < 2) rows = 2;
+  if (rows > kBwdMaxRowsPerCta) rows = kBwdMaxRowsPerCta;
+  return rows;
+}
+
 }  // namespace
 
 extern "C" {
 
-int xa_heads_backward_blocks(int batch) { return batch > 0 ? (batch + kBwdRowsPerCta - 1) / kBwdRowsPerCta : 0; }
+int xa_heads_backward_blocks(int batch) {
+  if (batch <= 0) return 0;
+  const int rows = bwd_rows_per_cta(batch);
+  return (batch + rows - 1) / rows;
+}
 
 int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float* actor, float* critic, int batch, int hidden, int n_actions,
                           xa_stream_t stream) {
@@ -207,8 +224,8 @@ int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float*
              "%s: batch=%d hidden=%d (must be %d) n_actions=%d (at most %d)", what, batch, hidden, kHidden, n_actions, kRows - 1);
   XA_REQUIRE(xa::aligned(h, 16) && xa::aligned(wh, 16), XA_EALIGN, "%s: h and wh must be 16-byte aligned", what);
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  const int want = (batch + kFwdThreads / 32 - 1) / (kFwdThreads / 32);
-  const int grid = want < 8 * sms ? want : 8 * sms;  // one frame per warp up to a full wave of 8 CTAs per SM: the kernel is latency-bound
+  const int want = (batch + 2 * (kFwdThreads / 32) - 1) / (2 * (kFwdThreads / 32));
+  const int grid = want < 4 * sms ? want : 4 * sms;  // a pair of frames per warp, up to four CTAs per SM
   heads_forward_kernel<<<grid, kFwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h),
                                                                                    static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch,
                                                                                    n_actions);
@@ -227,7 +244,7 @@ int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const vo
   XA_REQUIRE(partial_floats >= static_cast<int64_t>(grid) * (kRows + 2) * kHidden, XA_ENOSPACE, "%s: partial buffer too small", what);
   heads_backward_kernel<<<grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       d_actor, d_critic, static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(wh), static_cast<__nv_bfloat16*>(dh), partial,
-      batch, n_actions);
+      batch, n_actions, bwd_rows_per_cta(batch));
   return xa::check_launch(what);
 }
 
