@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument('--staging', type=int, default=2)
     ap.add_argument('--static-gather', action='store_true', help='deal the gather items statically instead of through a work counter')
     ap.add_argument('--late-fork', action='store_true', help='start the data stream after GAE + moments instead of beside them')
+    ap.add_argument('--obs-gather', default='auto', choices=['auto', 'on', 'off'],
+                    help='off: the network reads the rollout through the permutation (no frame gather); auto: off where the network can (nature-tc)')
     ap.add_argument('--sync', default='auto', choices=['auto', 'event', 'progress', 'progress-memop'], help='how losses learn their minibatch is staged (hotpath.PPOHotPath)')
     ap.add_argument('--gather-chunk', type=int, default=None, help='minibatches per gather launch (default: tapered schedule)')
     ap.add_argument('--gather-schedule', default=None, help='explicit launch schedule, e.g. 4,4,4,3,1')
@@ -389,6 +391,8 @@ def build_ppo(args, dev, comm, E, T, shape, dtype, A, n_params, rank, c1, networ
         opts['gather_chunk'] = [int(x) for x in args.gather_schedule.split(',')]
     elif args.gather_chunk:
         opts['gather_chunk'] = args.gather_chunk
+    if args.obs_gather != 'auto':
+        opts['obs_gather'] = args.obs_gather == 'on'
     agent.pipeline_options = opts
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -561,7 +565,7 @@ def run_ppo(args):
     agent, net, hp, host, perms, last_values = build_ppo(args, dev, comm, E, T, shape, dtype, A, n_params, rank, c1, args.network)
     N, B, K, M = hp.N, hp.B, hp.K, hp.M
     stream = torch.cuda.current_stream(dev)
-    n_gathers = hp.n_groups
+    n_gathers = hp.n_groups if hp.obs_gather else 0
 
     # the sampler starts before the warm-up (nvidia-smi, the fallback, takes ~100 ms to start); with NVML only the samples
     # taken inside the timed region are reported
@@ -723,8 +727,12 @@ def run_ppo(args):
     if rank != 0:
         return
     peak, peak_src = hbm_peak()
-    g_ms = statistics.mean(gather_ms)
-    achieved = alg['gather_per_launch'] / (g_ms * 1e-3) / 1e9
+    hp_obs_gather = bool(gather_ms)
+    if not gather_ms:           # the network fetched the frames through the permutation: there is no gather launch to rate
+        g_ms, achieved = None, 0.0
+    else:
+        g_ms = statistics.mean(gather_ms)
+        achieved = alg['gather_per_launch'] / (g_ms * 1e-3) / 1e9
     traffic, traffic_source = None, None
     try:
         with open(os.path.join(ROOT, 'profiles', 'gather_traffic.json')) as f:
@@ -748,7 +756,8 @@ def run_ppo(args):
         'config': {'workload': desc, 'n_envs_per_gpu': E, 'samples_per_step_per_gpu': N, 'mini_batch_size_per_gpu': B,
                    'api': 'xagents_b200.agents.PPO.train_step() (the drop-in agent; run_ppo_epochs drives hotpath.PPOHotPath in place '
                           'over the agent\'s rollout buffers), rollout resident in HBM',
-                   'gather_mode': args.gather_mode, 'minibatches_per_gather_launch': info['group_sizes'],
+                   'gather_mode': args.gather_mode if hp_obs_gather else 'none: the first layer of the network reads every frame through the permutation (xa_nature_cnn_forward_indexed)',
+                   'minibatches_per_gather_launch': info['group_sizes'] if hp_obs_gather else [],
                    'streams': 'gathers on a data stream, GAE/moments/losses/optimiser on the compute stream' if info['overlap'] else 'single stream',
                    'scalar_fields': 'read through the permutation inside the loss',
                    'after_each_loss': ('nothing (--no-optimizer)' if args.no_optimizer else
@@ -766,7 +775,7 @@ def run_ppo(args):
                                    f'C1 = {c1}: gradients of {info["n_params"]} fp32 parameters per minibatch; C2 = 1 NCCL all-gather of advantage '
                                    f'moments per step')},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'traffic_source': traffic_source, 'meaningful': meaningful,
+                     'traffic': traffic, 'traffic_source': traffic_source, 'meaningful': meaningful and hp_obs_gather,
                      'kernel': 'gather_bulk_kernel' if (args.gather_mode != 'vector' and dtype == 'uint8') else 'gather_vector_kernel',
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg['gather_per_launch'],
                      'avg_launch_ms': g_ms, 'launches_timed': len(gather_ms),

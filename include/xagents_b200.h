@@ -275,6 +275,14 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
  * xa_space_to_depth_u8_bf16 followed by xa_conv2d_nhwc_bf16. */
 int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch,
                           int height, int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream);
+/* The same layer on the `batch` frames frames[frame_idx[0 .. batch)] of a store of n_frames frames, read through the
+ * permutation by per-frame TMA bulk copies: get_mini_batches' tf.gather of the states (xagents/ppo/agent.py:139-155) folded
+ * into the layer -- the gathered minibatch never exists in HBM.  n_steps > 0: ids are env-major sample ids of a time-major
+ * [n_steps, n_envs] rollout (row = (id % n_steps) * n_envs + id / n_steps, xagents/base.py:559-564); ids must be in range.
+ * Bit-identical to xa_gather_rows followed by xa_conv2d_u8_s2d_bf16. */
+int xa_conv2d_u8_s2d_bf16_indexed(const uint8_t* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps, int n_envs,
+                                  const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height,
+                                  int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream);
 
 /* uint8 NHWC frames -> bf16 (optionally /255, xagents/base.py:505-506) rearranged block x block -> channels:
  * dst[b, y/s, x/s, (y%s, x%s, c)]. */
@@ -384,6 +392,11 @@ typedef struct xa_nature_cnn_t {
   int64_t n_grad;
 } xa_nature_cnn_t;
 int xa_nature_cnn_forward(const xa_nature_cnn_t* net, const void* frames, int frames_s2d, xa_stream_t stream);
+/* forward on the minibatch frames[frame_idx[0 .. batch)] of a frame store [n_frames, 84, 84, 4] uint8 without gathering it: the
+ * tf.gather of the states in get_mini_batches (xagents/ppo/agent.py:139-155) folded into the first layer (ids as in
+ * xa_gather_rows: env-major sample ids of a time-major [n_steps, n_envs] rollout when n_steps > 0, plain rows otherwise). */
+int xa_nature_cnn_forward_indexed(const xa_nature_cnn_t* net, const void* frames, int64_t n_frames,
+                                  const int32_t* frame_idx, int n_steps, int n_envs, xa_stream_t stream);
 int xa_nature_cnn_backward(const xa_nature_cnn_t* net, const void* frames_s2d_or_null, const float* d_actor,
                            const float* d_critic, float* flat_grad, xa_stream_t stream);
 

@@ -116,3 +116,11 @@ print(f'first layer straight from uint8 frames at B={B}: {t_u8:.0f} us (space-to
 x1_out = torch.empty((B, 21, 21, 64), dtype=torch.bfloat16, device=dev)
 t_u8s = timeit(lambda: ops.conv2d_u8_s2d_bf16(x, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True, x_s2d_out=x1_out), 20)
 print(f'... and also storing the bf16 space-to-depth tensor for the backward pass: {t_u8s:.0f} us')
+# ... reading the minibatch through a permutation of a 32768-frame rollout (the gather folded into the layer)
+store = torch.randint(0, 256, (128 * 256, 84, 84, 4), dtype=torch.uint8, device=dev)
+perm = torch.randperm(128 * 256, device=dev)[:B].to(torch.int32)
+t_idx = timeit(lambda: ops.conv2d_u8_s2d_bf16(store, tc.w1, 2, 2, bias=tc.b1, relu=True, out_s2d=True, x_s2d_out=x1_out, idx=perm, time_major=(128, 256)), 20)
+mb = torch.empty((B, 84, 84, 4), dtype=torch.uint8, device=dev)
+t_gather = timeit(lambda: ops.gather_rows(store.view(128, 256, 84, 84, 4), perm, out=mb, time_major=(128, 256)), 20)
+print(f'... through a permutation of a 32768-frame rollout (frames fetched by id, no gathered copy): {t_idx:.0f} us; '
+      f'the gather it replaces: {t_gather:.0f} us + {t_u8s:.0f} us')

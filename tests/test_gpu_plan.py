@@ -219,3 +219,30 @@ def test_first_layer_from_uint8_frames_is_bit_identical_to_space_to_depth_then_c
         xf = torch.full_like(x[:2], fill)
         assert torch.equal(ops.conv2d_u8_s2d_bf16(xf, w, 2, 2, bias=bias, relu=False).view(torch.int16),
                            ops.conv2d_nhwc_bf16(ops.space_to_depth_u8_bf16(xf, 4), w, 2, 2, bias=bias, relu=False).view(torch.int16))
+
+
+@pytest.mark.parametrize('B,T,E', [(1, 0, 0), (37, 0, 0), (256, 8, 40), (1000, 16, 64), (2048, 128, 16)])
+def test_first_layer_reads_the_minibatch_through_the_permutation(B, T, E):
+    """xa_conv2d_u8_s2d_bf16_indexed: the tf.gather of the states (ppo/agent.py:139-155) folded into the first layer -- per-frame
+    TMA bulk copies addressed through the ids -- is bit-identical to gathering the frames and running the layer on the copy:
+    outputs and the stored space-to-depth tensor, plain row ids and env-major sample ids of a time-major rollout, duplicates."""
+    from xagents_b200 import ops
+    torch.manual_seed(B + 3)
+    n_frames = T * E if T else 300
+    store = torch.randint(0, 256, (n_frames, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    idx = torch.randint(0, n_frames, (B,), dtype=torch.int32, device=DEV)      # with repetitions
+    idx[0], idx[-1] = n_frames - 1, 0
+    rows = ((idx % T) * E + idx // T).long() if T else idx.long()             # base.py:559-564
+    w = (torch.randn(32, 256, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(32, device=DEV) * 0.1
+    want_x1 = torch.empty((B, 21, 21, 64), dtype=torch.bfloat16, device=DEV)
+    want = ops.conv2d_u8_s2d_bf16(store[rows].contiguous(), w, 2, 2, bias=bias, relu=True, out_s2d=True, x_s2d_out=want_x1)
+    x1 = torch.full((B, 21, 21, 64), float('nan'), dtype=torch.bfloat16, device=DEV)
+    got = ops.conv2d_u8_s2d_bf16(store, w, 2, 2, bias=bias, relu=True, out_s2d=True, x_s2d_out=x1, idx=idx,
+                                 time_major=(T, E) if T else None)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and torch.equal(got.view(torch.int16), want.view(torch.int16))
+    assert torch.equal(x1.view(torch.int16), want_x1.view(torch.int16))
+    if T:
+        with pytest.raises(Exception, match='not the number of stored frames'):
+            ops.conv2d_u8_s2d_bf16(store, w, 2, 2, idx=idx, time_major=(T + 1, E))

@@ -419,3 +419,40 @@ def test_fused_rollout_steps_equal_the_generic_loop(network):
         assert torch.equal(f.get_states(), g.get_states()) and torch.equal(f.get_dones(), g.get_dones())
         assert f.steps == g.steps == (rollout + 1) * T * E and f.games == g.games and list(f.total_rewards) == list(g.total_rewards)
     assert f.games > 0
+
+
+@pytest.mark.timeout(300)
+def test_ppo_without_a_frame_gather_equals_ppo_with_it():
+    """PPO.run_ppo_epochs with a network whose first layer fetches every frame through the permutation
+    (`TorchModel.reads_through_permutation`: PPOHotPath(obs_gather=False), no staged copy of the minibatches) against the
+    same agent with the gather launch + the same network on the staged rows: identical weights and loss scalars."""
+    from xagents_b200 import feeds
+    from xagents_b200.agents import PPO, NatureCnnTc, TorchModel
+    T, E, A = 16, 24, 6
+    results = []
+    for gather in (False, True):
+        torch.manual_seed(11)
+        envs = feeds.FedEnvs(E, (84, 84, 4), torch.uint8, A, device=DEV)
+        net = TorchModel(NatureCnnTc(4, A).cuda())
+        assert net.reads_through_permutation
+        agent = PPO(envs, net, n_steps=T, mini_batches=3, ppo_epochs=2, quiet=True, seed=5, device=DEV)
+        agent.pipeline_options = dict(obs_gather=gather)
+        gen = torch.Generator(device=DEV)
+        gen.manual_seed(2)
+        agent.ro_states.copy_(torch.randint(0, 256, agent.ro_states.shape, dtype=torch.uint8, device=DEV, generator=gen))
+        for name, scale in (('ro_rewards', 1.0), ('ro_values', 0.5), ('ro_log_probs', 0.3)):
+            getattr(agent, name).copy_(torch.randn(getattr(agent, name).shape, device=DEV, generator=gen) * scale)
+        agent.ro_log_probs.abs_().neg_()
+        agent.ro_dones.copy_((torch.rand(agent.ro_dones.shape, device=DEV, generator=gen) < 0.1).float())
+        agent.ro_actions.copy_(torch.randint(0, A, agent.ro_actions.shape, device=DEV, generator=gen).float())
+        agent.ro_returns.copy_(torch.randn(agent.ro_returns.shape, device=DEV, generator=gen))
+        batch = agent.concat_step_batches(agent.ro_states, agent.ro_actions, agent.ro_returns, agent.ro_values, agent.ro_log_probs)
+        for _ in range(2):
+            agent.run_ppo_epochs(*batch)
+        torch.cuda.synchronize()
+        hp = agent.hot_path()
+        assert hp.obs_gather == gather and (hp.mb_obs is None) == (not gather)
+        results.append((net.flat_param.clone(), torch.stack(list(agent.loss_history)).clone(), net.step))
+    (p0, l0, s0), (p1, l1, s1) = results
+    assert s0 == s1 == 2 * 2 * 3 and torch.isfinite(p0).all()
+    assert torch.equal(l0, l1) and torch.equal(p0, p1)

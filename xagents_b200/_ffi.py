@@ -142,6 +142,10 @@ PROTOTYPES = {
     'xa_grad_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GradSegment), ctypes.c_int, ctypes.c_void_p,
                                             ctypes.c_int64, c_stream]),
     'xa_nature_cnn_forward': (ctypes.c_int, [ctypes.POINTER(NatureCnn), ctypes.c_void_p, ctypes.c_int, c_stream]),
+    'xa_nature_cnn_forward_indexed': (ctypes.c_int, [ctypes.POINTER(NatureCnn), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                     c_stream]),
+    'xa_conv2d_u8_s2d_bf16_indexed': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_f32p,
+                                                     ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 8 + [c_stream]),
     'xa_nature_cnn_backward': (ctypes.c_int, [ctypes.POINTER(NatureCnn)] + [ctypes.c_void_p] * 4 + [c_stream]),
     'xa_gather_s2d_u8_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64] +
                               [ctypes.c_int] * 7 + [c_stream]),

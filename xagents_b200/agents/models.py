@@ -117,9 +117,23 @@ class TorchModel:
         actor_dst.copy_(actor.reshape(actor_dst.shape))
         critic_dst.copy_(critic.reshape(critic_dst.shape))
 
-    def forward_into(self, states, actor_dst, critic_dst, i=0):
+    @property
+    def reads_through_permutation(self):
+        """True when `forward_into(store, ..., idx=ids)` evaluates the minibatch store[ids] without a gathered copy of it (the
+        native plan's first layer fetches every frame by its id): the prepared PPO pipeline then skips its frame gather."""
+        return self._native_plan and getattr(self.module, 'takes_uint8', False)
+
+    def forward_into(self, states, actor_dst, critic_dst, i=0, idx=None, time_major=None):
         """Training forward with the outputs written into the caller's tensors (the prepared pipelines' per-minibatch output
-        rows): no copies with the native plan, forward() + two copies otherwise."""
+        rows): no copies with the native plan, forward() + two copies otherwise.  `idx` (int32 [n], device; needs
+        `reads_through_permutation`): the minibatch is states[idx] -- env-major sample ids of the time-major rollout
+        `states` [T*E, ...] when `time_major=(T, E)` -- fetched by the first layer itself."""
+        if idx is not None:
+            assert self.reads_through_permutation and states.dtype == torch.uint8 and states.is_contiguous()
+            plan = self.module.plan(idx.numel(), self.flat_param, self.flat_grad.numel())
+            self._outputs = plan
+            plan.forward(states, out=(actor_dst, critic_dst), idx=idx, time_major=time_major)
+            return
         x = self.scaled(states)
         if self._native_plan and x.dtype in (torch.uint8, torch.bfloat16):
             plan = self.module.plan(x.shape[0], self.flat_param, self.flat_grad.numel())

@@ -107,12 +107,17 @@ class PPO(A2C):
         bound = {name: getattr(self, attr) for name, attr in self._ROLLOUT_BINDINGS}
         hp = self._pipeline
         if hp is None:
+            options = dict(self.pipeline_options)
+            # a network whose first layer fetches every frame by its id needs no gathered copy of the minibatch's frames
+            fetches = bool(getattr(self.net, 'reads_through_permutation', False)) and self.obs_dtype == torch.uint8 \
+                and tuple(self.input_shape) == (84, 84, 4)
+            options.setdefault('obs_gather', not fetches)
             hp = self._pipeline = PPOHotPath(
                 self.n_steps, self.n_envs, self.input_shape, self.n_actions, ppo_epochs=self.ppo_epochs,
                 mini_batches=self.mini_batches, gamma=self.gamma, lam=self.lam, clip_norm=self.clip_norm,
                 entropy_coef=self.entropy_coef, value_loss_coef=self.value_loss_coef,
                 advantage_epsilon=self.advantage_epsilon, actor_kind=self.actor_kind, device=self.device, comm=self.comm,
-                buffers=bound, **self.pipeline_options)
+                buffers=bound, **options)
         else:
             moved = {name: t for name, t in bound.items() if getattr(hp, name).data_ptr() != t.data_ptr()}
             if moved:                                              # a rollout feed swapped buffers (double-buffered uploads)
@@ -142,6 +147,10 @@ class PPO(A2C):
 
         def forward(i):                                            # minibatch i is staged: model forward on it
             n = hp.mb_rows[i]
+            if not hp.obs_gather:                                  # ... or read through the permutation by the first layer
+                forward_into(self.ro_states.view((hp.N,) + tuple(self.input_shape)), hp.actor_out[i, :n], hp.critic_out[i, :n], i,
+                             idx=hp.minibatch_ids(i), time_major=(self.n_steps, self.n_envs))
+                return
             states_mb = hp.mb_obs[hp._mb_place[i][1], hp._mb_place[i][2]:hp._mb_place[i][2] + n]
             if forward_into is not None:
                 forward_into(states_mb, hp.actor_out[i, :n], hp.critic_out[i, :n], i)

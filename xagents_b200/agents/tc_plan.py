@@ -46,7 +46,7 @@ class NaturePlan:
         self.has_backward = bool(backward)
         if backward:
             self._build_backward(lib, named, flat, n_grad)
-        self._fwd, self._bwd = lib.xa_nature_cnn_forward, lib.xa_nature_cnn_backward
+        self._fwd, self._bwd, self._fwd_idx = lib.xa_nature_cnn_forward, lib.xa_nature_cnn_backward, lib.xa_nature_cnn_forward_indexed
 
     # ---- backward buffers, scratch layout, gradient map -----------------------------------------------------------
     def _build_backward(self, lib, named, flat, n_grad):
@@ -136,10 +136,12 @@ class NaturePlan:
     def _stream(self, stream):
         return ctypes.c_void_p((stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream)
 
-    def forward(self, frames, stream=None, out=None):
+    def forward(self, frames, stream=None, out=None, idx=None, time_major=None):
         """uint8 [B,84,84,4] frames, or the bf16 [B,21,21,64] output of ops.gather_s2d_u8_bf16 -> (actor [B,A], critic [B]) fp32:
-        the plan's own buffers, valid until the next forward(), or the caller's `out` = (actor, critic) tensors."""
-        assert frames.is_cuda and frames.is_contiguous() and frames.shape[0] == self.batch, (tuple(frames.shape), self.batch)
+        the plan's own buffers, valid until the next forward(), or the caller's `out` = (actor, critic) tensors.
+        `idx` (int32 [B], device): the batch is frames[idx] of a larger uint8 frame store, read through the permutation by the
+        first layer (no gathered copy); `time_major=(T, E)`: ids are env-major sample ids of a time-major rollout."""
+        assert frames.is_cuda and frames.is_contiguous() and (idx is not None or frames.shape[0] == self.batch), (tuple(frames.shape), self.batch)
         actor, critic = out if out is not None else (self.actor, self.critic)
         if out is not None:
             assert actor.dtype == torch.float32 and actor.is_contiguous() and actor.numel() == self.actor.numel() and actor.device == self.device
@@ -155,7 +157,15 @@ class NaturePlan:
                 self.x1 = torch.empty((self.batch, 21, 21, 64), dtype=torch.bfloat16, device=self.device)
                 self.net.x1 = self.x1.data_ptr()
             self._x1_in = self.x1
-        self._launch(self._fwd, 'xa_nature_cnn_forward', ctypes.byref(self.net), ctypes.c_void_p(frames.data_ptr()), int(s2d), self._stream(stream))
+        if idx is not None:
+            assert not s2d and idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.numel() == self.batch
+            T, E = (int(time_major[0]), int(time_major[1])) if time_major is not None else (0, 0)
+            assert T <= 0 or T * E == frames.shape[0], (T, E, frames.shape[0])
+            self._launch(self._fwd_idx, 'xa_nature_cnn_forward_indexed', ctypes.byref(self.net), ctypes.c_void_p(frames.data_ptr()),
+                         int(frames.shape[0]), ctypes.c_void_p(idx.data_ptr()), T, E, self._stream(stream))
+        else:
+            self._launch(self._fwd, 'xa_nature_cnn_forward', ctypes.byref(self.net), ctypes.c_void_p(frames.data_ptr()), int(s2d),
+                         self._stream(stream))
         ops._count(6)
         return actor, critic
 

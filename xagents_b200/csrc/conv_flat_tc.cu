@@ -62,6 +62,12 @@ struct FlatParams {
   uint32_t raw_stage_bytes, raw_tx_bytes;  // uint8 input: bytes of one raw window stage / of one TMA box
   uint32_t div_w_magic;                    // (g * div_w_magic) >> 16 == g / W for every pixel index g inside a raw box
   int store_x1;                            // uint8 input: also write the converted bf16 rows to HBM through map_x1
+  // uint8 input read THROUGH A PERMUTATION (the minibatch gather folded into the first layer): frame f of the batch is row
+  // frame_idx[f] (env-major sample id when idx_T > 0: row = (id % T) * E + id / T, xagents/base.py:559-564) of `frames_base`
+  const uint8_t* frames_base;
+  const int32_t* frame_idx;
+  int idx_T, idx_E, box_rows;
+  uint32_t grid_row_bytes;                 // one row of the space-to-depth grid = 4 image rows
   uint32_t a_units[kMaxEntries];  // (byte offset of the entry's A operand inside a stage) >> 4
   uint32_t b_units[kMaxEntries];  // (byte offset of the entry's weight tile) >> 4
 };
@@ -140,7 +146,45 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
       int s = 0;
       uint32_t round = 0;
       const uint32_t blk_bytes = static_cast<uint32_t>(p.win_rows) * 128u;
-      if (kU8) {  // raw uint8 windows: the nY whole grid rows that contain pixels [q0, q0 + win_rows)
+      if (kU8 && p.frames_base != nullptr) {
+        // frames addressed one by one: a frame is contiguous (H grid rows of grid_row_bytes), so the box of a tile is one bulk
+        // copy of the grid rows [gy0, gy0 + n0) of frame f0 and, where the window runs into the next frame of the batch, a
+        // second one of that frame's first rows, placed behind it -- the same shared-memory picture the tensor-map box gives
+        // for frames that lie in batch order.  The frame ids of the NEXT tile are fetched while this tile's stage is awaited
+        // (a first version used them at once: one L2 round trip per tile in this single thread made the layer 256 us instead of 178).
+        const uint32_t frame_bytes = static_cast<uint32_t>(p.H) * p.grid_row_bytes;
+        const uint32_t hw = static_cast<uint32_t>(p.H) * p.W;
+        auto ids_of = [&](int tile, uint32_t& f0, int32_t& a, int32_t& b) {   // loads only: the arithmetic on them waits a tile
+          f0 = static_cast<uint32_t>(tile) * kBlockM / hw;
+          a = p.frame_idx != nullptr ? __ldg(p.frame_idx + f0) : static_cast<int32_t>(f0);
+          b = static_cast<int>(f0) + 1 < p.B ? (p.frame_idx != nullptr ? __ldg(p.frame_idx + f0 + 1) : static_cast<int32_t>(f0 + 1)) : 0;
+        };
+        auto row_of = [&](int32_t id) -> int64_t {
+          return p.idx_T > 0 ? static_cast<int64_t>(id % p.idx_T) * p.idx_E + id / p.idx_T : static_cast<int64_t>(id);
+        };
+        int tile = blockIdx.x;
+        uint32_t f0 = 0, nf0 = 0;
+        int32_t a = 0, b = 0, na = 0, nb = 0;
+        if (tile < n_tiles) ids_of(tile, f0, a, b);
+        for (; tile < n_tiles; tile += gridDim.x) {
+          const int next = tile + gridDim.x;
+          if (next < n_tiles) ids_of(next, nf0, na, nb);
+          const uint32_t q0 = static_cast<uint32_t>(tile) * kBlockM;
+          const int gy0 = static_cast<int>((q0 - f0 * hw) / p.W);
+          const int n0 = p.box_rows < p.H - gy0 ? p.box_rows : p.H - gy0;
+          const int n1 = static_cast<int>(f0) + 1 < p.B ? p.box_rows - n0 : 0;
+          const uint8_t* src0 = p.frames_base + row_of(a) * frame_bytes + static_cast<uint32_t>(gy0) * p.grid_row_bytes;
+          const uint8_t* src1 = p.frames_base + row_of(b) * frame_bytes;
+          if (round > 0) mbar_wait_wd(raw_empty + s, (round - 1) & 1);
+          uint8_t* dst = raw_ring + static_cast<size_t>(s) * p.raw_stage_bytes;
+          xa::mbar_expect_tx(raw_full + s, static_cast<uint32_t>(n0 + n1) * p.grid_row_bytes);
+          // no L2 hint: the rows a neighbouring tile's window shares with this one are re-read from L2 (evict-first measured the same)
+          xa::bulk_g2s_nohint(dst, src0, static_cast<uint32_t>(n0) * p.grid_row_bytes, raw_full + s);
+          if (n1 > 0) xa::bulk_g2s_nohint(dst + static_cast<uint32_t>(n0) * p.grid_row_bytes, src1, static_cast<uint32_t>(n1) * p.grid_row_bytes, raw_full + s);
+          f0 = nf0, a = na, b = nb;
+          if (++s == kRawStages) s = 0, ++round;
+        }
+      } else if (kU8) {  // raw uint8 windows: the nY whole grid rows that contain pixels [q0, q0 + win_rows)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
           if (round > 0) mbar_wait_wd(raw_empty + s, (round - 1) & 1);
           xa::mbar_expect_tx(raw_full + s, p.raw_tx_bytes);
@@ -460,9 +504,9 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
 // First layer straight from the uint8 frames (see conv_flat_kernel's kU8 notes): frames [B, height, width, 4] uint8, a
 // kh x kw stride-1 kernel over the 4x4 space-to-depth grid (= a 4kh x 4kw / 4 convolution of the frames), w [n_out, kh*kw*64]
 // bf16 with K ordered (kh, kw, dy, dx, c), x/255 applied on the way in.
-extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height,
-                                     int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
-  const char* what = "xa_conv2d_u8_s2d_bf16";
+static int conv_u8_s2d(const char* what, const uint8_t* frames, const int32_t* frame_idx, int64_t n_frames, int idx_n_steps, int idx_n_envs,
+                       const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height, int width, int kh, int kw, int n_out,
+                       int relu, int out_s2d, xa_stream_t stream) {
   XA_REQUIRE(frames && w && y, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(batch > 0 && height > 0 && width > 0 && height % 4 == 0 && width % 4 == 0 && kh > 0 && kw > 0, XA_EINVAL,
              "%s: batch=%d frames %dx%d kernel %dx%d", what, batch, height, width, kh, kw);
@@ -499,6 +543,14 @@ extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const
       p.a_units[e] = (static_cast<uint32_t>(i * W + j) * 128u) >> 4;
       p.b_units[e] = (static_cast<uint32_t>(e) * n_out * 128u) >> 4;
     }
+  if (frame_idx != nullptr) {
+    XA_REQUIRE(n_frames > 0 && box_rows <= H && xa::aligned(frame_idx, 4), XA_EINVAL, "%s: indexed frames need n_frames > 0 and a window within two frames", what);
+    XA_REQUIRE(idx_n_steps <= 0 || static_cast<int64_t>(idx_n_steps) * idx_n_envs == n_frames, XA_EINVAL,
+               "%s: n_steps * n_envs = %lld is not the number of stored frames %lld", what,
+               static_cast<long long>(idx_n_steps) * idx_n_envs, static_cast<long long>(n_frames));
+    p.frames_base = frames, p.frame_idx = frame_idx, p.idx_T = idx_n_steps > 0 ? idx_n_steps : 0, p.idx_E = idx_n_envs;
+    p.box_rows = box_rows, p.grid_row_bytes = static_cast<uint32_t>(W) * 64u;
+  }
   p.div_w_magic = (65536u + W - 1) / W;
   for (uint32_t g = 0; g < static_cast<uint32_t>((box_rows > H ? box_rows : H) * W); ++g)
     XA_REQUIRE(((g * p.div_w_magic) >> 16) == g / W, XA_EINVAL, "%s: no 16-bit reciprocal for a grid %d wide", what, W);
@@ -507,7 +559,7 @@ extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const
     EncodeTiledFn fn = encode_fn();
     XA_REQUIRE(fn != nullptr, XA_EINVAL, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
     // the frames as image rows of 32-bit words: [batch * height rows, width words]; a box = 4 * box_rows whole rows
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(batch) * height};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(frame_idx != nullptr ? n_frames : batch) * height};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * 4};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(width), static_cast<cuuint32_t>(4 * box_rows)};
     const cuuint32_t elem[2] = {1, 1};
@@ -527,4 +579,22 @@ extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const
                       epi_bytes;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n_out == 64 ? launch_flat<64, true>(mx, mw, mx1, p, smem, s, what) : launch_flat<32, true>(mx, mw, mx1, p, smem, s, what);
+}
+
+extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height,
+                                     int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16", frames, nullptr, 0, 0, 0, w, bias, y, x_s2d_out, batch, height, width, kh, kw, n_out, relu, out_s2d,
+                     stream);
+}
+
+// The same layer reading its `batch` frames THROUGH A PERMUTATION of a larger frame store: frame f = row frame_idx[f] of
+// frames [n_frames, height, width, 4] (with n_steps > 0 the ids are env-major sample ids of a time-major [n_steps, n_envs]
+// rollout, xagents/base.py:559-564) -- get_mini_batches' tf.gather of the states (ppo/agent.py:139-155) folded into the
+// network's first layer: the gathered minibatch is never written to or read back from HBM.
+extern "C" int xa_conv2d_u8_s2d_bf16_indexed(const uint8_t* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps, int n_envs,
+                                             const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height, int width,
+                                             int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+  XA_REQUIRE(frame_idx != nullptr, XA_EINVAL, "xa_conv2d_u8_s2d_bf16_indexed: null frame_idx");
+  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16_indexed", frames, frame_idx, n_frames, n_steps, n_envs, w, bias, y, x_s2d_out, batch, height, width,
+                     kh, kw, n_out, relu, out_s2d, stream);
 }

@@ -21,12 +21,15 @@ static int check_net(const xa_nature_cnn_t* n, const char* what) {
   return XA_OK;
 }
 
-int xa_nature_cnn_forward(const xa_nature_cnn_t* n, const void* frames, int frames_s2d, xa_stream_t stream) {
-  const char* what = "xa_nature_cnn_forward";
+static int forward_impl(const char* what, const xa_nature_cnn_t* n, const void* frames, int frames_s2d, int64_t n_frames, const int32_t* frame_idx,
+                        int n_steps, int n_envs, xa_stream_t stream) {
   XA_TRY(check_net(n, what));
   XA_REQUIRE(frames != nullptr, XA_EINVAL, "%s: null frames", what);
   const int B = n->batch;
-  if (frames_s2d)
+  if (frame_idx != nullptr)  // the minibatch gather folded into the first layer: frames = the whole rollout, read through the permutation
+    XA_TRY(xa_conv2d_u8_s2d_bf16_indexed(static_cast<const uint8_t*>(frames), n_frames, frame_idx, n_steps, n_envs, n->w1, n->b1, n->x2, n->x1, B,
+                                         84, 84, 2, 2, 32, 1, 1, stream));
+  else if (frames_s2d)
     XA_TRY(xa_conv2d_nhwc_bf16_ex(frames, n->w1, n->b1, n->x2, B, 21, 21, 64, 2, 2, 32, 0, 0, 1, 1, nullptr, 0, 0, 0, 0, 0, stream));
   else  // /255 + space-to-depth + conv1 in one kernel; x1 (only the backward pass reads it) is written from shared memory
     XA_TRY(xa_conv2d_u8_s2d_bf16(static_cast<const uint8_t*>(frames), n->w1, n->b1, n->x2, n->x1, B, 84, 84, 2, 2, 32, 1, 1, stream));
@@ -34,6 +37,16 @@ int xa_nature_cnn_forward(const xa_nature_cnn_t* n, const void* frames, int fram
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, 0, stream));
   XA_TRY(xa_gemm_bf16_tn_ex(n->y3, n->wf, n->h, n->bf, B, 512, 3136, 512, 1, 1, nullptr, 512, 0, 0, n->gemm_ws, n->gemm_ws_bytes, stream));
   return xa_heads_forward_bf16(n->h, n->wh, n->bh, n->actor, n->critic, B, 512, n->n_actions, stream);
+}
+
+int xa_nature_cnn_forward(const xa_nature_cnn_t* n, const void* frames, int frames_s2d, xa_stream_t stream) {
+  return forward_impl("xa_nature_cnn_forward", n, frames, frames_s2d, 0, nullptr, 0, 0, stream);
+}
+
+int xa_nature_cnn_forward_indexed(const xa_nature_cnn_t* n, const void* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps,
+                                  int n_envs, xa_stream_t stream) {
+  XA_REQUIRE(frame_idx != nullptr, XA_EINVAL, "xa_nature_cnn_forward_indexed: null frame_idx");
+  return forward_impl("xa_nature_cnn_forward_indexed", n, frames, 0, n_frames, frame_idx, n_steps, n_envs, stream);
 }
 
 int xa_nature_cnn_backward(const xa_nature_cnn_t* n, const void* frames_s2d_or_null, const float* d_actor, const float* d_critic,

@@ -46,9 +46,17 @@ class PPOHotPath:
     def __init__(self, n_steps, n_envs, obs_shape, n_actions, *, obs_dtype=torch.uint8, ppo_epochs=4, mini_batches=4,
                  gamma=0.99, lam=0.95, clip_norm=0.1, entropy_coef=0.01, value_loss_coef=0.5, advantage_epsilon=1e-8,
                  actor_kind='logits', device='cuda:0', gather_mode='auto', scan_mode='auto', comm=None,
-                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None, sync='auto', dynamic=True, late_fork=False):
+                 fuse_fields=True, staging=2, overlap=True, gather_chunk=None, buffers=None, sync='auto', dynamic=True, late_fork=False,
+                 obs_gather=True):
         """`buffers`: existing time-major device tensors to run on instead of allocating (any of ROLLOUT_FIELDS and
-        'returns') -- the agents pass their own `ro_*` rollout buffers, so the pipeline works in place (no copies)."""
+        'returns') -- the agents pass their own `ro_*` rollout buffers, so the pipeline works in place (no copies).
+        `obs_gather=False`: the consumer of the observations reads the rollout through `perms` itself (a network whose first
+        layer fetches every frame by its id, TorchModel.reads_through_permutation): no frame gather is launched and no staging
+        memory is allocated; `before_loss(i)` finds minibatch i's ids in `minibatch_ids(i)`."""
+        self.obs_gather = bool(obs_gather)
+        if not self.obs_gather:
+            assert fuse_fields, 'obs_gather=False reads every field through the permutation'
+            sync, gather_chunk, staging = 'event', int(ppo_epochs) * max(1, int(mini_batches)) * 2, 1
         self.T, self.E, self.A = int(n_steps), int(n_envs), int(n_actions)
         self.N = self.T * self.E
         obs_dtype = buffers['obs'].dtype if buffers and 'obs' in buffers else obs_dtype
@@ -144,7 +152,7 @@ class PPOHotPath:
         # permutations of env-major flat sample ids, one row per epoch
         self.perms = torch.empty((self.K, N), dtype=torch.int32, device=dev)
         # minibatch staging
-        self.mb_obs = torch.empty((self.staging, self.cap) + self.obs_shape, dtype=obs_dtype, device=dev)
+        self.mb_obs = torch.empty((self.staging, self.cap) + self.obs_shape, dtype=obs_dtype, device=dev) if self.obs_gather else None
         self.mb_fields = torch.empty((self.staging, len(self.FIELDS), self.cap), dtype=f32, device=dev)
         # model outputs for every minibatch (filled by the caller / the model forward)
         self.actor_out = torch.empty((self.n_mb, B, A), dtype=f32, device=dev)
@@ -258,8 +266,10 @@ class PPOHotPath:
         for g in range(self.n_groups):
             first, slot = self.group_first[g], g % self.staging
             idx_addr = self.perms.data_ptr() + 4 * flat_off[first]
-            obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * self.cap * self.row_bytes)
-            if self._progress_sync:
+            obs_dst = ctypes.c_void_p(self.mb_obs.data_ptr() + slot * self.cap * self.row_bytes) if self.obs_gather else None
+            if not self.obs_gather:
+                self._gathers.append(None)
+            elif self._progress_sync:
                 self._gathers.append((lib.xa_gather_rows_progress,
                                       (_p(self.obs), ctypes.c_void_p(idx_addr), obs_dst, self.group_rows[g], self.row_bytes, N, T, E,
                                        _p(self.progress), flat_off[first], N, B,
@@ -304,7 +314,7 @@ class PPOHotPath:
             self._loss_done = [torch.cuda.Event() for _ in range(self.n_groups)]
             self._fork = torch.cuda.Event()
         self._calls = True
-        self.kernel_launches_per_step = 2 + self.n_mb + self.n_groups
+        self.kernel_launches_per_step = 2 + self.n_mb + (self.n_groups if self.obs_gather else 0)
         return self
 
     # ---------------------------------------------------------------------------------- run
@@ -351,14 +361,15 @@ class PPOHotPath:
         if progress:
             self._step_no += 1
         for g in range(self.n_groups):
-            fn, args = self._gathers[g]
-            if two and g >= self.staging:
-                ds.wait_event(self._loss_done[g - self.staging])                # staging slot is free again
-            self._check('gather', on_gather(g, fn, args) if on_gather is not None else fn(*args))
-            if two:
-                self._gather_done[g].record(ds)
-                if not progress:
-                    cs.wait_event(self._gather_done[g])
+            if self._gathers[g] is not None:
+                fn, args = self._gathers[g]
+                if two and g >= self.staging:
+                    ds.wait_event(self._loss_done[g - self.staging])            # staging slot is free again
+                self._check('gather', on_gather(g, fn, args) if on_gather is not None else fn(*args))
+                if two:
+                    self._gather_done[g].record(ds)
+                    if not progress:
+                        cs.wait_event(self._gather_done[g])
             for i in range(self.group_first[g], self.group_first[g] + self.group_sizes[g]):
                 if progress:     # minibatch i is staged once its counter reached (launches so far) x (its rows) x (units per row)
                     target = (self._step_no * self.mb_rows[i] * self._units) & 0xffffffff
@@ -401,6 +412,10 @@ class PPOHotPath:
         self._capturing = False
         self.prepare(eager_streams[0])                       # eager path stays usable
         return graph.replay
+
+    def minibatch_ids(self, i):
+        """int32 [rows of minibatch i]: its env-major sample ids, a view of `perms` (what every kernel reads it through)."""
+        return self.perms.view(-1)[self._offsets[i]:self._offsets[i] + self.mb_rows[i]]
 
     def minibatch_views(self, i):
         """(states, actions, returns, old_values, old_log_probs) staging views of minibatch i."""

@@ -513,12 +513,17 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
     return y
 
 
-def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, x_s2d_out=None, stream=None):
+def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, x_s2d_out=None, idx=None, time_major=None,
+                       stream=None):
     """The 4x4-strided first layer straight from uint8 frames [B,H,W,4]: /255, space-to-depth and the kh x kw stride-1
     convolution over the [B,H/4,W/4,64] grid in one kernel (bit-identical to space_to_depth_u8_bf16 + conv2d_nhwc_bf16).
-    `x_s2d_out` [B,H/4,W/4,64] bf16 also receives the scaled space-to-depth tensor (for the weight gradient)."""
+    `x_s2d_out` [B,H/4,W/4,64] bf16 also receives the scaled space-to-depth tensor (for the weight gradient).
+    `idx` (int32 [B]): the layer runs on frames[idx] without gathering them (`frames` is then the whole store; with
+    `time_major=(T, E)` the ids are env-major sample ids of a time-major rollout, as for `gather_rows`)."""
     f, ww = _dev(frames, 'uint8'), _dev(w, 'bfloat16')
-    B, H, W, C = f.shape
+    n_frames, H, W, C = f.shape
+    ids = _dev(idx, 'int32') if idx is not None else None
+    B = ids.shape[0] if ids is not None else n_frames
     N = ww.shape[0]
     if C != 4 or ww.shape[1] != kh * kw * 64:
         raise ValueError(f'frames {f.shape} / weights {ww.shape}: built for 4-channel frames and K = kh*kw*64')
@@ -528,8 +533,13 @@ def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=Fals
     bias_a = _dev(bias, 'float32') if bias is not None else None
     if x_s2d_out is not None and (x_s2d_out.dtype != torch.bfloat16 or tuple(x_s2d_out.shape) != (B, H // 4, W // 4, 64) or not x_s2d_out.is_contiguous()):
         raise ValueError(f'x_s2d_out must be a contiguous bf16 [{B}, {H // 4}, {W // 4}, 64] tensor')
-    _call(f, 'xa_conv2d_u8_s2d_bf16', _ptr(f), _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W, kh, kw, N, int(bool(relu)),
-          int(bool(out_s2d)), stream)
+    if ids is not None:
+        T, E = _layout(time_major)
+        _call(f, 'xa_conv2d_u8_s2d_bf16_indexed', _ptr(f), n_frames, _ptr(ids), T, E, _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W,
+              kh, kw, N, int(bool(relu)), int(bool(out_s2d)), stream)
+    else:
+        _call(f, 'xa_conv2d_u8_s2d_bf16', _ptr(f), _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W, kh, kw, N, int(bool(relu)),
+              int(bool(out_s2d)), stream)
     _count()
     return y
 
