@@ -258,12 +258,18 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
  *   flags                   XA_CONV_INPUT_ZERO_BORDER: the caller guarantees that the last pad_x columns and pad_y rows
  *                           of every input image are zero (a gradient on a zero-bordered grid); padded convolutions
  *                           may then use the flat kernel that fetches every input pixel once (csrc/conv_flat_tc.cu)
+ *                           XA_CONV_MASK_BITS: relu_mask points to BIT masks (uint32 words: bit j of word i <=> element 32 i + j
+ *                           of the compact activation is > 0) instead of the bf16 activation itself
+ *   relu_bits_out           != NULL (ReLU layers with a compact or 2x2-packed output, flat kernel): such a bit mask of THIS
+ *                           layer's output, written from the epilogue (1/16 of the output's bytes) for the data gradient of
+ *                           the layer above -- the backward pass then never re-reads an activation only for its sign
  * relu_mask always has the natural compact [B, out_h, out_w, n_out] layout. */
 #define XA_CONV_INPUT_ZERO_BORDER 1
+#define XA_CONV_MASK_BITS 2
 int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width,
                            int channels, int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode,
-                           const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w, int flags,
-                           xa_stream_t stream);
+                           const void* relu_mask, int out_h, int out_w, int out_grid_h, int out_grid_w,
+                           uint32_t* relu_bits_out, int flags, xa_stream_t stream);
 
 /* The first (4x4-strided) layer straight from the uint8 frames: cast + /255 (xagents/base.py:505-506), space-to-depth and the
  * convolution in one kernel -- raw uint8 windows arrive by TMA, converter warps write the bf16 SWIZZLE_128B operand tiles
@@ -275,6 +281,11 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
  * xa_space_to_depth_u8_bf16 followed by xa_conv2d_nhwc_bf16. */
 int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch,
                           int height, int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream);
+/* The same layer with every option: frame_idx (may be NULL) as in xa_conv2d_u8_s2d_bf16_indexed below; relu_bits_out (may be NULL)
+ * as in xa_conv2d_nhwc_bf16_ex. */
+int xa_conv2d_u8_s2d_bf16_ex(const uint8_t* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps, int n_envs,
+                             const void* w, const float* bias, void* y, void* x_s2d_out, uint32_t* relu_bits_out, int batch,
+                             int height, int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream);
 /* The same layer on the `batch` frames frames[frame_idx[0 .. batch)] of a store of n_frames frames, read through the
  * permutation by per-frame TMA bulk copies: get_mini_batches' tf.gather of the states (xagents/ppo/agent.py:139-155) folded
  * into the layer -- the gathered minibatch never exists in HBM.  n_steps > 0: ids are env-major sample ids of a time-major
@@ -390,6 +401,8 @@ typedef struct xa_nature_cnn_t {
   xa_grad_segment_t segments[XA_MAX_GRAD_SEGMENTS];
   int32_t n_segments, reserved;
   int64_t n_grad;
+  uint32_t *relu_bits2, *relu_bits3; /* optional (both or none): ReLU-derivative bit masks of x2 / x3 (numel / 8 bytes each), written
+                                        by the forward pass and read by the data gradients instead of the activations */
 } xa_nature_cnn_t;
 int xa_nature_cnn_forward(const xa_nature_cnn_t* net, const void* frames, int frames_s2d, xa_stream_t stream);
 /* forward on the minibatch frames[frame_idx[0 .. batch)] of a frame store [n_frames, 84, 84, 4] uint8 without gathering it: the

@@ -59,6 +59,26 @@ def test_as_coded_reading_equals_the_hand_written_conv1d_network():
         assert torch.allclose(g, w, rtol=1e-5, atol=1e-6)
 
 
+def test_tensor_core_network_starts_from_the_weights_the_reader_gives_the_cfg():
+    """ModelReader.build_tensor_core_network (`--tensor-core-network`): the documented Conv2D network as `NatureCnnTc`, its
+    parameters the ones the reader's initialisers and seed produce for the file -- the FC weight moved from Keras' (h, w, c)
+    flatten order to the module's (c, h, w) -- so both modules compute the same function; other architectures are refused."""
+    from xagents_b200.agents import NatureCNN
+    ref = ModelReader(CNN, [5, 1], (84, 84, 4), conv_dims=2, seed=7).build_model()
+    net = ModelReader(CNN, [5, 1], (84, 84, 4), conv_dims=2, seed=7).build_tensor_core_network()
+    assert type(net).__name__ == 'NatureCnnTc' and net.takes_uint8 and not net.output_is_softmax
+    assert sum(p.numel() for p in net.parameters()) == sum(p.numel() for p in ref.parameters())
+    x = torch.rand(3, 84, 84, 4)
+    with torch.no_grad():
+        actor, critic = NatureCNN.forward(net, x)                  # the module's fp32 torch form (its own forward runs the kernels)
+        want_actor, want_critic = ref(x)
+    assert torch.allclose(actor, want_actor, atol=1e-5) and torch.allclose(critic, want_critic, atol=1e-5)
+    with pytest.raises(ValueError, match='not the documented 84x84x4 Nature CNN'):
+        ModelReader(CNN, [5, 1], (84, 84, 1), conv_dims=2).build_tensor_core_network()
+    with pytest.raises(ValueError, match='not the documented 84x84x4 Nature CNN'):
+        ModelReader(CNN, [12, 1], (84, 84, 4), conv_dims=2).build_tensor_core_network()       # more actions than the heads kernel holds
+
+
 def test_conv2d_reading_matches_a_channels_last_restatement():
     net = ModelReader(CNN, [4, 1], (84, 84, 4), conv_dims=2, seed=3).build_model()
     x = torch.rand(2, 84, 84, 4)

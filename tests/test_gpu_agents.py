@@ -278,6 +278,22 @@ def test_cli_train_a2c_on_synthetic_atari_frames_with_both_cfg_readings():
 
 
 @pytest.mark.timeout(300)
+def test_cli_train_ppo_with_the_tensor_core_network_on_the_device_environment():
+    """`--tensor-core-network`: the default cnn `.cfg` as `NatureCnnTc` (tcgen05 forward and backward, the file's initialisers and
+    seed) through the command line, on the device-resident synthetic Atari environments: rollout as one CUDA graph of fused steps,
+    update phase without a frame gather (the first layer reads the rollout through the permutation)."""
+    from xagents_b200 import cli
+    ex = cli.Executor()
+    ex.execute(['train', 'ppo', '--env', 'SyntheticAtariDevice-v0', '--n-envs', '8', '--n-steps', '16', '--max-steps', '384', '--seed', '2',
+                '--quiet', '--tensor-core-network', '--preprocess', '--mini-batches', '2', '--ppo-epochs', '2'])
+    agent = ex.agent
+    assert type(agent.net.module).__name__ == 'NatureCnnTc' and agent.net.n_params == 1_687_719 and agent.net.reads_through_permutation
+    assert agent.steps == 384 and agent.net.step == 3 * 2 * 2 and torch.isfinite(agent.net.flat_param).all()
+    assert agent._rollout_graph and agent._fused_rollout_applies() and agent._pipeline is not None and not agent._pipeline.obs_gather
+    assert agent._pipeline.mb_obs is None
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs of one box')
 def test_cli_train_shards_the_environments_over_two_gpus():
     """torchrun x2: 16 CartPole environments, 8 per rank, NCCL gradient all-reduce per minibatch and job-wide advantage

@@ -354,6 +354,43 @@ def test_gradients_written_straight_onto_zero_bordered_grids():
     g1f = torch.zeros_like(g1)
     ops.conv2d_nhwc_bf16(g2, w2, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=m2, out=g1f, unpack_s2d=True, zero_border=True)
     assert torch.equal(g1f, want1)
+    # the same two data gradients with the ReLU derivative given as BIT masks (one bit per element of the compact mask tensor)
+    g2b, g1b = torch.zeros_like(g2), torch.zeros_like(g1)
+    ops.conv2d_nhwc_bf16(grid, w3, 3, 3, pad=(2, 2), out_hw=(9, 9), relu_mask=_pack_bits(m3 > 0), out=g2b, zero_border=True)
+    ops.conv2d_nhwc_bf16(g2, w2, 2, 2, pad=(1, 1), out_hw=(10, 10), relu_mask=_pack_bits(m2 > 0), out=g1b, unpack_s2d=True, zero_border=True)
+    assert torch.equal(g2b, want2) and torch.equal(g1b, want1)
+
+
+def _pack_bits(flags):
+    """bool tensor -> int32 words, bit j of word i = element 32 i + j (the layout of the kernels' ReLU bit masks)."""
+    f = flags.reshape(-1, 32).to(torch.int64)
+    words = (f << torch.arange(32, device=f.device, dtype=torch.int64)).sum(1)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+
+
+@pytest.mark.parametrize('B', [1, 37, 300])
+def test_forward_layers_write_their_relu_bit_masks(B):
+    """relu_bits_out of the forward convolutions (the first layer from uint8 frames with its 2x2-packed output, and the compact
+    64-channel layers): exactly the bits of (output > 0), in the output tensor's own element order."""
+    torch.manual_seed(B)
+    frames = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    w1 = (torch.randn(32, 256, device=DEV) * 0.05).bfloat16()
+    b1 = torch.randn(32, device=DEV) * 0.1
+    bits2 = torch.full((B * 10 * 10 * 128 // 32,), -1, dtype=torch.int32, device=DEV)
+    x2 = ops.conv2d_u8_s2d_bf16(frames, w1, 2, 2, bias=b1, relu=True, out_s2d=True, relu_bits_out=bits2)
+    assert torch.equal(x2.view(torch.int16), ops.conv2d_u8_s2d_bf16(frames, w1, 2, 2, bias=b1, relu=True, out_s2d=True).view(torch.int16))
+    assert torch.equal(bits2, _pack_bits(x2 > 0)) and 0.2 < float((x2 > 0).float().mean()) < 0.8
+    x1 = ops.space_to_depth_u8_bf16(frames, 4)
+    bits2b = torch.full_like(bits2, -1)
+    ops.conv2d_nhwc_bf16(x1, w1, 2, 2, bias=b1, relu=True, out_s2d=True, relu_bits_out=bits2b)
+    assert torch.equal(bits2b, bits2)
+    w2 = (torch.randn(64, 2 * 2 * 128, device=DEV) * 0.05).bfloat16()
+    b2 = torch.randn(64, device=DEV) * 0.1
+    bits3 = torch.full((B * 9 * 9 * 64 // 32,), -1, dtype=torch.int32, device=DEV)
+    x3 = ops.conv2d_nhwc_bf16(x2, w2, 2, 2, bias=b2, relu=True, relu_bits_out=bits3)
+    assert torch.equal(bits3, _pack_bits(x3 > 0)) and 0.2 < float((x3 > 0).float().mean()) < 0.8
+    with pytest.raises(Exception, match='ReLU mask bits'):
+        ops.conv2d_nhwc_bf16(x2, w2, 2, 2, bias=b2, relu=False, relu_bits_out=bits3)
 
 
 @pytest.mark.timeout(120)

@@ -74,7 +74,7 @@ class NatureCnn(ctypes.Structure):
                 [('gemm_ws_bytes', ctypes.c_int64), ('scratch', ctypes.c_void_p), ('scratch_floats', ctypes.c_int64)] +
                 [(name, ctypes.c_int64) for name in ('off_c1', 'off_c2', 'off_c3', 'off_fc', 'off_heads')] +
                 [('grad_map', ctypes.c_void_p), ('grad_dest', ctypes.c_void_p), ('segments', GradSegment * XA_MAX_GRAD_SEGMENTS), ('n_segments', ctypes.c_int32),
-                 ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64)])
+                 ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64), ('relu_bits2', ctypes.c_void_p), ('relu_bits3', ctypes.c_void_p)])
 
 
 # name -> (restype, argtypes); every symbol include/xagents_b200.h declares
@@ -121,7 +121,9 @@ PROTOTYPES = {
     'xa_gemm_bf16_tn_ex': (ctypes.c_int, [ctypes.c_void_p] * 3 + [c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p] +
                            [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_conv2d_nhwc_bf16_ex': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
-                               [ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_stream]),
+                               [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, c_stream]),
+    'xa_conv2d_u8_s2d_bf16_ex': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_f32p,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 8 + [c_stream]),
     'xa_gather_cast_f32': (ctypes.c_int, [c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, c_stream]),
     'xa_gemm_atb_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_gemm_bf16_atb': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),

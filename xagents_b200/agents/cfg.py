@@ -242,12 +242,47 @@ class ModelReader:
         assert outputs, f'{self.cfg_file}: no section is marked output=1'
         return CfgNetwork(layers, plan, common, outputs, self.input_shape, activations)
 
-    def build_adapter(self, device='cuda:0', **adapter_kwargs):
+    def build_tensor_core_network(self):
+        """The `.cfg` as the documented Conv2D network ON THE TCGEN05 KERNELS, forward and backward (`NatureCnnTc`): possible when
+        the file describes exactly that network -- 84x84x4 frames, convolutions 32x8/4, 64x4/2, 64x3/1 (ReLU), flatten, one
+        common Dense of 512 (ReLU), an actor head and a one-unit critic head without output activations
+        (ppo/models/cnn-actor-critic.cfg:1-42).  The initial weights are the ones this reader's initialisers and seed produce
+        for the file (the FC weight re-ordered from Keras' (h, w, c) flatten to the module's (c, h, w))."""
+        from .tc_cnn import NatureCnnTc
+        assert self.conv_dims == 2, 'the tensor-core network is the Conv2D reading of the file: conv_dims=2'
+        ref = self.build_model()
+        layers = list(ref.layers)
+        convs = [l for l in layers if isinstance(l, _ConvChannelsLast)]
+        dense = [l for l in layers if isinstance(l, _Dense)]
+        spec = [(c.conv.in_channels, c.conv.out_channels, c.conv.kernel_size[0], c.conv.stride[0]) for c in convs]
+        ok = (self.input_shape == (84, 84, 4) and spec == [(4, 32, 8, 4), (32, 64, 4, 2), (64, 64, 3, 1)]
+              and all(isinstance(c.act, torch.nn.ReLU) for c in convs) and len(dense) == 3
+              and (dense[0].weight.shape[0], dense[0].weight.shape[1]) == (512, 3136) and isinstance(dense[0].act, torch.nn.ReLU)
+              and dense[1].act is None and dense[2].act is None and dense[2].weight.shape[0] == 1 and not ref.output_is_softmax
+              and len(ref.output_indices) == 2 and dense[1].weight.shape[0] <= 7)
+        if not ok:
+            raise ValueError(f'{self.cfg_file}: not the documented 84x84x4 Nature CNN actor-critic (32x8/4, 64x4/2, 64x3/1, Dense 512, actor <= 7 '
+                             f'units + critic heads without output activations) -- the tensor-core network implements exactly that one')
+        net = NatureCnnTc(4, dense[1].weight.shape[0])
+        mine = [m for m in net.trunk if isinstance(m, torch.nn.Conv2d)]
+        fc = [m for m in net.trunk if isinstance(m, torch.nn.Linear)][0]
+        with torch.no_grad():
+            for dst, src in zip(mine, convs):
+                dst.weight.copy_(src.weight)
+                dst.bias.copy_(src.bias)
+            fc.weight.copy_(dense[0].weight.view(512, 49, 64).permute(0, 2, 1).reshape(512, 3136))
+            fc.bias.copy_(dense[0].bias)
+            net.actor.weight.copy_(dense[1].weight), net.actor.bias.copy_(dense[1].bias)
+            net.critic.weight.copy_(dense[2].weight), net.critic.bias.copy_(dense[2].bias)
+        net.output_is_softmax = False
+        return net
+
+    def build_adapter(self, device='cuda:0', tensor_core_network=False, **adapter_kwargs):
         """Network on `device` inside the `TorchModel` adapter the agents drive, optimiser keywords applied."""
         from .models import TorchModel
         opt = dict(self.optimizer or {})
         kw = dict(lr=opt.get('learning_rate', 7e-4), beta1=opt.get('beta_1', 0.9), beta2=opt.get('beta_2', 0.999),
                   epsilon=opt.get('epsilon', 1e-7))
         kw.update(adapter_kwargs)
-        net = self.build_model().to(device)
+        net = (self.build_tensor_core_network() if tensor_core_network else self.build_model()).to(device)
         return TorchModel(net, output_is_softmax=net.output_is_softmax, **kw)

@@ -9,8 +9,9 @@ Flags, defaults, the agent/non-agent/command split and the assertion messages ar
 and the off-policy agents (dqn, ddpg, td3) are outside the hot path and are refused as invalid commands /
 agents;
 checkpoint, history and wandb flags are accepted by the parser and refused by the agent (agents/base.py).
-Three flags are new: `--conv-dims` (1 = the `.cfg` as the reference's reader builds it, Conv1D; 2 = the documented
-Conv2D network), `--tensor-core-dense` (Dense layers on the tcgen05 GEMM) and `--device`.
+Four flags are new: `--conv-dims` (1 = the `.cfg` as the reference's reader builds it, Conv1D; 2 = the documented
+Conv2D network), `--tensor-core-dense` (Dense layers on the tcgen05 GEMM), `--tensor-core-network` (that Conv2D network, forward
+and backward, on the tcgen05 kernels: `agents.NatureCnnTc` with the file's initialisers and seed) and `--device`.
 """
 import argparse
 import sys
@@ -46,6 +47,8 @@ non_agent_args = {
     'max-frame': _flag('Max & skip during preprocessing', action='store_true'),
     'conv-dims': _flag('1: convolutional sections as the reference reader builds them (Conv1D); 2: Conv2D', int, 1),
     'tensor-core-dense': _flag('Dense layers on the tcgen05 GEMM', action='store_true'),
+    'tensor-core-network': _flag('the documented Conv2D actor-critic CNN, forward and backward, on the tcgen05 kernels (a2c / ppo, 84x84x4 frames)',
+                                 action='store_true'),
     'device': _flag('CUDA device of this process', default='cuda:0'),
 }
 
@@ -153,7 +156,7 @@ commands = {'train': (train_args, 'fit', 'Train given an agent and environment')
 
 # ---------------------------------------------------------------------- factory
 def create_model(env, agent_id, model_type, optimizer_kwargs=None, seed=None, model_cfg=None, conv_dims=1,
-                 tensor_core_dense=False, device='cuda:0'):
+                 tensor_core_dense=False, device='cuda:0', tensor_core_network=False):
     """`.cfg` -> network -> device adapter.  Head widths as in common.py:447-471: n_actions (Discrete) or the action
     dimension (Box), then 1 for an actor-critic file."""
     space = env.action_space
@@ -172,6 +175,10 @@ def create_model(env, agent_id, model_type, optimizer_kwargs=None, seed=None, mo
     elif 'critic' in name:
         units[0] = 1
     role = {'model': 'actor_critic', 'actor_model': 'actor', 'critic_model': 'critic'}[model_type]
+    if tensor_core_network:
+        assert role == 'actor_critic' and agent_id in ('a2c', 'ppo'), '--tensor-core-network is the actor-critic CNN of a2c / ppo'
+        reader = ModelReader(model_cfg, units, env.observation_space.shape, optimizer_kwargs or {}, seed, conv_dims=2)
+        return reader.build_adapter(device, role=role, tensor_core_network=True)
     reader = ModelReader(model_cfg, units, env.observation_space.shape, optimizer_kwargs or {}, seed, conv_dims=conv_dims,
                          tensor_core_dense=tensor_core_dense and role != 'actor')
     return reader.build_adapter(device, role=role)
@@ -226,7 +233,8 @@ def create_agent(agent_id, agent_kwargs, non_agent_kwargs, trial=None):
                         'beta_2': non_agent_kwargs['beta2'], 'epsilon': non_agent_kwargs['opt_epsilon']}
     models = create_models(agent_kwargs, envs[0], agent_id, optimizer_kwargs=optimizer_kwargs,
                            seed=agent_kwargs.get('seed'), conv_dims=non_agent_kwargs.get('conv_dims', 1),
-                           tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device)
+                           tensor_core_dense=bool(non_agent_kwargs.get('tensor_core_dense')), device=device,
+                           tensor_core_network=bool(non_agent_kwargs.get('tensor_core_network')))
     if comm is not None:
         for model in models.values():
             comm.broadcast_(model.flat_param)

@@ -50,6 +50,11 @@ struct FlatParams {
   __nv_bfloat16* y;
   const float* bias;
   const __nv_bfloat16* mask;
+  // ReLU derivatives as BIT masks (bit j of word i <=> element 32 i + j of the compact [B, OH, OW, N] activation is > 0): a
+  // forward layer writes them from its epilogue (bits_out, 1/16 of the activation's bytes), the data gradient of the layer above
+  // reads them (bits_in) instead of re-reading the bf16 activation for its sign -- 210 MB less traffic for conv2's data gradient
+  uint32_t* bits_out;
+  const uint32_t* bits_in;
   int B, H, W, N, OH, OW, PH, PW;
   int relu, out_mode;
   int n_entries;   // taps x 64-channel blocks
@@ -99,12 +104,20 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
   uint32_t* s_a = reinterpret_cast<uint32_t*>(tail + 256);  // [kMaxEntries]
   uint32_t* s_b = s_a + kMaxEntries;
   float* s_bias = reinterpret_cast<float*>(tail + 256 + 2 * kMaxEntries * 4);  // [N <= 128]
-  uint8_t* epi_stage = tail + 2048;  // 8 warps x (32 rows x (2 BN + 16) bytes + 512)
+  uint8_t* epi_stage = tail + 2048;  // 8 warps x (32 rows x (2 BN + 16) bytes + 1024), then the 4 KB bit-expansion table
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   for (int i = threadIdx.x; i < p.n_entries; i += blockDim.x) s_a[i] = p.a_units[i], s_b[i] = p.b_units[i];
+  if (p.bits_in != nullptr) {  // byte b of a row's mask bits -> the AND masks of its eight bf16 values
+    constexpr int kPitchT = BN * 2 + 16;
+    uint32_t* table = reinterpret_cast<uint32_t*>(epi_stage + 8 * (32 * kPitchT + 1024));
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+      const int b = i >> 2, k = i & 3;
+      table[i] = (((b >> (2 * k)) & 1) ? 0x0000FFFFu : 0u) | (((b >> (2 * k + 1)) & 1) ? 0xFFFF0000u : 0u);
+    }
+  }
   const int n_tiles = static_cast<int>((p.Q + kBlockM - 1) / kBlockM);
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
   constexpr uint32_t kTmemCols = 2 * kAccStride;
@@ -320,11 +333,14 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
     const uint32_t hw = static_cast<uint32_t>(p.H) * p.W;
     constexpr int kPitch = BN * 2 + 16;   // bytes; +16 keeps 16-byte accesses of 32 rows conflict-free
     constexpr int kPieces = BN / 8;       // 16-byte pieces per row
-    uint8_t* my_stage = epi_stage + static_cast<size_t>(warp - 2) * (32 * kPitch + 512);
+    uint8_t* my_stage = epi_stage + static_cast<size_t>(warp - 2) * (32 * kPitch + 1024);
     // explicit shared-state-space accesses: through the aligned-up base pointer the compiler only sees generic addresses
     const uint32_t my_stage_u32 = xa::smem_u32(my_stage), s_bias_u32 = xa::smem_u32(s_bias);
     const uint32_t row_out_u32 = my_stage_u32 + 32 * kPitch;  // [32] int64 output offset of the row, -1 = dropped
     const uint32_t row_msk_u32 = row_out_u32 + 256;            // [32] int64 mask offset of the row
+    constexpr int kWords = BN / 32;                             // mask words per row
+    const uint32_t row_bits_u32 = row_out_u32 + 512;            // [32][kWords] this tile's mask bits, row by row (bits_in)
+    const uint32_t table_u32 = xa::smem_u32(epi_stage + 8 * (32 * kPitch + 1024));   // [256][4]: byte of mask bits -> four bf16x2 AND masks
     // phase-2 coordinates: iteration `it` moves 32 consecutive 16-byte pieces = kRowsPerIt rows, so a thread keeps its
     // piece (column group) for the whole kernel and only its row advances -- all per-iteration address arithmetic is
     // an add of a compile-time constant.
@@ -346,6 +362,7 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
       const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
       if (tile >= n_tiles) break;
       const uint32_t acc = grp;
+      int64_t my_out_off = -1;
       {  // phase 0: where does my row go?
         const int ob = static_cast<int>(ob_u);
         const uint32_t oy_u = p.div_w_magic != 0 ? (rem * p.div_w_magic) >> 16 : rem / p.W;
@@ -365,6 +382,21 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
         }
         sts_i64(row_out_u32 + lane * 8, out_off);
         sts_i64(row_msk_u32 + lane * 8, mask_off);
+        my_out_off = out_off;
+        if (p.bits_in != nullptr) {  // my row's mask bits (kWords consecutive words), parked in shared memory for phase 2
+          const uint32_t* src = p.bits_in + (mask_off >> 5);
+          const uint32_t dst = row_bits_u32 + lane * (kWords * 4);
+          if constexpr (kWords == 4) {
+            const uint4 v = valid ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
+            sts_u4(dst, v);
+          } else if constexpr (kWords == 2) {
+            const uint2 v = valid ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0, 0);
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
+          } else {
+            const uint32_t v = valid ? __ldg(src) : 0u;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+          }
+        }
       }
       __syncwarp();
       // the ReLU-derivative mask does not depend on the accumulator: fetch it (coalesced) before waiting
@@ -385,16 +417,25 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
         const uint32_t dst = my_stage_u32 + lane * kPitch + c0 * 2;
+        uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b0 = lds_f4(s_bias_u32 + (c0 + 8 * j) * 4), b1 = lds_f4(s_bias_u32 + (c0 + 8 * j + 4) * 4);
+          float f[8];
+          f[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, lo), f[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, lo);
+          f[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, lo), f[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, lo);
+          f[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, lo), f[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, lo);
+          f[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, lo), f[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, lo);
+          if (p.bits_out != nullptr) {  // ReLU output (>= +0): positive <=> its bit pattern, negated as an integer, has the sign bit set;
+#pragma unroll                          // one funnel shift per value collects the flags (first value in the top bit: reversed below)
+            for (int e = 0; e < 8; ++e) bits = __funnelshift_l(0u - __float_as_uint(f[e]), bits, 1);
+          }
           __nv_bfloat162 h[4];
-          h[0] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, lo), fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, lo));
-          h[1] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, lo), fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, lo));
-          h[2] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, lo), fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, lo));
-          h[3] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, lo), fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, lo));
+          h[0] = __floats2bfloat162_rn(f[0], f[1]), h[1] = __floats2bfloat162_rn(f[2], f[3]);
+          h[2] = __floats2bfloat162_rn(f[4], f[5]), h[3] = __floats2bfloat162_rn(f[6], f[7]);
           sts_u4(dst + j * 16, *reinterpret_cast<uint4*>(h));
         }
+        if (p.bits_out != nullptr && my_out_off >= 0) p.bits_out[(my_out_off >> 5) + (c0 >> 5)] = __brev(bits);
       }
       // the accumulator is drained: hand it back before the global stores
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -405,7 +446,12 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
         const int64_t off0 = lds_i64(row_out_u32 + (it * kRowsPerIt + row0) * 8);
         if (off0 >= 0) {
           uint4 val = lds_u4(my_piece_u32 + it * (kRowsPerIt * kPitch));
-          if (p.mask != nullptr) {  // ReLU derivative of the layer below: zero where its activation was <= 0
+          if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
+            uint32_t b;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row_bits_u32 + (it * kRowsPerIt + row0) * (kWords * 4) + piece));
+            const uint4 mk = lds_u4(table_u32 + b * 16);
+            val.x &= mk.x, val.y &= mk.y, val.z &= mk.z, val.w &= mk.w;
+          } else if (p.mask != nullptr) {  // ReLU derivative of the layer below: zero where its activation was <= 0
             const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw[it]);
             const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
             val.x &= __hgt2_mask(mk[0], zero);
@@ -451,8 +497,8 @@ int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap&
 
 // Returns XA_OK after launching, or 1 when the shape does not fit this kernel (the caller falls back to conv_tc.cu's).
 int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels, int kh, int kw,
-                     int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int OH, int OW, int PH, int PW,
-                     xa_stream_t stream) {
+                     int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int mask_is_bits, uint32_t* relu_bits_out,
+                     int OH, int OW, int PH, int PW, xa_stream_t stream) {
   const char* what = "xa_conv2d_nhwc_bf16";
   if (!(n_out == 32 || n_out == 64 || n_out == 128)) return 1;
   // Output pixels are indexed on the input grid, and a kept output (y < OH, x < OW) must never read below / right of its
@@ -470,12 +516,17 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   FlatParams p{};
   p.w_bytes = static_cast<uint32_t>(n_entries) * n_out * 128u;
   p.stage_bytes = static_cast<uint32_t>(kc_blocks) * win_rows * 128u;
-  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 512);  // the epilogue warps' transposing tiles
+  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 1024) + 4096;  // the epilogue warps' transposing tiles + row tables, the bit-expansion table
   const int64_t budget = 227 * 1024 - 1024 /*alignment*/ - 2048 /*barriers, tables, bias*/ - epi_bytes - p.w_bytes;
   int stages = static_cast<int>(budget / p.stage_bytes);
   if (stages < 2) return 1;
   if (stages > 6) stages = 6;
-  p.y = static_cast<__nv_bfloat16*>(y), p.bias = bias, p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+  p.y = static_cast<__nv_bfloat16*>(y), p.bias = bias;
+  p.mask = mask_is_bits ? nullptr : static_cast<const __nv_bfloat16*>(relu_mask);
+  p.bits_in = mask_is_bits ? static_cast<const uint32_t*>(relu_mask) : nullptr;
+  p.bits_out = relu_bits_out;
+  XA_REQUIRE(relu_bits_out == nullptr || (relu && (out_mode == 1 || (out_mode == 0 && PH == OH && PW == OW))), XA_EINVAL,
+             "%s: ReLU mask bits are written by ReLU layers with a compact output", what);
   p.B = batch, p.H = height, p.W = width, p.N = n_out, p.OH = OH, p.OW = OW, p.PH = PH, p.PW = PW;
   p.relu = relu, p.out_mode = out_mode;
   p.n_entries = n_entries, p.kc_blocks = kc_blocks, p.win_rows = win_rows, p.stages = stages, p.Q = Q;
@@ -505,8 +556,8 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
 // kh x kw stride-1 kernel over the 4x4 space-to-depth grid (= a 4kh x 4kw / 4 convolution of the frames), w [n_out, kh*kw*64]
 // bf16 with K ordered (kh, kw, dy, dx, c), x/255 applied on the way in.
 static int conv_u8_s2d(const char* what, const uint8_t* frames, const int32_t* frame_idx, int64_t n_frames, int idx_n_steps, int idx_n_envs,
-                       const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height, int width, int kh, int kw, int n_out,
-                       int relu, int out_s2d, xa_stream_t stream) {
+                       const void* w, const float* bias, void* y, void* x_s2d_out, uint32_t* relu_bits_out, int batch, int height, int width,
+                       int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
   XA_REQUIRE(frames && w && y, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(batch > 0 && height > 0 && width > 0 && height % 4 == 0 && width % 4 == 0 && kh > 0 && kw > 0, XA_EINVAL,
              "%s: batch=%d frames %dx%d kernel %dx%d", what, batch, height, width, kh, kw);
@@ -528,12 +579,14 @@ static int conv_u8_s2d(const char* what, const uint8_t* frames, const int32_t* f
   p.stage_bytes = static_cast<uint32_t>(win_rows) * 128u;
   p.raw_tx_bytes = static_cast<uint32_t>(box_rows) * W * 64u;
   p.raw_stage_bytes = ((p.raw_tx_bytes + 1023u) / 1024u) * 1024u;
-  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 512);
+  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 1024) + 4096;
   const int64_t budget = 227 * 1024 - 1024 - 2048 - epi_bytes - p.w_bytes - static_cast<int64_t>(kRawStages) * p.raw_stage_bytes;
   int stages = static_cast<int>(budget / p.stage_bytes);
   XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: shared memory does not hold two operand stages", what);
   if (stages > 6) stages = 6;
   p.y = static_cast<__nv_bfloat16*>(y), p.bias = bias, p.mask = nullptr;
+  XA_REQUIRE(relu_bits_out == nullptr || (relu && xa::aligned(relu_bits_out, 16)), XA_EINVAL, "%s: ReLU mask bits need relu = 1 and a 16-byte aligned buffer", what);
+  p.bits_out = relu_bits_out, p.bits_in = nullptr;
   p.B = batch, p.H = H, p.W = W, p.N = n_out, p.OH = OH, p.OW = OW, p.PH = OH, p.PW = OW;
   p.relu = relu, p.out_mode = out_s2d ? 1 : 0;
   p.n_entries = n_entries, p.kc_blocks = 1, p.win_rows = win_rows, p.stages = stages, p.Q = Q, p.min_shift = 0;
@@ -583,18 +636,26 @@ static int conv_u8_s2d(const char* what, const uint8_t* frames, const int32_t* f
 
 extern "C" int xa_conv2d_u8_s2d_bf16(const uint8_t* frames, const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height,
                                      int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
-  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16", frames, nullptr, 0, 0, 0, w, bias, y, x_s2d_out, batch, height, width, kh, kw, n_out, relu, out_s2d,
-                     stream);
+  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16", frames, nullptr, 0, 0, 0, w, bias, y, x_s2d_out, nullptr, batch, height, width, kh, kw, n_out, relu,
+                     out_s2d, stream);
 }
 
-// The same layer reading its `batch` frames THROUGH A PERMUTATION of a larger frame store: frame f = row frame_idx[f] of
-// frames [n_frames, height, width, 4] (with n_steps > 0 the ids are env-major sample ids of a time-major [n_steps, n_envs]
-// rollout, xagents/base.py:559-564) -- get_mini_batches' tf.gather of the states (ppo/agent.py:139-155) folded into the
-// network's first layer: the gathered minibatch is never written to or read back from HBM.
+// The same layer with its options spelled out.  frame_idx != NULL: the `batch` frames are read THROUGH A PERMUTATION of a larger
+// frame store: frame f = row frame_idx[f] of frames [n_frames, height, width, 4] (with n_steps > 0 the ids are env-major sample
+// ids of a time-major [n_steps, n_envs] rollout, xagents/base.py:559-564) -- get_mini_batches' tf.gather of the states
+// (ppo/agent.py:139-155) folded into the network's first layer: the gathered minibatch is never written to or read back from
+// HBM.  relu_bits_out != NULL: one bit per output element (> 0), the ReLU derivative the data gradient of the next layer needs.
+extern "C" int xa_conv2d_u8_s2d_bf16_ex(const uint8_t* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps, int n_envs,
+                                        const void* w, const float* bias, void* y, void* x_s2d_out, uint32_t* relu_bits_out, int batch,
+                                        int height, int width, int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
+  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16_ex", frames, frame_idx, n_frames, n_steps, n_envs, w, bias, y, x_s2d_out, relu_bits_out, batch, height,
+                     width, kh, kw, n_out, relu, out_s2d, stream);
+}
+
 extern "C" int xa_conv2d_u8_s2d_bf16_indexed(const uint8_t* frames, int64_t n_frames, const int32_t* frame_idx, int n_steps, int n_envs,
                                              const void* w, const float* bias, void* y, void* x_s2d_out, int batch, int height, int width,
                                              int kh, int kw, int n_out, int relu, int out_s2d, xa_stream_t stream) {
   XA_REQUIRE(frame_idx != nullptr, XA_EINVAL, "xa_conv2d_u8_s2d_bf16_indexed: null frame_idx");
-  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16_indexed", frames, frame_idx, n_frames, n_steps, n_envs, w, bias, y, x_s2d_out, batch, height, width,
-                     kh, kw, n_out, relu, out_s2d, stream);
+  return conv_u8_s2d("xa_conv2d_u8_s2d_bf16_indexed", frames, frame_idx, n_frames, n_steps, n_envs, w, bias, y, x_s2d_out, nullptr, batch, height,
+                     width, kh, kw, n_out, relu, out_s2d, stream);
 }

@@ -16,8 +16,8 @@
 #include <cstdlib>
 
 int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels, int kh, int kw,
-                     int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int OH, int OW, int PH, int PW,
-                     xa_stream_t stream);
+                     int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int mask_is_bits, uint32_t* relu_bits_out,
+                     int OH, int OW, int PH, int PW, xa_stream_t stream);
 
 namespace {
 
@@ -338,12 +338,12 @@ int xa_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y
                         int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_s2d, const void* relu_mask,
                         xa_stream_t stream) {
   return xa_conv2d_nhwc_bf16_ex(x, w, bias, y, batch, height, width, channels, kh, kw, n_out, pad_y, pad_x, relu, out_s2d, relu_mask, 0, 0,
-                                0, 0, 0, stream);
+                                0, 0, nullptr, 0, stream);
 }
 
 int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void* y, int batch, int height, int width, int channels,
                            int kh, int kw, int n_out, int pad_y, int pad_x, int relu, int out_mode, const void* relu_mask, int out_h,
-                           int out_w, int out_grid_h, int out_grid_w, int flags, xa_stream_t stream) {
+                           int out_w, int out_grid_h, int out_grid_w, uint32_t* relu_bits_out, int flags, xa_stream_t stream) {
   const char* what = "xa_conv2d_nhwc_bf16";
   const int out_s2d = out_mode;
   XA_REQUIRE(x && w && y, XA_EINVAL, "%s: null pointer", what);
@@ -373,6 +373,7 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
   p.relu = relu, p.out_s2d = out_s2d;
   p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
   XA_REQUIRE(p.OW <= kBlockM, XA_EINVAL, "%s: output width %d exceeds one tile (128)", what, p.OW);
+  XA_REQUIRE(xa::aligned(relu_bits_out, 16), XA_EALIGN, "%s: relu_bits_out must be 16-byte aligned", what);
   XA_REQUIRE(out_s2d != 1 || (p.OH % 2 == 0 && p.OW % 2 == 0 && relu_mask == nullptr), XA_EINVAL,
              "%s: out_s2d needs even output height/width and no mask", what);
   // Preferred: the flat kernel (conv_flat_tc.cu), every input pixel fetched once per tile.  It needs the taps' row shifts
@@ -380,9 +381,11 @@ int xa_conv2d_nhwc_bf16_ex(const void* x, const void* w, const float* bias, void
   static const bool flat_enabled = !(std::getenv("XA_CONV_FLAT") && std::atoi(std::getenv("XA_CONV_FLAT")) == 0);
   if (flat_enabled && ((pad_y == 0 && pad_x == 0) || (flags & XA_CONV_INPUT_ZERO_BORDER))) {
     const int rc = xa_conv_flat_try(x, w, bias, y, batch, height, width, channels, kh, kw, n_out, pad_y, pad_x, relu, out_mode, relu_mask,
-                                    p.OH, p.OW, p.PH, p.PW, stream);
+                                    (flags & XA_CONV_MASK_BITS) != 0 && relu_mask != nullptr, relu_bits_out, p.OH, p.OW, p.PH, p.PW, stream);
     if (rc != 1) return rc;  // launched (or failed with an error); 1 = shape not covered, use the per-tap kernel below
   }
+  XA_REQUIRE(relu_bits_out == nullptr && !((flags & XA_CONV_MASK_BITS) && relu_mask), XA_EINVAL,
+             "%s: ReLU mask bits are implemented by the flat kernel only (unpadded or zero-bordered input, n_out 32 / 64 / 128)", what);
   // tile box: whole output rows (bx = OW), by rows (a divisor of OH), bb images; maximise filled GEMM rows <= 128
   p.bx = p.OW;
   int best = 0;

@@ -26,15 +26,15 @@ static int forward_impl(const char* what, const xa_nature_cnn_t* n, const void* 
   XA_TRY(check_net(n, what));
   XA_REQUIRE(frames != nullptr, XA_EINVAL, "%s: null frames", what);
   const int B = n->batch;
-  if (frame_idx != nullptr)  // the minibatch gather folded into the first layer: frames = the whole rollout, read through the permutation
-    XA_TRY(xa_conv2d_u8_s2d_bf16_indexed(static_cast<const uint8_t*>(frames), n_frames, frame_idx, n_steps, n_envs, n->w1, n->b1, n->x2, n->x1, B,
-                                         84, 84, 2, 2, 32, 1, 1, stream));
-  else if (frames_s2d)
-    XA_TRY(xa_conv2d_nhwc_bf16_ex(frames, n->w1, n->b1, n->x2, B, 21, 21, 64, 2, 2, 32, 0, 0, 1, 1, nullptr, 0, 0, 0, 0, 0, stream));
-  else  // /255 + space-to-depth + conv1 in one kernel; x1 (only the backward pass reads it) is written from shared memory
-    XA_TRY(xa_conv2d_u8_s2d_bf16(static_cast<const uint8_t*>(frames), n->w1, n->b1, n->x2, n->x1, B, 84, 84, 2, 2, 32, 1, 1, stream));
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x2, n->w2, n->b2, n->x3, B, 10, 10, 128, 2, 2, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, 0, stream));
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, 0, stream));
+  XA_REQUIRE((n->relu_bits2 == nullptr) == (n->relu_bits3 == nullptr), XA_EINVAL, "%s: relu_bits2 and relu_bits3 go together", what);
+  if (frames_s2d)
+    XA_TRY(xa_conv2d_nhwc_bf16_ex(frames, n->w1, n->b1, n->x2, B, 21, 21, 64, 2, 2, 32, 0, 0, 1, 1, nullptr, 0, 0, 0, 0, n->relu_bits2, 0, stream));
+  else  // /255 + space-to-depth + conv1 in one kernel; x1 (only the backward pass reads it) is written from shared memory.  With
+        // frame_idx: the minibatch gather folded in as well -- frames = the whole rollout, read through the permutation
+    XA_TRY(xa_conv2d_u8_s2d_bf16_ex(static_cast<const uint8_t*>(frames), n_frames, frame_idx, n_steps, n_envs, n->w1, n->b1, n->x2, n->x1,
+                                    n->relu_bits2, B, 84, 84, 2, 2, 32, 1, 1, stream));
+  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x2, n->w2, n->b2, n->x3, B, 10, 10, 128, 2, 2, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, n->relu_bits3, 0, stream));
+  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
   XA_TRY(xa_gemm_bf16_tn_ex(n->y3, n->wf, n->h, n->bf, B, 512, 3136, 512, 1, 1, nullptr, 512, 0, 0, n->gemm_ws, n->gemm_ws_bytes, stream));
   return xa_heads_forward_bf16(n->h, n->wh, n->bh, n->actor, n->critic, B, 512, n->n_actions, stream);
 }
@@ -72,11 +72,12 @@ int xa_nature_cnn_backward(const xa_nature_cnn_t* n, const void* frames_s2d_or_n
   XA_TRY(xa_gemm_bf16_tn_ex(n->dh, n->wf_t, n->g3, nullptr, B, 3136, 512, 9 * 9 * 64, 1, 0, n->y3, 3136, 7 * 64, 9 * 64, nullptr, 0, stream));
   // conv3, conv2: weight gradient from the natural NHWC tensors, data gradient = flat convolution with flipped weights
   XA_TRY(xa_conv_wgrad_nhwc_bf16_partial(n->x3, n->g3, 64, 64, 3, 3, 9, static_cast<int64_t>(B) * 81, sc + n->off_c3, bytes_from(n->off_c3), stream));
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->g3, n->w3_flip, nullptr, n->g2, B, 9, 9, 64, 3, 3, 64, 2, 2, 0, 0, n->x3, 9, 9, 10, 10,
-                                XA_CONV_INPUT_ZERO_BORDER, stream));
+  const bool bits = n->relu_bits2 != nullptr && n->relu_bits3 != nullptr;  // ReLU derivatives from the forward pass's bit masks
+  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->g3, n->w3_flip, nullptr, n->g2, B, 9, 9, 64, 3, 3, 64, 2, 2, 0, 0, bits ? static_cast<const void*>(n->relu_bits3) : n->x3,
+                                9, 9, 10, 10, nullptr, XA_CONV_INPUT_ZERO_BORDER | (bits ? XA_CONV_MASK_BITS : 0), stream));
   XA_TRY(xa_conv_wgrad_nhwc_bf16_partial(n->x2, n->g2, 64, 128, 2, 2, 10, static_cast<int64_t>(B) * 100, sc + n->off_c2, bytes_from(n->off_c2), stream));
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->g2, n->w2_flip, nullptr, n->g1, B, 10, 10, 64, 2, 2, 128, 1, 1, 0, 2, n->x2, 10, 10, 21, 21,
-                                XA_CONV_INPUT_ZERO_BORDER, stream));
+  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->g2, n->w2_flip, nullptr, n->g1, B, 10, 10, 64, 2, 2, 128, 1, 1, 0, 2, bits ? static_cast<const void*>(n->relu_bits2) : n->x2,
+                                10, 10, 21, 21, nullptr, XA_CONV_INPUT_ZERO_BORDER | (bits ? XA_CONV_MASK_BITS : 0), stream));
   XA_TRY(xa_conv_wgrad_nhwc_bf16_partial(x1, n->g1, 32, 64, 2, 2, 21, static_cast<int64_t>(B) * 441, sc + n->off_c1, bytes_from(n->off_c1), stream));
   return xa_grad_finalize_f32(sc, n->grad_map, n->grad_dest, n->segments, n->n_segments, flat_grad, n->n_grad, stream);
 }

@@ -482,7 +482,7 @@ def to_bf16(src, *, transpose=False, pad_to=8, stream=None):
 
 
 def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=(0, 0), relu_mask=None, out=None, out_hw=None,
-                     unpack_s2d=False, zero_border=False, stream=None):
+                     unpack_s2d=False, zero_border=False, relu_bits_out=None, stream=None):
     """Stride-1 NHWC convolution on tcgen05 (implicit GEMM, no im2col).  x [B,H,W,C] bf16; w [N, kh*kw*C] bf16
     with K ordered (kh, kw, c); zero padding `pad`=(py, px).  Returns y [B,OH,OW,N] bf16, or its 2x2
     space-to-depth form [B,OH/2,OW/2,4N].  `relu_mask` (compact [B,OH,OW,N]) zeroes y where mask <= 0.
@@ -490,7 +490,10 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
     [B,GH,GW,N] larger than the output is a zero-bordered grid written in place; `unpack_s2d` spreads the N = (dy,dx,N/4)
     channels over pixels (2y+dy, 2x+dx) of `out` [B,GH,GW,N/4]; `zero_border` promises that the last pad columns / rows
     of every input image are zero (a gradient on a zero-bordered grid), which lets a padded convolution use the flat
-    kernel that fetches every input pixel once."""
+    kernel that fetches every input pixel once.
+    ReLU derivatives as bit masks: `relu_bits_out` (int32 [numel(y) / 32], a ReLU layer with a compact or 2x2-packed output)
+    receives one bit per output element (> 0); a `relu_mask` of dtype int32 is read as such a bit mask of the compact
+    [B,OH,OW,N] tensor instead of the bf16 activation."""
     xx, ww = _dev(x, 'bfloat16'), _dev(w, 'bfloat16')
     B, H, W, C = xx.shape
     N = ww.shape[0]
@@ -503,18 +506,21 @@ def conv2d_nhwc_bf16(x, w, kh, kw, *, bias=None, relu=False, out_s2d=False, pad=
         raise ValueError(f'out {tuple(y.shape)} cannot hold an output of {shape}')
     gh, gw = (y.shape[1], y.shape[2]) if tuple(y.shape) != shape else (0, 0)
     bias_a = _dev(bias, 'float32') if bias is not None else None
-    mask_a = _dev(relu_mask, 'bfloat16') if relu_mask is not None else None
-    if mask_a is not None and mask_a.size != B * OH * OW * N:
-        raise ValueError('relu_mask must have the compact output layout [B, OH, OW, N]')
+    mask_bits = relu_mask is not None and isinstance(relu_mask, torch.Tensor) and relu_mask.dtype == torch.int32
+    mask_a = _dev(relu_mask, 'int32' if mask_bits else 'bfloat16') if relu_mask is not None else None
+    if mask_a is not None and mask_a.size != B * OH * OW * N // (32 if mask_bits else 1):
+        raise ValueError('relu_mask must have the compact output layout [B, OH, OW, N] (one bit per element for an int32 mask)')
+    if relu_bits_out is not None and (relu_bits_out.dtype != torch.int32 or relu_bits_out.numel() != y.numel() // 32 or not relu_bits_out.is_contiguous()):
+        raise ValueError(f'relu_bits_out must be a contiguous int32 tensor of {y.numel() // 32} words')
     _call(xx, 'xa_conv2d_nhwc_bf16_ex', _ptr(xx), _ptr(ww), _ptr(bias_a), _tptr(y), B, H, W, C, kh, kw, N, int(pad[0]), int(pad[1]),
               int(bool(relu)), 2 if unpack_s2d else int(bool(out_s2d)), _ptr(mask_a), int(OH) if out_hw is not None else 0,
-              int(OW) if out_hw is not None else 0, int(gh), int(gw), int(bool(zero_border)), stream)
+              int(OW) if out_hw is not None else 0, int(gh), int(gw), _tptr(relu_bits_out), int(bool(zero_border)) | (2 if mask_bits else 0), stream)
     _count()
     return y
 
 
 def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=False, out=None, x_s2d_out=None, idx=None, time_major=None,
-                       stream=None):
+                       relu_bits_out=None, stream=None):
     """The 4x4-strided first layer straight from uint8 frames [B,H,W,4]: /255, space-to-depth and the kh x kw stride-1
     convolution over the [B,H/4,W/4,64] grid in one kernel (bit-identical to space_to_depth_u8_bf16 + conv2d_nhwc_bf16).
     `x_s2d_out` [B,H/4,W/4,64] bf16 also receives the scaled space-to-depth tensor (for the weight gradient).
@@ -533,10 +539,12 @@ def conv2d_u8_s2d_bf16(frames, w, kh, kw, *, bias=None, relu=False, out_s2d=Fals
     bias_a = _dev(bias, 'float32') if bias is not None else None
     if x_s2d_out is not None and (x_s2d_out.dtype != torch.bfloat16 or tuple(x_s2d_out.shape) != (B, H // 4, W // 4, 64) or not x_s2d_out.is_contiguous()):
         raise ValueError(f'x_s2d_out must be a contiguous bf16 [{B}, {H // 4}, {W // 4}, 64] tensor')
-    if ids is not None:
+    if relu_bits_out is not None and (relu_bits_out.dtype != torch.int32 or relu_bits_out.numel() != y.numel() // 32 or not relu_bits_out.is_contiguous()):
+        raise ValueError(f'relu_bits_out must be a contiguous int32 tensor of {y.numel() // 32} words')
+    if ids is not None or relu_bits_out is not None:
         T, E = _layout(time_major)
-        _call(f, 'xa_conv2d_u8_s2d_bf16_indexed', _ptr(f), n_frames, _ptr(ids), T, E, _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W,
-              kh, kw, N, int(bool(relu)), int(bool(out_s2d)), stream)
+        _call(f, 'xa_conv2d_u8_s2d_bf16_ex', _ptr(f), n_frames, _ptr(ids), T, E, _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out),
+              _tptr(relu_bits_out), B, H, W, kh, kw, N, int(bool(relu)), int(bool(out_s2d)), stream)
     else:
         _call(f, 'xa_conv2d_u8_s2d_bf16', _ptr(f), _ptr(ww), _ptr(bias_a), _tptr(y), _tptr(x_s2d_out), B, H, W, kh, kw, N, int(bool(relu)),
               int(bool(out_s2d)), stream)
