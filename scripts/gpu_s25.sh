@@ -1,0 +1,8 @@
+#!/bin/bash
+O=gpurun_out/s25; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_plan.py -m gpu -q -x > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+for i in 1 2; do timeout 300 python scripts/update_launches.py 2>&1 | tail -1; done > $O/update_eager.log
+for i in 1 2; do XA_NO_RELU_BITS=1 timeout 300 python scripts/update_launches.py 2>&1 | tail -1; done > $O/update_eager_nobits.log
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/update_launches.csv python scripts/update_launches.py > $O/ncu_update.log 2>&1
+XA_NO_RELU_BITS=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/update_launches_nobits.csv python scripts/update_launches.py > $O/ncu_update2.log 2>&1
+tail -3 $O/pytest.log; cat $O/update_eager.log; echo nobits; cat $O/update_eager_nobits.log

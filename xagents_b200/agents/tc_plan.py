@@ -9,6 +9,7 @@ clip + Adam (xagents/ppo/agent.py:112-137: model call, tape.gradient, clip_by_gl
 The autograd form of the same pipeline (agents/tc_cnn.py `_NatureCnnFn`) stays as the checker: tests compare the two.
 """
 import ctypes
+import os
 
 import torch
 
@@ -60,7 +61,8 @@ class NaturePlan:
         # the data gradients of conv2 / conv3 instead of the bf16 activations (295 MB -> 18 MB per 8192-frame minibatch)
         self.bits2 = torch.empty(B * 10 * 10 * 128 // 32, dtype=torch.int32, device=dev)
         self.bits3 = torch.empty(B * 9 * 9 * 64 // 32, dtype=torch.int32, device=dev)
-        net.relu_bits2, net.relu_bits3 = self.bits2.data_ptr(), self.bits3.data_ptr()
+        if os.environ.get('XA_NO_RELU_BITS') != '1':               # tuning switch: the data gradients read the bf16 activations instead
+            net.relu_bits2, net.relu_bits3 = self.bits2.data_ptr(), self.bits3.data_ptr()
         splits, ld = ctypes.c_int(), ctypes.c_int()
         conv = {}
         off = 0

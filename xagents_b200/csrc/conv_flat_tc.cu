@@ -20,9 +20,20 @@ namespace {
 
 using namespace xa_tc;
 
-constexpr int kFlatThreads = 64 + 8 * 32;
+// Epilogue groups of four warps, one TMEM accumulator each.  The bf16-input kernels run FOUR (all 512 TMEM columns at BN = 128):
+// with two, the data gradients and the 64-channel layers were bound by the instruction issue of their eight epilogue warps
+// (conv2's data gradient: 5600 epilogue warp-instructions per tile at IPC 1.3 = the 4200 cycles a tile took; DRAM, the tensor pipe
+// and shared memory all below 50 %) -- halving their DRAM reads with bit masks changed nothing.  The uint8 first layer keeps two
+// (its five converter warps need the registers, and its 32-column epilogue is short).
+constexpr int kGroupsU8 = 2;
+__host__ __device__ constexpr int groups_bf16(int bn) { return bn >= 128 ? 4 : 2; }   // measured: four groups gain 11 us at BN = 128, lose 2.5 at 64
 constexpr int kConvertWarps = 5;                              // uint8 input: five more warps turn raw windows into bf16 operand tiles
-constexpr int kFlatThreadsU8 = kFlatThreads + kConvertWarps * 32;
+__host__ __device__ constexpr int flat_threads(int bn, bool u8) {
+  return 64 + (u8 ? kGroupsU8 : groups_bf16(bn)) * 4 * 32 + (u8 ? kConvertWarps * 32 : 0);
+}
+constexpr int kEpiPitch = 32 * 2 + 16;                        // one staged row of a 32-column chunk; +16 keeps 16-byte accesses of 32 rows conflict-free
+__host__ __device__ constexpr int epi_warp_bytes(int bn) { return 32 * kEpiPitch + 512 + 32 * (bn / 32) * 4; }   // per epilogue warp: the chunk's tile + row tables
+//                                                                                            (output offsets, mask offsets, mask bits)
 constexpr int kRawStages = 4;
 
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
@@ -84,7 +95,7 @@ struct FlatParams {
 // to bf16 and write the SWIZZLE_128B operand tile the MMA reads -- the 2x larger bf16 space-to-depth tensor is never written to or read from HBM (xagents/base.py:505-506: the
 // cast and the division of the image batch, fused here into the first layer).
 template <int BN, bool kU8 = false>
-__global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat_kernel(const __grid_constant__ CUtensorMap map_x,
+__global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                  const __grid_constant__ CUtensorMap map_w,
                                                                  const __grid_constant__ CUtensorMap map_x1,
                                                                  const __grid_constant__ FlatParams p) {
@@ -95,24 +106,24 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
   uint8_t* tail = raw_ring + (kU8 ? static_cast<size_t>(kRawStages) * p.raw_stage_bytes : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + 8;
+  constexpr int kGroups = kU8 ? kGroupsU8 : groups_bf16(BN);
   uint64_t* acc_full = empty + 8;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* w_full = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* w_full = acc_empty + 4;
   uint64_t* raw_full = w_full + 1;             // [kRawStages]
   uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
-  uint32_t* s_a = reinterpret_cast<uint32_t*>(tail + 256);  // [kMaxEntries]
+  uint32_t* s_a = reinterpret_cast<uint32_t*>(tail + 512);  // [kMaxEntries]
   uint32_t* s_b = s_a + kMaxEntries;
-  float* s_bias = reinterpret_cast<float*>(tail + 256 + 2 * kMaxEntries * 4);  // [N <= 128]
-  uint8_t* epi_stage = tail + 2048;  // 8 warps x (32 rows x (2 BN + 16) bytes + 1024), then the 4 KB bit-expansion table
+  float* s_bias = reinterpret_cast<float*>(tail + 512 + 2 * kMaxEntries * 4);  // [N <= 128]
+  uint8_t* epi_stage = tail + 2048;  // 4 kGroups warps x epi_warp_bytes(BN), then (bits_in only) the 4 KB bit-expansion table
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   for (int i = threadIdx.x; i < p.n_entries; i += blockDim.x) s_a[i] = p.a_units[i], s_b[i] = p.b_units[i];
   if (p.bits_in != nullptr) {  // byte b of a row's mask bits -> the AND masks of its eight bf16 values
-    constexpr int kPitchT = BN * 2 + 16;
-    uint32_t* table = reinterpret_cast<uint32_t*>(epi_stage + 8 * (32 * kPitchT + 1024));
+    uint32_t* table = reinterpret_cast<uint32_t*>(epi_stage + 4 * kGroups * epi_warp_bytes(BN));
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
       const int b = i >> 2, k = i & 3;
       table[i] = (((b >> (2 * k)) & 1) ? 0x0000FFFFu : 0u) | (((b >> (2 * k + 1)) & 1) ? 0xFFFF0000u : 0u);
@@ -120,7 +131,8 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
   }
   const int n_tiles = static_cast<int>((p.Q + kBlockM - 1) / kBlockM);
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
-  constexpr uint32_t kTmemCols = 2 * kAccStride;
+  constexpr uint32_t kTmemCols = kGroups * kAccStride;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation: a power of two, at most 512 columns");
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
       xa::mbar_init(full + s, kU8 ? kConvertWarps : 1);  // filled by TMA, or by one arrival per converter warp
       xa::mbar_init(empty + s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kGroups; ++a) {
       xa::mbar_init(acc_full + a, 1);
       xa::mbar_init(acc_empty + a, 4);
     }
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
       uint32_t phase = 0, lt = 0;
       mbar_wait_wd(w_full, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t acc = lt & 1, use = lt >> 1;
+        const uint32_t acc = lt % kGroups, use = lt / kGroups;
         if (use > 0) {
           mbar_wait_wd(acc_empty + acc, (use - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
         if (++s == p.stages) s = 0, phase ^= 1;
       }
     }
-  } else if (kU8 && warp >= 10) {
+  } else if (kU8 && warp >= 2 + 4 * kGroupsU8) {
     // ---- converters (uint8 input): raw window stage -> bf16 operand stage.  A thread owns one window pixel: its four
     // 16-byte pieces (the (dx, c) bytes of dy = 0..3, one image row apart) become the eight 16-byte chunks of the pixel's
     // 128-byte operand row, stored where SWIZZLE_128B puts them (chunk ^ (row & 7): stage bases are 1024-byte aligned, so
@@ -259,7 +271,7 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
     // [Q, 64] bf16 space-to-depth tensor the weight-gradient kernel reads in the backward pass: each warp's elected lane
     // TMA-stores its 32 rows from the operand stage (SWIZZLE_128B undone by the store's tensor map) and, before writing
     // that stage again, waits until the store has read it.
-    const int cw = warp - 10;
+    const int cw = warp - (2 + 4 * kGroupsU8);
     const float mul = 1.0f / 255.0f, bias23 = -8388608.0f * mul;
     const uint32_t ring_u32 = xa::smem_u32(ring), raw_u32 = xa::smem_u32(raw_ring);
     const uint32_t dy_pitch = static_cast<uint32_t>(p.W) * 16u;  // one image row
@@ -321,44 +333,34 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
     }
     if (storing && lane == 0) xa::bulk_wait_all<0>();  // shared memory must outlive the stores
   } else {
-    // ---- epilogue: group `grp` (warps 2-5 / 6-9) owns accumulator `grp` = the CTA's tiles of that parity.
+    // ---- epilogue: group `grp` (warps 2 + 4 grp ..) owns accumulator `grp` = the CTA's tiles lt with lt % kGroups == grp.
     // tcgen05.ld hands every thread one ROW (32 consecutive columns): stored directly, a warp-wide 16-byte access touches
     // 32 different lines, and those load/store wavefronts -- not the tensor pipe, not HBM -- bounded the data-gradient
-    // layers (ncu: LSU 80 % busy).  So each warp transposes through its own padded shared-memory tile: phase 1 writes
-    // rows as they come out of TMEM (thread = row), phase 2 moves 16-byte pieces with consecutive lanes on consecutive
-    // pieces of a row, so that mask loads and output stores are coalesced (4 wavefronts per access instead of 32).
+    // layers (ncu: LSU 80 % busy).  So each warp transposes through its own padded shared-memory tile, one 32-column chunk at a
+    // time: phase 1 writes the chunk's rows as they come out of TMEM (thread = row), phase 2 moves 16-byte pieces with four
+    // consecutive lanes on the 64 bytes of a row, so that mask loads and output stores are coalesced.  Chunk by chunk the
+    // tile costs 2.5 KB of shared memory per warp whatever BN is, which is what lets four groups fit.
     const int quad = warp & 3;
     const uint32_t grp = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t hw = static_cast<uint32_t>(p.H) * p.W;
-    constexpr int kPitch = BN * 2 + 16;   // bytes; +16 keeps 16-byte accesses of 32 rows conflict-free
-    constexpr int kPieces = BN / 8;       // 16-byte pieces per row
-    uint8_t* my_stage = epi_stage + static_cast<size_t>(warp - 2) * (32 * kPitch + 1024);
+    constexpr int kWords = BN / 32;                             // mask words per row
+    uint8_t* my_stage = epi_stage + static_cast<size_t>(warp - 2) * epi_warp_bytes(BN);
     // explicit shared-state-space accesses: through the aligned-up base pointer the compiler only sees generic addresses
     const uint32_t my_stage_u32 = xa::smem_u32(my_stage), s_bias_u32 = xa::smem_u32(s_bias);
-    const uint32_t row_out_u32 = my_stage_u32 + 32 * kPitch;  // [32] int64 output offset of the row, -1 = dropped
-    const uint32_t row_msk_u32 = row_out_u32 + 256;            // [32] int64 mask offset of the row
-    constexpr int kWords = BN / 32;                             // mask words per row
-    const uint32_t row_bits_u32 = row_out_u32 + 512;            // [32][kWords] this tile's mask bits, row by row (bits_in)
-    const uint32_t table_u32 = xa::smem_u32(epi_stage + 8 * (32 * kPitch + 1024));   // [256][4]: byte of mask bits -> four bf16x2 AND masks
-    // phase-2 coordinates: iteration `it` moves 32 consecutive 16-byte pieces = kRowsPerIt rows, so a thread keeps its
-    // piece (column group) for the whole kernel and only its row advances -- all per-iteration address arithmetic is
-    // an add of a compile-time constant.
-    constexpr int kRowsPerIt = 32 / kPieces;
-    const int piece = lane % kPieces, row0 = lane / kPieces;
-    int col_delta = piece * 8;  // element offset of my piece inside the output row
-    if (p.out_mode == 2) {      // (dy, dx, c) channel blocks land on pixels (2y+dy, 2x+dx): see xa_conv2d_nhwc_bf16_ex
-      constexpr int kN4 = BN / 4;
-      const int sub = col_delta / kN4;
-      col_delta = ((sub >> 1) * p.PW + (sub & 1)) * kN4 + (col_delta - sub * kN4);
-    }
-    const uint32_t my_piece_u32 = my_stage_u32 + row0 * kPitch + piece * 16;
+    const uint32_t row_out_u32 = my_stage_u32 + 32 * kEpiPitch;  // [32] int64 output offset of the row, -1 = dropped
+    const uint32_t row_msk_u32 = row_out_u32 + 256;              // [32] int64 mask offset of the row
+    const uint32_t row_bits_u32 = row_out_u32 + 512;             // [32][kWords] this tile's mask bits, row by row (bits_in)
+    const uint32_t table_u32 = xa::smem_u32(epi_stage + 4 * kGroups * epi_warp_bytes(BN));   // [256][4]: byte of mask bits -> four bf16x2 AND masks
+    // phase-2 coordinates: iteration `it` moves 32 consecutive 16-byte pieces = 8 rows of the chunk; a thread keeps its piece
+    const int piece = lane & 3, row0 = lane >> 2;
+    const uint32_t my_piece_u32 = my_stage_u32 + row0 * kEpiPitch + piece * 16;
     // my row's pixel (image ob, position rem inside it) advances by a constant from one of this group's tiles to the next:
     // two divisions here instead of three per tile (the epilogue's instruction count is what these short-K layers wait for)
-    const uint32_t step_px = 2u * gridDim.x * kBlockM, step_b = step_px / hw, step_rem = step_px - step_b * hw;
+    const uint32_t step_px = static_cast<uint32_t>(kGroups) * gridDim.x * kBlockM, step_b = step_px / hw, step_rem = step_px - step_b * hw;
     int64_t q = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x) * kBlockM + r;
     uint32_t ob_u = static_cast<uint32_t>(q / hw), rem = static_cast<uint32_t>(q - static_cast<int64_t>(ob_u) * hw);
-    for (uint32_t lt = grp;; lt += 2, q += step_px) {
+    for (uint32_t lt = grp;; lt += kGroups, q += step_px) {
       const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
       if (tile >= n_tiles) break;
       const uint32_t acc = grp;
@@ -399,70 +401,71 @@ __global__ void __launch_bounds__(kU8 ? kFlatThreadsU8 : kFlatThreads) conv_flat
         }
       }
       __syncwarp();
-      // the ReLU-derivative mask does not depend on the accumulator: fetch it (coalesced) before waiting
-      uint4 mraw[kPieces];
-      if (p.mask != nullptr) {
-#pragma unroll
-        for (int it = 0; it < kPieces; ++it) {
-          const int row = it * kRowsPerIt + row0;
-          if (lds_i64(row_out_u32 + row * 8) >= 0)
-            mraw[it] = __ldg(reinterpret_cast<const uint4*>(p.mask + lds_i64(row_msk_u32 + row * 8)) + piece);
-        }
-      }
-      mbar_wait_backoff(acc_full + acc, (lt >> 1) & 1);  // polling eight warps took a sixth of the SM's issue slots (ncu)
+      mbar_wait_backoff(acc_full + acc, (lt / kGroups) & 1);  // polling eight warps took a sixth of the SM's issue slots (ncu)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float lo = p.relu ? 0.0f : -INFINITY;  // ReLU as one max per element, no per-element branch on the flag
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        {  // phase 1: TMEM -> (+bias, ReLU) -> the chunk's bf16 rows in shared memory
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
+          const uint32_t dst = my_stage_u32 + lane * kEpiPitch;
+          uint32_t bits = 0;
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {  // phase 1: TMEM -> (+bias, ReLU) -> bf16 rows in shared memory
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
-        const uint32_t dst = my_stage_u32 + lane * kPitch + c0 * 2;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0 = lds_f4(s_bias_u32 + (c0 + 8 * j) * 4), b1 = lds_f4(s_bias_u32 + (c0 + 8 * j + 4) * 4);
-          float f[8];
-          f[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, lo), f[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, lo);
-          f[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, lo), f[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, lo);
-          f[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, lo), f[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, lo);
-          f[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, lo), f[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, lo);
-          if (p.bits_out != nullptr) {  // ReLU output (>= +0): positive <=> its bit pattern, negated as an integer, has the sign bit set;
-#pragma unroll                          // one funnel shift per value collects the flags (first value in the top bit: reversed below)
-            for (int e = 0; e < 8; ++e) bits = __funnelshift_l(0u - __float_as_uint(f[e]), bits, 1);
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = lds_f4(s_bias_u32 + (c0 + 8 * j) * 4), b1 = lds_f4(s_bias_u32 + (c0 + 8 * j + 4) * 4);
+            float f[8];
+            f[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, lo), f[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, lo);
+            f[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, lo), f[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, lo);
+            f[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, lo), f[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, lo);
+            f[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, lo), f[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, lo);
+            if (p.bits_out != nullptr) {  // ReLU output (>= +0): positive <=> its bit pattern, negated as an integer, has the sign bit set;
+#pragma unroll                            // one funnel shift per value collects the flags (first value in the top bit: reversed below)
+              for (int e = 0; e < 8; ++e) bits = __funnelshift_l(0u - __float_as_uint(f[e]), bits, 1);
+            }
+            __nv_bfloat162 h[4];
+            h[0] = __floats2bfloat162_rn(f[0], f[1]), h[1] = __floats2bfloat162_rn(f[2], f[3]);
+            h[2] = __floats2bfloat162_rn(f[4], f[5]), h[3] = __floats2bfloat162_rn(f[6], f[7]);
+            sts_u4(dst + j * 16, *reinterpret_cast<uint4*>(h));
           }
-          __nv_bfloat162 h[4];
-          h[0] = __floats2bfloat162_rn(f[0], f[1]), h[1] = __floats2bfloat162_rn(f[2], f[3]);
-          h[2] = __floats2bfloat162_rn(f[4], f[5]), h[3] = __floats2bfloat162_rn(f[6], f[7]);
-          sts_u4(dst + j * 16, *reinterpret_cast<uint4*>(h));
+          if (p.bits_out != nullptr && my_out_off >= 0) p.bits_out[(my_out_off >> 5) + (c0 >> 5)] = __brev(bits);
         }
-        if (p.bits_out != nullptr && my_out_off >= 0) p.bits_out[(my_out_off >> 5) + (c0 >> 5)] = __brev(bits);
-      }
-      // the accumulator is drained: hand it back before the global stores
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+        if (c0 + 32 >= BN) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the accumulator is drained ...
+        __syncwarp();
+        if (c0 + 32 >= BN && lane == 0)                                                        // ... hand it back before the global stores
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+        // phase 2: coalesced mask application and stores of the chunk.  Element offset of my piece inside the output row:
+        int col_delta = c0 + piece * 8;
+        if (p.out_mode == 2) {  // (dy, dx, c) channel blocks land on pixels (2y+dy, 2x+dx): see xa_conv2d_nhwc_bf16_ex
+          constexpr int kN4 = BN / 4;
+          const int sub = col_delta / kN4;
+          col_delta = ((sub >> 1) * p.PW + (sub & 1)) * kN4 + (col_delta - sub * kN4);
+        }
 #pragma unroll
-      for (int it = 0; it < kPieces; ++it) {  // phase 2: coalesced mask application and stores
-        const int64_t off0 = lds_i64(row_out_u32 + (it * kRowsPerIt + row0) * 8);
-        if (off0 >= 0) {
-          uint4 val = lds_u4(my_piece_u32 + it * (kRowsPerIt * kPitch));
-          if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
-            uint32_t b;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row_bits_u32 + (it * kRowsPerIt + row0) * (kWords * 4) + piece));
-            const uint4 mk = lds_u4(table_u32 + b * 16);
-            val.x &= mk.x, val.y &= mk.y, val.z &= mk.z, val.w &= mk.w;
-          } else if (p.mask != nullptr) {  // ReLU derivative of the layer below: zero where its activation was <= 0
-            const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw[it]);
-            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
-            val.x &= __hgt2_mask(mk[0], zero);
-            val.y &= __hgt2_mask(mk[1], zero);
-            val.z &= __hgt2_mask(mk[2], zero);
-            val.w &= __hgt2_mask(mk[3], zero);
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + row0;
+          const int64_t off0 = lds_i64(row_out_u32 + row * 8);
+          if (off0 >= 0) {
+            uint4 val = lds_u4(my_piece_u32 + it * (8 * kEpiPitch));
+            if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
+              uint32_t b;
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row_bits_u32 + row * (kWords * 4) + (c0 >> 3) + piece));
+              const uint4 mk = lds_u4(table_u32 + b * 16);
+              val.x &= mk.x, val.y &= mk.y, val.z &= mk.z, val.w &= mk.w;
+            } else if (p.mask != nullptr) {  // ... or from the bf16 activation of the layer below: zero where it was <= 0
+              const uint4 mraw = __ldg(reinterpret_cast<const uint4*>(p.mask + lds_i64(row_msk_u32 + row * 8) + c0) + piece);
+              const __nv_bfloat162* mk = reinterpret_cast<const __nv_bfloat162*>(&mraw);
+              const __nv_bfloat162 zero = __floats2bfloat162_rn(0.0f, 0.0f);
+              val.x &= __hgt2_mask(mk[0], zero);
+              val.y &= __hgt2_mask(mk[1], zero);
+              val.z &= __hgt2_mask(mk[2], zero);
+              val.w &= __hgt2_mask(mk[3], zero);
+            }
+            *reinterpret_cast<uint4*>(p.y + off0 + col_delta) = val;
           }
-          *reinterpret_cast<uint4*>(p.y + off0 + col_delta) = val;
         }
+        __syncwarp();  // the chunk's staging rows are free again
       }
-      __syncwarp();  // the tile's staging rows are free again
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -489,7 +492,7 @@ int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap&
   }
   const int64_t tiles = (p.Q + kBlockM - 1) / kBlockM;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  conv_flat_kernel<BN, kU8><<<static_cast<unsigned>(tiles < sms ? tiles : sms), kU8 ? kFlatThreadsU8 : kFlatThreads, smem, stream>>>(mx, mw, mx1, p);
+  conv_flat_kernel<BN, kU8><<<static_cast<unsigned>(tiles < sms ? tiles : sms), flat_threads(BN, kU8), smem, stream>>>(mx, mw, mx1, p);
   return xa::check_launch(what);
 }
 
@@ -516,7 +519,8 @@ int xa_conv_flat_try(const void* x, const void* w, const float* bias, void* y, i
   FlatParams p{};
   p.w_bytes = static_cast<uint32_t>(n_entries) * n_out * 128u;
   p.stage_bytes = static_cast<uint32_t>(kc_blocks) * win_rows * 128u;
-  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 1024) + 4096;  // the epilogue warps' transposing tiles + row tables, the bit-expansion table
+  // the epilogue warps' transposing tiles + row tables, the bit-expansion table
+  const int64_t epi_bytes = 4 * groups_bf16(n_out) * epi_warp_bytes(n_out) + (mask_is_bits ? 4096 : 0);
   const int64_t budget = 227 * 1024 - 1024 /*alignment*/ - 2048 /*barriers, tables, bias*/ - epi_bytes - p.w_bytes;
   int stages = static_cast<int>(budget / p.stage_bytes);
   if (stages < 2) return 1;
@@ -579,7 +583,7 @@ static int conv_u8_s2d(const char* what, const uint8_t* frames, const int32_t* f
   p.stage_bytes = static_cast<uint32_t>(win_rows) * 128u;
   p.raw_tx_bytes = static_cast<uint32_t>(box_rows) * W * 64u;
   p.raw_stage_bytes = ((p.raw_tx_bytes + 1023u) / 1024u) * 1024u;
-  const int64_t epi_bytes = 8 * (32 * (2 * n_out + 16) + 1024) + 4096;
+  const int64_t epi_bytes = 4 * kGroupsU8 * epi_warp_bytes(n_out);
   const int64_t budget = 227 * 1024 - 1024 - 2048 - epi_bytes - p.w_bytes - static_cast<int64_t>(kRawStages) * p.raw_stage_bytes;
   int stages = static_cast<int>(budget / p.stage_bytes);
   XA_REQUIRE(stages >= 2, XA_EINVAL, "%s: shared memory does not hold two operand stages", what);
