@@ -42,6 +42,13 @@ int xa_version(void);
 const char* xa_last_error(void);
 /* sm_count / cc of `device` (host out-params; any may be NULL). Fails when no CUDA device exists. */
 int xa_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* Chained launches (programmatic dependent launch, csrc/xa_common.cuh): kernels of the rollout step, the network pass and the
+ * loss -> optimiser chain may be scheduled while their predecessor on the stream drains; each waits for the predecessor's
+ * completion before its first global-memory access, so results do not depend on the level.  0 = never, 1 = small launches
+ * (default; XA_PDL in the environment sets the initial value), 2 = every launch, 3 = small tensor-core / rollout launches
+ * only.  Returns the previous level; a level outside 0..3 only queries.  Process-wide; the reference has no counterpart
+ * (TensorFlow orders its kernels on one stream, xagents/a2c/agent.py:96-139 / ppo/agent.py:215-225 being the loops served). */
+int xa_set_chained_launches(int level);
 
 /* ---- returns -------------------------------------------------------------------------------- */
 #define XA_SCAN_AUTO 0       /* pick by shape */

@@ -456,3 +456,41 @@ def test_ppo_without_a_frame_gather_equals_ppo_with_it():
     (p0, l0, s0), (p1, l1, s1) = results
     assert s0 == s1 == 2 * 2 * 3 and torch.isfinite(p0).all()
     assert torch.equal(l0, l1) and torch.equal(p0, p1)
+
+
+@pytest.mark.timeout(300)
+def test_chained_launches_do_not_change_results():
+    """Programmatic dependent launches (csrc/xa_common.cuh `launch_chained`; xa_set_chained_launches): a kernel of the rollout
+    step / network pass / loss -> optimiser chain may be scheduled while its predecessor drains, and waits for the predecessor's
+    completion before its first global access.  Rollouts (fused three-call steps on the tcgen05 network) followed by PPO update
+    phases must give bit-identical buffers, weights and loss scalars at level 0 (plain stream order), 1 (default policy) and 2
+    (every launch chained)."""
+    from xagents_b200 import _ffi, envs
+    from xagents_b200.agents import PPO, NatureCnnTc, TorchModel
+    lib = _ffi.lib()
+    T, E, A = 8, 32, 6
+    before = lib.xa_set_chained_launches(-1)
+    assert before in (0, 1, 2, 3)
+    results = []
+    try:
+        for level in (0, 1, 2):
+            assert lib.xa_set_chained_launches(level) in (0, 1, 2, 3) and lib.xa_set_chained_launches(-1) == level
+            made = envs.create_envs('SyntheticAtariDevice-v0', E, preprocess=True, device=DEV)
+            made.seed(5)
+            made.p_done = 0.1
+            made.reset_all()
+            torch.manual_seed(0)
+            net = TorchModel(NatureCnnTc(4, A).cuda())
+            agent = PPO(made, net, n_steps=T, mini_batches=4, ppo_epochs=2, quiet=True, seed=3)
+            agent.graph_rollout = False
+            for _ in range(3):
+                agent.train_step()
+            torch.cuda.synchronize()
+            results.append([t.clone() for t in (agent.ro_states, agent.ro_actions, agent.ro_values, agent.ro_log_probs, agent.ro_returns, net.flat_param,
+                                                torch.stack(list(agent.loss_history)))])
+    finally:
+        lib.xa_set_chained_launches(before)
+    assert torch.isfinite(results[0][5]).all()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert torch.equal(a, b)

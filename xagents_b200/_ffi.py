@@ -82,6 +82,7 @@ PROTOTYPES = {
     'xa_version': (ctypes.c_int, []),
     'xa_last_error': (ctypes.c_char_p, []),
     'xa_device_info': (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3),
+    'xa_set_chained_launches': (ctypes.c_int, [ctypes.c_int]),
     'xa_gae_f32': (ctypes.c_int, [c_f32p] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                   ctypes.c_int, c_stream]),
     'xa_nstep_returns_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,

@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <stdlib.h>
+
 #include "xa_common.cuh"
 
 namespace xa {
@@ -20,6 +22,16 @@ int check_launch(const char* what) {
   if (e == cudaSuccess) return XA_OK;
   set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   return static_cast<int>(e);
+}
+
+static int g_pdl_level = -1;   // -1: not read yet (XA_PDL in the environment, else 1)
+
+int pdl_level() {
+  if (g_pdl_level < 0) {
+    const char* e = getenv("XA_PDL");
+    g_pdl_level = e != nullptr && e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 1;
+  }
+  return g_pdl_level;
 }
 
 int sm_count() {
@@ -48,6 +60,12 @@ extern "C" {
 int xa_version(void) { return XA_VERSION; }
 
 const char* xa_last_error(void) { return xa::g_error; }
+
+int xa_set_chained_launches(int level) {
+  const int before = xa::pdl_level();
+  if (level >= 0 && level <= 3) xa::g_pdl_level = level;
+  return before;
+}
 
 int xa_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   int n = 0;

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the on-chip set-up below overlaps the predecessor's tail
   for (int i = threadIdx.x; i < p.n_entries; i += blockDim.x) s_a[i] = p.a_units[i], s_b[i] = p.b_units[i];
   if (p.bits_in != nullptr) {  // byte b of a row's mask bits -> the AND masks of its eight bf16 values
     uint32_t* table = reinterpret_cast<uint32_t*>(epi_stage + 4 * kGroups * epi_warp_bytes(BN));
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  xa::pdl_wait();      // first global-memory access below: the predecessor grid has completed
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -492,7 +494,7 @@ int launch_flat(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap&
   }
   const int64_t tiles = (p.Q + kBlockM - 1) / kBlockM;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
-  conv_flat_kernel<BN, kU8><<<static_cast<unsigned>(tiles < sms ? tiles : sms), flat_threads(BN, kU8), smem, stream>>>(mx, mw, mx1, p);
+  xa::launch_chained(tiles <= 16 * sms ? xa::kChainSmall : xa::kChainLarge, conv_flat_kernel<BN, kU8>, dim3(static_cast<unsigned>(tiles < sms ? tiles : sms)), dim3(flat_threads(BN, kU8)), smem, stream, mx, mw, mx1, p);
   return xa::check_launch(what);
 }
 

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kThreads) gemm_atb_kernel(const __grid_constan
   uint64_t* acc_full = empty + S::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the on-chip set-up below overlaps the predecessor's tail
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = static_cast<int>((p.m + kBlockM - 1) / kBlockM);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kThreads) gemm_atb_kernel(const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  xa::pdl_wait();      // first global-memory access below: the predecessor grid has completed
 
   if (warp == 0) {
     if (elect_one()) {  // ---- TMA producer: 64 k-rows of 128 A columns and BN B columns per stage (columns past M / N read as zero)
@@ -192,7 +194,7 @@ int launch_atb(const CUtensorMap& ma, const CUtensorMap& mb, const AtbParams& p,
     configured_dev = dev;
   }
   const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN);
-  gemm_atb_kernel<BN><<<static_cast<unsigned>(tiles * p.splits), kThreads, AtbSmem<BN>::kBytes, s>>>(ma, mb, p);
+  xa::launch_chained(xa::kChainLarge, gemm_atb_kernel<BN>, dim3(static_cast<unsigned>(tiles * p.splits)), dim3(kThreads), AtbSmem<BN>::kBytes, s, ma, mb, p);
   if (int rc = xa::check_launch(what)) return rc;
   if (p.splits > 1 && reduce) {
     const int64_t want = (p.m * p.n + 255) / 256;

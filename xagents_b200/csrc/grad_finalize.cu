@@ -46,6 +46,8 @@ __device__ __forceinline__ int find_segment(const FinalizeParams& p, int64_t j) 
 // 74 loads per lane of those 4 600 outputs were the tail of the whole kernel); lanes of one output read different splits, so a
 // warp-wide load touches 32 / lanes consecutive outputs per sector: eight lanes keep half of every sector useful.
 __global__ void __launch_bounds__(kThreads) grad_finalize_kernel(const __grid_constant__ FinalizeParams p, int narrow_blocks) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   if (static_cast<int>(blockIdx.x) < narrow_blocks) {
     for (int64_t j = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; j < p.n; j += static_cast<int64_t>(narrow_blocks) * kThreads) {
       const xa_grad_segment_t& sg = p.seg[find_segment(p, j)];
@@ -126,6 +128,6 @@ extern "C" int xa_grad_finalize_f32(const float* src, const int32_t* map, const 
   if (nb > 8 * sms) nb = 8 * sms;
   int64_t wb = (slots + kThreads - 1) / kThreads;
   if (wb > 16 * sms) wb = 16 * sms;
-  grad_finalize_kernel<<<static_cast<unsigned>(nb + wb), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<int>(nb));
+  xa::launch_chained(xa::kChainElementwise, grad_finalize_kernel, dim3(static_cast<unsigned>(nb + wb)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), p, static_cast<int>(nb));
   return xa::check_launch(what);
 }

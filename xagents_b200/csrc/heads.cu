@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_b
                                                                   const float* __restrict__ bh, float* __restrict__ actor,
                                                                   float* __restrict__ critic, int batch, int n_actions) {
   __shared__ __align__(16) float s_w[kRows][kHidden];
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   for (int i = threadIdx.x; i < kRows * kHidden / 8; i += kFwdThreads) {   // 512 16-byte pieces, two per thread, both in flight
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(wh) + i), f);
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) heads_backward_kernel(const fl
                                                                       int n_actions, int rows_per_cta) {
   __shared__ __align__(16) float s_d[kBwdMaxRowsPerCta][kRows];
   __shared__ float s_red[kRows + 1][4][kChunkThreads];   // row group 1's accumulators (18 KB)
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   const int chunk = threadIdx.x % kChunkThreads, grp = threadIdx.x / kChunkThreads;
   const int row0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, batch - row0);
@@ -226,9 +230,8 @@ int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float*
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int want = (batch + 2 * (kFwdThreads / 32) - 1) / (2 * (kFwdThreads / 32));
   const int grid = want < 4 * sms ? want : 4 * sms;  // a pair of frames per warp, up to four CTAs per SM
-  heads_forward_kernel<<<grid, kFwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h),
-                                                                                   static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch,
-                                                                                   n_actions);
+  xa::launch_chained(batch <= 1024 ? xa::kChainSmall : xa::kChainElementwise, heads_forward_kernel, dim3(grid), dim3(kFwdThreads), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(h),
+                     static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch, n_actions);
   return xa::check_launch(what);
 }
 
@@ -242,9 +245,9 @@ int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const vo
              "%s: 16-byte alignment required", what);
   const int grid = xa_heads_backward_blocks(batch);
   XA_REQUIRE(partial_floats >= static_cast<int64_t>(grid) * (kRows + 2) * kHidden, XA_ENOSPACE, "%s: partial buffer too small", what);
-  heads_backward_kernel<<<grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_actor, d_critic, static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(wh), static_cast<__nv_bfloat16*>(dh), partial,
-      batch, n_actions, bwd_rows_per_cta(batch));
+  xa::launch_chained(xa::kChainElementwise, heads_backward_kernel, dim3(grid), dim3(kBwdThreads), 0, static_cast<cudaStream_t>(stream), d_actor, d_critic,
+                     static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(wh), static_cast<__nv_bfloat16*>(dh), partial, batch, n_actions,
+                     bwd_rows_per_cta(batch));
   return xa::check_launch(what);
 }
 

@@ -41,6 +41,8 @@ struct MomentParams {
 __global__ void __launch_bounds__(kMomentThreads) adv_moments_kernel(const MomentParams p, const MomentOffsets offsets) {
   __shared__ double scratch[kMomentThreads / 32];
   __shared__ double s_mean;
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   const int m = blockIdx.x;
   const int64_t lo = offsets.v[m], hi = offsets.v[m + 1];
   const int64_t n = hi - lo;
@@ -124,6 +126,8 @@ struct LossWorkspace {  // layout of xa_loss_args.workspace
 
 template <bool kPpo, int kActorKind, int kRegActions /*0 = loop over global memory*/>
 __global__ void __launch_bounds__(kLossThreads) loss_kernel(const xa_loss_args a) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   __shared__ double scratch[kLossWarps];
   __shared__ float s_mean, s_denom;
   __shared__ bool s_last;
@@ -321,9 +325,9 @@ int64_t loss_blocks(int64_t n) { return (n + kLossThreads - 1) / kLossThreads; }
 template <bool kPpo, int kActorKind>
 void dispatch_width(const xa_loss_args& a, unsigned grid, cudaStream_t stream) {
   if (kActorKind != XA_ACTOR_NORMAL && a.n_actions <= kMaxRegActions)
-    loss_kernel<kPpo, kActorKind, kMaxRegActions><<<grid, kLossThreads, 0, stream>>>(a);
+    xa::launch_chained(xa::kChainElementwise, loss_kernel<kPpo, kActorKind, kMaxRegActions>, dim3(grid), dim3(kLossThreads), 0, stream, a);
   else
-    loss_kernel<kPpo, kActorKind, 0><<<grid, kLossThreads, 0, stream>>>(a);
+    xa::launch_chained(xa::kChainElementwise, loss_kernel<kPpo, kActorKind, 0>, dim3(grid), dim3(kLossThreads), 0, stream, a);
 }
 
 template <bool kPpo>
@@ -373,7 +377,7 @@ int xa_adv_moments_f32(const float* returns, const float* old_values, const int3
     MomentOffsets off{};
     for (int m = 0; m <= count; ++m) off.v[m] = mb_offsets[first + m];
     MomentParams p{returns, old_values, idx, n_steps, n_envs, moments + static_cast<int64_t>(first) * XA_MOMENT_STRIDE};
-    adv_moments_kernel<<<count, kMomentThreads, 0, s>>>(p, off);
+    xa::launch_chained(xa::kChainElementwise, adv_moments_kernel, dim3(count), dim3(kMomentThreads), 0, s, p, off);
     if (int rc = xa::check_launch("xa_adv_moments_f32")) return rc;
   }
   return XA_OK;

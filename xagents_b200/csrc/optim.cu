@@ -24,6 +24,8 @@ struct OptimWorkspace {
 };
 
 __global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(const float* __restrict__ g, int64_t n, OptimWorkspace* ws) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   __shared__ double scratch[kThreads / 32];
   __shared__ bool s_last;
   double acc = 0.0;
@@ -73,6 +75,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   float scale = a.grad_scale;
   if (a.clip > 0.0f) {
     // tf.clip_by_global_norm: g * clip * min(1/norm, 1/clip)
@@ -104,6 +108,8 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a)
 // minibatch, as in training.  6.75 MB written per call for the Nature CNN's 1.69 M parameters.
 __global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float* __restrict__ d_actor, const float* __restrict__ d_values,
                                                                      uint32_t n, uint32_t na, float* __restrict__ grad, int64_t n_params) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   // one float4 of "parameter gradients" per thread and pass; 32-bit index arithmetic (n_params, n * A < 2^31 are checked)
   const uint32_t n4 = static_cast<uint32_t>(n_params / 4);
   const uint32_t stride = gridDim.x * kThreads;
@@ -144,7 +150,7 @@ int xa_grad_sumsq_f32(const float* grads, int64_t n, void* workspace, int64_t wo
   XA_REQUIRE(n > 0, XA_EINVAL, "xa_grad_sumsq_f32: n=%lld", static_cast<long long>(n));
   XA_REQUIRE(workspace_bytes >= xa_clip_adam_workspace_bytes(n), XA_ENOSPACE, "xa_grad_sumsq_f32: workspace too small");
   XA_REQUIRE(xa::aligned(grads, 16) && xa::aligned(workspace, 16), XA_EALIGN, "xa_grad_sumsq_f32: 16-byte alignment required");
-  grad_sumsq_kernel<<<blocks_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(grads, n, static_cast<OptimWorkspace*>(workspace));
+  xa::launch_chained(xa::kChainElementwise, grad_sumsq_kernel, dim3(blocks_for(n)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), grads, n, static_cast<OptimWorkspace*>(workspace));
   return xa::check_launch("xa_grad_sumsq_f32");
 }
 
@@ -157,8 +163,8 @@ int xa_grad_from_outputs_f32(const float* d_actor, const float* d_values, int64_
   XA_REQUIRE(xa::aligned(grad, 16), XA_EALIGN, "xa_grad_from_outputs_f32: grad must be 16-byte aligned");
   const int64_t want = (n_params / 4 + kThreads - 1) / kThreads;
   const unsigned grid = static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
-  grad_from_outputs_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_actor, d_values, static_cast<uint32_t>(n), static_cast<uint32_t>(n * n_actions), grad, n_params);
+  xa::launch_chained(xa::kChainElementwise, grad_from_outputs_kernel, dim3(grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), d_actor, d_values, static_cast<uint32_t>(n),
+                     static_cast<uint32_t>(n * n_actions), grad, n_params);
   return xa::check_launch("xa_grad_from_outputs_f32");
 }
 
@@ -185,7 +191,7 @@ int xa_clip_adam_f32(float* param, const float* grad, float* m, float* v, int64_
   a.eps = static_cast<float>(eps);
   a.clip = static_cast<float>(clip_norm);
   a.grad_scale = static_cast<float>(grad_scale);
-  clip_adam_kernel<<<blocks_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  xa::launch_chained(xa::kChainElementwise, clip_adam_kernel, dim3(blocks_for(n)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), a);
   return xa::check_launch("xa_clip_adam_f32");
 }
 

@@ -40,6 +40,8 @@ struct PolicyParams {
 
 template <int kActorKind>
 __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   const int A = p.n_actions;
@@ -100,14 +102,18 @@ __global__ void __launch_bounds__(128) policy_step_kernel(const PolicyParams p) 
   if (p.entropies) p.entropies[i] = ent;
 }
 
-__global__ void bump_u64_kernel(uint64_t* p, uint64_t delta) { *p += delta; }
+__global__ void bump_u64_kernel(uint64_t* p, uint64_t delta) {
+  xa::pdl_trigger();
+  xa::pdl_wait();
+  *p += delta;
+}
 
 int launch_policy(const PolicyParams& p, int actor_kind, cudaStream_t s, const char* what) {
   const unsigned grid = static_cast<unsigned>((p.n + 127) / 128);
   switch (actor_kind) {
-    case XA_ACTOR_LOGITS: policy_step_kernel<XA_ACTOR_LOGITS><<<grid, 128, 0, s>>>(p); break;
-    case XA_ACTOR_PROBS: policy_step_kernel<XA_ACTOR_PROBS><<<grid, 128, 0, s>>>(p); break;
-    default: policy_step_kernel<XA_ACTOR_NORMAL><<<grid, 128, 0, s>>>(p); break;
+    case XA_ACTOR_LOGITS: xa::launch_chained(xa::kChainSmall, policy_step_kernel<XA_ACTOR_LOGITS>, dim3(grid), dim3(128), 0, s, p); break;
+    case XA_ACTOR_PROBS: xa::launch_chained(xa::kChainSmall, policy_step_kernel<XA_ACTOR_PROBS>, dim3(grid), dim3(128), 0, s, p); break;
+    default: xa::launch_chained(xa::kChainSmall, policy_step_kernel<XA_ACTOR_NORMAL>, dim3(grid), dim3(128), 0, s, p); break;
   }
   return xa::check_launch(what);
 }
@@ -128,7 +134,7 @@ extern "C" int xa_policy_step_counter_f32(const float* actor_out, int actor_kind
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int rc = launch_policy(p, actor_kind, s, "xa_policy_step_counter_f32")) return rc;
   if (advance == 0) return XA_OK;
-  bump_u64_kernel<<<1, 1, 0, s>>>(offset_dev, advance);
+  xa::launch_chained(xa::kChainSmall, bump_u64_kernel, dim3(1), dim3(1), 0, s, offset_dev, advance);
   return xa::check_launch("xa_policy_step_counter_f32");
 }
 

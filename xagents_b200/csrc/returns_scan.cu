@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps) returns_scan_kernel(const Scan
   __shared__ float s_c[kMulti ? kMaxWarps : 1][32];
   __shared__ float s_b[kMulti ? kMaxWarps : 1][32];
   __shared__ float s_carry[32];
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
 
   const int lane = threadIdx.x;
   const int w = threadIdx.y;
@@ -247,9 +249,9 @@ int launch(const ScanParams& p, int mode, cudaStream_t stream, const char* what)
   const dim3 block(32, n_warps);
   const dim3 grid((p.n_envs + 31) / 32);
   if (n_warps == 1)
-    returns_scan_kernel<kNstep, false><<<grid, block, 0, stream>>>(p);
+    xa::launch_chained(xa::kChainElementwise, returns_scan_kernel<kNstep, false>, dim3(grid), dim3(block), 0, stream, p);
   else
-    returns_scan_kernel<kNstep, true><<<grid, block, 0, stream>>>(p);
+    xa::launch_chained(xa::kChainElementwise, returns_scan_kernel<kNstep, true>, dim3(grid), dim3(block), 0, stream, p);
   return xa::check_launch(what);
 }
 

@@ -45,6 +45,8 @@ struct SynthParams {
 };
 
 __global__ void __launch_bounds__(256) synth_env_step_kernel(const SynthParams p) {
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
+  xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
   const int e = blockIdx.x / p.ctas_per_env, part = blockIdx.x - e * p.ctas_per_env;
   const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
   const uint64_t off = (p.offset_dev ? *p.offset_dev : 0) + p.offset;
@@ -74,7 +76,11 @@ __global__ void __launch_bounds__(256) synth_env_step_kernel(const SynthParams p
   }
 }
 
-__global__ void bump_u64_kernel(uint64_t* p, uint64_t delta) { *p += delta; }
+__global__ void bump_u64_kernel(uint64_t* p, uint64_t delta) {
+  xa::pdl_trigger();
+  xa::pdl_wait();
+  *p += delta;
+}
 
 }  // namespace
 
@@ -97,13 +103,13 @@ extern "C" int xa_synth_env_step_u8(const uint8_t* pool, int pool_size, int64_t 
   if (per > max_per) per = static_cast<int>(max_per);
   if (per < 1) per = 1;
   p.ctas_per_env = per;
-  synth_env_step_kernel<<<static_cast<unsigned>(n_envs) * per, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  xa::launch_chained(xa::kChainSmall, synth_env_step_kernel, dim3(static_cast<unsigned>(n_envs) * per), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return xa::check_launch(what);
 }
 
 // *counter += delta on the stream: Philox offsets kept in device memory are advanced once per captured rollout, not per step.
 extern "C" int xa_bump_u64(uint64_t* counter, uint64_t delta, xa_stream_t stream) {
   XA_REQUIRE(counter != nullptr && xa::aligned(counter, 8), XA_EINVAL, "xa_bump_u64: counter must be a non-null 8-byte aligned device pointer");
-  bump_u64_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter, delta);
+  xa::launch_chained(xa::kChainSmall, bump_u64_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), counter, delta);
   return xa::check_launch("xa_bump_u64");
 }

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   uint64_t* desc_tab = acc_full + 2;  // [stages][kMB]: A descriptor of (stage, column block) at K step 0
 
+  xa::pdl_trigger();   // chained launch (xa_common.cuh): the on-chip set-up below overlaps the predecessor's tail
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.x;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_mn_kernel(const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  xa::pdl_wait();      // first global-memory access below: the predecessor grid has completed
 
   if (warp == 0) {
     if (elect_one()) {  // ---- TMA producer (no division / modulo per K block: `stages` is a run-time value)
@@ -266,7 +268,7 @@ int launch_wgrad_mn(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradMn
     }
     configured_dev = dev;
   }
-  wgrad_mn_kernel<kMB><<<splits, kThreads, smem, s>>>(mx, mdy, p, stages);
+  xa::launch_chained(xa::kChainLarge, wgrad_mn_kernel<kMB>, dim3(splits), dim3(kThreads), smem, s, mx, mdy, p, stages);
   return xa::check_launch(what);
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "xagents_b200.h"
 
 namespace xa {
@@ -20,9 +22,39 @@ int sm_count();                      // cached multiProcessorCount of the curren
     }                                \
   } while (0)
 
+// ---- chained launches (programmatic dependent launch) -----------------------------------------------------------
+// The rollout step, the network pass and the loss -> optimiser chain are sequences of SHORT kernels on one stream (8-60 us
+// each at rollout batch sizes): between two of them the GPU idles for the launch latency plus the next kernel's on-chip
+// set-up (barrier initialisation, TMEM allocation, descriptor prefetch).  Kernels launched through `launch_chained` may
+// start while their predecessor on the stream is still draining; each such kernel executes `xa::pdl_wait()` before its
+// first global-memory access (it returns once the predecessor grid has completed and its writes are visible) and
+// `xa::pdl_trigger()` to let its own successor be scheduled early.  Both are no-ops for a kernel launched the plain way.
+// Measured (profiles/r2_chained_launches.md): the rollout's 256-frame forward pass 49 -> 41 us, a 128-step rollout graph 6.6 ->
+// 5.7 ms, the loss -> optimiser chain of the benchmarked step +1 %; device-filling launches (the 8192-frame network kernels)
+// LOSE ~1 us each, so every launch site says whether its launch is `small` (tensor-core kernels: a few tiles per CTA).
+// XA_PDL in the environment: 0 = never (plain stream order), 1 = small launches (default), 2 = every launch, 3 = small
+// tensor-core launches only.
+int pdl_level();
+enum : int { kChainSmall = 1, kChainLarge = 0, kChainElementwise = 2 };
+template <typename... P, typename... A>
+inline void launch_chained(int kind, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  const int level = pdl_level();
+  const bool chain = level == 2 || (level == 1 && kind != kChainLarge) || (level == 3 && kind == kChainSmall);
+  cfg.attrs = &attr, cfg.numAttrs = chain ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);   // a failure stays in cudaGetLastError for check_launch
+}
+
 __host__ __device__ static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---- device side ------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // env-major flat sample id b = e*T + t  ->  row of the time-major [T*E] buffer (base.py:559-564)
 __device__ __forceinline__ int64_t sample_row(int32_t b, int n_steps, int n_envs) {
   if (n_steps <= 0) return b;
