@@ -240,6 +240,11 @@ int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias,
 /* Scratch for split-K (few output tiles, long K: the weight-gradient products); 0 when the shape does not split.
  * Passing workspace = NULL simply disables splitting.  relu_mask: optional bf16 [m, ldc], c *= (mask > 0). */
 int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
+/* The split-K product without its reduction pass: fp32 partial tiles [*splits_out, m, n] in `workspace` for a consumer that
+ * adds them itself (xa_heads_forward_partial_bf16).  *splits_out = 1 and nothing is launched when the shape is not split
+ * or the workspace is too small: take xa_gemm_bf16_tn(_ex) then.  (Keras Dense of the trunk, xagents/utils/common.py:239-258.) */
+int xa_gemm_bf16_tn_partial(const void* a, const void* b, int64_t m, int64_t n, int64_t k, void* workspace, int64_t workspace_bytes,
+                            int* splits_out, xa_stream_t stream);
 
 /* Stride-1 NHWC convolution as an implicit GEMM on tcgen05, no im2col buffer.  Two kernels behind one entry point:
  * the flat kernel (csrc/conv_flat_tc.cu: pixels flattened, one window per 128-pixel tile, each tap a row-shifted view
@@ -360,6 +365,12 @@ int xa_gemm_bf16_atb_partial(const void* a, const void* b, int64_t m, int64_t n,
 int xa_heads_backward_blocks(int batch);
 int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float* actor, float* critic, int batch,
                           int hidden, int n_actions, xa_stream_t stream);
+/* The same forward when h does not exist yet: `partial` [splits, batch, hidden] fp32 are the split-K partial products of the
+ * layer that produces h (xa_gemm_bf16_tn_partial); they are added in split order, `bias` (may be NULL) added, ReLU applied and
+ * the result rounded to bf16 -- bit for bit what the GEMM's own reduction pass writes -- stored to h_out (may be NULL) and fed
+ * to the heads.  One launch less per rollout step (a2c/agent.py:96-139, the model call inside get_batch's loop). */
+int xa_heads_forward_partial_bf16(const float* partial, int splits, const float* bias, void* h_out, const void* wh, const float* bh,
+                                  float* actor, float* critic, int batch, int hidden, int n_actions, xa_stream_t stream);
 int xa_heads_backward_bf16(const float* d_actor, const float* d_critic, const void* h, const void* wh, void* dh,
                            float* partial, int64_t partial_floats, int batch, int hidden, int n_actions,
                            xa_stream_t stream);

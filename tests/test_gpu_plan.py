@@ -40,6 +40,51 @@ def test_heads_forward_vs_torch(B, A):
     torch.testing.assert_close(critic, ref[:, A], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (256, 4), (1000, 7)])
+def test_heads_forward_from_split_k_partials_is_bit_identical_to_gemm_then_heads(B, A):
+    """xa_gemm_bf16_tn_partial + xa_heads_forward_partial_bf16 (the FC layer's split-K partial sums are added, biased, rectified and
+    rounded by the heads kernel: one launch less per rollout step) against xa_gemm_bf16_tn_ex (its own reduction pass) +
+    xa_heads_forward_bf16: h, logits and values identical bit for bit."""
+    from xagents_b200 import _ffi
+    lib = _ffi.lib()
+    torch.manual_seed(B)
+    K, H = 3136, 512
+    y3 = (torch.randn(B, K, device=DEV).relu() * 0.3).bfloat16()
+    wf = (torch.randn(H, K, device=DEV) * 0.02).bfloat16()
+    bf = torch.randn(H, device=DEV) * 0.1
+    wh = torch.zeros(8, H, device=DEV)
+    wh[:A + 1] = torch.randn(A + 1, H, device=DEV) * 0.05
+    wh16 = wh.bfloat16()
+    bh = torch.zeros(8, device=DEV)
+    bh[:A + 1] = torch.randn(A + 1, device=DEV)
+    ws_bytes = lib.xa_gemm_workspace_bytes(B, H, K)
+    assert ws_bytes > 0, 'these batch sizes are split along K'
+    out = {}
+    for fused in (False, True):
+        ws = torch.full((ws_bytes // 4,), float('nan'), device=DEV)
+        h = torch.full((B, H), float('nan'), device=DEV).bfloat16()
+        actor = torch.full((B, A), float('nan'), device=DEV)
+        critic = torch.full((B,), float('nan'), device=DEV)
+        if fused:
+            splits = ctypes.c_int(0)
+            _call('xa_gemm_bf16_tn_partial', _p(y3), _p(wf), B, H, K, _p(ws), ws_bytes, ctypes.byref(splits), _s())
+            assert splits.value > 1
+            _call('xa_heads_forward_partial_bf16', _p(ws), splits.value, _p(bf), _p(h), _p(wh16), _p(bh), _p(actor), _p(critic), B, H, A, _s())
+        else:
+            _call('xa_gemm_bf16_tn_ex', _p(y3), _p(wf), _p(h), _p(bf), B, H, K, H, 1, 1, None, H, 0, 0, _p(ws), ws_bytes, _s())
+            _call('xa_heads_forward_bf16', _p(h), _p(wh16), _p(bh), _p(actor), _p(critic), B, H, A, _s())
+        torch.cuda.synchronize()
+        out[fused] = (h, actor, critic)
+    for a, b in zip(out[False], out[True]):
+        assert torch.isfinite(a.float()).all() and torch.equal(a, b)
+    ref = (y3.float() @ wf.float().t() + bf).relu()
+    torch.testing.assert_close(out[True][0].float(), ref, rtol=2e-2, atol=2e-2)
+    # too small a workspace: nothing is launched and the caller is told to take the plain path
+    splits = ctypes.c_int(7)
+    _call('xa_gemm_bf16_tn_partial', _p(y3), _p(wf), B, H, K, _p(ws), 16, ctypes.byref(splits), _s())
+    assert splits.value == 1
+
+
 @pytest.mark.parametrize('B,A', [(1, 6), (37, 6), (100, 3), (8192, 6), (40001, 6)])
 def test_heads_backward_vs_torch(B, A):
     from xagents_b200 import _ffi

@@ -129,6 +129,7 @@ PROTOTYPES = {
     'xa_gemm_atb_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_gemm_bf16_atb': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
+    'xa_gemm_bf16_tn_partial': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int), c_stream]),
     'xa_conv2d_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                             [ctypes.c_void_p, c_stream]),
     'xa_conv2d_u8_s2d_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 8 + [c_stream]),
@@ -141,6 +142,7 @@ PROTOTYPES = {
     'xa_gemm_bf16_atb_partial': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_heads_backward_blocks': (ctypes.c_int, [ctypes.c_int]),
     'xa_heads_forward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [c_stream]),
+    'xa_heads_forward_partial_bf16': (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 3 + [c_stream]),
     'xa_heads_backward_bf16': (ctypes.c_int, [ctypes.c_void_p] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 3 + [c_stream]),
     'xa_grad_finalize_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GradSegment), ctypes.c_int, ctypes.c_void_p,
                                             ctypes.c_int64, c_stream]),

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
 }
 
 template <int BN, bool kOutBf16>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what, bool reduce = true) {
   auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16>;
   static thread_local int configured_dev = -1;  // opt-in shared memory is a per-device attribute of the kernel
   int dev = 0;
@@ -370,7 +370,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);  // persistent: at most one CTA per SM
   xa::launch_chained(items * ((p.k + kBlockK - 1) / kBlockK) <= 16 * sms ? xa::kChainSmall : xa::kChainLarge, kernel, dim3(grid), dim3(kGemmThreads), Smem<BN>::kBytes, stream, ma, mb, p);
   if (int rc = xa::check_launch(what)) return rc;
-  if (p.splits > 1) {
+  if (p.splits > 1 && reduce) {
     const int64_t want = (p.m * p.n + 255) / 256;
     splitk_reduce_kernel<kOutBf16><<<static_cast<unsigned>(want < 4096 ? want : 4096), 256, 0, stream>>>(p);
     return xa::check_launch(what);
@@ -444,6 +444,41 @@ extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const f
   if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);
   if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
   return out_bf16 ? launch<16, true>(ma, mb, p, s, what) : launch<16, false>(ma, mb, p, s, what);
+}
+
+// The split-K product WITHOUT its reduction pass: fp32 partial tiles [splits, m, n] in `workspace`, for a consumer that adds
+// them itself (xa_heads_forward_partial_bf16: at rollout batch sizes the reduction kernel was one launch in eight of an
+// environment step).  *splits_out = 1 and nothing launched when the shape is not split: the caller takes the plain path.
+extern "C" int xa_gemm_bf16_tn_partial(const void* a, const void* b, int64_t m, int64_t n, int64_t k, void* workspace, int64_t workspace_bytes,
+                                       int* splits_out, xa_stream_t stream) {
+  const char* what = "xa_gemm_bf16_tn_partial";
+  XA_REQUIRE(a && b && splits_out, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(m > 0 && n > 0 && k > 0 && k % 8 == 0, XA_EINVAL, "%s: m=%lld n=%lld k=%lld (k a multiple of 8)", what, static_cast<long long>(m),
+             static_cast<long long>(n), static_cast<long long>(k));
+  XA_REQUIRE(xa::aligned(a, 16) && xa::aligned(b, 16), XA_EALIGN, "%s: a and b must be 16-byte aligned", what);
+  XA_REQUIRE(m < (int64_t(1) << 31) && n < (int64_t(1) << 31) && k < (int64_t(1) << 31), XA_EOVERFLOW, "%s: dimension too large", what);
+  const int splits = gemm_auto_splits(m, n, k);
+  *splits_out = 1;
+  if (splits <= 1 || workspace == nullptr || workspace_bytes < static_cast<int64_t>(splits) * m * n * 4) return XA_OK;
+  const int bn = gemm_tile_n(n);
+  CUtensorMap ma, mb;
+  if (int rc = make_map_2d(&ma, a, m, k, kBlockM, what)) return rc;
+  if (int rc = make_map_2d(&mb, b, n, k, bn, what)) return rc;
+  GemmParams p{};
+  p.m = m, p.n = n, p.k = k, p.ldc = n;
+  const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
+  p.kb_per_split = static_cast<int>((k_blocks + splits - 1) / splits);
+  p.splits = static_cast<int>((k_blocks + p.kb_per_split - 1) / p.kb_per_split);
+  p.partial = static_cast<float*>(workspace);
+  if (p.splits <= 1) return XA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (bn == 256) rc = launch<256, false>(ma, mb, p, s, what, false);
+  else if (bn == 128) rc = launch<128, false>(ma, mb, p, s, what, false);
+  else if (bn == 64) rc = launch<64, false>(ma, mb, p, s, what, false);
+  else rc = launch<16, false>(ma, mb, p, s, what, false);
+  if (rc == XA_OK) *splits_out = p.splits;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- layout helper

@@ -42,9 +42,58 @@ __device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
 // stride 16 bytes across the lanes (conflict-free: the first version's 32-byte lane stride made every read a 2-way
 // conflict, and with 32 vector reads per frame the kernel was bound by shared-memory wavefronts -- ncu: 2.7 M of them, 10 us),
 // each weight vector feeding both frames; R dot products are reduced with a butterfly.
-__global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ wh,
-                                                                  const float* __restrict__ bh, float* __restrict__ actor,
-                                                                  float* __restrict__ critic, int batch, int n_actions) {
+// kPartial: h does not exist yet -- the trunk's last Dense layer left `splits` fp32 partial products [splits, batch, 512]
+// (xa_gemm_bf16_tn_partial); this kernel adds them in split order, adds that layer's bias, applies its ReLU and rounds to bf16
+// -- the arithmetic of the GEMM's own reduction pass, bit for bit -- writes h (the backward pass reads it) and goes on as above:
+// one launch less per rollout step.
+struct HeadsPartial {
+  const float* partial;   // [splits, batch, 512]
+  const float* bias;      // [512] bias of the layer that produces h (may be NULL)
+  __nv_bfloat16* h_out;   // [batch, 512] (may be NULL)
+  int splits;
+};
+
+template <bool kPartial>
+__device__ __forceinline__ void load_h_row(const __nv_bfloat16* __restrict__ h, const HeadsPartial& hp, int64_t row, int64_t batch, int lane,
+                                           float (&x)[4][4]) {
+  if (!kPartial) {
+    const uint2* hr = reinterpret_cast<const uint2*>(h + row * kHidden);
+    uint2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(hr + 32 * j + lane);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack4(v[j], x[j]);
+  } else {
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float4* p0 = reinterpret_cast<const float4*>(hp.partial + row * kHidden);
+    const int64_t stride4 = batch * (kHidden / 4);
+    for (int s = 0; s < hp.splits; ++s) {   // split order, as splitk_reduce_kernel adds them
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = __ldg(p0 + s * stride4 + 32 * j + lane);
+        acc[j].x += v.x, acc[j].y += v.y, acc[j].z += v.z, acc[j].w += v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (hp.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(hp.bias) + 32 * j + lane);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(acc[j].x + b.x, 0.0f), fmaxf(acc[j].y + b.y, 0.0f));
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(acc[j].z + b.z, 0.0f), fmaxf(acc[j].w + b.w, 0.0f));
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo), packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      if (hp.h_out != nullptr) reinterpret_cast<uint2*>(hp.h_out + row * kHidden)[32 * j + lane] = packed;
+      unpack4(packed, x[j]);
+    }
+  }
+}
+
+template <bool kPartial>
+__global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_bfloat16* __restrict__ h, const HeadsPartial hp,
+                                                                  const __nv_bfloat16* __restrict__ wh, const float* __restrict__ bh,
+                                                                  float* __restrict__ actor, float* __restrict__ critic, int batch, int n_actions) {
   __shared__ __align__(16) float s_w[kRows][kHidden];
   xa::pdl_trigger();   // chained launch (xa_common.cuh): the successor may be scheduled early;
   xa::pdl_wait();      // the predecessor grid has completed before anything below touches global memory
@@ -61,14 +110,9 @@ __global__ void __launch_bounds__(kFwdThreads) heads_forward_kernel(const __nv_b
   const float my_bias = lane < kRows && lane <= n_actions ? bh[lane] : 0.0f;
   for (int row = 2 * (blockIdx.x * (kFwdThreads / 32) + warp); row < batch; row += 2 * warps) {
     const bool two = row + 1 < batch;
-    const uint2* h0 = reinterpret_cast<const uint2*>(h + static_cast<int64_t>(row) * kHidden);
-    const uint2* h1 = reinterpret_cast<const uint2*>(h + static_cast<int64_t>(row + (two ? 1 : 0)) * kHidden);
-    uint2 v0[4], v1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v0[j] = __ldg(h0 + 32 * j + lane), v1[j] = __ldg(h1 + 32 * j + lane);
     float x0[4][4], x1[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) unpack4(v0[j], x0[j]), unpack4(v1[j], x1[j]);
+    load_h_row<kPartial>(h, hp, row, batch, lane, x0);
+    load_h_row<kPartial>(h, hp, row + (two ? 1 : 0), batch, lane, x1);
     float acc0[kRows], acc1[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -230,8 +274,27 @@ int xa_heads_forward_bf16(const void* h, const void* wh, const float* bh, float*
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const int want = (batch + 2 * (kFwdThreads / 32) - 1) / (2 * (kFwdThreads / 32));
   const int grid = want < 4 * sms ? want : 4 * sms;  // a pair of frames per warp, up to four CTAs per SM
-  xa::launch_chained(batch <= 1024 ? xa::kChainSmall : xa::kChainElementwise, heads_forward_kernel, dim3(grid), dim3(kFwdThreads), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(h),
-                     static_cast<const __nv_bfloat16*>(wh), bh, actor, critic, batch, n_actions);
+  xa::launch_chained(batch <= 1024 ? xa::kChainSmall : xa::kChainElementwise, heads_forward_kernel<false>, dim3(grid), dim3(kFwdThreads), 0,
+                     static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(h), HeadsPartial{}, static_cast<const __nv_bfloat16*>(wh), bh, actor,
+                     critic, batch, n_actions);
+  return xa::check_launch(what);
+}
+
+int xa_heads_forward_partial_bf16(const float* partial, int splits, const float* bias, void* h_out, const void* wh, const float* bh, float* actor,
+                                  float* critic, int batch, int hidden, int n_actions, xa_stream_t stream) {
+  const char* what = "xa_heads_forward_partial_bf16";
+  XA_REQUIRE(partial && wh && bh && actor && critic, XA_EINVAL, "%s: null pointer", what);
+  XA_REQUIRE(batch > 0 && splits >= 1 && hidden == kHidden && n_actions > 0 && n_actions + 1 <= kRows, XA_EINVAL,
+             "%s: batch=%d splits=%d hidden=%d (must be %d) n_actions=%d (at most %d)", what, batch, splits, hidden, kHidden, n_actions, kRows - 1);
+  XA_REQUIRE(xa::aligned(partial, 16) && xa::aligned(wh, 16) && xa::aligned(bias, 16) && xa::aligned(h_out, 8), XA_EALIGN,
+             "%s: partial, bias and wh must be 16-byte aligned", what);
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int want = (batch + 2 * (kFwdThreads / 32) - 1) / (2 * (kFwdThreads / 32));
+  const int grid = want < 4 * sms ? want : 4 * sms;
+  HeadsPartial hp{partial, bias, static_cast<__nv_bfloat16*>(h_out), splits};
+  xa::launch_chained(batch <= 1024 ? xa::kChainSmall : xa::kChainElementwise, heads_forward_kernel<true>, dim3(grid), dim3(kFwdThreads), 0,
+                     static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(nullptr), hp, static_cast<const __nv_bfloat16*>(wh), bh, actor,
+                     critic, batch, n_actions);
   return xa::check_launch(what);
 }
 

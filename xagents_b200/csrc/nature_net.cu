@@ -35,6 +35,12 @@ static int forward_impl(const char* what, const xa_nature_cnn_t* n, const void* 
                                     n->relu_bits2, B, 84, 84, 2, 2, 32, 1, 1, stream));
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x2, n->w2, n->b2, n->x3, B, 10, 10, 128, 2, 2, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, n->relu_bits3, 0, stream));
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+  // small batches (rollout inference): the FC product is split along K; its partial sums are added by the heads kernel
+  int splits = 1;
+  XA_TRY(xa_gemm_bf16_tn_partial(n->y3, n->wf, B, 512, 3136, n->gemm_ws, n->gemm_ws_bytes, &splits, stream));
+  if (splits > 1)
+    return xa_heads_forward_partial_bf16(static_cast<const float*>(n->gemm_ws), splits, n->bf, n->h, n->wh, n->bh, n->actor, n->critic, B, 512,
+                                         n->n_actions, stream);
   XA_TRY(xa_gemm_bf16_tn_ex(n->y3, n->wf, n->h, n->bf, B, 512, 3136, 512, 1, 1, nullptr, 512, 0, 0, n->gemm_ws, n->gemm_ws_bytes, stream));
   return xa_heads_forward_bf16(n->h, n->wh, n->bh, n->actor, n->critic, B, 512, n->n_actions, stream);
 }
