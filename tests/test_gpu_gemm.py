@@ -12,7 +12,8 @@ DEV = 'cuda:0'
 
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize('m,n,k', [(128, 128, 64), (128, 128, 512), (256, 512, 3136), (8192, 512, 3136), (8192, 7, 512),
-                                   (300, 70, 136), (1, 16, 8), (129, 130, 72), (4096, 64, 576)])
+                                   (300, 70, 136), (1, 16, 8), (129, 130, 72), (4096, 64, 576),
+                                   (1100, 300, 200), (2048, 3136, 512), (1280, 256, 64), (600, 520, 72)])   # CTA pairs (m >= 512, n >= 256): ragged M / N, one K block
 @pytest.mark.parametrize('bias,relu,out_bf16', [(False, False, False), (True, True, False), (True, False, True)])
 def test_gemm_bf16_tn_vs_torch_fp32(m, n, k, bias, relu, out_bf16):
     g = torch.Generator(device=DEV)

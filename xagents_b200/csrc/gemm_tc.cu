@@ -18,6 +18,8 @@
 //   warps 2-5 epilogue: tcgen05.ld their TMEM lane quadrant (32 rows x 32 columns per instruction), add
 //            bias, apply ReLU, convert, store, then hand the accumulator back ("acc_empty").
 // SASS carries UTCHMMA / UTMALDG / LDTM (B200_PROFILING.md evidence table).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -37,10 +39,10 @@ struct GemmParams {
   int64_t col_group, col_group_pitch;  // col_group > 0: output column j lands at (j / col_group) * col_group_pitch + j % col_group
 };
 
-template <int BN>
+template <int BN, bool kPair = false>
 struct Smem {
   static constexpr int kStageA = kBlockM * kBlockK * 2;
-  static constexpr int kStageB = BN * kBlockK * 2;
+  static constexpr int kStageB = (kPair ? BN / 2 : BN) * kBlockK * 2;   // a CTA pair splits B's rows between its two CTAs
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (208 * 1024) / kStage > 8 ? 8 : (208 * 1024) / kStage;
   static constexpr int kEpiPitch = 32 * 2 + 16;  // bf16 epilogue: a warp's 32 x 32 chunk, rows padded against bank conflicts
@@ -52,10 +54,15 @@ struct Smem {
 // tile of the CTA), so two epilogues are in flight per SM and their latencies (tcgen05.ld, mask loads) overlap.
 constexpr int kGemmThreads = 64 + 8 * 32;
 
-template <int BN, bool kOutBf16>
+// kPair: launched as clusters of two CTAs (the two SMs of a TPC) that run ONE 256 x BN tile with cta_group::2 MMAs: each CTA
+// loads its 128 rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB per 128 x 256 x 64 block of products --
+// the FC products at 8192 frames were bound by L2 -> SM operand traffic (every CTA pulled 48 KB per 512 MMA cycles, ~28 TB/s
+// over 148 SMs).  The leader (cluster rank 0) issues the MMAs and owns the `full` / `acc_empty` barriers; tcgen05.commit
+// multicasts `empty` / `acc_full` arrivals to both CTAs; each CTA drains its own 128 accumulator rows.
+template <int BN, bool kOutBf16, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
-  using S = Smem<BN>;
+  using S = Smem<BN, kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStage);
@@ -69,10 +76,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int k_blocks = static_cast<int>((p.k + kBlockK - 1) / kBlockK);
-  const int tiles_m = static_cast<int>((p.m + kBlockM - 1) / kBlockM);
+  constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;   // rows of one work item (a pair's item is 256 rows, 128 per CTA)
+  const int tiles_m = static_cast<int>((p.m + kTileM - 1) / kTileM);
   const int tiles_n = static_cast<int>((p.n + BN - 1) / BN);
   const int n_tiles = tiles_m * tiles_n;
   const int n_items = n_tiles * p.splits;  // (tile, K split) pairs; tile varies fastest
+  const uint32_t rank = kPair ? cluster_rank() : 0u;
+  const int unit = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);       // this CTA's (pair's) first item ...
+  const int n_units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);       // ... and the stride between its items
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;  // the epilogue reads 32 columns at a time
   constexpr uint32_t kTmemCols = 2 * kAccStride;      // two accumulators
 
@@ -85,17 +96,22 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       xa::mbar_init(acc_full + a, 1);
-      xa::mbar_init(acc_empty + a, 4);  // one arrival per epilogue warp
+      xa::mbar_init(acc_empty + a, kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
     }
     xa::fence_barrier_init();
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(xa::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   xa::pdl_wait();      // first global-memory access below: the predecessor grid has completed
@@ -104,7 +120,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
     if (elect_one()) {  // ---- TMA producer: one ring of stages shared by all of this CTA's tiles
       int s = 0;
       uint32_t round = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = unit; item < n_items; item += n_units) {
         const int tile = item % n_tiles, split = item / n_tiles;
         const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
         const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
@@ -112,20 +128,26 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
           if (round > 0) mbar_wait_wd(empty + s, (round - 1) & 1);
           uint8_t* a_dst = smem + s * S::kStage;
           uint8_t* b_dst = a_dst + S::kStageA;
-          xa::mbar_expect_tx(full + s, S::kStage);
-          tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
-          tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+          if (kPair) {  // the leader's barrier counts the bytes of both CTAs' boxes; each CTA loads its rows of A and its half of B
+            if (rank == 0) xa::mbar_expect_tx(full + s, 2 * S::kStage);
+            tma_load_2d_pair(a_dst, &map_a, kb * kBlockK, tile_m * kTileM + static_cast<int>(rank) * kBlockM, full + s);
+            tma_load_2d_pair(b_dst, &map_b, kb * kBlockK, tile_n * BN + static_cast<int>(rank) * (BN / 2), full + s);
+          } else {
+            xa::mbar_expect_tx(full + s, S::kStage);
+            tma_load_2d(a_dst, &map_a, kb * kBlockK, tile_m * kBlockM, full + s);
+            tma_load_2d(b_dst, &map_b, kb * kBlockK, tile_n * BN, full + s);
+          }
           if (++s == S::kStages) s = 0, ++round;
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {  // ---- MMA issuer
-      constexpr uint32_t idesc = make_idesc(kBlockM, BN);
+    if ((!kPair || rank == 0) && elect_one()) {  // ---- MMA issuer (a pair's leader only)
+      constexpr uint32_t idesc = make_idesc(kTileM, BN);
       uint32_t lt = 0, phase = 0;
       int s = 0;
       const uint64_t desc0 = make_smem_desc(smem);  // stage 0; stage s adds s * kStage to the address field
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++lt) {
+      for (int item = unit; item < n_items; item += n_units, ++lt) {
         const int split = item / n_tiles;
         const int kb0 = split * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
         const uint32_t acc = lt & 1, use = lt >> 1;
@@ -142,12 +164,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (address >> 4) field
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            if (kPair) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
-          umma_commit(empty + s);  // stage may be refilled once these MMAs have read it
+          if (kPair) umma_commit_pair(empty + s);   // both CTAs' producers may refill the stage once these MMAs have read it
+          else umma_commit(empty + s);
           if (++s == S::kStages) s = 0, phase ^= 1;
         }
-        umma_commit(acc_full + acc);  // accumulator complete
+        if (kPair) umma_commit_pair(acc_full + acc);  // accumulator complete: both CTAs' epilogue groups
+        else umma_commit(acc_full + acc);
       }
     }
   } else {
@@ -158,10 +183,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
     const bool bias_vec = xa::aligned(p.bias, 16);
     constexpr int kChunks = BN < 32 ? 1 : BN / 32;
     for (uint32_t lt = grp;; lt += 2) {
-      const int item = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
+      const int item = unit + static_cast<int>(lt) * n_units;
       if (item >= n_items) break;
       const int tile = item % n_tiles, split = item / n_tiles;
-      const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
+      const int tile_n = tile / tiles_m;
+      const int tile_m = kPair ? 2 * (tile % tiles_m) + static_cast<int>(rank) : tile % tiles_m;   // in units of this CTA's 128 rows
       const uint32_t acc = grp;
       const int64_t row = static_cast<int64_t>(tile_m) * kBlockM + quad * 32 + lane;
       // The ReLU-derivative mask does not depend on the accumulator: chunks 0 and 1 are fetched before the wait, chunk
@@ -321,14 +347,19 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+      if (lane == 0) {
+        if (kPair) mbar_arrive_leader(acc_empty + acc);   // the issuing CTA waits for both CTAs' epilogues
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (kPair) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other still arrives on its barriers / reads its operands
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -349,6 +380,45 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
     else
       static_cast<float*>(p.c)[row * p.ldc + col] = acc;
   }
+}
+
+// CTA pairs: clusters of two CTAs, at most one pair per TPC.  The launch attribute makes the hardware co-schedule the two
+// CTAs of a pair on the two SMs of one TPC (what cta_group::2 needs).
+template <int BN, bool kOutBf16>
+int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
+  auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16, true>;
+  using S = Smem<BN, true>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+    if (e != cudaSuccess) {
+      xa::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    configured_dev = dev;
+  }
+  const int64_t items = ((p.m + 2 * kBlockM - 1) / (2 * kBlockM)) * ((p.n + BN - 1) / BN) * p.splits;
+  const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
+  const int64_t pairs = items < sms / 2 ? items : sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs)), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = S::kBytes, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, ma, mb, p);
+  return xa::check_launch(what);
+}
+
+// XA_GEMM_PAIR=0 in the environment keeps every product on single CTAs (A/B switch; read once)
+static bool gemm_pairs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XA_GEMM_PAIR");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 template <int BN, bool kOutBf16>
@@ -440,6 +510,11 @@ extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const f
     p.kb_per_split = static_cast<int>(k_blocks);
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bn == 256 && p.splits == 1 && m >= 512 && gemm_pairs_enabled()) {  // CTA pairs: each CTA loads half of the B tile
+    CUtensorMap mb2;
+    if (int rc = make_map_2d(&mb2, b, n, k, bn / 2, what)) return rc;
+    return out_bf16 ? launch_pair<256, true>(ma, mb2, p, s, what) : launch_pair<256, false>(ma, mb2, p, s, what);
+  }
   if (bn == 256) return out_bf16 ? launch<256, true>(ma, mb, p, s, what) : launch<256, false>(ma, mb, p, s, what);
   if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);
   if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
