@@ -240,6 +240,14 @@ int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias,
 /* Scratch for split-K (few output tiles, long K: the weight-gradient products); 0 when the shape does not split.
  * Passing workspace = NULL simply disables splitting.  relu_mask: optional bf16 [m, ldc], c *= (mask > 0). */
 int64_t xa_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
+/* c [m, ldc] bf16 = (a b^T) * (mask > 0) with the ReLU-derivative mask as BITS: bit j of word i of mask_bits <=> element
+ * 32 i + j of the [m, mask_ld] activation is > 0 (what xa_conv2d_nhwc_bf16_ex writes through relu_bits_out).  The data
+ * gradient of a Dense layer behind a ReLU (tape.gradient through Dense + relu, xagents/ppo/agent.py:134): 1/16 of the mask
+ * bytes, and the epilogue stores 32 x 32 boxes by TMA.  n and mask_ld multiples of 32, ldc a multiple of 8, c 16-byte
+ * aligned; col_group / col_group_pitch as in xa_gemm_bf16_tn_ex. */
+int xa_gemm_bf16_tn_maskbits(const void* a, const void* b, void* c, int64_t m, int64_t n, int64_t k, int64_t ldc,
+                             const uint32_t* mask_bits, int64_t mask_ld, int64_t col_group, int64_t col_group_pitch,
+                             xa_stream_t stream);
 /* The split-K product without its reduction pass: fp32 partial tiles [*splits_out, m, n] in `workspace` for a consumer that
  * adds them itself (xa_heads_forward_partial_bf16).  *splits_out = 1 and nothing is launched when the shape is not split
  * or the workspace is too small: take xa_gemm_bf16_tn(_ex) then.  (Keras Dense of the trunk, xagents/utils/common.py:239-258.) */
@@ -421,6 +429,7 @@ typedef struct xa_nature_cnn_t {
   int64_t n_grad;
   uint32_t *relu_bits2, *relu_bits3; /* optional (both or none): ReLU-derivative bit masks of x2 / x3 (numel / 8 bytes each), written
                                         by the forward pass and read by the data gradients instead of the activations */
+  uint32_t* relu_bitsf;              /* optional: the same for y3 (batch * 3136 / 8 bytes), read by the FC layer's data gradient */
 } xa_nature_cnn_t;
 int xa_nature_cnn_forward(const xa_nature_cnn_t* net, const void* frames, int frames_s2d, xa_stream_t stream);
 /* forward on the minibatch frames[frame_idx[0 .. batch)] of a frame store [n_frames, 84, 84, 4] uint8 without gathering it: the

@@ -147,3 +147,44 @@ def test_gemm_atb_from_row_major_operands(k, m, n):
     assert float((got.double() - want).abs().max()) <= 2e-5 * float(want.abs().max()) * max(1.0, (k / 1000) ** 0.5)
     one = ops.gemm_bf16_atb(a, b, split_k=False)
     assert float((one.double() - want).abs().max()) <= 2e-3 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('m,n,k,group', [(8192, 3136, 512, (448, 576)), (1000, 3136, 512, (448, 576)), (300, 64, 72, None), (129, 288, 200, (96, 128))])
+def test_gemm_with_the_relu_mask_as_bits_equals_the_bf16_mask_form(m, n, k, group):
+    """xa_gemm_bf16_tn_maskbits (mask = one bit per element, epilogue through TMA stores of 32 x 32 boxes) against xa_gemm_bf16_tn_ex with
+    the bf16 activation as the mask (shared-memory transpose + per-lane stores): identical outputs, untouched bytes stay untouched
+    (the grouped-column form writes a [m, h*w*c] gradient onto a zero-bordered grid)."""
+    import ctypes
+    from xagents_b200 import _ffi
+    lib = _ffi.lib()
+    g = torch.Generator(device=DEV)
+    g.manual_seed(m + n)
+    a = (torch.randn(m, k, device=DEV, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(n, k, device=DEV, generator=g) * 0.1).bfloat16()
+    act = torch.randn(m, n, device=DEV, generator=g).relu().bfloat16()          # the layer's output: about half of it zero
+    bits = (act > 0).view(m, n // 32, 32).to(torch.int64)
+    words = (bits << torch.arange(32, device=DEV)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+    cg, cp = group if group is not None else (0, 0)
+    ldc = (n // cg) * cp + 64 if group is not None else n + 8
+    outs = []
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for form in ('bf16', 'bits'):
+        c = torch.full((m, ldc), 7.0, device=DEV).bfloat16()
+        if form == 'bits':
+            _ffi.check('maskbits', lib.xa_gemm_bf16_tn_maskbits(p(a), p(b), p(c), m, n, k, ldc, p(words), n, cg, cp, s))
+        else:
+            _ffi.check('ex', lib.xa_gemm_bf16_tn_ex(p(a), p(b), p(c), None, m, n, k, ldc, 1, 0, p(act), n, cg, cp, None, 0, s))
+        torch.cuda.synchronize()
+        outs.append(c)
+    assert torch.equal(outs[0], outs[1])
+    ref = (a.float() @ b.float().t()) * (act > 0)
+    got = outs[1].float()
+    if group is not None:
+        got = got[:, :(n // cg) * cp].view(m, n // cg, cp)[:, :, :cg].reshape(m, n)
+        assert bool((outs[1].float().view(m, -1)[:, :(n // cg) * cp].view(m, n // cg, cp)[:, :, cg:] == 7.0).all())   # the border columns
+    else:
+        got = got[:, :n]
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
+    assert bool((outs[1][:, -8:].float() == 7.0).all())

@@ -74,7 +74,8 @@ class NatureCnn(ctypes.Structure):
                 [('gemm_ws_bytes', ctypes.c_int64), ('scratch', ctypes.c_void_p), ('scratch_floats', ctypes.c_int64)] +
                 [(name, ctypes.c_int64) for name in ('off_c1', 'off_c2', 'off_c3', 'off_fc', 'off_heads')] +
                 [('grad_map', ctypes.c_void_p), ('grad_dest', ctypes.c_void_p), ('segments', GradSegment * XA_MAX_GRAD_SEGMENTS), ('n_segments', ctypes.c_int32),
-                 ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64), ('relu_bits2', ctypes.c_void_p), ('relu_bits3', ctypes.c_void_p)])
+                 ('reserved', ctypes.c_int32), ('n_grad', ctypes.c_int64), ('relu_bits2', ctypes.c_void_p), ('relu_bits3', ctypes.c_void_p),
+                 ('relu_bitsf', ctypes.c_void_p)])
 
 
 # name -> (restype, argtypes); every symbol include/xagents_b200.h declares
@@ -129,6 +130,7 @@ PROTOTYPES = {
     'xa_gemm_atb_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
     'xa_gemm_bf16_atb': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p] + [ctypes.c_int64] * 4 + [ctypes.c_void_p, ctypes.c_int64, c_stream]),
     'xa_gemm_workspace_bytes': (ctypes.c_int64, [ctypes.c_int64] * 3),
+    'xa_gemm_bf16_tn_maskbits': (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int64] * 4 + [ctypes.c_void_p] + [ctypes.c_int64] * 3 + [c_stream]),
     'xa_gemm_bf16_tn_partial': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int), c_stream]),
     'xa_conv2d_nhwc_bf16': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_f32p, ctypes.c_void_p] + [ctypes.c_int] * 11 +
                             [ctypes.c_void_p, c_stream]),

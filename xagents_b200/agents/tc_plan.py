@@ -63,6 +63,8 @@ class NaturePlan:
         self.bits3 = torch.empty(B * 9 * 9 * 64 // 32, dtype=torch.int32, device=dev)
         if os.environ.get('XA_NO_RELU_BITS') != '1':               # tuning switch: the data gradients read the bf16 activations instead
             net.relu_bits2, net.relu_bits3 = self.bits2.data_ptr(), self.bits3.data_ptr()
+            self.bitsf = torch.empty(B * 3136 // 32, dtype=torch.int32, device=dev)      # y3's signs, for the FC layer's data gradient
+            net.relu_bitsf = self.bitsf.data_ptr()
         splits, ld = ctypes.c_int(), ctypes.c_int()
         conv = {}
         off = 0

@@ -37,6 +37,13 @@ struct GemmParams {
   const __nv_bfloat16* mask;   // optional [m, mask_ld]: result *= (mask > 0)  (ReLU derivative in a backward product)
   int64_t mask_ld;
   int64_t col_group, col_group_pitch;  // col_group > 0: output column j lands at (j / col_group) * col_group_pitch + j % col_group
+  // bf16 output through TMA stores (tma_store != 0; map_c covers c as [m, ldc] in 32 x 32 boxes, SWIZZLE_64B): the epilogue's
+  // thread = row registers go to shared memory once and ONE instruction per warp and chunk writes the 32 x 32 box -- no
+  // transpose, no per-lane address arithmetic, no per-lane stores.  The ReLU-derivative mask is then a BIT mask (bit j of
+  // word i <=> element 32 i + j of the [m, mask_ld] activation is > 0): one word per row and chunk.
+  const uint32_t* mask_bits;
+  int64_t mask_words;  // words per row of mask_bits
+  int tma_store;
 };
 
 template <int BN, bool kPair = false>
@@ -46,8 +53,10 @@ struct Smem {
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (208 * 1024) / kStage > 8 ? 8 : (208 * 1024) / kStage;
   static constexpr int kEpiPitch = 32 * 2 + 16;  // bf16 epilogue: a warp's 32 x 32 chunk, rows padded against bank conflicts
-  static constexpr int kEpiBytes = 8 * 32 * kEpiPitch;
-  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiBytes;
+  static constexpr int kEpiWarp = 32 * kEpiPitch;  // 2560 B per warp = 5 x 512: also holds the 2 KB, 512-byte-aligned box of the TMA-store path
+  static constexpr int kEpiBytes = 8 * kEpiWarp;
+  static constexpr int kTableBytes = 4096;       // byte of mask bits -> four bf16x2 AND masks
+  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + kEpiBytes + kTableBytes + 256 /*barriers*/;
 };
 
 // 2 + 8 warps: TMA producer, MMA issuer, two epilogue groups of four warps; group g drains accumulator g (every other
@@ -61,16 +70,18 @@ constexpr int kGemmThreads = 64 + 8 * 32;
 // multicasts `empty` / `acc_full` arrivals to both CTAs; each CTA drains its own 128 accumulator rows.
 template <int BN, bool kOutBf16, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                 const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+                                                                 const __grid_constant__ CUtensorMap map_b,
+                                                                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   using S = Smem<BN, kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStage);
+  uint8_t* epi_stage = smem + S::kStages * S::kStage;  // [8 warps][32 rows][kEpiPitch]; 1024-byte aligned (stages are multiples of 1 KB)
+  uint32_t* bit_table = reinterpret_cast<uint32_t*>(epi_stage + S::kEpiBytes);   // [256][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_stage + S::kEpiBytes + S::kTableBytes);
   uint64_t* empty = full + S::kStages;
   uint64_t* acc_full = empty + S::kStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* epi_stage = smem + S::kStages * S::kStage + 256;  // [8 warps][32 rows][kEpiPitch]
 
   xa::pdl_trigger();   // chained launch (xa_common.cuh): the on-chip set-up below overlaps the predecessor's tail
   const int warp = threadIdx.x >> 5;
@@ -87,9 +98,16 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
   constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;  // the epilogue reads 32 columns at a time
   constexpr uint32_t kTmemCols = 2 * kAccStride;      // two accumulators
 
+  if (kOutBf16 && p.mask_bits != nullptr) {  // byte b of a row's mask bits -> the AND masks of its eight bf16 values
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+      const int b = i >> 2, k = i & 3;
+      bit_table[i] = (((b >> (2 * k)) & 1) ? 0x0000FFFFu : 0u) | (((b >> (2 * k + 1)) & 1) ? 0xFFFF0000u : 0u);
+    }
+  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (kOutBf16 && p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < S::kStages; ++s) {
       xa::mbar_init(full + s, 1);
       xa::mbar_init(empty + s, 1);
@@ -241,6 +259,58 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
               for (int j = 0; j < 32 && col0 + j < p.n; ++j) dstp[j] = __uint_as_float(v[j]);
             }
           }
+        } else if (kOutBf16 && p.tma_store && col0 + 32 <= p.n && bias_vec && p.mask == nullptr) {  // warp-uniform
+          // TMA-store path: thread = row all the way.  The short-K products are bound by the instruction count of this epilogue
+          // (ncu: the FC data gradient ran 12 400 warp-instructions per 128 x 256 tile against 4096 MMA cycles, eight epilogue
+          // warps 74 % busy); staged through a shared-memory transpose a chunk cost ~190 instructions per warp, here ~70.
+          const int64_t ocol0 = p.col_group > 0 ? (col0 / p.col_group) * p.col_group_pitch + col0 % p.col_group : col0;
+          uint32_t h[16];
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(bp + q);
+              float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
+              float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
+              if (p.relu) x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f), x2 = fmaxf(x2, 0.0f), x3 = fmaxf(x3, 0.0f);
+              const __nv_bfloat162 lo2 = __floats2bfloat162_rn(x0, x1), hi2 = __floats2bfloat162_rn(x2, x3);
+              h[2 * q] = *reinterpret_cast<const uint32_t*>(&lo2), h[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hi2);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
+              if (p.relu) x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f);
+              const __nv_bfloat162 t = __floats2bfloat162_rn(x0, x1);
+              h[q] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+          }
+          if (p.mask_bits != nullptr) {  // ReLU derivative of the layer below: my row's 32 bits of this chunk
+            const uint32_t bits = row < p.m ? __ldg(p.mask_bits + row * p.mask_words + (col0 >> 5)) : 0u;
+            const uint32_t tb = xa::smem_u32(bit_table);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 mk;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mk.x), "=r"(mk.y), "=r"(mk.z), "=r"(mk.w) : "r"(tb + ((bits >> (8 * q)) & 255u) * 16u));
+              h[4 * q] &= mk.x, h[4 * q + 1] &= mk.y, h[4 * q + 2] &= mk.z, h[4 * q + 3] &= mk.w;
+            }
+          }
+          const uint32_t st = xa::smem_u32(epi_stage + (warp - 2) * S::kEpiWarp);   // this warp's 32 x 64-byte box (SWIZZLE_64B)
+          if (lane == 0) xa::bulk_wait_read<0>();   // the previous chunk's store has read the box
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // 16-byte piece j of my row sits at piece j ^ ((row >> 1) & 3): conflict-free, and the tensor map's swizzle
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)), "r"(h[4 * j]), "r"(h[4 * j + 1]),
+                         "r"(h[4 * j + 2]), "r"(h[4 * j + 3])
+                         : "memory");
+          xa::fence_proxy_async();   // my writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_c), "r"(static_cast<int>(ocol0)),
+                         "r"(tile_m * kBlockM + quad * 32), "r"(st)
+                         : "memory");
+            xa::bulk_commit();
+          }
         } else if ((kOutBf16 || row < p.m) && col0 + 32 <= p.n && vec_ok && bias_vec && (p.mask == nullptr || fast_mask)) {  // warp-uniform for bf16
           // Fast path (a full chunk of 32 columns, vector-aligned): the epilogue of the short-K products is bounded by its
           // instruction count, so no per-element flag tests here -- bias by vector loads, ReLU as one max, the mask as a
@@ -353,6 +423,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
       }
     }
   }
+  if (kOutBf16 && p.tma_store && warp >= 2 && lane == 0) xa::bulk_wait_all<0>();   // shared memory must outlive the stores
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (kPair) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other still arrives on its barriers / reads its operands
   else __syncthreads();
@@ -364,6 +435,16 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_tn_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------- host
+}  // namespace
+// XA_GEMM_TMA_STORE=0 keeps the bf16 epilogue on the shared-memory transpose + per-lane stores (A/B switch; read once)
+bool xa::gemm_tma_store_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XA_GEMM_TMA_STORE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+namespace {
 // split-K second pass: C = sum_s partial[s] (+ bias) (ReLU), in split order -> deterministic
 template <bool kOutBf16>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
@@ -385,7 +466,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
 // CTA pairs: clusters of two CTAs, at most one pair per TPC.  The launch attribute makes the hardware co-schedule the two
 // CTAs of a pair on the two SMs of one TPC (what cta_group::2 needs).
 template <int BN, bool kOutBf16>
-int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what) {
+int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, cudaStream_t stream, const char* what) {
   auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16, true>;
   using S = Smem<BN, true>;
   static thread_local int configured_dev = -1;
@@ -408,7 +489,7 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  (void)cudaLaunchKernelEx(&cfg, kernel, ma, mb, p);
+  (void)cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, p);
   return xa::check_launch(what);
 }
 
@@ -421,8 +502,10 @@ static bool gemm_pairs_enabled() {
   return on;
 }
 
+
 template <int BN, bool kOutBf16>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream, const char* what, bool reduce = true) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, cudaStream_t stream, const char* what,
+           bool reduce = true) {
   auto kernel = gemm_bf16_tn_kernel<BN, kOutBf16>;
   static thread_local int configured_dev = -1;  // opt-in shared memory is a per-device attribute of the kernel
   int dev = 0;
@@ -438,7 +521,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   const int64_t items = ((p.m + kBlockM - 1) / kBlockM) * ((p.n + BN - 1) / BN) * p.splits;
   const int sms = xa::sm_count() > 0 ? xa::sm_count() : 148;
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);  // persistent: at most one CTA per SM
-  xa::launch_chained(items * ((p.k + kBlockK - 1) / kBlockK) <= 16 * sms ? xa::kChainSmall : xa::kChainLarge, kernel, dim3(grid), dim3(kGemmThreads), Smem<BN>::kBytes, stream, ma, mb, p);
+  xa::launch_chained(items * ((p.k + kBlockK - 1) / kBlockK) <= 16 * sms ? xa::kChainSmall : xa::kChainLarge, kernel, dim3(grid), dim3(kGemmThreads), Smem<BN>::kBytes, stream, ma, mb, mc, p);
   if (int rc = xa::check_launch(what)) return rc;
   if (p.splits > 1 && reduce) {
     const int64_t want = (p.m * p.n + 255) / 256;
@@ -476,10 +559,30 @@ extern "C" int xa_gemm_bf16_tn(const void* a, const void* b, void* c, const floa
   return xa_gemm_bf16_tn_ex(a, b, c, bias, m, n, k, ldc, out_bf16, relu, relu_mask, ldc, 0, 0, workspace, workspace_bytes, stream);
 }
 
+static int gemm_impl(const char* what, const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k, int64_t ldc,
+                     int out_bf16, int relu, const void* relu_mask, int mask_is_bits, int64_t mask_ld, int64_t col_group, int64_t col_group_pitch,
+                     void* workspace, int64_t workspace_bytes, xa_stream_t stream);
+
 extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k,
                                   int64_t ldc, int out_bf16, int relu, const void* relu_mask, int64_t mask_ld, int64_t col_group,
                                   int64_t col_group_pitch, void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
-  const char* what = "xa_gemm_bf16_tn";
+  return gemm_impl("xa_gemm_bf16_tn", a, b, c, bias, m, n, k, ldc, out_bf16, relu, relu_mask, 0, mask_ld, col_group, col_group_pitch, workspace,
+                   workspace_bytes, stream);
+}
+
+// The same product with the ReLU-derivative mask as BITS (bit j of word i <=> element 32 i + j of the [m, mask_ld] activation is > 0;
+// written by the forward epilogue of the layer below, xa_conv2d_nhwc_bf16_ex bits_out): bf16 output only, mask_ld a multiple of 32.
+extern "C" int xa_gemm_bf16_tn_maskbits(const void* a, const void* b, void* c, int64_t m, int64_t n, int64_t k, int64_t ldc, const uint32_t* mask_bits,
+                                        int64_t mask_ld, int64_t col_group, int64_t col_group_pitch, xa_stream_t stream) {
+  const char* what = "xa_gemm_bf16_tn_maskbits";
+  XA_REQUIRE(mask_bits != nullptr && mask_ld % 32 == 0 && xa::aligned(mask_bits, 4), XA_EINVAL, "%s: mask_bits null or mask_ld=%lld not a multiple of 32", what,
+             static_cast<long long>(mask_ld));
+  return gemm_impl(what, a, b, c, nullptr, m, n, k, ldc, 1, 0, mask_bits, 1, mask_ld, col_group, col_group_pitch, nullptr, 0, stream);
+}
+
+static int gemm_impl(const char* what, const void* a, const void* b, void* c, const float* bias, int64_t m, int64_t n, int64_t k, int64_t ldc,
+                     int out_bf16, int relu, const void* relu_mask, int mask_is_bits, int64_t mask_ld, int64_t col_group, int64_t col_group_pitch,
+                     void* workspace, int64_t workspace_bytes, xa_stream_t stream) {
   XA_REQUIRE(a && b && c, XA_EINVAL, "%s: null pointer", what);
   XA_REQUIRE(col_group >= 0 && (col_group == 0 || (col_group % 32 == 0 && col_group_pitch >= col_group &&
                                                    ((n + col_group - 1) / col_group - 1) * col_group_pitch + col_group <= ldc)),
@@ -497,7 +600,9 @@ extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const f
   if (int rc = make_map_2d(&mb, b, n, k, bn, what)) return rc;
   GemmParams p{};
   p.c = c, p.bias = bias, p.m = m, p.n = n, p.k = k, p.ldc = ldc, p.relu = relu;
-  p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+  p.mask = mask_is_bits ? nullptr : static_cast<const __nv_bfloat16*>(relu_mask);
+  p.mask_bits = mask_is_bits ? static_cast<const uint32_t*>(relu_mask) : nullptr;
+  p.mask_words = mask_ld / 32;
   p.mask_ld = mask_ld, p.col_group = col_group, p.col_group_pitch = col_group_pitch;
   const int64_t k_blocks = (k + kBlockK - 1) / kBlockK;
   int splits = workspace != nullptr ? gemm_auto_splits(m, n, k) : 1;
@@ -510,15 +615,24 @@ extern "C" int xa_gemm_bf16_tn_ex(const void* a, const void* b, void* c, const f
     p.kb_per_split = static_cast<int>(k_blocks);
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // bf16 output through TMA stores: c as a [m, ldc] tensor in 32 x 32 boxes (bf16 masks keep the transposed per-lane path)
+  const bool store_ok = out_bf16 && bn >= 32 && p.splits == 1 && p.mask == nullptr && ldc % 8 == 0 && xa::aligned(c, 16) && xa::aligned(bias, 16) &&
+                        (col_group == 0 || col_group_pitch % 8 == 0) && (!mask_is_bits || (n % 32 == 0 && mask_ld % 32 == 0));
+  XA_REQUIRE(!mask_is_bits || store_ok, XA_EALIGN, "%s: the bit-mask form needs ldc %% 8 == 0, n %% 32 == 0 and a 16-byte aligned c", what);
+  CUtensorMap mc = ma;
+  if (store_ok && (mask_is_bits || xa::gemm_tma_store_enabled())) {
+    if (int rc = make_map_2d_box(&mc, c, m, ldc, 32, 32, what)) return rc;
+    p.tma_store = 1;
+  }
   if (bn == 256 && p.splits == 1 && m >= 512 && gemm_pairs_enabled()) {  // CTA pairs: each CTA loads half of the B tile
     CUtensorMap mb2;
     if (int rc = make_map_2d(&mb2, b, n, k, bn / 2, what)) return rc;
-    return out_bf16 ? launch_pair<256, true>(ma, mb2, p, s, what) : launch_pair<256, false>(ma, mb2, p, s, what);
+    return out_bf16 ? launch_pair<256, true>(ma, mb2, mc, p, s, what) : launch_pair<256, false>(ma, mb2, mc, p, s, what);
   }
-  if (bn == 256) return out_bf16 ? launch<256, true>(ma, mb, p, s, what) : launch<256, false>(ma, mb, p, s, what);
-  if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, p, s, what) : launch<128, false>(ma, mb, p, s, what);
-  if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, p, s, what) : launch<64, false>(ma, mb, p, s, what);
-  return out_bf16 ? launch<16, true>(ma, mb, p, s, what) : launch<16, false>(ma, mb, p, s, what);
+  if (bn == 256) return out_bf16 ? launch<256, true>(ma, mb, mc, p, s, what) : launch<256, false>(ma, mb, mc, p, s, what);
+  if (bn == 128) return out_bf16 ? launch<128, true>(ma, mb, mc, p, s, what) : launch<128, false>(ma, mb, mc, p, s, what);
+  if (bn == 64) return out_bf16 ? launch<64, true>(ma, mb, mc, p, s, what) : launch<64, false>(ma, mb, mc, p, s, what);
+  return out_bf16 ? launch<16, true>(ma, mb, mc, p, s, what) : launch<16, false>(ma, mb, mc, p, s, what);
 }
 
 // The split-K product WITHOUT its reduction pass: fp32 partial tiles [splits, m, n] in `workspace`, for a consumer that adds
@@ -548,10 +662,10 @@ extern "C" int xa_gemm_bf16_tn_partial(const void* a, const void* b, int64_t m, 
   if (p.splits <= 1) return XA_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
-  if (bn == 256) rc = launch<256, false>(ma, mb, p, s, what, false);
-  else if (bn == 128) rc = launch<128, false>(ma, mb, p, s, what, false);
-  else if (bn == 64) rc = launch<64, false>(ma, mb, p, s, what, false);
-  else rc = launch<16, false>(ma, mb, p, s, what, false);
+  if (bn == 256) rc = launch<256, false>(ma, mb, ma, p, s, what, false);
+  else if (bn == 128) rc = launch<128, false>(ma, mb, ma, p, s, what, false);
+  else if (bn == 64) rc = launch<64, false>(ma, mb, ma, p, s, what, false);
+  else rc = launch<16, false>(ma, mb, ma, p, s, what, false);
   if (rc == XA_OK) *splits_out = p.splits;
   return rc;
 }

@@ -34,7 +34,7 @@ static int forward_impl(const char* what, const xa_nature_cnn_t* n, const void* 
     XA_TRY(xa_conv2d_u8_s2d_bf16_ex(static_cast<const uint8_t*>(frames), n_frames, frame_idx, n_steps, n_envs, n->w1, n->b1, n->x2, n->x1,
                                     n->relu_bits2, B, 84, 84, 2, 2, 32, 1, 1, stream));
   XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x2, n->w2, n->b2, n->x3, B, 10, 10, 128, 2, 2, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, n->relu_bits3, 0, stream));
-  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+  XA_TRY(xa_conv2d_nhwc_bf16_ex(n->x3, n->w3, n->b3, n->y3, B, 9, 9, 64, 3, 3, 64, 0, 0, 1, 0, nullptr, 0, 0, 0, 0, n->relu_bitsf, 0, stream));
   // small batches (rollout inference): the FC product is split along K; its partial sums are added by the heads kernel
   int splits = 1;
   XA_TRY(xa_gemm_bf16_tn_partial(n->y3, n->wf, B, 512, 3136, n->gemm_ws, n->gemm_ws_bytes, &splits, stream));
@@ -75,7 +75,10 @@ int xa_nature_cnn_backward(const xa_nature_cnn_t* n, const void* frames_s2d_or_n
   XA_TRY(xa_heads_backward_bf16(d_actor, d_critic, n->h, n->wh, n->dh, sc + n->off_heads, room - n->off_heads, B, 512, n->n_actions, stream));
   // FC512: dW = dh^T y3 (split partials), dX = dh Wf masked by y3 > 0, written as 7x7 onto conv3's zero-bordered 9x9 grid
   XA_TRY(xa_gemm_bf16_atb_partial(n->dh, n->y3, 512, 3136, B, sc + n->off_fc, bytes_from(n->off_fc), stream));
-  XA_TRY(xa_gemm_bf16_tn_ex(n->dh, n->wf_t, n->g3, nullptr, B, 3136, 512, 9 * 9 * 64, 1, 0, n->y3, 3136, 7 * 64, 9 * 64, nullptr, 0, stream));
+  if (n->relu_bitsf != nullptr && xa::gemm_tma_store_enabled())   // y3's signs as bits (written by conv3's forward epilogue), 32 x 32 boxes stored by TMA
+    XA_TRY(xa_gemm_bf16_tn_maskbits(n->dh, n->wf_t, n->g3, B, 3136, 512, 9 * 9 * 64, n->relu_bitsf, 3136, 7 * 64, 9 * 64, stream));
+  else
+    XA_TRY(xa_gemm_bf16_tn_ex(n->dh, n->wf_t, n->g3, nullptr, B, 3136, 512, 9 * 9 * 64, 1, 0, n->y3, 3136, 7 * 64, 9 * 64, nullptr, 0, stream));
   // conv3, conv2: weight gradient from the natural NHWC tensors, data gradient = flat convolution with flipped weights
   XA_TRY(xa_conv_wgrad_nhwc_bf16_partial(n->x3, n->g3, 64, 64, 3, 3, 9, static_cast<int64_t>(B) * 81, sc + n->off_c3, bytes_from(n->off_c3), stream));
   const bool bits = n->relu_bits2 != nullptr && n->relu_bits3 != nullptr;  // ReLU derivatives from the forward pass's bit masks

@@ -35,6 +35,7 @@ int sm_count();                      // cached multiProcessorCount of the curren
 // XA_PDL in the environment: 0 = never (plain stream order), 1 = small launches (default), 2 = every launch, 3 = small
 // tensor-core launches only.
 int pdl_level();
+bool gemm_tma_store_enabled();   // csrc/gemm_tc.cu: bf16 GEMM epilogues through TMA stores (XA_GEMM_TMA_STORE=0 turns them off)
 enum : int { kChainSmall = 1, kChainLarge = 0, kChainElementwise = 2 };
 template <typename... P, typename... A>
 inline void launch_chained(int kind, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
