@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
       if (tile >= n_tiles) break;
       const uint32_t acc = grp;
       int64_t my_out_off = -1;
+      uint4 my_bits = make_uint4(0, 0, 0, 0);   // my row's mask bits (bits_in), words c0 / 32 = 0..3
       {  // phase 0: where does my row go?
         const int ob = static_cast<int>(ob_u);
         const uint32_t oy_u = p.div_w_magic != 0 ? (rem * p.div_w_magic) >> 16 : rem / p.W;
@@ -393,12 +394,15 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
           if constexpr (kWords == 4) {
             const uint4 v = valid ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
             sts_u4(dst, v);
+            my_bits = v;
           } else if constexpr (kWords == 2) {
             const uint2 v = valid ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0, 0);
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
+            my_bits.x = v.x, my_bits.y = v.y;
           } else {
             const uint32_t v = valid ? __ldg(src) : 0u;
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+            my_bits.x = v;
           }
         }
       }
@@ -406,9 +410,34 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
       mbar_wait_backoff(acc_full + acc, (lt / kGroups) & 1);  // polling eight warps took a sixth of the SM's issue slots (ncu)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float lo = p.relu ? 0.0f : -INFINITY;  // ReLU as one max per element, no per-element branch on the flag
+      // data gradients (no bias, no ReLU, no bits to write; the mask, if any, as bits): the epilogue is what these layers wait
+      // for (conv2's data gradient: 1024 MMA cycles per tile against ~3700 of epilogue), so this form does nothing it does not
+      // need -- no bias loads / adds / maxima (72 of ~150 instructions per chunk), and the mask is applied HERE, in the thread = row
+      // registers, from the row's own bit words (phase 2 then only moves 16-byte pieces)
+      const bool plain = p.bias == nullptr && !p.relu && p.bits_out == nullptr && (p.mask == nullptr || p.bits_in != nullptr);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        {  // phase 1: TMEM -> (+bias, ReLU) -> the chunk's bf16 rows in shared memory
+        if (plain) {  // phase 1, plain form: TMEM -> bf16 pairs -> (mask bits) -> the chunk's rows in shared memory
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
+          const uint32_t dst = my_stage_u32 + lane * kEpiPitch;
+          uint32_t h[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            h[e] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          if (p.bits_in != nullptr) {
+            const uint32_t word = c0 == 0 ? my_bits.x : (c0 == 32 ? my_bits.y : (c0 == 64 ? my_bits.z : my_bits.w));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {   // byte e of the word = values 8 e .. 8 e + 7 of the chunk
+              const uint4 mk = lds_u4(table_u32 + ((word >> (8 * e)) & 255u) * 16u);
+              h[4 * e] &= mk.x, h[4 * e + 1] &= mk.y, h[4 * e + 2] &= mk.z, h[4 * e + 3] &= mk.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sts_u4(dst + j * 16, make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+        } else {  // phase 1: TMEM -> (+bias, ReLU) -> the chunk's bf16 rows in shared memory
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
           const uint32_t dst = my_stage_u32 + lane * kEpiPitch;
@@ -449,7 +478,9 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
           const int64_t off0 = lds_i64(row_out_u32 + row * 8);
           if (off0 >= 0) {
             uint4 val = lds_u4(my_piece_u32 + it * (8 * kEpiPitch));
-            if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
+            if (plain) {
+              // masked in phase 1
+            } else if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
               uint32_t b;
               asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row_bits_u32 + row * (kWords * 4) + (c0 >> 3) + piece));
               const uint4 mk = lds_u4(table_u32 + b * 16);
