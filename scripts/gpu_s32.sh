@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/s39; mkdir -p $O
+O=gpurun_out/s42; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_plan.py tests/test_gpu_conv.py tests/test_gpu_agents.py -m gpu -q -x > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 timeout 300 python scripts/cnn_bench.py > $O/cnn_bench.md 2>&1
 for i in 1 2; do timeout 300 python scripts/update_launches.py 2>&1 | tail -1; done > $O/update_eager.log

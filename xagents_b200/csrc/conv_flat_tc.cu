@@ -31,7 +31,13 @@ constexpr int kConvertWarps = 5;                              // uint8 input: fi
 __host__ __device__ constexpr int flat_threads(int bn, bool u8) {
   return 64 + (u8 ? kGroupsU8 : groups_bf16(bn)) * 4 * 32 + (u8 ? kConvertWarps * 32 : 0);
 }
-constexpr int kEpiPitch = 32 * 2 + 16;                        // one staged row of a 32-column chunk; +16 keeps 16-byte accesses of 32 rows conflict-free
+// One staged row of a 32-column chunk = 64 bytes, unpadded; the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3).  That keeps
+// BOTH access patterns of the epilogue conflict-free: rows in (lane = row, piece j: a quarter-warp covers eight different 16-byte bank
+// groups) and pieces out (four lanes per row, eight rows per access).  The padded 80-byte pitch it replaces was conflict-free only for the
+// writes: every piece-wise read cost 8 wavefronts instead of 4, and these kernels are bound by shared-memory bandwidth (conv2's data
+// gradient: 1024 cycles of MMA operand reads + ~1500 LSU wavefronts per tile of ~3300 cycles, ncu).
+constexpr int kEpiPitch = 32 * 2;
+__device__ __forceinline__ uint32_t epi_piece(int row, int piece) { return static_cast<uint32_t>(row * kEpiPitch + ((piece ^ ((row >> 1) & 3)) << 4)); }
 __host__ __device__ constexpr int epi_warp_bytes(int bn) { return 32 * kEpiPitch + 512 + 32 * (bn / 32) * 4; }   // per epilogue warp: the chunk's tile + row tables
 //                                                                                            (output offsets, mask offsets, mask bits)
 constexpr int kRawStages = 4;
@@ -356,12 +362,13 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
     const uint32_t table_u32 = xa::smem_u32(epi_stage + 4 * kGroups * epi_warp_bytes(BN));   // [256][4]: byte of mask bits -> four bf16x2 AND masks
     // phase-2 coordinates: iteration `it` moves 32 consecutive 16-byte pieces = 8 rows of the chunk; a thread keeps its piece
     const int piece = lane & 3, row0 = lane >> 2;
-    const uint32_t my_piece_u32 = my_stage_u32 + row0 * kEpiPitch + piece * 16;
+    const uint32_t my_piece_u32 = my_stage_u32 + epi_piece(row0, piece);   // rows it * 8 + row0 share (row >> 1) & 3: the piece index holds for all four
     // my row's pixel (image ob, position rem inside it) advances by a constant from one of this group's tiles to the next:
     // two divisions here instead of three per tile (the epilogue's instruction count is what these short-K layers wait for)
     const uint32_t step_px = static_cast<uint32_t>(kGroups) * gridDim.x * kBlockM, step_b = step_px / hw, step_rem = step_px - step_b * hw;
     int64_t q = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x) * kBlockM + r;
     uint32_t ob_u = static_cast<uint32_t>(q / hw), rem = static_cast<uint32_t>(q - static_cast<int64_t>(ob_u) * hw);
+    const bool plain = p.bias == nullptr && !p.relu && p.bits_out == nullptr && (p.mask == nullptr || p.bits_in != nullptr);
     for (uint32_t lt = grp;; lt += kGroups, q += step_px) {
       const int tile = blockIdx.x + static_cast<int>(lt) * static_cast<int>(gridDim.x);
       if (tile >= n_tiles) break;
@@ -393,15 +400,15 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
           const uint32_t dst = row_bits_u32 + lane * (kWords * 4);
           if constexpr (kWords == 4) {
             const uint4 v = valid ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
-            sts_u4(dst, v);
+            if (!plain) sts_u4(dst, v);   // the plain form masks from registers: storing here would wait for the load (ncu: 9 % of all stalls)
             my_bits = v;
           } else if constexpr (kWords == 2) {
             const uint2 v = valid ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0, 0);
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
+            if (!plain) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
             my_bits.x = v.x, my_bits.y = v.y;
           } else {
             const uint32_t v = valid ? __ldg(src) : 0u;
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+            if (!plain) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
             my_bits.x = v;
           }
         }
@@ -414,7 +421,6 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
       // for (conv2's data gradient: 1024 MMA cycles per tile against ~3700 of epilogue), so this form does nothing it does not
       // need -- no bias loads / adds / maxima (72 of ~150 instructions per chunk), and the mask is applied HERE, in the thread = row
       // registers, from the row's own bit words (phase 2 then only moves 16-byte pieces)
-      const bool plain = p.bias == nullptr && !p.relu && p.bits_out == nullptr && (p.mask == nullptr || p.bits_in != nullptr);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (plain) {  // phase 1, plain form: TMEM -> bf16 pairs -> (mask bits) -> the chunk's rows in shared memory
@@ -428,15 +434,22 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
             h[e] = *reinterpret_cast<const uint32_t*>(&t);
           }
           if (p.bits_in != nullptr) {
+            // bit 2e / 2e + 1 of my row's word -> keep / clear the low / high half of pair e.  Arithmetic, not a table: the multiply
+            // moves four bits into the sign bits of four bytes (no two partial products meet, so no carries), PRMT's sign-replicate mode
+            // turns each into 0x00 / 0xFF bytes.  (A 4 KB byte -> mask table in shared memory cost 42 wavefronts per chunk and warp --
+            // random rows, 2-3-way bank conflicts -- in a kernel bound by shared-memory bandwidth.)
             const uint32_t word = c0 == 0 ? my_bits.x : (c0 == 32 ? my_bits.y : (c0 == 64 ? my_bits.z : my_bits.w));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {   // byte e of the word = values 8 e .. 8 e + 7 of the chunk
-              const uint4 mk = lds_u4(table_u32 + ((word >> (8 * e)) & 255u) * 16u);
-              h[4 * e] &= mk.x, h[4 * e + 1] &= mk.y, h[4 * e + 2] &= mk.z, h[4 * e + 3] &= mk.w;
+            for (int e = 0; e < 8; ++e) {   // nibble e = values 4 e .. 4 e + 3 = pairs 2 e, 2 e + 1
+              const uint32_t x = ((word >> (4 * e)) & 15u) * 0x10204080u;
+              uint32_t m0, m1;
+              asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m0) : "r"(x));
+              asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m1) : "r"(x));
+              h[2 * e] &= m0, h[2 * e + 1] &= m1;
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sts_u4(dst + j * 16, make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+          for (int j = 0; j < 4; ++j) sts_u4(dst + ((j ^ ((lane >> 1) & 3)) << 4), make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
         } else {  // phase 1: TMEM -> (+bias, ReLU) -> the chunk's bf16 rows in shared memory
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride + c0, v);
@@ -457,14 +470,14 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
             __nv_bfloat162 h[4];
             h[0] = __floats2bfloat162_rn(f[0], f[1]), h[1] = __floats2bfloat162_rn(f[2], f[3]);
             h[2] = __floats2bfloat162_rn(f[4], f[5]), h[3] = __floats2bfloat162_rn(f[6], f[7]);
-            sts_u4(dst + j * 16, *reinterpret_cast<uint4*>(h));
+            sts_u4(dst + ((j ^ ((lane >> 1) & 3)) << 4), *reinterpret_cast<uint4*>(h));
           }
           if (p.bits_out != nullptr && my_out_off >= 0) p.bits_out[(my_out_off >> 5) + (c0 >> 5)] = __brev(bits);
         }
         if (c0 + 32 >= BN) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the accumulator is drained ...
         __syncwarp();
-        if (c0 + 32 >= BN && lane == 0)                                                        // ... hand it back before the global stores
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");
+        if (c0 + 32 >= BN && elect_one())                                                      // ... hand it back before the global stores
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xa::smem_u32(acc_empty + acc)) : "memory");   // (lane == 0 made ptxas re-read %tid per chunk)
         // phase 2: coalesced mask application and stores of the chunk.  Element offset of my piece inside the output row:
         int col_delta = c0 + piece * 8;
         if (p.out_mode == 2) {  // (dy, dx, c) channel blocks land on pixels (2y+dy, 2x+dx): see xa_conv2d_nhwc_bf16_ex
@@ -472,15 +485,23 @@ __global__ void __launch_bounds__(flat_threads(BN, kU8)) conv_flat_kernel(const 
           const int sub = col_delta / kN4;
           col_delta = ((sub >> 1) * p.PW + (sub & 1)) * kN4 + (col_delta - sub * kN4);
         }
+        if (plain) {  // masked in phase 1: all eight shared-memory loads first (four dependent load -> test -> load -> store chains were
+                      // half of this kernel's stall samples), then the stores
+          int64_t off[4];
+          uint4 val[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) off[it] = lds_i64(row_out_u32 + (it * 8 + row0) * 8), val[it] = lds_u4(my_piece_u32 + it * (8 * kEpiPitch));
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (off[it] >= 0) *reinterpret_cast<uint4*>(p.y + off[it] + col_delta) = val[it];
+        } else
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int row = it * 8 + row0;
           const int64_t off0 = lds_i64(row_out_u32 + row * 8);
           if (off0 >= 0) {
             uint4 val = lds_u4(my_piece_u32 + it * (8 * kEpiPitch));
-            if (plain) {
-              // masked in phase 1
-            } else if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
+            if (p.bits_in != nullptr) {  // ReLU derivative from the mask bits: one byte = this piece's eight values
               uint32_t b;
               asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(row_bits_u32 + row * (kWords * 4) + (c0 >> 3) + piece));
               const uint4 mk = lds_u4(table_u32 + b * 16);
