@@ -726,6 +726,7 @@ __global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restric
   // eight outputs per thread and pass: two 16-byte loads of map entries, eight independent parameter loads in flight, one 16-byte
   // (bf16) or two 16-byte (fp32) stores (one output per thread left the kernel waiting on its two dependent loads: 16 us for 3.4 M
   // elements, 13.8 us with four per thread)
+  const uint64_t keep = xa::policy_evict_last();   // the parameters stay in L2 for the optimiser's next pass
   const int64_t n8 = vec_ok ? n / 8 : 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n8; q += stride) {
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restric
     const int32_t j[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (j[e] >= 0 ? j[e] : 0));   // unconditional loads: all eight issue before the first use
+    for (int e = 0; e < 8; ++e) v[e] = xa::ld_keep(src + (j[e] >= 0 ? j[e] : 0), keep);   // unconditional loads: all eight issue before the first use
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = j[e] >= 0 ? v[e] : 0.0f;
     if (out_bf16) {

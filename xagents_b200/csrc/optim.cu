@@ -7,6 +7,7 @@
 // g, m, v, theta once and writes m, v, theta once (28 B per parameter) with the clip scale and an
 // optional 1/world_size factor (gradient averaging after the all-reduce) folded in.
 #include <math.h>
+#include <stdlib.h>
 
 #include "xa_common.cuh"
 
@@ -32,8 +33,9 @@ __global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(const float* __res
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
   const int64_t n4 = n / kVec;
   const float4* g4 = reinterpret_cast<const float4*>(g);
+  const uint64_t keep = xa::policy_evict_last();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
-    const float4 x = __ldg(g4 + i);
+    const float4 x = xa::ld_keep(g4 + i, keep);
     acc += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y + static_cast<double>(x.z) * x.z +
            static_cast<double>(x.w) * x.w;
   }
@@ -85,18 +87,19 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(const AdamParams a)
   }
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
   const int64_t n4 = a.n / kVec;
+  const uint64_t keep = xa::policy_evict_last();   // parameters, moments and gradient stay in L2 from one minibatch to the next
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
-    float4 p = reinterpret_cast<float4*>(a.param)[i];
-    const float4 g = __ldg(reinterpret_cast<const float4*>(a.grad) + i);
-    float4 m = reinterpret_cast<float4*>(a.m)[i];
-    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float4 p = xa::ld_keep(reinterpret_cast<const float4*>(a.param) + i, keep);
+    const float4 g = xa::ld_keep(reinterpret_cast<const float4*>(a.grad) + i, keep);
+    float4 m = xa::ld_keep(reinterpret_cast<const float4*>(a.m) + i, keep);
+    float4 v = xa::ld_keep(reinterpret_cast<const float4*>(a.v) + i, keep);
     adam_one(p.x, g.x, m.x, v.x, a, scale);
     adam_one(p.y, g.y, m.y, v.y, a, scale);
     adam_one(p.z, g.z, m.z, v.z, a, scale);
     adam_one(p.w, g.w, m.w, v.w, a, scale);
-    reinterpret_cast<float4*>(a.param)[i] = p;
-    reinterpret_cast<float4*>(a.m)[i] = m;
-    reinterpret_cast<float4*>(a.v)[i] = v;
+    xa::st_keep(reinterpret_cast<float4*>(a.param) + i, p, keep);
+    xa::st_keep(reinterpret_cast<float4*>(a.m) + i, m, keep);
+    xa::st_keep(reinterpret_cast<float4*>(a.v) + i, v, keep);
   }
   for (int64_t i = n4 * kVec + static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < a.n; i += stride)
     adam_one(a.param[i], a.grad[i], a.m[i], a.v[i], a, scale);
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float
   // one float4 of "parameter gradients" per thread and pass; 32-bit index arithmetic (n_params, n * A < 2^31 are checked)
   const uint32_t n4 = static_cast<uint32_t>(n_params / 4);
   const uint32_t stride = gridDim.x * kThreads;
+  const uint64_t keep = xa::policy_evict_last();
   for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n4; q += stride) {
     const uint32_t j = q * 4u;
     uint32_t ia = j % na, iv = j % n;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float
       ia = ia + 1 == na ? 0 : ia + 1;
       iv = iv + 1 == n ? 0 : iv + 1;
     }
-    reinterpret_cast<float4*>(grad)[q] = make_float4(out[0], out[1], out[2], out[3]);
+    xa::st_keep(reinterpret_cast<float4*>(grad) + q, make_float4(out[0], out[1], out[2], out[3]), keep);
   }
   if (blockIdx.x == 0 && threadIdx.x < static_cast<uint32_t>(n_params % 4)) {
     const uint32_t j = n4 * 4u + threadIdx.x;
@@ -131,9 +135,21 @@ __global__ void __launch_bounds__(kThreads) grad_from_outputs_kernel(const float
   }
 }
 
+// grid of the optimiser-chain kernels: XA_OPT_BLOCKS in the environment caps it (tuning: these kernels run beside the gather's
+// one CTA per SM; read once)
+int opt_block_cap() {
+  static const int cap = [] {
+    const char* e = getenv("XA_OPT_BLOCKS");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v > 0 && v < kMaxBlocks ? v : kMaxBlocks;
+  }();
+  return cap;
+}
+
 unsigned blocks_for(int64_t n) {
   const int64_t want = (n + kThreads * kVec - 1) / (kThreads * kVec);
-  return static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
+  const int cap = opt_block_cap();
+  return static_cast<unsigned>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
 }  // namespace
@@ -162,7 +178,7 @@ int xa_grad_from_outputs_f32(const float* d_actor, const float* d_values, int64_
   XA_REQUIRE(n_params < (int64_t(1) << 31) && n * n_actions < (int64_t(1) << 31), XA_EOVERFLOW, "xa_grad_from_outputs_f32: sizes exceed 32-bit indices");
   XA_REQUIRE(xa::aligned(grad, 16), XA_EALIGN, "xa_grad_from_outputs_f32: grad must be 16-byte aligned");
   const int64_t want = (n_params / 4 + kThreads - 1) / kThreads;
-  const unsigned grid = static_cast<unsigned>(want < 1 ? 1 : (want > kMaxBlocks ? kMaxBlocks : want));
+  const unsigned grid = static_cast<unsigned>(want < 1 ? 1 : (want > opt_block_cap() ? opt_block_cap() : want));
   xa::launch_chained(xa::kChainElementwise, grad_from_outputs_kernel, dim3(grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), d_actor, d_values, static_cast<uint32_t>(n),
                      static_cast<uint32_t>(n * n_actions), grad, n_params);
   return xa::check_launch("xa_grad_from_outputs_f32");
