@@ -749,7 +749,7 @@ def run_ppo(args):
         'metric': METRIC if args.network == 'stand-in' else 'ppo_env_steps_per_sec_update_phase_with_network',
         'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
         'ms_per_step': ms_per_step, 'ms_per_step_median': med, 'ms_per_step_min': min(per_step), 'ms_per_step_max': max(per_step),
-        'host_issue_ms_per_step': host_ms, 'ms_per_step_each': [round(x, 4) for x in per_step], 'gather_launch_ms_each': [round(x, 3) for x in gather_ms],
+        'host_issue_ms_per_step': host_ms, 'host_issue_note': 'wall time of the issuing loop / steps: an upper bound on interpreter time -- when a step has more launches than the launch queue lets the host run ahead, it includes waiting for the GPU', 'ms_per_step_each': [round(x, 4) for x in per_step], 'gather_launch_ms_each': [round(x, 3) for x in gather_ms],
         'value_at_median_step': N * 1e3 / med * world if world == 1 else None,
         'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong',
         'vs_baseline': None, 'dtype': 'u8 rows + f32 scalars' if dtype == 'uint8' else 'f32', 'data': 'synthetic',

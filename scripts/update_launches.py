@@ -27,11 +27,15 @@ batch = agent.concat_step_batches(agent.ro_states, agent.ro_actions, agent.ro_re
 for _ in range(2):
     agent.run_ppo_epochs(*batch)
 torch.cuda.synchronize()
+import time
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-agent.run_ppo_epochs(*batch)
+t0 = time.perf_counter()
+agent.run_ppo_epochs(*batch)                                      # the queue is empty: the host is not throttled by the GPU
+host_ms = (time.perf_counter() - t0) * 1e3
 b.record()
 torch.cuda.synchronize()
+print('host issue time of one update phase (empty queue):', round(host_ms, 3), 'ms')
 print('update phase, eager:', a.elapsed_time(b), 'ms')
 torch.cuda.cudart().cudaProfilerStart()
 agent.run_ppo_epochs(*batch)
