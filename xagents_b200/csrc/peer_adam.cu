@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_adam_kernel(const xa_
 
   // ---- phase 1: owner pulls its shard from every rank, sums in rank order ---------------------------------
   float4* mine = reinterpret_cast<float4*>(a.grad[me]) + base4;
+  const uint64_t keep1 = xa::policy_evict_last();
   double acc = 0.0;
   for (int64_t i = first; i < n4; i += stride) {
     float4 part[XA_MAX_PEERS];
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_adam_kernel(const xa_
         s.z += part[r].z;
         s.w += part[r].w;
       }
-    mine[i] = s;   // only the owner reads this region of its own buffer
+    xa::st_keep(mine + i, s, keep1);   // only the owner reads this region of its own buffer (phase 3: keep it in L2)
     acc += static_cast<double>(s.x) * s.x + static_cast<double>(s.y) * s.y + static_cast<double>(s.z) * s.z +
            static_cast<double>(s.w) * s.w;
   }
@@ -158,10 +159,11 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_adam_kernel(const xa_
   // ---- phase 3: Adam on the owned shard; push the new weights to every rank ---------------------------------
   float4* m4 = reinterpret_cast<float4*>(a.m);
   float4* v4 = reinterpret_cast<float4*>(a.v);
+  const uint64_t keep = xa::policy_evict_last();
   for (int64_t i = first; i < n4; i += stride) {
-    const float4 g = mine[i];
-    float4 p = reinterpret_cast<const float4*>(a.param[me])[base4 + i];
-    float4 m = m4[i], v = v4[i];
+    const float4 g = xa::ld_keep(mine + i, keep);
+    float4 p = xa::ld_keep(reinterpret_cast<const float4*>(a.param[me]) + base4 + i, keep);
+    float4 m = xa::ld_keep(m4 + i, keep), v = xa::ld_keep(v4 + i, keep);   // local optimiser state: stays in L2 under the gather's stream
     const float gx[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
     float* pp = &p.x;
     float* mm = &m.x;
@@ -172,8 +174,8 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_adam_kernel(const xa_
       vv[c] = a.beta2 * vv[c] + (1.0f - a.beta2) * gx[c] * gx[c];
       pp[c] -= a.lr_t * mm[c] / (sqrtf(vv[c]) + a.eps);
     }
-    m4[i] = m;
-    v4[i] = v;
+    xa::st_keep(m4 + i, m, keep);
+    xa::st_keep(v4 + i, v, keep);
 #pragma unroll
     for (int r = 0; r < XA_MAX_PEERS; ++r)
       if (r < G) reinterpret_cast<float4*>(a.param[r])[base4 + i] = p;
