@@ -43,7 +43,8 @@ def run(env_id, tensor_cores, graph_rollout='auto'):
         return wrapper
 
     agent.get_batch, agent.run_ppo_epochs = timed('rollout', inner_batch), timed('update', inner_epochs)
-    agent.fit(max_steps=T * E)                                     # warm-up: first launches, graph capture, allocator
+    agent.fit(max_steps=3 * T * E)                                 # warm-up: first launches, graph capture, allocator (the permutation draw
+    #                                                                of the THIRD update still takes one cudaMalloc, 0.5-80 ms: scripts/fit_step_times.py)
     phases.update(rollout=0.0, update=0.0)
     ops.reset_launch_count()
     torch.cuda.synchronize()
