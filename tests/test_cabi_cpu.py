@@ -158,3 +158,32 @@ def test_bench_reference_arm_runs_the_stated_small_workloads_on_the_host():
         assert line['impl'] == 'reference' and line['metric'] == metric and line['value'] > 0 and line['steps'] == 3
         assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == 1 and workload in line['config']['workload']
         assert line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
+
+
+def test_chained_launch_level_is_a_host_side_setting(lib):
+    """xa_set_chained_launches: returns the previous level, ignores levels outside 0..3 (a query), needs no device."""
+    before = lib.xa_set_chained_launches(-1)
+    assert before in (0, 1, 2, 3)
+    try:
+        assert lib.xa_set_chained_launches(0) == before
+        assert lib.xa_set_chained_launches(7) == 0 and lib.xa_set_chained_launches(-1) == 0      # out of range: nothing changes
+        assert lib.xa_set_chained_launches(2) == 0 and lib.xa_set_chained_launches(-1) == 2
+    finally:
+        lib.xa_set_chained_launches(before)
+    assert lib.xa_set_chained_launches(-1) == before
+
+
+def test_new_entry_points_validate_before_touching_cuda(lib):
+    splits = ctypes.c_int(5)
+    rc = lib.xa_gemm_bf16_tn_partial(None, None, 256, 512, 3136, None, 0, ctypes.byref(splits), None)
+    assert rc == -1 and b'null pointer' in lib.xa_last_error()
+    rc = lib.xa_gemm_bf16_tn_partial(16, 16, 256, 512, 3133, None, 0, ctypes.byref(splits), None)
+    assert rc == -1 and b'multiple of 8' in lib.xa_last_error()
+    rc = lib.xa_heads_forward_partial_bf16(None, 2, None, None, None, None, None, None, 8, 512, 6, None)
+    assert rc == -1 and b'null pointer' in lib.xa_last_error()
+    rc = lib.xa_heads_forward_partial_bf16(16, 2, None, None, 16, 16, 16, 16, 8, 256, 6, None)
+    assert rc == -1 and b'hidden' in lib.xa_last_error()
+    rc = lib.xa_gemm_bf16_tn_maskbits(16, 16, 16, 64, 64, 64, 64, None, 64, 0, 0, None)
+    assert rc == -1 and b'mask_bits' in lib.xa_last_error()
+    rc = lib.xa_gemm_bf16_tn_maskbits(16, 16, 16, 64, 64, 64, 64, 16, 40, 0, 0, None)
+    assert rc == -1 and b'multiple of 32' in lib.xa_last_error()
